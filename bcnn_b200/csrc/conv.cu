@@ -1,0 +1,42 @@
+// conv.cu -- C-ABI convolution entry points (include/bcnn_b200.h) and the dispatcher
+// between the FP32 SIMT implicit GEMM (conv_simt.cu) and the BF16 tcgen05 implicit GEMM
+// (conv_tc.cu). There is no CPU fallback and no cuDNN / cuBLAS on either path.
+#include "common.cuh"
+#include "conv_impl.cuh"
+
+using namespace b200;
+
+extern "C" size_t bcnn_b200_conv_workspace_bytes(const bcnn_b200_conv_desc *d, int math) {
+    size_t a = conv_simt_workspace_bytes(d);
+    size_t b = (math == BCNN_B200_MATH_TC) ? conv_tc_workspace_bytes(d) : 0;
+    return a > b ? a : b;
+}
+
+extern "C" int bcnn_b200_conv_forward(const bcnn_b200_conv_desc *d, const float *x,
+                                      const float *w, const float *bias, int act, float *y,
+                                      void *workspace, size_t workspace_bytes, int math,
+                                      void *stream) {
+    cudaStream_t st = as_stream(stream);
+    if (math == BCNN_B200_MATH_TC && conv_tc_supports_fprop(d))
+        return conv_tc_forward(d, x, w, bias, act, y, workspace, workspace_bytes, st);
+    return conv_simt_forward(d, x, w, bias, act, y, st);
+}
+
+extern "C" int bcnn_b200_conv_backward_data(const bcnn_b200_conv_desc *d, const float *w,
+                                            const float *dy, float *dx, int accumulate,
+                                            void *workspace, size_t workspace_bytes, int math,
+                                            void *stream) {
+    cudaStream_t st = as_stream(stream);
+    if (math == BCNN_B200_MATH_TC && conv_tc_supports_dgrad(d))
+        return conv_tc_backward_data(d, w, dy, dx, accumulate, workspace, workspace_bytes, st);
+    return conv_simt_backward_data(d, w, dy, dx, accumulate, st);
+}
+
+extern "C" int bcnn_b200_conv_backward_weights(const bcnn_b200_conv_desc *d, const float *x,
+                                               const float *dy, float *gw, void *workspace,
+                                               size_t workspace_bytes, int math, void *stream) {
+    cudaStream_t st = as_stream(stream);
+    if (math == BCNN_B200_MATH_TC && conv_tc_supports_wgrad(d))
+        return conv_tc_backward_weights(d, x, dy, gw, workspace, workspace_bytes, st);
+    return conv_simt_backward_weights(d, x, dy, gw, workspace, workspace_bytes, st);
+}

@@ -1,0 +1,35 @@
+// conv_impl.cuh -- internal interface between the conv dispatcher (conv.cu) and the two
+// implicit-GEMM implementations.
+#pragma once
+#include <cuda_runtime.h>
+
+#include "bcnn_b200.h"
+
+namespace b200 {
+
+// FP32 SIMT path (conv_simt.cu) -- covers every shape.
+size_t conv_simt_workspace_bytes(const bcnn_b200_conv_desc *d);
+int conv_simt_forward(const bcnn_b200_conv_desc *d, const float *x, const float *w,
+                      const float *bias, int act, float *y, cudaStream_t st);
+int conv_simt_backward_data(const bcnn_b200_conv_desc *d, const float *w, const float *dy,
+                            float *dx, int accumulate, cudaStream_t st);
+int conv_simt_backward_weights(const bcnn_b200_conv_desc *d, const float *x, const float *dy,
+                               float *gw, void *workspace, size_t workspace_bytes,
+                               cudaStream_t st);
+
+// BF16 tcgen05 path (conv_tc.cu) -- covers the shapes conv_tc_supports_* accepts.
+bool conv_tc_supports_fprop(const bcnn_b200_conv_desc *d);
+bool conv_tc_supports_dgrad(const bcnn_b200_conv_desc *d);
+bool conv_tc_supports_wgrad(const bcnn_b200_conv_desc *d);
+size_t conv_tc_workspace_bytes(const bcnn_b200_conv_desc *d);
+int conv_tc_forward(const bcnn_b200_conv_desc *d, const float *x, const float *w,
+                    const float *bias, int act, float *y, void *workspace,
+                    size_t workspace_bytes, cudaStream_t st);
+int conv_tc_backward_data(const bcnn_b200_conv_desc *d, const float *w, const float *dy,
+                          float *dx, int accumulate, void *workspace, size_t workspace_bytes,
+                          cudaStream_t st);
+int conv_tc_backward_weights(const bcnn_b200_conv_desc *d, const float *x, const float *dy,
+                             float *gw, void *workspace, size_t workspace_bytes,
+                             cudaStream_t st);
+
+}  // namespace b200

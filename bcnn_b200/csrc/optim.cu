@@ -1,0 +1,152 @@
+// optim.cu -- fused SGD-momentum update, softmax and euclidean cost for sm_100a.
+//
+// SGD: the reference spends five BLAS-1 launches per parameter tensor
+// (bcnn_sgd_update_gpu, src/bcnn_learner.c:86-103: axpy, scal, axpy, axpy, scal);
+// here it is one read-modify-write pass over (w, g): 16 B/element instead of 40.
+// Momentum stays in the gradient buffer exactly as in the reference.
+#include <float.h>
+
+#include "common.cuh"
+
+using namespace b200;
+
+namespace {
+
+inline bool aligned16(const void *p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
+
+__global__ void __launch_bounds__(256)
+sgd_kernel(float *__restrict__ w, float *__restrict__ g, size_t n, float wd_scale, float step,
+           float g_scale, bool vec) {
+    size_t gstride = (size_t)gridDim.x * blockDim.x;
+    size_t tid = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    size_t done = 0;
+    if (vec) {
+        size_t n4 = n >> 2;
+        for (size_t j = tid; j < n4; j += gstride) {
+            float4 wv = reinterpret_cast<float4 *>(w)[j];
+            float4 gv = reinterpret_cast<float4 *>(g)[j];
+            // separate mul / add roundings, as the reference's axpy (no FMA contraction)
+            gv.x = __fadd_rn(gv.x, __fmul_rn(wd_scale, wv.x));
+            gv.y = __fadd_rn(gv.y, __fmul_rn(wd_scale, wv.y));
+            gv.z = __fadd_rn(gv.z, __fmul_rn(wd_scale, wv.z));
+            gv.w = __fadd_rn(gv.w, __fmul_rn(wd_scale, wv.w));
+            wv.x = __fadd_rn(wv.x, __fmul_rn(step, gv.x));
+            wv.y = __fadd_rn(wv.y, __fmul_rn(step, gv.y));
+            wv.z = __fadd_rn(wv.z, __fmul_rn(step, gv.z));
+            wv.w = __fadd_rn(wv.w, __fmul_rn(step, gv.w));
+            gv.x *= g_scale; gv.y *= g_scale; gv.z *= g_scale; gv.w *= g_scale;
+            reinterpret_cast<float4 *>(w)[j] = wv;
+            reinterpret_cast<float4 *>(g)[j] = gv;
+        }
+        done = n4 << 2;
+    }
+    for (size_t j = done + tid; j < n; j += gstride) {
+        float gv = __fadd_rn(g[j], __fmul_rn(wd_scale, w[j]));
+        w[j] = __fadd_rn(w[j], __fmul_rn(step, gv));
+        g[j] = gv * g_scale;
+    }
+}
+
+// One warp per (sample, spatial position): softmax over channels in the
+// log-sum-exp form of src/layers/bcnn_softmax_layer.c:88-155 (double exp/log rounded
+// to float at each step, as the reference's casts do).
+__global__ void __launch_bounds__(256)
+softmax_kernel(const float *__restrict__ x, float *__restrict__ y, int rows, int c, int hw,
+               FastDiv d_hw) {
+    const int lane = threadIdx.x & 31;
+    const int warps = (gridDim.x * blockDim.x) >> 5;
+    for (int r = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; r < rows; r += warps) {
+        uint32_t b, i;
+        d_hw.divmod(r, b, i);
+        const float *p = x + (size_t)b * c * hw + i;
+        float *q = y + (size_t)b * c * hw + i;
+        float vmax = -FLT_MAX;
+        for (int j = lane; j < c; j += 32) vmax = fmaxf(vmax, p[(size_t)j * hw]);
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) vmax = fmaxf(vmax, __shfl_xor_sync(0xffffffffu, vmax, o));
+        float sum = 0.f;
+        for (int j = lane; j < c; j += 32) sum += (float)exp((double)(p[(size_t)j * hw] - vmax));
+        sum = warp_sum(sum);
+        float lse = sum ? vmax + (float)log((double)sum) : vmax - 100.0f;
+        for (int j = lane; j < c; j += 32)
+            q[(size_t)j * hw] = (float)exp((double)(p[(size_t)j * hw] - lse));
+    }
+}
+
+// grad = pred - label, plus the scalar metric, in one single-CTA pass (the cost
+// tensors are n x classes: tiny). metric kinds = bcnn_loss_metric.
+__global__ void __launch_bounds__(1024)
+cost_kernel(const float *__restrict__ pred, const float *__restrict__ label,
+            float *__restrict__ grad, float *__restrict__ metric, int n, int input_size,
+            int kind) {
+    __shared__ float red[32];
+    const int total = n * input_size;
+    float acc[1] = {0.f};
+    for (int i = threadIdx.x; i < total; i += 1024) {
+        float e = pred[i] - label[i];
+        if (grad) grad[i] = e;
+        if (kind == 2 || kind == 3 || kind == 4) acc[0] += e * e;  // SSE / MSE / CRPS
+        if (kind == 1 && label[i] > 0.0f) {                         // LOGLOSS
+            float pv = fminf(fmaxf(pred[i], 1e-8f), 1.0f - 1e-8f);
+            acc[0] += (float)-log((double)pv);
+        }
+    }
+    if (kind == 0) {  // ERROR_RATE: argmax with strict '>' from FLT_MIN, first max wins
+        for (int b = threadIdx.x; b < n; b += 1024) {
+            float pmax = FLT_MIN;
+            int best = 0;
+            for (int j = 0; j < input_size; ++j) {
+                float v = pred[(size_t)b * input_size + j];
+                if (v > pmax) { pmax = v; best = j; }
+            }
+            if (label[(size_t)b * input_size + best] == 0) acc[0] += 1.0f;
+        }
+    }
+    if (kind == 5) {  // DICE
+        for (int b = threadIdx.x; b < n; b += 1024) {
+            int num = 0, den = 0;
+            for (int j = 0; j < input_size; ++j) {
+                float l = label[(size_t)b * input_size + j];
+                float hit = (float)(pred[(size_t)b * input_size + j] > 0.5f);
+                num += (int)(l * hit);
+                den += (int)(l + hit);
+            }
+            acc[0] += (float)(2.0f * num + 1.0f) / (den + 1.0f);
+        }
+    }
+    block_sum<1, 1024>(acc, red);
+    if (threadIdx.x == 0) {
+        float m = acc[0];
+        if (kind == 3) m /= input_size;
+        metric[0] = m;
+    }
+}
+
+}  // namespace
+
+extern "C" int bcnn_b200_sgd_update(float *w, float *g, size_t n, float wd_scale, float step,
+                                    float g_scale, void *stream) {
+    if (n == 0) return 0;
+    bool vec = aligned16(w) && aligned16(g);
+    sgd_kernel<<<stream_grid(vec ? n / 4 + 1 : n, 256), 256, 0, as_stream(stream)>>>(
+        w, g, n, wd_scale, step, g_scale, vec);
+    return launched();
+}
+
+extern "C" int bcnn_b200_softmax_forward(const float *x, float *y, int n, int c, int hw,
+                                         void *stream) {
+    int rows = n * hw;
+    if (rows <= 0 || c <= 0) return 0;
+    softmax_kernel<<<stream_grid((size_t)rows * 32, 256), 256, 0, as_stream(stream)>>>(
+        x, y, rows, c, hw, FastDiv(hw));
+    return launched();
+}
+
+extern "C" int bcnn_b200_cost_forward(const float *pred, const float *label, float *grad,
+                                      float *metric, int n, int input_size, int metric_kind,
+                                      void *stream) {
+    if (n <= 0 || input_size <= 0) return 0;
+    cost_kernel<<<1, 1024, 0, as_stream(stream)>>>(pred, label, grad, metric, n, input_size,
+                                                   metric_kind);
+    return launched();
+}

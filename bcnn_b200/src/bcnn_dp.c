@@ -1,0 +1,171 @@
+/*
+ * bcnn_dp.c -- data-parallel training: one bcnn_net replica per GPU (one process each),
+ * NCCL sum all-reduce of every parameter-gradient tensor over NVLink, queued on a
+ * dedicated comm stream as soon as the owning node's backward has been enqueued, so the
+ * transfer overlaps the rest of the backward pass; bcnn_update joins it.
+ *
+ * NCCL is bound at run time (dlopen) so the library has no link-time dependency and
+ * re-uses the copy torch already loaded in a bench/test process.
+ *
+ * Momentum-in-gradient-buffer (reference src/bcnn_learner.c:74,80): the
+ * gradient buffer holds m*v_prev + g_local when backward ends. Every rank holds the same
+ * m*v_prev, so the SGD kernel leaves (m / world) * v behind instead of m * v: the sum
+ * over ranks then restores exactly m*v_prev + sum_r g_r with no extra pass or buffer.
+ */
+#include "bcnn_dp.h"
+
+#include <dlfcn.h>
+
+#include <bcnn_b200_net.h>
+
+typedef struct { char internal[128]; } nccl_uid;
+typedef int (*fn_get_uid)(nccl_uid *);
+typedef int (*fn_init_rank)(void **comm, int nranks, nccl_uid id, int rank);
+typedef int (*fn_allreduce)(const void *send, void *recv, size_t count, int dtype, int op,
+                            void *comm, void *stream);
+typedef int (*fn_void)(void);
+typedef int (*fn_comm)(void *comm);
+typedef const char *(*fn_errstr)(int);
+
+enum { NCCL_FLOAT32 = 7, NCCL_SUM = 0 };
+
+static struct {
+    void *lib;
+    fn_get_uid get_uid;
+    fn_init_rank init_rank;
+    fn_allreduce allreduce;
+    fn_void group_start, group_end;
+    fn_comm destroy;
+    fn_errstr errstr;
+} nccl;
+
+struct bcnn_dp_state {
+    int rank, world;
+    void *comm;
+    void *comm_stream;
+    void *evt_ready; /* compute -> comm */
+    void *evt_done;  /* comm -> compute */
+    size_t bytes_per_step, bytes_this_step;
+};
+
+static int nccl_bind(void) {
+    if (nccl.lib) return 0;
+    void *lib = dlopen("libnccl.so.2", RTLD_NOW | RTLD_NOLOAD | RTLD_GLOBAL);
+    if (!lib) lib = dlopen("libnccl.so.2", RTLD_NOW | RTLD_GLOBAL);
+    if (!lib) lib = dlopen("libnccl.so", RTLD_NOW | RTLD_GLOBAL);
+    if (!lib) {
+        fprintf(stderr, "[ERROR] [NCCL] cannot load libnccl.so.2: %s\n", dlerror());
+        return -1;
+    }
+    nccl.get_uid = (fn_get_uid)dlsym(lib, "ncclGetUniqueId");
+    nccl.init_rank = (fn_init_rank)dlsym(lib, "ncclCommInitRank");
+    nccl.allreduce = (fn_allreduce)dlsym(lib, "ncclAllReduce");
+    nccl.group_start = (fn_void)dlsym(lib, "ncclGroupStart");
+    nccl.group_end = (fn_void)dlsym(lib, "ncclGroupEnd");
+    nccl.destroy = (fn_comm)dlsym(lib, "ncclCommDestroy");
+    nccl.errstr = (fn_errstr)dlsym(lib, "ncclGetErrorString");
+    if (!nccl.get_uid || !nccl.init_rank || !nccl.allreduce || !nccl.group_start ||
+        !nccl.group_end || !nccl.destroy) {
+        fprintf(stderr, "[ERROR] [NCCL] libnccl.so.2 lacks an expected symbol\n");
+        return -1;
+    }
+    nccl.lib = lib;
+    return 0;
+}
+
+#define nccl_check(RET)                                                              \
+    do { int r_ = (RET);                                                             \
+         if (r_ != 0) {                                                              \
+             fprintf(stderr, "[ERROR] [NCCL] %s (%s:%d)\n",                          \
+                     nccl.errstr ? nccl.errstr(r_) : "error", __FILE__, __LINE__);   \
+             exit(r_); } } while (0)
+
+int bcnn_b200_dp_get_unique_id(char id[BCNN_B200_DP_ID_BYTES]) {
+    if (nccl_bind() != 0) return -1;
+    nccl_uid uid;
+    memset(&uid, 0, sizeof(uid));
+    int r = nccl.get_uid(&uid);
+    memcpy(id, uid.internal, sizeof(uid.internal));
+    return r;
+}
+
+int bcnn_b200_dp_init(bcnn_net *net, int rank, int world, const char id[BCNN_B200_DP_ID_BYTES]) {
+    if (world <= 1) return 0;
+    if (nccl_bind() != 0) return -1;
+    bcnn_cuda_context *ctx = bcnn_ctx(net);
+    struct bcnn_dp_state *dp = (struct bcnn_dp_state *)calloc(1, sizeof(*dp));
+    if (!dp) return -1;
+    nccl_uid uid;
+    memcpy(uid.internal, id, sizeof(uid.internal));
+    nccl_check(nccl.init_rank(&dp->comm, world, uid, rank));
+    dp->rank = rank;
+    dp->world = world;
+    dp->comm_stream = bcnn_b200_stream_create();
+    dp->evt_ready = bcnn_b200_event_create();
+    dp->evt_done = bcnn_b200_event_create();
+    ctx->dp = dp;
+    return 0;
+}
+
+int bcnn_dp_world_size(bcnn_net *net) {
+    struct bcnn_dp_state *dp = bcnn_ctx(net)->dp;
+    return dp ? dp->world : 1;
+}
+
+int bcnn_b200_dp_world(bcnn_net *net) { return bcnn_dp_world_size(net); }
+
+size_t bcnn_b200_dp_bytes_per_step(bcnn_net *net) {
+    struct bcnn_dp_state *dp = bcnn_ctx(net)->dp;
+    return dp ? dp->bytes_per_step : 0;
+}
+
+void bcnn_dp_after_node_backward(bcnn_net *net, bcnn_node *node) {
+    struct bcnn_dp_state *dp = bcnn_ctx(net)->dp;
+    if (!dp) return;
+    int queued = 0;
+    for (int i = 1; i < node->num_src; ++i) { /* src[0] is the activation input */
+        bcnn_tensor *t = &net->tensors[node->src[i]];
+        if (node->type == BCNN_LAYER_COST || node->type == BCNN_LAYER_ELTWISE) break;
+        if (!t->has_grad || !t->grad_data_gpu) continue;
+        if (!queued) {
+            bcnn_cuda_check(bcnn_b200_event_record(dp->evt_ready, bcnn_stream(net)));
+            bcnn_cuda_check(bcnn_b200_stream_wait_event(dp->comm_stream, dp->evt_ready));
+            nccl_check(nccl.group_start());
+            queued = 1;
+        }
+        size_t count = (size_t)bcnn_tensor_size(t);
+        nccl_check(nccl.allreduce(t->grad_data_gpu, t->grad_data_gpu, count, NCCL_FLOAT32, NCCL_SUM,
+                                  dp->comm, dp->comm_stream));
+        dp->bytes_this_step += count * sizeof(float);
+    }
+    if (queued) nccl_check(nccl.group_end());
+}
+
+void bcnn_dp_before_update(bcnn_net *net) {
+    struct bcnn_dp_state *dp = bcnn_ctx(net)->dp;
+    if (!dp) return;
+    bcnn_cuda_check(bcnn_b200_event_record(dp->evt_done, dp->comm_stream));
+    bcnn_cuda_check(bcnn_b200_stream_wait_event(bcnn_stream(net), dp->evt_done));
+    dp->bytes_per_step = dp->bytes_this_step;
+    dp->bytes_this_step = 0;
+}
+
+void bcnn_dp_sync(bcnn_net *net) {
+    struct bcnn_dp_state *dp = bcnn_ctx(net)->dp;
+    if (dp) bcnn_cuda_check(bcnn_b200_stream_sync(dp->comm_stream));
+}
+
+void bcnn_dp_release(bcnn_net *net) {
+    bcnn_cuda_context *ctx = bcnn_ctx(net);
+    struct bcnn_dp_state *dp = ctx ? ctx->dp : NULL;
+    if (!dp) return;
+    bcnn_b200_stream_sync(dp->comm_stream);
+    if (dp->comm) nccl.destroy(dp->comm);
+    bcnn_b200_event_destroy(dp->evt_ready);
+    bcnn_b200_event_destroy(dp->evt_done);
+    bcnn_b200_stream_destroy(dp->comm_stream);
+    free(dp);
+    ctx->dp = NULL;
+}
+
+void bcnn_b200_dp_shutdown(bcnn_net *net) { bcnn_dp_release(net); }

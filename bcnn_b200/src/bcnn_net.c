@@ -1,0 +1,313 @@
+/*
+ * bcnn_net.c -- graph runtime of the hot path: net lifetime, tensor / node tables, the
+ * forward / backward loops and tensor getters.
+ *
+ * Mirrors the behaviour of jnbraun/bcnn src/bcnn_net.c:61-463 for the functions on the
+ * path (bcnn_init_net :61, bcnn_net_add_node/_tensor :236-258, bcnn_set_input_shape :280,
+ * bcnn_compile_net :356, bcnn_reset_gradients :361, getters :377-408, bcnn_forward :410,
+ * bcnn_backward :424). The cfg parser, weight files and data loaders of that file are out
+ * of scope. Everything runs on one CUDA stream per net; nothing synchronises unless a
+ * getter needs host data.
+ */
+#include "bcnn_net.h"
+
+#include "bcnn_dp.h"
+#include "bcnn_tensor.h"
+#include <bcnn_b200_net.h>
+
+bcnn_status bcnn_net_create_cuda_context(bcnn_net *net) {
+    bcnn_cuda_context *ctx = (bcnn_cuda_context *)calloc(1, sizeof(bcnn_cuda_context));
+    BCNN_CHECK(ctx != NULL, BCNN_FAILED_ALLOC);
+    ctx->stream = bcnn_b200_stream_create();
+    if (!ctx->stream) {
+        fprintf(stderr,
+                "[ERROR] [CUDA] bcnn_b200 needs a CUDA device (sm_100a); there is no CPU path\n");
+        free(ctx);
+        return BCNN_CUDA_FAILED_ALLOC;
+    }
+    const char *math = getenv("BCNN_B200_CONV_MATH");
+    ctx->conv_math = (math && (math[0] == 't' || math[0] == 'T' || math[0] == '1'))
+                         ? BCNN_B200_MATH_TC
+                         : BCNN_B200_MATH_FP32;
+    net->cuda_ctx = ctx;
+    return BCNN_SUCCESS;
+}
+
+bcnn_status bcnn_init_net(bcnn_net **net, bcnn_mode mode) {
+    bcnn_net *p = (bcnn_net *)calloc(1, sizeof(bcnn_net));
+    BCNN_CHECK(p != NULL, BCNN_FAILED_ALLOC);
+    p->mode = mode;
+    /* tensors[0] = "input", tensors[1] = "label", shaped later */
+    bcnn_tensor input = {0}, label = {0};
+    input.name = bcnn_strdup_("input");
+    label.name = bcnn_strdup_("label");
+    bcnn_net_add_tensor(p, input);
+    bcnn_net_add_tensor(p, label);
+    if (mode != BCNN_MODE_PREDICT) p->learner = (bcnn_learner *)calloc(1, sizeof(bcnn_learner));
+    p->num_inputs = 1;
+    p->inputs = (int *)calloc(1, sizeof(int));
+    p->num_threads = 1;
+    bcnn_status st = bcnn_net_create_cuda_context(p);
+    if (st != BCNN_SUCCESS) {
+        bcnn_end_net(&p);
+        return st;
+    }
+    *net = p;
+    return BCNN_SUCCESS;
+}
+
+void bcnn_end_net(bcnn_net **net) {
+    bcnn_net *p = *net;
+    if (!p) return;
+    bcnn_cuda_context *ctx = bcnn_ctx(p);
+    if (ctx) {
+        bcnn_b200_stream_sync(ctx->stream);
+        bcnn_dp_release(p);
+    }
+    for (int i = 0; i < p->num_nodes; ++i) {
+        bcnn_node *node = &p->nodes[i];
+        if (node->release_param) node->release_param(node);
+        free(node->src);
+        free(node->dst);
+        free(node->param);
+    }
+    free(p->nodes);
+    for (int i = 0; i < p->num_tensors; ++i) bcnn_tensor_destroy(&p->tensors[i]);
+    free(p->tensors);
+    free(p->learner);
+    free(p->inputs);
+    if (ctx) {
+        bcnn_b200_free(ctx->workspace_gpu);
+        bcnn_b200_stream_destroy(ctx->stream);
+        free(ctx);
+    }
+    free(p); /* like the reference, the caller's pointer is left dangling */
+}
+
+void bcnn_set_log_context(bcnn_net *net, bcnn_log_callback fct, bcnn_log_level level) {
+    net->log_ctx.fct = fct;
+    net->log_ctx.lvl = level;
+}
+
+bcnn_status bcnn_set_num_threads(bcnn_net *net, int num_threads, const int *cpu_ids) {
+    (void)cpu_ids; /* host threads do no arithmetic on this path */
+    net->num_threads = num_threads < 1 ? 1 : num_threads;
+    return BCNN_SUCCESS;
+}
+
+int bcnn_get_num_threads(bcnn_net *net) { return net->num_threads; }
+
+bcnn_status bcnn_net_add_node(bcnn_net *net, bcnn_node node) {
+    bcnn_node *grown = (bcnn_node *)realloc(net->nodes, (size_t)(net->num_nodes + 1) * sizeof(bcnn_node));
+    BCNN_CHECK_AND_LOG(net->log_ctx, grown != NULL, BCNN_FAILED_ALLOC, "Internal allocation error\n");
+    grown[net->num_nodes++] = node;
+    net->nodes = grown;
+    return BCNN_SUCCESS;
+}
+
+bcnn_status bcnn_net_add_tensor(bcnn_net *net, bcnn_tensor tensor) {
+    bcnn_tensor *grown =
+        (bcnn_tensor *)realloc(net->tensors, (size_t)(net->num_tensors + 1) * sizeof(bcnn_tensor));
+    BCNN_CHECK_AND_LOG(net->log_ctx, grown != NULL, BCNN_FAILED_ALLOC, "Internal allocation error\n");
+    grown[net->num_tensors++] = tensor;
+    net->tensors = grown;
+    return BCNN_SUCCESS;
+}
+
+void bcnn_set_input_shape(bcnn_net *net, int width, int height, int channels, int batch_size) {
+    net->batch_size = batch_size;
+    bcnn_tensor_set_shape(&net->tensors[0], batch_size, channels, height, width, 0);
+}
+
+int bcnn_get_batch_size(bcnn_net *net) { return net->batch_size; }
+
+bcnn_status bcnn_set_mode(bcnn_net *net, bcnn_mode mode) {
+    /* TRAIN <-> VALID switches are free; gradient buffers exist only if the net was
+     * created in TRAIN / VALID mode (as in the reference, bcnn_tensor.c:111). */
+    net->mode = mode;
+    return BCNN_SUCCESS;
+}
+
+bcnn_status bcnn_compile_net(bcnn_net *net) {
+    bcnn_cuda_context *ctx = bcnn_ctx(net);
+    /* (re)allocate the input tensor, with an eager pinned host mirror the caller fills */
+    BCNN_CHECK_STATUS(bcnn_tensor_allocate(&net->tensors[0], net->mode));
+    BCNN_CHECK_STATUS(bcnn_tensor_ensure_host(&net->tensors[0]));
+    if (net->tensors[1].data_gpu) BCNN_CHECK_STATUS(bcnn_tensor_ensure_host(&net->tensors[1]));
+    /* shared conv workspace = max requirement over the conv nodes */
+    bcnn_b200_free(ctx->workspace_gpu);
+    ctx->workspace_gpu = NULL;
+    if (ctx->workspace_bytes) {
+        ctx->workspace_gpu = (float *)bcnn_b200_malloc(ctx->workspace_bytes);
+        BCNN_CHECK(ctx->workspace_gpu != NULL, BCNN_CUDA_FAILED_ALLOC);
+    }
+    ctx->workspace_size = (int)(ctx->workspace_bytes / sizeof(float));
+    return BCNN_SUCCESS;
+}
+
+int bcnn_get_tensor_index_by_name(bcnn_net *net, const char *name) {
+    for (int i = net->num_tensors - 1; i >= 0; --i)
+        if (net->tensors[i].name && strcmp(net->tensors[i].name, name) == 0) return i;
+    return -1;
+}
+
+bcnn_tensor *bcnn_get_tensor_by_index(bcnn_net *net, int index) {
+    if (index < 0 || index >= net->num_tensors) return NULL;
+    bcnn_tensor *t = &net->tensors[index];
+    size_t bytes = (size_t)bcnn_tensor_size(t) * sizeof(float);
+    if (bytes == 0 || !t->data_gpu) return t;
+    void *stream = bcnn_stream(net);
+    if (bcnn_tensor_ensure_host(t) != BCNN_SUCCESS) return NULL;
+    bcnn_cuda_check(bcnn_b200_memcpy_d2h(t->data, t->data_gpu, bytes, stream));
+    if (t->grad_data_gpu && t->grad_data)
+        bcnn_cuda_check(bcnn_b200_memcpy_d2h(t->grad_data, t->grad_data_gpu, bytes, stream));
+    bcnn_cuda_check(bcnn_b200_stream_sync(stream));
+    return t;
+}
+
+bcnn_tensor *bcnn_get_tensor_by_name(bcnn_net *net, const char *name) {
+    return bcnn_get_tensor_by_index(net, bcnn_get_tensor_index_by_name(net, name));
+}
+
+/* Zero the gradient of a node's outputs before its forward (TRAIN only), as
+ * bcnn_reset_gradients does; weight gradients are never reset (momentum lives there). */
+static void reset_output_gradients(bcnn_net *net, bcnn_node *node) {
+    for (int i = 0; i < node->num_dst; ++i) {
+        bcnn_tensor *t = &net->tensors[node->dst[i]];
+        if (t->grad_data_gpu)
+            bcnn_cuda_check(bcnn_b200_fill_f32(t->grad_data_gpu, (size_t)bcnn_tensor_size(t), 0.0f,
+                                               bcnn_stream(net)));
+    }
+}
+
+void bcnn_forward(bcnn_net *net) {
+    for (int i = 0; i < net->num_nodes; ++i) {
+        bcnn_node *node = &net->nodes[i];
+        if (net->mode == BCNN_MODE_TRAIN) reset_output_gradients(net, node);
+        node->forward(net, node);
+    }
+}
+
+void bcnn_backward(bcnn_net *net) {
+    for (int i = net->num_nodes - 1; i >= 0; --i) {
+        bcnn_node *node = &net->nodes[i];
+        node->backward(net, node);
+        bcnn_dp_after_node_backward(net, node); /* no-op without data parallelism */
+    }
+}
+
+/* ---------------- helpers for the layer constructors ---------------- */
+
+int bcnn_net_find_src(bcnn_net *net, const char *src_id) {
+    if (net->num_nodes == 0) return 0;
+    return bcnn_get_tensor_index_by_name(net, src_id);
+}
+
+bcnn_status bcnn_net_add_param_tensor(bcnn_net *net, bcnn_node *node, int n, int c, int h, int w,
+                                      int has_grad, const char *prefix, const char *suffix,
+                                      const bcnn_tensor_filler *filler) {
+    char name[320];
+    snprintf(name, sizeof(name), "%s%s", prefix, suffix);
+    bcnn_tensor t = {0};
+    bcnn_tensor_create(&t, n, c, h, w, has_grad, name, net->mode);
+    BCNN_CHECK_AND_LOG(net->log_ctx, t.data_gpu != NULL, BCNN_CUDA_FAILED_ALLOC,
+                       "Failed to allocate tensor %s\n", name);
+    if (filler) bcnn_tensor_fill(&t, *filler);
+    BCNN_CHECK_STATUS(bcnn_net_add_tensor(net, t));
+    return bcnn_node_add_input(net, node, net->num_tensors - 1);
+}
+
+bcnn_status bcnn_net_add_dst_tensor(bcnn_net *net, bcnn_node *node, int n, int c, int h, int w,
+                                    const char *dst_id) {
+    bcnn_tensor t = {0};
+    bcnn_tensor_set_shape(&t, n, c, h, w, 1);
+    BCNN_CHECK_STATUS(bcnn_tensor_allocate(&t, net->mode));
+    t.name = bcnn_strdup_(dst_id);
+    BCNN_CHECK_STATUS(bcnn_net_add_tensor(net, t));
+    return bcnn_node_add_output(net, node, net->num_tensors - 1);
+}
+
+void bcnn_net_require_workspace(bcnn_net *net, size_t bytes) {
+    bcnn_cuda_context *ctx = bcnn_ctx(net);
+    if (bytes > ctx->workspace_bytes) ctx->workspace_bytes = bytes;
+}
+
+int bcnn_net_global_batch(bcnn_net *net) { return net->batch_size * bcnn_dp_world_size(net); }
+
+float bcnn_net_grad_post_scale(bcnn_net *net, float momentum) {
+    return momentum / (float)bcnn_dp_world_size(net);
+}
+
+/* ---------------- extension API (include/bcnn_b200_net.h) ---------------- */
+
+void bcnn_b200_set_conv_math(bcnn_net *net, int math) { bcnn_ctx(net)->conv_math = math; }
+int bcnn_b200_get_conv_math(bcnn_net *net) { return bcnn_ctx(net)->conv_math; }
+void *bcnn_b200_get_stream(bcnn_net *net) { return bcnn_stream(net); }
+
+void bcnn_b200_sync(bcnn_net *net) {
+    bcnn_dp_sync(net);
+    bcnn_cuda_check(bcnn_b200_stream_sync(bcnn_stream(net)));
+}
+
+bcnn_status bcnn_b200_upload_tensor(bcnn_net *net, int index) {
+    if (index < 0 || index >= net->num_tensors) return BCNN_INVALID_PARAMETER;
+    bcnn_tensor *t = &net->tensors[index];
+    size_t bytes = (size_t)bcnn_tensor_size(t) * sizeof(float);
+    void *stream = bcnn_stream(net);
+    if (t->data && t->data_gpu) bcnn_cuda_check(bcnn_b200_memcpy_h2d(t->data_gpu, t->data, bytes, stream));
+    if (t->grad_data && t->grad_data_gpu)
+        bcnn_cuda_check(bcnn_b200_memcpy_h2d(t->grad_data_gpu, t->grad_data, bytes, stream));
+    bcnn_cuda_check(bcnn_b200_stream_sync(stream));
+    return BCNN_SUCCESS;
+}
+
+size_t bcnn_b200_upload_inputs(bcnn_net *net) {
+    size_t queued = 0;
+    void *stream = bcnn_stream(net);
+    for (int i = 0; i <= net->num_inputs; ++i) { /* inputs[], then the label (tensor 1) */
+        bcnn_tensor *t = &net->tensors[i < net->num_inputs ? net->inputs[i] : 1];
+        size_t bytes = (size_t)bcnn_tensor_size(t) * sizeof(float);
+        if (!t->data || !t->data_gpu || bytes == 0) continue;
+        bcnn_cuda_check(bcnn_b200_memcpy_h2d(t->data_gpu, t->data, bytes, stream));
+        queued += bytes;
+    }
+    return queued;
+}
+
+float bcnn_b200_get_loss(bcnn_net *net) {
+    float loss = 0.f;
+    int count = 0;
+    void *stream = bcnn_stream(net);
+    for (int i = 0; i < net->num_nodes; ++i) {
+        if (net->nodes[i].type != BCNN_LAYER_COST) continue;
+        float v = 0.f;
+        bcnn_cuda_check(bcnn_b200_memcpy_d2h(&v, net->tensors[net->nodes[i].dst[0]].data_gpu,
+                                             sizeof(float), stream));
+        bcnn_cuda_check(bcnn_b200_stream_sync(stream));
+        loss += v;
+        ++count;
+    }
+    return count ? loss / count : 0.f;
+}
+
+float bcnn_b200_train_step(bcnn_net *net, int upload_inputs, int fetch_loss) {
+    if (upload_inputs) bcnn_b200_upload_inputs(net);
+    bcnn_forward(net);
+    bcnn_backward(net);
+    bcnn_update(net);
+    return fetch_loss ? bcnn_b200_get_loss(net) : 0.f;
+}
+
+int bcnn_b200_num_nodes(bcnn_net *net) { return net->num_nodes; }
+int bcnn_b200_num_tensors(bcnn_net *net) { return net->num_tensors; }
+int bcnn_b200_node_type(bcnn_net *net, int node) {
+    return (node >= 0 && node < net->num_nodes) ? (int)net->nodes[node].type : -1;
+}
+int bcnn_b200_node_src(bcnn_net *net, int node, int i) {
+    if (node < 0 || node >= net->num_nodes || i < 0 || i >= net->nodes[node].num_src) return -1;
+    return net->nodes[node].src[i];
+}
+int bcnn_b200_node_dst(bcnn_net *net, int node, int i) {
+    if (node < 0 || node >= net->num_nodes || i < 0 || i >= net->nodes[node].num_dst) return -1;
+    return net->nodes[node].dst[i];
+}

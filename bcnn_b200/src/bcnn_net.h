@@ -1,0 +1,79 @@
+/*
+ * bcnn_net.h -- the net object. Field order of the reference's CUDA flavour
+ * (jnbraun/bcnn src/bcnn_net.h:34-67) so code that peeks at net->tensors[] /
+ * net->nodes[] keeps working; the B200 state hangs off cuda_ctx.
+ */
+#ifndef BCNN_NET_H
+#define BCNN_NET_H
+
+#include <bcnn/bcnn.h>
+
+#include "bcnn_learner.h"
+#include "bcnn_node.h"
+#include "bcnn_tensor.h"
+#include "bcnn_utils.h"
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+struct bcnn_dp_state; /* bcnn_dp.c */
+
+typedef struct bcnn_cuda_context {
+    int workspace_size;   /* floats; kept for source compatibility */
+    float *workspace_gpu; /* conv workspace shared by all conv nodes */
+    /* --- B200 extensions --- */
+    size_t workspace_bytes;   /* max over conv nodes, sized at construction */
+    void *stream;             /* compute stream (cudaStream_t) */
+    int conv_math;            /* BCNN_B200_MATH_* */
+    struct bcnn_dp_state *dp; /* NULL unless bcnn_b200_dp_init succeeded */
+} bcnn_cuda_context;
+
+struct bcnn_net {
+    int batch_size;
+    int num_nodes;
+    int num_tensors;
+    int num_inputs;
+    int *inputs; /* indexes of the input tensors in tensors[] */
+    bcnn_mode mode;
+    bcnn_log_context log_ctx;
+    bcnn_node *nodes;
+    bcnn_tensor *tensors;
+    bcnn_learner *learner;
+    void *data_loader; /* unused: file loaders are out of scope */
+    void *data_aug;    /* unused */
+    void *gemm_ctx;    /* unused: no CPU GEMM on this path */
+    void *cuda_ctx;    /* bcnn_cuda_context* */
+    int num_threads;
+};
+
+bcnn_status bcnn_net_create_cuda_context(bcnn_net *net);
+bcnn_status bcnn_net_add_node(bcnn_net *net, bcnn_node node);
+bcnn_status bcnn_net_add_tensor(bcnn_net *net, bcnn_tensor tensor);
+
+/* -- helpers shared by the layer files -- */
+static inline bcnn_cuda_context *bcnn_ctx(bcnn_net *net) {
+    return (bcnn_cuda_context *)net->cuda_ctx;
+}
+static inline void *bcnn_stream(bcnn_net *net) { return bcnn_ctx(net)->stream; }
+/* Resolve the source tensor of a new node: by name (reverse scan, last definition wins),
+ * or tensor 0 when the net is still empty. Returns the index or -1. */
+int bcnn_net_find_src(bcnn_net *net, const char *src_id);
+/* Create a named parameter tensor, append it to the net and to node->src[]. */
+bcnn_status bcnn_net_add_param_tensor(bcnn_net *net, bcnn_node *node, int n, int c, int h, int w,
+                                      int has_grad, const char *prefix, const char *suffix,
+                                      const bcnn_tensor_filler *filler);
+/* Allocate the output tensor of a node (device buffers), name it, append it. */
+bcnn_status bcnn_net_add_dst_tensor(bcnn_net *net, bcnn_node *node, int n, int c, int h, int w,
+                                    const char *dst_id);
+/* Grow the shared conv workspace requirement. */
+void bcnn_net_require_workspace(bcnn_net *net, size_t bytes);
+/* Global batch (local batch x data-parallel world) and the factor gradients are scaled
+ * with after an SGD step (momentum, or momentum / world under data parallelism). */
+int bcnn_net_global_batch(bcnn_net *net);
+float bcnn_net_grad_post_scale(bcnn_net *net, float momentum);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* BCNN_NET_H */

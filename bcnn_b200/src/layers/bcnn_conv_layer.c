@@ -1,0 +1,220 @@
+/*
+ * bcnn_conv_layer.c -- convolution node on the B200 kernels.
+ *
+ * Node layout is the reference's (jnbraun/bcnn src/layers/bcnn_conv_layer.c:45-365):
+ * src[0] = x, src[1] = W [Cout, Cin/g, k, k] ("<src>_w"), src[2] = bias / beta ("<src>_b"),
+ * with batch_norm: src[3] = running mean, src[4] = running var, src[5] = gamma
+ * ("<src>_scales"); PReLU slopes follow at src[3 + 3*batch_norm]. Output extent
+ * (H + 2p - k) / s + 1.
+ *
+ * Execution differs from the reference's GPU path (:590-790: per-image im2col + cuBLAS
+ * SGEMM, then separate bias / BN / activation kernels): one implicit-GEMM launch covers
+ * the whole batch; bias + activation are fused into its epilogue, or, with batch_norm,
+ * the raw result goes to bn_workspace_gpu and one fused BN(+activation) pass writes dst.
+ * Backward fuses activation-backward into the BN (or bias-gradient) reduction.
+ * Semantics kept from the CPU path (:487-587): weight gradients accumulate (beta = 1),
+ * the data gradient overwrites src.grad (beta = 0 + zero-filling col2im).
+ */
+#include "bcnn_conv_layer.h"
+
+#include "bcnn_activation_layer.h"
+#include "bcnn_batchnorm_layer.h"
+#include "bcnn_learner.h"
+#include "bcnn_tensor.h"
+
+bcnn_status bcnn_add_convolutional_layer(bcnn_net *net, int n, int size, int stride, int pad,
+                                         int num_groups, int batch_norm, bcnn_filler_type init,
+                                         bcnn_activation activation, int quantize,
+                                         const char *src_id, const char *dst_id) {
+    (void)quantize;
+    bcnn_node node = {0};
+    int src = bcnn_net_find_src(net, src_id);
+    if (net->num_nodes > 0) {
+        BCNN_CHECK_AND_LOG(net->log_ctx, src >= 0, BCNN_INVALID_PARAMETER,
+                           "Convolution layer: invalid input node name %s\n", src_id);
+    } else {
+        BCNN_CHECK_AND_LOG(net->log_ctx, bcnn_tensor_size(&net->tensors[0]) > 0,
+                           BCNN_INVALID_PARAMETER,
+                           "Invalid input size of the network. Hint: Use 'bcnn_set_input_shape' "
+                           "to set the network input size\n");
+    }
+    BCNN_CHECK_STATUS(bcnn_node_add_input(net, &node, src));
+    const int batch = net->tensors[src].n, cin = net->tensors[src].c, h = net->tensors[src].h,
+              w = net->tensors[src].w;
+    BCNN_CHECK_AND_LOG(net->log_ctx, num_groups > 0 && cin % num_groups == 0,
+                       BCNN_INVALID_PARAMETER,
+                       "Number of input channels has to be a multiple of the number of groups\n");
+    BCNN_CHECK_AND_LOG(net->log_ctx, n % num_groups == 0, BCNN_INVALID_PARAMETER,
+                       "Number of output channels has to be a multiple of the number of groups\n");
+    BCNN_CHECK_AND_LOG(net->log_ctx, size > 0 && stride > 0 && pad >= 0, BCNN_INVALID_PARAMETER,
+                       "Convolution layer: invalid kernel size / stride / pad\n");
+    const int cin_g = cin / num_groups;
+    bcnn_tensor_filler wfill = {.range = size * size * cin_g, .type = init};
+    BCNN_CHECK_STATUS(
+        bcnn_net_add_param_tensor(net, &node, n, cin_g, size, size, 1, src_id, "_w", &wfill));
+    BCNN_CHECK_STATUS(bcnn_net_add_param_tensor(net, &node, 1, 1, 1, n, 1, src_id, "_b", NULL));
+
+    node.type = BCNN_LAYER_CONV2D;
+    node.param_size = sizeof(bcnn_conv_param);
+    bcnn_conv_param *param = (bcnn_conv_param *)calloc(1, node.param_size);
+    BCNN_CHECK(param != NULL, BCNN_FAILED_ALLOC);
+    node.param = param;
+    param->activation = activation;
+    param->pad = pad;
+    param->num = n;
+    param->size = size;
+    param->stride = stride;
+    param->num_groups = num_groups;
+    node.forward = bcnn_forward_conv_layer;
+    node.backward = bcnn_backward_conv_layer;
+    node.update = bcnn_update_conv_layer;
+    node.release_param = bcnn_release_param_conv_layer;
+
+    const int ho = (h + 2 * pad - size) / stride + 1, wo = (w + 2 * pad - size) / stride + 1;
+    BCNN_CHECK_AND_LOG(net->log_ctx, ho > 0 && wo > 0, BCNN_INVALID_PARAMETER,
+                       "Convolution layer: empty output\n");
+    BCNN_CHECK_STATUS(bcnn_net_add_dst_tensor(net, &node, batch, n, ho, wo, dst_id));
+    bcnn_b200_conv_desc desc = {batch, cin, h, w, n, ho, wo, size, stride, pad, num_groups};
+    param->desc = desc;
+    param->workspace_size =
+        bcnn_b200_conv_workspace_bytes(&desc, BCNN_B200_MATH_TC) / sizeof(float);
+    bcnn_net_require_workspace(net, param->workspace_size * sizeof(float));
+    param->reduce_scratch_gpu =
+        (float *)bcnn_b200_malloc(bcnn_b200_bn_scratch_floats(n) * sizeof(float));
+    BCNN_CHECK(param->reduce_scratch_gpu != NULL, BCNN_CUDA_FAILED_ALLOC);
+
+    if (batch_norm) {
+        param->batch_norm = 1;
+        char name[320];
+        snprintf(name, sizeof(name), "%s_sav_mean", src_id);
+        bcnn_tensor_create(&param->saved_mean, 1, 1, 1, n, 1, name, net->mode);
+        snprintf(name, sizeof(name), "%s_sav_var", src_id);
+        bcnn_tensor_create(&param->saved_variance, 1, 1, 1, n, 1, name, net->mode);
+        bcnn_tensor_filler ones = {.value = 1.0f, .type = BCNN_FILLER_FIXED};
+        BCNN_CHECK_STATUS(
+            bcnn_net_add_param_tensor(net, &node, 1, 1, 1, n, 0, src_id, "_run_mean", NULL));
+        BCNN_CHECK_STATUS(
+            bcnn_net_add_param_tensor(net, &node, 1, 1, 1, n, 0, src_id, "_run_var", NULL));
+        BCNN_CHECK_STATUS(
+            bcnn_net_add_param_tensor(net, &node, 1, 1, 1, n, 1, src_id, "_scales", &ones));
+        if (net->mode != BCNN_MODE_PREDICT) { /* raw conv output, needed by BN backward */
+            param->bn_workspace_gpu =
+                (float *)bcnn_b200_malloc((size_t)batch * n * ho * wo * sizeof(float));
+            BCNN_CHECK(param->bn_workspace_gpu != NULL, BCNN_CUDA_FAILED_ALLOC);
+        }
+    }
+    if (activation == BCNN_ACT_PRELU)
+        BCNN_CHECK_STATUS(
+            bcnn_net_add_param_tensor(net, &node, 1, 1, 1, n, 0, src_id, "_prelu_slopes", NULL));
+
+    BCNN_CHECK_STATUS(bcnn_net_add_node(net, node));
+    BCNN_INFO(net->log_ctx,
+              "[Conv2d]%s[%s] %-8s (%4d x%4d x%4d) -> %-8s (%4d x%4d x%4d) %5d (%d) %2d x %2d / "
+              "%2d,%2d\n",
+              batch_norm ? "[BN]" : "", bcnn_act2str(activation), src_id, w, h, cin, dst_id, wo,
+              ho, n, n, num_groups, size, size, stride, pad);
+    return BCNN_SUCCESS;
+}
+
+void bcnn_forward_conv_layer_gpu(bcnn_net *net, bcnn_node *node) {
+    bcnn_conv_param *param = (bcnn_conv_param *)node->param;
+    bcnn_cuda_context *ctx = bcnn_ctx(net);
+    bcnn_tensor *t = net->tensors;
+    bcnn_tensor *src = &t[node->src[0]], *dst = &t[node->dst[0]];
+    bcnn_tensor *weights = &t[node->src[1]], *biases = &t[node->src[2]];
+    void *stream = ctx->stream;
+    param->conv_workspace_gpu = ctx->workspace_gpu;
+    const bcnn_activation act = param->activation;
+    /* PReLU needs per-channel slopes: run it as a separate pass after the fused part */
+    const bcnn_activation fused_act = (act == BCNN_ACT_PRELU) ? BCNN_ACT_NONE : act;
+
+    if (!param->batch_norm) {
+        bcnn_cuda_check(bcnn_b200_conv_forward(&param->desc, src->data_gpu, weights->data_gpu,
+                                               biases->data_gpu, fused_act, dst->data_gpu,
+                                               ctx->workspace_gpu, ctx->workspace_bytes,
+                                               ctx->conv_math, stream));
+    } else {
+        float *raw = param->bn_workspace_gpu ? param->bn_workspace_gpu : dst->data_gpu;
+        bcnn_cuda_check(bcnn_b200_conv_forward(&param->desc, src->data_gpu, weights->data_gpu,
+                                               NULL, BCNN_ACT_NONE, raw, ctx->workspace_gpu,
+                                               ctx->workspace_bytes, ctx->conv_math, stream));
+        bcnn_forward_batchnorm_gpu(net, raw, dst, &t[node->src[3]], &t[node->src[4]],
+                                   &t[node->src[5]], biases, &param->saved_mean,
+                                   &param->saved_variance, param->reduce_scratch_gpu, net->mode,
+                                   fused_act);
+    }
+    if (act == BCNN_ACT_PRELU) {
+        bcnn_tensor *slopes = &t[node->src[3 + 3 * param->batch_norm]];
+        bcnn_cuda_check(bcnn_b200_activation_forward(dst->data_gpu, bcnn_tensor_size(dst), act,
+                                                     slopes->data_gpu, dst->w * dst->h, dst->c,
+                                                     stream));
+    }
+}
+
+void bcnn_backward_conv_layer_gpu(bcnn_net *net, bcnn_node *node) {
+    bcnn_conv_param *param = (bcnn_conv_param *)node->param;
+    bcnn_cuda_context *ctx = bcnn_ctx(net);
+    bcnn_tensor *t = net->tensors;
+    bcnn_tensor *src = &t[node->src[0]], *dst = &t[node->dst[0]];
+    bcnn_tensor *weights = &t[node->src[1]], *biases = &t[node->src[2]];
+    void *stream = ctx->stream;
+    bcnn_activation act = param->activation;
+
+    if (act == BCNN_ACT_PRELU) {
+        bcnn_tensor *slopes = &t[node->src[3 + 3 * param->batch_norm]];
+        bcnn_cuda_check(bcnn_b200_activation_backward(
+            dst->data_gpu, dst->grad_data_gpu, bcnn_tensor_size(dst), act, slopes->data_gpu,
+            slopes->grad_data_gpu, dst->w * dst->h, dst->c, stream));
+        act = BCNN_ACT_NONE;
+    }
+    if (param->batch_norm) {
+        bcnn_backward_batchnorm_gpu(net, param->bn_workspace_gpu, dst->data_gpu, dst,
+                                    &t[node->src[3]], &t[node->src[4]], &t[node->src[5]], biases,
+                                    &param->saved_mean, &param->saved_variance,
+                                    param->reduce_scratch_gpu, net->mode, act);
+    } else {
+        bcnn_cuda_check(bcnn_b200_actbwd_grad_bias(biases->grad_data_gpu, dst->grad_data_gpu,
+                                                   dst->data_gpu, act, dst->n, dst->c,
+                                                   dst->h * dst->w, param->reduce_scratch_gpu,
+                                                   stream));
+    }
+    bcnn_cuda_check(bcnn_b200_conv_backward_weights(
+        &param->desc, src->data_gpu, dst->grad_data_gpu, weights->grad_data_gpu,
+        ctx->workspace_gpu, ctx->workspace_bytes, ctx->conv_math, stream));
+    if (src->grad_data_gpu)
+        bcnn_cuda_check(bcnn_b200_conv_backward_data(
+            &param->desc, weights->data_gpu, dst->grad_data_gpu, src->grad_data_gpu,
+            /*accumulate=*/0, ctx->workspace_gpu, ctx->workspace_bytes, ctx->conv_math, stream));
+}
+
+void bcnn_forward_conv_layer(bcnn_net *net, bcnn_node *node) {
+    bcnn_forward_conv_layer_gpu(net, node);
+}
+
+void bcnn_backward_conv_layer(bcnn_net *net, bcnn_node *node) {
+    bcnn_backward_conv_layer_gpu(net, node);
+}
+
+/* bcnn_update_conv_layer (reference :810-855): only W and the bias / beta are stepped;
+ * gamma ("scales") receives gradients that no update ever applies. */
+void bcnn_update_conv_layer(bcnn_net *net, bcnn_node *node) {
+    bcnn_tensor *weights = &net->tensors[node->src[1]];
+    bcnn_tensor *biases = &net->tensors[node->src[2]];
+    if (net->learner->optimizer != BCNN_OPTIM_SGD) {
+        BCNN_WARNING(net->log_ctx, "Only the SGD optimizer is implemented on the B200 path\n");
+        return;
+    }
+    bcnn_sgd_update_gpu(net, weights->data_gpu, biases->data_gpu, weights->grad_data_gpu,
+                        biases->grad_data_gpu, bcnn_tensor_size(weights), bcnn_tensor_size(biases),
+                        bcnn_net_global_batch(net), net->learner->learning_rate,
+                        net->learner->momentum, net->learner->decay);
+}
+
+void bcnn_release_param_conv_layer(bcnn_node *node) {
+    bcnn_conv_param *param = (bcnn_conv_param *)node->param;
+    bcnn_tensor_destroy(&param->saved_mean);
+    bcnn_tensor_destroy(&param->saved_variance);
+    bcnn_b200_free(param->bn_workspace_gpu);
+    bcnn_b200_free(param->reduce_scratch_gpu);
+    /* conv_workspace_gpu belongs to the net */
+}

@@ -1,0 +1,59 @@
+/*
+ * bcnn_conv_layer.h -- convolution node (optionally with fused batchnorm + activation).
+ * Leading fields of bcnn_conv_param follow jnbraun/bcnn src/layers/bcnn_conv_layer.h:34-74
+ * (CUDA flavour, no cuDNN) because the runtime and tools peek at num/size/stride/pad/
+ * num_groups/batch_norm; the CPU-only scratch pointers stay NULL; B200 state is appended.
+ */
+#ifndef BCNN_CONV_LAYER_H
+#define BCNN_CONV_LAYER_H
+
+#include "bcnn_net.h"
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct bcnn_conv_param {
+    int num;
+    int size;
+    int stride;
+    int pad;
+    int num_groups;
+    int batch_norm;
+    int post_func;
+    size_t workspace_size;
+    bcnn_activation activation;
+    bcnn_tensor saved_mean;     /* data_gpu: batch mean;  grad_data_gpu: d(mean)  */
+    bcnn_tensor saved_variance; /* data_gpu: batch var;   grad_data_gpu: d(var)   */
+    float *conv_workspace;      /* CPU im2col buffer of the reference: unused (NULL) */
+    float *workspace;
+    float *weights_workspace;
+    float *biases_workspace;
+    float *scales_workspace;
+    float *slopes_workspace;
+    float *src_workspace;
+    float *dst_workspace;
+    float *x_norm;
+    float *adam_m;
+    float *adam_v;
+    float *conv_workspace_gpu; /* -> net-level shared workspace (split-K partials, packs) */
+    float *bn_workspace_gpu;   /* pre-normalisation conv output, kept for backward */
+    float *x_norm_gpu;         /* not materialised: x_hat is recomputed from saved stats */
+    float *adam_m_gpu;
+    float *adam_v_gpu;
+    /* ---- B200 additions ---- */
+    bcnn_b200_conv_desc desc;
+    float *reduce_scratch_gpu; /* per-layer scratch of the per-channel reductions */
+} bcnn_conv_param;
+
+void bcnn_forward_conv_layer(bcnn_net *net, bcnn_node *node);
+void bcnn_backward_conv_layer(bcnn_net *net, bcnn_node *node);
+void bcnn_update_conv_layer(bcnn_net *net, bcnn_node *node);
+void bcnn_release_param_conv_layer(bcnn_node *node);
+void bcnn_forward_conv_layer_gpu(bcnn_net *net, bcnn_node *node);
+void bcnn_backward_conv_layer_gpu(bcnn_net *net, bcnn_node *node);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* BCNN_CONV_LAYER_H */

@@ -1,0 +1,169 @@
+/*
+ * bcnn_glue_layers.c -- softmax, euclidean cost and residual-add nodes on the device.
+ *
+ * softmax : jnbraun/bcnn src/layers/bcnn_softmax_layer.c:36-166 (forward = softmax over
+ *           channels; backward passes the gradient through: src.grad += dst.grad).
+ * cost    : src/layers/bcnn_cost_layer.c:35-284, euclidean loss only: forward writes
+ *           dst.grad = pred - label and the scalar metric into dst.data[0] (on the device;
+ *           the reference copies three tensors to the host every step); backward does
+ *           src.grad += scale * dst.grad. The label tensor (tensors[1]) takes the source's
+ *           shape when the cost node is added (:70-74).
+ * eltwise : src/layers/bcnn_eltwise_layer.c:33-161, equal-shape inputs only. DEVIATION:
+ *           the reference adds only sample 0 of the batch on this path (:119-121, 148-150,
+ *           SURVEY.md H3); this node adds every sample. Source order follows the
+ *           reference's reverse scan (the later-defined tensor becomes src[0]).
+ */
+#include "bcnn_glue_layers.h"
+
+#include "bcnn_tensor.h"
+
+/* ------------------------------- softmax ------------------------------- */
+
+bcnn_status bcnn_add_softmax_layer(bcnn_net *net, const char *src_id, const char *dst_id) {
+    bcnn_node node = {0};
+    BCNN_CHECK_AND_LOG(net->log_ctx, net->num_nodes >= 1, BCNN_INVALID_PARAMETER,
+                       "Softmax layer can't be the first layer of the network\n");
+    int src = bcnn_get_tensor_index_by_name(net, src_id);
+    BCNN_CHECK_AND_LOG(net->log_ctx, src >= 0, BCNN_INVALID_PARAMETER,
+                       "Softmax layer: invalid input node name %s\n", src_id);
+    BCNN_CHECK_STATUS(bcnn_node_add_input(net, &node, src));
+    const bcnn_tensor *s = &net->tensors[src];
+    BCNN_CHECK_STATUS(bcnn_net_add_dst_tensor(net, &node, s->n, s->c, s->h, s->w, dst_id));
+    node.type = BCNN_LAYER_SOFTMAX;
+    node.forward = bcnn_forward_softmax_layer;
+    node.backward = bcnn_backward_softmax_layer;
+    BCNN_CHECK_STATUS(bcnn_net_add_node(net, node));
+    return BCNN_SUCCESS;
+}
+
+void bcnn_forward_softmax_layer(bcnn_net *net, bcnn_node *node) {
+    bcnn_tensor *src = &net->tensors[node->src[0]], *dst = &net->tensors[node->dst[0]];
+    bcnn_cuda_check(bcnn_b200_softmax_forward(src->data_gpu, dst->data_gpu, src->n, src->c,
+                                              src->h * src->w, bcnn_stream(net)));
+}
+
+void bcnn_backward_softmax_layer(bcnn_net *net, bcnn_node *node) {
+    bcnn_tensor *src = &net->tensors[node->src[0]], *dst = &net->tensors[node->dst[0]];
+    if (!src->grad_data_gpu) return;
+    bcnn_cuda_check(bcnn_b200_axpy(src->grad_data_gpu, dst->grad_data_gpu,
+                                   (size_t)bcnn_tensor_size(src), 1.0f, bcnn_stream(net)));
+}
+
+/* -------------------------------- cost -------------------------------- */
+
+bcnn_status bcnn_add_cost_layer(bcnn_net *net, bcnn_loss loss, bcnn_loss_metric loss_metric,
+                                float scale, const char *src_id, const char *label_id,
+                                const char *dst_id) {
+    (void)label_id; /* the reference always binds tensors[1] */
+    bcnn_node node = {0};
+    BCNN_CHECK_AND_LOG(net->log_ctx, net->num_nodes >= 1, BCNN_INVALID_PARAMETER,
+                       "Cost layer can't be the first layer of the network\n");
+    BCNN_CHECK_AND_LOG(net->log_ctx, loss == BCNN_LOSS_EUCLIDEAN, BCNN_INVALID_PARAMETER,
+                       "Cost layer: only the euclidean loss is available on the B200 path\n");
+    int src = bcnn_get_tensor_index_by_name(net, src_id);
+    BCNN_CHECK_AND_LOG(net->log_ctx, src >= 0, BCNN_INVALID_PARAMETER,
+                       "Cost layer: invalid input node name %s\n", src_id);
+    BCNN_CHECK_STATUS(bcnn_node_add_input(net, &node, src));
+    node.type = BCNN_LAYER_COST;
+    node.param_size = sizeof(bcnn_cost_param);
+    bcnn_cost_param *param = (bcnn_cost_param *)calloc(1, node.param_size);
+    BCNN_CHECK(param != NULL, BCNN_FAILED_ALLOC);
+    node.param = param;
+    param->scale = scale;
+    param->loss = loss;
+    param->loss_metric = loss_metric;
+    node.forward = bcnn_forward_cost_layer;
+    node.backward = bcnn_backward_cost_layer;
+    const bcnn_tensor *s = &net->tensors[src];
+    const int n = s->n, c = s->c, h = s->h, w = s->w;
+    bcnn_tensor_set_shape(&net->tensors[1], n, c, h, w, 0);
+    BCNN_CHECK_STATUS(bcnn_tensor_allocate(&net->tensors[1], net->mode));
+    BCNN_CHECK_STATUS(bcnn_tensor_ensure_host(&net->tensors[1]));
+    BCNN_CHECK_STATUS(bcnn_node_add_input(net, &node, 1));
+    BCNN_CHECK_STATUS(bcnn_net_add_dst_tensor(net, &node, n, c, h, w, dst_id));
+    BCNN_CHECK_STATUS(bcnn_net_add_node(net, node));
+    return BCNN_SUCCESS;
+}
+
+void bcnn_forward_cost_layer(bcnn_net *net, bcnn_node *node) {
+    bcnn_cost_param *param = (bcnn_cost_param *)node->param;
+    bcnn_tensor *src = &net->tensors[node->src[0]], *dst = &net->tensors[node->dst[0]];
+    bcnn_tensor *label = &net->tensors[1];
+    if (!label->data_gpu) return;
+    bcnn_cuda_check(bcnn_b200_cost_forward(src->data_gpu, label->data_gpu, dst->grad_data_gpu,
+                                           dst->data_gpu, src->n, src->c * src->h * src->w,
+                                           (int)param->loss_metric, bcnn_stream(net)));
+}
+
+void bcnn_backward_cost_layer(bcnn_net *net, bcnn_node *node) {
+    bcnn_cost_param *param = (bcnn_cost_param *)node->param;
+    bcnn_tensor *src = &net->tensors[node->src[0]], *dst = &net->tensors[node->dst[0]];
+    if (!src->grad_data_gpu || !dst->grad_data_gpu) return;
+    bcnn_cuda_check(bcnn_b200_axpy(src->grad_data_gpu, dst->grad_data_gpu,
+                                   (size_t)bcnn_tensor_size(src), param->scale, bcnn_stream(net)));
+}
+
+/* ------------------------------- eltwise ------------------------------- */
+
+bcnn_status bcnn_add_eltwise_layer(bcnn_net *net, bcnn_activation activation, const char *src_id1,
+                                   const char *src_id2, const char *dst_id) {
+    bcnn_node node = {0};
+    int found1 = 0, found2 = 0;
+    for (int i = net->num_tensors - 1; i >= 0 && !(found1 && found2); --i) {
+        const char *name = net->tensors[i].name;
+        if (!name) continue;
+        if (!found1 && strcmp(name, src_id1) == 0) {
+            BCNN_CHECK_STATUS(bcnn_node_add_input(net, &node, i));
+            found1 = 1;
+        } else if (!found2 && strcmp(name, src_id2) == 0) {
+            BCNN_CHECK_STATUS(bcnn_node_add_input(net, &node, i));
+            found2 = 1;
+        }
+    }
+    BCNN_CHECK_AND_LOG(net->log_ctx, found1, BCNN_INVALID_PARAMETER,
+                       "Eltwise layer: invalid input node name %s\n", src_id1);
+    BCNN_CHECK_AND_LOG(net->log_ctx, found2, BCNN_INVALID_PARAMETER,
+                       "Eltwise layer: invalid input node name %s\n", src_id2);
+    const bcnn_tensor *a = &net->tensors[node.src[0]], *b = &net->tensors[node.src[1]];
+    BCNN_CHECK_AND_LOG(net->log_ctx, a->n == b->n && a->c == b->c && a->h == b->h && a->w == b->w,
+                       BCNN_INVALID_PARAMETER,
+                       "Eltwise layer: tensors %s and %s must have the same shape on the B200 "
+                       "path\n", src_id1, src_id2);
+    node.type = BCNN_LAYER_ELTWISE;
+    node.param_size = sizeof(bcnn_eltwise_param);
+    bcnn_eltwise_param *param = (bcnn_eltwise_param *)calloc(1, node.param_size);
+    BCNN_CHECK(param != NULL, BCNN_FAILED_ALLOC);
+    node.param = param;
+    param->activation = activation;
+    param->stride[0] = param->stride[1] = 1;
+    param->min_dim[0] = a->c;
+    param->min_dim[1] = a->h;
+    param->min_dim[2] = a->w;
+    node.forward = bcnn_forward_eltwise_layer;
+    node.backward = bcnn_backward_eltwise_layer;
+    const int n = a->n, c = a->c, h = a->h, w = a->w;
+    BCNN_CHECK_STATUS(bcnn_net_add_dst_tensor(net, &node, n, c, h, w, dst_id));
+    BCNN_CHECK_STATUS(bcnn_net_add_node(net, node));
+    BCNN_INFO(net->log_ctx, "[EltWiseAdd] %-8s , %-16s -> %-8s (%4d x%4d x%4d)\n", src_id1,
+              src_id2, dst_id, w, h, c);
+    return BCNN_SUCCESS;
+}
+
+void bcnn_forward_eltwise_layer(bcnn_net *net, bcnn_node *node) {
+    bcnn_eltwise_param *param = (bcnn_eltwise_param *)node->param;
+    bcnn_tensor *t = net->tensors;
+    bcnn_tensor *dst = &t[node->dst[0]];
+    bcnn_cuda_check(bcnn_b200_eltwise_forward(t[node->src[0]].data_gpu, t[node->src[1]].data_gpu,
+                                              dst->data_gpu, bcnn_tensor_size(dst),
+                                              param->activation, bcnn_stream(net)));
+}
+
+void bcnn_backward_eltwise_layer(bcnn_net *net, bcnn_node *node) {
+    bcnn_eltwise_param *param = (bcnn_eltwise_param *)node->param;
+    bcnn_tensor *t = net->tensors;
+    bcnn_tensor *dst = &t[node->dst[0]];
+    bcnn_cuda_check(bcnn_b200_eltwise_backward(
+        dst->data_gpu, dst->grad_data_gpu, t[node->src[0]].grad_data_gpu,
+        t[node->src[1]].grad_data_gpu, bcnn_tensor_size(dst), param->activation,
+        bcnn_stream(net)));
+}

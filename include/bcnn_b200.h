@@ -1,0 +1,241 @@
+/*
+ * bcnn_b200.h -- kernel-level C ABI of libbcnn_b200.so.
+ *
+ * These are the entry points the C layer files (bcnn_b200/src/layers/*.c) call
+ * where jnbraun/bcnn's layer files call its bcnn_cuda_* helpers, cuBLAS and
+ * cuDNN.  Plain pointers and sizes only: device pointers are raw `float *` /
+ * `int *` into cudaMalloc'd memory, `stream` is a cudaStream_t passed as
+ * `void *` (NULL = legacy default stream).  Every launcher returns 0 on success
+ * or the cudaError_t of the failed launch; nothing here synchronises.
+ * All tensors are NCHW float32; element counts fit an int (bcnn_tensor_size,
+ * reference src/bcnn_tensor.c:97).
+ *
+ * Each declaration cites the reference interface it replaces
+ * (paths relative to jnbraun/bcnn @ 3825c4f).
+ */
+#ifndef BCNN_B200_H
+#define BCNN_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define BCNN_B200_API __attribute__((visibility("default")))
+
+/* Convolution arithmetic selection (per net, see bcnn_b200_set_conv_math). */
+enum {
+    BCNN_B200_MATH_FP32 = 0, /* FP32 SIMT implicit GEMM: 1e-5 verification path */
+    BCNN_B200_MATH_TC = 1    /* BF16 tcgen05 implicit GEMM, FP32 accumulate in TMEM:
+                                2e-2 path; falls back per layer to FP32 for shapes
+                                it does not cover (never to the CPU) */
+};
+
+/* Geometry of one convolution; shared by fprop / dgrad / wgrad. */
+typedef struct bcnn_b200_conv_desc {
+    int batch, cin, h, w;      /* input  [batch, cin, h, w]          */
+    int cout, ho, wo;          /* output [batch, cout, ho, wo]       */
+    int ksize, stride, pad;    /* square kernel                      */
+    int groups;                /* cin % groups == cout % groups == 0 */
+} bcnn_b200_conv_desc;
+
+/* ---- device / stream / memory helpers --------------------------------- */
+/* replaces bcnn_cuda_set_device, src/bcnn_utils.c:201 */
+BCNN_B200_API int bcnn_b200_set_device(int device);
+BCNN_B200_API int bcnn_b200_device_count(void);
+BCNN_B200_API int bcnn_b200_sm_count(void);
+/* replaces bcnn_cuda_malloc_f32 / _i32 / bcnn_cuda_free, src/bcnn_utils.c:124-160
+ * (memory comes back zero-filled, like the reference's calloc + H2D copy) */
+BCNN_B200_API void *bcnn_b200_malloc(size_t bytes);
+BCNN_B200_API void bcnn_b200_free(void *dev_ptr);
+BCNN_B200_API void *bcnn_b200_malloc_host(size_t bytes); /* pinned */
+BCNN_B200_API void bcnn_b200_free_host(void *host_ptr);
+/* replaces bcnn_cuda_memcpy_host2dev / dev2host, src/bcnn_utils.c:189-199 */
+BCNN_B200_API int bcnn_b200_memcpy_h2d(void *dst_dev, const void *src_host,
+                                       size_t bytes, void *stream);
+BCNN_B200_API int bcnn_b200_memcpy_d2h(void *dst_host, const void *src_dev,
+                                       size_t bytes, void *stream);
+BCNN_B200_API int bcnn_b200_memcpy_d2d(void *dst_dev, const void *src_dev,
+                                       size_t bytes, void *stream);
+BCNN_B200_API void *bcnn_b200_stream_create(void);
+BCNN_B200_API void bcnn_b200_stream_destroy(void *stream);
+BCNN_B200_API int bcnn_b200_stream_sync(void *stream);
+BCNN_B200_API void *bcnn_b200_event_create(void);
+BCNN_B200_API void bcnn_b200_event_destroy(void *event);
+BCNN_B200_API int bcnn_b200_event_record(void *event, void *stream);
+BCNN_B200_API int bcnn_b200_stream_wait_event(void *stream, void *event);
+BCNN_B200_API float bcnn_b200_event_elapsed_ms(void *start, void *stop);
+BCNN_B200_API const char *bcnn_b200_error_string(int err);
+/* number of kernels this library has launched in this process (bench.py's
+ * gpu_launches claim) */
+BCNN_B200_API uint64_t bcnn_b200_launch_count(void);
+
+/* ---- BLAS-1 class ------------------------------------------------------ */
+/* replaces bcnn_cuda_fill_f32, src/kernels/bcnn_mat.h:264 */
+BCNN_B200_API int bcnn_b200_fill_f32(float *x, size_t n, float value, void *stream);
+/* y += a*x ; replaces bcnn_cuda_axpy, bcnn_mat.h:266 */
+BCNN_B200_API int bcnn_b200_axpy(float *y, const float *x, size_t n, float a,
+                                 void *stream);
+
+/* ---- max pooling ------------------------------------------------------- */
+/* replaces bcnn_forward_maxpool_layer_kernel, src/layers/bcnn_maxpool_layer.cu:28-70
+ * with the CPU rule of src/layers/bcnn_maxpool_layer.c:145-191 (first max wins,
+ * int32 flat NCHW argmax, -1 when the window is empty). */
+BCNN_B200_API int bcnn_b200_maxpool_forward(const float *x, float *y, int *indexes,
+                                            int n, int c, int h, int w, int ksize,
+                                            int stride, int ho, int wo, void *stream);
+/* dx[indexes[o]] += dy[o]; replaces bcnn_backward_maxpool_layer_kernel,
+ * bcnn_maxpool_layer.cu:97-138 (gather form, no atomics, CPU summation order). */
+BCNN_B200_API int bcnn_b200_maxpool_backward(float *dx, const float *dy,
+                                             const int *indexes, int n, int c, int h,
+                                             int w, int ksize, int stride, int ho,
+                                             int wo, void *stream);
+
+/* ---- global average pooling -------------------------------------------- */
+/* replaces _bcnn_forward_avgpool_layer_kernel / _backward_, src/layers/
+ * bcnn_avgpool_layer.cu:29-75; planes = n*c, hw = h*w.  y = mean; dx += dy/hw. */
+BCNN_B200_API int bcnn_b200_avgpool_forward(const float *x, float *y, int planes,
+                                            int hw, void *stream);
+BCNN_B200_API int bcnn_b200_avgpool_backward(float *dx, const float *dy, int planes,
+                                             int hw, void *stream);
+
+/* ---- activations ------------------------------------------------------- */
+/* `act` is a bcnn_activation value.  slope / g_slope are the per-channel PReLU
+ * parameters (NULL otherwise).  In place.  replaces bcnn_forward_activation_gpu /
+ * bcnn_backward_activation_gpu, src/layers/bcnn_activation_layer.cu:64-81,115-135,
+ * with all ten activations of the CPU path (bcnn_activation_layer.c:90-226). */
+BCNN_B200_API int bcnn_b200_activation_forward(float *x, int sz, int act,
+                                               const float *slope, int hw, int c,
+                                               void *stream);
+BCNN_B200_API int bcnn_b200_activation_backward(const float *y, float *dy, int sz,
+                                                int act, const float *slope,
+                                                float *g_slope, int hw, int c,
+                                                void *stream);
+
+/* ---- per-channel bias -------------------------------------------------- */
+/* y[n,c,:] += b[c]; replaces bcnn_cuda_add_bias, src/kernels/bcnn_mat.cu:348-368 */
+BCNN_B200_API int bcnn_b200_add_bias(float *y, const float *bias, int n, int c, int hw,
+                                     void *stream);
+/* gb[c] += sum dy[:,c,:]; replaces bcnn_cuda_grad_bias, bcnn_mat.cu:370-391 (which
+ * races); optionally applies the activation derivative first (dy *= act'(y) in
+ * place, y may be NULL when act == NONE). */
+BCNN_B200_API int bcnn_b200_actbwd_grad_bias(float *gb, float *dy, const float *y,
+                                             int act, int n, int c, int hw,
+                                             float *scratch, void *stream);
+
+/* ---- batch normalisation ----------------------------------------------- */
+/* Scratch needed by the two reduction entry points, in floats. */
+BCNN_B200_API size_t bcnn_b200_bn_scratch_floats(int c);
+/* TRAIN statistics: mean = sum(x)/m, var = sum(x^2)/m - mean^2 (biased, as
+ * _mean_variance_forward, src/layers/bcnn_batchnorm_layer.c:147-168), then
+ * running = 0.9 running + 0.1 batch (:221-224).  replaces fast_mean_kernel /
+ * fast_variance_kernel, src/layers/bcnn_batchnorm_layer.cu:28-89. */
+BCNN_B200_API int bcnn_b200_bn_stats(const float *x, int n, int c, int hw,
+                                     float *saved_mean, float *saved_var,
+                                     float *run_mean, float *run_var, float *scratch,
+                                     void *stream);
+/* y = act(gamma * (x - mean) / sqrt(var + 1e-6) + beta)  (x may alias y).
+ * replaces _norm_forward_kernel + bcnn_scales_kernel + bcnn_cuda_add_bias_kernel
+ * (+ activation kernel), src/kernels/bcnn_mat.cu:179-193,393-410,348-368. */
+BCNN_B200_API int bcnn_b200_bn_apply(const float *x, float *y, const float *mean,
+                                     const float *var, const float *gamma,
+                                     const float *beta, int n, int c, int hw, int act,
+                                     void *stream);
+/* PREDICT mode: y = act(gamma * x + beta) (statistics pre-folded at load time,
+ * scale_and_add_bias, bcnn_batchnorm_layer.c:184-194). */
+BCNN_B200_API int bcnn_b200_scale_bias(const float *x, float *y, const float *gamma,
+                                       const float *beta, int n, int c, int hw,
+                                       int act, void *stream);
+/* Backward of (activation o batchnorm), in place on dy -> dx:
+ *   dy' = dy * act'(y);  g_beta += sum dy';  g_gamma += sum dy' * xhat;
+ *   d_mean, d_var as _mean_variance_backward (bcnn_batchnorm_layer.c:263-281,
+ *   eps 1e-5, var*sqrt(var) form); dx as _normalize_backward (:283-299).
+ * x is the pre-normalisation input kept by the forward pass; y the
+ * post-activation output (may be NULL when act == NONE).  dx_out may alias dy.
+ * replaces fast_mean_delta_kernel / fast_variance_delta_kernel /
+ * _norm_backward_kernel / bcnn_grad_scales_kernel. */
+BCNN_B200_API int bcnn_b200_bn_backward(const float *x, const float *y, float *dy,
+                                        float *dx_out, const float *mean,
+                                        const float *var, const float *gamma,
+                                        float *g_gamma, float *g_beta, float *d_mean,
+                                        float *d_var, int n, int c, int hw, int act,
+                                        float *scratch, void *stream);
+
+/* ---- convolution ------------------------------------------------------- */
+/* Bytes of device workspace the three conv entry points may use for `d`. */
+BCNN_B200_API size_t bcnn_b200_conv_workspace_bytes(const bcnn_b200_conv_desc *d,
+                                                    int math);
+/* y = act(W (*) x + bias)   (bias may be NULL, act may be NONE).
+ * replaces the per-image bcnn_cuda_im2col + bcnn_cuda_gemm loop and
+ * bcnn_cuda_add_bias, src/layers/bcnn_conv_layer.c:628-656 (and the cuDNN
+ * branch :609-620).  One launch for the whole batch. */
+BCNN_B200_API int bcnn_b200_conv_forward(const bcnn_b200_conv_desc *d, const float *x,
+                                         const float *w, const float *bias, int act,
+                                         float *y, void *workspace,
+                                         size_t workspace_bytes, int math,
+                                         void *stream);
+/* dx = W^T (*) dy, overwriting dx (beta = 0 GEMM + zero-filling col2im of the
+ * reference, bcnn_conv_layer.c:567-578, bcnn_mat.c:944); accumulate != 0 gives
+ * dx += (used by the fully-connected layer, bcnn_fc_layer.c:217-223). */
+BCNN_B200_API int bcnn_b200_conv_backward_data(const bcnn_b200_conv_desc *d,
+                                               const float *w, const float *dy,
+                                               float *dx, int accumulate,
+                                               void *workspace, size_t workspace_bytes,
+                                               int math, void *stream);
+/* gw += dy (*) x over the whole batch (beta = 1, bcnn_conv_layer.c:551). */
+BCNN_B200_API int bcnn_b200_conv_backward_weights(const bcnn_b200_conv_desc *d,
+                                                  const float *x, const float *dy,
+                                                  float *gw, void *workspace,
+                                                  size_t workspace_bytes, int math,
+                                                  void *stream);
+
+/* ---- depthwise convolution --------------------------------------------- */
+/* y = act(dw(x, w) + bias); replaces _bcnn_forward_depthwise_conv_weight_kernel,
+ * src/layers/bcnn_depthwise_conv_layer.cu:33-62 (+ add_bias + activation). */
+BCNN_B200_API int bcnn_b200_depthwise_forward(const float *x, const float *w,
+                                              const float *bias, int act, float *y,
+                                              int n, int c, int h, int wd, int ksize,
+                                              int stride, int pad, void *stream);
+/* gw += ..., dx += ... ; replaces the racy weight kernel and the data kernel,
+ * bcnn_depthwise_conv_layer.cu:88-155. */
+BCNN_B200_API int bcnn_b200_depthwise_backward(const float *x, const float *w,
+                                               const float *dy, float *gw, float *dx,
+                                               int n, int c, int h, int wd, int ksize,
+                                               int stride, int pad, float *scratch,
+                                               size_t scratch_floats, void *stream);
+BCNN_B200_API size_t bcnn_b200_depthwise_scratch_floats(int n, int c, int ksize);
+
+/* ---- optimizer --------------------------------------------------------- */
+/* One fused pass of bcnn_sgd_update_gpu (src/bcnn_learner.c:86-103):
+ *   g += wd_scale * w;  w += step * g;  g *= g_scale
+ * with wd_scale = decay*batch (0 for biases), step = -lr/batch, g_scale =
+ * momentum (momentum / world_size under data parallelism). */
+BCNN_B200_API int bcnn_b200_sgd_update(float *w, float *g, size_t n, float wd_scale,
+                                       float step, float g_scale, void *stream);
+
+/* ---- glue kernels ---------------------------------------- */
+/* softmax over channels at each spatial position, log-sum-exp form of
+ * src/layers/bcnn_softmax_layer.c:88-155 */
+BCNN_B200_API int bcnn_b200_softmax_forward(const float *x, float *y, int n, int c,
+                                            int hw, void *stream);
+/* grad = pred - label (bcnn_euclidean_loss_forward, src/layers/bcnn_cost_layer.c
+ * :111-128) and metric[0] = #misclassified (ERROR_RATE) / sum sq (SSE) /
+ * SSE/input_size (MSE) / logloss, computed on device (the reference copies to
+ * the host, :142-158). metric_kind is a bcnn_loss_metric. */
+BCNN_B200_API int bcnn_b200_cost_forward(const float *pred, const float *label,
+                                         float *grad, float *metric, int n,
+                                         int input_size, int metric_kind,
+                                         void *stream);
+/* y = act(a + b) over sz elements (batch-correct residual add). */
+BCNN_B200_API int bcnn_b200_eltwise_forward(const float *a, const float *b, float *y,
+                                            int sz, int act, void *stream);
+/* dy *= act'(y); da += dy; db += dy */
+BCNN_B200_API int bcnn_b200_eltwise_backward(const float *y, float *dy, float *da,
+                                             float *db, int sz, int act, void *stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* BCNN_B200_H */

@@ -1,0 +1,76 @@
+/*
+ * bcnn_b200_net.h -- net-level extensions of libbcnn_b200.so beyond bcnn's public API.
+ *
+ * bcnn's GPU build moves data with synchronous cudaMemcpy hidden in its loader and
+ * weight reader (src/bcnn_data.c:413-425, src/bcnn_net.c:1240-1299), which are out of
+ * scope here; these calls are the explicit equivalents, plus the data-parallel hooks
+ * (bcnn has no multi-GPU support at all) and read-only accessors the parity tests use.
+ * Plain C ABI: pointers, ints, floats.
+ */
+#ifndef BCNN_B200_NET_H
+#define BCNN_B200_NET_H
+
+#include <bcnn/bcnn.h>
+#include <bcnn_b200.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* Convolution arithmetic for every conv node of `net` (BCNN_B200_MATH_*). Default FP32. */
+BCNN_B200_API void bcnn_b200_set_conv_math(bcnn_net *net, int math);
+BCNN_B200_API int bcnn_b200_get_conv_math(bcnn_net *net);
+/* The CUDA stream (cudaStream_t) every kernel of this net is launched on. */
+BCNN_B200_API void *bcnn_b200_get_stream(bcnn_net *net);
+/* Block the host until the net's stream (and its comm stream) are idle. */
+BCNN_B200_API void bcnn_b200_sync(bcnn_net *net);
+
+/* Host -> device copy of tensor `index` (data, and grad when both mirrors exist).
+ * Equivalent of the H2D copies in bcnn_load_weights / bcnn_loader_next. Synchronous. */
+BCNN_B200_API bcnn_status bcnn_b200_upload_tensor(bcnn_net *net, int index);
+/* Asynchronous upload of the input tensors and the label from their pinned host
+ * mirrors on the net's stream (what bcnn_loader_next does every step). Returns the
+ * number of bytes queued. */
+BCNN_B200_API size_t bcnn_b200_upload_inputs(bcnn_net *net);
+/* Mean loss over the cost nodes, as bcnn_get_loss (src/bcnn_net.c:431-450): a
+ * device -> host read of one float per cost node; synchronises the stream. */
+BCNN_B200_API float bcnn_b200_get_loss(bcnn_net *net);
+/* One training step = optional input upload + bcnn_forward + bcnn_backward +
+ * bcnn_update, the body of bcnn_train_on_batch (src/bcnn_net.c:452-463) without the
+ * file loader. Returns the loss when fetch_loss != 0 (which synchronises), else 0. */
+BCNN_B200_API float bcnn_b200_train_step(bcnn_net *net, int upload_inputs, int fetch_loss);
+
+/* ---- introspection for tests ---- */
+BCNN_B200_API int bcnn_b200_num_nodes(bcnn_net *net);
+BCNN_B200_API int bcnn_b200_num_tensors(bcnn_net *net);
+BCNN_B200_API int bcnn_b200_node_type(bcnn_net *net, int node);
+BCNN_B200_API int bcnn_b200_node_src(bcnn_net *net, int node, int i); /* -1 if out of range */
+BCNN_B200_API int bcnn_b200_node_dst(bcnn_net *net, int node, int i);
+/* Copies the max-pool argmax of node `node` (param->indexes_gpu) into host_out
+ * (count = size of the node's dst tensor). Returns the count or -1. */
+BCNN_B200_API int bcnn_b200_maxpool_indexes(bcnn_net *net, int node, int *host_out);
+/* Copies saved_mean / saved_variance of a conv(+BN) or batchnorm node. Returns the
+ * channel count or -1. */
+BCNN_B200_API int bcnn_b200_bn_saved_stats(bcnn_net *net, int node, float *mean_out,
+                                           float *var_out);
+
+/* ---- data parallelism (one process per GPU, NCCL all-reduce of weight grads) ---- */
+#define BCNN_B200_DP_ID_BYTES 128
+/* Rank 0 creates the NCCL unique id; the launcher broadcasts the 128 bytes to every
+ * rank (torch.distributed / MPI / a file -- plumbing, not part of this library). */
+BCNN_B200_API int bcnn_b200_dp_get_unique_id(char id[BCNN_B200_DP_ID_BYTES]);
+/* Join the communicator. After this, bcnn_backward all-reduces each node's parameter
+ * gradients on a dedicated comm stream as soon as that node's backward is queued, and
+ * bcnn_update waits for them, uses batch_size * world as divisor and keeps the
+ * momentum-in-gradient-buffer invariant. */
+BCNN_B200_API int bcnn_b200_dp_init(bcnn_net *net, int rank, int world,
+                                    const char id[BCNN_B200_DP_ID_BYTES]);
+BCNN_B200_API void bcnn_b200_dp_shutdown(bcnn_net *net);
+BCNN_B200_API int bcnn_b200_dp_world(bcnn_net *net);
+/* Bytes all-reduced per step (sum over parameter gradient tensors). */
+BCNN_B200_API size_t bcnn_b200_dp_bytes_per_step(bcnn_net *net);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* BCNN_B200_NET_H */
