@@ -177,14 +177,15 @@ actbwd_gradbias_kernel(float *__restrict__ gb, float *__restrict__ dy, const flo
 // ---- residual add -----------------------------------------------------------------
 __global__ void __launch_bounds__(256)
 eltwise_fwd_kernel(const float *__restrict__ a, const float *__restrict__ b, float *__restrict__ y,
-                   size_t n, int act, bool vec) {
+                   size_t n, size_t n_add, int act, bool vec) {
     size_t gstride = (size_t)gridDim.x * blockDim.x;
     size_t tid = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     size_t done = 0;
     if (vec) {
         size_t n4 = n >> 2;
         for (size_t j = tid; j < n4; j += gstride) {
-            float4 u = ld_stream4(a + (j << 2)), v = ld_stream4(b + (j << 2));
+            float4 u = ld_stream4(a + (j << 2));
+            float4 v = ((j << 2) < n_add) ? ld_stream4(b + (j << 2)) : make_float4(0.f, 0.f, 0.f, 0.f);
             float4 r;
             r.x = act_fwd(u.x + v.x, act, 0.f);
             r.y = act_fwd(u.y + v.y, act, 0.f);
@@ -194,12 +195,13 @@ eltwise_fwd_kernel(const float *__restrict__ a, const float *__restrict__ b, flo
         }
         done = n4 << 2;
     }
-    for (size_t j = done + tid; j < n; j += gstride) y[j] = act_fwd(a[j] + b[j], act, 0.f);
+    for (size_t j = done + tid; j < n; j += gstride)
+        y[j] = act_fwd(a[j] + (j < n_add ? b[j] : 0.f), act, 0.f);
 }
 
 __global__ void __launch_bounds__(256)
 eltwise_bwd_kernel(const float *__restrict__ y, float *__restrict__ dy, float *__restrict__ da,
-                   float *__restrict__ db, size_t n, int act, bool vec) {
+                   float *__restrict__ db, size_t n, size_t n_add, int act, bool vec) {
     size_t gstride = (size_t)gridDim.x * blockDim.x;
     size_t tid = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     size_t done = 0;
@@ -220,7 +222,7 @@ eltwise_bwd_kernel(const float *__restrict__ y, float *__restrict__ dy, float *_
                 u.x += g.x; u.y += g.y; u.z += g.z; u.w += g.w;
                 reinterpret_cast<float4 *>(da)[j] = u;
             }
-            if (db) {
+            if (db && (j << 2) < n_add) {
                 float4 w = reinterpret_cast<float4 *>(db)[j];
                 w.x += g.x; w.y += g.y; w.z += g.z; w.w += g.w;
                 reinterpret_cast<float4 *>(db)[j] = w;
@@ -235,7 +237,7 @@ eltwise_bwd_kernel(const float *__restrict__ y, float *__restrict__ dy, float *_
             dy[j] = g;
         }
         if (da) da[j] += g;
-        if (db) db[j] += g;
+        if (db && j < n_add) db[j] += g;
     }
 }
 
@@ -311,20 +313,20 @@ extern "C" int bcnn_b200_actbwd_grad_bias(float *gb, float *dy, const float *y, 
     return launched();
 }
 
-extern "C" int bcnn_b200_eltwise_forward(const float *a, const float *b, float *y, int sz, int act,
-                                         void *stream) {
+extern "C" int bcnn_b200_eltwise_forward(const float *a, const float *b, float *y, int sz,
+                                         int n_add, int act, void *stream) {
     if (sz <= 0) return 0;
-    bool vec = aligned16(a) && aligned16(b) && aligned16(y);
+    bool vec = aligned16(a) && aligned16(b) && aligned16(y) && (n_add % 4) == 0;
     eltwise_fwd_kernel<<<stream_grid(vec ? sz / 4 + 1 : sz, 256), 256, 0, as_stream(stream)>>>(
-        a, b, y, (size_t)sz, act, vec);
+        a, b, y, (size_t)sz, (size_t)n_add, act, vec);
     return launched();
 }
 
 extern "C" int bcnn_b200_eltwise_backward(const float *y, float *dy, float *da, float *db, int sz,
-                                          int act, void *stream) {
+                                          int n_add, int act, void *stream) {
     if (sz <= 0) return 0;
-    bool vec = aligned16(y) && aligned16(dy) && aligned16(da) && aligned16(db);
+    bool vec = aligned16(y) && aligned16(dy) && aligned16(da) && aligned16(db) && (n_add % 4) == 0;
     eltwise_bwd_kernel<<<stream_grid(vec ? sz / 4 + 1 : sz, 256), 256, 0, as_stream(stream)>>>(
-        y, dy, da, db, (size_t)sz, act, vec);
+        y, dy, da, db, (size_t)sz, (size_t)n_add, act, vec);
     return launched();
 }

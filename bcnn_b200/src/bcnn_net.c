@@ -29,6 +29,7 @@ bcnn_status bcnn_net_create_cuda_context(bcnn_net *net) {
     ctx->conv_math = (math && (math[0] == 't' || math[0] == 'T' || math[0] == '1'))
                          ? BCNN_B200_MATH_TC
                          : BCNN_B200_MATH_FP32;
+    ctx->reference_quirks = 1;
     net->cuda_ctx = ctx;
     return BCNN_SUCCESS;
 }
@@ -227,6 +228,18 @@ bcnn_status bcnn_net_add_dst_tensor(bcnn_net *net, bcnn_node *node, int n, int c
     return bcnn_node_add_output(net, node, net->num_tensors - 1);
 }
 
+int bcnn_net_num_consumers(bcnn_net *net, int index) {
+    int count = 0;
+    for (int i = 0; i < net->num_nodes; ++i) {
+        const bcnn_node *node = &net->nodes[i];
+        if (node->type == BCNN_LAYER_ACTIVATION) continue; /* in place: not a new reader */
+        int inputs = node->type == BCNN_LAYER_ELTWISE ? 2 : 1;
+        for (int j = 0; j < inputs && j < node->num_src; ++j)
+            if (node->src[j] == index) ++count;
+    }
+    return count;
+}
+
 void bcnn_net_require_workspace(bcnn_net *net, size_t bytes) {
     bcnn_cuda_context *ctx = bcnn_ctx(net);
     if (bytes > ctx->workspace_bytes) ctx->workspace_bytes = bytes;
@@ -241,6 +254,7 @@ float bcnn_net_grad_post_scale(bcnn_net *net, float momentum) {
 /* ---------------- extension API (include/bcnn_b200_net.h) ---------------- */
 
 void bcnn_b200_set_conv_math(bcnn_net *net, int math) { bcnn_ctx(net)->conv_math = math; }
+void bcnn_b200_set_reference_quirks(bcnn_net *net, int on) { bcnn_ctx(net)->reference_quirks = on; }
 int bcnn_b200_get_conv_math(bcnn_net *net) { return bcnn_ctx(net)->conv_math; }
 void *bcnn_b200_get_stream(bcnn_net *net) { return bcnn_stream(net); }
 

@@ -26,6 +26,7 @@ typedef struct bcnn_cuda_context {
     size_t workspace_bytes;   /* max over conv nodes, sized at construction */
     void *stream;             /* compute stream (cudaStream_t) */
     int conv_math;            /* BCNN_B200_MATH_* */
+    int reference_quirks;     /* see bcnn_b200_set_reference_quirks; default 1 */
     struct bcnn_dp_state *dp; /* NULL unless bcnn_b200_dp_init succeeded */
 } bcnn_cuda_context;
 
@@ -66,6 +67,9 @@ bcnn_status bcnn_net_add_param_tensor(bcnn_net *net, bcnn_node *node, int n, int
 /* Allocate the output tensor of a node (device buffers), name it, append it. */
 bcnn_status bcnn_net_add_dst_tensor(bcnn_net *net, bcnn_node *node, int n, int c, int h, int w,
                                     const char *dst_id);
+/* Number of nodes that read tensor `index` as an activation input (src[0], or both
+ * inputs of an eltwise node). */
+int bcnn_net_num_consumers(bcnn_net *net, int index);
 /* Grow the shared conv workspace requirement. */
 void bcnn_net_require_workspace(bcnn_net *net, size_t bytes);
 /* Global batch (local batch x data-parallel world) and the factor gradients are scaled

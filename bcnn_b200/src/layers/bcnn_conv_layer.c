@@ -181,10 +181,15 @@ void bcnn_backward_conv_layer_gpu(bcnn_net *net, bcnn_node *node) {
     bcnn_cuda_check(bcnn_b200_conv_backward_weights(
         &param->desc, src->data_gpu, dst->grad_data_gpu, weights->grad_data_gpu,
         ctx->workspace_gpu, ctx->workspace_bytes, ctx->conv_math, stream));
-    if (src->grad_data_gpu)
+    if (src->grad_data_gpu) {
+        /* reference semantics: overwrite. With the quirks off, a source read by several
+         * nodes (residual branches) accumulates instead -- its gradient was zeroed by
+         * bcnn_forward, so every consumer's contribution is summed. */
+        int accumulate = !ctx->reference_quirks && bcnn_net_num_consumers(net, node->src[0]) > 1;
         bcnn_cuda_check(bcnn_b200_conv_backward_data(
-            &param->desc, weights->data_gpu, dst->grad_data_gpu, src->grad_data_gpu,
-            /*accumulate=*/0, ctx->workspace_gpu, ctx->workspace_bytes, ctx->conv_math, stream));
+            &param->desc, weights->data_gpu, dst->grad_data_gpu, src->grad_data_gpu, accumulate,
+            ctx->workspace_gpu, ctx->workspace_bytes, ctx->conv_math, stream));
+    }
 }
 
 void bcnn_forward_conv_layer(bcnn_net *net, bcnn_node *node) {

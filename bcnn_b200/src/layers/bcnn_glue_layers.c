@@ -8,10 +8,11 @@
  *           the reference copies three tensors to the host every step); backward does
  *           src.grad += scale * dst.grad. The label tensor (tensors[1]) takes the source's
  *           shape when the cost node is added (:70-74).
- * eltwise : src/layers/bcnn_eltwise_layer.c:33-161, equal-shape inputs only. DEVIATION:
- *           the reference adds only sample 0 of the batch on this path (:119-121, 148-150,
- *           SURVEY.md H3); this node adds every sample. Source order follows the
- *           reference's reverse scan (the later-defined tensor becomes src[0]).
+ * eltwise : src/layers/bcnn_eltwise_layer.c:33-161, equal-shape inputs only. The
+ *           reference adds only sample 0 of the second input on this path (:119-121,
+ *           148-150); that is reproduced while reference_quirks is on
+ *           (default) and replaced by the batch-correct add when it is off. Source order
+ *           follows the reference's reverse scan (the later-defined tensor becomes src[0]).
  */
 #include "bcnn_glue_layers.h"
 
@@ -153,17 +154,20 @@ void bcnn_forward_eltwise_layer(bcnn_net *net, bcnn_node *node) {
     bcnn_eltwise_param *param = (bcnn_eltwise_param *)node->param;
     bcnn_tensor *t = net->tensors;
     bcnn_tensor *dst = &t[node->dst[0]];
+    const int sz = bcnn_tensor_size(dst);
+    const int n_add = bcnn_ctx(net)->reference_quirks ? param->min_dim[0] * dst->h * dst->w : sz;
     bcnn_cuda_check(bcnn_b200_eltwise_forward(t[node->src[0]].data_gpu, t[node->src[1]].data_gpu,
-                                              dst->data_gpu, bcnn_tensor_size(dst),
-                                              param->activation, bcnn_stream(net)));
+                                              dst->data_gpu, sz, n_add, param->activation,
+                                              bcnn_stream(net)));
 }
 
 void bcnn_backward_eltwise_layer(bcnn_net *net, bcnn_node *node) {
     bcnn_eltwise_param *param = (bcnn_eltwise_param *)node->param;
     bcnn_tensor *t = net->tensors;
     bcnn_tensor *dst = &t[node->dst[0]];
+    const int sz = bcnn_tensor_size(dst);
+    const int n_add = bcnn_ctx(net)->reference_quirks ? param->min_dim[0] * dst->h * dst->w : sz;
     bcnn_cuda_check(bcnn_b200_eltwise_backward(
         dst->data_gpu, dst->grad_data_gpu, t[node->src[0]].grad_data_gpu,
-        t[node->src[1]].grad_data_gpu, bcnn_tensor_size(dst), param->activation,
-        bcnn_stream(net)));
+        t[node->src[1]].grad_data_gpu, sz, n_add, param->activation, bcnn_stream(net)));
 }

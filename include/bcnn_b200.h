@@ -228,12 +228,16 @@ BCNN_B200_API int bcnn_b200_cost_forward(const float *pred, const float *label,
                                          float *grad, float *metric, int n,
                                          int input_size, int metric_kind,
                                          void *stream);
-/* y = act(a + b) over sz elements (batch-correct residual add). */
+/* y = act(a + b') over sz elements, where b' = b on the first n_add elements and 0
+ * beyond. n_add = sz is the batch-correct residual add; n_add = C*H*W reproduces the
+ * reference, whose equal-shape path adds only sample 0 (src/layers/bcnn_eltwise_layer.c
+ * :119-121). replaces bcnn_cuda_copy_f32 + bcnn_cuda_axpy + activation kernel. */
 BCNN_B200_API int bcnn_b200_eltwise_forward(const float *a, const float *b, float *y,
-                                            int sz, int act, void *stream);
-/* dy *= act'(y); da += dy; db += dy */
+                                            int sz, int n_add, int act, void *stream);
+/* dy *= act'(y); da += dy; db[:n_add] += dy[:n_add]  (da / db may be NULL) */
 BCNN_B200_API int bcnn_b200_eltwise_backward(const float *y, float *dy, float *da,
-                                             float *db, int sz, int act, void *stream);
+                                             float *db, int sz, int n_add, int act,
+                                             void *stream);
 
 #ifdef __cplusplus
 }

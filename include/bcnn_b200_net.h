@@ -20,6 +20,13 @@ extern "C" {
 /* Convolution arithmetic for every conv node of `net` (BCNN_B200_MATH_*). Default FP32. */
 BCNN_B200_API void bcnn_b200_set_conv_math(bcnn_net *net, int math);
 BCNN_B200_API int bcnn_b200_get_conv_math(bcnn_net *net);
+/* Reference-quirk mode (default ON = results identical to bcnn's CPU path):
+ *   ON : the residual add touches only sample 0 of the second input (bcnn_eltwise_layer.c
+ *        :119-121) and a convolution's data gradient always overwrites src.grad
+ *        (bcnn_conv_layer.c:567-578), even when src feeds several nodes;
+ *   OFF: batch-correct residual add, and data gradients accumulate into tensors that have
+ *        more than one consumer. ResNet-style training needs OFF to be meaningful. */
+BCNN_B200_API void bcnn_b200_set_reference_quirks(bcnn_net *net, int on);
 /* The CUDA stream (cudaStream_t) every kernel of this net is launched on. */
 BCNN_B200_API void *bcnn_b200_get_stream(bcnn_net *net);
 /* Block the host until the net's stream (and its comm stream) are idle. */

@@ -1,0 +1,52 @@
+"""Regenerate tests/golden/*.npz by running the UNMODIFIED reference CPU library
+(oracle/_ref/libbcnn_ref.so, built from /root/reference by oracle/Makefile) through its own
+public API on the seeded synthetic cases of tests/netcases.py.
+
+    python tests/golden/make_golden.py
+
+The reference ships no golden vectors of its own, so these files are
+the pin: they record what the reference computes, never hand-edited. Large tensors are
+stored as a deterministic 4096-element subsample (key suffix '@sub') to keep fixtures small.
+"""
+import sys
+from pathlib import Path
+
+import numpy as np
+
+ROOT = Path(__file__).resolve().parents[2]
+sys.path.insert(0, str(ROOT))
+sys.path.insert(0, str(ROOT / "tests"))
+
+import netcases  # noqa: E402
+from helpers import GOLDEN, ref_net  # noqa: E402
+
+SUB = 4096
+FULL_CASES = {"chain_b4", "resnet_small_b4"}  # small enough to keep every tensor whole
+
+
+def subsample(a: np.ndarray) -> np.ndarray:
+    flat = a.ravel()
+    if flat.size <= SUB:
+        return flat.copy()
+    idx = np.linspace(0, flat.size - 1, SUB).astype(np.int64)
+    return flat[idx].copy()
+
+
+def main():
+    for name in netcases.CASES:
+        net = ref_net(threads=1)
+        out = netcases.run_case(net, name)
+        net.close()
+        packed = {}
+        for k, v in out.items():
+            if name in FULL_CASES or v.size <= SUB:
+                packed[k] = v
+            else:
+                packed[k + "@sub"] = subsample(v)
+        path = GOLDEN / f"{name}.npz"
+        np.savez_compressed(path, **packed)
+        print(f"{path.name}: {len(packed)} arrays, {path.stat().st_size / 1024:.0f} KiB")
+
+
+if __name__ == "__main__":
+    main()

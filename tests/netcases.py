@@ -1,0 +1,92 @@
+"""Whole-net parity cases shared by the golden generator (tests/golden/make_golden.py), the
+live reference comparison and the GPU tests: build a BASELINE-style net through the bcnn C
+API on either library, inject identical synthetic parameters / inputs / labels, run training
+steps and collect every observable tensor."""
+from __future__ import annotations
+
+import numpy as np
+
+from bcnn_b200 import capi, configs
+
+
+def small_resnet(net, batch=4):
+    """Two bottleneck blocks (one with a projection shortcut, one identity) at 16x16:
+    every ResNet-50 layer kind, including the residual add, at oracle-friendly size."""
+    return configs.resnet50(net, batch=batch, res=32, classes=10, widths=(8, 16), blocks=(1, 2))
+
+
+def chain_convnet(net, batch=4):
+    """Chain-shaped net covering conv(+BN)(+act) variants, both pools, depthwise, avgpool."""
+    net.set_input_shape(20, 20, 3, batch)
+    net.conv(8, 3, 1, 1, 1, 1, "lrelu", "input", "c1")
+    net.maxpool(2, 2, capi.PAD_SAME, "c1", "p1")
+    net.conv(12, 3, 2, 1, 1, 0, "relu", "p1", "c2")
+    net.depthwise(3, 1, 1, "relu", "c2", "dw")
+    net.conv(16, 1, 1, 0, 2, 1, "none", "dw", "c3")
+    net.maxpool(3, 2, capi.PAD_SAME, "c3", "p2")
+    net.avgpool("p2", "gap")
+    net.fullc(10, "none", "gap", "fc")
+    net.softmax("fc", "softmax")
+    net.cost("softmax", "cost")
+    net.sgd(0.01, 0.9, 0.0005)
+    return dict(classes=10, out="softmax")
+
+
+CASES = {
+    # name: (builder, kwargs, steps)
+    "mnist_b8": (configs.mnist, dict(batch=8), 3),
+    "cifar_b4": (configs.cifar, dict(batch=4), 3),
+    "chain_b4": (chain_convnet, dict(batch=4), 2),
+    "resnet_small_b4": (small_resnet, dict(batch=4), 2),
+}
+
+
+def observable_tensors(net):
+    """Indexes of every tensor a user can fetch (all of net->tensors[])."""
+    return list(range(net.lib.bcnn_b200_num_tensors(net.handle)))
+
+
+def run_case(net, name, seed=7, collect_steps=True):
+    """Returns {key: array}: per step the loss-layer metric, all data + grad tensors after
+    backward (before update) for step 0, and all parameter tensors after the last update."""
+    builder, kwargs, steps = CASES[name]
+    builder(net, **kwargs)
+    net.compile()
+    configs.init_params(net, seed=seed)
+    x = configs.synth_input(net.shape("input"), seed=seed + 1)
+    y = configs.synth_labels(net.shape("label"))
+    out = {}
+    pool_nodes = [i for i in range(net.lib.bcnn_b200_num_nodes(net.handle))
+                  if net.lib.bcnn_b200_node_type(net.handle, i) == capi.LAYER_MAXPOOL]
+    for step in range(steps):
+        net.set("input", x)
+        net.set("label", y)
+        net.forward()
+        net.backward()
+        if step == 0:
+            for idx in observable_tensors(net):
+                t = net._tensor(idx)
+                nm = t.name.decode()
+                if t.data:
+                    out[f"s0/data/{idx}:{nm}"] = net.get(idx)
+                if t.grad_data:
+                    out[f"s0/grad/{idx}:{nm}"] = net.get(idx, grad=True)
+            for node in pool_nodes:
+                out[f"s0/argmax/{node}"] = _pool_indexes(net, node)
+        out[f"s{step}/cost"] = net.get("cost").ravel()[:1].copy()
+        net.update()
+    for idx, nm, _ in configs.param_tensors(net):
+        out[f"final/data/{idx}:{nm}"] = net.get(idx)
+        t = net._tensor(idx)
+        if t.grad_data:
+            out[f"final/grad/{idx}:{nm}"] = net.get(idx, grad=True)
+    return out
+
+
+def _pool_indexes(net, node):
+    dst = net.lib.bcnn_b200_node_dst(net.handle, node, 0)
+    t = net._tensor(dst)
+    buf = np.empty(t.n * t.c * t.h * t.w, dtype=np.int32)
+    n = net.lib.bcnn_b200_maxpool_indexes(net.handle, node, buf.ctypes.data)
+    assert n == buf.size
+    return buf

@@ -1,0 +1,449 @@
+"""GPU parity of every kernel-level C-ABI entry point (include/bcnn_b200.h) against the
+oracle restatement (oracle/bcnn_oracle.c) on identical seeded inputs.
+
+Bar: bit-exact for max-pool values and int32 argmax; 1e-5 normalised (tests/helpers.py
+rel_err) for floating point on the FP32 path; 2e-2 on the tensor-core path.
+"""
+import numpy as np
+import pytest
+
+from bcnn_b200 import capi
+from helpers import FP32_TOL, TC_TOL, assert_close, check, dev, dev_zeros, f32, oracle, p
+
+pytestmark = pytest.mark.gpu
+ACT = capi.ACT
+
+
+def rng(seed):
+    return np.random.default_rng(seed)
+
+
+# ------------------------------------------------------------------ max pooling
+POOL_CASES = [
+    # n, c, h, w, k, stride, padding
+    (2, 3, 28, 28, 2, 2, capi.PAD_SAME),    # C1/C2 shape class (vector path)
+    (2, 4, 13, 13, 2, 1, capi.PAD_SAME),    # yolo-tiny k2 s1: bottom/right -FLT_MAX taps
+    (2, 4, 112, 112, 3, 2, capi.PAD_SAME),  # resnet stem pool, overlapping windows
+    (1, 2, 15, 17, 2, 2, capi.PAD_SAME),    # odd sizes (ragged right/bottom)
+    (1, 2, 15, 17, 3, 2, capi.PAD_VALID),
+    (1, 2, 15, 17, 3, 2, capi.PAD_CAFFE),
+    (3, 5, 8, 12, 2, 2, capi.PAD_VALID),
+    (1, 1, 1, 1, 2, 2, capi.PAD_SAME),      # degenerate 1x1
+    (2, 3, 26, 28, 2, 2, capi.PAD_SAME),    # vector path with h even, w % 4 == 0
+    (2, 3, 27, 28, 2, 2, capi.PAD_SAME),    # vector path with odd h (missing bottom row)
+]
+
+
+@pytest.mark.parametrize("case", POOL_CASES)
+@pytest.mark.parametrize("ties", ["random", "relu_zeros", "constant"])
+def test_maxpool_forward_backward_bit_exact(case, ties):
+    n, c, h, w, k, s, pad = case
+    lib, orc = capi.b200(), oracle()
+    r = rng(hash(case) % 2**31)
+    x = f32(r.uniform(-1, 1, size=(n, c, h, w)))
+    if ties == "relu_zeros":
+        x = np.maximum(x, 0).astype(np.float32)     # many exact-zero ties
+    elif ties == "constant":
+        x = np.full_like(x, 0.25)                   # every window is a tie
+    ho = orc.orc_maxpool_out_dim(h, k, s, pad)
+    wo = orc.orc_maxpool_out_dim(w, k, s, pad)
+    y_ref = np.zeros((n, c, ho, wo), np.float32)
+    i_ref = np.zeros((n, c, ho, wo), np.int32)
+    orc.orc_maxpool_forward(p(x), p(y_ref), p(i_ref), n, c, h, w, k, s, ho, wo)
+
+    dx, dy_, di = dev(x), dev_zeros(y_ref.size), dev_zeros(i_ref.size)
+    check(lib.bcnn_b200_maxpool_forward(dx.ptr, dy_.ptr, di.ptr, n, c, h, w, k, s, ho, wo, None))
+    y = dy_.download(np.float32, y_ref.shape)
+    idx = di.download(np.int32, i_ref.shape)
+    assert np.array_equal(idx, i_ref), "argmax indices must be bit-exact"
+    assert np.array_equal(y.view(np.uint32), y_ref.view(np.uint32)), "max values must be bit-exact"
+
+    # backward: dx += scatter(dy) on a non-zero dx (the += contract)
+    g = f32(r.uniform(-1, 1, size=y_ref.shape))
+    gx0 = f32(r.uniform(-1, 1, size=x.shape))
+    gx_ref = gx0.copy()
+    orc.orc_maxpool_backward(p(gx_ref), p(g), p(i_ref), g.size)
+    dgx, dg = dev(gx0), dev(g)
+    check(lib.bcnn_b200_maxpool_backward(dgx.ptr, dg.ptr, di.ptr, n, c, h, w, k, s, ho, wo, None))
+    gx = dgx.download(np.float32, x.shape)
+    assert np.array_equal(gx.view(np.uint32), gx_ref.view(np.uint32)), \
+        "scatter-add must reproduce the CPU summation order bit for bit"
+
+
+def test_maxpool_all_minus_flt_max_gives_index_minus_one():
+    lib, orc = capi.b200(), oracle()
+    x = np.full((1, 1, 4, 4), -np.finfo(np.float32).max, np.float32)
+    y_ref = np.zeros((1, 1, 2, 2), np.float32)
+    i_ref = np.zeros((1, 1, 2, 2), np.int32)
+    orc.orc_maxpool_forward(p(x), p(y_ref), p(i_ref), 1, 1, 4, 4, 2, 2, 2, 2)
+    assert (i_ref == -1).all()
+    dx, dy_, di = dev(x), dev_zeros(4), dev_zeros(4)
+    check(lib.bcnn_b200_maxpool_forward(dx.ptr, dy_.ptr, di.ptr, 1, 1, 4, 4, 2, 2, 2, 2, None))
+    assert np.array_equal(di.download(np.int32), i_ref.ravel())
+    # backward must skip the -1 entries instead of writing out of bounds
+    dgx, dg = dev_zeros(16), dev(np.ones(4, np.float32))
+    check(lib.bcnn_b200_maxpool_backward(dgx.ptr, dg.ptr, di.ptr, 1, 1, 4, 4, 2, 2, 2, 2, None))
+    assert (dgx.download() == 0).all()
+
+
+# ------------------------------------------------------------------ avg pooling
+@pytest.mark.parametrize("n,c,hw", [(2, 1024, 49), (3, 7, 64), (1, 5, 1), (4, 33, 169)])
+def test_avgpool(n, c, hw):
+    lib, orc = capi.b200(), oracle()
+    r = rng(n * 1000 + c)
+    x = f32(r.uniform(-1, 1, size=(n, c, hw)))
+    y_ref = np.zeros((n, c), np.float32)
+    orc.orc_avgpool_forward(p(x), p(y_ref), n, c, hw)
+    dx, dy_ = dev(x), dev_zeros(n * c)
+    check(lib.bcnn_b200_avgpool_forward(dx.ptr, dy_.ptr, n * c, hw, None))
+    assert_close(dy_.download(np.float32, (n, c)), y_ref, FP32_TOL, "avgpool fwd")
+    g = f32(r.uniform(-1, 1, size=(n, c)))
+    gx0 = f32(r.uniform(-1, 1, size=x.shape))
+    gx_ref = gx0.copy()
+    orc.orc_avgpool_backward(p(gx_ref), p(g), n, c, hw)
+    dgx, dg = dev(gx0), dev(g)
+    check(lib.bcnn_b200_avgpool_backward(dgx.ptr, dg.ptr, n * c, hw, None))
+    assert_close(dgx.download(np.float32, x.shape), gx_ref, FP32_TOL, "avgpool bwd")
+
+
+# ------------------------------------------------------------------ activations
+@pytest.mark.parametrize("act", ["tanh", "relu", "ramp", "softplus", "lrelu", "abs", "clamp",
+                                 "prelu", "logistic"])
+@pytest.mark.parametrize("shape", [(2, 6, 8, 8), (3, 5, 7, 7), (1, 1, 1, 3)])
+def test_activation_forward_backward(act, shape):
+    lib, orc = capi.b200(), oracle()
+    n, c, h, w = shape
+    r = rng(len(act) * 97 + n)
+    x = f32(r.uniform(-2, 2, size=shape))
+    x.ravel()[:: 7] = 0.0  # exact zeros: the x > 0 / x >= 0 edges
+    slope = f32(r.uniform(0.05, 0.4, size=c))
+    y_ref = x.copy()
+    orc.orc_activation_forward(p(y_ref), x.size, p(slope), h * w, c, ACT[act])
+    dx, dslope = dev(x), dev(slope)
+    check(lib.bcnn_b200_activation_forward(dx.ptr, x.size, ACT[act],
+                                           dslope.ptr if act == "prelu" else None, h * w, c, None))
+    y = dx.download(np.float32, shape)
+    assert_close(y, y_ref, FP32_TOL, f"{act} fwd")
+
+    g = f32(r.uniform(-1, 1, size=shape))
+    g_ref = g.copy()
+    gs_ref = f32(r.uniform(-1, 1, size=c))
+    gs0 = gs_ref.copy()
+    orc.orc_activation_backward(p(y_ref), p(g_ref), x.size, p(slope), p(gs_ref), h * w, c, ACT[act])
+    dyv, dg, dgs = dev(y_ref), dev(g), dev(gs0)
+    check(lib.bcnn_b200_activation_backward(dyv.ptr, dg.ptr, x.size, ACT[act],
+                                            dslope.ptr if act == "prelu" else None,
+                                            dgs.ptr if act == "prelu" else None, h * w, c, None))
+    assert_close(dg.download(np.float32, shape), g_ref, FP32_TOL, f"{act} bwd")
+    if act == "prelu":
+        assert_close(dgs.download(), gs_ref, FP32_TOL, "prelu slope grad")
+
+
+# ------------------------------------------------------------------ bias kernels
+@pytest.mark.parametrize("n,c,hw", [(4, 32, 196), (3, 7, 49), (2, 255, 169), (64, 10, 1)])
+@pytest.mark.parametrize("act", ["none", "relu", "lrelu"])
+def test_add_bias_and_fused_actbwd_grad_bias(n, c, hw, act):
+    lib, orc = capi.b200(), oracle()
+    r = rng(n * 31 + c)
+    y0 = f32(r.uniform(-1, 1, size=(n, c, hw)))
+    b = f32(r.uniform(-0.5, 0.5, size=c))
+    y_ref = y0.copy()
+    orc.orc_add_bias(p(y_ref), p(b), n, c, hw)
+    dy_, db = dev(y0), dev(b)
+    check(lib.bcnn_b200_add_bias(dy_.ptr, db.ptr, n, c, hw, None))
+    assert_close(dy_.download(np.float32, y0.shape), y_ref, FP32_TOL, "add_bias")
+
+    # fused: dy *= act'(y); gb += sum dy
+    yv = y_ref.copy()
+    orc.orc_activation_forward(p(yv), yv.size, None, hw, c, ACT[act])
+    g = f32(r.uniform(-1, 1, size=(n, c, hw)))
+    g_ref = g.copy()
+    orc.orc_activation_backward(p(yv), p(g_ref), g.size, None, None, hw, c, ACT[act])
+    gb0 = f32(r.uniform(-1, 1, size=c))
+    gb_ref = gb0.copy()
+    orc.orc_grad_bias(p(gb_ref), p(g_ref), n, c, hw)
+    scratch = dev_zeros(lib.bcnn_b200_bn_scratch_floats(c))
+    dg, dyv, dgb = dev(g), dev(yv), dev(gb0)
+    for _ in range(2):  # twice: the ticket counters must re-arm
+        dgb.upload(gb0)
+        dg.upload(g)
+        check(lib.bcnn_b200_actbwd_grad_bias(dgb.ptr, dg.ptr, dyv.ptr, ACT[act], n, c, hw,
+                                             scratch.ptr, None))
+        assert_close(dg.download(np.float32, g.shape), g_ref, FP32_TOL, "act-bwd in place")
+        assert_close(dgb.download(), gb_ref, FP32_TOL, "grad_bias")
+
+
+# ------------------------------------------------------------------ batchnorm
+BN_SHAPES = [(8, 32, 28 * 28), (4, 64, 49), (16, 7, 13 * 13), (128, 512, 1), (2, 3, 5),
+             (6, 256, 196)]
+
+
+@pytest.mark.parametrize("n,c,hw", BN_SHAPES)
+def test_bn_forward_train_and_valid(n, c, hw):
+    lib, orc = capi.b200(), oracle()
+    r = rng(n * 7 + c * 3 + hw)
+    x = f32(r.normal(0.3, 1.2, size=(n, c, hw)))
+    gamma = f32(r.uniform(0.5, 1.5, size=c))
+    beta = f32(r.uniform(-0.3, 0.3, size=c))
+    rm0 = f32(r.uniform(-0.2, 0.2, size=c))
+    rv0 = f32(r.uniform(0.5, 1.5, size=c))
+    for mode in (1, 2):  # TRAIN, VALID
+        y_ref = x.copy()
+        rm, rv = rm0.copy(), rv0.copy()
+        sm, sv = np.zeros(c, np.float32), np.zeros(c, np.float32)
+        xn, xc = np.zeros_like(x), np.zeros_like(x)
+        orc.orc_bn_forward(p(y_ref), n, c, hw, p(rm), p(rv), p(gamma), p(beta), p(sm), p(sv),
+                           p(xn), p(xc), mode)
+        dx, dyo = dev(x), dev_zeros(x.size)
+        dg, db, drm, drv = dev(gamma), dev(beta), dev(rm0), dev(rv0)
+        dsm, dsv = dev_zeros(c), dev_zeros(c)
+        scratch = dev_zeros(lib.bcnn_b200_bn_scratch_floats(c))
+        if mode == 1:
+            check(lib.bcnn_b200_bn_stats(dx.ptr, n, c, hw, dsm.ptr, dsv.ptr, drm.ptr, drv.ptr,
+                                         scratch.ptr, None))
+            check(lib.bcnn_b200_bn_apply(dx.ptr, dyo.ptr, dsm.ptr, dsv.ptr, dg.ptr, db.ptr, n, c,
+                                         hw, 0, None))
+            assert_close(dsm.download(), sm, FP32_TOL, "saved_mean")
+            # var = E[x^2]-mean^2 cancels: normalise against the second moment's scale
+            assert np.abs(dsv.download() - sv).max() <= 2e-5 * (np.abs(sv).max() + np.abs(sm).max() ** 2)
+            assert_close(drm.download(), rm, FP32_TOL, "running mean")
+            assert_close(drv.download(), rv, 2e-5, "running var")
+        else:
+            check(lib.bcnn_b200_bn_apply(dx.ptr, dyo.ptr, drm.ptr, drv.ptr, dg.ptr, db.ptr, n, c,
+                                         hw, 0, None))
+        assert_close(dyo.download(np.float32, x.shape), y_ref, 2e-5, f"bn fwd mode {mode}")
+
+
+@pytest.mark.parametrize("n,c,hw", BN_SHAPES)
+@pytest.mark.parametrize("act", ["none", "relu", "lrelu"])
+def test_bn_backward_fused_with_activation(n, c, hw, act):
+    lib, orc = capi.b200(), oracle()
+    r = rng(n * 5 + c * 11 + hw)
+    x = f32(r.normal(0.1, 1.0, size=(n, c, hw)))
+    gamma = f32(r.uniform(0.5, 1.5, size=c))
+    beta = f32(r.uniform(-0.3, 0.3, size=c))
+    y = x.copy()
+    rm, rv = np.zeros(c, np.float32), np.zeros(c, np.float32)
+    sm, sv = np.zeros(c, np.float32), np.zeros(c, np.float32)
+    xn, xc = np.zeros_like(x), np.zeros_like(x)
+    orc.orc_bn_forward(p(y), n, c, hw, p(rm), p(rv), p(gamma), p(beta), p(sm), p(sv), p(xn), p(xc), 1)
+    orc.orc_activation_forward(p(y), y.size, None, hw, c, ACT[act])
+    g = f32(r.uniform(-1, 1, size=x.shape))
+    g_ref = g.copy()
+    orc.orc_activation_backward(p(y), p(g_ref), g.size, None, None, hw, c, ACT[act])
+    gg0, gb0 = f32(r.uniform(-1, 1, size=c)), f32(r.uniform(-1, 1, size=c))
+    gg, gb = gg0.copy(), gb0.copy()
+    dm, dv = np.zeros(c, np.float32), np.zeros(c, np.float32)
+    orc.orc_bn_backward(p(g_ref), n, c, hw, p(gamma), p(gg), p(gb), p(sm), p(sv), p(dm), p(dv),
+                        p(xn), p(xc))
+    dx, dyv, dg = dev(x), dev(y), dev(g)
+    dsm, dsv, dgam = dev(sm), dev(sv), dev(gamma)
+    dgg, dgb, ddm, ddv = dev(gg0), dev(gb0), dev_zeros(c), dev_zeros(c)
+    scratch = dev_zeros(lib.bcnn_b200_bn_scratch_floats(c))
+    check(lib.bcnn_b200_bn_backward(dx.ptr, dyv.ptr if act != "none" else None, dg.ptr, dg.ptr,
+                                    dsm.ptr, dsv.ptr, dgam.ptr, dgg.ptr, dgb.ptr, ddm.ptr, ddv.ptr,
+                                    n, c, hw, ACT[act], scratch.ptr, None))
+    tol = 5e-5  # two chained FP32 reductions with a different (tree) summation order
+    assert_close(dgb.download(), gb, tol, "g_beta")
+    assert_close(dgg.download(), gg, tol, "g_gamma")
+    assert_close(dg.download(np.float32, x.shape), g_ref, tol, "bn dx")
+
+
+# ------------------------------------------------------------------ convolution
+CONV_CASES = [
+    # batch, cin, h, w, cout, k, stride, pad, groups
+    (4, 1, 28, 28, 32, 3, 1, 1, 1),    # C1 conv1 (K = 9)
+    (4, 32, 14, 14, 32, 3, 1, 1, 1),   # C1 conv2
+    (2, 3, 32, 32, 32, 3, 1, 1, 1),    # C2 conv1 (K = 27)
+    (2, 32, 16, 16, 64, 3, 1, 1, 1),   # C2 conv2_1
+    (2, 3, 32, 32, 16, 7, 2, 3, 1),    # resnet stem class (7x7 s2 p3)
+    (2, 64, 14, 14, 128, 3, 2, 1, 1),  # resnet 3x3 stride 2
+    (2, 64, 14, 14, 256, 1, 1, 0, 1),  # 1x1 expand
+    (2, 96, 14, 14, 48, 1, 2, 0, 1),   # 1x1 stride-2 shortcut
+    (3, 16, 13, 13, 255, 1, 1, 0, 1),  # yolo head: Cout = 255, HW = 169 (odd tails)
+    (2, 8, 9, 11, 12, 3, 1, 0, 2),     # groups = 2, pad 0, ragged
+    (1, 5, 7, 7, 3, 5, 1, 2, 1),       # 5x5
+    (5, 20, 1, 1, 33, 1, 1, 0, 1),     # FC-shaped
+]
+
+
+def _conv_reference(case, seed):
+    batch, cin, h, w, cout, k, s, pad, groups = case
+    orc = oracle()
+    r = rng(seed)
+    d = capi.ConvDesc.make(batch, cin, h, w, cout, k, s, pad, groups)
+    x = f32(r.uniform(-1, 1, size=(batch, cin, h, w)))
+    wt = f32(r.uniform(-1, 1, size=(cout, cin // groups, k, k)) * np.sqrt(3.0 / (cin // groups * k * k)))
+    bias = f32(r.uniform(-0.2, 0.2, size=cout))
+    y = np.zeros((batch, cout, d.ho, d.wo), np.float32)
+    orc.orc_conv_forward(p(x), p(wt), p(y), batch, cin, h, w, cout, k, s, pad, groups)
+    dy = f32(r.uniform(-1, 1, size=y.shape))
+    gw0 = f32(r.uniform(-0.1, 0.1, size=wt.shape))
+    gw = gw0.copy()
+    dx = np.zeros_like(x)
+    orc.orc_conv_backward(p(x), p(wt), p(dy), p(gw), p(dx), batch, cin, h, w, cout, k, s, pad, groups)
+    return d, x, wt, bias, y, dy, gw0, gw, dx
+
+
+@pytest.mark.parametrize("case", CONV_CASES)
+@pytest.mark.parametrize("math,tol", [(capi.MATH_FP32, FP32_TOL), (capi.MATH_TC, TC_TOL)])
+def test_conv_fprop_dgrad_wgrad(case, math, tol):
+    lib, orc = capi.b200(), oracle()
+    d, x, wt, bias, y_ref, dy, gw0, gw_ref, dx_ref = _conv_reference(case, hash(case) % 2**31)
+    ws_bytes = lib.bcnn_b200_conv_workspace_bytes(d, math)
+    ws = capi.DeviceBuffer(nbytes=max(ws_bytes, 4))
+    dxv, dwt, dyo = dev(x), dev(wt), dev_zeros(y_ref.size)
+    # raw forward
+    check(lib.bcnn_b200_conv_forward(d, dxv.ptr, dwt.ptr, None, 0, dyo.ptr, ws.ptr, ws_bytes, math, None))
+    assert_close(dyo.download(np.float32, y_ref.shape), y_ref, tol, "fprop")
+    # fused bias + relu epilogue
+    yb = y_ref.copy()
+    orc.orc_add_bias(p(yb), p(bias), d.batch, d.cout, d.ho * d.wo)
+    orc.orc_activation_forward(p(yb), yb.size, None, d.ho * d.wo, d.cout, ACT["relu"])
+    db = dev(bias)
+    check(lib.bcnn_b200_conv_forward(d, dxv.ptr, dwt.ptr, db.ptr, ACT["relu"], dyo.ptr, ws.ptr,
+                                     ws_bytes, math, None))
+    assert_close(dyo.download(np.float32, y_ref.shape), yb, tol, "fprop + bias + relu")
+    # wgrad accumulates on top of gw0
+    ddy, dgw = dev(dy), dev(gw0)
+    check(lib.bcnn_b200_conv_backward_weights(d, dxv.ptr, ddy.ptr, dgw.ptr, ws.ptr, ws_bytes, math, None))
+    assert_close(dgw.download(np.float32, wt.shape), gw_ref, tol, "wgrad (+=)")
+    # dgrad overwrites garbage
+    ddx = dev(np.full(x.shape, 7.0, np.float32))
+    check(lib.bcnn_b200_conv_backward_data(d, dwt.ptr, ddy.ptr, ddx.ptr, 0, ws.ptr, ws_bytes, math, None))
+    assert_close(ddx.download(np.float32, x.shape), dx_ref, tol, "dgrad (overwrite)")
+    # dgrad accumulate flavour (fully-connected layer contract)
+    base = np.full(x.shape, 0.5, np.float32)
+    ddx.upload(base)
+    check(lib.bcnn_b200_conv_backward_data(d, dwt.ptr, ddy.ptr, ddx.ptr, 1, ws.ptr, ws_bytes, math, None))
+    assert_close(ddx.download(np.float32, x.shape), dx_ref + base, tol, "dgrad (+=)")
+
+
+def test_conv_linearity_at_resnet_size():
+    """Size-independent property at a BASELINE-size layer (too slow for the scalar oracle):
+    conv(a*x1 + x2) == a*conv(x1) + conv(x2), and dgrad/wgrad adjointness
+    <conv(x), dy> == <x, dgrad(dy)> == <W, wgrad(x, dy)>."""
+    lib = capi.b200()
+    case = (8, 64, 56, 56, 64, 3, 1, 1, 1)
+    batch, cin, h, w, cout, k, s, pad, groups = case
+    d = capi.ConvDesc.make(*case)
+    r = rng(99)
+    x1 = f32(r.uniform(-1, 1, size=(batch, cin, h, w)))
+    x2 = f32(r.uniform(-1, 1, size=(batch, cin, h, w)))
+    wt = f32(r.uniform(-1, 1, size=(cout, cin, k, k)) / np.sqrt(cin * k * k))
+    dy = f32(r.uniform(-1, 1, size=(batch, cout, d.ho, d.wo)))
+    ws_bytes = lib.bcnn_b200_conv_workspace_bytes(d, capi.MATH_FP32)
+    ws = capi.DeviceBuffer(nbytes=max(ws_bytes, 4))
+    dw = dev(wt)
+
+    def fwd(x):
+        dxv, dyo = dev(x), dev_zeros(dy.size)
+        check(lib.bcnn_b200_conv_forward(d, dxv.ptr, dw.ptr, None, 0, dyo.ptr, ws.ptr, ws_bytes,
+                                         capi.MATH_FP32, None))
+        return dyo.download(np.float32, dy.shape)
+
+    y1, y2, y12 = fwd(x1), fwd(x2), fwd(f32(0.5 * x1 + x2))
+    assert_close(y12, 0.5 * y1 + y2, 2e-5, "linearity")
+    ddy, ddx, dgw = dev(dy), dev_zeros(x1.size), dev_zeros(wt.size)
+    check(lib.bcnn_b200_conv_backward_data(d, dw.ptr, ddy.ptr, ddx.ptr, 0, ws.ptr, ws_bytes,
+                                           capi.MATH_FP32, None))
+    dxv = dev(x1)
+    check(lib.bcnn_b200_conv_backward_weights(d, dxv.ptr, ddy.ptr, dgw.ptr, ws.ptr, ws_bytes,
+                                              capi.MATH_FP32, None))
+    lhs = float(np.sum(y1.astype(np.float64) * dy))
+    via_dx = float(np.sum(x1.astype(np.float64) * ddx.download(np.float32, x1.shape)))
+    via_gw = float(np.sum(wt.astype(np.float64) * dgw.download(np.float32, wt.shape)))
+    assert abs(lhs - via_dx) <= 1e-4 * abs(lhs) and abs(lhs - via_gw) <= 1e-4 * abs(lhs)
+
+
+# ------------------------------------------------------------------ depthwise
+@pytest.mark.parametrize("n,c,h,w,k,s,pad", [(2, 32, 28, 28, 3, 1, 1), (2, 16, 28, 28, 3, 2, 1),
+                                             (1, 7, 9, 11, 3, 1, 0), (2, 4, 12, 12, 5, 1, 2)])
+def test_depthwise(n, c, h, w, k, s, pad):
+    lib, orc = capi.b200(), oracle()
+    r = rng(n + c * 13 + h)
+    x = f32(r.uniform(-1, 1, size=(n, c, h, w)))
+    wt = f32(r.uniform(-0.5, 0.5, size=(c, k, k)))
+    bias = f32(r.uniform(-0.2, 0.2, size=c))
+    ho, wo = (h + 2 * pad - k) // s + 1, (w + 2 * pad - k) // s + 1
+    y_ref = np.zeros((n, c, ho, wo), np.float32)
+    orc.orc_depthwise_forward(p(x), p(wt), p(y_ref), n, c, h, w, k, s, pad)
+    orc.orc_add_bias(p(y_ref), p(bias), n, c, ho * wo)
+    orc.orc_activation_forward(p(y_ref), y_ref.size, None, ho * wo, c, ACT["relu"])
+    dx, dw, db, dyo = dev(x), dev(wt), dev(bias), dev_zeros(y_ref.size)
+    check(lib.bcnn_b200_depthwise_forward(dx.ptr, dw.ptr, db.ptr, ACT["relu"], dyo.ptr, n, c, h, w,
+                                          k, s, pad, None))
+    assert_close(dyo.download(np.float32, y_ref.shape), y_ref, FP32_TOL, "depthwise fwd")
+    dy = f32(r.uniform(-1, 1, size=y_ref.shape))
+    gw0 = f32(r.uniform(-0.1, 0.1, size=wt.shape))
+    gx0 = f32(r.uniform(-0.1, 0.1, size=x.shape))
+    gw, gx = gw0.copy(), gx0.copy()
+    orc.orc_depthwise_backward(p(x), p(wt), p(dy), p(gw), p(gx), n, c, h, w, k, s, pad)
+    nscr = lib.bcnn_b200_depthwise_scratch_floats(n, c, k)
+    scratch = dev_zeros(nscr)
+    ddy, dgw, dgx = dev(dy), dev(gw0), dev(gx0)
+    check(lib.bcnn_b200_depthwise_backward(dx.ptr, dw.ptr, ddy.ptr, dgw.ptr, dgx.ptr, n, c, h, w, k,
+                                           s, pad, scratch.ptr, nscr, None))
+    assert_close(dgw.download(np.float32, wt.shape), gw, 2e-5, "depthwise wgrad")
+    assert_close(dgx.download(np.float32, x.shape), gx, FP32_TOL, "depthwise dgrad")
+
+
+# ------------------------------------------------------------------ optimizer + glue
+@pytest.mark.parametrize("n", [1, 7, 4096, 100003])
+def test_sgd_update_matches_reference_sequence(n):
+    lib, orc = capi.b200(), oracle()
+    r = rng(n)
+    w0, g0 = f32(r.uniform(-1, 1, size=n)), f32(r.uniform(-1, 1, size=n))
+    w, g = w0.copy(), g0.copy()
+    batch, lr, mom, decay = 64, 0.003, 0.9, 0.0005
+    orc.orc_sgd_update(p(w), None, p(g), None, n, 0, batch, lr, mom, decay)
+    dw, dg = dev(w0), dev(g0)
+    wd = float(np.float32(decay) * np.float32(batch))      # float arithmetic, as the C host
+    step = float(-np.float32(lr) / np.float32(batch))
+    check(lib.bcnn_b200_sgd_update(dw.ptr, dg.ptr, n, wd, step, mom, None))
+    # same mul/add sequence without contraction => bit-exact
+    assert np.array_equal(dw.download().view(np.uint32), w.view(np.uint32))
+    assert np.array_equal(dg.download().view(np.uint32), g.view(np.uint32))
+
+
+@pytest.mark.parametrize("n,c,hw", [(64, 10, 1), (3, 1000, 1), (2, 5, 9)])
+def test_softmax(n, c, hw):
+    lib, orc = capi.b200(), oracle()
+    x = f32(rng(c).uniform(-5, 5, size=(n, c, hw)))
+    y_ref = np.zeros_like(x)
+    orc.orc_softmax_forward(p(x), p(y_ref), n, c, hw)
+    dx, dyo = dev(x), dev_zeros(x.size)
+    check(lib.bcnn_b200_softmax_forward(dx.ptr, dyo.ptr, n, c, hw, None))
+    assert_close(dyo.download(np.float32, x.shape), y_ref, FP32_TOL, "softmax")
+
+
+def test_cost_forward_error_rate_and_grad():
+    lib = capi.b200()
+    n, c = 16, 10
+    r = rng(5)
+    pred = f32(r.uniform(0, 1, size=(n, c)))
+    label = np.zeros((n, c), np.float32)
+    label[np.arange(n), np.arange(n) % c] = 1
+    dp_, dl, dg, dm = dev(pred), dev(label), dev_zeros(n * c), dev_zeros(1)
+    check(lib.bcnn_b200_cost_forward(dp_.ptr, dl.ptr, dg.ptr, dm.ptr, n, c, capi.METRIC_ERROR_RATE, None))
+    assert np.array_equal(dg.download(np.float32, pred.shape), pred - label)
+    wrong = float(np.sum(label[np.arange(n), pred.argmax(1)] == 0))
+    assert dm.download()[0] == wrong
+    check(lib.bcnn_b200_cost_forward(dp_.ptr, dl.ptr, dg.ptr, dm.ptr, n, c, capi.METRIC_SSE, None))
+    assert abs(dm.download()[0] - float(((pred - label) ** 2).sum())) < 1e-3
+
+
+def test_eltwise_forward_backward():
+    lib = capi.b200()
+    r = rng(17)
+    a, b = f32(r.uniform(-1, 1, size=4099)), f32(r.uniform(-1, 1, size=4099))
+    da, db, dyo = dev(a), dev(b), dev_zeros(a.size)
+    check(lib.bcnn_b200_eltwise_forward(da.ptr, db.ptr, dyo.ptr, a.size, a.size, ACT["relu"], None))
+    y = dyo.download()
+    assert np.array_equal(y, np.maximum(a + b, 0) * 1.0)
+    g = f32(r.uniform(-1, 1, size=a.size))
+    ga0, gb0 = f32(r.uniform(-1, 1, size=a.size)), f32(r.uniform(-1, 1, size=a.size))
+    dg, dga, dgb = dev(g), dev(ga0), dev(gb0)
+    check(lib.bcnn_b200_eltwise_backward(dyo.ptr, dg.ptr, dga.ptr, dgb.ptr, a.size, a.size, ACT["relu"], None))
+    gm = g * (y > 0)
+    assert np.array_equal(dga.download(), ga0 + gm) and np.array_equal(dgb.download(), gb0 + gm)
