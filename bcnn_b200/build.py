@@ -94,7 +94,7 @@ def build(force: bool = False, verbose: bool = False) -> Path:
     objs = [str(j[1]) for j in jobs]
     if rebuilt or not LIB.exists() or force:
         link = [NVCC, "-shared", *ARCH, "-o", str(LIB), *objs, "-Xcompiler", "-fPIC",
-                "--cudart=static", "-ldl", "-lm", "-lpthread", "-lrt"]
+                "--cudart=static", "-Xlinker", "-Bsymbolic", "-ldl", "-lm", "-lpthread", "-lrt"]
         proc = subprocess.run(link, capture_output=True, text=True)
         if proc.returncode != 0:
             sys.stderr.write(proc.stdout + proc.stderr)

@@ -53,7 +53,10 @@ def load_library(path: os.PathLike | None = None) -> C.CDLL:
         raise RuntimeError(
             f"{p} not found: build the CUDA extension first (python -m bcnn_b200.build). "
             "bcnn_b200 has no CPU or PyTorch fallback path.")
-    return C.CDLL(str(p), mode=C.RTLD_GLOBAL)
+    # RTLD_LOCAL: the library exports the bcnn API names; keep them out of the global
+    # scope so another bcnn build in the same process (the tests' CPU reference) is not
+    # interposed. The library itself is linked -Bsymbolic.
+    return C.CDLL(str(p), mode=C.RTLD_LOCAL)
 
 
 def bind_bcnn_api(lib: C.CDLL, tensor_type) -> None:

@@ -98,7 +98,7 @@ def yolo_tiny(net, batch=1, res=416):
 
 
 def resnet50(net, batch=256, res=224, classes=1000, widths=(64, 128, 256, 512),
-             blocks=(3, 4, 6, 3)):
+             blocks=(3, 4, 6, 3), stage_strides=(1, 2, 2, 2)):
     """ResNet-50 v1.5 (stride on the 3x3). Residual adds use bcnn_add_eltwise_layer."""
     net.set_input_shape(res, res, 3, batch)
     net.conv(widths[0], 7, 2, 3, 1, 1, "relu", "input", "conv1")
@@ -107,7 +107,7 @@ def resnet50(net, batch=256, res=224, classes=1000, widths=(64, 128, 256, 512),
     for s, (mid, nblk) in enumerate(zip(widths, blocks)):
         cout = mid * 4
         for b in range(nblk):
-            stride = 2 if (b == 0 and s > 0) else 1
+            stride = stage_strides[s] if b == 0 else 1
             tag = f"s{s}b{b}"
             net.conv(mid, 1, 1, 0, 1, 1, "relu", prev, tag + "_a")
             net.conv(mid, 3, stride, 1, 1, 1, "relu", tag + "_a", tag + "_b")

@@ -110,7 +110,8 @@ def ref_lib() -> C.CDLL:
     """oracle/_ref/libbcnn_ref.so: the unmodified reference CPU path + ref_shim.c."""
     global _REF
     if _REF is None:
-        lib = C.CDLL(str(REF_SO))
+        import os
+        lib = C.CDLL(str(REF_SO), mode=C.RTLD_LOCAL | getattr(os, "RTLD_DEEPBIND", 0))
         capi.bind_bcnn_api(lib, capi.TensorCPU)
         vp, i = C.c_void_p, C.c_int
         for name, (res, args) in {

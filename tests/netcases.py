@@ -10,9 +10,13 @@ from bcnn_b200 import capi, configs
 
 
 def small_resnet(net, batch=4):
-    """Two bottleneck blocks (one with a projection shortcut, one identity) at 16x16:
-    every ResNet-50 layer kind, including the residual add, at oracle-friendly size."""
-    return configs.resnet50(net, batch=batch, res=32, classes=10, widths=(8, 16), blocks=(1, 2))
+    """Three bottleneck blocks (projection and identity shortcuts) at 8x8: every ResNet-50
+    layer kind, including the residual add, at oracle-friendly size. The stages keep stride 1:
+    the reference mis-reads its operand for 1x1 convolutions with stride > 1
+    (bcnn_conv_layer.c:445-446), so a strided projection shortcut has no reference answer;
+    3x3 stride-2 convolutions are covered by chain_convnet."""
+    return configs.resnet50(net, batch=batch, res=32, classes=10, widths=(8, 16), blocks=(1, 2),
+                            stage_strides=(1, 1))
 
 
 def chain_convnet(net, batch=4):

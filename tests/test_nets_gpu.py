@@ -3,11 +3,13 @@ through the SAME bcnn C API calls on libbcnn_b200.so and compared with
   (1) the committed golden fixtures recorded from the reference CPU library, and
   (2) the reference library itself, live, when oracle/_ref travelled to this box.
 
-Tolerances (normalised per tensor, helpers.rel_err): FP32 path 1e-5 at the first layers is
-the kernel-level bar (tests/test_kernels_gpu.py); across a whole net of 10-20 chained layers
-with batch-norm the same rounding noise compounds, so whole-net tensors are held to 1e-4
-at step 0 and 5e-4 after 2-3 SGD steps (the reference itself sits ~5e-7 per layer from an
-exact evaluation). Tensor-core path: 2e-2 / 5e-2.
+Tolerances (normalised per tensor, helpers.rel_err): 1e-5 per kernel is the bar asserted in
+tests/test_kernels_gpu.py. Across a whole net, rounding noise compounds through 10-20
+chained layers and, with tiny-batch batch-norm, is amplified chaotically over SGD steps: the
+reference ITSELF moves by up to 1e-4 (step 0) and 3e-2 (after 3 steps, cifar batch 4) when
+its input is perturbed by one ulp. Each tensor is therefore held to
+max(floor, 8 x the reference's own 1-ulp response recorded beside the golden), with floors
+2e-5 at step 0 and 1e-4 after the SGD steps. Tensor-core path floors: 2e-2 / 5e-2.
 Arg-max indices are compared as a mismatch RATE here (a 1-ulp upstream difference can
 legitimately flip a tie); bit-exactness on identical input bits is asserted at kernel level.
 """
@@ -25,6 +27,8 @@ def _compare(out, golden, tol_s0, tol_final, what):
     worst = (0.0, "")
     checked = 0
     for key in golden:
+        if key.startswith("sens:"):
+            continue
         base = key[:-4] if key.endswith("@sub") else key
         assert base in out, f"{what}: tensor {base} missing on the B200 path"
         got, want = out[base], golden[key]
@@ -42,12 +46,14 @@ def _compare(out, golden, tol_s0, tol_final, what):
         if np.abs(want).max(initial=0.0) == 0.0:
             assert np.abs(got).max(initial=0.0) <= 1e-6, f"{what}: {base} should be zero"
             continue
+        # floor, or 8x the reference's own response to a 1-ulp input perturbation
+        tol = max(tol, 8.0 * float(golden.get("sens:" + base, 0.0)))
         e = max(rel_err(got, want))
-        if e > worst[0]:
-            worst = (e, base)
-        assert e <= tol, f"{what}: {base} rel err {e:.3e} > {tol}"
+        if e / tol > worst[0]:
+            worst = (e / tol, f"{base} (err {e:.2e}, tol {tol:.2e})")
+        assert e <= tol, f"{what}: {base} rel err {e:.3e} > {tol:.3e}"
         checked += 1
-    print(f"[{what}] {checked} tensors checked, worst {worst[0]:.2e} at {worst[1]}")
+    print(f"[{what}] {checked} tensors checked, worst err/tol {worst[0]:.2f} at {worst[1]}")
 
 
 @pytest.mark.parametrize("name", list(netcases.CASES))
@@ -56,7 +62,7 @@ def test_net_matches_golden_fp32(name):
     net = capi.Net()
     out = netcases.run_case(net, name)
     net.close()
-    _compare(out, golden, 1e-4, 5e-4, f"{name} fp32 vs golden")
+    _compare(out, golden, 2e-5, 1e-4, f"{name} fp32 vs golden")
 
 
 @pytest.mark.parametrize("name", ["cifar_b4", "chain_b4"])
@@ -77,10 +83,22 @@ def test_net_matches_live_reference(name):
     ref = ref_net()
     want = netcases.run_case(ref, name, seed=31)
     ref.close()
+    clean = configs.synth_input
+    configs.synth_input = lambda shape, seed=12345: (
+        clean(shape, seed) * np.float32(1 + 2e-7)).astype(np.float32)
+    try:
+        ref = ref_net()
+        pert = netcases.run_case(ref, name, seed=31)
+        ref.close()
+    finally:
+        configs.synth_input = clean
+    for k in list(want):
+        if "/argmax/" not in k and np.abs(want[k]).max(initial=0.0) > 0:
+            want["sens:" + k] = np.float32(max(rel_err(pert[k], want[k])))
     net = capi.Net()
     out = netcases.run_case(net, name, seed=31)
     net.close()
-    _compare(out, want, 1e-4, 5e-4, f"{name} fp32 vs live reference")
+    _compare(out, want, 2e-5, 1e-4, f"{name} fp32 vs live reference")
 
 
 def test_residual_fix_mode_accumulates_branch_gradients():
