@@ -109,6 +109,8 @@ def bind_b200_ext(lib: C.CDLL) -> None:
         "bcnn_b200_upload_inputs": (sz, [vp]),
         "bcnn_b200_get_loss": (f, [vp]),
         "bcnn_b200_train_step": (f, [vp, i, i]),
+        "bcnn_b200_profile": (None, [vp, i]),
+        "bcnn_b200_profile_node_ms": (i, [vp, i, C.POINTER(C.c_float), C.POINTER(C.c_float)]),
         "bcnn_b200_num_nodes": (i, [vp]),
         "bcnn_b200_num_tensors": (i, [vp]),
         "bcnn_b200_node_type": (i, [vp, i]),

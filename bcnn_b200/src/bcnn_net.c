@@ -78,6 +78,8 @@ void bcnn_end_net(bcnn_net **net) {
     free(p->learner);
     free(p->inputs);
     if (ctx) {
+        for (int i = 0; i < 4 * ctx->profile_nodes; ++i) bcnn_b200_event_destroy(ctx->profile_events[i]);
+        free(ctx->profile_events);
         bcnn_b200_free(ctx->workspace_gpu);
         bcnn_b200_stream_destroy(ctx->stream);
         free(ctx);
@@ -181,20 +183,52 @@ static void reset_output_gradients(bcnn_net *net, bcnn_node *node) {
     }
 }
 
+static inline void profile_mark(bcnn_net *net, int node, int slot) {
+    bcnn_cuda_context *ctx = bcnn_ctx(net);
+    if (ctx->profile && node < ctx->profile_nodes)
+        bcnn_cuda_check(bcnn_b200_event_record(ctx->profile_events[4 * node + slot], ctx->stream));
+}
+
 void bcnn_forward(bcnn_net *net) {
     for (int i = 0; i < net->num_nodes; ++i) {
         bcnn_node *node = &net->nodes[i];
+        profile_mark(net, i, 0);
         if (net->mode == BCNN_MODE_TRAIN) reset_output_gradients(net, node);
         node->forward(net, node);
+        profile_mark(net, i, 1);
     }
 }
 
 void bcnn_backward(bcnn_net *net) {
     for (int i = net->num_nodes - 1; i >= 0; --i) {
         bcnn_node *node = &net->nodes[i];
+        profile_mark(net, i, 2);
         node->backward(net, node);
+        profile_mark(net, i, 3);
         bcnn_dp_after_node_backward(net, node); /* no-op without data parallelism */
     }
+}
+
+void bcnn_b200_profile(bcnn_net *net, int enable) {
+    bcnn_cuda_context *ctx = bcnn_ctx(net);
+    if (enable && ctx->profile_nodes != net->num_nodes) {
+        for (int i = 0; i < 4 * ctx->profile_nodes; ++i) bcnn_b200_event_destroy(ctx->profile_events[i]);
+        free(ctx->profile_events);
+        ctx->profile_nodes = net->num_nodes;
+        ctx->profile_events = (void **)calloc((size_t)4 * net->num_nodes, sizeof(void *));
+        for (int i = 0; i < 4 * net->num_nodes; ++i) ctx->profile_events[i] = bcnn_b200_event_create();
+    }
+    ctx->profile = enable;
+}
+
+int bcnn_b200_profile_node_ms(bcnn_net *net, int node, float *fwd_ms, float *bwd_ms) {
+    bcnn_cuda_context *ctx = bcnn_ctx(net);
+    if (!ctx->profile_events || node < 0 || node >= ctx->profile_nodes) return -1;
+    bcnn_cuda_check(bcnn_b200_stream_sync(ctx->stream));
+    void **e = ctx->profile_events + 4 * node;
+    if (fwd_ms) *fwd_ms = bcnn_b200_event_elapsed_ms(e[0], e[1]);
+    if (bwd_ms) *bwd_ms = bcnn_b200_event_elapsed_ms(e[2], e[3]);
+    return 0;
 }
 
 /* ---------------- helpers for the layer constructors ---------------- */

@@ -28,6 +28,11 @@ typedef struct bcnn_cuda_context {
     int conv_math;            /* BCNN_B200_MATH_* */
     int reference_quirks;     /* see bcnn_b200_set_reference_quirks; default 1 */
     struct bcnn_dp_state *dp; /* NULL unless bcnn_b200_dp_init succeeded */
+    /* per-node CUDA-event timers (the reference only has commented-out bh_timer calls in
+     * bcnn_forward, src/bcnn_net.c:416-420); 4 events per node: fwd begin/end, bwd begin/end */
+    int profile;
+    int profile_nodes;
+    void **profile_events;
 } bcnn_cuda_context;
 
 struct bcnn_net {

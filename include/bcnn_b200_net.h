@@ -47,6 +47,12 @@ BCNN_B200_API float bcnn_b200_get_loss(bcnn_net *net);
  * file loader. Returns the loss when fetch_loss != 0 (which synchronises), else 0. */
 BCNN_B200_API float bcnn_b200_train_step(bcnn_net *net, int upload_inputs, int fetch_loss);
 
+/* Per-node CUDA-event timers: when enabled, bcnn_forward / bcnn_backward bracket every
+ * node with events on the net's stream; read the last step's durations per node. */
+BCNN_B200_API void bcnn_b200_profile(bcnn_net *net, int enable);
+BCNN_B200_API int bcnn_b200_profile_node_ms(bcnn_net *net, int node, float *fwd_ms,
+                                            float *bwd_ms);
+
 /* ---- introspection for tests ---- */
 BCNN_B200_API int bcnn_b200_num_nodes(bcnn_net *net);
 BCNN_B200_API int bcnn_b200_num_tensors(bcnn_net *net);
