@@ -117,13 +117,16 @@ def test_residual_fix_mode_accumulates_branch_gradients():
         net.forward()
         net.backward()
         grads[quirks] = (net.get("s1b0_out", grad=True), net.get("s1b1_out", grad=True),
-                         net.get("s1b1_out"))
+                         net.get("s1b1_out"), net.get("s1b0_out"))
         net.close()
-    prev_on, out_on, y_on = grads[True]
-    prev_off, out_off, y_off = grads[False]
+    prev_on, out_on, y_on, prev_data = grads[True]
+    prev_off, out_off, y_off, _ = grads[False]
     assert_close(y_off, y_on, 1e-6, "forward identical at batch 1")
     assert_close(out_off, out_on, 1e-6, "block output gradient identical")
-    assert_close(prev_off, prev_on + out_on, 1e-5, "branch gradients accumulate")
+    # what is fetched is prev.grad after the PREVIOUS block's eltwise backward has applied
+    # its ReLU derivative in place, hence the mask
+    mask = (prev_data > 0).astype(np.float32)
+    assert_close(prev_off, prev_on + out_on * mask, 1e-5, "branch gradients accumulate")
 
 
 def test_valid_and_predict_modes_follow_reference_semantics():
