@@ -394,6 +394,7 @@ def bind_kernel_abi(lib: C.CDLL) -> None:
         "bcnn_b200_bn_backward": (i, [vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, i, i, i, i,
                                       vp, vp]),
         "bcnn_b200_conv_workspace_bytes": (sz, [dp, i]),
+        "bcnn_b200_conv_uses_tensor_cores": (i, [dp, i]),
         "bcnn_b200_conv_forward": (i, [dp, vp, vp, vp, i, vp, vp, sz, i, vp]),
         "bcnn_b200_conv_backward_data": (i, [dp, vp, vp, vp, i, vp, sz, i, vp]),
         "bcnn_b200_conv_backward_weights": (i, [dp, vp, vp, vp, vp, sz, i, vp]),

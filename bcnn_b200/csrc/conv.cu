@@ -6,6 +6,15 @@
 
 using namespace b200;
 
+extern "C" int bcnn_b200_conv_uses_tensor_cores(const bcnn_b200_conv_desc *d, int pass) {
+    switch (pass) {
+        case 0: return conv_tc_supports_fprop(d) ? 1 : 0;
+        case 1: return conv_tc_supports_dgrad(d) ? 1 : 0;
+        case 2: return conv_tc_supports_wgrad(d) ? 1 : 0;
+    }
+    return 0;
+}
+
 extern "C" size_t bcnn_b200_conv_workspace_bytes(const bcnn_b200_conv_desc *d, int math) {
     size_t a = conv_simt_workspace_bytes(d);
     size_t b = (math == BCNN_B200_MATH_TC) ? conv_tc_workspace_bytes(d) : 0;

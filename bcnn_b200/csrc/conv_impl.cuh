@@ -22,6 +22,7 @@ bool conv_tc_supports_fprop(const bcnn_b200_conv_desc *d);
 bool conv_tc_supports_dgrad(const bcnn_b200_conv_desc *d);
 bool conv_tc_supports_wgrad(const bcnn_b200_conv_desc *d);
 size_t conv_tc_workspace_bytes(const bcnn_b200_conv_desc *d);
+size_t conv_tc_wgrad_workspace_bytes(const bcnn_b200_conv_desc *d);  // conv_tc_wgrad.cu
 int conv_tc_forward(const bcnn_b200_conv_desc *d, const float *x, const float *w,
                     const float *bias, int act, float *y, void *workspace,
                     size_t workspace_bytes, cudaStream_t st);

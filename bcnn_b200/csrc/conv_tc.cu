@@ -18,19 +18,21 @@
 //                     never exists in memory, and no NHWC/BF16 shadow of the activations is
 //                     kept.
 //   pipeline        : 3-4 smem stages; tcgen05.mma is issued by one thread and tracked with
-//                     tcgen05.commit -> mbarrier, so the gather of stage k+1.. overlaps the
-//                     MMAs of stage k.
+//                     tcgen05.commit -> mbarrier; the global loads of k-block k+1 are issued
+//                     into registers before block k is stored / synchronised / multiplied.
 //   epilogue        : tcgen05.ld (32x32b.x32) TMEM -> registers, fused bias + activation,
 //                     coalesced NCHW FP32 stores (a warp's 32 lanes are 32 consecutive
 //                     positions of one channel plane).
 //
-// wgrad stays on the FP32 SIMT kernel in this revision (conv_simt.cu).
+// wgrad lives in conv_tc_wgrad.cu.
 #include <cuda_bf16.h>
 
 #include "common.cuh"
 #include "conv_impl.cuh"
+#include "tc_ptx.cuh"
 
 using namespace b200;
+using namespace b200::tc;
 
 namespace {
 
@@ -60,110 +62,6 @@ struct TcParams {
     int total_pos;             // batch * dst_h * dst_w
     FastDiv d_plane, d_w, d_ks, d_kc, d_stride;
 };
-
-// ---------------------------------------------------------------- PTX wrappers
-__device__ __forceinline__ uint32_t smem_u32(const void *p) {
-    return (uint32_t)__cvta_generic_to_shared(p);
-}
-__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" :: "r"(bar), "r"(count));
-}
-__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(bar), "r"(bytes)
-                 : "memory");
-}
-__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
-    uint32_t done;
-    do {
-        asm volatile(
-            "{\n"
-            ".reg .pred p;\n"
-            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
-            "selp.b32 %0, 1, 0, p;\n"
-            "}\n" : "=r"(done) : "r"(bar), "r"(parity) : "memory");
-    } while (!done);
-}
-__device__ __forceinline__ void bulk_copy_g2s(uint32_t dst_smem, const void *src, uint32_t bytes,
-                                              uint32_t bar) {
-    asm volatile(
-        "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
-        :: "r"(dst_smem), "l"(src), "r"(bytes), "r"(bar) : "memory");
-}
-__device__ __forceinline__ void fence_proxy_async() {
-    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-}
-__device__ __forceinline__ void fence_barrier_init() {
-    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-}
-__device__ __forceinline__ void tc_fence_before() {
-    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-}
-__device__ __forceinline__ void tc_fence_after() {
-    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-}
-__device__ __forceinline__ void tmem_alloc(uint32_t dst_smem, uint32_t ncols) {
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;"
-                 :: "r"(dst_smem), "r"(ncols) : "memory");
-    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
-}
-__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t ncols) {
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" :: "r"(taddr), "r"(ncols)
-                 : "memory");
-}
-// D[tmem] (+)= A[smem] * B[smem]^T, BF16 inputs, FP32 accumulate.
-__device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b,
-                                          uint32_t idesc, uint32_t accumulate) {
-    asm volatile(
-        "{\n"
-        ".reg .pred p;\n"
-        "setp.ne.b32 p, %4, 0;\n"
-        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n"
-        "}\n" :: "r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate) : "memory");
-}
-// Arrive on an mbarrier once every previously issued tcgen05.mma of this thread completed.
-__device__ __forceinline__ void umma_commit(uint32_t bar) {
-    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];"
-                 :: "r"(bar) : "memory");
-}
-__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
-    asm volatile(
-        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
-        "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,%23,"
-        "%24,%25,%26,%27,%28,%29,%30,%31}, [%32];"
-        : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]),
-          "=r"(v[7]), "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]),
-          "=r"(v[14]), "=r"(v[15]), "=r"(v[16]), "=r"(v[17]), "=r"(v[18]), "=r"(v[19]),
-          "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]), "=r"(v[25]),
-          "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
-        : "r"(taddr));
-    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-}
-
-// K-major, 128-byte-swizzled shared-memory matrix descriptor (cute::UMMA::SmemDescriptor):
-// start address >> 4 in [0,14), LBO (unused for swizzled K-major) = 1 in [16,30),
-// SBO = 1024 B (8 rows x 128 B) >> 4 in [32,46), version = 1 in [46,48), layout type
-// SWIZZLE_128B = 2 in [61,64).
-__device__ __forceinline__ uint64_t make_desc_sw128(uint32_t smem_addr) {
-    uint64_t d = 0;
-    d |= (uint64_t)((smem_addr & 0x3FFFF) >> 4);
-    d |= (uint64_t)1 << 16;
-    d |= (uint64_t)(1024 >> 4) << 32;
-    d |= (uint64_t)1 << 46;
-    d |= (uint64_t)2 << 61;
-    return d;
-}
-// Instruction descriptor (cute::UMMA::InstrDescriptor): D = F32 (1 << 4), A = B = BF16
-// (1 << 7, 1 << 10), both K-major, N >> 3 at [17,23), M >> 4 at [24,29).
-__device__ __forceinline__ uint32_t make_idesc(int m, int n) {
-    return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(n >> 3) << 17) |
-           ((uint32_t)(m >> 4) << 24);
-}
-
-__device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
-    uint32_t r;
-    asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
-    return r;
-}
 
 // ---------------------------------------------------------------- weight repack
 // wpack[tile][kb][row][64] with the 16-byte chunk index XOR-swizzled by (row & 7):
@@ -258,21 +156,11 @@ conv_tc_kernel(const TcParams p) {
     const uint32_t idesc = make_idesc(TILE_M, n_tile);
     const uint32_t row_off = (uint32_t)((row >> 3) * 1024 + (row & 7) * 128);
 
-    for (int kb = 0; kb < p.k_blocks; ++kb) {
-        const int s = kb % S;
-        const int round = kb / S;
-        uint8_t *a_stage = smem + (size_t)s * stage_bytes;
-        uint8_t *b_stage = a_stage + A_STAGE_BYTES;
-        // stage s is free once the MMAs issued S k-blocks ago have retired
-        if (kb >= S) mbar_wait(smem_u32(bars + S + s), (round - 1) & 1);
+    float v_raw[32];  // next k-block: global loads in flight (FP32)
+    uint4 pk[4];      // current k-block: packed BF16, ready to store
 
-        if (t == 0) {  // weights: one bulk async copy of the pre-swizzled tile
-            mbar_expect_tx(smem_u32(bars + s), (uint32_t)b_stage_bytes);
-            bulk_copy_g2s(smem_u32(b_stage), wtile + (size_t)kb * n_tile * 64,
-                          (uint32_t)b_stage_bytes, smem_u32(bars + s));
-        }
-
-        // ---- gather A: 32 channels x 1 position per thread
+    // gather A for k-block kb: 32 channels x 1 position per thread
+    auto issue_loads = [&](int kb) {
         uint32_t tap, cb, kh, kw;
         p.d_kc.divmod(kb, tap, cb);
         p.d_ks.divmod(tap, kh, kw);
@@ -295,19 +183,43 @@ conv_tc_kernel(const TcParams p) {
         const int c0 = (int)cb * 64 + chalf * 32;
         const float *gp = src_img + (size_t)c0 * src_plane + (valid ? sh * p.src_w + sw : 0);
         const int c_left = p.src_c - c0;  // channels still inside the tensor
-        float v[32];
 #pragma unroll
         for (int j = 0; j < 32; ++j)
-            v[j] = (valid && j < c_left) ? __ldg(gp + (size_t)j * src_plane) : 0.f;
+            v_raw[j] = (valid && j < c_left) ? __ldg(gp + (size_t)j * src_plane) : 0.f;
+    };
+    auto convert = [&]() {
 #pragma unroll
         for (int q = 0; q < 4; ++q) {
-            uint4 pk;
-            pk.x = pack_bf16x2(v[q * 8 + 0], v[q * 8 + 1]);
-            pk.y = pack_bf16x2(v[q * 8 + 2], v[q * 8 + 3]);
-            pk.z = pack_bf16x2(v[q * 8 + 4], v[q * 8 + 5]);
-            pk.w = pack_bf16x2(v[q * 8 + 6], v[q * 8 + 7]);
+            pk[q].x = pack_bf16x2(v_raw[q * 8 + 0], v_raw[q * 8 + 1]);
+            pk[q].y = pack_bf16x2(v_raw[q * 8 + 2], v_raw[q * 8 + 3]);
+            pk[q].z = pack_bf16x2(v_raw[q * 8 + 4], v_raw[q * 8 + 5]);
+            pk[q].w = pack_bf16x2(v_raw[q * 8 + 6], v_raw[q * 8 + 7]);
+        }
+    };
+
+    issue_loads(0);
+    convert();
+    for (int kb = 0; kb < p.k_blocks; ++kb) {
+        const int s = kb % S;
+        const int round = kb / S;
+        uint8_t *a_stage = smem + (size_t)s * stage_bytes;
+        uint8_t *b_stage = a_stage + A_STAGE_BYTES;
+        // the next block's loads go out first: their latency overlaps the stores, the CTA
+        // barrier and the MMA issue of this block
+        const bool more = kb + 1 < p.k_blocks;
+        if (more) issue_loads(kb + 1);
+        // stage s is free once the MMAs issued S k-blocks ago have retired
+        if (kb >= S) mbar_wait(smem_u32(bars + S + s), (round - 1) & 1);
+
+        if (t == 0) {  // weights: one bulk async copy of the pre-swizzled tile
+            mbar_expect_tx(smem_u32(bars + s), (uint32_t)b_stage_bytes);
+            bulk_copy_g2s(smem_u32(b_stage), wtile + (size_t)kb * n_tile * 64,
+                          (uint32_t)b_stage_bytes, smem_u32(bars + s));
+        }
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
             const uint32_t chunk = (uint32_t)(chalf * 4 + q);
-            *reinterpret_cast<uint4 *>(a_stage + row_off + ((chunk ^ (uint32_t)(row & 7)) << 4)) = pk;
+            *reinterpret_cast<uint4 *>(a_stage + row_off + ((chunk ^ (uint32_t)(row & 7)) << 4)) = pk[q];
         }
         fence_proxy_async();  // generic-proxy smem writes -> visible to the tensor core
         __syncthreads();
@@ -326,6 +238,7 @@ conv_tc_kernel(const TcParams p) {
             umma_commit(smem_u32(bars + S + s));       // frees this stage when the MMAs retire
             if (kb == p.k_blocks - 1) umma_commit(smem_u32(bars + 2 * S));  // accumulator ready
         }
+        if (more) convert();
     }
 
     // ---------------- epilogue: TMEM -> registers -> bias/activation -> NCHW global
@@ -457,11 +370,13 @@ namespace b200 {
 
 bool conv_tc_supports_fprop(const bcnn_b200_conv_desc *d) { return shape_ok(d, d->cin); }
 bool conv_tc_supports_dgrad(const bcnn_b200_conv_desc *d) { return shape_ok(d, d->cout); }
-bool conv_tc_supports_wgrad(const bcnn_b200_conv_desc *) { return false; }
 
 size_t conv_tc_workspace_bytes(const bcnn_b200_conv_desc *d) {
-    size_t need = 0;
-    if (conv_tc_supports_fprop(d)) need = make_plan(d->cout, d->cin, d->ksize).wpack_bytes;
+    size_t need = conv_tc_wgrad_workspace_bytes(d);
+    if (conv_tc_supports_fprop(d)) {
+        size_t a = make_plan(d->cout, d->cin, d->ksize).wpack_bytes;
+        if (a > need) need = a;
+    }
     if (conv_tc_supports_dgrad(d)) {
         size_t b = make_plan(d->cin, d->cout, d->ksize).wpack_bytes;
         if (b > need) need = b;
@@ -479,11 +394,6 @@ int conv_tc_backward_data(const bcnn_b200_conv_desc *d, const float *w, const fl
                           int accumulate, void *workspace, size_t workspace_bytes,
                           cudaStream_t st) {
     return launch_tc<TC_DGRAD>(d, dy, w, nullptr, 0, dx, accumulate, workspace, workspace_bytes, st);
-}
-
-int conv_tc_backward_weights(const bcnn_b200_conv_desc *, const float *, const float *, float *,
-                             void *, size_t, cudaStream_t) {
-    return (int)cudaErrorNotSupported;
 }
 
 }  // namespace b200

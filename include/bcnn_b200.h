@@ -164,6 +164,9 @@ BCNN_B200_API int bcnn_b200_bn_backward(const float *x, const float *y, float *d
                                         float *scratch, void *stream);
 
 /* ---- convolution ------------------------------------------------------- */
+/* 1 when pass (0 fprop, 1 dgrad, 2 wgrad) of `d` runs on the tcgen05 kernel under
+ * BCNN_B200_MATH_TC, 0 when it takes the FP32 SIMT kernel (thin-K first layers, groups). */
+BCNN_B200_API int bcnn_b200_conv_uses_tensor_cores(const bcnn_b200_conv_desc *d, int pass);
 /* Bytes of device workspace the three conv entry points may use for `d`. */
 BCNN_B200_API size_t bcnn_b200_conv_workspace_bytes(const bcnn_b200_conv_desc *d,
                                                     int math);

@@ -8,7 +8,7 @@ import numpy as np
 import pytest
 
 from bcnn_b200 import capi
-from helpers import FP32_TOL, TC_TOL, assert_close, check, dev, dev_zeros, f32, oracle, p
+from helpers import FP32_TOL, TC_TOL, assert_close, check, dev, dev_zeros, f32, oracle, p, rel_err
 
 pytestmark = pytest.mark.gpu
 ACT = capi.ACT
@@ -295,7 +295,11 @@ def test_conv_fprop_dgrad_wgrad(case, math, tol):
     dxv, dwt, dyo = dev(x), dev(wt), dev_zeros(y_ref.size)
     # raw forward
     check(lib.bcnn_b200_conv_forward(d, dxv.ptr, dwt.ptr, None, 0, dyo.ptr, ws.ptr, ws_bytes, math, None))
-    assert_close(dyo.download(np.float32, y_ref.shape), y_ref, tol, "fprop")
+    y_gpu = dyo.download(np.float32, y_ref.shape)
+    assert_close(y_gpu, y_ref, tol, "fprop")
+    if math == capi.MATH_TC and lib.bcnn_b200_conv_uses_tensor_cores(d, 0):
+        # the tensor-core path really ran: BF16 operands leave a ~1e-3 signature
+        assert rel_err(y_gpu, y_ref)[1] > 1e-5, "TC path produced FP32-exact results?"
     # fused bias + relu epilogue
     yb = y_ref.copy()
     orc.orc_add_bias(p(yb), p(bias), d.batch, d.cout, d.ho * d.wo)

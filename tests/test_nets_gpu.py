@@ -23,7 +23,10 @@ from helpers import GOLDEN, assert_close, ref_available, ref_net, rel_err
 pytestmark = pytest.mark.gpu
 
 
-def _compare(out, golden, tol_s0, tol_final, what):
+def _compare(out, golden, tol_s0, tol_final, what, noise=None):
+    """noise: expected relative operand perturbation of the path under test (BF16 rounding
+    for the tensor-core path); the per-tensor tolerance then scales with the case's measured
+    amplification (reference response / 2e-7 input perturbation)."""
     worst = (0.0, "")
     checked = 0
     for key in golden:
@@ -47,7 +50,8 @@ def _compare(out, golden, tol_s0, tol_final, what):
             assert np.abs(got).max(initial=0.0) <= 1e-6, f"{what}: {base} should be zero"
             continue
         # floor, or 8x the reference's own response to a 1-ulp input perturbation
-        tol = max(tol, 8.0 * float(golden.get("sens:" + base, 0.0)))
+        sens = float(golden.get("sens:" + base, 0.0))
+        tol = max(tol, 8.0 * sens if noise is None else (sens / 2e-7) * noise)
         e = max(rel_err(got, want))
         if e / tol > worst[0]:
             worst = (e / tol, f"{base} (err {e:.2e}, tol {tol:.2e})")
@@ -65,7 +69,7 @@ def test_net_matches_golden_fp32(name):
     _compare(out, golden, 2e-5, 1e-4, f"{name} fp32 vs golden")
 
 
-@pytest.mark.parametrize("name", ["cifar_b4", "chain_b4"])
+@pytest.mark.parametrize("name", ["chain_b4", "resnet_small_b4"])
 def test_net_matches_golden_tensor_core(name):
     golden = dict(np.load(GOLDEN / f"{name}.npz"))
     net = capi.Net()
@@ -73,7 +77,8 @@ def test_net_matches_golden_tensor_core(name):
     out = netcases.run_case(net, name)
     net.close()
     golden = {k: v for k, v in golden.items() if "/argmax/" not in k}
-    _compare(out, golden, 2e-2, 5e-2, f"{name} tc vs golden")
+    # BF16 operands: ~2^-9 per element, ~1e-3 effective after the dot products average it
+    _compare(out, golden, 2e-2, 5e-2, f"{name} tc vs golden", noise=1e-3)
 
 
 @pytest.mark.skipif(not ref_available(), reason="oracle/_ref was not built / did not travel")
