@@ -8,9 +8,9 @@ using namespace b200;
 
 extern "C" int bcnn_b200_conv_uses_tensor_cores(const bcnn_b200_conv_desc *d, int pass) {
     switch (pass) {
-        case 0: return conv_tc_supports_fprop(d) ? 1 : 0;
-        case 1: return conv_tc_supports_dgrad(d) ? 1 : 0;
-        case 2: return conv_tc_supports_wgrad(d) ? 1 : 0;
+        case 0: return (conv_tma_supports_fprop(d) || conv_tc_supports_fprop(d)) ? 1 : 0;
+        case 1: return (conv_tma_supports_dgrad(d) || conv_tc_supports_dgrad(d)) ? 1 : 0;
+        case 2: return (conv_tma_supports_wgrad(d) || conv_tc_supports_wgrad(d)) ? 1 : 0;
     }
     return 0;
 }
@@ -18,7 +18,9 @@ extern "C" int bcnn_b200_conv_uses_tensor_cores(const bcnn_b200_conv_desc *d, in
 extern "C" size_t bcnn_b200_conv_workspace_bytes(const bcnn_b200_conv_desc *d, int math) {
     size_t a = conv_simt_workspace_bytes(d);
     size_t b = (math == BCNN_B200_MATH_TC) ? conv_tc_workspace_bytes(d) : 0;
-    return a > b ? a : b;
+    size_t c = (math == BCNN_B200_MATH_TC) ? conv_tma_workspace_bytes(d) : 0;
+    if (b > a) a = b;
+    return a > c ? a : c;
 }
 
 extern "C" int bcnn_b200_conv_forward(const bcnn_b200_conv_desc *d, const float *x,
@@ -26,6 +28,8 @@ extern "C" int bcnn_b200_conv_forward(const bcnn_b200_conv_desc *d, const float 
                                       void *workspace, size_t workspace_bytes, int math,
                                       void *stream) {
     cudaStream_t st = as_stream(stream);
+    if (math == BCNN_B200_MATH_TC && conv_tma_supports_fprop(d))
+        return conv_tma_forward(d, x, w, bias, act, y, workspace, workspace_bytes, st);
     if (math == BCNN_B200_MATH_TC && conv_tc_supports_fprop(d))
         return conv_tc_forward(d, x, w, bias, act, y, workspace, workspace_bytes, st);
     return conv_simt_forward(d, x, w, bias, act, y, st);
@@ -36,6 +40,8 @@ extern "C" int bcnn_b200_conv_backward_data(const bcnn_b200_conv_desc *d, const 
                                             void *workspace, size_t workspace_bytes, int math,
                                             void *stream) {
     cudaStream_t st = as_stream(stream);
+    if (math == BCNN_B200_MATH_TC && conv_tma_supports_dgrad(d))
+        return conv_tma_backward_data(d, w, dy, dx, accumulate, workspace, workspace_bytes, st);
     if (math == BCNN_B200_MATH_TC && conv_tc_supports_dgrad(d))
         return conv_tc_backward_data(d, w, dy, dx, accumulate, workspace, workspace_bytes, st);
     return conv_simt_backward_data(d, w, dy, dx, accumulate, st);
@@ -45,6 +51,8 @@ extern "C" int bcnn_b200_conv_backward_weights(const bcnn_b200_conv_desc *d, con
                                                const float *dy, float *gw, void *workspace,
                                                size_t workspace_bytes, int math, void *stream) {
     cudaStream_t st = as_stream(stream);
+    if (math == BCNN_B200_MATH_TC && conv_tma_supports_wgrad(d))
+        return conv_tma_backward_weights(d, x, dy, gw, workspace, workspace_bytes, st);
     if (math == BCNN_B200_MATH_TC && conv_tc_supports_wgrad(d))
         return conv_tc_backward_weights(d, x, dy, gw, workspace, workspace_bytes, st);
     return conv_simt_backward_weights(d, x, dy, gw, workspace, workspace_bytes, st);

@@ -264,6 +264,14 @@ CONV_CASES = [
     (2, 8, 9, 11, 12, 3, 1, 0, 2),     # groups = 2, pad 0, ragged
     (1, 5, 7, 7, 3, 5, 1, 2, 1),       # 5x5
     (5, 20, 1, 1, 33, 1, 1, 0, 1),     # FC-shaped
+    # TMA-addressable shapes (row pitch % 16 B == 0, stride 1): TF32 tcgen05 + TMA path
+    (2, 64, 56, 56, 64, 3, 1, 1, 1),   # resnet stage-1 3x3 (2 column chunks x 2 rows per tile)
+    (2, 256, 28, 28, 128, 1, 1, 0, 1), # resnet 1x1 reduce (flat plane view, ragged last tile)
+    (3, 48, 32, 32, 40, 3, 1, 1, 1),   # Cin, Cout not multiples of the 32-wide k-block / 16
+    (1, 16, 8, 8, 16, 5, 1, 2, 1),     # 5x5 pad 2 on an 8-wide plane (box wider than the row)
+    (2, 24, 12, 12, 24, 3, 1, 0, 1),   # pad 0: fprop / wgrad on TMA, dgrad (10-wide dY) gathered
+    (1, 32, 104, 104, 64, 3, 1, 1, 1), # yolo-tiny conv2 class: 4 column chunks per tile
+    (2, 160, 8, 8, 300, 1, 1, 0, 1),   # Cout > 128: several N tiles
 ]
 
 
