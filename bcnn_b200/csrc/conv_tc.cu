@@ -259,6 +259,15 @@ conv_tc_kernel(const TcParams p) {
             uint32_t r[32];
             tmem_ld32(tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(ck * 32), r);
             if (!e_valid) continue;
+            float old[32];
+            if (MODE == TC_DGRAD && p.accumulate) {  // issue every RMW load before the stores
+#pragma unroll
+                for (int j = 0; j < 32; ++j) {
+                    const int ch = tile_n * n_tile + ck * 32 + j;
+                    old[j] = (ck * 32 + j < n_tile && ch < p.dst_c)
+                                 ? __ldcs(dst_img + (size_t)ch * dst_plane) : 0.f;
+                }
+            }
 #pragma unroll
             for (int j = 0; j < 32; ++j) {
                 const int ch = tile_n * n_tile + ck * 32 + j;
@@ -270,7 +279,7 @@ conv_tc_kernel(const TcParams p) {
                         val = act_fwd(val, p.act, 0.f);
                         *d = val;
                     } else {
-                        *d = p.accumulate ? (*d + val) : val;
+                        *d = p.accumulate ? (old[j] + val) : val;
                     }
                 }
             }

@@ -202,6 +202,12 @@ __device__ __forceinline__ TileCoord decode_tile(const FwdParams &p, int tile) {
 template <int ACT, bool HAS_BIAS, bool ACCUM, bool FULL>
 __device__ __forceinline__ void store_chunk(const uint32_t (&v)[32], float *d, uint32_t plane,
                                             const float *bias, int nvalid) {
+    float old[ACCUM ? 32 : 1];
+    if (ACCUM) {  // all 32 read-modify-write loads go out before the first dependent store
+#pragma unroll
+        for (int j = 0; j < 32; ++j)
+            old[j] = (FULL || j < nvalid) ? __ldcs(d + (size_t)((uint32_t)j * plane)) : 0.f;
+    }
 #pragma unroll
     for (int j = 0; j < 32; ++j) {
         if (FULL || j < nvalid) {
@@ -209,9 +215,8 @@ __device__ __forceinline__ void store_chunk(const uint32_t (&v)[32], float *d, u
             if (HAS_BIAS) val += __ldg(bias + j);
             if (ACT == ACT_RELU) val = fmaxf(val, 0.f);
             else if (ACT == ACT_LRELU) val = val > 0 ? val : 0.1f * val;
-            float *q = d + (size_t)((uint32_t)j * plane);
-            if (ACCUM) val += *q;
-            *q = val;
+            if (ACCUM) val += old[j];
+            d[(size_t)((uint32_t)j * plane)] = val;
         }
     }
 }

@@ -157,7 +157,9 @@ def test_valid_and_predict_modes_follow_reference_semantics():
         orc.orc_conv_forward(p(x), p(f32(prm["input_w"])), p(raw), 2, 3, 12, 12, 8, 3, 1, 1, 1)
         rm, rv = f32(prm["input_run_mean"]).ravel().copy(), f32(prm["input_run_var"]).ravel().copy()
         sm, sv = np.zeros(8, np.float32), np.zeros(8, np.float32)
-        orc.orc_bn_forward(p(raw), 2, 8, 144, p(rm), p(rv), p(f32(prm["input_scales"]).ravel().copy()),
-                           p(f32(prm["input_b"]).ravel().copy()), p(sm), p(sv), None, None, mode)
+        # keep the arrays alive across the call: p() hands out a raw pointer
+        gamma, beta = f32(prm["input_scales"]).ravel().copy(), f32(prm["input_b"]).ravel().copy()
+        orc.orc_bn_forward(p(raw), 2, 8, 144, p(rm), p(rv), p(gamma), p(beta), p(sm), p(sv), None,
+                           None, mode)
         orc.orc_activation_forward(p(raw), raw.size, None, 144, 8, capi.ACT["relu"])
         assert_close(y, raw, 2e-5, f"mode {mode}")
