@@ -1,31 +1,35 @@
-// conv_tma.cu -- TF32 implicit-GEMM convolution on tcgen05 tensor cores, operands staged by
-// the TMA straight from the FP32 NCHW tensors (sm_100a).
+// conv_tma.cu -- TF32 implicit-GEMM convolution on tcgen05 tensor cores with every operand
+// staged by the TMA (sm_100a). Accumulation is FP32 in TMEM; kind::tf32 consumes FP32 bits as
+// they are, so no precision-conversion pass exists anywhere.
 //
-// No im2col matrix, no layout change and no precision-conversion pass exists anywhere: a
-// 4-D tensor map over the NCHW activation (dims w, h, c, n) lets one TMA box fetch
-// "32 consecutive output columns x 32 channels" of one filter tap -- shifted by (kh - pad,
-// kw - pad), zero-filled outside the image by the TMA's out-of-bounds rule -- into
-// 128-byte-swizzled shared memory, which is exactly a tcgen05 *MN-major* TF32 operand atom
-// (positions contiguous, channels strided). kind::tf32 consumes the FP32 bits as they are.
+// Two ways to let the TMA see an activation tensor (bcnn tensors are FP32 NCHW):
 //
-//   fprop / stride-1 dgrad  (conv_tma_fwd_kernel):
-//       D[128 positions x N channels] += A[128 x 32ch] (MN-major, TMA) * B[N x 32ch]^T
-//       (K-major packed weights, one bulk copy per k-block); K order: tap-major, channel-minor.
-//       A tile = 4 atoms of 32 positions: 4 column chunks of one output row, 2 x 2, or 1 x 4 rows
-//       (1x1 convolutions see the image plane as one long row, so tiles are dense).
-//       dgrad with stride 1 is the same kernel on dY with flipped taps and pad' = k-1-pad.
-//   wgrad  (conv_tma_wgrad_kernel):
-//       D[128 co x N ci] += dY[128 co x 32 pos] * X_shift[N ci x 32 pos]^T, both operands
-//       K-major (positions contiguous in NCHW) and both fetched by TMA; split-K over
-//       (image, row, column chunk) across CTAs, deterministic second-stage reduction.
+//  (1) DIRECT (1x1, stride 1, pad 0, H*W % 4 == 0): a 4-D map (w, h, c, n) over the NCHW tensor
+//      itself, the image plane seen as one long row. A box "32 positions x 32 channels" lands
+//      in shared memory as a tcgen05 *MN-major* TF32 atom (positions contiguous, channels
+//      strided; SWIZZLE_128B_ATOM_32B, the only MN-major layout 32-bit operands accept).
+//  (2) NHWC SHADOW (k > 1, stride 2, odd widths): the inner TMA coordinate must be a multiple of
+//      16 bytes, so a filter tap cannot shift an NCHW row by one pixel. The tensor is therefore
+//      transposed once into an NHWC copy in the workspace (one HBM-bound pass); over it the
+//      4-D map (c, w, h, n) lets a single box fetch "32 channels x TW x TH x TN positions" of
+//      one tap at any (kh - pad, kw - pad) shift and any stride (TMA element strides), zero-
+//      filled outside the image by the TMA's out-of-bounds rule: a K-major SWIZZLE_128B tile.
 //
-// Warp roles (192 threads): warp 0 = TMA producer (one lane), warp 1 = TMEM allocator + MMA
-// issuer (one lane), warps 2-5 = epilogue (tcgen05.ld -> bias/activation -> coalesced NCHW
-// stores). smem ring of 2-4 stages with full/empty mbarriers; two CTAs fit per SM so one
-// CTA's epilogue overlaps the other's main loop.
+//   conv_tma_fwd_kernel   fprop and stride-1 dgrad (same kernel on dY with flipped taps and
+//       pad' = k-1-pad): D[128 positions x N channels] += A[128 x 32ch] * B[N x 32ch]^T,
+//       B = K-major packed weights (one bulk copy per k-block); K order tap-major, channel-
+//       minor. Persistent CTAs (one per SM) walk the tile list; the TMA producer runs ahead
+//       across tiles; two TMEM accumulators overlap the epilogue of tile i with the MMAs of
+//       tile i+1. Warp roles: warp 0 TMA producer, warp 1 MMA issuer + TMEM allocator, warps
+//       2-9 epilogue (tcgen05.ld -> bias/activation -> coalesced NCHW stores).
+//   conv_tma_wgrad_kernel  dW[co, ci, tap] = sum_pos dY[co, pos] * X[ci, pos (+) tap]:
+//       D[128 co x N ci], reduction over positions. DIRECT: both operands K-major rows of 32
+//       positions. NHWC: both operands MN-major (channels contiguous), K-block = bw x bh
+//       positions of one tap-shifted window. Split-K across CTAs, deterministic second-stage
+//       reduction in split order.
 //
-// Shapes the TMA cannot address (row pitch not a multiple of 16 bytes, stride > 1, groups)
-// stay on the register-gather tcgen05 kernels of conv_tc.cu / conv_tc_wgrad.cu.
+// Shapes outside both (groups, C % 4 != 0, thin first layers, stride-2 dgrad) stay on the
+// register-gather tcgen05 kernels of conv_tc.cu / conv_tc_wgrad.cu or the FP32 SIMT kernels.
 #include <cuda.h>
 #include <stdlib.h>
 
@@ -43,7 +47,7 @@ constexpr int BLOCK_K = 32;                 // fp32 elements per k-block = one 1
 constexpr int UMMA_K = 8;                   // kind::tf32
 constexpr int ATOM_BYTES = 32 * BLOCK_K * 4;   // 4 KiB: 32 positions x 32 channels
 constexpr int A_STAGE_BYTES = TILE_M * BLOCK_K * 4;  // 16 KiB
-constexpr int NTHREADS = 192;
+constexpr int WG_THREADS = 192;
 
 // ------------------------------------------------------------------ PTX helpers (TF32 / TMA)
 __device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b,
@@ -79,10 +83,10 @@ __device__ __forceinline__ uint64_t make_desc_mn_sw128(uint32_t smem_addr, uint3
     d |= (uint64_t)1 << 61;
     return d;
 }
-// D = F32, A = B = TF32; a_mn != 0 marks A as MN-major (bit 15); B is K-major.
-__device__ __forceinline__ uint32_t make_idesc_tf32(int m, int n, int a_mn) {
+// D = F32, A = B = TF32; a_mn / b_mn mark an MN-major operand (bits 15 / 16).
+__device__ __forceinline__ uint32_t make_idesc_tf32(int m, int n, int a_mn, int b_mn) {
     return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(a_mn ? 1 : 0) << 15) |
-           ((uint32_t)(n >> 3) << 17) | ((uint32_t)(m >> 4) << 24);
+           ((uint32_t)(b_mn ? 1 : 0) << 16) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(m >> 4) << 24);
 }
 
 // ------------------------------------------------------------------ tensor maps (host)
@@ -109,8 +113,8 @@ EncodeTiledFn encode_fn() {
 
 // Map over an NCHW fp32 tensor seen as (w, h, c, n); box = 32 columns x 1 row x box_c channels.
 // Out-of-bounds elements (negative or past-the-end coordinates) read as zero.
-bool make_map(CUtensorMap *map, const float *base, int w, int h, int c, int n, int box_c,
-              bool mn_major) {
+bool make_map_nchw(CUtensorMap *map, const float *base, int w, int h, int c, int n, int box_c,
+                   bool mn_major) {
     EncodeTiledFn fn = encode_fn();
     if (!fn) return false;
     cuuint64_t dims[4] = {(cuuint64_t)w, (cuuint64_t)h, (cuuint64_t)c, (cuuint64_t)n};
@@ -122,6 +126,53 @@ bool make_map(CUtensorMap *map, const float *base, int w, int h, int c, int n, i
                     mn_major ? CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B : CU_TENSOR_MAP_SWIZZLE_128B,
                     CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     return r == CUDA_SUCCESS;
+}
+
+// Map over an NHWC fp32 shadow seen as (c, w, h, n); box = 32 channels x bw x bh x bn positions,
+// walking w and h with the convolution stride.
+bool make_map_nhwc(CUtensorMap *map, const float *base, int c, int w, int h, int n, int bw, int bh,
+                   int bn, int stride, bool mn_major) {
+    EncodeTiledFn fn = encode_fn();
+    if (!fn) return false;
+    cuuint64_t dims[4] = {(cuuint64_t)c, (cuuint64_t)w, (cuuint64_t)h, (cuuint64_t)n};
+    cuuint64_t strides[3] = {(cuuint64_t)c * 4, (cuuint64_t)w * c * 4, (cuuint64_t)w * h * c * 4};
+    cuuint32_t box[4] = {32, (cuuint32_t)(bw * stride), (cuuint32_t)(bh * stride), (cuuint32_t)bn};
+    cuuint32_t estr[4] = {1, (cuuint32_t)stride, (cuuint32_t)stride, 1};
+    CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, const_cast<float *>(base), dims, strides,
+                    box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                    mn_major ? CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B : CU_TENSOR_MAP_SWIZZLE_128B,
+                    CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    return r == CUDA_SUCCESS;
+}
+
+// ------------------------------------------------------------------ NCHW -> NHWC shadow
+// out[n][p][c] = in[n][c][p]; 32 x 32 tiles through padded shared memory, 128-byte coalesced on
+// both sides.
+__global__ void __launch_bounds__(256)
+nchw_to_nhwc_kernel(const float *__restrict__ in, float *__restrict__ out, int C, int P) {
+    __shared__ float tile[32][33];
+    const int n = blockIdx.z;
+    const int p0 = blockIdx.x * 32, c0 = blockIdx.y * 32;
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+    const float *src = in + (size_t)n * C * P;
+    float *dst = out + (size_t)n * C * P;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const int c = c0 + ty + 8 * i, p = p0 + tx;
+        tile[ty + 8 * i][tx] = (c < C && p < P) ? __ldg(src + (size_t)c * P + p) : 0.f;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const int p = p0 + ty + 8 * i, c = c0 + tx;
+        if (p < P && c < C) dst[(size_t)p * C + c] = tile[tx][ty + 8 * i];
+    }
+}
+
+int launch_transpose(const float *in, float *out, int n, int c, int p, cudaStream_t st) {
+    dim3 grid(ceil_div(p, 32), ceil_div(c, 32), n);
+    nchw_to_nhwc_kernel<<<grid, 256, 0, st>>>(in, out, c, p);
+    return launched();
 }
 
 // ------------------------------------------------------------------ weight repack (TF32 = fp32 bits)
@@ -170,15 +221,18 @@ struct FwdParams {
     const float *bias;
     const float *wpack;
     int act, accumulate;
-    int src_c, dst_c;
-    int out_w, out_h;     // output plane as the kernel sees it (1x1: (H*W, 1))
-    int ks, pad;
+    int src_c, dst_c, batch;
+    int out_w, out_h;     // output plane as the kernel sees it (DIRECT: (H*W, 1))
+    int ks, pad, stride;
     int kc_blocks, k_blocks, n_tile, n_tiles, stages;
-    int wc, rows;         // tile = wc column chunks of 32 x rows output rows, wc * rows == 4
-    int tiles_w;          // tiles per output row band
-    int tiles_img;        // position tiles per image
-    int total_tiles;      // n_tiles * tiles_img * batch
-    FastDiv d_ntiles, d_tiles_img, d_tiles_w;
+    // DIRECT: tile = wc column chunks of 32 x rows output rows (wc * rows == 4), one image
+    int wc, rows;
+    // NHWC: tile = tw x th x tn output positions (<= 128), row m = w + tw * (h + th * n)
+    int tw, th, tn;
+    uint32_t a_bytes;     // TMA bytes of the activation operand per stage
+    int tiles_w, tiles_h, tiles_b;   // tiles along w, h and the batch
+    int total_tiles;      // n_tiles * tiles_w * tiles_h * tiles_b
+    FastDiv d_ntiles, d_tiles_w, d_tiles_h, d_tw, d_th;
 };
 
 constexpr int FWD_EPI_WARPS = 8;
@@ -186,14 +240,19 @@ constexpr int FWD_THREADS = 64 + 32 * FWD_EPI_WARPS;
 
 struct TileCoord { int tile_n, img, w0, h0; };
 
+template <bool NHWC>
 __device__ __forceinline__ TileCoord decode_tile(const FwdParams &p, int tile) {
-    uint32_t rest, tn, img, pt, th, tw;
+    uint32_t rest, tn, rest2, tw, tb, th;
     p.d_ntiles.divmod((uint32_t)tile, rest, tn);
-    p.d_tiles_img.divmod(rest, img, pt);
-    p.d_tiles_w.divmod(pt, th, tw);
+    p.d_tiles_w.divmod(rest, rest2, tw);
+    p.d_tiles_h.divmod(rest2, tb, th);
     TileCoord c;
-    c.tile_n = (int)tn; c.img = (int)img;
-    c.w0 = (int)tw * p.wc * 32; c.h0 = (int)th * p.rows;
+    c.tile_n = (int)tn;
+    if (NHWC) {
+        c.img = (int)tb * p.tn; c.w0 = (int)tw * p.tw; c.h0 = (int)th * p.th;
+    } else {
+        c.img = (int)tb; c.w0 = (int)tw * p.wc * 32; c.h0 = (int)th * p.rows;
+    }
     return c;
 }
 
@@ -231,6 +290,7 @@ __device__ __forceinline__ void store_chunk_any(const uint32_t (&v)[32], float *
 // CTAs working at the same time share an activation tile through L2). The TMA producer runs
 // ahead across tile boundaries; two TMEM accumulators let the epilogue of tile i overlap the
 // MMAs of tile i+1.
+template <bool NHWC>
 __global__ void __launch_bounds__(FWD_THREADS, 1)
 conv_tma_fwd_kernel(const __grid_constant__ CUtensorMap tm_src, const FwdParams p) {
     extern __shared__ __align__(1024) uint8_t smem_raw[];
@@ -267,8 +327,9 @@ conv_tma_fwd_kernel(const __grid_constant__ CUtensorMap tm_src, const FwdParams 
         if (lane == 0) {
             // ---------------- TMA producer
             uint32_t it = 0;
+            const uint32_t tx_bytes = p.a_bytes + (uint32_t)b_stage_bytes;
             for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
-                const TileCoord c = decode_tile(p, tile);
+                const TileCoord c = decode_tile<NHWC>(p, tile);
                 const float *wtile = p.wpack + (size_t)c.tile_n * p.k_blocks * n_tile * BLOCK_K;
                 int kb = 0;
                 for (int kh = 0; kh < p.ks; ++kh) {
@@ -278,12 +339,18 @@ conv_tma_fwd_kernel(const __grid_constant__ CUtensorMap tm_src, const FwdParams 
                             mbar_wait(smem_u32(empty + s), ((it / (uint32_t)S) & 1) ^ 1);
                             const uint32_t fb = smem_u32(full + s);
                             uint8_t *a_stage = smem + (size_t)s * stage_bytes;
-                            mbar_expect_tx(fb, (uint32_t)stage_bytes);
-                            for (int a = 0; a < 4; ++a) {  // atom a = (column chunk, row) of the tile
-                                const int wci = a / p.rows, r = a - wci * p.rows;
-                                tma_load_4d(smem_u32(a_stage + a * ATOM_BYTES), &tm_src,
-                                            c.w0 + wci * 32 + kw - p.pad, c.h0 + r + kh - p.pad,
-                                            cb * BLOCK_K, c.img, fb);
+                            mbar_expect_tx(fb, tx_bytes);
+                            if (NHWC) {
+                                tma_load_4d(smem_u32(a_stage), &tm_src, cb * BLOCK_K,
+                                            c.w0 * p.stride + kw - p.pad, c.h0 * p.stride + kh - p.pad,
+                                            c.img, fb);
+                            } else {
+                                for (int a = 0; a < 4; ++a) {  // atom a = (column chunk, row) of the tile
+                                    const int wci = a / p.rows, r = a - wci * p.rows;
+                                    tma_load_4d(smem_u32(a_stage + a * ATOM_BYTES), &tm_src,
+                                                c.w0 + wci * 32 + kw - p.pad, c.h0 + r + kh - p.pad,
+                                                cb * BLOCK_K, c.img, fb);
+                                }
                             }
                             bulk_copy_g2s(smem_u32(a_stage + A_STAGE_BYTES),
                                           wtile + (size_t)kb * n_tile * BLOCK_K, (uint32_t)b_stage_bytes, fb);
@@ -295,7 +362,7 @@ conv_tma_fwd_kernel(const __grid_constant__ CUtensorMap tm_src, const FwdParams 
     } else if (warp == 1) {
         if (lane == 0) {
             // ---------------- MMA issuer
-            const uint32_t idesc = make_idesc_tf32(TILE_M, n_tile, 1);
+            const uint32_t idesc = make_idesc_tf32(TILE_M, n_tile, NHWC ? 0 : 1, 0);
             uint32_t it = 0, local = 0;
             for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++local) {
                 const uint32_t buf = local & 1, use = local >> 1;
@@ -310,9 +377,10 @@ conv_tma_fwd_kernel(const __grid_constant__ CUtensorMap tm_src, const FwdParams 
                     const uint32_t b_addr = a_addr + A_STAGE_BYTES;
 #pragma unroll
                     for (int g = 0; g < BLOCK_K / UMMA_K; ++g) {
-                        // A: K-group g = 8 channel rows = 1 KiB further inside every 4 KiB atom
-                        const uint64_t da = make_desc_mn_sw128(a_addr + g * 1024, ATOM_BYTES, 512);
-                        // B: 8 fp32 = 32 bytes further along the 128-byte K row
+                        // DIRECT A: K-group g = 8 channel rows = 1 KiB further inside every 4 KiB atom
+                        // NHWC A / B: 8 fp32 = 32 bytes further along the 128-byte K row
+                        const uint64_t da = NHWC ? make_desc_sw128(a_addr) + (uint64_t)(2 * g)
+                                                 : make_desc_mn_sw128(a_addr + g * 1024, ATOM_BYTES, 512);
                         const uint64_t db = make_desc_sw128(b_addr) + (uint64_t)(2 * g);
                         umma_tf32(d_tmem, da, db, idesc, (kb > 0 || g > 0) ? 1u : 0u);
                     }
@@ -322,21 +390,32 @@ conv_tma_fwd_kernel(const __grid_constant__ CUtensorMap tm_src, const FwdParams 
             }
         }
     } else {
-        // ---------------- epilogue warps: TMEM lane quarter = warp & 3 = one atom of 32 positions;
-        // the two warps sharing a quarter split the 32-column chunks between them
+        // ---------------- epilogue warps: TMEM lane quarter = warp & 3 (32 tile rows); the two
+        // warps sharing a quarter split the 32-column chunks between them
         const int ew = warp - 2;
         const int q = warp & 3;
         const int half = ew >> 2;
-        const int wci = q / p.rows, r = q - wci * p.rows;
         const uint32_t plane = (uint32_t)(p.out_w * p.out_h);
         const int chunks32 = (n_tile + 31) / 32;
+        // position of this thread's tile row relative to the tile origin
+        int rw, rh, rn;
+        if (NHWC) {
+            uint32_t m = (uint32_t)(q * 32 + lane), t2, w_, n_, h_;
+            p.d_tw.divmod(m, t2, w_);
+            p.d_th.divmod(t2, n_, h_);
+            rw = (int)w_; rh = (int)h_; rn = (int)n_;
+        } else {
+            const int wci = q / p.rows;
+            rw = wci * 32 + lane; rh = q - wci * p.rows; rn = 0;
+        }
         uint32_t local = 0;
         for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++local) {
-            const TileCoord c = decode_tile(p, tile);
+            const TileCoord c = decode_tile<NHWC>(p, tile);
             const uint32_t buf = local & 1, use = local >> 1;
-            const int ow = c.w0 + wci * 32 + lane, oh = c.h0 + r;
-            const bool valid = ow < p.out_w && oh < p.out_h;
-            float *dst = p.dst + (size_t)c.img * p.dst_c * plane + (size_t)oh * p.out_w + ow;
+            const int ow = c.w0 + rw, oh = c.h0 + rh, img = c.img + rn;
+            bool valid = ow < p.out_w && oh < p.out_h && img < p.batch;
+            if (NHWC) valid = valid && rn < p.tn;
+            float *dst = p.dst + (size_t)img * p.dst_c * plane + (size_t)oh * p.out_w + ow;
             if (lane == 0) mbar_wait(smem_u32(acc_full + buf), use & 1);
             __syncwarp();
             tc_fence_after();
@@ -382,11 +461,14 @@ conv_tma_fwd_kernel(const __grid_constant__ CUtensorMap tm_src, const FwdParams 
 }
 
 struct FwdPlan {
+    bool nhwc;
     int n_tile, n_tiles, kc_blocks, k_blocks, stages;
-    int view_w, view_h;      // source plane as the TMA sees it
+    int view_w, view_h;      // DIRECT: source plane as the TMA sees it
     int out_w, out_h;
-    int wc, rows, tiles_w, tiles_h;
-    size_t wpack_bytes, smem_bytes;
+    int wc, rows, tw, th, tn;
+    int tiles_w, tiles_h, tiles_b;
+    uint32_t a_bytes;
+    size_t shadow_bytes, wpack_bytes, smem_bytes;
 };
 
 bool tma_disabled() {
@@ -397,16 +479,25 @@ bool tma_disabled() {
     }
     return v == 1;
 }
+bool nhwc_disabled() {
+    static int v = -1;
+    if (v < 0) {
+        const char *e = getenv("BCNN_B200_NO_NHWC");
+        v = (e && e[0] && e[0] != '0') ? 1 : 0;
+    }
+    return v == 1;
+}
+
+size_t align256(size_t b) { return (b + 255) & ~(size_t)255; }
 
 // Geometry shared by fprop (src = x) and stride-1 dgrad (src = dy): src plane (sh, sw) with
 // src_c channels -> dst plane (dh, dw) with dst_c channels.
-bool plan_fwd(int src_c, int sh, int sw, int dst_c, int dh, int dw, int ks, FwdPlan *pl) {
-    const bool flat = (ks == 1);  // pad 0, stride 1: positions are one long contiguous row
-    pl->view_w = flat ? sh * sw : sw;
-    pl->view_h = flat ? 1 : sh;
-    pl->out_w = flat ? dh * dw : dw;
-    pl->out_h = flat ? 1 : dh;
-    if (pl->view_w % 4 != 0) return false;  // TMA: row pitch must be a multiple of 16 bytes
+bool plan_fwd(int batch, int src_c, int sh, int sw, int dst_c, int dh, int dw, int ks, int stride,
+              int pad, FwdPlan *pl) {
+    if (src_c < 16) return false;  // K too thin (first layers): SIMT kernel
+    const bool direct = ks == 1 && stride == 1 && pad == 0 && (sh * sw) % 4 == 0;
+    pl->nhwc = !direct;
+    if (!direct && (nhwc_disabled() || src_c % 4 != 0 || stride > 4)) return false;
     static int nmax = 0;
     if (!nmax) {
         const char *e = getenv("BCNN_B200_FWD_NMAX");
@@ -424,43 +515,92 @@ bool plan_fwd(int src_c, int sh, int sw, int dst_c, int dh, int dw, int ks, FwdP
     pl->n_tiles = ceil_div(dst_c, n);
     pl->kc_blocks = ceil_div(src_c, BLOCK_K);
     pl->k_blocks = ks * ks * pl->kc_blocks;
-    const int chunks = ceil_div(pl->out_w, 32);
-    pl->wc = chunks >= 4 ? 4 : (chunks >= 2 ? 2 : 1);
-    pl->rows = 4 / pl->wc;
-    pl->tiles_w = ceil_div(chunks, pl->wc);
-    pl->tiles_h = ceil_div(pl->out_h, pl->rows);
+    pl->wc = pl->rows = 1; pl->tw = pl->th = pl->tn = 1;
+    if (direct) {
+        pl->view_w = sh * sw; pl->view_h = 1;
+        pl->out_w = dh * dw; pl->out_h = 1;
+        const int chunks = ceil_div(pl->out_w, 32);
+        pl->wc = chunks >= 4 ? 4 : (chunks >= 2 ? 2 : 1);
+        pl->rows = 4 / pl->wc;
+        pl->tiles_w = ceil_div(chunks, pl->wc);
+        pl->tiles_h = ceil_div(pl->out_h, pl->rows);
+        pl->tiles_b = batch;
+        pl->a_bytes = A_STAGE_BYTES;
+        pl->shadow_bytes = 0;
+    } else {
+        pl->view_w = sw; pl->view_h = sh;
+        pl->out_w = dw; pl->out_h = dh;
+        // tile = tw x th x tn output positions, <= 128 rows, TMA box dims <= 256
+        int tw = dw < 128 ? dw : 128;
+        while (tw * stride > 256) --tw;
+        const int tiles_w = ceil_div(dw, tw);
+        tw = ceil_div(dw, tiles_w);  // balanced
+        int th_max = 128 / tw;
+        if (th_max < 1) th_max = 1;
+        while (th_max * stride > 256) --th_max;
+        int th = dh < th_max ? dh : th_max;
+        const int tiles_h = ceil_div(dh, th);
+        th = ceil_div(dh, tiles_h);
+        int tn = 1;
+        if (tiles_w == 1 && tiles_h == 1) {
+            tn = 128 / (tw * th);
+            if (tn > batch) tn = batch;
+            if (tn < 1) tn = 1;
+        }
+        pl->tw = tw; pl->th = th; pl->tn = tn;
+        pl->tiles_w = tiles_w; pl->tiles_h = tiles_h; pl->tiles_b = ceil_div(batch, tn);
+        pl->a_bytes = (uint32_t)(tw * th * tn * 128);
+        pl->shadow_bytes = align256((size_t)batch * src_c * sh * sw * sizeof(float));
+    }
     const int stage = A_STAGE_BYTES + n * BLOCK_K * 4;
     int stages = (200 * 1024) / stage;  // persistent: one CTA per SM owns the shared memory
     if (stages > 8) stages = 8;
     if (stages < 2) stages = 2;
     pl->stages = stages;
-    pl->wpack_bytes = (size_t)pl->n_tiles * pl->k_blocks * n * BLOCK_K * sizeof(float);
+    pl->wpack_bytes = align256((size_t)pl->n_tiles * pl->k_blocks * n * BLOCK_K * sizeof(float));
     pl->smem_bytes = (size_t)stages * stage + 1024 + 256;
-    return true;
+    const long long total = (long long)pl->n_tiles * pl->tiles_w * pl->tiles_h * pl->tiles_b;
+    return total < (1LL << 31);
 }
 
-bool fwd_shape_ok(const bcnn_b200_conv_desc *d, bool dgrad) {
+bool plan_fwd_desc(const bcnn_b200_conv_desc *d, bool dgrad, FwdPlan *pl) {
     if (tma_disabled() || !encode_fn()) return false;
-    if (d->groups != 1 || d->stride != 1) return false;
-    const int src_c = dgrad ? d->cout : d->cin;
-    if (src_c < 16) return false;  // K too thin (first layers): SIMT kernel
-    if (d->ksize != 1 || d->pad != 0) return false;  // taps shift the inner TMA coordinate by 4 B
-    FwdPlan pl;
-    if (dgrad) return plan_fwd(d->cout, d->ho, d->wo, d->cin, d->h, d->w, d->ksize, &pl);
-    return plan_fwd(d->cin, d->h, d->w, d->cout, d->ho, d->wo, d->ksize, &pl);
+    if (d->groups != 1) return false;
+    if (dgrad) {
+        if (d->stride != 1 || d->pad > d->ksize - 1) return false;
+        return plan_fwd(d->batch, d->cout, d->ho, d->wo, d->cin, d->h, d->w, d->ksize, 1,
+                        d->ksize - 1 - d->pad, pl);
+    }
+    return plan_fwd(d->batch, d->cin, d->h, d->w, d->cout, d->ho, d->wo, d->ksize, d->stride, d->pad, pl);
+}
+
+template <bool NHWC>
+int launch_fwd_kernel(const CUtensorMap &tm, const FwdParams &p, size_t smem, cudaStream_t st) {
+    static bool attr_set = false;
+    if (!attr_set) {
+        cudaError_t e = cudaFuncSetAttribute(conv_tma_fwd_kernel<NHWC>,
+                                             cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+        if (e != cudaSuccess) return (int)e;
+        attr_set = true;
+    }
+    const int grid = p.total_tiles < sm_count() ? p.total_tiles : sm_count();
+    conv_tma_fwd_kernel<NHWC><<<grid, FWD_THREADS, smem, st>>>(tm, p);
+    return launched();
 }
 
 int launch_fwd(const bcnn_b200_conv_desc *d, bool dgrad, const float *src, const float *w,
                const float *bias, int act, float *dst, int accumulate, void *workspace,
                size_t workspace_bytes, cudaStream_t st) {
     FwdPlan pl;
+    if (!plan_fwd_desc(d, dgrad, &pl)) return (int)cudaErrorInvalidValue;
     const int src_c = dgrad ? d->cout : d->cin, dst_c = dgrad ? d->cin : d->cout;
     const int sh = dgrad ? d->ho : d->h, sw = dgrad ? d->wo : d->w;
-    const int dh = dgrad ? d->h : d->ho, dw = dgrad ? d->w : d->wo;
-    if (!plan_fwd(src_c, sh, sw, dst_c, dh, dw, d->ksize, &pl)) return (int)cudaErrorInvalidValue;
-    if (workspace == nullptr || workspace_bytes < pl.wpack_bytes) return (int)cudaErrorInvalidValue;
-    if ((reinterpret_cast<uintptr_t>(src) & 15) != 0) return (int)cudaErrorMisalignedAddress;
-    float *wpack = reinterpret_cast<float *>(workspace);
+    if (workspace == nullptr || workspace_bytes < pl.shadow_bytes + pl.wpack_bytes)
+        return (int)cudaErrorInvalidValue;
+    if ((reinterpret_cast<uintptr_t>(src) & 15) != 0 || (reinterpret_cast<uintptr_t>(workspace) & 255) != 0)
+        return (int)cudaErrorMisalignedAddress;
+    float *shadow = reinterpret_cast<float *>(workspace);
+    float *wpack = reinterpret_cast<float *>(reinterpret_cast<uint8_t *>(workspace) + pl.shadow_bytes);
     const int kk = d->ksize * d->ksize;
     const size_t chunks = (size_t)pl.n_tiles * pl.n_tile * pl.k_blocks * 8;
     pack_weights_tf32_kernel<<<stream_grid(chunks, 256), 256, 0, st>>>(
@@ -469,57 +609,61 @@ int launch_fwd(const bcnn_b200_conv_desc *d, bool dgrad, const float *src, const
     if (err) return err;
 
     CUtensorMap tm;
-    if (!make_map(&tm, src, pl.view_w, pl.view_h, src_c, d->batch, BLOCK_K, true))
+    if (pl.nhwc) {
+        err = launch_transpose(src, shadow, d->batch, src_c, sh * sw, st);
+        if (err) return err;
+        if (!make_map_nhwc(&tm, shadow, src_c, sw, sh, d->batch, pl.tw, pl.th, pl.tn,
+                           dgrad ? 1 : d->stride, false))
+            return (int)cudaErrorInvalidValue;
+    } else if (!make_map_nchw(&tm, src, pl.view_w, pl.view_h, src_c, d->batch, BLOCK_K, true)) {
         return (int)cudaErrorInvalidValue;
+    }
     FwdParams p;
     p.dst = dst; p.bias = bias; p.wpack = wpack; p.act = act; p.accumulate = accumulate;
-    p.src_c = src_c; p.dst_c = dst_c;
+    p.src_c = src_c; p.dst_c = dst_c; p.batch = d->batch;
     p.out_w = pl.out_w; p.out_h = pl.out_h;
     p.ks = d->ksize; p.pad = dgrad ? d->ksize - 1 - d->pad : d->pad;
+    p.stride = dgrad ? 1 : d->stride;
     p.kc_blocks = pl.kc_blocks; p.k_blocks = pl.k_blocks; p.n_tile = pl.n_tile; p.stages = pl.stages;
     p.n_tiles = pl.n_tiles;
-    p.wc = pl.wc; p.rows = pl.rows; p.tiles_w = pl.tiles_w;
-    p.tiles_img = pl.tiles_w * pl.tiles_h;
-    const long long total = (long long)pl.n_tiles * p.tiles_img * d->batch;
-    if (total >= (1LL << 31)) return (int)cudaErrorInvalidValue;
-    p.total_tiles = (int)total;
+    p.wc = pl.wc; p.rows = pl.rows; p.tw = pl.tw; p.th = pl.th; p.tn = pl.tn;
+    p.a_bytes = pl.a_bytes;
+    p.tiles_w = pl.tiles_w; p.tiles_h = pl.tiles_h; p.tiles_b = pl.tiles_b;
+    p.total_tiles = pl.n_tiles * pl.tiles_w * pl.tiles_h * pl.tiles_b;
     p.d_ntiles = FastDiv((uint32_t)pl.n_tiles);
-    p.d_tiles_img = FastDiv((uint32_t)p.tiles_img);
     p.d_tiles_w = FastDiv((uint32_t)pl.tiles_w);
-
-    static bool attr_set = false;
-    if (!attr_set) {
-        cudaError_t e = cudaFuncSetAttribute(conv_tma_fwd_kernel,
-                                             cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
-        if (e != cudaSuccess) return (int)e;
-        attr_set = true;
-    }
-    const int grid = p.total_tiles < sm_count() ? p.total_tiles : sm_count();
-    conv_tma_fwd_kernel<<<grid, FWD_THREADS, pl.smem_bytes, st>>>(tm, p);
-    return launched();
+    p.d_tiles_h = FastDiv((uint32_t)pl.tiles_h);
+    p.d_tw = FastDiv((uint32_t)pl.tw);
+    p.d_th = FastDiv((uint32_t)pl.th);
+    return pl.nhwc ? launch_fwd_kernel<true>(tm, p, pl.smem_bytes, st)
+                   : launch_fwd_kernel<false>(tm, p, pl.smem_bytes, st);
 }
 
 // ------------------------------------------------------------------ wgrad
 struct WgParams {
     float *out;  // split-K partial slabs [split][cout][cin][kk], or gw itself when splits == 1
-    int cin, cout, kk, ks, pad;
+    int cin, cout, kk, ks, pad, stride;
     int n_tile;
-    int chunks_w, out_h;   // k-blocks per image = out_h * chunks_w (32 output columns each)
-    int kb_total, kb_per_split, splits;
+    int bw, bh;            // k-block = bw x bh output positions (DIRECT: 32 x 1)
+    int kpos;              // bw * bh
+    int nb;                // NHWC: 32-channel atoms of the B operand
+    uint32_t stage_bytes, a_bytes, atom_bytes;
+    int blocks_w, blocks_h;   // k-blocks per image = blocks_h * blocks_w
+    int kb_total, kb_per_split, splits, stages;
     size_t split_stride;
-    FastDiv d_img, d_cw;
+    FastDiv d_img, d_bw;
 };
 
-__global__ void __launch_bounds__(NTHREADS, 1)
+template <bool NHWC>
+__global__ void __launch_bounds__(WG_THREADS, 1)
 conv_tma_wgrad_kernel(const __grid_constant__ CUtensorMap tm_dy, const __grid_constant__ CUtensorMap tm_x,
                       const WgParams p) {
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     uint8_t *smem = reinterpret_cast<uint8_t *>(
         (reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
-    constexpr int S = 4;
+    const int S = p.stages;
     const int n_tile = p.n_tile;
-    const int b_stage_bytes = n_tile * BLOCK_K * 4;
-    const int stage_bytes = A_STAGE_BYTES + b_stage_bytes;
+    const uint32_t stage_bytes = p.stage_bytes;
     uint64_t *bars = reinterpret_cast<uint64_t *>(smem + (size_t)S * stage_bytes);
     uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bars + 2 * S + 1);
 
@@ -550,32 +694,49 @@ conv_tma_wgrad_kernel(const __grid_constant__ CUtensorMap tm_dy, const __grid_co
         if (lane == 0) {
             for (int it = 0; it < iters; ++it) {
                 const int s = it % S;
-                if (it >= S) mbar_wait(smem_u32(bars + S + s), ((it / S) - 1) & 1);
-                uint32_t img, rem, oh, cw;
+                mbar_wait(smem_u32(bars + S + s), ((it / S) & 1) ^ 1);
+                uint32_t img, rem, hb, wb;
                 p.d_img.divmod((uint32_t)(kb_begin + it), img, rem);
-                p.d_cw.divmod(rem, oh, cw);
+                p.d_bw.divmod(rem, hb, wb);
                 const uint32_t full = smem_u32(bars + s);
                 uint8_t *a_stage = smem + (size_t)s * stage_bytes;
-                mbar_expect_tx(full, (uint32_t)stage_bytes);
-                tma_load_4d(smem_u32(a_stage), &tm_dy, (int)cw * 32, (int)oh, co0, (int)img, full);
-                tma_load_4d(smem_u32(a_stage + A_STAGE_BYTES), &tm_x, (int)cw * 32 + kw - p.pad,
-                            (int)oh + kh - p.pad, ci0, (int)img, full);
+                mbar_expect_tx(full, stage_bytes);
+                if (NHWC) {
+                    const int ow0 = (int)wb * p.bw, oh0 = (int)hb * p.bh;
+                    for (int a = 0; a < 4; ++a)
+                        tma_load_4d(smem_u32(a_stage + a * p.atom_bytes), &tm_dy, co0 + 32 * a, ow0, oh0,
+                                    (int)img, full);
+                    for (int b = 0; b < p.nb; ++b)
+                        tma_load_4d(smem_u32(a_stage + p.a_bytes + b * p.atom_bytes), &tm_x, ci0 + 32 * b,
+                                    ow0 * p.stride + kw - p.pad, oh0 * p.stride + kh - p.pad, (int)img, full);
+                } else {
+                    tma_load_4d(smem_u32(a_stage), &tm_dy, (int)wb * 32, (int)hb, co0, (int)img, full);
+                    tma_load_4d(smem_u32(a_stage + p.a_bytes), &tm_x, (int)wb * 32 + kw - p.pad,
+                                (int)hb + kh - p.pad, ci0, (int)img, full);
+                }
             }
         }
     } else if (warp == 1) {
         if (lane == 0) {
-            const uint32_t idesc = make_idesc_tf32(TILE_M, n_tile, 0);
+            const uint32_t idesc = make_idesc_tf32(TILE_M, n_tile, NHWC ? 1 : 0, NHWC ? 1 : 0);
+            const int mmas = p.kpos / UMMA_K;
             for (int it = 0; it < iters; ++it) {
                 const int s = it % S;
                 mbar_wait(smem_u32(bars + s), (it / S) & 1);
                 tc_fence_after();
                 const uint32_t a_addr = smem_u32(smem + (size_t)s * stage_bytes);
-                const uint64_t da = make_desc_sw128(a_addr);
-                const uint64_t db = make_desc_sw128(a_addr + A_STAGE_BYTES);
-#pragma unroll
-                for (int g = 0; g < BLOCK_K / UMMA_K; ++g)
-                    umma_tf32(tmem_base, da + (uint64_t)(2 * g), db + (uint64_t)(2 * g), idesc,
-                              (it > 0 || g > 0) ? 1u : 0u);
+                const uint32_t b_addr = a_addr + p.a_bytes;
+                for (int g = 0; g < mmas; ++g) {
+                    uint64_t da, db;
+                    if (NHWC) {  // 8 position rows = 1 KiB further inside every atom
+                        da = make_desc_mn_sw128(a_addr + g * 1024, p.atom_bytes, 512);
+                        db = make_desc_mn_sw128(b_addr + g * 1024, p.atom_bytes, 512);
+                    } else {
+                        da = make_desc_sw128(a_addr) + (uint64_t)(2 * g);
+                        db = make_desc_sw128(b_addr) + (uint64_t)(2 * g);
+                    }
+                    umma_tf32(tmem_base, da, db, idesc, (it > 0 || g > 0) ? 1u : 0u);
+                }
                 umma_commit(smem_u32(bars + S + s));
                 if (it == iters - 1) umma_commit(smem_u32(bars + 2 * S));
             }
@@ -627,19 +788,23 @@ wgrad_reduce_tma_kernel(float *__restrict__ gw, const float *__restrict__ partia
 }
 
 struct WgPlan {
-    int n_tile, ci_tiles, co_tiles;
-    int view_w, view_h, out_w, out_h, chunks_w;
-    int kb_total, splits, kb_per_split;
-    size_t smem_bytes, partial_bytes;
+    bool nhwc;
+    int n_tile, ci_tiles, co_tiles, nb;
+    int view_w, view_h, out_w, out_h;   // DIRECT views
+    int bw, bh, blocks_w, blocks_h;
+    uint32_t atom_bytes, a_bytes, stage_bytes;
+    int kb_total, splits, kb_per_split, stages;
+    size_t smem_bytes, partial_bytes, shadow_x_bytes, shadow_dy_bytes;
 };
 
 bool plan_wgrad(const bcnn_b200_conv_desc *d, WgPlan *pl) {
-    const bool flat = d->ksize == 1;
-    pl->view_w = flat ? d->h * d->w : d->w;
-    pl->view_h = flat ? 1 : d->h;
-    pl->out_w = flat ? d->ho * d->wo : d->wo;
-    pl->out_h = flat ? 1 : d->ho;
-    if (pl->view_w % 4 != 0 || pl->out_w % 4 != 0) return false;
+    if (tma_disabled() || !encode_fn()) return false;
+    if (d->groups != 1) return false;
+    if (d->cin < 16 || d->cout < 32) return false;
+    if ((long long)d->batch * d->ho * d->wo < 512) return false;  // tiny reductions (fc-shaped)
+    const bool direct = d->ksize == 1 && d->stride == 1 && d->pad == 0 && (d->h * d->w) % 4 == 0;
+    pl->nhwc = !direct;
+    if (!direct && (nhwc_disabled() || d->cin % 4 != 0 || d->cout % 4 != 0 || d->stride > 4)) return false;
     int n = d->cin;
     if (n > 128) {
         int tiles = ceil_div(n, 128);
@@ -650,8 +815,34 @@ bool plan_wgrad(const bcnn_b200_conv_desc *d, WgPlan *pl) {
     pl->n_tile = n;
     pl->ci_tiles = ceil_div(d->cin, n);
     pl->co_tiles = ceil_div(d->cout, TILE_M);
-    pl->chunks_w = ceil_div(pl->out_w, 32);
-    const long long kb_total = (long long)d->batch * pl->out_h * pl->chunks_w;
+    pl->nb = ceil_div(n, 32);
+    if (direct) {
+        pl->view_w = d->h * d->w; pl->view_h = 1;
+        pl->out_w = d->ho * d->wo; pl->out_h = 1;
+        pl->bw = 32; pl->bh = 1;
+        pl->blocks_w = ceil_div(pl->out_w, 32); pl->blocks_h = 1;
+        pl->atom_bytes = 0;
+        pl->a_bytes = A_STAGE_BYTES;
+        pl->stage_bytes = A_STAGE_BYTES + (uint32_t)n * BLOCK_K * 4;
+        pl->shadow_x_bytes = pl->shadow_dy_bytes = 0;
+    } else {
+        // k-block = bw x bh output positions: multiple of 8, at most 64; columns past the row end
+        // are out of bounds in dY and read as zero
+        int bw = d->wo >= 64 ? 64 : ceil_div(d->wo, 8) * 8;
+        int bh = 64 / bw;
+        if (bh < 1) bh = 1;
+        if (bh > d->ho) bh = d->ho;
+        while (bw * d->stride > 256) bw -= 8;
+        pl->bw = bw; pl->bh = bh;
+        pl->blocks_w = ceil_div(d->wo, bw);
+        pl->blocks_h = ceil_div(d->ho, bh);
+        pl->atom_bytes = (uint32_t)(bw * bh * 128);
+        pl->a_bytes = 4 * pl->atom_bytes;
+        pl->stage_bytes = (uint32_t)(4 + pl->nb) * pl->atom_bytes;
+        pl->shadow_x_bytes = align256((size_t)d->batch * d->cin * d->h * d->w * sizeof(float));
+        pl->shadow_dy_bytes = align256((size_t)d->batch * d->cout * d->ho * d->wo * sizeof(float));
+    }
+    const long long kb_total = (long long)d->batch * pl->blocks_h * pl->blocks_w;
     if (kb_total >= (1LL << 31)) return false;
     pl->kb_total = (int)kb_total;
     const int kk = d->ksize * d->ksize;
@@ -663,40 +854,58 @@ bool plan_wgrad(const bcnn_b200_conv_desc *d, WgPlan *pl) {
     if (want < 1) want = 1;
     pl->kb_per_split = ceil_div(pl->kb_total, (int)want);
     pl->splits = ceil_div(pl->kb_total, pl->kb_per_split);
-    pl->smem_bytes = (size_t)4 * (A_STAGE_BYTES + n * BLOCK_K * 4) + 1024 + 256;
+    int stages = (int)((200u * 1024u) / pl->stage_bytes);
+    if (stages > 6) stages = 6;
+    if (stages < 2) return false;
+    pl->stages = stages;
+    pl->smem_bytes = (size_t)stages * pl->stage_bytes + 1024 + 256;
     const size_t wsize = (size_t)d->cout * d->cin * kk;
-    pl->partial_bytes = pl->splits > 1 ? (size_t)pl->splits * wsize * sizeof(float) : 0;
+    pl->partial_bytes = pl->splits > 1 ? align256((size_t)pl->splits * wsize * sizeof(float)) : 0;
     return true;
 }
 
-bool wg_shape_ok(const bcnn_b200_conv_desc *d) {
-    if (tma_disabled() || !encode_fn()) return false;
-    if (d->groups != 1 || d->stride != 1) return false;
-    if (d->cin < 16 || d->cout < 32) return false;
-    if (d->ksize != 1 || d->pad != 0) return false;
-    if ((long long)d->batch * d->ho * d->wo < 512) return false;
-    WgPlan pl;
-    return plan_wgrad(d, &pl);
+template <bool NHWC>
+int launch_wgrad_kernel(const CUtensorMap &tm_dy, const CUtensorMap &tm_x, const WgParams &p, dim3 grid,
+                        size_t smem, cudaStream_t st) {
+    static bool attr_set = false;
+    if (!attr_set) {
+        cudaError_t e = cudaFuncSetAttribute(conv_tma_wgrad_kernel<NHWC>,
+                                             cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+        if (e != cudaSuccess) return (int)e;
+        attr_set = true;
+    }
+    conv_tma_wgrad_kernel<NHWC><<<grid, WG_THREADS, smem, st>>>(tm_dy, tm_x, p);
+    return launched();
 }
 
 }  // namespace
 
 namespace b200 {
 
-bool conv_tma_supports_fprop(const bcnn_b200_conv_desc *d) { return fwd_shape_ok(d, false); }
-bool conv_tma_supports_dgrad(const bcnn_b200_conv_desc *d) { return fwd_shape_ok(d, true); }
-bool conv_tma_supports_wgrad(const bcnn_b200_conv_desc *d) { return wg_shape_ok(d); }
+bool conv_tma_supports_fprop(const bcnn_b200_conv_desc *d) {
+    FwdPlan pl;
+    return plan_fwd_desc(d, false, &pl);
+}
+bool conv_tma_supports_dgrad(const bcnn_b200_conv_desc *d) {
+    FwdPlan pl;
+    return plan_fwd_desc(d, true, &pl);
+}
+bool conv_tma_supports_wgrad(const bcnn_b200_conv_desc *d) {
+    WgPlan pl;
+    return plan_wgrad(d, &pl);
+}
 
 size_t conv_tma_workspace_bytes(const bcnn_b200_conv_desc *d) {
     size_t need = 0;
     FwdPlan pl;
-    if (fwd_shape_ok(d, false) && plan_fwd(d->cin, d->h, d->w, d->cout, d->ho, d->wo, d->ksize, &pl))
-        need = pl.wpack_bytes;
-    if (fwd_shape_ok(d, true) && plan_fwd(d->cout, d->ho, d->wo, d->cin, d->h, d->w, d->ksize, &pl) &&
-        pl.wpack_bytes > need)
-        need = pl.wpack_bytes;
+    if (plan_fwd_desc(d, false, &pl)) need = pl.shadow_bytes + pl.wpack_bytes;
+    if (plan_fwd_desc(d, true, &pl) && pl.shadow_bytes + pl.wpack_bytes > need)
+        need = pl.shadow_bytes + pl.wpack_bytes;
     WgPlan wp;
-    if (wg_shape_ok(d) && plan_wgrad(d, &wp) && wp.partial_bytes > need) need = wp.partial_bytes;
+    if (plan_wgrad(d, &wp)) {
+        const size_t w = wp.shadow_x_bytes + wp.shadow_dy_bytes + wp.partial_bytes;
+        if (w > need) need = w;
+    }
     return need;
 }
 
@@ -714,37 +923,48 @@ int conv_tma_backward_weights(const bcnn_b200_conv_desc *d, const float *x, cons
                               void *workspace, size_t workspace_bytes, cudaStream_t st) {
     WgPlan pl;
     if (!plan_wgrad(d, &pl)) return (int)cudaErrorInvalidValue;
-    if (pl.splits > 1 && (workspace == nullptr || workspace_bytes < pl.partial_bytes))
-        return (int)cudaErrorInvalidValue;
-    if (((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(dy)) & 15) != 0)
+    const size_t need = pl.shadow_x_bytes + pl.shadow_dy_bytes + pl.partial_bytes;
+    if (need > 0 && (workspace == nullptr || workspace_bytes < need)) return (int)cudaErrorInvalidValue;
+    if (((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(dy)) & 15) != 0 ||
+        (reinterpret_cast<uintptr_t>(workspace) & 255) != 0)
         return (int)cudaErrorMisalignedAddress;
+    uint8_t *ws = reinterpret_cast<uint8_t *>(workspace);
+    float *x_shadow = reinterpret_cast<float *>(ws);
+    float *dy_shadow = reinterpret_cast<float *>(ws + pl.shadow_x_bytes);
+    float *partial = reinterpret_cast<float *>(ws + pl.shadow_x_bytes + pl.shadow_dy_bytes);
     CUtensorMap tm_dy, tm_x;
-    if (!make_map(&tm_dy, dy, pl.out_w, pl.out_h, d->cout, d->batch, TILE_M, false) ||
-        !make_map(&tm_x, x, pl.view_w, pl.view_h, d->cin, d->batch, pl.n_tile, false))
+    int err;
+    if (pl.nhwc) {
+        err = launch_transpose(x, x_shadow, d->batch, d->cin, d->h * d->w, st);
+        if (err) return err;
+        err = launch_transpose(dy, dy_shadow, d->batch, d->cout, d->ho * d->wo, st);
+        if (err) return err;
+        if (!make_map_nhwc(&tm_dy, dy_shadow, d->cout, d->wo, d->ho, d->batch, pl.bw, pl.bh, 1, 1, true) ||
+            !make_map_nhwc(&tm_x, x_shadow, d->cin, d->w, d->h, d->batch, pl.bw, pl.bh, 1, d->stride, true))
+            return (int)cudaErrorInvalidValue;
+    } else if (!make_map_nchw(&tm_dy, dy, pl.out_w, pl.out_h, d->cout, d->batch, TILE_M, false) ||
+               !make_map_nchw(&tm_x, x, pl.view_w, pl.view_h, d->cin, d->batch, pl.n_tile, false)) {
         return (int)cudaErrorInvalidValue;
+    }
     WgParams p;
     p.cin = d->cin; p.cout = d->cout; p.ks = d->ksize; p.kk = d->ksize * d->ksize; p.pad = d->pad;
-    p.n_tile = pl.n_tile; p.chunks_w = pl.chunks_w; p.out_h = pl.out_h;
+    p.stride = d->stride;
+    p.n_tile = pl.n_tile; p.bw = pl.bw; p.bh = pl.bh; p.kpos = pl.bw * pl.bh; p.nb = pl.nb;
+    p.stage_bytes = pl.stage_bytes; p.a_bytes = pl.a_bytes; p.atom_bytes = pl.atom_bytes;
+    p.blocks_w = pl.blocks_w; p.blocks_h = pl.blocks_h;
     p.kb_total = pl.kb_total; p.kb_per_split = pl.kb_per_split; p.splits = pl.splits;
+    p.stages = pl.stages;
     const size_t wsize = (size_t)d->cout * d->cin * p.kk;
     p.split_stride = pl.splits > 1 ? wsize : 0;
-    p.out = pl.splits > 1 ? reinterpret_cast<float *>(workspace) : gw;
-    p.d_img = FastDiv((uint32_t)(pl.out_h * pl.chunks_w));
-    p.d_cw = FastDiv((uint32_t)pl.chunks_w);
-    static bool attr_set = false;
-    if (!attr_set) {
-        cudaError_t e = cudaFuncSetAttribute(conv_tma_wgrad_kernel,
-                                             cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
-        if (e != cudaSuccess) return (int)e;
-        attr_set = true;
-    }
+    p.out = pl.splits > 1 ? partial : gw;
+    p.d_img = FastDiv((uint32_t)(pl.blocks_h * pl.blocks_w));
+    p.d_bw = FastDiv((uint32_t)pl.blocks_w);
     dim3 grid(pl.splits, pl.ci_tiles * p.kk, pl.co_tiles);
-    conv_tma_wgrad_kernel<<<grid, NTHREADS, pl.smem_bytes, st>>>(tm_dy, tm_x, p);
-    int err = launched();
+    err = pl.nhwc ? launch_wgrad_kernel<true>(tm_dy, tm_x, p, grid, pl.smem_bytes, st)
+                  : launch_wgrad_kernel<false>(tm_dy, tm_x, p, grid, pl.smem_bytes, st);
     if (err) return err;
     if (pl.splits > 1) {
-        wgrad_reduce_tma_kernel<<<stream_grid(wsize, 256), 256, 0, st>>>(
-            gw, reinterpret_cast<const float *>(workspace), wsize, pl.splits);
+        wgrad_reduce_tma_kernel<<<stream_grid(wsize, 256), 256, 0, st>>>(gw, partial, wsize, pl.splits);
         return launched();
     }
     return 0;
