@@ -433,7 +433,8 @@ def run_own_arm(args):
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms_total / args.steps, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None,
-            "dtype": "bf16 (tcgen05, fp32 accumulate; fp32 elsewhere)" if math == capi.MATH_TC else "f32",
+            "dtype": "tf32 (tcgen05 kind::tf32 on fp32 tensors, fp32 accumulate in TMEM; fp32 elsewhere)"
+                     if math == capi.MATH_TC else "f32",
             "data": "synthetic",
             "config": {"workload": f"{args.workload} {args.res}x{args.res} training "
                                    f"(fwd+bwd+SGD) via the bcnn C API",

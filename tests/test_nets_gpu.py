@@ -23,7 +23,7 @@ from helpers import GOLDEN, assert_close, ref_available, ref_net, rel_err
 pytestmark = pytest.mark.gpu
 
 
-def _compare(out, golden, tol_s0, tol_final, what, noise=None):
+def _compare(out, golden, tol_s0, tol_final, what, noise=None, grad_l2_tol=None):
     """noise: expected relative operand perturbation of the path under test (BF16 rounding
     for the tensor-core path); the per-tensor tolerance then scales with the case's measured
     amplification (reference response / 2e-7 input perturbation)."""
@@ -53,6 +53,11 @@ def _compare(out, golden, tol_s0, tol_final, what, noise=None):
         sens = float(golden.get("sens:" + base, 0.0))
         tol = max(tol, 8.0 * sens if noise is None else (sens / 2e-7) * noise)
         e = max(rel_err(got, want))
+        if grad_l2_tol is not None and "/grad/" in base:
+            # ReLU-mask flips (a pre-activation within rounding noise of zero changes sign) put
+            # a few full-size errors into a gradient tensor and tiny-batch batchnorm spreads
+            # them: the max-abs metric is meaningless there, the L2 metric is not
+            e, tol = rel_err(got, want)[1], max(tol, grad_l2_tol)
         if e / tol > worst[0]:
             worst = (e / tol, f"{base} (err {e:.2e}, tol {tol:.2e})")
         assert e <= tol, f"{what}: {base} rel err {e:.3e} > {tol:.3e}"
@@ -77,8 +82,10 @@ def test_net_matches_golden_tensor_core(name):
     out = netcases.run_case(net, name)
     net.close()
     golden = {k: v for k, v in golden.items() if "/argmax/" not in k}
-    # BF16 operands: ~2^-9 per element, ~1e-3 effective after the dot products average it
-    _compare(out, golden, 2e-2, 5e-2, f"{name} tc vs golden", noise=1e-3)
+    # TF32 / BF16 operands: 2^-11 .. 2^-9 per element, <= 1e-3 effective after the dot products
+    # average it. Forward tensors and the loss are held to 2e-2; gradients of the ReLU nets to
+    # an L2-relative 0.15 (see _compare: mask flips at batch 4)
+    _compare(out, golden, 2e-2, 5e-2, f"{name} tc vs golden", noise=1e-3, grad_l2_tol=0.15)
 
 
 @pytest.mark.skipif(not ref_available(), reason="oracle/_ref was not built / did not travel")

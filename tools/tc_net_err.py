@@ -21,8 +21,10 @@ for math in (capi.MATH_FP32, capi.MATH_TC):
         if key.endswith("@sub"):
             idx = np.linspace(0, got.size - 1, want.size).astype(np.int64); got = got.ravel()[idx]
         if np.abs(want).max(initial=0) == 0: continue
-        e = max(rel_err(got, want))
-        print(f"{base:50s} {e:.3e} sens {float(golden.get('sens:'+base, 0)):.2e}")
+        e = rel_err(got, want)
+        d = np.abs(got.astype(np.float64).ravel() - want.astype(np.float64).ravel())
+        out_frac = float(np.mean(d > 2e-2 * np.abs(want).max()))
+        print(f"{base:50s} max {e[0]:.3e} l2 {e[1]:.3e} outliers {out_frac:.2e} sens {float(golden.get('sens:'+base, 0)):.2e}")
     for k in ("s0/grad/77:s1b1_out", "s0/grad/73:s1b1_c", "s0/data/77:s1b1_out"):
         g, w = out[k].ravel(), golden[k].ravel() if k in golden else golden[k+"@sub"].ravel()
         print(k, g.shape, w.shape, "got", g[:8], "want", w[:8], "absmax", np.abs(g).max(), np.abs(w).max(),
