@@ -406,7 +406,7 @@ def bind_kernel_abi(lib: C.CDLL) -> None:
         "bcnn_b200_softmax_forward": (i, [vp, vp, i, i, i, vp]),
         "bcnn_b200_cost_forward": (i, [vp, vp, vp, vp, i, i, i, vp]),
         "bcnn_b200_eltwise_forward": (i, [vp, vp, vp, i, i, i, vp]),
-        "bcnn_b200_eltwise_backward": (i, [vp, vp, vp, vp, i, i, i, vp]),
+        "bcnn_b200_eltwise_backward": (i, [vp, vp, vp, vp, i, i, i, i, vp]),
     }
     for name, (res, args) in sigs.items():
         fn = getattr(lib, name)

@@ -201,7 +201,8 @@ eltwise_fwd_kernel(const float *__restrict__ a, const float *__restrict__ b, flo
 
 __global__ void __launch_bounds__(256)
 eltwise_bwd_kernel(const float *__restrict__ y, float *__restrict__ dy, float *__restrict__ da,
-                   float *__restrict__ db, size_t n, size_t n_add, int act, bool vec) {
+                   float *__restrict__ db, size_t n, size_t n_add, int act, bool vec, bool acc_a,
+                   bool acc_b) {
     size_t gstride = (size_t)gridDim.x * blockDim.x;
     size_t tid = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     size_t done = 0;
@@ -218,14 +219,23 @@ eltwise_bwd_kernel(const float *__restrict__ y, float *__restrict__ dy, float *_
                 reinterpret_cast<float4 *>(dy)[j] = g;
             }
             if (da) {
-                float4 u = reinterpret_cast<float4 *>(da)[j];
-                u.x += g.x; u.y += g.y; u.z += g.z; u.w += g.w;
+                float4 u = g;
+                if (acc_a) {
+                    const float4 o = reinterpret_cast<float4 *>(da)[j];
+                    u.x += o.x; u.y += o.y; u.z += o.z; u.w += o.w;
+                }
                 reinterpret_cast<float4 *>(da)[j] = u;
             }
-            if (db && (j << 2) < n_add) {
-                float4 w = reinterpret_cast<float4 *>(db)[j];
-                w.x += g.x; w.y += g.y; w.z += g.z; w.w += g.w;
-                reinterpret_cast<float4 *>(db)[j] = w;
+            if (db) {
+                const bool in = (j << 2) < n_add;
+                if (in || !acc_b) {
+                    float4 w = in ? g : make_float4(0.f, 0.f, 0.f, 0.f);
+                    if (acc_b) {
+                        const float4 o = reinterpret_cast<float4 *>(db)[j];
+                        w.x += o.x; w.y += o.y; w.z += o.z; w.w += o.w;
+                    }
+                    reinterpret_cast<float4 *>(db)[j] = w;
+                }
             }
         }
         done = n4 << 2;
@@ -236,8 +246,11 @@ eltwise_bwd_kernel(const float *__restrict__ y, float *__restrict__ dy, float *_
             g *= act_bwd_factor(y[j], act, 0.f);
             dy[j] = g;
         }
-        if (da) da[j] += g;
-        if (db && j < n_add) db[j] += g;
+        if (da) da[j] = acc_a ? da[j] + g : g;
+        if (db) {
+            if (acc_b) { if (j < n_add) db[j] += g; }
+            else db[j] = j < n_add ? g : 0.f;
+        }
     }
 }
 
@@ -323,10 +336,11 @@ extern "C" int bcnn_b200_eltwise_forward(const float *a, const float *b, float *
 }
 
 extern "C" int bcnn_b200_eltwise_backward(const float *y, float *dy, float *da, float *db, int sz,
-                                          int n_add, int act, void *stream) {
+                                          int n_add, int act, int accumulate_flags, void *stream) {
     if (sz <= 0) return 0;
     bool vec = aligned16(y) && aligned16(dy) && aligned16(da) && aligned16(db) && (n_add % 4) == 0;
     eltwise_bwd_kernel<<<stream_grid(vec ? sz / 4 + 1 : sz, 256), 256, 0, as_stream(stream)>>>(
-        y, dy, da, db, (size_t)sz, (size_t)n_add, act, vec);
+        y, dy, da, db, (size_t)sz, (size_t)n_add, act, vec, (accumulate_flags & 1) != 0,
+        (accumulate_flags & 2) != 0);
     return launched();
 }

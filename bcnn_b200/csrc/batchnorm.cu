@@ -52,12 +52,27 @@ bn_stats_kernel(const float *__restrict__ x, int n, int c, int hw, float *__rest
     if (vec) {
         const int hw4 = hw >> 2;
         const uint32_t total4 = (uint32_t)(b1 - b0) * hw4;
-        for (uint32_t j = threadIdx.x; j < total4; j += RT) {
-            uint32_t b, i4;
-            div_hw4.divmod(j, b, i4);
-            float4 v = ld_stream4(x + ((size_t)(b0 + b) * c + ch) * hw + (i4 << 2));
-            acc[0] += (v.x + v.y) + (v.z + v.w);
-            acc[1] += (v.x * v.x + v.y * v.y) + (v.z * v.z + v.w * v.w);
+        // UNROLL independent 16-byte loads in flight per thread: a channel's reduction runs on
+        // few CTAs, so memory-level parallelism has to come from inside the thread
+        constexpr int UNROLL = 4;
+        for (uint32_t j0 = threadIdx.x; j0 < total4; j0 += RT * UNROLL) {
+            float4 v[UNROLL];
+#pragma unroll
+            for (int u = 0; u < UNROLL; ++u) {
+                const uint32_t j = j0 + u * RT;
+                if (j < total4) {
+                    uint32_t b, i4;
+                    div_hw4.divmod(j, b, i4);
+                    v[u] = ld_stream4(x + ((size_t)(b0 + b) * c + ch) * hw + (i4 << 2));
+                } else {
+                    v[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+                }
+            }
+#pragma unroll
+            for (int u = 0; u < UNROLL; ++u) {
+                acc[0] += (v[u].x + v[u].y) + (v[u].z + v[u].w);
+                acc[1] += (v[u].x * v[u].x + v[u].y * v[u].y) + (v[u].z * v[u].z + v[u].w * v[u].w);
+            }
         }
     } else {
         const uint32_t total = (uint32_t)(b1 - b0) * hw;
@@ -108,23 +123,35 @@ bn_apply_kernel(const float *__restrict__ x, float *__restrict__ y, const float 
     size_t gstride = (size_t)gridDim.x * blockDim.x;
     size_t tid = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (vec) {
-        size_t n4 = total >> 2;
-        for (size_t j = tid; j < n4; j += gstride) {
-            uint32_t q, ch;
-            div_c.divmod(div_hw.div((uint32_t)(j << 2)), q, ch);
-            float g = __ldg(gamma + ch), b = __ldg(beta + ch);
-            float m = 0.f, inv = 1.f;
-            if (NORMALISE) {
-                m = __ldg(mean + ch);
-                inv = 1.0f / sqrtf(__ldg(var + ch) + 0.000001f);
+        const size_t n4 = total >> 2;
+        constexpr int UNROLL = 2;  // independent 16-byte loads in flight per thread
+        for (size_t j0 = tid; j0 < n4; j0 += gstride * UNROLL) {
+            float4 v[UNROLL];
+#pragma unroll
+            for (int u = 0; u < UNROLL; ++u) {
+                const size_t j = j0 + u * gstride;
+                // in-place use (x == y) must not go through the non-coherent path
+                if (j < n4) v[u] = (x == y) ? reinterpret_cast<const float4 *>(x)[j] : ld_stream4(x + (j << 2));
             }
-            // in-place use (x == y) must not go through the non-coherent path
-            float4 v = (x == y) ? reinterpret_cast<const float4 *>(x)[j] : ld_stream4(x + (j << 2));
-            v.x = act_fwd((v.x - m) * inv * g + b, act, 0.f);
-            v.y = act_fwd((v.y - m) * inv * g + b, act, 0.f);
-            v.z = act_fwd((v.z - m) * inv * g + b, act, 0.f);
-            v.w = act_fwd((v.w - m) * inv * g + b, act, 0.f);
-            reinterpret_cast<float4 *>(y)[j] = v;
+#pragma unroll
+            for (int u = 0; u < UNROLL; ++u) {
+                const size_t j = j0 + u * gstride;
+                if (j >= n4) break;
+                uint32_t q, ch;
+                div_c.divmod(div_hw.div((uint32_t)(j << 2)), q, ch);
+                const float g = __ldg(gamma + ch), b = __ldg(beta + ch);
+                float m = 0.f, inv = 1.f;
+                if (NORMALISE) {
+                    m = __ldg(mean + ch);
+                    inv = 1.0f / sqrtf(__ldg(var + ch) + 0.000001f);
+                }
+                float4 r;
+                r.x = act_fwd((v[u].x - m) * inv * g + b, act, 0.f);
+                r.y = act_fwd((v[u].y - m) * inv * g + b, act, 0.f);
+                r.z = act_fwd((v[u].z - m) * inv * g + b, act, 0.f);
+                r.w = act_fwd((v[u].w - m) * inv * g + b, act, 0.f);
+                reinterpret_cast<float4 *>(y)[j] = r;
+            }
         }
     } else {
         for (size_t j = tid; j < total; j += gstride) {
@@ -160,21 +187,34 @@ bn_bwd_reduce_kernel(const float *__restrict__ x, const float *__restrict__ y,
     if (vec) {
         const int hw4 = hw >> 2;
         const uint32_t total4 = (uint32_t)(b1 - b0) * hw4;
-        for (uint32_t j = threadIdx.x; j < total4; j += RT) {
-            uint32_t b, i4;
-            div_hw4.divmod(j, b, i4);
-            size_t off = ((size_t)(b0 + b) * c + ch) * hw + (i4 << 2);
-            float4 xv = ld_stream4(x + off);
-            float4 g = ld_stream4(dy + off);
-            if (act != ACT_NONE) {
-                float4 yv = ld_stream4(y + off);
-                g.x *= act_bwd_factor(yv.x, act, 0.f);
-                g.y *= act_bwd_factor(yv.y, act, 0.f);
-                g.z *= act_bwd_factor(yv.z, act, 0.f);
-                g.w *= act_bwd_factor(yv.w, act, 0.f);
+        constexpr int UNROLL = 2;
+        for (uint32_t j0 = threadIdx.x; j0 < total4; j0 += RT * UNROLL) {
+            float4 xv[UNROLL], g[UNROLL], yv[UNROLL];
+#pragma unroll
+            for (int u = 0; u < UNROLL; ++u) {
+                const uint32_t j = j0 + u * RT;
+                xv[u] = g[u] = yv[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (j < total4) {
+                    uint32_t b, i4;
+                    div_hw4.divmod(j, b, i4);
+                    size_t off = ((size_t)(b0 + b) * c + ch) * hw + (i4 << 2);
+                    xv[u] = ld_stream4(x + off);
+                    g[u] = ld_stream4(dy + off);
+                    if (act != ACT_NONE) yv[u] = ld_stream4(y + off);
+                }
             }
-            acc[0] += (g.x + g.y) + (g.z + g.w);
-            acc[1] += (g.x * (xv.x - m) + g.y * (xv.y - m)) + (g.z * (xv.z - m) + g.w * (xv.w - m));
+#pragma unroll
+            for (int u = 0; u < UNROLL; ++u) {
+                if (act != ACT_NONE) {
+                    g[u].x *= act_bwd_factor(yv[u].x, act, 0.f);
+                    g[u].y *= act_bwd_factor(yv[u].y, act, 0.f);
+                    g[u].z *= act_bwd_factor(yv[u].z, act, 0.f);
+                    g[u].w *= act_bwd_factor(yv[u].w, act, 0.f);
+                }
+                acc[0] += (g[u].x + g[u].y) + (g[u].z + g[u].w);
+                acc[1] += (g[u].x * (xv[u].x - m) + g[u].y * (xv[u].y - m)) +
+                          (g[u].z * (xv[u].z - m) + g[u].w * (xv[u].w - m));
+            }
         }
     } else {
         const uint32_t total = (uint32_t)(b1 - b0) * hw;
@@ -225,29 +265,43 @@ bn_bwd_apply_kernel(const float *__restrict__ x, const float *__restrict__ y,
     size_t tid = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     const float inv_count = 1.0f / (float)count;
     if (vec) {
-        size_t n4 = total >> 2;
-        for (size_t j = tid; j < n4; j += gstride) {
-            uint32_t q, ch;
-            div_c.divmod(div_hw.div((uint32_t)(j << 2)), q, ch);
-            const float m = __ldg(mean + ch);
-            const float k1 = __ldg(gamma + ch) / sqrtf(__ldg(var + ch) + 0.00001f);
-            const float k2 = __ldg(d_var + ch) * 2.0f * inv_count;
-            const float k3 = __ldg(d_mean + ch) * inv_count;
-            float4 xv = ld_stream4(x + (j << 2));
-            float4 g = reinterpret_cast<const float4 *>(dy)[j];
-            if (act != ACT_NONE) {
-                float4 yv = ld_stream4(y + (j << 2));
-                g.x *= act_bwd_factor(yv.x, act, 0.f);
-                g.y *= act_bwd_factor(yv.y, act, 0.f);
-                g.z *= act_bwd_factor(yv.z, act, 0.f);
-                g.w *= act_bwd_factor(yv.w, act, 0.f);
+        const size_t n4 = total >> 2;
+        constexpr int UNROLL = 2;
+        for (size_t j0 = tid; j0 < n4; j0 += gstride * UNROLL) {
+            float4 xv[UNROLL], gv[UNROLL], yv[UNROLL];
+#pragma unroll
+            for (int u = 0; u < UNROLL; ++u) {
+                const size_t j = j0 + u * gstride;
+                if (j < n4) {
+                    xv[u] = ld_stream4(x + (j << 2));
+                    gv[u] = reinterpret_cast<const float4 *>(dy)[j];
+                    if (act != ACT_NONE) yv[u] = ld_stream4(y + (j << 2));
+                }
             }
-            float4 r;
-            r.x = g.x * k1 + k2 * (xv.x - m) + k3;
-            r.y = g.y * k1 + k2 * (xv.y - m) + k3;
-            r.z = g.z * k1 + k2 * (xv.z - m) + k3;
-            r.w = g.w * k1 + k2 * (xv.w - m) + k3;
-            reinterpret_cast<float4 *>(dx)[j] = r;
+#pragma unroll
+            for (int u = 0; u < UNROLL; ++u) {
+                const size_t j = j0 + u * gstride;
+                if (j >= n4) break;
+                uint32_t q, ch;
+                div_c.divmod(div_hw.div((uint32_t)(j << 2)), q, ch);
+                const float m = __ldg(mean + ch);
+                const float k1 = __ldg(gamma + ch) / sqrtf(__ldg(var + ch) + 0.00001f);
+                const float k2 = __ldg(d_var + ch) * 2.0f * inv_count;
+                const float k3 = __ldg(d_mean + ch) * inv_count;
+                float4 g = gv[u];
+                if (act != ACT_NONE) {
+                    g.x *= act_bwd_factor(yv[u].x, act, 0.f);
+                    g.y *= act_bwd_factor(yv[u].y, act, 0.f);
+                    g.z *= act_bwd_factor(yv[u].z, act, 0.f);
+                    g.w *= act_bwd_factor(yv[u].w, act, 0.f);
+                }
+                float4 r;
+                r.x = g.x * k1 + k2 * (xv[u].x - m) + k3;
+                r.y = g.y * k1 + k2 * (xv[u].y - m) + k3;
+                r.z = g.z * k1 + k2 * (xv[u].z - m) + k3;
+                r.w = g.w * k1 + k2 * (xv[u].w - m) + k3;
+                reinterpret_cast<float4 *>(dx)[j] = r;
+            }
         }
     } else {
         for (size_t j = tid; j < total; j += gstride) {

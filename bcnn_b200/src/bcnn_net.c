@@ -80,6 +80,8 @@ void bcnn_end_net(bcnn_net **net) {
     if (ctx) {
         for (int i = 0; i < 4 * ctx->profile_nodes; ++i) bcnn_b200_event_destroy(ctx->profile_events[i]);
         free(ctx->profile_events);
+        free(ctx->grad_fresh);
+        free(ctx->consumers);
         bcnn_b200_free(ctx->workspace_gpu);
         bcnn_b200_stream_destroy(ctx->stream);
         free(ctx);
@@ -172,15 +174,56 @@ bcnn_tensor *bcnn_get_tensor_by_name(bcnn_net *net, const char *name) {
     return bcnn_get_tensor_by_index(net, bcnn_get_tensor_index_by_name(net, name));
 }
 
-/* Zero the gradient of a node's outputs before its forward (TRAIN only), as
- * bcnn_reset_gradients does; weight gradients are never reset (momentum lives there). */
+/* (Re)build the per-tensor gradient state tables after the graph changed. */
+static void grad_state_sync(bcnn_net *net) {
+    bcnn_cuda_context *ctx = bcnn_ctx(net);
+    if (ctx->grad_state_tensors == net->num_tensors && ctx->grad_state_nodes == net->num_nodes &&
+        ctx->grad_fresh)
+        return;
+    free(ctx->grad_fresh);
+    free(ctx->consumers);
+    ctx->grad_fresh = (unsigned char *)malloc((size_t)net->num_tensors);
+    ctx->consumers = (int *)malloc((size_t)net->num_tensors * sizeof(int));
+    memset(ctx->grad_fresh, 1, (size_t)net->num_tensors); /* outside TRAIN: always accumulate */
+    for (int i = 0; i < net->num_tensors; ++i) ctx->consumers[i] = bcnn_net_num_consumers(net, i);
+    ctx->grad_state_tensors = net->num_tensors;
+    ctx->grad_state_nodes = net->num_nodes;
+}
+
+/* The reference zero-fills the gradient of a node's outputs before its forward (TRAIN only,
+ * bcnn_reset_gradients); weight gradients are never reset (momentum lives there). Here the
+ * buffers are only marked stale (see bcnn_cuda_context.grad_fresh); a tensor nobody consumes
+ * has no backward writer and is really filled. */
 static void reset_output_gradients(bcnn_net *net, bcnn_node *node) {
+    bcnn_cuda_context *ctx = bcnn_ctx(net);
     for (int i = 0; i < node->num_dst; ++i) {
-        bcnn_tensor *t = &net->tensors[node->dst[i]];
-        if (t->grad_data_gpu)
+        const int idx = node->dst[i];
+        bcnn_tensor *t = &net->tensors[idx];
+        if (!t->grad_data_gpu) continue;
+        if (ctx->consumers[idx] == 0) {
             bcnn_cuda_check(bcnn_b200_fill_f32(t->grad_data_gpu, (size_t)bcnn_tensor_size(t), 0.0f,
                                                bcnn_stream(net)));
+            ctx->grad_fresh[idx] = 1;
+        } else {
+            ctx->grad_fresh[idx] = 0;
+        }
     }
+}
+
+int bcnn_net_grad_accumulate(bcnn_net *net, int index) {
+    bcnn_cuda_context *ctx = bcnn_ctx(net);
+    grad_state_sync(net);
+    const int fresh = ctx->grad_fresh[index];
+    ctx->grad_fresh[index] = 1;
+    return fresh;
+}
+
+void bcnn_net_grad_prepare_accumulate(bcnn_net *net, int index) {
+    if (bcnn_net_grad_accumulate(net, index)) return;
+    bcnn_tensor *t = &net->tensors[index];
+    if (t->grad_data_gpu)
+        bcnn_cuda_check(bcnn_b200_fill_f32(t->grad_data_gpu, (size_t)bcnn_tensor_size(t), 0.0f,
+                                           bcnn_stream(net)));
 }
 
 static inline void profile_mark(bcnn_net *net, int node, int slot) {
@@ -190,6 +233,7 @@ static inline void profile_mark(bcnn_net *net, int node, int slot) {
 }
 
 void bcnn_forward(bcnn_net *net) {
+    grad_state_sync(net);
     for (int i = 0; i < net->num_nodes; ++i) {
         bcnn_node *node = &net->nodes[i];
         profile_mark(net, i, 0);

@@ -33,6 +33,15 @@ typedef struct bcnn_cuda_context {
     int profile;
     int profile_nodes;
     void **profile_events;
+    /* Lazy gradient reset. bcnn_reset_gradients (reference src/bcnn_net.c:361-375) zero-fills
+     * every output gradient before each node's forward so that backward writers can `+=`.
+     * Here bcnn_forward only marks those buffers stale; the first backward writer of a step
+     * overwrites (no fill, no read), later writers accumulate: same values, two memory
+     * passes fewer per activation. grad_fresh[t] != 0 <=> tensor t's gradient holds a partial
+     * sum of the current step. */
+    unsigned char *grad_fresh;
+    int *consumers; /* activation consumers per tensor (bcnn_net_num_consumers) */
+    int grad_state_tensors, grad_state_nodes;
 } bcnn_cuda_context;
 
 struct bcnn_net {
@@ -75,6 +84,12 @@ bcnn_status bcnn_net_add_dst_tensor(bcnn_net *net, bcnn_node *node, int n, int c
 /* Number of nodes that read tensor `index` as an activation input (src[0], or both
  * inputs of an eltwise node). */
 int bcnn_net_num_consumers(bcnn_net *net, int index);
+/* For a backward writer that can overwrite: returns 1 when tensor `index`'s gradient already
+ * holds a partial sum of this step (accumulate into it), 0 when it is stale (overwrite it);
+ * either way the buffer counts as fresh afterwards. */
+int bcnn_net_grad_accumulate(bcnn_net *net, int index);
+/* For a backward writer that can only accumulate: zero-fill the buffer now if it is stale. */
+void bcnn_net_grad_prepare_accumulate(bcnn_net *net, int index);
 /* Grow the shared conv workspace requirement. */
 void bcnn_net_require_workspace(bcnn_net *net, size_t bytes);
 /* Global batch (local batch x data-parallel world) and the factor gradients are scaled

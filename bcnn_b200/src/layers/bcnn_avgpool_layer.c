@@ -34,6 +34,7 @@ void bcnn_forward_avgpool_layer_gpu(bcnn_net *net, bcnn_node *node) {
 void bcnn_backward_avgpool_layer_gpu(bcnn_net *net, bcnn_node *node) {
     bcnn_tensor *src = &net->tensors[node->src[0]], *dst = &net->tensors[node->dst[0]];
     if (!src->grad_data_gpu) return;
+    bcnn_net_grad_prepare_accumulate(net, node->src[0]); /* the kernel does += */
     bcnn_cuda_check(bcnn_b200_avgpool_backward(src->grad_data_gpu, dst->grad_data_gpu,
                                                src->n * src->c, src->h * src->w,
                                                bcnn_stream(net)));

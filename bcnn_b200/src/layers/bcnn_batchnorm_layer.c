@@ -111,10 +111,12 @@ void bcnn_backward_batchnorm_layer_gpu(bcnn_net *net, bcnn_node *node) {
                                 &t[node->src[3]], &t[node->src[4]], &param->saved_mean,
                                 &param->saved_variance, param->reduce_scratch_gpu, net->mode,
                                 BCNN_ACT_NONE);
-    if (src->grad_data_gpu) /* overwrite, as the reference's bcnn_copy_f32 (:327-330) */
+    if (src->grad_data_gpu) { /* overwrite, as the reference's bcnn_copy_f32 (:327-330) */
+        (void)bcnn_net_grad_accumulate(net, node->src[0]);
         bcnn_cuda_check(bcnn_b200_memcpy_d2d(src->grad_data_gpu, dst->grad_data_gpu,
                                              (size_t)bcnn_tensor_size(dst) * sizeof(float),
                                              bcnn_stream(net)));
+    }
 }
 
 void bcnn_forward_batchnorm_layer(bcnn_net *net, bcnn_node *node) {

@@ -183,9 +183,10 @@ void bcnn_backward_conv_layer_gpu(bcnn_net *net, bcnn_node *node) {
         ctx->workspace_gpu, ctx->workspace_bytes, ctx->conv_math, stream));
     if (src->grad_data_gpu) {
         /* reference semantics: overwrite. With the quirks off, a source read by several
-         * nodes (residual branches) accumulates instead -- its gradient was zeroed by
-         * bcnn_forward, so every consumer's contribution is summed. */
-        int accumulate = !ctx->reference_quirks && bcnn_net_num_consumers(net, node->src[0]) > 1;
+         * nodes (residual branches) accumulates instead: the first backward writer of the
+         * step overwrites the stale buffer, every later consumer's contribution is summed. */
+        int accumulate = bcnn_net_grad_accumulate(net, node->src[0]);
+        if (ctx->reference_quirks) accumulate = 0;
         bcnn_cuda_check(bcnn_b200_conv_backward_data(
             &param->desc, weights->data_gpu, dst->grad_data_gpu, src->grad_data_gpu, accumulate,
             ctx->workspace_gpu, ctx->workspace_bytes, ctx->conv_math, stream));

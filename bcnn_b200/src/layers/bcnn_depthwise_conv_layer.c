@@ -78,6 +78,7 @@ void bcnn_backward_depthwise_conv_layer_gpu(bcnn_net *net, bcnn_node *node) {
                                                dst->data_gpu, param->activation, dst->n, dst->c,
                                                dst->h * dst->w, param->reduce_scratch_gpu, stream));
     if (!src->grad_data_gpu) return;
+    bcnn_net_grad_prepare_accumulate(net, node->src[0]); /* the kernel does dx += */
     bcnn_cuda_check(bcnn_b200_depthwise_backward(
         src->data_gpu, weights->data_gpu, dst->grad_data_gpu, weights->grad_data_gpu,
         src->grad_data_gpu, src->n, src->c, src->h, src->w, param->size, param->stride, param->pad,

@@ -76,7 +76,8 @@ void bcnn_backward_fullc_layer(bcnn_net *net, bcnn_node *node) {
     if (src->grad_data_gpu)
         bcnn_cuda_check(bcnn_b200_conv_backward_data(
             &param->desc, weights->data_gpu, dst->grad_data_gpu, src->grad_data_gpu,
-            /*accumulate=*/1, ctx->workspace_gpu, ctx->workspace_bytes, BCNN_B200_MATH_FP32,
+            /*accumulate (the reference's +=)*/ bcnn_net_grad_accumulate(net, node->src[0]),
+            ctx->workspace_gpu, ctx->workspace_bytes, BCNN_B200_MATH_FP32,
             ctx->stream));
 }
 

@@ -46,6 +46,7 @@ void bcnn_forward_softmax_layer(bcnn_net *net, bcnn_node *node) {
 void bcnn_backward_softmax_layer(bcnn_net *net, bcnn_node *node) {
     bcnn_tensor *src = &net->tensors[node->src[0]], *dst = &net->tensors[node->dst[0]];
     if (!src->grad_data_gpu) return;
+    bcnn_net_grad_prepare_accumulate(net, node->src[0]);
     bcnn_cuda_check(bcnn_b200_axpy(src->grad_data_gpu, dst->grad_data_gpu,
                                    (size_t)bcnn_tensor_size(src), 1.0f, bcnn_stream(net)));
 }
@@ -100,6 +101,7 @@ void bcnn_backward_cost_layer(bcnn_net *net, bcnn_node *node) {
     bcnn_cost_param *param = (bcnn_cost_param *)node->param;
     bcnn_tensor *src = &net->tensors[node->src[0]], *dst = &net->tensors[node->dst[0]];
     if (!src->grad_data_gpu || !dst->grad_data_gpu) return;
+    bcnn_net_grad_prepare_accumulate(net, node->src[0]);
     bcnn_cuda_check(bcnn_b200_axpy(src->grad_data_gpu, dst->grad_data_gpu,
                                    (size_t)bcnn_tensor_size(src), param->scale, bcnn_stream(net)));
 }
@@ -167,7 +169,10 @@ void bcnn_backward_eltwise_layer(bcnn_net *net, bcnn_node *node) {
     bcnn_tensor *dst = &t[node->dst[0]];
     const int sz = bcnn_tensor_size(dst);
     const int n_add = bcnn_ctx(net)->reference_quirks ? param->min_dim[0] * dst->h * dst->w : sz;
+    int flags = 0;
+    if (t[node->src[0]].grad_data_gpu && bcnn_net_grad_accumulate(net, node->src[0])) flags |= 1;
+    if (t[node->src[1]].grad_data_gpu && bcnn_net_grad_accumulate(net, node->src[1])) flags |= 2;
     bcnn_cuda_check(bcnn_b200_eltwise_backward(
         dst->data_gpu, dst->grad_data_gpu, t[node->src[0]].grad_data_gpu,
-        t[node->src[1]].grad_data_gpu, sz, n_add, param->activation, bcnn_stream(net)));
+        t[node->src[1]].grad_data_gpu, sz, n_add, param->activation, flags, bcnn_stream(net)));
 }

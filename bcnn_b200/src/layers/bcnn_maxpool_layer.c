@@ -67,6 +67,7 @@ void bcnn_backward_maxpool_layer_gpu(bcnn_net *net, bcnn_node *node) {
     bcnn_maxpool_param *param = (bcnn_maxpool_param *)node->param;
     bcnn_tensor *src = &net->tensors[node->src[0]], *dst = &net->tensors[node->dst[0]];
     if (!src->grad_data_gpu) return;
+    bcnn_net_grad_prepare_accumulate(net, node->src[0]); /* the kernel does += */
     bcnn_cuda_check(bcnn_b200_maxpool_backward(src->grad_data_gpu, dst->grad_data_gpu,
                                                param->indexes_gpu, src->n, src->c, src->h, src->w,
                                                param->size, param->stride, dst->h, dst->w,

@@ -237,10 +237,14 @@ BCNN_B200_API int bcnn_b200_cost_forward(const float *pred, const float *label,
  * :119-121). replaces bcnn_cuda_copy_f32 + bcnn_cuda_axpy + activation kernel. */
 BCNN_B200_API int bcnn_b200_eltwise_forward(const float *a, const float *b, float *y,
                                             int sz, int n_add, int act, void *stream);
-/* dy *= act'(y); da += dy; db[:n_add] += dy[:n_add]  (da / db may be NULL) */
+/* dy *= act'(y); da (+)= dy; db[:n_add] (+)= dy[:n_add]  (da / db may be NULL).
+ * accumulate_flags bit 0 / bit 1: da / db already hold a partial sum of this step and are
+ * added to (the reference's +=, bcnn_eltwise_layer.c:148-158); a clear bit means the buffer is
+ * stale and is overwritten (db beyond n_add with zero) -- same result as += onto the zero-
+ * filled gradient of bcnn_reset_gradients without the fill and the read. */
 BCNN_B200_API int bcnn_b200_eltwise_backward(const float *y, float *dy, float *da,
                                              float *db, int sz, int n_add, int act,
-                                             void *stream);
+                                             int accumulate_flags, void *stream);
 
 #ifdef __cplusplus
 }

@@ -456,6 +456,15 @@ def test_eltwise_forward_backward():
     g = f32(r.uniform(-1, 1, size=a.size))
     ga0, gb0 = f32(r.uniform(-1, 1, size=a.size)), f32(r.uniform(-1, 1, size=a.size))
     dg, dga, dgb = dev(g), dev(ga0), dev(gb0)
-    check(lib.bcnn_b200_eltwise_backward(dyo.ptr, dg.ptr, dga.ptr, dgb.ptr, a.size, a.size, ACT["relu"], None))
+    check(lib.bcnn_b200_eltwise_backward(dyo.ptr, dg.ptr, dga.ptr, dgb.ptr, a.size, a.size, ACT["relu"], 3, None))
     gm = g * (y > 0)
     assert np.array_equal(dga.download(), ga0 + gm) and np.array_equal(dgb.download(), gb0 + gm)
+    # stale-buffer flavour: da overwritten, db accumulated; then both overwritten with the
+    # reference quirk (only the first n_add elements of db receive a gradient)
+    dg.upload(g)
+    check(lib.bcnn_b200_eltwise_backward(dyo.ptr, dg.ptr, dga.ptr, dgb.ptr, a.size, a.size, ACT["relu"], 2, None))
+    assert np.array_equal(dga.download(), gm) and np.array_equal(dgb.download(), gb0 + gm + gm)
+    dg.upload(g)
+    check(lib.bcnn_b200_eltwise_backward(dyo.ptr, dg.ptr, dga.ptr, dgb.ptr, a.size, 1024, ACT["relu"], 0, None))
+    want_b = np.where(np.arange(a.size) < 1024, gm, 0).astype(np.float32)
+    assert np.array_equal(dga.download(), gm) and np.array_equal(dgb.download(), want_b)
