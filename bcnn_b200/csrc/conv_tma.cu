@@ -180,10 +180,16 @@ int launch_transpose(const float *in, float *out, int n, int c, int p, cudaStrea
 // K-major SWIZZLE_128B shared-memory image, so a k-block tile is one bulk copy.
 //   fprop: row = co, k = ci, tap as is            -> W[co][ci][tap]
 //   dgrad: row = ci, k = co, tap flipped (kk-1-t) -> W[co][ci][kk-1-tap]
+//   sub-sampled dgrad classes (stride > 1): taps.idx lists the filter taps of the class
+struct TapMap {
+    int n;            // taps of this (sub-)convolution, in the kernel's (kh, kw) walk order
+    short idx[64];    // tap t reads W[..][..][idx[t]]
+};
+
 __global__ void __launch_bounds__(256)
 pack_weights_tf32_kernel(const float *__restrict__ w, float *__restrict__ wpack, int dgrad, int cout,
-                         int cin, int kk, int n_tile, int n_tiles, int kc_blocks) {
-    const int k_blocks = kk * kc_blocks;
+                         int cin, int kk, int n_tile, int n_tiles, int kc_blocks, const TapMap taps) {
+    const int k_blocks = taps.n * kc_blocks;
     const size_t chunks = (size_t)n_tiles * n_tile * k_blocks * 8;
     for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < chunks;
          i += (size_t)gridDim.x * blockDim.x) {
@@ -197,7 +203,7 @@ pack_weights_tf32_kernel(const float *__restrict__ w, float *__restrict__ wpack,
         const int tap = kb / kc_blocks, cb = kb - tap * kc_blocks;
         const int row_c = dgrad ? cin : cout;
         const int k_c = dgrad ? cout : cin;
-        const int wtap = dgrad ? kk - 1 - tap : tap;
+        const int wtap = taps.idx[tap];
         float v[4];
 #pragma unroll
         for (int e = 0; e < 4; ++e) {
@@ -223,7 +229,10 @@ struct FwdParams {
     int act, accumulate;
     int src_c, dst_c, batch;
     int out_w, out_h;     // output plane as the kernel sees it (DIRECT: (H*W, 1))
-    int ks, pad, stride;
+    int ksh, ksw, pad_h, pad_w, stride;   // tap window (rows x columns) and its leading pads
+    // output scatter: logical position (oh, ow) lands at (oh * o_s + o_oy, ow * o_s + o_ox) of a
+    // plane dst_w wide holding dst_plane elements (strided-dgrad classes; 1 / 0 / 0 otherwise)
+    int o_s, o_oy, o_ox, dst_w, dst_plane;
     int kc_blocks, k_blocks, n_tile, n_tiles, stages;
     // DIRECT: tile = wc column chunks of 32 x rows output rows (wc * rows == 4), one image
     int wc, rows;
@@ -332,8 +341,8 @@ conv_tma_fwd_kernel(const __grid_constant__ CUtensorMap tm_src, const FwdParams 
                 const TileCoord c = decode_tile<NHWC>(p, tile);
                 const float *wtile = p.wpack + (size_t)c.tile_n * p.k_blocks * n_tile * BLOCK_K;
                 int kb = 0;
-                for (int kh = 0; kh < p.ks; ++kh) {
-                    for (int kw = 0; kw < p.ks; ++kw) {
+                for (int kh = 0; kh < p.ksh; ++kh) {
+                    for (int kw = 0; kw < p.ksw; ++kw) {
                         for (int cb = 0; cb < p.kc_blocks; ++cb, ++kb, ++it) {
                             const uint32_t s = it % (uint32_t)S;
                             mbar_wait(smem_u32(empty + s), ((it / (uint32_t)S) & 1) ^ 1);
@@ -342,13 +351,13 @@ conv_tma_fwd_kernel(const __grid_constant__ CUtensorMap tm_src, const FwdParams 
                             mbar_expect_tx(fb, tx_bytes);
                             if (NHWC) {
                                 tma_load_4d(smem_u32(a_stage), &tm_src, cb * BLOCK_K,
-                                            c.w0 * p.stride + kw - p.pad, c.h0 * p.stride + kh - p.pad,
-                                            c.img, fb);
+                                            c.w0 * p.stride + kw - p.pad_w,
+                                            c.h0 * p.stride + kh - p.pad_h, c.img, fb);
                             } else {
                                 for (int a = 0; a < 4; ++a) {  // atom a = (column chunk, row) of the tile
                                     const int wci = a / p.rows, r = a - wci * p.rows;
                                     tma_load_4d(smem_u32(a_stage + a * ATOM_BYTES), &tm_src,
-                                                c.w0 + wci * 32 + kw - p.pad, c.h0 + r + kh - p.pad,
+                                                c.w0 + wci * 32 + kw - p.pad_w, c.h0 + r + kh - p.pad_h,
                                                 cb * BLOCK_K, c.img, fb);
                                 }
                             }
@@ -395,7 +404,7 @@ conv_tma_fwd_kernel(const __grid_constant__ CUtensorMap tm_src, const FwdParams 
         const int ew = warp - 2;
         const int q = warp & 3;
         const int half = ew >> 2;
-        const uint32_t plane = (uint32_t)(p.out_w * p.out_h);
+        const uint32_t plane = (uint32_t)p.dst_plane;
         const int chunks32 = (n_tile + 31) / 32;
         // position of this thread's tile row relative to the tile origin
         int rw, rh, rn;
@@ -415,7 +424,8 @@ conv_tma_fwd_kernel(const __grid_constant__ CUtensorMap tm_src, const FwdParams 
             const int ow = c.w0 + rw, oh = c.h0 + rh, img = c.img + rn;
             bool valid = ow < p.out_w && oh < p.out_h && img < p.batch;
             if (NHWC) valid = valid && rn < p.tn;
-            float *dst = p.dst + (size_t)img * p.dst_c * plane + (size_t)oh * p.out_w + ow;
+            float *dst = p.dst + (size_t)img * p.dst_c * plane +
+                         (size_t)(oh * p.o_s + p.o_oy) * p.dst_w + (ow * p.o_s + p.o_ox);
             if (lane == 0) mbar_wait(smem_u32(acc_full + buf), use & 1);
             __syncwarp();
             tc_fence_after();
@@ -460,6 +470,17 @@ conv_tma_fwd_kernel(const __grid_constant__ CUtensorMap tm_src, const FwdParams 
     if (warp == 1) tmem_dealloc(tmem_base, tmem_cols);
 }
 
+// One launch of conv_tma_fwd_kernel: a stride-`stride` correlation of a ksh x ksw tap window
+// over the source tensor (sh x sw, src_c channels), producing dh x dw logical positions of
+// dst_c channels that are scattered into the destination plane.
+struct FwdGeom {
+    int batch, src_c, sh, sw;
+    int dst_c, dh, dw;
+    int ksh, ksw, pad_h, pad_w, stride;
+    int o_s, o_oy, o_ox, dst_w, dst_plane;
+    bool direct;   // source may be read in place through the NCHW map
+};
+
 struct FwdPlan {
     bool nhwc;
     int n_tile, n_tiles, kc_blocks, k_blocks, stages;
@@ -487,24 +508,27 @@ bool nhwc_disabled() {
     }
     return v == 1;
 }
+bool env_off(const char *name) {
+    const char *e = getenv(name);
+    return e && e[0] && e[0] != '0';
+}
 
 size_t align256(size_t b) { return (b + 255) & ~(size_t)255; }
 
-// Geometry shared by fprop (src = x) and stride-1 dgrad (src = dy): src plane (sh, sw) with
-// src_c channels -> dst plane (dh, dw) with dst_c channels.
-bool plan_fwd(int batch, int src_c, int sh, int sw, int dst_c, int dh, int dw, int ks, int stride,
-              int pad, FwdPlan *pl) {
-    if (src_c < 16) return false;  // K too thin (first layers): SIMT kernel
-    const bool direct = ks == 1 && stride == 1 && pad == 0 && (sh * sw) % 4 == 0;
+bool plan_fwd(const FwdGeom &g, FwdPlan *pl) {
+    if (g.src_c < 16) return false;  // K too thin: im2col route or SIMT kernel
+    const bool direct = g.direct && g.ksh == 1 && g.ksw == 1 && g.stride == 1 && g.pad_h == 0 &&
+                        g.pad_w == 0 && g.o_s == 1 && (g.sh * g.sw) % 4 == 0;
     pl->nhwc = !direct;
-    if (!direct && (nhwc_disabled() || src_c % 4 != 0 || stride > 4)) return false;
+    if (!direct && (nhwc_disabled() || g.src_c % 4 != 0 || g.stride > 4)) return false;
+    if (g.ksh * g.ksw > 64) return false;   // TapMap capacity
     static int nmax = 0;
     if (!nmax) {
         const char *e = getenv("BCNN_B200_FWD_NMAX");
         nmax = e ? atoi(e) : 256;
         if (nmax < 16 || nmax > 256) nmax = 256;
     }
-    int n = dst_c;
+    int n = g.dst_c;
     if (n > nmax) {
         int tiles = ceil_div(n, nmax);
         n = ceil_div(ceil_div(n, tiles), 16) * 16;
@@ -512,45 +536,45 @@ bool plan_fwd(int batch, int src_c, int sh, int sw, int dst_c, int dh, int dw, i
         n = ceil_div(n, 16) * 16;
     }
     pl->n_tile = n;
-    pl->n_tiles = ceil_div(dst_c, n);
-    pl->kc_blocks = ceil_div(src_c, BLOCK_K);
-    pl->k_blocks = ks * ks * pl->kc_blocks;
+    pl->n_tiles = ceil_div(g.dst_c, n);
+    pl->kc_blocks = ceil_div(g.src_c, BLOCK_K);
+    pl->k_blocks = g.ksh * g.ksw * pl->kc_blocks;
     pl->wc = pl->rows = 1; pl->tw = pl->th = pl->tn = 1;
     if (direct) {
-        pl->view_w = sh * sw; pl->view_h = 1;
-        pl->out_w = dh * dw; pl->out_h = 1;
+        pl->view_w = g.sh * g.sw; pl->view_h = 1;
+        pl->out_w = g.dh * g.dw; pl->out_h = 1;
         const int chunks = ceil_div(pl->out_w, 32);
         pl->wc = chunks >= 4 ? 4 : (chunks >= 2 ? 2 : 1);
         pl->rows = 4 / pl->wc;
         pl->tiles_w = ceil_div(chunks, pl->wc);
         pl->tiles_h = ceil_div(pl->out_h, pl->rows);
-        pl->tiles_b = batch;
+        pl->tiles_b = g.batch;
         pl->a_bytes = A_STAGE_BYTES;
         pl->shadow_bytes = 0;
     } else {
-        pl->view_w = sw; pl->view_h = sh;
-        pl->out_w = dw; pl->out_h = dh;
+        pl->view_w = g.sw; pl->view_h = g.sh;
+        pl->out_w = g.dw; pl->out_h = g.dh;
         // tile = tw x th x tn output positions, <= 128 rows, TMA box dims <= 256
-        int tw = dw < 128 ? dw : 128;
-        while (tw * stride > 256) --tw;
-        const int tiles_w = ceil_div(dw, tw);
-        tw = ceil_div(dw, tiles_w);  // balanced
+        int tw = g.dw < 128 ? g.dw : 128;
+        while (tw * g.stride > 256) --tw;
+        const int tiles_w = ceil_div(g.dw, tw);
+        tw = ceil_div(g.dw, tiles_w);  // balanced
         int th_max = 128 / tw;
         if (th_max < 1) th_max = 1;
-        while (th_max * stride > 256) --th_max;
-        int th = dh < th_max ? dh : th_max;
-        const int tiles_h = ceil_div(dh, th);
-        th = ceil_div(dh, tiles_h);
+        while (th_max * g.stride > 256) --th_max;
+        int th = g.dh < th_max ? g.dh : th_max;
+        const int tiles_h = ceil_div(g.dh, th);
+        th = ceil_div(g.dh, tiles_h);
         int tn = 1;
         if (tiles_w == 1 && tiles_h == 1) {
             tn = 128 / (tw * th);
-            if (tn > batch) tn = batch;
+            if (tn > g.batch) tn = g.batch;
             if (tn < 1) tn = 1;
         }
         pl->tw = tw; pl->th = th; pl->tn = tn;
-        pl->tiles_w = tiles_w; pl->tiles_h = tiles_h; pl->tiles_b = ceil_div(batch, tn);
+        pl->tiles_w = tiles_w; pl->tiles_h = tiles_h; pl->tiles_b = ceil_div(g.batch, tn);
         pl->a_bytes = (uint32_t)(tw * th * tn * 128);
-        pl->shadow_bytes = align256((size_t)batch * src_c * sh * sw * sizeof(float));
+        pl->shadow_bytes = align256((size_t)g.batch * g.src_c * g.sh * g.sw * sizeof(float));
     }
     const int stage = A_STAGE_BYTES + n * BLOCK_K * 4;
     int stages = (200 * 1024) / stage;  // persistent: one CTA per SM owns the shared memory
@@ -563,15 +587,112 @@ bool plan_fwd(int batch, int src_c, int sh, int sw, int dst_c, int dh, int dw, i
     return total < (1LL << 31);
 }
 
-bool plan_fwd_desc(const bcnn_b200_conv_desc *d, bool dgrad, FwdPlan *pl) {
-    if (tma_disabled() || !encode_fn()) return false;
-    if (d->groups != 1) return false;
-    if (dgrad) {
-        if (d->stride != 1 || d->pad > d->ksize - 1) return false;
-        return plan_fwd(d->batch, d->cout, d->ho, d->wo, d->cin, d->h, d->w, d->ksize, 1,
-                        d->ksize - 1 - d->pad, pl);
+// ---- how a (descriptor, pass) maps onto launches of the kernel
+enum FwdRoute { ROUTE_NONE = 0, ROUTE_PLAIN, ROUTE_IM2COL, ROUTE_STRIDED_DGRAD };
+
+// Thin first layers (Cin = 3): an explicit im2col buffer [n, ho, wo, Kp] (Kp = Cin * k * k rounded
+// up to 4 floats) is an NHWC tensor with Kp channels; over it the convolution is 1x1.
+int im2col_kp(const bcnn_b200_conv_desc *d) { return ceil_div(d->cin * d->ksize * d->ksize, 4) * 4; }
+bool im2col_shape(const bcnn_b200_conv_desc *d) {
+    static int off = -1;
+    if (off < 0) off = env_off("BCNN_B200_NO_IM2COL") ? 1 : 0;
+    return !off && d->groups == 1 && d->cin < 16 && d->cin * d->ksize * d->ksize >= 24 &&
+           d->cout >= 16 && (long long)d->batch * d->ho * d->wo >= 4096;
+}
+
+FwdGeom geom_plain(const bcnn_b200_conv_desc *d, bool dgrad) {
+    FwdGeom g;
+    g.batch = d->batch;
+    if (dgrad) {  // stride 1: correlation of dy with the flipped filter, pad' = k - 1 - pad
+        g.src_c = d->cout; g.sh = d->ho; g.sw = d->wo;
+        g.dst_c = d->cin; g.dh = d->h; g.dw = d->w;
+        g.pad_h = g.pad_w = d->ksize - 1 - d->pad;
+        g.stride = 1;
+    } else {
+        g.src_c = d->cin; g.sh = d->h; g.sw = d->w;
+        g.dst_c = d->cout; g.dh = d->ho; g.dw = d->wo;
+        g.pad_h = g.pad_w = d->pad;
+        g.stride = d->stride;
     }
-    return plan_fwd(d->batch, d->cin, d->h, d->w, d->cout, d->ho, d->wo, d->ksize, d->stride, d->pad, pl);
+    g.ksh = g.ksw = d->ksize;
+    g.o_s = 1; g.o_oy = g.o_ox = 0; g.dst_w = g.dw; g.dst_plane = g.dh * g.dw;
+    g.direct = true;
+    return g;
+}
+
+FwdGeom geom_im2col(const bcnn_b200_conv_desc *d) {
+    FwdGeom g;
+    g.batch = d->batch;
+    g.src_c = im2col_kp(d); g.sh = d->ho; g.sw = d->wo;
+    g.dst_c = d->cout; g.dh = d->ho; g.dw = d->wo;
+    g.ksh = g.ksw = 1; g.pad_h = g.pad_w = 0; g.stride = 1;
+    g.o_s = 1; g.o_oy = g.o_ox = 0; g.dst_w = g.dw; g.dst_plane = g.dh * g.dw;
+    g.direct = false;
+    return g;
+}
+
+// Strided dgrad, class (ph, pw) of input positions (h, w) = (s * i + ph, s * j + pw):
+//   dx[h] = sum over kh with (ph + pad - kh) % s == 0 of W[kh] * dy[i + (ph + pad - kh) / s]
+// i.e. a stride-1 correlation of dy with the sub-sampled filter. Along one axis the class has
+// `n` taps; sub-tap t reads dy[i - lead + t] and uses filter tap kfirst - s * t.
+struct ClassAxis { int n, lead, kfirst, extent; };
+ClassAxis class_axis(int ph, int s, int pad, int k, int in_extent) {
+    ClassAxis a;
+    const int k0 = (ph + pad) % s;                 // smallest matching filter tap
+    a.n = k0 < k ? (k - 1 - k0) / s + 1 : 0;
+    const int k_last = k0 + s * (a.n - 1);         // largest matching filter tap: smallest offset
+    const int q_min = (ph + pad - k_last) / s;     // exact division by construction
+    a.lead = -q_min;
+    a.kfirst = k_last;
+    a.extent = ph < in_extent ? (in_extent - ph + s - 1) / s : 0;
+    return a;
+}
+
+FwdGeom geom_dgrad_class(const bcnn_b200_conv_desc *d, const ClassAxis &ah, const ClassAxis &aw, int ph,
+                         int pw) {
+    FwdGeom g;
+    g.batch = d->batch;
+    g.src_c = d->cout; g.sh = d->ho; g.sw = d->wo;
+    g.dst_c = d->cin; g.dh = ah.extent; g.dw = aw.extent;
+    g.ksh = ah.n; g.ksw = aw.n; g.pad_h = ah.lead; g.pad_w = aw.lead; g.stride = 1;
+    g.o_s = d->stride; g.o_oy = ph; g.o_ox = pw; g.dst_w = d->w; g.dst_plane = d->h * d->w;
+    g.direct = false;
+    return g;
+}
+
+bool strided_dgrad_shape(const bcnn_b200_conv_desc *d) {
+    static int off = -1;
+    if (off < 0) off = env_off("BCNN_B200_NO_STRIDED_DGRAD") ? 1 : 0;
+    return !off && d->groups == 1 && d->stride > 1 && d->stride <= 4 && d->ksize <= 8 &&
+           d->pad < d->ksize && d->cout % 4 == 0 && d->cout >= 16;
+}
+
+// Workspace bytes of the strided-dgrad route (0 = not applicable): dy shadow + all class packs.
+size_t strided_dgrad_bytes(const bcnn_b200_conv_desc *d) {
+    if (!strided_dgrad_shape(d)) return 0;
+    size_t shadow = 0, packs = 0;
+    for (int ph = 0; ph < d->stride; ++ph)
+        for (int pw = 0; pw < d->stride; ++pw) {
+            const ClassAxis ah = class_axis(ph, d->stride, d->pad, d->ksize, d->h);
+            const ClassAxis aw = class_axis(pw, d->stride, d->pad, d->ksize, d->w);
+            if (ah.n == 0 || aw.n == 0 || ah.extent == 0 || aw.extent == 0) continue;
+            FwdPlan pl;
+            if (!plan_fwd(geom_dgrad_class(d, ah, aw, ph, pw), &pl)) return 0;
+            shadow = pl.shadow_bytes;
+            packs += pl.wpack_bytes;
+        }
+    return shadow + packs;
+}
+
+FwdRoute route_fwd(const bcnn_b200_conv_desc *d, bool dgrad, FwdPlan *pl) {
+    if (tma_disabled() || !encode_fn() || d->groups != 1) return ROUTE_NONE;
+    if (dgrad) {
+        if (d->stride != 1) return strided_dgrad_bytes(d) ? ROUTE_STRIDED_DGRAD : ROUTE_NONE;
+        if (d->pad > d->ksize - 1) return ROUTE_NONE;
+        return plan_fwd(geom_plain(d, true), pl) ? ROUTE_PLAIN : ROUTE_NONE;
+    }
+    if (im2col_shape(d)) return plan_fwd(geom_im2col(d), pl) ? ROUTE_IM2COL : ROUTE_NONE;
+    return plan_fwd(geom_plain(d, false), pl) ? ROUTE_PLAIN : ROUTE_NONE;
 }
 
 template <bool NHWC>
@@ -588,42 +709,23 @@ int launch_fwd_kernel(const CUtensorMap &tm, const FwdParams &p, size_t smem, cu
     return launched();
 }
 
-int launch_fwd(const bcnn_b200_conv_desc *d, bool dgrad, const float *src, const float *w,
-               const float *bias, int act, float *dst, int accumulate, void *workspace,
-               size_t workspace_bytes, cudaStream_t st) {
-    FwdPlan pl;
-    if (!plan_fwd_desc(d, dgrad, &pl)) return (int)cudaErrorInvalidValue;
-    const int src_c = dgrad ? d->cout : d->cin, dst_c = dgrad ? d->cin : d->cout;
-    const int sh = dgrad ? d->ho : d->h, sw = dgrad ? d->wo : d->w;
-    if (workspace == nullptr || workspace_bytes < pl.shadow_bytes + pl.wpack_bytes)
-        return (int)cudaErrorInvalidValue;
-    if ((reinterpret_cast<uintptr_t>(src) & 15) != 0 || (reinterpret_cast<uintptr_t>(workspace) & 255) != 0)
-        return (int)cudaErrorMisalignedAddress;
-    float *shadow = reinterpret_cast<float *>(workspace);
-    float *wpack = reinterpret_cast<float *>(reinterpret_cast<uint8_t *>(workspace) + pl.shadow_bytes);
-    const int kk = d->ksize * d->ksize;
-    const size_t chunks = (size_t)pl.n_tiles * pl.n_tile * pl.k_blocks * 8;
-    pack_weights_tf32_kernel<<<stream_grid(chunks, 256), 256, 0, st>>>(
-        w, wpack, dgrad ? 1 : 0, d->cout, d->cin, kk, pl.n_tile, pl.n_tiles, pl.kc_blocks);
-    int err = launched();
-    if (err) return err;
-
+// src: the NCHW tensor (DIRECT plans) or the NHWC-shaped shadow (all others).
+int run_fwd(const FwdGeom &g, const FwdPlan &pl, const float *src, const float *wpack, const float *bias,
+            int act, float *dst, int accumulate, cudaStream_t st) {
     CUtensorMap tm;
     if (pl.nhwc) {
-        err = launch_transpose(src, shadow, d->batch, src_c, sh * sw, st);
-        if (err) return err;
-        if (!make_map_nhwc(&tm, shadow, src_c, sw, sh, d->batch, pl.tw, pl.th, pl.tn,
-                           dgrad ? 1 : d->stride, false))
+        if (!make_map_nhwc(&tm, src, g.src_c, g.sw, g.sh, g.batch, pl.tw, pl.th, pl.tn, g.stride, false))
             return (int)cudaErrorInvalidValue;
-    } else if (!make_map_nchw(&tm, src, pl.view_w, pl.view_h, src_c, d->batch, BLOCK_K, true)) {
+    } else if (!make_map_nchw(&tm, src, pl.view_w, pl.view_h, g.src_c, g.batch, BLOCK_K, true)) {
         return (int)cudaErrorInvalidValue;
     }
     FwdParams p;
     p.dst = dst; p.bias = bias; p.wpack = wpack; p.act = act; p.accumulate = accumulate;
-    p.src_c = src_c; p.dst_c = dst_c; p.batch = d->batch;
+    p.src_c = g.src_c; p.dst_c = g.dst_c; p.batch = g.batch;
     p.out_w = pl.out_w; p.out_h = pl.out_h;
-    p.ks = d->ksize; p.pad = dgrad ? d->ksize - 1 - d->pad : d->pad;
-    p.stride = dgrad ? 1 : d->stride;
+    p.ksh = g.ksh; p.ksw = g.ksw; p.pad_h = g.pad_h; p.pad_w = g.pad_w; p.stride = g.stride;
+    p.o_s = g.o_s; p.o_oy = g.o_oy; p.o_ox = g.o_ox;
+    p.dst_w = pl.nhwc ? g.dst_w : pl.out_w; p.dst_plane = g.dst_plane;
     p.kc_blocks = pl.kc_blocks; p.k_blocks = pl.k_blocks; p.n_tile = pl.n_tile; p.stages = pl.stages;
     p.n_tiles = pl.n_tiles;
     p.wc = pl.wc; p.rows = pl.rows; p.tw = pl.tw; p.th = pl.th; p.tn = pl.tn;
@@ -638,6 +740,101 @@ int launch_fwd(const bcnn_b200_conv_desc *d, bool dgrad, const float *src, const
     return pl.nhwc ? launch_fwd_kernel<true>(tm, p, pl.smem_bytes, st)
                    : launch_fwd_kernel<false>(tm, p, pl.smem_bytes, st);
 }
+
+int launch_pack(const float *w, float *wpack, bool dgrad, int cout, int cin, int kk, const FwdPlan &pl,
+                const TapMap &taps, cudaStream_t st) {
+    const size_t chunks = (size_t)pl.n_tiles * pl.n_tile * pl.k_blocks * 8;
+    pack_weights_tf32_kernel<<<stream_grid(chunks, 256), 256, 0, st>>>(
+        w, wpack, dgrad ? 1 : 0, cout, cin, kk, pl.n_tile, pl.n_tiles, pl.kc_blocks, taps);
+    return launched();
+}
+
+int launch_im2col(const bcnn_b200_conv_desc *d, const float *x, float *col, cudaStream_t st);
+
+int launch_strided_dgrad(const bcnn_b200_conv_desc *d, const float *dy, const float *w, float *dx,
+                         int accumulate, void *workspace, size_t workspace_bytes, cudaStream_t st) {
+    const size_t need = strided_dgrad_bytes(d);
+    if (!need || workspace == nullptr || workspace_bytes < need) return (int)cudaErrorInvalidValue;
+    if ((reinterpret_cast<uintptr_t>(workspace) & 255) != 0) return (int)cudaErrorMisalignedAddress;
+    float *shadow = reinterpret_cast<float *>(workspace);
+    int err = launch_transpose(dy, shadow, d->batch, d->cout, d->ho * d->wo, st);
+    if (err) return err;
+    const int s = d->stride, kk = d->ksize * d->ksize;
+    // classes without taps (e.g. 1x1 stride 2: three of four) receive no gradient
+    bool holes = false;
+    for (int ph = 0; ph < s; ++ph)
+        for (int pw = 0; pw < s; ++pw)
+            if (class_axis(ph, s, d->pad, d->ksize, d->h).n == 0 ||
+                class_axis(pw, s, d->pad, d->ksize, d->w).n == 0)
+                holes = true;
+    if (holes && !accumulate) {
+        cudaError_t e = cudaMemsetAsync(dx, 0, (size_t)d->batch * d->cin * d->h * d->w * sizeof(float), st);
+        if (e != cudaSuccess) return (int)e;
+    }
+    size_t off = 0;
+    bool have_shadow_bytes = false;
+    for (int ph = 0; ph < s; ++ph)
+        for (int pw = 0; pw < s; ++pw) {
+            const ClassAxis ah = class_axis(ph, s, d->pad, d->ksize, d->h);
+            const ClassAxis aw = class_axis(pw, s, d->pad, d->ksize, d->w);
+            if (ah.n == 0 || aw.n == 0 || ah.extent == 0 || aw.extent == 0) continue;
+            const FwdGeom g = geom_dgrad_class(d, ah, aw, ph, pw);
+            FwdPlan pl;
+            if (!plan_fwd(g, &pl)) return (int)cudaErrorInvalidValue;
+            if (!have_shadow_bytes) { off = pl.shadow_bytes; have_shadow_bytes = true; }
+            float *wpack = reinterpret_cast<float *>(reinterpret_cast<uint8_t *>(workspace) + off);
+            off += pl.wpack_bytes;
+            TapMap taps;
+            taps.n = ah.n * aw.n;
+            for (int th = 0; th < ah.n; ++th)
+                for (int tw = 0; tw < aw.n; ++tw)
+                    taps.idx[th * aw.n + tw] = (short)((ah.kfirst - s * th) * d->ksize + (aw.kfirst - s * tw));
+            err = launch_pack(w, wpack, true, d->cout, d->cin, kk, pl, taps, st);
+            if (err) return err;
+            err = run_fwd(g, pl, shadow, wpack, nullptr, 0, dx, accumulate, st);
+            if (err) return err;
+        }
+    return 0;
+}
+
+int launch_fwd(const bcnn_b200_conv_desc *d, bool dgrad, const float *src, const float *w,
+               const float *bias, int act, float *dst, int accumulate, void *workspace,
+               size_t workspace_bytes, cudaStream_t st) {
+    FwdPlan pl;
+    const FwdRoute route = route_fwd(d, dgrad, &pl);
+    if (route == ROUTE_NONE) return (int)cudaErrorInvalidValue;
+    if ((reinterpret_cast<uintptr_t>(src) & 15) != 0) return (int)cudaErrorMisalignedAddress;
+    if (route == ROUTE_STRIDED_DGRAD)
+        return launch_strided_dgrad(d, src, w, dst, accumulate, workspace, workspace_bytes, st);
+    if (workspace == nullptr || workspace_bytes < pl.shadow_bytes + pl.wpack_bytes)
+        return (int)cudaErrorInvalidValue;
+    if ((reinterpret_cast<uintptr_t>(workspace) & 255) != 0) return (int)cudaErrorMisalignedAddress;
+    float *shadow = reinterpret_cast<float *>(workspace);
+    float *wpack = reinterpret_cast<float *>(reinterpret_cast<uint8_t *>(workspace) + pl.shadow_bytes);
+    const int kk = d->ksize * d->ksize;
+    TapMap taps;
+    int err;
+    if (route == ROUTE_IM2COL) {
+        // W [cout][cin * kk] is already the K-major matrix of the 1x1 problem
+        taps.n = 1; taps.idx[0] = 0;
+        err = launch_pack(w, wpack, false, d->cout, d->cin * kk, 1, pl, taps, st);
+        if (err) return err;
+        err = launch_im2col(d, src, shadow, st);
+        if (err) return err;
+        return run_fwd(geom_im2col(d), pl, shadow, wpack, bias, act, dst, accumulate, st);
+    }
+    taps.n = kk;
+    for (int t = 0; t < kk; ++t) taps.idx[t] = (short)(dgrad ? kk - 1 - t : t);
+    err = launch_pack(w, wpack, dgrad, d->cout, d->cin, kk, pl, taps, st);
+    if (err) return err;
+    const FwdGeom g = geom_plain(d, dgrad);
+    if (pl.nhwc) {
+        err = launch_transpose(src, shadow, g.batch, g.src_c, g.sh * g.sw, st);
+        if (err) return err;
+    }
+    return run_fwd(g, pl, pl.nhwc ? shadow : src, wpack, bias, act, dst, accumulate, st);
+}
+
 
 // ------------------------------------------------------------------ wgrad
 struct WgParams {
@@ -797,14 +994,39 @@ struct WgPlan {
     size_t smem_bytes, partial_bytes, shadow_x_bytes, shadow_dy_bytes;
 };
 
-bool plan_wgrad(const bcnn_b200_conv_desc *d, WgPlan *pl) {
+// The wgrad problem the kernel sees. Thin first layers go through the im2col buffer: a 1x1
+// problem whose "input channels" are the Cin * k * k patch elements (cin = logical count and
+// leading dimension of gw, cin_phys = channels of the buffer, a multiple of 4).
+struct WgEff {
+    int batch, cin, cin_phys, h, w, cout, ho, wo, ksize, stride, pad;
+    bool im2col;
+};
+WgEff wg_effective(const bcnn_b200_conv_desc *d) {
+    WgEff e;
+    e.batch = d->batch; e.cout = d->cout; e.ho = d->ho; e.wo = d->wo;
+    e.im2col = im2col_shape(d);
+    if (e.im2col) {
+        e.cin = d->cin * d->ksize * d->ksize; e.cin_phys = im2col_kp(d);
+        e.h = d->ho; e.w = d->wo; e.ksize = 1; e.stride = 1; e.pad = 0;
+    } else {
+        e.cin = e.cin_phys = d->cin; e.h = d->h; e.w = d->w;
+        e.ksize = d->ksize; e.stride = d->stride; e.pad = d->pad;
+    }
+    return e;
+}
+
+bool plan_wgrad(const bcnn_b200_conv_desc *desc, WgPlan *pl) {
     if (tma_disabled() || !encode_fn()) return false;
-    if (d->groups != 1) return false;
+    if (desc->groups != 1) return false;
+    const WgEff e = wg_effective(desc);
+    const WgEff *d = &e;
     if (d->cin < 16 || d->cout < 32) return false;
     if ((long long)d->batch * d->ho * d->wo < 512) return false;  // tiny reductions (fc-shaped)
-    const bool direct = d->ksize == 1 && d->stride == 1 && d->pad == 0 && (d->h * d->w) % 4 == 0;
+    const bool direct = !d->im2col && d->ksize == 1 && d->stride == 1 && d->pad == 0 &&
+                        (d->h * d->w) % 4 == 0;
     pl->nhwc = !direct;
-    if (!direct && (nhwc_disabled() || d->cin % 4 != 0 || d->cout % 4 != 0 || d->stride > 4)) return false;
+    if (!direct && (nhwc_disabled() || d->cin_phys % 4 != 0 || d->cout % 4 != 0 || d->stride > 4))
+        return false;
     int n = d->cin;
     if (n > 128) {
         int tiles = ceil_div(n, 128);
@@ -839,26 +1061,37 @@ bool plan_wgrad(const bcnn_b200_conv_desc *d, WgPlan *pl) {
         pl->atom_bytes = (uint32_t)(bw * bh * 128);
         pl->a_bytes = 4 * pl->atom_bytes;
         pl->stage_bytes = (uint32_t)(4 + pl->nb) * pl->atom_bytes;
-        pl->shadow_x_bytes = align256((size_t)d->batch * d->cin * d->h * d->w * sizeof(float));
+        pl->shadow_x_bytes = align256((size_t)d->batch * d->cin_phys * d->h * d->w * sizeof(float));
         pl->shadow_dy_bytes = align256((size_t)d->batch * d->cout * d->ho * d->wo * sizeof(float));
     }
     const long long kb_total = (long long)d->batch * pl->blocks_h * pl->blocks_w;
     if (kb_total >= (1LL << 31)) return false;
     pl->kb_total = (int)kb_total;
+    // Shared memory: two co-resident CTAs per SM (one's epilogue under the other's main loop)
+    // when three stages fit in half the SM, else one CTA per SM.
+    int ctas_per_sm = 1;
+    int stages = (int)((100u * 1024u) / pl->stage_bytes);
+    if (stages >= 3) {
+        ctas_per_sm = 2;
+        if (stages > 4) stages = 4;
+    } else {
+        stages = (int)((200u * 1024u) / pl->stage_bytes);
+        if (stages > 6) stages = 6;
+        if (stages < 2) return false;
+    }
+    pl->stages = stages;
+    pl->smem_bytes = (size_t)stages * pl->stage_bytes + 1024 + 256;
+    // Split-K so that the whole grid is ONE resident wave (a partial extra wave costs a full
+    // CTA lifetime): floor, never above ctas_per_sm * SMs unless the tile count alone exceeds it.
     const int kk = d->ksize * d->ksize;
     const long long tiles = (long long)pl->ci_tiles * pl->co_tiles * kk;
-    long long want = (2LL * sm_count() + tiles - 1) / tiles;
+    long long want = ((long long)ctas_per_sm * sm_count()) / tiles;
     long long max_by_k = pl->kb_total / 16;  // >= 16 k-blocks per split
     if (want > max_by_k) want = max_by_k;
     if (want > 256) want = 256;
     if (want < 1) want = 1;
     pl->kb_per_split = ceil_div(pl->kb_total, (int)want);
     pl->splits = ceil_div(pl->kb_total, pl->kb_per_split);
-    int stages = (int)((200u * 1024u) / pl->stage_bytes);
-    if (stages > 6) stages = 6;
-    if (stages < 2) return false;
-    pl->stages = stages;
-    pl->smem_bytes = (size_t)stages * pl->stage_bytes + 1024 + 256;
     const size_t wsize = (size_t)d->cout * d->cin * kk;
     pl->partial_bytes = pl->splits > 1 ? align256((size_t)pl->splits * wsize * sizeof(float)) : 0;
     return true;
@@ -878,17 +1111,59 @@ int launch_wgrad_kernel(const CUtensorMap &tm_dy, const CUtensorMap &tm_x, const
     return launched();
 }
 
+// ------------------------------------------------------------------ im2col for thin first layers
+// col[n][oh][ow][k], k = (ci * ks + kh) * ks + kw fastest (the order of W[co][ci][kh][kw]), padded
+// with zeros to kp = 4 * kp4 columns. One thread writes one float4; a warp covers 512 contiguous
+// bytes of the buffer and gathers from a few image rows that stay in L1.
+__global__ void __launch_bounds__(256)
+im2col_nhwc_kernel(const float *__restrict__ x, float *__restrict__ col, int cin, int h, int w, int ks,
+                   int stride, int pad, int kdim, uint32_t total4, FastDiv d_kp4, FastDiv d_wo,
+                   FastDiv d_ho, FastDiv d_ks, FastDiv d_kk) {
+    const uint32_t gstride = gridDim.x * blockDim.x;
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < total4; i += gstride) {
+        uint32_t pos, q4, t, ow, n, oh;
+        d_kp4.divmod(i, pos, q4);
+        d_wo.divmod(pos, t, ow);
+        d_ho.divmod(t, n, oh);
+        const float *xn = x + (size_t)n * cin * h * w;
+        const int ih0 = (int)oh * stride - pad, iw0 = (int)ow * stride - pad;
+        float v[4];
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+            const uint32_t k = q4 * 4 + e;
+            uint32_t ci, r, kh, kw;
+            d_kk.divmod(k, ci, r);
+            d_ks.divmod(r, kh, kw);
+            const int ih = ih0 + (int)kh, iw = iw0 + (int)kw;
+            const bool ok = k < (uint32_t)kdim && ih >= 0 && ih < h && iw >= 0 && iw < w;
+            v[e] = ok ? __ldg(xn + ((size_t)ci * h + ih) * w + iw) : 0.f;
+        }
+        *reinterpret_cast<float4 *>(col + (size_t)i * 4) = make_float4(v[0], v[1], v[2], v[3]);
+    }
+}
+
+int launch_im2col(const bcnn_b200_conv_desc *d, const float *x, float *col, cudaStream_t st) {
+    const int kk = d->ksize * d->ksize, kp = im2col_kp(d);
+    const size_t total4 = (size_t)d->batch * d->ho * d->wo * (kp / 4);
+    if (total4 >= (1ull << 31)) return (int)cudaErrorInvalidValue;
+    im2col_nhwc_kernel<<<stream_grid(total4, 256, 16), 256, 0, st>>>(
+        x, col, d->cin, d->h, d->w, d->ksize, d->stride, d->pad, d->cin * kk, (uint32_t)total4,
+        FastDiv((uint32_t)(kp / 4)), FastDiv((uint32_t)d->wo), FastDiv((uint32_t)d->ho),
+        FastDiv((uint32_t)d->ksize), FastDiv((uint32_t)kk));
+    return launched();
+}
+
 }  // namespace
 
 namespace b200 {
 
 bool conv_tma_supports_fprop(const bcnn_b200_conv_desc *d) {
     FwdPlan pl;
-    return plan_fwd_desc(d, false, &pl);
+    return route_fwd(d, false, &pl) != ROUTE_NONE;
 }
 bool conv_tma_supports_dgrad(const bcnn_b200_conv_desc *d) {
     FwdPlan pl;
-    return plan_fwd_desc(d, true, &pl);
+    return route_fwd(d, true, &pl) != ROUTE_NONE;
 }
 bool conv_tma_supports_wgrad(const bcnn_b200_conv_desc *d) {
     WgPlan pl;
@@ -898,9 +1173,13 @@ bool conv_tma_supports_wgrad(const bcnn_b200_conv_desc *d) {
 size_t conv_tma_workspace_bytes(const bcnn_b200_conv_desc *d) {
     size_t need = 0;
     FwdPlan pl;
-    if (plan_fwd_desc(d, false, &pl)) need = pl.shadow_bytes + pl.wpack_bytes;
-    if (plan_fwd_desc(d, true, &pl) && pl.shadow_bytes + pl.wpack_bytes > need)
-        need = pl.shadow_bytes + pl.wpack_bytes;
+    for (int dgrad = 0; dgrad < 2; ++dgrad) {
+        const FwdRoute r = route_fwd(d, dgrad != 0, &pl);
+        size_t b = 0;
+        if (r == ROUTE_STRIDED_DGRAD) b = strided_dgrad_bytes(d);
+        else if (r != ROUTE_NONE) b = pl.shadow_bytes + pl.wpack_bytes;
+        if (b > need) need = b;
+    }
     WgPlan wp;
     if (plan_wgrad(d, &wp)) {
         const size_t w = wp.shadow_x_bytes + wp.shadow_dy_bytes + wp.partial_bytes;
@@ -919,10 +1198,12 @@ int conv_tma_backward_data(const bcnn_b200_conv_desc *d, const float *w, const f
     return launch_fwd(d, true, dy, w, nullptr, 0, dx, accumulate, workspace, workspace_bytes, st);
 }
 
-int conv_tma_backward_weights(const bcnn_b200_conv_desc *d, const float *x, const float *dy, float *gw,
+int conv_tma_backward_weights(const bcnn_b200_conv_desc *desc, const float *x, const float *dy, float *gw,
                               void *workspace, size_t workspace_bytes, cudaStream_t st) {
     WgPlan pl;
-    if (!plan_wgrad(d, &pl)) return (int)cudaErrorInvalidValue;
+    if (!plan_wgrad(desc, &pl)) return (int)cudaErrorInvalidValue;
+    const WgEff e = wg_effective(desc);
+    const WgEff *d = &e;
     const size_t need = pl.shadow_x_bytes + pl.shadow_dy_bytes + pl.partial_bytes;
     if (need > 0 && (workspace == nullptr || workspace_bytes < need)) return (int)cudaErrorInvalidValue;
     if (((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(dy)) & 15) != 0 ||
@@ -935,12 +1216,14 @@ int conv_tma_backward_weights(const bcnn_b200_conv_desc *d, const float *x, cons
     CUtensorMap tm_dy, tm_x;
     int err;
     if (pl.nhwc) {
-        err = launch_transpose(x, x_shadow, d->batch, d->cin, d->h * d->w, st);
+        err = d->im2col ? launch_im2col(desc, x, x_shadow, st)
+                        : launch_transpose(x, x_shadow, d->batch, d->cin, d->h * d->w, st);
         if (err) return err;
         err = launch_transpose(dy, dy_shadow, d->batch, d->cout, d->ho * d->wo, st);
         if (err) return err;
         if (!make_map_nhwc(&tm_dy, dy_shadow, d->cout, d->wo, d->ho, d->batch, pl.bw, pl.bh, 1, 1, true) ||
-            !make_map_nhwc(&tm_x, x_shadow, d->cin, d->w, d->h, d->batch, pl.bw, pl.bh, 1, d->stride, true))
+            !make_map_nhwc(&tm_x, x_shadow, d->cin_phys, d->w, d->h, d->batch, pl.bw, pl.bh, 1, d->stride,
+                           true))
             return (int)cudaErrorInvalidValue;
     } else if (!make_map_nchw(&tm_dy, dy, pl.out_w, pl.out_h, d->cout, d->batch, TILE_M, false) ||
                !make_map_nchw(&tm_x, x, pl.view_w, pl.view_h, d->cin, d->batch, pl.n_tile, false)) {

@@ -87,6 +87,93 @@ maxpool_fwd_k2s2(const float *__restrict__ x, float *__restrict__ y, int *__rest
     }
 }
 
+// ---- forward, 3x3 / stride 2 / w % 8 == 0 (ResNet stem): four outputs per thread. The 3 x 9
+// input patch is read as two float4 + one scalar per row; windows are scanned in the
+// reference's (row, column) order with the strict '>' so ties resolve identically.
+__global__ void __launch_bounds__(256)
+maxpool_fwd_k3s2(const float *__restrict__ x, float *__restrict__ y, int *__restrict__ idx,
+                 int h, int w, int ho, int wo, size_t total_quads, FastDiv div_wo4,
+                 FastDiv div_ho) {
+    size_t gstride = (size_t)gridDim.x * blockDim.x;
+    for (size_t q = (size_t)blockIdx.x * blockDim.x + threadIdx.x; q < total_quads; q += gstride) {
+        uint32_t t, jq, i, plane;
+        div_wo4.divmod((uint32_t)q, t, jq);
+        div_ho.divmod(t, plane, i);
+        const int base = (int)plane * h * w;
+        const int ih0 = 2 * (int)i, iw0 = 8 * (int)jq;
+        const bool has_c8 = iw0 + 8 < w;
+        float v[3][9];
+#pragma unroll
+        for (int r = 0; r < 3; ++r) {
+            if (ih0 + r < h) {
+                const float *row = x + base + (ih0 + r) * w + iw0;
+                const float4 a = ld_stream4(row), b = ld_stream4(row + 4);
+                v[r][0] = a.x; v[r][1] = a.y; v[r][2] = a.z; v[r][3] = a.w;
+                v[r][4] = b.x; v[r][5] = b.y; v[r][6] = b.z; v[r][7] = b.w;
+                v[r][8] = has_c8 ? __ldg(row + 8) : -FLT_MAX;
+            } else {
+#pragma unroll
+                for (int s = 0; s < 9; ++s) v[r][s] = -FLT_MAX;
+            }
+        }
+        float best[4];
+        int bi[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            float b = -FLT_MAX;
+            int at = -1;
+#pragma unroll
+            for (int r = 0; r < 3; ++r)
+#pragma unroll
+                for (int s = 0; s < 3; ++s) {
+                    const float val = v[r][2 * j + s];
+                    if (val > b) { b = val; at = base + (ih0 + r) * w + iw0 + 2 * j + s; }
+                }
+            best[j] = b; bi[j] = at;
+        }
+        const size_t o = ((size_t)plane * ho + i) * wo + 4 * jq;
+        *reinterpret_cast<float4 *>(y + o) = make_float4(best[0], best[1], best[2], best[3]);
+        *reinterpret_cast<int4 *>(idx + o) = make_int4(bi[0], bi[1], bi[2], bi[3]);
+    }
+}
+
+// ---- backward, 3x3 / stride 2 / w % 4 == 0: four input columns of one row per thread. Input
+// column iw belongs to output columns ceil((iw - 2) / 2) .. iw / 2, so the quad 4jq .. 4jq+3
+// sees output columns 2jq-1 .. 2jq+1 of at most two output rows; contributions are summed in
+// increasing output index (the CPU scatter order) like the generic kernel.
+__global__ void __launch_bounds__(256)
+maxpool_bwd_k3s2(float *__restrict__ dx, const float *__restrict__ dy,
+                 const int *__restrict__ idx, int h, int w, int ho, int wo, size_t total_quads,
+                 FastDiv div_w4, FastDiv div_h) {
+    size_t gstride = (size_t)gridDim.x * blockDim.x;
+    for (size_t q = (size_t)blockIdx.x * blockDim.x + threadIdx.x; q < total_quads; q += gstride) {
+        uint32_t t, jq, ih, plane;
+        div_w4.divmod((uint32_t)q, t, jq);
+        div_h.divmod(t, plane, ih);
+        const int e0 = ((int)plane * h + (int)ih) * w + 4 * (int)jq;
+        float4 d = *reinterpret_cast<float4 *>(dx + e0);
+        const int oh_hi = min((int)ih >> 1, ho - 1);
+        const int oh_lo = max(0, ((int)ih - 1) >> 1);  // ceil((ih - 2) / 2) for ih >= 1, 0 for ih = 0
+        const int ow0 = 2 * (int)jq;
+        const size_t obase = (size_t)plane * ho * wo;
+        for (int oh = oh_lo; oh <= oh_hi; ++oh) {
+            const size_t o = obase + (size_t)oh * wo + ow0;
+            int im = -1, i0, i1 = -1;
+            float gm = 0.f, g0, g1 = 0.f;
+            if (ow0 > 0) { im = __ldg(idx + o - 1); gm = __ldg(dy + o - 1); }
+            i0 = __ldg(idx + o); g0 = __ldg(dy + o);
+            if (ow0 + 1 < wo) { i1 = __ldg(idx + o + 1); g1 = __ldg(dy + o + 1); }
+            if (im == e0) d.x += gm;             // column 4jq     <- windows 2jq-1, 2jq
+            if (i0 == e0) d.x += g0;
+            if (i0 == e0 + 1) d.y += g0;         // column 4jq + 1 <- window 2jq
+            if (i0 == e0 + 2) d.z += g0;         // column 4jq + 2 <- windows 2jq, 2jq+1
+            if (i1 == e0 + 2) d.z += g1;
+            if (i1 == e0 + 3) d.w += g1;         // column 4jq + 3 <- window 2jq+1
+        }
+        *reinterpret_cast<float4 *>(dx + e0) = d;
+    }
+}
+
 // ---- backward: gather form. One thread per INPUT element sums, in increasing
 // output-index order (the CPU scatter order, bcnn_maxpool_layer.c:268-271), the dy of
 // every window that selected it. No atomics, deterministic.
@@ -180,6 +267,11 @@ extern "C" int bcnn_b200_maxpool_forward(const float *x, float *y, int *indexes,
         size_t pairs = total / 2;
         maxpool_fwd_k2s2<<<stream_grid(pairs, 256), 256, 0, st>>>(
             x, y, indexes, h, w, ho, wo, pairs, FastDiv(wo / 2), FastDiv(ho));
+    } else if (ksize == 3 && stride == 2 && (w % 8) == 0 && wo == w / 2 && ho == (h + 1) / 2 &&
+               aligned16(x) && aligned16(y) && aligned16(indexes)) {
+        size_t quads = total / 4;
+        maxpool_fwd_k3s2<<<stream_grid(quads, 256), 256, 0, st>>>(
+            x, y, indexes, h, w, ho, wo, quads, FastDiv(wo / 4), FastDiv(ho));
     } else {
         maxpool_fwd_generic<<<stream_grid(total, 256), 256, 0, st>>>(
             x, y, indexes, h, w, ksize, stride, ho, wo, total, FastDiv(wo), FastDiv(ho));
@@ -197,6 +289,11 @@ extern "C" int bcnn_b200_maxpool_backward(float *dx, const float *dy, const int 
         ho == h / 2 && aligned16(dx) && aligned16(dy) && aligned16(indexes)) {
         size_t quads = total_in / 4;
         maxpool_bwd_k2s2<<<stream_grid(quads, 256), 256, 0, st>>>(
+            dx, dy, indexes, h, w, ho, wo, quads, FastDiv(w / 4), FastDiv(h));
+    } else if (ksize == 3 && stride == 2 && (w % 4) == 0 && wo == (w + 1) / 2 && ho == (h + 1) / 2 &&
+               aligned16(dx)) {
+        size_t quads = total_in / 4;
+        maxpool_bwd_k3s2<<<stream_grid(quads, 256), 256, 0, st>>>(
             dx, dy, indexes, h, w, ho, wo, quads, FastDiv(w / 4), FastDiv(h));
     } else {
         maxpool_bwd_generic<<<stream_grid(total_in, 256), 256, 0, st>>>(

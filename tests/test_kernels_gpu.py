@@ -31,6 +31,10 @@ POOL_CASES = [
     (1, 1, 1, 1, 2, 2, capi.PAD_SAME),      # degenerate 1x1
     (2, 3, 26, 28, 2, 2, capi.PAD_SAME),    # vector path with h even, w % 4 == 0
     (2, 3, 27, 28, 2, 2, capi.PAD_SAME),    # vector path with odd h (missing bottom row)
+    (2, 3, 24, 32, 3, 2, capi.PAD_SAME),    # k3 s2 quad kernels (w % 8 == 0), bottom row missing
+    (2, 3, 25, 40, 3, 2, capi.PAD_SAME),    # k3 s2 quad kernels, odd h
+    (1, 2, 14, 20, 3, 2, capi.PAD_SAME),    # k3 s2: forward generic (w % 8 != 0), backward quads
+    (1, 2, 9, 8, 3, 2, capi.PAD_SAME),      # k3 s2: a single quad per output row
 ]
 
 
@@ -272,6 +276,16 @@ CONV_CASES = [
     (2, 24, 12, 12, 24, 3, 1, 0, 1),   # pad 0: fprop / wgrad on TMA, dgrad (10-wide dY) gathered
     (1, 32, 104, 104, 64, 3, 1, 1, 1), # yolo-tiny conv2 class: 4 column chunks per tile
     (2, 160, 8, 8, 300, 1, 1, 0, 1),   # Cout > 128: several N tiles
+    # thin first layers through the im2col buffer (fprop / wgrad as a 1x1 problem over Cin*k*k)
+    (4, 3, 64, 64, 64, 7, 2, 3, 1),    # resnet stem: K = 147 -> 148 columns, two wgrad N tiles
+    (8, 3, 32, 32, 32, 3, 1, 1, 1),    # cifar conv1: K = 27 -> 28 columns
+    # strided dgrad as stride^2 sub-sampled stride-1 problems scattered into dX
+    (2, 32, 15, 15, 32, 3, 2, 1, 1),   # odd extents: classes of different sizes
+    (2, 32, 16, 16, 32, 3, 2, 0, 1),   # pad 0: trailing input row / column get zero gradient
+    (1, 16, 20, 20, 16, 5, 3, 2, 1),   # stride 3, 5x5: nine classes, 1..4 taps each
+    (2, 32, 12, 12, 32, 2, 2, 0, 1),   # k2 s2: one tap per class
+    (2, 32, 9, 9, 16, 1, 2, 0, 1),     # 1x1 s2 on an odd plane: three empty classes
+    (2, 64, 28, 28, 64, 3, 2, 1, 1),   # resnet stride-2 3x3 at a size with several tiles
 ]
 
 
