@@ -391,7 +391,7 @@ def bind_kernel_abi(lib: C.CDLL) -> None:
         "bcnn_b200_bn_stats": (i, [vp, i, i, i, vp, vp, vp, vp, vp, vp]),
         "bcnn_b200_bn_apply": (i, [vp, vp, vp, vp, vp, vp, i, i, i, i, vp]),
         "bcnn_b200_scale_bias": (i, [vp, vp, vp, vp, i, i, i, i, vp]),
-        "bcnn_b200_bn_backward": (i, [vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, i, i, i, i,
+        "bcnn_b200_bn_backward": (i, [vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, i, i, i, i,
                                       vp, vp]),
         "bcnn_b200_conv_workspace_bytes": (sz, [dp, i]),
         "bcnn_b200_conv_uses_tensor_cores": (i, [dp, i]),

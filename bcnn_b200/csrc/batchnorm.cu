@@ -37,6 +37,17 @@ __device__ __forceinline__ void split_range(int n, int s, int splits, int &b0, i
     b1 = (int)(((long long)n * (s + 1)) / splits);
 }
 
+// gamma * (x - mean) * inv + beta, every step rounded separately (the reference scales and adds
+// the bias in separate passes). Forward and backward share it so that the backward can rebuild
+// the sign of the pre-activation bit for bit instead of re-reading y.
+__device__ __forceinline__ float bn_affine(float v, float m, float inv, float g, float b) {
+    return __fadd_rn(__fmul_rn(__fmul_rn(__fsub_rn(v, m), inv), g), b);
+}
+// ReLU / leaky-ReLU derivative from the pre-activation (y > 0 <=> pre > 0 for both).
+__device__ __forceinline__ float relu_factor(float pre, float neg_slope) {
+    return pre > 0.f ? 1.0f : neg_slope;
+}
+
 // ---- forward statistics ---------------------------------------------------------
 __global__ void __launch_bounds__(RT)
 bn_stats_kernel(const float *__restrict__ x, int n, int c, int hw, float *__restrict__ saved_mean,
@@ -146,10 +157,10 @@ bn_apply_kernel(const float *__restrict__ x, float *__restrict__ y, const float 
                     inv = 1.0f / sqrtf(__ldg(var + ch) + 0.000001f);
                 }
                 float4 r;
-                r.x = act_fwd((v[u].x - m) * inv * g + b, act, 0.f);
-                r.y = act_fwd((v[u].y - m) * inv * g + b, act, 0.f);
-                r.z = act_fwd((v[u].z - m) * inv * g + b, act, 0.f);
-                r.w = act_fwd((v[u].w - m) * inv * g + b, act, 0.f);
+                r.x = act_fwd(bn_affine(v[u].x, m, inv, g, b), act, 0.f);
+                r.y = act_fwd(bn_affine(v[u].y, m, inv, g, b), act, 0.f);
+                r.z = act_fwd(bn_affine(v[u].z, m, inv, g, b), act, 0.f);
+                r.w = act_fwd(bn_affine(v[u].w, m, inv, g, b), act, 0.f);
                 reinterpret_cast<float4 *>(y)[j] = r;
             }
         }
@@ -163,7 +174,7 @@ bn_apply_kernel(const float *__restrict__ x, float *__restrict__ y, const float 
                 m = __ldg(mean + ch);
                 inv = 1.0f / sqrtf(__ldg(var + ch) + 0.000001f);
             }
-            y[j] = act_fwd((x[j] - m) * inv * g + b, act, 0.f);
+            y[j] = act_fwd(bn_affine(x[j], m, inv, g, b), act, 0.f);
         }
     }
 }
@@ -173,7 +184,8 @@ __global__ void __launch_bounds__(RT)
 bn_bwd_reduce_kernel(const float *__restrict__ x, const float *__restrict__ y,
                      const float *__restrict__ dy, const float *__restrict__ mean,
                      const float *__restrict__ var, const float *__restrict__ gamma,
-                     float *__restrict__ g_gamma, float *__restrict__ g_beta,
+                     const float *__restrict__ beta, float *__restrict__ g_gamma,
+                     float *__restrict__ g_beta,
                      float *__restrict__ d_mean, float *__restrict__ d_var, int n, int c, int hw,
                      int act, float *__restrict__ partial, unsigned int *__restrict__ tickets,
                      FastDiv div_hw, FastDiv div_hw4, bool vec) {
@@ -183,11 +195,16 @@ bn_bwd_reduce_kernel(const float *__restrict__ x, const float *__restrict__ y,
     int b0, b1;
     split_range(n, split, splits, b0, b1);
     const float m = mean[ch];
+    // ReLU family with beta known: the mask comes from the recomputed pre-activation, y is not read
+    const bool remask = beta != nullptr && (act == ACT_RELU || act == ACT_LRELU);
+    const float inv6 = remask ? 1.0f / sqrtf(var[ch] + 0.000001f) : 0.f;
+    const float gch = remask ? gamma[ch] : 0.f, bch = remask ? beta[ch] : 0.f;
+    const float neg = act == ACT_LRELU ? 0.1f : 0.f;
     float acc[2] = {0.f, 0.f};
     if (vec) {
         const int hw4 = hw >> 2;
         const uint32_t total4 = (uint32_t)(b1 - b0) * hw4;
-        constexpr int UNROLL = 2;
+        constexpr int UNROLL = 4;
         for (uint32_t j0 = threadIdx.x; j0 < total4; j0 += RT * UNROLL) {
             float4 xv[UNROLL], g[UNROLL], yv[UNROLL];
 #pragma unroll
@@ -200,12 +217,17 @@ bn_bwd_reduce_kernel(const float *__restrict__ x, const float *__restrict__ y,
                     size_t off = ((size_t)(b0 + b) * c + ch) * hw + (i4 << 2);
                     xv[u] = ld_stream4(x + off);
                     g[u] = ld_stream4(dy + off);
-                    if (act != ACT_NONE) yv[u] = ld_stream4(y + off);
+                    if (act != ACT_NONE && !remask) yv[u] = ld_stream4(y + off);
                 }
             }
 #pragma unroll
             for (int u = 0; u < UNROLL; ++u) {
-                if (act != ACT_NONE) {
+                if (remask) {
+                    g[u].x *= relu_factor(bn_affine(xv[u].x, m, inv6, gch, bch), neg);
+                    g[u].y *= relu_factor(bn_affine(xv[u].y, m, inv6, gch, bch), neg);
+                    g[u].z *= relu_factor(bn_affine(xv[u].z, m, inv6, gch, bch), neg);
+                    g[u].w *= relu_factor(bn_affine(xv[u].w, m, inv6, gch, bch), neg);
+                } else if (act != ACT_NONE) {
                     g[u].x *= act_bwd_factor(yv[u].x, act, 0.f);
                     g[u].y *= act_bwd_factor(yv[u].y, act, 0.f);
                     g[u].z *= act_bwd_factor(yv[u].z, act, 0.f);
@@ -223,9 +245,11 @@ bn_bwd_reduce_kernel(const float *__restrict__ x, const float *__restrict__ y,
             div_hw.divmod(j, b, i);
             size_t off = ((size_t)(b0 + b) * c + ch) * hw + i;
             float g = __ldg(dy + off);
-            if (act != ACT_NONE) g *= act_bwd_factor(__ldg(y + off), act, 0.f);
+            const float xv = __ldg(x + off);
+            if (remask) g *= relu_factor(bn_affine(xv, m, inv6, gch, bch), neg);
+            else if (act != ACT_NONE) g *= act_bwd_factor(__ldg(y + off), act, 0.f);
             acc[0] += g;
-            acc[1] += g * (__ldg(x + off) - m);
+            acc[1] += g * (xv - m);
         }
     }
     block_sum<2, RT>(acc, red);
@@ -258,12 +282,15 @@ __global__ void __launch_bounds__(256)
 bn_bwd_apply_kernel(const float *__restrict__ x, const float *__restrict__ y,
                     const float *dy, float *dx, const float *__restrict__ mean,
                     const float *__restrict__ var, const float *__restrict__ gamma,
-                    const float *__restrict__ d_mean, const float *__restrict__ d_var,
+                    const float *__restrict__ beta, const float *__restrict__ d_mean,
+                    const float *__restrict__ d_var,
                     size_t total, int count /* n*hw */, int act, FastDiv div_hw, FastDiv div_c,
                     bool vec) {
     size_t gstride = (size_t)gridDim.x * blockDim.x;
     size_t tid = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     const float inv_count = 1.0f / (float)count;
+    const bool remask = beta != nullptr && (act == ACT_RELU || act == ACT_LRELU);
+    const float neg = act == ACT_LRELU ? 0.1f : 0.f;
     if (vec) {
         const size_t n4 = total >> 2;
         constexpr int UNROLL = 2;
@@ -275,7 +302,7 @@ bn_bwd_apply_kernel(const float *__restrict__ x, const float *__restrict__ y,
                 if (j < n4) {
                     xv[u] = ld_stream4(x + (j << 2));
                     gv[u] = reinterpret_cast<const float4 *>(dy)[j];
-                    if (act != ACT_NONE) yv[u] = ld_stream4(y + (j << 2));
+                    if (act != ACT_NONE && !remask) yv[u] = ld_stream4(y + (j << 2));
                 }
             }
 #pragma unroll
@@ -289,7 +316,14 @@ bn_bwd_apply_kernel(const float *__restrict__ x, const float *__restrict__ y,
                 const float k2 = __ldg(d_var + ch) * 2.0f * inv_count;
                 const float k3 = __ldg(d_mean + ch) * inv_count;
                 float4 g = gv[u];
-                if (act != ACT_NONE) {
+                if (remask) {
+                    const float inv6 = 1.0f / sqrtf(__ldg(var + ch) + 0.000001f);
+                    const float gch = __ldg(gamma + ch), bch = __ldg(beta + ch);
+                    g.x *= relu_factor(bn_affine(xv[u].x, m, inv6, gch, bch), neg);
+                    g.y *= relu_factor(bn_affine(xv[u].y, m, inv6, gch, bch), neg);
+                    g.z *= relu_factor(bn_affine(xv[u].z, m, inv6, gch, bch), neg);
+                    g.w *= relu_factor(bn_affine(xv[u].w, m, inv6, gch, bch), neg);
+                } else if (act != ACT_NONE) {
                     g.x *= act_bwd_factor(yv[u].x, act, 0.f);
                     g.y *= act_bwd_factor(yv[u].y, act, 0.f);
                     g.z *= act_bwd_factor(yv[u].z, act, 0.f);
@@ -312,8 +346,12 @@ bn_bwd_apply_kernel(const float *__restrict__ x, const float *__restrict__ y,
             const float k2 = __ldg(d_var + ch) * 2.0f * inv_count;
             const float k3 = __ldg(d_mean + ch) * inv_count;
             float g = dy[j];
-            if (act != ACT_NONE) g *= act_bwd_factor(__ldg(y + j), act, 0.f);
-            dx[j] = g * k1 + k2 * (__ldg(x + j) - m) + k3;
+            const float xv = __ldg(x + j);
+            if (remask)
+                g *= relu_factor(bn_affine(xv, m, 1.0f / sqrtf(__ldg(var + ch) + 0.000001f),
+                                           __ldg(gamma + ch), __ldg(beta + ch)), neg);
+            else if (act != ACT_NONE) g *= act_bwd_factor(__ldg(y + j), act, 0.f);
+            dx[j] = g * k1 + k2 * (xv - m) + k3;
         }
     }
 }
@@ -359,15 +397,16 @@ extern "C" int bcnn_b200_scale_bias(const float *x, float *y, const float *gamma
 
 extern "C" int bcnn_b200_bn_backward(const float *x, const float *y, float *dy, float *dx_out,
                                      const float *mean, const float *var, const float *gamma,
-                                     float *g_gamma, float *g_beta, float *d_mean, float *d_var,
-                                     int n, int c, int hw, int act, float *scratch, void *stream) {
+                                     const float *beta, float *g_gamma, float *g_beta,
+                                     float *d_mean, float *d_var, int n, int c, int hw, int act,
+                                     float *scratch, void *stream) {
     size_t total = (size_t)n * c * hw;
     if (total == 0) return 0;
     cudaStream_t st = as_stream(stream);
     int splits = reduce_splits(n, c);
     unsigned int *tickets = reinterpret_cast<unsigned int *>(scratch + (size_t)c * MAX_SPLITS * 4);
     dim3 grid(c, splits);
-    bn_bwd_reduce_kernel<<<grid, RT, 0, st>>>(x, y, dy, mean, var, gamma, g_gamma, g_beta, d_mean,
+    bn_bwd_reduce_kernel<<<grid, RT, 0, st>>>(x, y, dy, mean, var, gamma, beta, g_gamma, g_beta, d_mean,
                                               d_var, n, c, hw, act, scratch, tickets, FastDiv(hw),
                                               FastDiv(hw >> 2 ? hw >> 2 : 1),
                                               (hw % 4) == 0 && aligned16(x) && aligned16(dy) &&
@@ -377,7 +416,7 @@ extern "C" int bcnn_b200_bn_backward(const float *x, const float *y, float *dy, 
     bool vec = (hw % 4) == 0 && aligned16(x) && aligned16(dy) && aligned16(dx_out) &&
                (y == nullptr || aligned16(y));
     bn_bwd_apply_kernel<<<stream_grid(vec ? total / 4 : total, 256), 256, 0, st>>>(
-        x, y, dy, dx_out, mean, var, gamma, d_mean, d_var, total, n * hw, act, FastDiv(hw),
+        x, y, dy, dx_out, mean, var, gamma, beta, d_mean, d_var, total, n * hw, act, FastDiv(hw),
         FastDiv(c), vec);
     return launched();
 }

@@ -83,6 +83,23 @@ __device__ __forceinline__ uint64_t make_desc_mn_sw128(uint32_t smem_addr, uint3
     d |= (uint64_t)1 << 61;
     return d;
 }
+// MN-major 16-bit operand, plain SWIZZLE_128B (layout type 2): 64 bf16 along MN are contiguous
+// (128 B), 8 K-rows form a 1 KiB atom with 16-byte chunks XOR-swizzled by (K-row & 7).
+// LBO = byte stride between MN atoms, SBO = byte stride between groups of 8 K-rows.
+__device__ __forceinline__ uint64_t make_desc_mn_sw128_b16(uint32_t smem_addr, uint32_t lbo, uint32_t sbo) {
+    uint64_t d = 0;
+    d |= (uint64_t)((smem_addr & 0x3FFFF) >> 4);
+    d |= (uint64_t)(lbo >> 4) << 16;
+    d |= (uint64_t)(sbo >> 4) << 32;
+    d |= (uint64_t)1 << 46;
+    d |= (uint64_t)2 << 61;
+    return d;
+}
+// D = F32, A = B = BF16 (kind::f16); a_mn / b_mn mark an MN-major operand.
+__device__ __forceinline__ uint32_t make_idesc_bf16(int m, int n, int a_mn, int b_mn) {
+    return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(a_mn ? 1 : 0) << 15) |
+           ((uint32_t)(b_mn ? 1 : 0) << 16) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(m >> 4) << 24);
+}
 // D = F32, A = B = TF32; a_mn / b_mn mark an MN-major operand (bits 15 / 16).
 __device__ __forceinline__ uint32_t make_idesc_tf32(int m, int n, int a_mn, int b_mn) {
     return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(a_mn ? 1 : 0) << 15) |
@@ -130,17 +147,20 @@ bool make_map_nchw(CUtensorMap *map, const float *base, int w, int h, int c, int
 
 // Map over an NHWC fp32 shadow seen as (c, w, h, n); box = 32 channels x bw x bh x bn positions,
 // walking w and h with the convolution stride.
-bool make_map_nhwc(CUtensorMap *map, const float *base, int c, int w, int h, int n, int bw, int bh,
-                   int bn, int stride, bool mn_major) {
+// bf16 shadows: 64 channels per 128-byte row, plain SWIZZLE_128B for both operand majors.
+bool make_map_nhwc(CUtensorMap *map, const void *base, int c, int w, int h, int n, int bw, int bh,
+                   int bn, int stride, bool mn_major, bool bf16) {
     EncodeTiledFn fn = encode_fn();
     if (!fn) return false;
+    const cuuint64_t es = bf16 ? 2 : 4;
     cuuint64_t dims[4] = {(cuuint64_t)c, (cuuint64_t)w, (cuuint64_t)h, (cuuint64_t)n};
-    cuuint64_t strides[3] = {(cuuint64_t)c * 4, (cuuint64_t)w * c * 4, (cuuint64_t)w * h * c * 4};
-    cuuint32_t box[4] = {32, (cuuint32_t)(bw * stride), (cuuint32_t)(bh * stride), (cuuint32_t)bn};
+    cuuint64_t strides[3] = {(cuuint64_t)c * es, (cuuint64_t)w * c * es, (cuuint64_t)w * h * c * es};
+    cuuint32_t box[4] = {bf16 ? 64u : 32u, (cuuint32_t)(bw * stride), (cuuint32_t)(bh * stride),
+                         (cuuint32_t)bn};
     cuuint32_t estr[4] = {1, (cuuint32_t)stride, (cuuint32_t)stride, 1};
-    CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, const_cast<float *>(base), dims, strides,
-                    box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                    mn_major ? CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B : CU_TENSOR_MAP_SWIZZLE_128B,
+    CUresult r = fn(map, bf16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4,
+                    const_cast<void *>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                    (mn_major && !bf16) ? CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B : CU_TENSOR_MAP_SWIZZLE_128B,
                     CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     return r == CUDA_SUCCESS;
 }
@@ -169,10 +189,50 @@ nchw_to_nhwc_kernel(const float *__restrict__ in, float *__restrict__ out, int C
     }
 }
 
-int launch_transpose(const float *in, float *out, int n, int c, int p, cudaStream_t st) {
-    dim3 grid(ceil_div(p, 32), ceil_div(c, 32), n);
-    nchw_to_nhwc_kernel<<<grid, 256, 0, st>>>(in, out, c, p);
+// bf16 flavour: 64 channels x 32 positions per CTA, each thread stores a bf16 pair so a warp
+// still writes 128 contiguous bytes. C % 8 == 0 (16-byte rows for the TMA).
+__global__ void __launch_bounds__(256)
+nchw_to_nhwc_bf16_kernel(const float *__restrict__ in, __nv_bfloat16 *__restrict__ out, int C, int P) {
+    __shared__ float tile[64][33];
+    const int n = blockIdx.z;
+    const int p0 = blockIdx.x * 32, c0 = blockIdx.y * 64;
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+    const float *src = in + (size_t)n * C * P;
+    __nv_bfloat16 *dst = out + (size_t)n * C * P;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        const int c = c0 + ty + 8 * i, p = p0 + tx;
+        tile[ty + 8 * i][tx] = (c < C && p < P) ? __ldg(src + (size_t)c * P + p) : 0.f;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const int p = p0 + ty + 8 * i, c = c0 + 2 * tx;
+        if (p < P && c < C)
+            *reinterpret_cast<uint32_t *>(dst + (size_t)p * C + c) =
+                pack_bf16x2(tile[2 * tx][ty + 8 * i], tile[2 * tx + 1][ty + 8 * i]);
+    }
+}
+
+int launch_transpose(const float *in, void *out, int n, int c, int p, bool bf16, cudaStream_t st) {
+    if (bf16) {
+        dim3 grid(ceil_div(p, 32), ceil_div(c, 64), n);
+        nchw_to_nhwc_bf16_kernel<<<grid, 256, 0, st>>>(in, reinterpret_cast<__nv_bfloat16 *>(out), c, p);
+    } else {
+        dim3 grid(ceil_div(p, 32), ceil_div(c, 32), n);
+        nchw_to_nhwc_kernel<<<grid, 256, 0, st>>>(in, reinterpret_cast<float *>(out), c, p);
+    }
     return launched();
+}
+
+// Shadows and packed weights are bf16 unless BCNN_B200_SHADOW=fp32 (TF32 on the shadow routes too).
+bool shadow_bf16() {
+    static int v = -1;
+    if (v < 0) {
+        const char *e = getenv("BCNN_B200_SHADOW");
+        v = (e && (e[0] == 'f' || e[0] == 'F')) ? 0 : 1;
+    }
+    return v == 1;
 }
 
 // ------------------------------------------------------------------ weight repack (TF32 = fp32 bits)
@@ -186,9 +246,12 @@ struct TapMap {
     short idx[64];    // tap t reads W[..][..][idx[t]]
 };
 
+// BF16: rows of 64 bf16 (same 128 bytes, same 16-byte chunk swizzle), 8 elements per chunk.
+template <bool BF16>
 __global__ void __launch_bounds__(256)
-pack_weights_tf32_kernel(const float *__restrict__ w, float *__restrict__ wpack, int dgrad, int cout,
+pack_weights_tf32_kernel(const float *__restrict__ w, uint8_t *__restrict__ wpack, int dgrad, int cout,
                          int cin, int kk, int n_tile, int n_tiles, int kc_blocks, const TapMap taps) {
+    constexpr int EPC = BF16 ? 8 : 4;   // elements per 16-byte chunk
     const int k_blocks = taps.n * kc_blocks;
     const size_t chunks = (size_t)n_tiles * n_tile * k_blocks * 8;
     for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < chunks;
@@ -204,10 +267,10 @@ pack_weights_tf32_kernel(const float *__restrict__ w, float *__restrict__ wpack,
         const int row_c = dgrad ? cin : cout;
         const int k_c = dgrad ? cout : cin;
         const int wtap = taps.idx[tap];
-        float v[4];
+        float v[EPC];
 #pragma unroll
-        for (int e = 0; e < 4; ++e) {
-            const int kc = cb * BLOCK_K + chunk * 4 + e;
+        for (int e = 0; e < EPC; ++e) {
+            const int kc = (cb * 8 + chunk) * EPC + e;
             float val = 0.f;
             if (row < row_c && kc < k_c) {
                 const int co = dgrad ? kc : row, ci = dgrad ? row : kc;
@@ -215,9 +278,15 @@ pack_weights_tf32_kernel(const float *__restrict__ w, float *__restrict__ wpack,
             }
             v[e] = val;
         }
-        const size_t tile_base = ((size_t)tile * k_blocks + kb) * (size_t)n_tile * BLOCK_K;
-        const size_t off = tile_base + (size_t)row_in_tile * BLOCK_K + (size_t)((chunk ^ (row_in_tile & 7)) * 4);
-        *reinterpret_cast<float4 *>(wpack + off) = make_float4(v[0], v[1], v[2], v[3]);
+        const size_t tile_base = ((size_t)tile * k_blocks + kb) * (size_t)n_tile * 128;
+        const size_t off = tile_base + (size_t)row_in_tile * 128 + (size_t)((chunk ^ (row_in_tile & 7)) * 16);
+        if constexpr (BF16) {
+            *reinterpret_cast<uint4 *>(wpack + off) =
+                make_uint4(pack_bf16x2(v[0], v[1]), pack_bf16x2(v[2], v[3]), pack_bf16x2(v[4], v[5]),
+                           pack_bf16x2(v[EPC - 2], v[EPC - 1]));
+        } else {
+            *reinterpret_cast<float4 *>(wpack + off) = make_float4(v[0], v[1], v[2], v[3]);
+        }
     }
 }
 
@@ -225,7 +294,7 @@ pack_weights_tf32_kernel(const float *__restrict__ w, float *__restrict__ wpack,
 struct FwdParams {
     float *dst;
     const float *bias;
-    const float *wpack;
+    const uint8_t *wpack;
     int act, accumulate;
     int src_c, dst_c, batch;
     int out_w, out_h;     // output plane as the kernel sees it (DIRECT: (H*W, 1))
@@ -299,9 +368,10 @@ __device__ __forceinline__ void store_chunk_any(const uint32_t (&v)[32], float *
 // CTAs working at the same time share an activation tile through L2). The TMA producer runs
 // ahead across tile boundaries; two TMEM accumulators let the epilogue of tile i overlap the
 // MMAs of tile i+1.
-template <bool NHWC>
+template <bool NHWC, bool BF16>
 __global__ void __launch_bounds__(FWD_THREADS, 1)
 conv_tma_fwd_kernel(const __grid_constant__ CUtensorMap tm_src, const FwdParams p) {
+    constexpr int KC = BF16 ? 64 : 32;   // channels per 128-byte k-block row
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     uint8_t *smem = reinterpret_cast<uint8_t *>(
         (reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
@@ -339,7 +409,7 @@ conv_tma_fwd_kernel(const __grid_constant__ CUtensorMap tm_src, const FwdParams 
             const uint32_t tx_bytes = p.a_bytes + (uint32_t)b_stage_bytes;
             for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
                 const TileCoord c = decode_tile<NHWC>(p, tile);
-                const float *wtile = p.wpack + (size_t)c.tile_n * p.k_blocks * n_tile * BLOCK_K;
+                const uint8_t *wtile = p.wpack + (size_t)c.tile_n * p.k_blocks * b_stage_bytes;
                 int kb = 0;
                 for (int kh = 0; kh < p.ksh; ++kh) {
                     for (int kw = 0; kw < p.ksw; ++kw) {
@@ -350,7 +420,7 @@ conv_tma_fwd_kernel(const __grid_constant__ CUtensorMap tm_src, const FwdParams 
                             uint8_t *a_stage = smem + (size_t)s * stage_bytes;
                             mbar_expect_tx(fb, tx_bytes);
                             if (NHWC) {
-                                tma_load_4d(smem_u32(a_stage), &tm_src, cb * BLOCK_K,
+                                tma_load_4d(smem_u32(a_stage), &tm_src, cb * KC,
                                             c.w0 * p.stride + kw - p.pad_w,
                                             c.h0 * p.stride + kh - p.pad_h, c.img, fb);
                             } else {
@@ -362,7 +432,7 @@ conv_tma_fwd_kernel(const __grid_constant__ CUtensorMap tm_src, const FwdParams 
                                 }
                             }
                             bulk_copy_g2s(smem_u32(a_stage + A_STAGE_BYTES),
-                                          wtile + (size_t)kb * n_tile * BLOCK_K, (uint32_t)b_stage_bytes, fb);
+                                          wtile + (size_t)kb * b_stage_bytes, (uint32_t)b_stage_bytes, fb);
                         }
                     }
                 }
@@ -371,7 +441,8 @@ conv_tma_fwd_kernel(const __grid_constant__ CUtensorMap tm_src, const FwdParams 
     } else if (warp == 1) {
         if (lane == 0) {
             // ---------------- MMA issuer
-            const uint32_t idesc = make_idesc_tf32(TILE_M, n_tile, NHWC ? 0 : 1, 0);
+            const uint32_t idesc = BF16 ? make_idesc_bf16(TILE_M, n_tile, 0, 0)
+                                        : make_idesc_tf32(TILE_M, n_tile, NHWC ? 0 : 1, 0);
             uint32_t it = 0, local = 0;
             for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++local) {
                 const uint32_t buf = local & 1, use = local >> 1;
@@ -391,7 +462,8 @@ conv_tma_fwd_kernel(const __grid_constant__ CUtensorMap tm_src, const FwdParams 
                         const uint64_t da = NHWC ? make_desc_sw128(a_addr) + (uint64_t)(2 * g)
                                                  : make_desc_mn_sw128(a_addr + g * 1024, ATOM_BYTES, 512);
                         const uint64_t db = make_desc_sw128(b_addr) + (uint64_t)(2 * g);
-                        umma_tf32(d_tmem, da, db, idesc, (kb > 0 || g > 0) ? 1u : 0u);
+                        if (BF16) umma_bf16(d_tmem, da, db, idesc, (kb > 0 || g > 0) ? 1u : 0u);
+                        else umma_tf32(d_tmem, da, db, idesc, (kb > 0 || g > 0) ? 1u : 0u);
                     }
                     umma_commit(smem_u32(empty + s));
                 }
@@ -482,7 +554,7 @@ struct FwdGeom {
 };
 
 struct FwdPlan {
-    bool nhwc;
+    bool nhwc, bf16;
     int n_tile, n_tiles, kc_blocks, k_blocks, stages;
     int view_w, view_h;      // DIRECT: source plane as the TMA sees it
     int out_w, out_h;
@@ -522,6 +594,8 @@ bool plan_fwd(const FwdGeom &g, FwdPlan *pl) {
     pl->nhwc = !direct;
     if (!direct && (nhwc_disabled() || g.src_c % 4 != 0 || g.stride > 4)) return false;
     if (g.ksh * g.ksw > 64) return false;   // TapMap capacity
+    pl->bf16 = !direct && shadow_bf16() && g.src_c % 8 == 0;
+    const int kc = pl->bf16 ? 64 : 32;       // channels per 128-byte k-block row
     static int nmax = 0;
     if (!nmax) {
         const char *e = getenv("BCNN_B200_FWD_NMAX");
@@ -537,7 +611,7 @@ bool plan_fwd(const FwdGeom &g, FwdPlan *pl) {
     }
     pl->n_tile = n;
     pl->n_tiles = ceil_div(g.dst_c, n);
-    pl->kc_blocks = ceil_div(g.src_c, BLOCK_K);
+    pl->kc_blocks = ceil_div(g.src_c, kc);
     pl->k_blocks = g.ksh * g.ksw * pl->kc_blocks;
     pl->wc = pl->rows = 1; pl->tw = pl->th = pl->tn = 1;
     if (direct) {
@@ -574,7 +648,7 @@ bool plan_fwd(const FwdGeom &g, FwdPlan *pl) {
         pl->tw = tw; pl->th = th; pl->tn = tn;
         pl->tiles_w = tiles_w; pl->tiles_h = tiles_h; pl->tiles_b = ceil_div(g.batch, tn);
         pl->a_bytes = (uint32_t)(tw * th * tn * 128);
-        pl->shadow_bytes = align256((size_t)g.batch * g.src_c * g.sh * g.sw * sizeof(float));
+        pl->shadow_bytes = align256((size_t)g.batch * g.src_c * g.sh * g.sw * (pl->bf16 ? 2 : 4));
     }
     const int stage = A_STAGE_BYTES + n * BLOCK_K * 4;
     int stages = (200 * 1024) / stage;  // persistent: one CTA per SM owns the shared memory
@@ -591,8 +665,8 @@ bool plan_fwd(const FwdGeom &g, FwdPlan *pl) {
 enum FwdRoute { ROUTE_NONE = 0, ROUTE_PLAIN, ROUTE_IM2COL, ROUTE_STRIDED_DGRAD };
 
 // Thin first layers (Cin = 3): an explicit im2col buffer [n, ho, wo, Kp] (Kp = Cin * k * k rounded
-// up to 4 floats) is an NHWC tensor with Kp channels; over it the convolution is 1x1.
-int im2col_kp(const bcnn_b200_conv_desc *d) { return ceil_div(d->cin * d->ksize * d->ksize, 4) * 4; }
+// up to 8 elements) is an NHWC tensor with Kp channels; over it the convolution is 1x1.
+int im2col_kp(const bcnn_b200_conv_desc *d) { return ceil_div(d->cin * d->ksize * d->ksize, 8) * 8; }
 bool im2col_shape(const bcnn_b200_conv_desc *d) {
     static int off = -1;
     if (off < 0) off = env_off("BCNN_B200_NO_IM2COL") ? 1 : 0;
@@ -695,28 +769,30 @@ FwdRoute route_fwd(const bcnn_b200_conv_desc *d, bool dgrad, FwdPlan *pl) {
     return plan_fwd(geom_plain(d, false), pl) ? ROUTE_PLAIN : ROUTE_NONE;
 }
 
-template <bool NHWC>
+template <bool NHWC, bool BF16>
 int launch_fwd_kernel(const CUtensorMap &tm, const FwdParams &p, size_t smem, cudaStream_t st) {
     static bool attr_set = false;
     if (!attr_set) {
-        cudaError_t e = cudaFuncSetAttribute(conv_tma_fwd_kernel<NHWC>,
+        cudaError_t e = cudaFuncSetAttribute(conv_tma_fwd_kernel<NHWC, BF16>,
                                              cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
         if (e != cudaSuccess) return (int)e;
         attr_set = true;
     }
     const int grid = p.total_tiles < sm_count() ? p.total_tiles : sm_count();
-    conv_tma_fwd_kernel<NHWC><<<grid, FWD_THREADS, smem, st>>>(tm, p);
+    conv_tma_fwd_kernel<NHWC, BF16><<<grid, FWD_THREADS, smem, st>>>(tm, p);
     return launched();
 }
 
 // src: the NCHW tensor (DIRECT plans) or the NHWC-shaped shadow (all others).
-int run_fwd(const FwdGeom &g, const FwdPlan &pl, const float *src, const float *wpack, const float *bias,
+int run_fwd(const FwdGeom &g, const FwdPlan &pl, const void *src, const uint8_t *wpack, const float *bias,
             int act, float *dst, int accumulate, cudaStream_t st) {
     CUtensorMap tm;
     if (pl.nhwc) {
-        if (!make_map_nhwc(&tm, src, g.src_c, g.sw, g.sh, g.batch, pl.tw, pl.th, pl.tn, g.stride, false))
+        if (!make_map_nhwc(&tm, src, g.src_c, g.sw, g.sh, g.batch, pl.tw, pl.th, pl.tn, g.stride, false,
+                           pl.bf16))
             return (int)cudaErrorInvalidValue;
-    } else if (!make_map_nchw(&tm, src, pl.view_w, pl.view_h, g.src_c, g.batch, BLOCK_K, true)) {
+    } else if (!make_map_nchw(&tm, reinterpret_cast<const float *>(src), pl.view_w, pl.view_h, g.src_c,
+                              g.batch, BLOCK_K, true)) {
         return (int)cudaErrorInvalidValue;
     }
     FwdParams p;
@@ -737,27 +813,33 @@ int run_fwd(const FwdGeom &g, const FwdPlan &pl, const float *src, const float *
     p.d_tiles_h = FastDiv((uint32_t)pl.tiles_h);
     p.d_tw = FastDiv((uint32_t)pl.tw);
     p.d_th = FastDiv((uint32_t)pl.th);
-    return pl.nhwc ? launch_fwd_kernel<true>(tm, p, pl.smem_bytes, st)
-                   : launch_fwd_kernel<false>(tm, p, pl.smem_bytes, st);
+    if (!pl.nhwc) return launch_fwd_kernel<false, false>(tm, p, pl.smem_bytes, st);
+    return pl.bf16 ? launch_fwd_kernel<true, true>(tm, p, pl.smem_bytes, st)
+                   : launch_fwd_kernel<true, false>(tm, p, pl.smem_bytes, st);
 }
 
-int launch_pack(const float *w, float *wpack, bool dgrad, int cout, int cin, int kk, const FwdPlan &pl,
+int launch_pack(const float *w, uint8_t *wpack, bool dgrad, int cout, int cin, int kk, const FwdPlan &pl,
                 const TapMap &taps, cudaStream_t st) {
     const size_t chunks = (size_t)pl.n_tiles * pl.n_tile * pl.k_blocks * 8;
-    pack_weights_tf32_kernel<<<stream_grid(chunks, 256), 256, 0, st>>>(
-        w, wpack, dgrad ? 1 : 0, cout, cin, kk, pl.n_tile, pl.n_tiles, pl.kc_blocks, taps);
+    if (pl.bf16)
+        pack_weights_tf32_kernel<true><<<stream_grid(chunks, 256), 256, 0, st>>>(
+            w, wpack, dgrad ? 1 : 0, cout, cin, kk, pl.n_tile, pl.n_tiles, pl.kc_blocks, taps);
+    else
+        pack_weights_tf32_kernel<false><<<stream_grid(chunks, 256), 256, 0, st>>>(
+            w, wpack, dgrad ? 1 : 0, cout, cin, kk, pl.n_tile, pl.n_tiles, pl.kc_blocks, taps);
     return launched();
 }
 
-int launch_im2col(const bcnn_b200_conv_desc *d, const float *x, float *col, cudaStream_t st);
+int launch_im2col(const bcnn_b200_conv_desc *d, const float *x, void *col, bool bf16, cudaStream_t st);
 
 int launch_strided_dgrad(const bcnn_b200_conv_desc *d, const float *dy, const float *w, float *dx,
                          int accumulate, void *workspace, size_t workspace_bytes, cudaStream_t st) {
     const size_t need = strided_dgrad_bytes(d);
     if (!need || workspace == nullptr || workspace_bytes < need) return (int)cudaErrorInvalidValue;
     if ((reinterpret_cast<uintptr_t>(workspace) & 255) != 0) return (int)cudaErrorMisalignedAddress;
-    float *shadow = reinterpret_cast<float *>(workspace);
-    int err = launch_transpose(dy, shadow, d->batch, d->cout, d->ho * d->wo, st);
+    void *shadow = workspace;
+    const bool bf16 = shadow_bf16() && d->cout % 8 == 0;   // what plan_fwd decides for every class
+    int err = launch_transpose(dy, shadow, d->batch, d->cout, d->ho * d->wo, bf16, st);
     if (err) return err;
     const int s = d->stride, kk = d->ksize * d->ksize;
     // classes without taps (e.g. 1x1 stride 2: three of four) receive no gradient
@@ -782,7 +864,7 @@ int launch_strided_dgrad(const bcnn_b200_conv_desc *d, const float *dy, const fl
             FwdPlan pl;
             if (!plan_fwd(g, &pl)) return (int)cudaErrorInvalidValue;
             if (!have_shadow_bytes) { off = pl.shadow_bytes; have_shadow_bytes = true; }
-            float *wpack = reinterpret_cast<float *>(reinterpret_cast<uint8_t *>(workspace) + off);
+            uint8_t *wpack = reinterpret_cast<uint8_t *>(workspace) + off;
             off += pl.wpack_bytes;
             TapMap taps;
             taps.n = ah.n * aw.n;
@@ -809,8 +891,8 @@ int launch_fwd(const bcnn_b200_conv_desc *d, bool dgrad, const float *src, const
     if (workspace == nullptr || workspace_bytes < pl.shadow_bytes + pl.wpack_bytes)
         return (int)cudaErrorInvalidValue;
     if ((reinterpret_cast<uintptr_t>(workspace) & 255) != 0) return (int)cudaErrorMisalignedAddress;
-    float *shadow = reinterpret_cast<float *>(workspace);
-    float *wpack = reinterpret_cast<float *>(reinterpret_cast<uint8_t *>(workspace) + pl.shadow_bytes);
+    void *shadow = workspace;
+    uint8_t *wpack = reinterpret_cast<uint8_t *>(workspace) + pl.shadow_bytes;
     const int kk = d->ksize * d->ksize;
     TapMap taps;
     int err;
@@ -819,7 +901,7 @@ int launch_fwd(const bcnn_b200_conv_desc *d, bool dgrad, const float *src, const
         taps.n = 1; taps.idx[0] = 0;
         err = launch_pack(w, wpack, false, d->cout, d->cin * kk, 1, pl, taps, st);
         if (err) return err;
-        err = launch_im2col(d, src, shadow, st);
+        err = launch_im2col(d, src, shadow, pl.bf16, st);
         if (err) return err;
         return run_fwd(geom_im2col(d), pl, shadow, wpack, bias, act, dst, accumulate, st);
     }
@@ -829,10 +911,10 @@ int launch_fwd(const bcnn_b200_conv_desc *d, bool dgrad, const float *src, const
     if (err) return err;
     const FwdGeom g = geom_plain(d, dgrad);
     if (pl.nhwc) {
-        err = launch_transpose(src, shadow, g.batch, g.src_c, g.sh * g.sw, st);
+        err = launch_transpose(src, shadow, g.batch, g.src_c, g.sh * g.sw, pl.bf16, st);
         if (err) return err;
     }
-    return run_fwd(g, pl, pl.nhwc ? shadow : src, wpack, bias, act, dst, accumulate, st);
+    return run_fwd(g, pl, pl.nhwc ? shadow : (const void *)src, wpack, bias, act, dst, accumulate, st);
 }
 
 
@@ -851,7 +933,7 @@ struct WgParams {
     FastDiv d_img, d_bw;
 };
 
-template <bool NHWC>
+template <bool NHWC, bool BF16>
 __global__ void __launch_bounds__(WG_THREADS, 1)
 conv_tma_wgrad_kernel(const __grid_constant__ CUtensorMap tm_dy, const __grid_constant__ CUtensorMap tm_x,
                       const WgParams p) {
@@ -900,11 +982,12 @@ conv_tma_wgrad_kernel(const __grid_constant__ CUtensorMap tm_dy, const __grid_co
                 mbar_expect_tx(full, stage_bytes);
                 if (NHWC) {
                     const int ow0 = (int)wb * p.bw, oh0 = (int)hb * p.bh;
-                    for (int a = 0; a < 4; ++a)
-                        tma_load_4d(smem_u32(a_stage + a * p.atom_bytes), &tm_dy, co0 + 32 * a, ow0, oh0,
+                    constexpr int CA = BF16 ? 64 : 32;   // channels per atom (128-byte rows)
+                    for (int a = 0; a < TILE_M / CA; ++a)
+                        tma_load_4d(smem_u32(a_stage + a * p.atom_bytes), &tm_dy, co0 + CA * a, ow0, oh0,
                                     (int)img, full);
                     for (int b = 0; b < p.nb; ++b)
-                        tma_load_4d(smem_u32(a_stage + p.a_bytes + b * p.atom_bytes), &tm_x, ci0 + 32 * b,
+                        tma_load_4d(smem_u32(a_stage + p.a_bytes + b * p.atom_bytes), &tm_x, ci0 + CA * b,
                                     ow0 * p.stride + kw - p.pad, oh0 * p.stride + kh - p.pad, (int)img, full);
                 } else {
                     tma_load_4d(smem_u32(a_stage), &tm_dy, (int)wb * 32, (int)hb, co0, (int)img, full);
@@ -915,8 +998,9 @@ conv_tma_wgrad_kernel(const __grid_constant__ CUtensorMap tm_dy, const __grid_co
         }
     } else if (warp == 1) {
         if (lane == 0) {
-            const uint32_t idesc = make_idesc_tf32(TILE_M, n_tile, NHWC ? 1 : 0, NHWC ? 1 : 0);
-            const int mmas = p.kpos / UMMA_K;
+            const uint32_t idesc = BF16 ? make_idesc_bf16(TILE_M, n_tile, 1, 1)
+                                        : make_idesc_tf32(TILE_M, n_tile, NHWC ? 1 : 0, NHWC ? 1 : 0);
+            const int mmas = p.kpos / (BF16 ? 16 : UMMA_K);
             for (int it = 0; it < iters; ++it) {
                 const int s = it % S;
                 mbar_wait(smem_u32(bars + s), (it / S) & 1);
@@ -925,14 +1009,18 @@ conv_tma_wgrad_kernel(const __grid_constant__ CUtensorMap tm_dy, const __grid_co
                 const uint32_t b_addr = a_addr + p.a_bytes;
                 for (int g = 0; g < mmas; ++g) {
                     uint64_t da, db;
-                    if (NHWC) {  // 8 position rows = 1 KiB further inside every atom
+                    if (BF16) {  // 16 position rows = 2 KiB further inside every atom
+                        da = make_desc_mn_sw128_b16(a_addr + g * 2048, p.atom_bytes, 1024);
+                        db = make_desc_mn_sw128_b16(b_addr + g * 2048, p.atom_bytes, 1024);
+                    } else if (NHWC) {  // 8 position rows = 1 KiB further inside every atom
                         da = make_desc_mn_sw128(a_addr + g * 1024, p.atom_bytes, 512);
                         db = make_desc_mn_sw128(b_addr + g * 1024, p.atom_bytes, 512);
                     } else {
                         da = make_desc_sw128(a_addr) + (uint64_t)(2 * g);
                         db = make_desc_sw128(b_addr) + (uint64_t)(2 * g);
                     }
-                    umma_tf32(tmem_base, da, db, idesc, (it > 0 || g > 0) ? 1u : 0u);
+                    if (BF16) umma_bf16(tmem_base, da, db, idesc, (it > 0 || g > 0) ? 1u : 0u);
+                    else umma_tf32(tmem_base, da, db, idesc, (it > 0 || g > 0) ? 1u : 0u);
                 }
                 umma_commit(smem_u32(bars + S + s));
                 if (it == iters - 1) umma_commit(smem_u32(bars + 2 * S));
@@ -985,7 +1073,7 @@ wgrad_reduce_tma_kernel(float *__restrict__ gw, const float *__restrict__ partia
 }
 
 struct WgPlan {
-    bool nhwc;
+    bool nhwc, bf16;
     int n_tile, ci_tiles, co_tiles, nb;
     int view_w, view_h, out_w, out_h;   // DIRECT views
     int bw, bh, blocks_w, blocks_h;
@@ -1037,7 +1125,8 @@ bool plan_wgrad(const bcnn_b200_conv_desc *desc, WgPlan *pl) {
     pl->n_tile = n;
     pl->ci_tiles = ceil_div(d->cin, n);
     pl->co_tiles = ceil_div(d->cout, TILE_M);
-    pl->nb = ceil_div(n, 32);
+    pl->bf16 = !direct && shadow_bf16() && d->cin_phys % 8 == 0 && d->cout % 8 == 0;
+    pl->nb = ceil_div(n, pl->bf16 ? 64 : 32);
     if (direct) {
         pl->view_w = d->h * d->w; pl->view_h = 1;
         pl->out_w = d->ho * d->wo; pl->out_h = 1;
@@ -1050,19 +1139,24 @@ bool plan_wgrad(const bcnn_b200_conv_desc *desc, WgPlan *pl) {
     } else {
         // k-block = bw x bh output positions: multiple of 8, at most 64; columns past the row end
         // are out of bounds in dY and read as zero
+        // (bf16: K = 16 positions per MMA, so bw * bh is kept a multiple of 16; rows past the
+        // image are out of bounds too and read as zero)
         int bw = d->wo >= 64 ? 64 : ceil_div(d->wo, 8) * 8;
         int bh = 64 / bw;
         if (bh < 1) bh = 1;
         if (bh > d->ho) bh = d->ho;
         while (bw * d->stride > 256) bw -= 8;
+        if (pl->bf16 && (bw * bh) % 16 != 0) ++bh;
         pl->bw = bw; pl->bh = bh;
         pl->blocks_w = ceil_div(d->wo, bw);
         pl->blocks_h = ceil_div(d->ho, bh);
         pl->atom_bytes = (uint32_t)(bw * bh * 128);
-        pl->a_bytes = 4 * pl->atom_bytes;
-        pl->stage_bytes = (uint32_t)(4 + pl->nb) * pl->atom_bytes;
-        pl->shadow_x_bytes = align256((size_t)d->batch * d->cin_phys * d->h * d->w * sizeof(float));
-        pl->shadow_dy_bytes = align256((size_t)d->batch * d->cout * d->ho * d->wo * sizeof(float));
+        const int a_atoms = pl->bf16 ? 2 : 4;
+        const size_t es = pl->bf16 ? 2 : 4;
+        pl->a_bytes = a_atoms * pl->atom_bytes;
+        pl->stage_bytes = (uint32_t)(a_atoms + pl->nb) * pl->atom_bytes;
+        pl->shadow_x_bytes = align256((size_t)d->batch * d->cin_phys * d->h * d->w * es);
+        pl->shadow_dy_bytes = align256((size_t)d->batch * d->cout * d->ho * d->wo * es);
     }
     const long long kb_total = (long long)d->batch * pl->blocks_h * pl->blocks_w;
     if (kb_total >= (1LL << 31)) return false;
@@ -1097,17 +1191,17 @@ bool plan_wgrad(const bcnn_b200_conv_desc *desc, WgPlan *pl) {
     return true;
 }
 
-template <bool NHWC>
+template <bool NHWC, bool BF16>
 int launch_wgrad_kernel(const CUtensorMap &tm_dy, const CUtensorMap &tm_x, const WgParams &p, dim3 grid,
                         size_t smem, cudaStream_t st) {
     static bool attr_set = false;
     if (!attr_set) {
-        cudaError_t e = cudaFuncSetAttribute(conv_tma_wgrad_kernel<NHWC>,
+        cudaError_t e = cudaFuncSetAttribute(conv_tma_wgrad_kernel<NHWC, BF16>,
                                              cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
         if (e != cudaSuccess) return (int)e;
         attr_set = true;
     }
-    conv_tma_wgrad_kernel<NHWC><<<grid, WG_THREADS, smem, st>>>(tm_dy, tm_x, p);
+    conv_tma_wgrad_kernel<NHWC, BF16><<<grid, WG_THREADS, smem, st>>>(tm_dy, tm_x, p);
     return launched();
 }
 
@@ -1115,10 +1209,12 @@ int launch_wgrad_kernel(const CUtensorMap &tm_dy, const CUtensorMap &tm_x, const
 // col[n][oh][ow][k], k = (ci * ks + kh) * ks + kw fastest (the order of W[co][ci][kh][kw]), padded
 // with zeros to kp = 4 * kp4 columns. One thread writes one float4; a warp covers 512 contiguous
 // bytes of the buffer and gathers from a few image rows that stay in L1.
+template <bool BF16>
 __global__ void __launch_bounds__(256)
-im2col_nhwc_kernel(const float *__restrict__ x, float *__restrict__ col, int cin, int h, int w, int ks,
+im2col_nhwc_kernel(const float *__restrict__ x, void *__restrict__ col, int cin, int h, int w, int ks,
                    int stride, int pad, int kdim, uint32_t total4, FastDiv d_kp4, FastDiv d_wo,
                    FastDiv d_ho, FastDiv d_ks, FastDiv d_kk) {
+    constexpr int EPT = BF16 ? 8 : 4;   // elements per thread = one 16-byte store
     const uint32_t gstride = gridDim.x * blockDim.x;
     for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < total4; i += gstride) {
         uint32_t pos, q4, t, ow, n, oh;
@@ -1127,10 +1223,10 @@ im2col_nhwc_kernel(const float *__restrict__ x, float *__restrict__ col, int cin
         d_ho.divmod(t, n, oh);
         const float *xn = x + (size_t)n * cin * h * w;
         const int ih0 = (int)oh * stride - pad, iw0 = (int)ow * stride - pad;
-        float v[4];
+        float v[EPT];
 #pragma unroll
-        for (int e = 0; e < 4; ++e) {
-            const uint32_t k = q4 * 4 + e;
+        for (int e = 0; e < EPT; ++e) {
+            const uint32_t k = q4 * EPT + e;
             uint32_t ci, r, kh, kw;
             d_kk.divmod(k, ci, r);
             d_ks.divmod(r, kh, kw);
@@ -1138,18 +1234,32 @@ im2col_nhwc_kernel(const float *__restrict__ x, float *__restrict__ col, int cin
             const bool ok = k < (uint32_t)kdim && ih >= 0 && ih < h && iw >= 0 && iw < w;
             v[e] = ok ? __ldg(xn + ((size_t)ci * h + ih) * w + iw) : 0.f;
         }
-        *reinterpret_cast<float4 *>(col + (size_t)i * 4) = make_float4(v[0], v[1], v[2], v[3]);
+        uint8_t *out = reinterpret_cast<uint8_t *>(col) + (size_t)i * 16;
+        if constexpr (BF16)
+            *reinterpret_cast<uint4 *>(out) =
+                make_uint4(pack_bf16x2(v[0], v[1]), pack_bf16x2(v[2], v[3]), pack_bf16x2(v[4], v[5]),
+                           pack_bf16x2(v[EPT - 2], v[EPT - 1]));
+        else
+            *reinterpret_cast<float4 *>(out) = make_float4(v[0], v[1], v[2], v[3]);
     }
 }
 
-int launch_im2col(const bcnn_b200_conv_desc *d, const float *x, float *col, cudaStream_t st) {
+int launch_im2col(const bcnn_b200_conv_desc *d, const float *x, void *col, bool bf16, cudaStream_t st) {
     const int kk = d->ksize * d->ksize, kp = im2col_kp(d);
-    const size_t total4 = (size_t)d->batch * d->ho * d->wo * (kp / 4);
+    const int ept = bf16 ? 8 : 4;
+    const size_t total4 = (size_t)d->batch * d->ho * d->wo * (kp / ept);
     if (total4 >= (1ull << 31)) return (int)cudaErrorInvalidValue;
-    im2col_nhwc_kernel<<<stream_grid(total4, 256, 16), 256, 0, st>>>(
-        x, col, d->cin, d->h, d->w, d->ksize, d->stride, d->pad, d->cin * kk, (uint32_t)total4,
-        FastDiv((uint32_t)(kp / 4)), FastDiv((uint32_t)d->wo), FastDiv((uint32_t)d->ho),
-        FastDiv((uint32_t)d->ksize), FastDiv((uint32_t)kk));
+    const int grid = stream_grid(total4, 256, 16);
+    if (bf16)
+        im2col_nhwc_kernel<true><<<grid, 256, 0, st>>>(
+            x, col, d->cin, d->h, d->w, d->ksize, d->stride, d->pad, d->cin * kk, (uint32_t)total4,
+            FastDiv((uint32_t)(kp / ept)), FastDiv((uint32_t)d->wo), FastDiv((uint32_t)d->ho),
+            FastDiv((uint32_t)d->ksize), FastDiv((uint32_t)kk));
+    else
+        im2col_nhwc_kernel<false><<<grid, 256, 0, st>>>(
+            x, col, d->cin, d->h, d->w, d->ksize, d->stride, d->pad, d->cin * kk, (uint32_t)total4,
+            FastDiv((uint32_t)(kp / ept)), FastDiv((uint32_t)d->wo), FastDiv((uint32_t)d->ho),
+            FastDiv((uint32_t)d->ksize), FastDiv((uint32_t)kk));
     return launched();
 }
 
@@ -1210,20 +1320,21 @@ int conv_tma_backward_weights(const bcnn_b200_conv_desc *desc, const float *x, c
         (reinterpret_cast<uintptr_t>(workspace) & 255) != 0)
         return (int)cudaErrorMisalignedAddress;
     uint8_t *ws = reinterpret_cast<uint8_t *>(workspace);
-    float *x_shadow = reinterpret_cast<float *>(ws);
-    float *dy_shadow = reinterpret_cast<float *>(ws + pl.shadow_x_bytes);
+    void *x_shadow = ws;
+    void *dy_shadow = ws + pl.shadow_x_bytes;
     float *partial = reinterpret_cast<float *>(ws + pl.shadow_x_bytes + pl.shadow_dy_bytes);
     CUtensorMap tm_dy, tm_x;
     int err;
     if (pl.nhwc) {
-        err = d->im2col ? launch_im2col(desc, x, x_shadow, st)
-                        : launch_transpose(x, x_shadow, d->batch, d->cin, d->h * d->w, st);
+        err = d->im2col ? launch_im2col(desc, x, x_shadow, pl.bf16, st)
+                        : launch_transpose(x, x_shadow, d->batch, d->cin, d->h * d->w, pl.bf16, st);
         if (err) return err;
-        err = launch_transpose(dy, dy_shadow, d->batch, d->cout, d->ho * d->wo, st);
+        err = launch_transpose(dy, dy_shadow, d->batch, d->cout, d->ho * d->wo, pl.bf16, st);
         if (err) return err;
-        if (!make_map_nhwc(&tm_dy, dy_shadow, d->cout, d->wo, d->ho, d->batch, pl.bw, pl.bh, 1, 1, true) ||
+        if (!make_map_nhwc(&tm_dy, dy_shadow, d->cout, d->wo, d->ho, d->batch, pl.bw, pl.bh, 1, 1, true,
+                           pl.bf16) ||
             !make_map_nhwc(&tm_x, x_shadow, d->cin_phys, d->w, d->h, d->batch, pl.bw, pl.bh, 1, d->stride,
-                           true))
+                           true, pl.bf16))
             return (int)cudaErrorInvalidValue;
     } else if (!make_map_nchw(&tm_dy, dy, pl.out_w, pl.out_h, d->cout, d->batch, TILE_M, false) ||
                !make_map_nchw(&tm_x, x, pl.view_w, pl.view_h, d->cin, d->batch, pl.n_tile, false)) {
@@ -1243,8 +1354,9 @@ int conv_tma_backward_weights(const bcnn_b200_conv_desc *desc, const float *x, c
     p.d_img = FastDiv((uint32_t)(pl.blocks_h * pl.blocks_w));
     p.d_bw = FastDiv((uint32_t)pl.blocks_w);
     dim3 grid(pl.splits, pl.ci_tiles * p.kk, pl.co_tiles);
-    err = pl.nhwc ? launch_wgrad_kernel<true>(tm_dy, tm_x, p, grid, pl.smem_bytes, st)
-                  : launch_wgrad_kernel<false>(tm_dy, tm_x, p, grid, pl.smem_bytes, st);
+    err = !pl.nhwc ? launch_wgrad_kernel<false, false>(tm_dy, tm_x, p, grid, pl.smem_bytes, st)
+          : pl.bf16 ? launch_wgrad_kernel<true, true>(tm_dy, tm_x, p, grid, pl.smem_bytes, st)
+                    : launch_wgrad_kernel<true, false>(tm_dy, tm_x, p, grid, pl.smem_bytes, st);
     if (err) return err;
     if (pl.splits > 1) {
         wgrad_reduce_tma_kernel<<<stream_grid(wsize, 256), 256, 0, st>>>(gw, partial, wsize, pl.splits);

@@ -90,7 +90,7 @@ void bcnn_backward_batchnorm_gpu(bcnn_net *net, const float *x_gpu, const float 
     const float *var = (mode == BCNN_MODE_TRAIN) ? saved_var->data_gpu : bn_var->data_gpu;
     bcnn_cuda_check(bcnn_b200_bn_backward(
         x_gpu, y_gpu, dst->grad_data_gpu, dst->grad_data_gpu, mean, var, bn_scales->data_gpu,
-        bn_scales->grad_data_gpu, biases->grad_data_gpu, saved_mean->grad_data_gpu,
+        biases->data_gpu, bn_scales->grad_data_gpu, biases->grad_data_gpu, saved_mean->grad_data_gpu,
         saved_var->grad_data_gpu, n, c, hw, act, scratch_gpu, bcnn_stream(net)));
 }
 

@@ -248,8 +248,8 @@ def kernel_rooflines(lib, stream, math, peaks, batch):
     out.append(dict(kernel="bn_forward_train(stats+apply+relu)", shape=[n, c, 56, 56], bound="hbm",
                     bytes=12 * E, ms=ms))
     ms = event_time_ms(lib, stream, lambda: lib.bcnn_b200_bn_backward(
-        x.ptr, y.ptr, dy.ptr, dy.ptr, prm[0].ptr, prm[3].ptr, prm[4].ptr, prm[6].ptr, prm[7].ptr,
-        prm[8].ptr, prm[2].ptr, n, c, hw, 2, scratch.ptr, stream), 5)
+        x.ptr, y.ptr, dy.ptr, dy.ptr, prm[0].ptr, prm[3].ptr, prm[4].ptr, prm[5].ptr, prm[6].ptr,
+        prm[7].ptr, prm[8].ptr, prm[2].ptr, n, c, hw, 2, scratch.ptr, stream), 5)
     out.append(dict(kernel="bn_backward(reduce+apply, relu fused)", shape=[n, c, 56, 56],
                     bound="hbm", bytes=20 * E, ms=ms))
     # --- max pool 3x3 s2 on [n, 64, 112, 112]

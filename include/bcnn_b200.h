@@ -154,14 +154,18 @@ BCNN_B200_API int bcnn_b200_scale_bias(const float *x, float *y, const float *ga
  *   eps 1e-5, var*sqrt(var) form); dx as _normalize_backward (:283-299).
  * x is the pre-normalisation input kept by the forward pass; y the
  * post-activation output (may be NULL when act == NONE).  dx_out may alias dy.
+ * beta (may be NULL): the shift the forward used. With it, ReLU / leaky-ReLU masks
+ * are rebuilt from x with the forward's own arithmetic (y > 0 <=> gamma * xhat +
+ * beta > 0) and y is not read: 20 instead of 28 bytes per element.
  * replaces fast_mean_delta_kernel / fast_variance_delta_kernel /
  * _norm_backward_kernel / bcnn_grad_scales_kernel. */
 BCNN_B200_API int bcnn_b200_bn_backward(const float *x, const float *y, float *dy,
                                         float *dx_out, const float *mean,
                                         const float *var, const float *gamma,
-                                        float *g_gamma, float *g_beta, float *d_mean,
-                                        float *d_var, int n, int c, int hw, int act,
-                                        float *scratch, void *stream);
+                                        const float *beta, float *g_gamma,
+                                        float *g_beta, float *d_mean, float *d_var,
+                                        int n, int c, int hw, int act, float *scratch,
+                                        void *stream);
 
 /* ---- convolution ------------------------------------------------------- */
 /* 1 when pass (0 fprop, 1 dgrad, 2 wgrad) of `d` runs on the tcgen05 kernel under

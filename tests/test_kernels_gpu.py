@@ -220,7 +220,8 @@ def test_bn_forward_train_and_valid(n, c, hw):
 
 @pytest.mark.parametrize("n,c,hw", BN_SHAPES)
 @pytest.mark.parametrize("act", ["none", "relu", "lrelu"])
-def test_bn_backward_fused_with_activation(n, c, hw, act):
+@pytest.mark.parametrize("remask", [False, True])
+def test_bn_backward_fused_with_activation(n, c, hw, act, remask):
     lib, orc = capi.b200(), oracle()
     r = rng(n * 5 + c * 11 + hw)
     x = f32(r.normal(0.1, 1.0, size=(n, c, hw)))
@@ -241,12 +242,16 @@ def test_bn_backward_fused_with_activation(n, c, hw, act):
     orc.orc_bn_backward(p(g_ref), n, c, hw, p(gamma), p(gg), p(gb), p(sm), p(sv), p(dm), p(dv),
                         p(xn), p(xc))
     dx, dyv, dg = dev(x), dev(y), dev(g)
-    dsm, dsv, dgam = dev(sm), dev(sv), dev(gamma)
+    dsm, dsv, dgam, dbeta = dev(sm), dev(sv), dev(gamma), dev(beta)
     dgg, dgb, ddm, ddv = dev(gg0), dev(gb0), dev_zeros(c), dev_zeros(c)
     scratch = dev_zeros(lib.bcnn_b200_bn_scratch_floats(c))
-    check(lib.bcnn_b200_bn_backward(dx.ptr, dyv.ptr if act != "none" else None, dg.ptr, dg.ptr,
-                                    dsm.ptr, dsv.ptr, dgam.ptr, dgg.ptr, dgb.ptr, ddm.ptr, ddv.ptr,
-                                    n, c, hw, ACT[act], scratch.ptr, None))
+    # remask: the ReLU mask is rebuilt from x and beta, y is never read (pass a NULL y to prove it)
+    y_ptr = dyv.ptr if act != "none" and not remask else None
+    if remask and act == "none":
+        pytest.skip("no activation: nothing to rebuild")
+    check(lib.bcnn_b200_bn_backward(dx.ptr, y_ptr, dg.ptr, dg.ptr, dsm.ptr, dsv.ptr, dgam.ptr,
+                                    dbeta.ptr if remask else None, dgg.ptr, dgb.ptr, ddm.ptr,
+                                    ddv.ptr, n, c, hw, ACT[act], scratch.ptr, None))
     tol = 5e-5  # two chained FP32 reductions with a different (tree) summation order
     assert_close(dgb.download(), gb, tol, "g_beta")
     assert_close(dgg.download(), gg, tol, "g_gamma")
