@@ -374,9 +374,16 @@ class ConvDesc(C.Structure):
         return cls(batch, cin, h, w, cout, ho, wo, ksize, stride, pad, groups)
 
 
+class ConvShadows(C.Structure):
+    """bcnn_b200_conv_shadows: NHWC shadow storage kept between the passes of one layer."""
+    _fields_ = [("x", C.c_void_p), ("x_bytes", C.c_size_t), ("x_fmt", C.c_int),
+                ("dy", C.c_void_p), ("dy_bytes", C.c_size_t), ("dy_fmt", C.c_int)]
+
+
 def bind_kernel_abi(lib: C.CDLL) -> None:
     vp, i, f, sz = C.c_void_p, C.c_int, C.c_float, C.c_size_t
     dp = C.POINTER(ConvDesc)
+    shp = C.POINTER(ConvShadows)
     sigs = {
         "bcnn_b200_axpy": (i, [vp, vp, sz, f, vp]),
         "bcnn_b200_maxpool_forward": (i, [vp, vp, vp, i, i, i, i, i, i, i, i, vp]),
@@ -398,6 +405,11 @@ def bind_kernel_abi(lib: C.CDLL) -> None:
         "bcnn_b200_conv_forward": (i, [dp, vp, vp, vp, i, vp, vp, sz, i, vp]),
         "bcnn_b200_conv_backward_data": (i, [dp, vp, vp, vp, i, vp, sz, i, vp]),
         "bcnn_b200_conv_backward_weights": (i, [dp, vp, vp, vp, vp, sz, i, vp]),
+        "bcnn_b200_conv_x_shadow_bytes": (sz, [dp, i]),
+        "bcnn_b200_conv_dy_shadow_bytes": (sz, [dp, i]),
+        "bcnn_b200_conv_forward_sh": (i, [dp, vp, vp, vp, i, vp, vp, sz, i, shp, vp]),
+        "bcnn_b200_conv_backward_data_sh": (i, [dp, vp, vp, vp, i, vp, sz, i, shp, vp]),
+        "bcnn_b200_conv_backward_weights_sh": (i, [dp, vp, vp, vp, vp, sz, i, shp, vp]),
         "bcnn_b200_depthwise_forward": (i, [vp, vp, vp, i, vp, i, i, i, i, i, i, i, vp]),
         "bcnn_b200_depthwise_backward": (i, [vp, vp, vp, vp, vp, i, i, i, i, i, i, i, vp, sz,
                                              vp]),

@@ -23,36 +23,68 @@ extern "C" size_t bcnn_b200_conv_workspace_bytes(const bcnn_b200_conv_desc *d, i
     return a > c ? a : c;
 }
 
+extern "C" size_t bcnn_b200_conv_x_shadow_bytes(const bcnn_b200_conv_desc *d, int math) {
+    return math == BCNN_B200_MATH_TC ? conv_tma_x_shadow_bytes(d) : 0;
+}
+
+extern "C" size_t bcnn_b200_conv_dy_shadow_bytes(const bcnn_b200_conv_desc *d, int math) {
+    return math == BCNN_B200_MATH_TC ? conv_tma_dy_shadow_bytes(d) : 0;
+}
+
 extern "C" int bcnn_b200_conv_forward(const bcnn_b200_conv_desc *d, const float *x,
                                       const float *w, const float *bias, int act, float *y,
                                       void *workspace, size_t workspace_bytes, int math,
                                       void *stream) {
-    cudaStream_t st = as_stream(stream);
-    if (math == BCNN_B200_MATH_TC && conv_tma_supports_fprop(d))
-        return conv_tma_forward(d, x, w, bias, act, y, workspace, workspace_bytes, st);
-    if (math == BCNN_B200_MATH_TC && conv_tc_supports_fprop(d))
-        return conv_tc_forward(d, x, w, bias, act, y, workspace, workspace_bytes, st);
-    return conv_simt_forward(d, x, w, bias, act, y, st);
+    return bcnn_b200_conv_forward_sh(d, x, w, bias, act, y, workspace, workspace_bytes, math,
+                                     nullptr, stream);
 }
 
 extern "C" int bcnn_b200_conv_backward_data(const bcnn_b200_conv_desc *d, const float *w,
                                             const float *dy, float *dx, int accumulate,
                                             void *workspace, size_t workspace_bytes, int math,
                                             void *stream) {
-    cudaStream_t st = as_stream(stream);
-    if (math == BCNN_B200_MATH_TC && conv_tma_supports_dgrad(d))
-        return conv_tma_backward_data(d, w, dy, dx, accumulate, workspace, workspace_bytes, st);
-    if (math == BCNN_B200_MATH_TC && conv_tc_supports_dgrad(d))
-        return conv_tc_backward_data(d, w, dy, dx, accumulate, workspace, workspace_bytes, st);
-    return conv_simt_backward_data(d, w, dy, dx, accumulate, st);
+    return bcnn_b200_conv_backward_data_sh(d, w, dy, dx, accumulate, workspace, workspace_bytes,
+                                           math, nullptr, stream);
 }
 
 extern "C" int bcnn_b200_conv_backward_weights(const bcnn_b200_conv_desc *d, const float *x,
                                                const float *dy, float *gw, void *workspace,
                                                size_t workspace_bytes, int math, void *stream) {
+    return bcnn_b200_conv_backward_weights_sh(d, x, dy, gw, workspace, workspace_bytes, math,
+                                              nullptr, stream);
+}
+
+extern "C" int bcnn_b200_conv_forward_sh(const bcnn_b200_conv_desc *d, const float *x,
+                                         const float *w, const float *bias, int act, float *y,
+                                         void *workspace, size_t workspace_bytes, int math,
+                                         bcnn_b200_conv_shadows *sh, void *stream) {
+    cudaStream_t st = as_stream(stream);
+    if (math == BCNN_B200_MATH_TC && conv_tma_supports_fprop(d))
+        return conv_tma_forward(d, x, w, bias, act, y, workspace, workspace_bytes, sh, st);
+    if (math == BCNN_B200_MATH_TC && conv_tc_supports_fprop(d))
+        return conv_tc_forward(d, x, w, bias, act, y, workspace, workspace_bytes, st);
+    return conv_simt_forward(d, x, w, bias, act, y, st);
+}
+
+extern "C" int bcnn_b200_conv_backward_data_sh(const bcnn_b200_conv_desc *d, const float *w,
+                                               const float *dy, float *dx, int accumulate,
+                                               void *workspace, size_t workspace_bytes, int math,
+                                               bcnn_b200_conv_shadows *sh, void *stream) {
+    cudaStream_t st = as_stream(stream);
+    if (math == BCNN_B200_MATH_TC && conv_tma_supports_dgrad(d))
+        return conv_tma_backward_data(d, w, dy, dx, accumulate, workspace, workspace_bytes, sh, st);
+    if (math == BCNN_B200_MATH_TC && conv_tc_supports_dgrad(d))
+        return conv_tc_backward_data(d, w, dy, dx, accumulate, workspace, workspace_bytes, st);
+    return conv_simt_backward_data(d, w, dy, dx, accumulate, st);
+}
+
+extern "C" int bcnn_b200_conv_backward_weights_sh(const bcnn_b200_conv_desc *d, const float *x,
+                                                  const float *dy, float *gw, void *workspace,
+                                                  size_t workspace_bytes, int math,
+                                                  bcnn_b200_conv_shadows *sh, void *stream) {
     cudaStream_t st = as_stream(stream);
     if (math == BCNN_B200_MATH_TC && conv_tma_supports_wgrad(d))
-        return conv_tma_backward_weights(d, x, dy, gw, workspace, workspace_bytes, st);
+        return conv_tma_backward_weights(d, x, dy, gw, workspace, workspace_bytes, sh, st);
     if (math == BCNN_B200_MATH_TC && conv_tc_supports_wgrad(d))
         return conv_tc_backward_weights(d, x, dy, gw, workspace, workspace_bytes, st);
     return conv_simt_backward_weights(d, x, dy, gw, workspace, workspace_bytes, st);

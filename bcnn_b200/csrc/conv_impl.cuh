@@ -39,14 +39,17 @@ bool conv_tma_supports_fprop(const bcnn_b200_conv_desc *d);
 bool conv_tma_supports_dgrad(const bcnn_b200_conv_desc *d);
 bool conv_tma_supports_wgrad(const bcnn_b200_conv_desc *d);
 size_t conv_tma_workspace_bytes(const bcnn_b200_conv_desc *d);
+size_t conv_tma_x_shadow_bytes(const bcnn_b200_conv_desc *d);
+size_t conv_tma_dy_shadow_bytes(const bcnn_b200_conv_desc *d);
+// sh (may be NULL): NHWC shadows kept between the passes of one layer (bcnn_b200_conv_shadows)
 int conv_tma_forward(const bcnn_b200_conv_desc *d, const float *x, const float *w,
                      const float *bias, int act, float *y, void *workspace,
-                     size_t workspace_bytes, cudaStream_t st);
+                     size_t workspace_bytes, bcnn_b200_conv_shadows *sh, cudaStream_t st);
 int conv_tma_backward_data(const bcnn_b200_conv_desc *d, const float *w, const float *dy,
                            float *dx, int accumulate, void *workspace, size_t workspace_bytes,
-                           cudaStream_t st);
+                           bcnn_b200_conv_shadows *sh, cudaStream_t st);
 int conv_tma_backward_weights(const bcnn_b200_conv_desc *d, const float *x, const float *dy,
                               float *gw, void *workspace, size_t workspace_bytes,
-                              cudaStream_t st);
+                              bcnn_b200_conv_shadows *sh, cudaStream_t st);
 
 }  // namespace b200

@@ -832,14 +832,36 @@ int launch_pack(const float *w, uint8_t *wpack, bool dgrad, int cout, int cin, i
 
 int launch_im2col(const bcnn_b200_conv_desc *d, const float *x, void *col, bool bf16, cudaStream_t st);
 
+// The dY shadow of a layer's backward pass: taken from `sh` when an earlier call of the same pass
+// left one of the right format there, else transposed into sh->dy (kept for the next call) or, with no
+// shadow storage, into `fallback` (the workspace).
+int dy_shadow(const float *dy, int batch, int c, int plane, bool bf16, size_t bytes,
+              bcnn_b200_conv_shadows *sh, void *fallback, const void **out, cudaStream_t st) {
+    const int fmt = bf16 ? BCNN_B200_SHADOW_NHWC_BF16 : BCNN_B200_SHADOW_NHWC_F32;
+    if (sh && sh->dy && sh->dy_fmt == fmt && sh->dy_bytes >= bytes) {
+        *out = sh->dy;
+        return 0;
+    }
+    void *dst = fallback;
+    if (sh && sh->dy && sh->dy_bytes >= bytes && (reinterpret_cast<uintptr_t>(sh->dy) & 255) == 0) {
+        dst = sh->dy;
+        sh->dy_fmt = fmt;
+    }
+    *out = dst;
+    return launch_transpose(dy, dst, batch, c, plane, bf16, st);
+}
+
 int launch_strided_dgrad(const bcnn_b200_conv_desc *d, const float *dy, const float *w, float *dx,
-                         int accumulate, void *workspace, size_t workspace_bytes, cudaStream_t st) {
+                         int accumulate, void *workspace, size_t workspace_bytes,
+                         bcnn_b200_conv_shadows *sh, cudaStream_t st) {
     const size_t need = strided_dgrad_bytes(d);
     if (!need || workspace == nullptr || workspace_bytes < need) return (int)cudaErrorInvalidValue;
     if ((reinterpret_cast<uintptr_t>(workspace) & 255) != 0) return (int)cudaErrorMisalignedAddress;
-    void *shadow = workspace;
     const bool bf16 = shadow_bf16() && d->cout % 8 == 0;   // what plan_fwd decides for every class
-    int err = launch_transpose(dy, shadow, d->batch, d->cout, d->ho * d->wo, bf16, st);
+    const void *shadow = nullptr;
+    int err = dy_shadow(dy, d->batch, d->cout, d->ho * d->wo, bf16,
+                        align256((size_t)d->batch * d->cout * d->ho * d->wo * (bf16 ? 2 : 4)), sh,
+                        workspace, &shadow, st);
     if (err) return err;
     const int s = d->stride, kk = d->ksize * d->ksize;
     // classes without taps (e.g. 1x1 stride 2: three of four) receive no gradient
@@ -881,17 +903,21 @@ int launch_strided_dgrad(const bcnn_b200_conv_desc *d, const float *dy, const fl
 
 int launch_fwd(const bcnn_b200_conv_desc *d, bool dgrad, const float *src, const float *w,
                const float *bias, int act, float *dst, int accumulate, void *workspace,
-               size_t workspace_bytes, cudaStream_t st) {
+               size_t workspace_bytes, bcnn_b200_conv_shadows *sh, cudaStream_t st) {
     FwdPlan pl;
     const FwdRoute route = route_fwd(d, dgrad, &pl);
     if (route == ROUTE_NONE) return (int)cudaErrorInvalidValue;
     if ((reinterpret_cast<uintptr_t>(src) & 15) != 0) return (int)cudaErrorMisalignedAddress;
     if (route == ROUTE_STRIDED_DGRAD)
-        return launch_strided_dgrad(d, src, w, dst, accumulate, workspace, workspace_bytes, st);
+        return launch_strided_dgrad(d, src, w, dst, accumulate, workspace, workspace_bytes, sh, st);
     if (workspace == nullptr || workspace_bytes < pl.shadow_bytes + pl.wpack_bytes)
         return (int)cudaErrorInvalidValue;
     if ((reinterpret_cast<uintptr_t>(workspace) & 255) != 0) return (int)cudaErrorMisalignedAddress;
     void *shadow = workspace;
+    // fprop: the x shadow goes to the layer's own storage when there is one (wgrad reuses it)
+    const bool keep_x = !dgrad && sh && sh->x && sh->x_bytes >= pl.shadow_bytes &&
+                        (reinterpret_cast<uintptr_t>(sh->x) & 255) == 0;
+    if (keep_x) shadow = sh->x;
     uint8_t *wpack = reinterpret_cast<uint8_t *>(workspace) + pl.shadow_bytes;
     const int kk = d->ksize * d->ksize;
     TapMap taps;
@@ -903,6 +929,7 @@ int launch_fwd(const bcnn_b200_conv_desc *d, bool dgrad, const float *src, const
         if (err) return err;
         err = launch_im2col(d, src, shadow, pl.bf16, st);
         if (err) return err;
+        if (keep_x) sh->x_fmt = pl.bf16 ? BCNN_B200_SHADOW_IM2COL_BF16 : BCNN_B200_SHADOW_IM2COL_F32;
         return run_fwd(geom_im2col(d), pl, shadow, wpack, bias, act, dst, accumulate, st);
     }
     taps.n = kk;
@@ -910,11 +937,18 @@ int launch_fwd(const bcnn_b200_conv_desc *d, bool dgrad, const float *src, const
     err = launch_pack(w, wpack, dgrad, d->cout, d->cin, kk, pl, taps, st);
     if (err) return err;
     const FwdGeom g = geom_plain(d, dgrad);
-    if (pl.nhwc) {
+    const void *operand = src;
+    if (pl.nhwc && dgrad) {
+        err = dy_shadow(src, g.batch, g.src_c, g.sh * g.sw, pl.bf16, pl.shadow_bytes, sh, workspace,
+                        &operand, st);
+        if (err) return err;
+    } else if (pl.nhwc) {
         err = launch_transpose(src, shadow, g.batch, g.src_c, g.sh * g.sw, pl.bf16, st);
         if (err) return err;
+        if (keep_x) sh->x_fmt = pl.bf16 ? BCNN_B200_SHADOW_NHWC_BF16 : BCNN_B200_SHADOW_NHWC_F32;
+        operand = shadow;
     }
-    return run_fwd(g, pl, pl.nhwc ? shadow : (const void *)src, wpack, bias, act, dst, accumulate, st);
+    return run_fwd(g, pl, operand, wpack, bias, act, dst, accumulate, st);
 }
 
 
@@ -1298,18 +1332,42 @@ size_t conv_tma_workspace_bytes(const bcnn_b200_conv_desc *d) {
     return need;
 }
 
+// Shadow storage a layer may keep (0 = the TMA route of `d` uses no such shadow).
+size_t conv_tma_x_shadow_bytes(const bcnn_b200_conv_desc *d) {
+    FwdPlan pl;
+    const FwdRoute r = route_fwd(d, false, &pl);
+    return (r == ROUTE_PLAIN || r == ROUTE_IM2COL) ? pl.shadow_bytes : 0;
+}
+size_t conv_tma_dy_shadow_bytes(const bcnn_b200_conv_desc *d) {
+    size_t need = 0;
+    FwdPlan pl;
+    const FwdRoute r = route_fwd(d, true, &pl);
+    if (r == ROUTE_STRIDED_DGRAD) {
+        const bool bf16 = shadow_bf16() && d->cout % 8 == 0;
+        need = align256((size_t)d->batch * d->cout * d->ho * d->wo * (bf16 ? 2 : 4));
+    } else if (r == ROUTE_PLAIN) {
+        need = pl.shadow_bytes;
+    }
+    WgPlan wp;
+    if (plan_wgrad(d, &wp) && wp.shadow_dy_bytes > need) need = wp.shadow_dy_bytes;
+    return need;
+}
+
 int conv_tma_forward(const bcnn_b200_conv_desc *d, const float *x, const float *w, const float *bias,
-                     int act, float *y, void *workspace, size_t workspace_bytes, cudaStream_t st) {
-    return launch_fwd(d, false, x, w, bias, act, y, 0, workspace, workspace_bytes, st);
+                     int act, float *y, void *workspace, size_t workspace_bytes,
+                     bcnn_b200_conv_shadows *sh, cudaStream_t st) {
+    return launch_fwd(d, false, x, w, bias, act, y, 0, workspace, workspace_bytes, sh, st);
 }
 
 int conv_tma_backward_data(const bcnn_b200_conv_desc *d, const float *w, const float *dy, float *dx,
-                           int accumulate, void *workspace, size_t workspace_bytes, cudaStream_t st) {
-    return launch_fwd(d, true, dy, w, nullptr, 0, dx, accumulate, workspace, workspace_bytes, st);
+                           int accumulate, void *workspace, size_t workspace_bytes,
+                           bcnn_b200_conv_shadows *sh, cudaStream_t st) {
+    return launch_fwd(d, true, dy, w, nullptr, 0, dx, accumulate, workspace, workspace_bytes, sh, st);
 }
 
 int conv_tma_backward_weights(const bcnn_b200_conv_desc *desc, const float *x, const float *dy, float *gw,
-                              void *workspace, size_t workspace_bytes, cudaStream_t st) {
+                              void *workspace, size_t workspace_bytes, bcnn_b200_conv_shadows *sh,
+                              cudaStream_t st) {
     WgPlan pl;
     if (!plan_wgrad(desc, &pl)) return (int)cudaErrorInvalidValue;
     const WgEff e = wg_effective(desc);
@@ -1320,18 +1378,26 @@ int conv_tma_backward_weights(const bcnn_b200_conv_desc *desc, const float *x, c
         (reinterpret_cast<uintptr_t>(workspace) & 255) != 0)
         return (int)cudaErrorMisalignedAddress;
     uint8_t *ws = reinterpret_cast<uint8_t *>(workspace);
-    void *x_shadow = ws;
-    void *dy_shadow = ws + pl.shadow_x_bytes;
+    const void *x_shadow = ws;
+    const void *dy_sh = ws + pl.shadow_x_bytes;
     float *partial = reinterpret_cast<float *>(ws + pl.shadow_x_bytes + pl.shadow_dy_bytes);
     CUtensorMap tm_dy, tm_x;
     int err;
     if (pl.nhwc) {
-        err = d->im2col ? launch_im2col(desc, x, x_shadow, pl.bf16, st)
-                        : launch_transpose(x, x_shadow, d->batch, d->cin, d->h * d->w, pl.bf16, st);
+        // x: the shadow (or im2col buffer) the forward pass of this layer kept, when its format fits
+        const int x_fmt = d->im2col ? (pl.bf16 ? BCNN_B200_SHADOW_IM2COL_BF16 : BCNN_B200_SHADOW_IM2COL_F32)
+                                    : (pl.bf16 ? BCNN_B200_SHADOW_NHWC_BF16 : BCNN_B200_SHADOW_NHWC_F32);
+        if (sh && sh->x && sh->x_fmt == x_fmt && sh->x_bytes >= pl.shadow_x_bytes) {
+            x_shadow = sh->x;
+        } else {
+            err = d->im2col ? launch_im2col(desc, x, ws, pl.bf16, st)
+                            : launch_transpose(x, ws, d->batch, d->cin, d->h * d->w, pl.bf16, st);
+            if (err) return err;
+        }
+        err = dy_shadow(dy, d->batch, d->cout, d->ho * d->wo, pl.bf16, pl.shadow_dy_bytes, sh,
+                        ws + pl.shadow_x_bytes, &dy_sh, st);
         if (err) return err;
-        err = launch_transpose(dy, dy_shadow, d->batch, d->cout, d->ho * d->wo, pl.bf16, st);
-        if (err) return err;
-        if (!make_map_nhwc(&tm_dy, dy_shadow, d->cout, d->wo, d->ho, d->batch, pl.bw, pl.bh, 1, 1, true,
+        if (!make_map_nhwc(&tm_dy, dy_sh, d->cout, d->wo, d->ho, d->batch, pl.bw, pl.bh, 1, 1, true,
                            pl.bf16) ||
             !make_map_nhwc(&tm_x, x_shadow, d->cin_phys, d->w, d->h, d->batch, pl.bw, pl.bh, 1, d->stride,
                            true, pl.bf16))

@@ -83,6 +83,7 @@ void bcnn_end_net(bcnn_net **net) {
         free(ctx->grad_fresh);
         free(ctx->consumers);
         bcnn_b200_free(ctx->workspace_gpu);
+        bcnn_b200_free(ctx->dy_shadow_gpu);
         bcnn_b200_stream_destroy(ctx->stream);
         free(ctx);
     }
@@ -147,6 +148,12 @@ bcnn_status bcnn_compile_net(bcnn_net *net) {
         BCNN_CHECK(ctx->workspace_gpu != NULL, BCNN_CUDA_FAILED_ALLOC);
     }
     ctx->workspace_size = (int)(ctx->workspace_bytes / sizeof(float));
+    bcnn_b200_free(ctx->dy_shadow_gpu);
+    ctx->dy_shadow_gpu = NULL;
+    if (ctx->dy_shadow_bytes && net->mode == BCNN_MODE_TRAIN) {
+        ctx->dy_shadow_gpu = bcnn_b200_malloc(ctx->dy_shadow_bytes);
+        BCNN_CHECK(ctx->dy_shadow_gpu != NULL, BCNN_CUDA_FAILED_ALLOC);
+    }
     return BCNN_SUCCESS;
 }
 
@@ -316,6 +323,11 @@ int bcnn_net_num_consumers(bcnn_net *net, int index) {
             if (node->src[j] == index) ++count;
     }
     return count;
+}
+
+void bcnn_net_require_dy_shadow(bcnn_net *net, size_t bytes) {
+    bcnn_cuda_context *ctx = bcnn_ctx(net);
+    if (bytes > ctx->dy_shadow_bytes) ctx->dy_shadow_bytes = bytes;
 }
 
 void bcnn_net_require_workspace(bcnn_net *net, size_t bytes) {

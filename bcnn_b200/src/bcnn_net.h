@@ -24,6 +24,9 @@ typedef struct bcnn_cuda_context {
     float *workspace_gpu; /* conv workspace shared by all conv nodes */
     /* --- B200 extensions --- */
     size_t workspace_bytes;   /* max over conv nodes, sized at construction */
+    void *dy_shadow_gpu;      /* NHWC shadow of the output gradient of the conv node running
+                                 backward (shared by its wgrad and dgrad), max over nodes */
+    size_t dy_shadow_bytes;
     void *stream;             /* compute stream (cudaStream_t) */
     int conv_math;            /* BCNN_B200_MATH_* */
     int reference_quirks;     /* see bcnn_b200_set_reference_quirks; default 1 */
@@ -92,6 +95,7 @@ int bcnn_net_grad_accumulate(bcnn_net *net, int index);
 void bcnn_net_grad_prepare_accumulate(bcnn_net *net, int index);
 /* Grow the shared conv workspace requirement. */
 void bcnn_net_require_workspace(bcnn_net *net, size_t bytes);
+void bcnn_net_require_dy_shadow(bcnn_net *net, size_t bytes);
 /* Global batch (local batch x data-parallel world) and the factor gradients are scaled
  * with after an SGD step (momentum, or momentum / world under data parallelism). */
 int bcnn_net_global_batch(bcnn_net *net);

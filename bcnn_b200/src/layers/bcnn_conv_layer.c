@@ -79,6 +79,7 @@ bcnn_status bcnn_add_convolutional_layer(bcnn_net *net, int n, int size, int str
     param->workspace_size =
         bcnn_b200_conv_workspace_bytes(&desc, BCNN_B200_MATH_TC) / sizeof(float);
     bcnn_net_require_workspace(net, param->workspace_size * sizeof(float));
+    bcnn_net_require_dy_shadow(net, bcnn_b200_conv_dy_shadow_bytes(&desc, BCNN_B200_MATH_TC));
     param->reduce_scratch_gpu =
         (float *)bcnn_b200_malloc(bcnn_b200_bn_scratch_floats(n) * sizeof(float));
     BCNN_CHECK(param->reduce_scratch_gpu != NULL, BCNN_CUDA_FAILED_ALLOC);
@@ -127,17 +128,31 @@ void bcnn_forward_conv_layer_gpu(bcnn_net *net, bcnn_node *node) {
     const bcnn_activation act = param->activation;
     /* PReLU needs per-channel slopes: run it as a separate pass after the fused part */
     const bcnn_activation fused_act = (act == BCNN_ACT_PRELU) ? BCNN_ACT_NONE : act;
+    /* TRAIN: keep the NHWC shadow of the input for this step's wgrad */
+    bcnn_b200_conv_shadows *sh = NULL;
+    if (net->mode == BCNN_MODE_TRAIN && ctx->conv_math == BCNN_B200_MATH_TC) {
+        sh = &param->shadows;
+        if (!sh->x) {
+            size_t bytes = bcnn_b200_conv_x_shadow_bytes(&param->desc, ctx->conv_math);
+            if (bytes) {
+                sh->x = bcnn_b200_malloc(bytes);
+                sh->x_bytes = sh->x ? bytes : 0; /* without storage the passes transpose again */
+            }
+        }
+        sh->x_fmt = BCNN_B200_SHADOW_NONE;
+    }
 
     if (!param->batch_norm) {
-        bcnn_cuda_check(bcnn_b200_conv_forward(&param->desc, src->data_gpu, weights->data_gpu,
-                                               biases->data_gpu, fused_act, dst->data_gpu,
-                                               ctx->workspace_gpu, ctx->workspace_bytes,
-                                               ctx->conv_math, stream));
+        bcnn_cuda_check(bcnn_b200_conv_forward_sh(&param->desc, src->data_gpu, weights->data_gpu,
+                                                  biases->data_gpu, fused_act, dst->data_gpu,
+                                                  ctx->workspace_gpu, ctx->workspace_bytes,
+                                                  ctx->conv_math, sh, stream));
     } else {
         float *raw = param->bn_workspace_gpu ? param->bn_workspace_gpu : dst->data_gpu;
-        bcnn_cuda_check(bcnn_b200_conv_forward(&param->desc, src->data_gpu, weights->data_gpu,
-                                               NULL, BCNN_ACT_NONE, raw, ctx->workspace_gpu,
-                                               ctx->workspace_bytes, ctx->conv_math, stream));
+        bcnn_cuda_check(bcnn_b200_conv_forward_sh(&param->desc, src->data_gpu, weights->data_gpu,
+                                                  NULL, BCNN_ACT_NONE, raw, ctx->workspace_gpu,
+                                                  ctx->workspace_bytes, ctx->conv_math, sh,
+                                                  stream));
         bcnn_forward_batchnorm_gpu(net, raw, dst, &t[node->src[3]], &t[node->src[4]],
                                    &t[node->src[5]], biases, &param->saved_mean,
                                    &param->saved_variance, param->reduce_scratch_gpu, net->mode,
@@ -178,19 +193,25 @@ void bcnn_backward_conv_layer_gpu(bcnn_net *net, bcnn_node *node) {
                                                    dst->h * dst->w, param->reduce_scratch_gpu,
                                                    stream));
     }
-    bcnn_cuda_check(bcnn_b200_conv_backward_weights(
+    /* the dy shadow written by wgrad serves dgrad below; the x shadow is the forward's */
+    bcnn_b200_conv_shadows *sh = &param->shadows;
+    sh->dy = ctx->dy_shadow_gpu;
+    sh->dy_bytes = ctx->dy_shadow_gpu ? ctx->dy_shadow_bytes : 0;
+    sh->dy_fmt = BCNN_B200_SHADOW_NONE;
+    bcnn_cuda_check(bcnn_b200_conv_backward_weights_sh(
         &param->desc, src->data_gpu, dst->grad_data_gpu, weights->grad_data_gpu,
-        ctx->workspace_gpu, ctx->workspace_bytes, ctx->conv_math, stream));
+        ctx->workspace_gpu, ctx->workspace_bytes, ctx->conv_math, sh, stream));
     if (src->grad_data_gpu) {
         /* reference semantics: overwrite. With the quirks off, a source read by several
          * nodes (residual branches) accumulates instead: the first backward writer of the
          * step overwrites the stale buffer, every later consumer's contribution is summed. */
         int accumulate = bcnn_net_grad_accumulate(net, node->src[0]);
         if (ctx->reference_quirks) accumulate = 0;
-        bcnn_cuda_check(bcnn_b200_conv_backward_data(
+        bcnn_cuda_check(bcnn_b200_conv_backward_data_sh(
             &param->desc, weights->data_gpu, dst->grad_data_gpu, src->grad_data_gpu, accumulate,
-            ctx->workspace_gpu, ctx->workspace_bytes, ctx->conv_math, stream));
+            ctx->workspace_gpu, ctx->workspace_bytes, ctx->conv_math, sh, stream));
     }
+    sh->dy_fmt = BCNN_B200_SHADOW_NONE;
 }
 
 void bcnn_forward_conv_layer(bcnn_net *net, bcnn_node *node) {
@@ -221,6 +242,7 @@ void bcnn_release_param_conv_layer(bcnn_node *node) {
     bcnn_tensor_destroy(&param->saved_mean);
     bcnn_tensor_destroy(&param->saved_variance);
     bcnn_b200_free(param->bn_workspace_gpu);
+    bcnn_b200_free(param->shadows.x);
     bcnn_b200_free(param->reduce_scratch_gpu);
     /* conv_workspace_gpu belongs to the net */
 }

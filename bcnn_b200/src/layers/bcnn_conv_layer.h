@@ -44,6 +44,10 @@ typedef struct bcnn_conv_param {
     /* ---- B200 additions ---- */
     bcnn_b200_conv_desc desc;
     float *reduce_scratch_gpu; /* per-layer scratch of the per-channel reductions */
+    /* NHWC shadows kept across the passes of a training step: x belongs to the layer
+     * (written by forward, read by wgrad), dy points into the net-level buffer (written by
+     * wgrad, read by dgrad of the same backward call) */
+    bcnn_b200_conv_shadows shadows;
 } bcnn_conv_param;
 
 void bcnn_forward_conv_layer(bcnn_net *net, bcnn_node *node);

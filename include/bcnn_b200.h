@@ -41,6 +41,27 @@ typedef struct bcnn_b200_conv_desc {
     int groups;                /* cin % groups == cout % groups == 0 */
 } bcnn_b200_conv_desc;
 
+/* NHWC shadows of one convolution layer, kept between the passes of a training step.
+ * The TMA cannot shift an NCHW row by one pixel, so k > 1 / strided / odd-plane layers read
+ * an NHWC (BF16 or FP32) copy of their operand.  A layer that owns storage for them hands
+ * it to the *_sh entry points: fprop leaves the x shadow (or the im2col buffer of a thin
+ * first layer) in `x` for wgrad, wgrad leaves the dy shadow in `dy` for dgrad, so each
+ * operand is transposed once per step instead of once per pass.  `*_fmt` says what the
+ * buffer currently holds (BCNN_B200_SHADOW_*); the caller resets it to NONE whenever the
+ * FP32 tensor it mirrors changes.  No reference counterpart (its im2col workspace,
+ * src/layers/bcnn_conv_layer.c:141-144, plays the same role per image). */
+enum {
+    BCNN_B200_SHADOW_NONE = 0,
+    BCNN_B200_SHADOW_NHWC_F32 = 1,
+    BCNN_B200_SHADOW_NHWC_BF16 = 2,
+    BCNN_B200_SHADOW_IM2COL_F32 = 3,
+    BCNN_B200_SHADOW_IM2COL_BF16 = 4
+};
+typedef struct bcnn_b200_conv_shadows {
+    void *x;  size_t x_bytes;  int x_fmt;  /* 256-byte aligned device memory or NULL */
+    void *dy; size_t dy_bytes; int dy_fmt;
+} bcnn_b200_conv_shadows;
+
 /* ---- device / stream / memory helpers --------------------------------- */
 /* replaces bcnn_cuda_set_device, src/bcnn_utils.c:201 */
 BCNN_B200_API int bcnn_b200_set_device(int device);
@@ -174,6 +195,9 @@ BCNN_B200_API int bcnn_b200_conv_uses_tensor_cores(const bcnn_b200_conv_desc *d,
 /* Bytes of device workspace the three conv entry points may use for `d`. */
 BCNN_B200_API size_t bcnn_b200_conv_workspace_bytes(const bcnn_b200_conv_desc *d,
                                                     int math);
+/* Bytes of shadow storage worth keeping for `d` (0: its passes read NCHW directly). */
+BCNN_B200_API size_t bcnn_b200_conv_x_shadow_bytes(const bcnn_b200_conv_desc *d, int math);
+BCNN_B200_API size_t bcnn_b200_conv_dy_shadow_bytes(const bcnn_b200_conv_desc *d, int math);
 /* y = act(W (*) x + bias)   (bias may be NULL, act may be NONE).
  * replaces the per-image bcnn_cuda_im2col + bcnn_cuda_gemm loop and
  * bcnn_cuda_add_bias, src/layers/bcnn_conv_layer.c:628-656 (and the cuDNN
@@ -197,6 +221,24 @@ BCNN_B200_API int bcnn_b200_conv_backward_weights(const bcnn_b200_conv_desc *d,
                                                   float *gw, void *workspace,
                                                   size_t workspace_bytes, int math,
                                                   void *stream);
+/* The same three passes with shadow storage (sh may be NULL = the plain entry points). */
+BCNN_B200_API int bcnn_b200_conv_forward_sh(const bcnn_b200_conv_desc *d, const float *x,
+                                            const float *w, const float *bias, int act,
+                                            float *y, void *workspace,
+                                            size_t workspace_bytes, int math,
+                                            bcnn_b200_conv_shadows *sh, void *stream);
+BCNN_B200_API int bcnn_b200_conv_backward_data_sh(const bcnn_b200_conv_desc *d,
+                                                  const float *w, const float *dy,
+                                                  float *dx, int accumulate,
+                                                  void *workspace, size_t workspace_bytes,
+                                                  int math, bcnn_b200_conv_shadows *sh,
+                                                  void *stream);
+BCNN_B200_API int bcnn_b200_conv_backward_weights_sh(const bcnn_b200_conv_desc *d,
+                                                     const float *x, const float *dy,
+                                                     float *gw, void *workspace,
+                                                     size_t workspace_bytes, int math,
+                                                     bcnn_b200_conv_shadows *sh,
+                                                     void *stream);
 
 /* ---- depthwise convolution --------------------------------------------- */
 /* y = act(dw(x, w) + bias); replaces _bcnn_forward_depthwise_conv_weight_kernel,

@@ -4,6 +4,8 @@ oracle restatement (oracle/bcnn_oracle.c) on identical seeded inputs.
 Bar: bit-exact for max-pool values and int32 argmax; 1e-5 normalised (tests/helpers.py
 rel_err) for floating point on the FP32 path; 2e-2 on the tensor-core path.
 """
+import ctypes as C
+
 import numpy as np
 import pytest
 
@@ -385,6 +387,69 @@ def test_conv_linearity_at_resnet_size():
     via_dx = float(np.sum(x1.astype(np.float64) * ddx.download(np.float32, x1.shape)))
     via_gw = float(np.sum(wt.astype(np.float64) * dgw.download(np.float32, wt.shape)))
     assert abs(lhs - via_dx) <= 1e-4 * abs(lhs) and abs(lhs - via_gw) <= 1e-4 * abs(lhs)
+
+
+@pytest.mark.parametrize("case", [
+    (4, 32, 14, 14, 48, 3, 1, 1, 1),    # 3x3: x shadow fprop -> wgrad, dy shadow wgrad -> dgrad
+    (8, 32, 16, 16, 64, 3, 2, 1, 1),    # strided dgrad classes read the kept dy shadow
+    (16, 64, 7, 7, 32, 1, 1, 0, 1),     # 1x1 on an odd plane (49 positions): shadow route
+    (8, 64, 8, 8, 32, 1, 1, 0, 1),      # DIRECT route: shadows must stay untouched
+    (32, 3, 32, 32, 32, 7, 2, 3, 1),    # thin first layer: the im2col buffer is the x shadow
+])
+def test_conv_shadow_storage_matches_plain_entry_points(case):
+    """The *_sh entry points keep NHWC shadows between passes (one transpose per operand and
+    step); their results are bit-identical to the plain entry points, which transpose per pass."""
+    lib = capi.b200()
+    batch, cin, h, w, cout, k, s, pad, groups = case
+    d = capi.ConvDesc.make(*case)
+    r = rng(sum(case))
+    x = f32(r.uniform(-1, 1, size=(batch, cin, h, w)))
+    wt = f32(r.uniform(-1, 1, size=(cout, cin, k, k)) / np.sqrt(cin * k * k))
+    dy = f32(r.uniform(-1, 1, size=(batch, cout, d.ho, d.wo)))
+    math = capi.MATH_TC
+    ws_bytes = lib.bcnn_b200_conv_workspace_bytes(d, math)
+    ws = capi.DeviceBuffer(nbytes=max(ws_bytes, 4))
+    xb = lib.bcnn_b200_conv_x_shadow_bytes(d, math)
+    yb = lib.bcnn_b200_conv_dy_shadow_bytes(d, math)
+    xs, ys = capi.DeviceBuffer(nbytes=max(xb, 4)), capi.DeviceBuffer(nbytes=max(yb, 4))
+    sh = capi.ConvShadows(xs.ptr if xb else None, xb, 0, ys.ptr if yb else None, yb, 0)
+    dxv, dwt, ddy = dev(x), dev(wt), dev(dy)
+
+    def run(use_sh):
+        shp = C.byref(sh) if use_sh else None
+        y, gw, gx = dev_zeros(dy.size), dev_zeros(wt.size), dev_zeros(x.size)
+        if use_sh:
+            check(lib.bcnn_b200_conv_forward_sh(d, dxv.ptr, dwt.ptr, None, 0, y.ptr, ws.ptr, ws_bytes,
+                                                math, shp, None))
+            fmt_after_fwd = sh.x_fmt
+            check(lib.bcnn_b200_conv_backward_weights_sh(d, dxv.ptr, ddy.ptr, gw.ptr, ws.ptr,
+                                                         ws_bytes, math, shp, None))
+            fmt_after_wgrad = sh.dy_fmt
+            check(lib.bcnn_b200_conv_backward_data_sh(d, dwt.ptr, ddy.ptr, gx.ptr, 0, ws.ptr,
+                                                      ws_bytes, math, shp, None))
+            assert (fmt_after_fwd != 0) == (xb > 0), "fprop must leave its shadow when storage exists"
+            assert (fmt_after_wgrad != 0) == (yb > 0), "wgrad must leave the dy shadow for dgrad"
+        else:
+            check(lib.bcnn_b200_conv_forward(d, dxv.ptr, dwt.ptr, None, 0, y.ptr, ws.ptr, ws_bytes,
+                                             math, None))
+            check(lib.bcnn_b200_conv_backward_weights(d, dxv.ptr, ddy.ptr, gw.ptr, ws.ptr, ws_bytes,
+                                                      math, None))
+            check(lib.bcnn_b200_conv_backward_data(d, dwt.ptr, ddy.ptr, gx.ptr, 0, ws.ptr, ws_bytes,
+                                                   math, None))
+        return (y.download(np.float32, dy.shape), gw.download(np.float32, wt.shape),
+                gx.download(np.float32, x.shape))
+
+    plain, kept = run(False), run(True)
+    for a, b, what in zip(plain, kept, ("fprop", "wgrad", "dgrad")):
+        assert np.array_equal(a, b), f"{what}: shadow storage changed the result"
+    if k == 1 and s == 1 and (h * w) % 4 == 0:
+        assert xb == 0 and sh.x_fmt == 0 and sh.dy_fmt == 0
+    # a stale x shadow (format NONE) must be ignored, not read
+    sh.x_fmt = 0
+    gw2 = dev_zeros(wt.size)
+    check(lib.bcnn_b200_conv_backward_weights_sh(d, dxv.ptr, ddy.ptr, gw2.ptr, ws.ptr, ws_bytes, math,
+                                                 C.byref(sh), None))
+    assert np.array_equal(gw2.download(np.float32, wt.shape), plain[1])
 
 
 # ------------------------------------------------------------------ depthwise
