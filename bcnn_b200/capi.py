@@ -408,6 +408,7 @@ def bind_kernel_abi(lib: C.CDLL) -> None:
         "bcnn_b200_conv_x_shadow_bytes": (sz, [dp, i]),
         "bcnn_b200_conv_dy_shadow_bytes": (sz, [dp, i]),
         "bcnn_b200_conv_forward_sh": (i, [dp, vp, vp, vp, i, vp, vp, sz, i, shp, vp]),
+        "bcnn_b200_conv_forward_bn_stats": (i, [dp, vp, vp, vp, vp, sz, i, shp, vp, vp, vp, vp, vp, vp]),
         "bcnn_b200_conv_backward_data_sh": (i, [dp, vp, vp, vp, i, vp, sz, i, shp, vp]),
         "bcnn_b200_conv_backward_weights_sh": (i, [dp, vp, vp, vp, vp, sz, i, shp, vp]),
         "bcnn_b200_depthwise_forward": (i, [vp, vp, vp, i, vp, i, i, i, i, i, i, i, vp]),

@@ -13,6 +13,7 @@
 //   backward: src/layers/bcnn_batchnorm_layer.c:263-332 + src/kernels/bcnn_mat.c:692-727
 //             (eps 1e-5, var*sqrt(var) + 1e-5 in the variance term)
 #include "common.cuh"
+#include "conv_impl.cuh"
 
 using namespace b200;
 
@@ -120,6 +121,77 @@ bn_stats_kernel(const float *__restrict__ x, int n, int c, int hw, float *__rest
             run_var[ch] = run_var[ch] * 0.9f + 0.1f * var;
         }
         tickets[ch] = 0;
+    }
+}
+
+// ---- forward statistics from the partial sums of a convolution epilogue ----------------
+// partial[(row * 2 + k) * c + ch]; grid = (channel groups of 32, row segments). A warp reads 128
+// contiguous bytes per row; warps, segments and rows are folded in a fixed order.
+__global__ void __launch_bounds__(256)
+bn_stats_finalize_kernel(const float *__restrict__ partial, int rows, int c, float inv_count,
+                         float *__restrict__ saved_mean, float *__restrict__ saved_var,
+                         float *__restrict__ run_mean, float *__restrict__ run_var,
+                         float *__restrict__ seg_sums, unsigned int *__restrict__ tickets) {
+    __shared__ float red[8][32][2];
+    __shared__ bool last;
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    const int ch = blockIdx.x * 32 + lane;
+    const int seg = blockIdx.y, segs = gridDim.y;
+    const int r0 = (int)(((long long)rows * seg) / segs), r1 = (int)(((long long)rows * (seg + 1)) / segs);
+    float s1 = 0.f, s2 = 0.f;
+    if (ch < c) {
+        const size_t pitch = (size_t)2 * c;
+        int r = r0 + w;
+        for (; r + 24 < r1; r += 32) {  // four independent rows in flight per thread
+            const float *q = partial + (size_t)r * pitch + ch;
+            const float a0 = __ldcs(q), b0 = __ldcs(q + c);
+            const float a1 = __ldcs(q + 8 * pitch), b1 = __ldcs(q + 8 * pitch + c);
+            const float a2 = __ldcs(q + 16 * pitch), b2 = __ldcs(q + 16 * pitch + c);
+            const float a3 = __ldcs(q + 24 * pitch), b3 = __ldcs(q + 24 * pitch + c);
+            s1 += (a0 + a1) + (a2 + a3);
+            s2 += (b0 + b1) + (b2 + b3);
+        }
+        for (; r < r1; r += 8) {
+            const float *q = partial + (size_t)r * pitch + ch;
+            s1 += __ldcs(q);
+            s2 += __ldcs(q + c);
+        }
+    }
+    red[w][lane][0] = s1;
+    red[w][lane][1] = s2;
+    __syncthreads();
+    if (w == 0) {
+        for (int i = 1; i < 8; ++i) {
+            s1 += red[i][lane][0];
+            s2 += red[i][lane][1];
+        }
+        if (ch < c) {
+            seg_sums[((size_t)ch * MAX_SPLITS + seg) * 2 + 0] = s1;
+            seg_sums[((size_t)ch * MAX_SPLITS + seg) * 2 + 1] = s2;
+        }
+        __threadfence();
+        __syncwarp();
+        if (lane == 0) last = (atomicAdd(tickets + blockIdx.x, 1u) == (unsigned)segs - 1);
+    }
+    __syncthreads();
+    if (last && w == 0) {
+        __threadfence();
+        if (ch < c) {
+            float t1 = 0.f, t2 = 0.f;
+            for (int i = 0; i < segs; ++i) {
+                t1 += __ldcg(seg_sums + ((size_t)ch * MAX_SPLITS + i) * 2 + 0);
+                t2 += __ldcg(seg_sums + ((size_t)ch * MAX_SPLITS + i) * 2 + 1);
+            }
+            const float mean = t1 * inv_count;
+            const float var = t2 * inv_count - mean * mean;
+            saved_mean[ch] = mean;
+            saved_var[ch] = var;
+            if (run_mean) {
+                run_mean[ch] = run_mean[ch] * 0.9f + 0.1f * mean;
+                run_var[ch] = run_var[ch] * 0.9f + 0.1f * var;
+            }
+        }
+        if (lane == 0) tickets[blockIdx.x] = 0;
     }
 }
 
@@ -369,6 +441,22 @@ extern "C" int bcnn_b200_bn_stats(const float *x, int n, int c, int hw, float *s
                                                         run_mean, run_var, scratch, tickets,
                                                         FastDiv(hw), FastDiv(hw >> 2 ? hw >> 2 : 1),
                                                         (hw % 4) == 0 && aligned16(x));
+    return launched();
+}
+
+int b200::bn_stats_from_partials(const float *partial, int rows, int c, double count,
+                                 float *saved_mean, float *saved_var, float *run_mean,
+                                 float *run_var, float *scratch, cudaStream_t st) {
+    if (rows <= 0 || c <= 0) return 0;
+    unsigned int *tickets = reinterpret_cast<unsigned int *>(scratch + (size_t)c * MAX_SPLITS * 4);
+    const int groups = ceil_div(c, 32);
+    int segs = ceil_div(2 * sm_count(), groups);
+    if (segs > rows / 16) segs = rows / 16;
+    if (segs > MAX_SPLITS) segs = MAX_SPLITS;
+    if (segs < 1) segs = 1;
+    dim3 grid(groups, segs);
+    bn_stats_finalize_kernel<<<grid, 256, 0, st>>>(partial, rows, c, (float)(1.0 / count), saved_mean,
+                                                   saved_var, run_mean, run_var, scratch, tickets);
     return launched();
 }
 

@@ -1,6 +1,8 @@
 // conv.cu -- C-ABI convolution entry points (include/bcnn_b200.h) and the dispatcher
 // between the FP32 SIMT implicit GEMM (conv_simt.cu) and the BF16 tcgen05 implicit GEMM
 // (conv_tc.cu). There is no CPU fallback and no cuDNN / cuBLAS on either path.
+#include <cstdlib>
+
 #include "common.cuh"
 #include "conv_impl.cuh"
 
@@ -64,6 +66,36 @@ extern "C" int bcnn_b200_conv_forward_sh(const bcnn_b200_conv_desc *d, const flo
     if (math == BCNN_B200_MATH_TC && conv_tc_supports_fprop(d))
         return conv_tc_forward(d, x, w, bias, act, y, workspace, workspace_bytes, st);
     return conv_simt_forward(d, x, w, bias, act, y, st);
+}
+
+extern "C" int bcnn_b200_conv_forward_bn_stats(const bcnn_b200_conv_desc *d, const float *x,
+                                               const float *w, float *y, void *workspace,
+                                               size_t workspace_bytes, int math,
+                                               bcnn_b200_conv_shadows *sh, float *saved_mean,
+                                               float *saved_var, float *run_mean, float *run_var,
+                                               float *scratch, void *stream) {
+    cudaStream_t st = as_stream(stream);
+    static int unfused = -1;
+    if (unfused < 0) {
+        const char *e = getenv("BCNN_B200_NO_FUSED_BN_STATS");
+        unfused = (e && e[0] && e[0] != '0') ? 1 : 0;
+    }
+    if (!unfused && math == BCNN_B200_MATH_TC && conv_tma_supports_fprop(d)) {
+        const float *partial = nullptr;
+        int rows = 0;
+        int err = conv_tma_forward_stats(d, x, w, y, workspace, workspace_bytes, sh, &partial, &rows, st);
+        if (err) return err;
+        if (partial)
+            return bn_stats_from_partials(partial, rows, d->cout,
+                                          (double)d->batch * d->ho * d->wo, saved_mean, saved_var,
+                                          run_mean, run_var, scratch, st);
+    } else {
+        int err = bcnn_b200_conv_forward_sh(d, x, w, nullptr, 0, y, workspace, workspace_bytes, math, sh,
+                                            stream);
+        if (err) return err;
+    }
+    return bcnn_b200_bn_stats(y, d->batch, d->cout, d->ho * d->wo, saved_mean, saved_var, run_mean,
+                              run_var, scratch, stream);
 }
 
 extern "C" int bcnn_b200_conv_backward_data_sh(const bcnn_b200_conv_desc *d, const float *w,

@@ -45,11 +45,20 @@ size_t conv_tma_dy_shadow_bytes(const bcnn_b200_conv_desc *d);
 int conv_tma_forward(const bcnn_b200_conv_desc *d, const float *x, const float *w,
                      const float *bias, int act, float *y, void *workspace,
                      size_t workspace_bytes, bcnn_b200_conv_shadows *sh, cudaStream_t st);
+int conv_tma_forward_stats(const bcnn_b200_conv_desc *d, const float *x, const float *w, float *y,
+                           void *workspace, size_t workspace_bytes, bcnn_b200_conv_shadows *sh,
+                           const float **stat_partial, int *stat_rows, cudaStream_t st);
 int conv_tma_backward_data(const bcnn_b200_conv_desc *d, const float *w, const float *dy,
                            float *dx, int accumulate, void *workspace, size_t workspace_bytes,
                            bcnn_b200_conv_shadows *sh, cudaStream_t st);
 int conv_tma_backward_weights(const bcnn_b200_conv_desc *d, const float *x, const float *dy,
                               float *gw, void *workspace, size_t workspace_bytes,
                               bcnn_b200_conv_shadows *sh, cudaStream_t st);
+
+// batchnorm.cu: TRAIN statistics from the per-tile partial sums a convolution epilogue left
+// (partial[(row * 2 + {0: sum, 1: sum of squares}) * c + channel]), folded in a fixed order.
+int bn_stats_from_partials(const float *partial, int rows, int c, double count, float *saved_mean,
+                           float *saved_var, float *run_mean, float *run_var, float *scratch,
+                           cudaStream_t st);
 
 }  // namespace b200

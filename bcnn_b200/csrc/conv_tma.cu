@@ -293,6 +293,13 @@ pack_weights_tf32_kernel(const float *__restrict__ w, uint8_t *__restrict__ wpac
 // ------------------------------------------------------------------ fprop / stride-1 dgrad
 struct FwdParams {
     float *dst;
+    // batch-norm statistics fused into the epilogue (nullptr = off): every epilogue warp sums the
+    // accumulator rows (and their squares) of all the tiles its CTA walks and leaves one row per
+    // (CTA of the channel tile, TMEM lane quarter): stat_partial[(row * 2 + {0, 1}) * dst_c + channel],
+    // row = (blockIdx.x / n_tiles) * 4 + quarter; the grid is a multiple of n_tiles, so a CTA stays on
+    // one channel tile. Every entry is written exactly once; bn_stats_from_partials folds the rows in
+    // a fixed order.
+    float *stat_partial;
     const float *bias;
     const uint8_t *wpack;
     int act, accumulate;
@@ -315,8 +322,11 @@ struct FwdParams {
 
 constexpr int FWD_EPI_WARPS = 8;
 constexpr int FWD_THREADS = 64 + 32 * FWD_EPI_WARPS;
+// fused batch-norm statistics: per epilogue warp the running sums of its <= 4 column chunks
+constexpr int STAT_ACC_FLOATS = 4 * 2 * 32;
+constexpr int STAT_PAD_BYTES = FWD_EPI_WARPS * STAT_ACC_FLOATS * 4;
 
-struct TileCoord { int tile_n, img, w0, h0; };
+struct TileCoord { int tile_n, m_tile, img, w0, h0; };
 
 template <bool NHWC>
 __device__ __forceinline__ TileCoord decode_tile(const FwdParams &p, int tile) {
@@ -326,6 +336,7 @@ __device__ __forceinline__ TileCoord decode_tile(const FwdParams &p, int tile) {
     p.d_tiles_h.divmod(rest2, tb, th);
     TileCoord c;
     c.tile_n = (int)tn;
+    c.m_tile = (int)rest;
     if (NHWC) {
         c.img = (int)tb * p.tn; c.w0 = (int)tw * p.tw; c.h0 = (int)th * p.th;
     } else {
@@ -476,6 +487,12 @@ conv_tma_fwd_kernel(const __grid_constant__ CUtensorMap tm_src, const FwdParams 
         const int ew = warp - 2;
         const int q = warp & 3;
         const int half = ew >> 2;
+        // fused statistics: running sums of this warp, [chunk of the warp][sum | sum of squares][lane]
+        float *stat_acc = reinterpret_cast<float *>(smem + (size_t)S * stage_bytes + 256) + ew * STAT_ACC_FLOATS;
+        if (p.stat_partial != nullptr) {
+#pragma unroll
+            for (int i = 0; i < STAT_ACC_FLOATS / 32; ++i) stat_acc[i * 32 + lane] = 0.f;
+        }
         const uint32_t plane = (uint32_t)p.dst_plane;
         const int chunks32 = (n_tile + 31) / 32;
         // position of this thread's tile row relative to the tile origin
@@ -530,11 +547,50 @@ conv_tma_fwd_kernel(const __grid_constant__ CUtensorMap tm_src, const FwdParams 
                         }
                     }
                 }
+                if (p.stat_partial != nullptr) {
+                    // Per-channel sum / sum of squares over this warp's 32 positions: a transposing
+                    // butterfly (31 shuffles per quantity) leaves channel ch0 + lane in lane `lane`;
+                    // the warp keeps running sums over all its tiles (a CTA sees one channel tile:
+                    // the grid is a multiple of n_tiles) in a private shared-memory row.
+                    float s1[32], s2[32];
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) {
+                        const float x = valid ? __uint_as_float(v[j]) : 0.f;
+                        s1[j] = x;
+                        s2[j] = x * x;
+                    }
+#pragma unroll
+                    for (int off = 16; off >= 1; off >>= 1) {
+                        const bool hi = (lane & off) != 0;
+#pragma unroll
+                        for (int i = 0; i < off; ++i) {
+                            const float k1 = hi ? s1[i + off] : s1[i], g1 = hi ? s1[i] : s1[i + off];
+                            const float k2 = hi ? s2[i + off] : s2[i], g2 = hi ? s2[i] : s2[i + off];
+                            s1[i] = k1 + __shfl_xor_sync(0xffffffffu, g1, off);
+                            s2[i] = k2 + __shfl_xor_sync(0xffffffffu, g2, off);
+                        }
+                    }
+                    float *acc = stat_acc + (ck >> 1) * 64 + lane;
+                    acc[0] += s1[0];
+                    acc[32] += s2[0];
+                }
             }
             // all of this warp's tcgen05.ld have completed (wait::ld inside tmem_ld32)
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(smem_u32(acc_empty + buf));
+        }
+        if (p.stat_partial != nullptr) {
+            // row = (CTA index among those of this channel tile) * 4 + lane quarter
+            const uint32_t tile_n = blockIdx.x % (uint32_t)p.n_tiles;
+            const size_t row = (size_t)(blockIdx.x / (uint32_t)p.n_tiles) * 4 + (size_t)q;
+            for (int ck = half; ck < chunks32; ck += 2) {
+                const int ch = (int)tile_n * n_tile + ck * 32 + lane;
+                if (lane < n_tile - ck * 32 && ch < p.dst_c) {
+                    p.stat_partial[(row * 2 + 0) * p.dst_c + ch] = stat_acc[(ck >> 1) * 64 + lane];
+                    p.stat_partial[(row * 2 + 1) * p.dst_c + ch] = stat_acc[(ck >> 1) * 64 + 32 + lane];
+                }
+            }
         }
     }
     tc_fence_before();
@@ -562,6 +618,8 @@ struct FwdPlan {
     int tiles_w, tiles_h, tiles_b;
     uint32_t a_bytes;
     size_t shadow_bytes, wpack_bytes, smem_bytes;
+    int stat_rows;           // rows of the fused batch-norm partials: 4 per position tile
+    size_t stat_bytes;
 };
 
 bool tma_disabled() {
@@ -658,8 +716,16 @@ bool plan_fwd(const FwdGeom &g, FwdPlan *pl) {
     pl->wpack_bytes = align256((size_t)pl->n_tiles * pl->k_blocks * n * BLOCK_K * sizeof(float));
     pl->smem_bytes = (size_t)stages * stage + 1024 + 256;
     const long long total = (long long)pl->n_tiles * pl->tiles_w * pl->tiles_h * pl->tiles_b;
-    return total < (1LL << 31);
+    if (total >= (1LL << 31)) return false;
+    // fused statistics: grid = a multiple of n_tiles (0 rows: more channel tiles than SMs, no fusion)
+    const long long per_tile = sm_count() / pl->n_tiles;
+    const long long m_tiles = total / pl->n_tiles;
+    pl->stat_rows = (int)(4 * (per_tile < m_tiles ? per_tile : m_tiles));
+    pl->stat_bytes = align256((size_t)pl->stat_rows * 2 * g.dst_c * sizeof(float));
+    return true;
 }
+
+int stat_grid(const FwdPlan &pl) { return pl.stat_rows / 4 * pl.n_tiles; }
 
 // ---- how a (descriptor, pass) maps onto launches of the kernel
 enum FwdRoute { ROUTE_NONE = 0, ROUTE_PLAIN, ROUTE_IM2COL, ROUTE_STRIDED_DGRAD };
@@ -770,7 +836,7 @@ FwdRoute route_fwd(const bcnn_b200_conv_desc *d, bool dgrad, FwdPlan *pl) {
 }
 
 template <bool NHWC, bool BF16>
-int launch_fwd_kernel(const CUtensorMap &tm, const FwdParams &p, size_t smem, cudaStream_t st) {
+int launch_fwd_kernel(const CUtensorMap &tm, const FwdParams &p, size_t smem, cudaStream_t st, int grid_override) {
     static bool attr_set = false;
     if (!attr_set) {
         cudaError_t e = cudaFuncSetAttribute(conv_tma_fwd_kernel<NHWC, BF16>,
@@ -778,14 +844,15 @@ int launch_fwd_kernel(const CUtensorMap &tm, const FwdParams &p, size_t smem, cu
         if (e != cudaSuccess) return (int)e;
         attr_set = true;
     }
-    const int grid = p.total_tiles < sm_count() ? p.total_tiles : sm_count();
+    int grid = p.total_tiles < sm_count() ? p.total_tiles : sm_count();
+    if (grid_override > 0) grid = grid_override;
     conv_tma_fwd_kernel<NHWC, BF16><<<grid, FWD_THREADS, smem, st>>>(tm, p);
     return launched();
 }
 
 // src: the NCHW tensor (DIRECT plans) or the NHWC-shaped shadow (all others).
 int run_fwd(const FwdGeom &g, const FwdPlan &pl, const void *src, const uint8_t *wpack, const float *bias,
-            int act, float *dst, int accumulate, cudaStream_t st) {
+            int act, float *dst, int accumulate, cudaStream_t st, float *stat_partial = nullptr) {
     CUtensorMap tm;
     if (pl.nhwc) {
         if (!make_map_nhwc(&tm, src, g.src_c, g.sw, g.sh, g.batch, pl.tw, pl.th, pl.tn, g.stride, false,
@@ -797,6 +864,7 @@ int run_fwd(const FwdGeom &g, const FwdPlan &pl, const void *src, const uint8_t 
     }
     FwdParams p;
     p.dst = dst; p.bias = bias; p.wpack = wpack; p.act = act; p.accumulate = accumulate;
+    p.stat_partial = stat_partial;
     p.src_c = g.src_c; p.dst_c = g.dst_c; p.batch = g.batch;
     p.out_w = pl.out_w; p.out_h = pl.out_h;
     p.ksh = g.ksh; p.ksw = g.ksw; p.pad_h = g.pad_h; p.pad_w = g.pad_w; p.stride = g.stride;
@@ -813,9 +881,11 @@ int run_fwd(const FwdGeom &g, const FwdPlan &pl, const void *src, const uint8_t 
     p.d_tiles_h = FastDiv((uint32_t)pl.tiles_h);
     p.d_tw = FastDiv((uint32_t)pl.tw);
     p.d_th = FastDiv((uint32_t)pl.th);
-    if (!pl.nhwc) return launch_fwd_kernel<false, false>(tm, p, pl.smem_bytes, st);
-    return pl.bf16 ? launch_fwd_kernel<true, true>(tm, p, pl.smem_bytes, st)
-                   : launch_fwd_kernel<true, false>(tm, p, pl.smem_bytes, st);
+    const size_t smem = pl.smem_bytes + (stat_partial ? STAT_PAD_BYTES : 0);
+    const int grid = stat_partial ? stat_grid(pl) : 0;
+    if (!pl.nhwc) return launch_fwd_kernel<false, false>(tm, p, smem, st, grid);
+    return pl.bf16 ? launch_fwd_kernel<true, true>(tm, p, smem, st, grid)
+                   : launch_fwd_kernel<true, false>(tm, p, smem, st, grid);
 }
 
 int launch_pack(const float *w, uint8_t *wpack, bool dgrad, int cout, int cin, int kk, const FwdPlan &pl,
@@ -903,7 +973,8 @@ int launch_strided_dgrad(const bcnn_b200_conv_desc *d, const float *dy, const fl
 
 int launch_fwd(const bcnn_b200_conv_desc *d, bool dgrad, const float *src, const float *w,
                const float *bias, int act, float *dst, int accumulate, void *workspace,
-               size_t workspace_bytes, bcnn_b200_conv_shadows *sh, cudaStream_t st) {
+               size_t workspace_bytes, bcnn_b200_conv_shadows *sh, cudaStream_t st,
+               const float **stat_partial = nullptr, int *stat_rows = nullptr) {
     FwdPlan pl;
     const FwdRoute route = route_fwd(d, dgrad, &pl);
     if (route == ROUTE_NONE) return (int)cudaErrorInvalidValue;
@@ -913,6 +984,15 @@ int launch_fwd(const bcnn_b200_conv_desc *d, bool dgrad, const float *src, const
     if (workspace == nullptr || workspace_bytes < pl.shadow_bytes + pl.wpack_bytes)
         return (int)cudaErrorInvalidValue;
     if ((reinterpret_cast<uintptr_t>(workspace) & 255) != 0) return (int)cudaErrorMisalignedAddress;
+    // fused batch-norm partials live behind the packed weights when the workspace has the room
+    float *stats = nullptr;
+    if (stat_partial && !dgrad && !accumulate && pl.stat_rows > 0 &&
+        workspace_bytes >= pl.shadow_bytes + pl.wpack_bytes + pl.stat_bytes) {
+        stats = reinterpret_cast<float *>(reinterpret_cast<uint8_t *>(workspace) + pl.shadow_bytes +
+                                          pl.wpack_bytes);
+        *stat_partial = stats;
+        *stat_rows = pl.stat_rows;
+    }
     void *shadow = workspace;
     // fprop: the x shadow goes to the layer's own storage when there is one (wgrad reuses it)
     const bool keep_x = !dgrad && sh && sh->x && sh->x_bytes >= pl.shadow_bytes &&
@@ -930,7 +1010,7 @@ int launch_fwd(const bcnn_b200_conv_desc *d, bool dgrad, const float *src, const
         err = launch_im2col(d, src, shadow, pl.bf16, st);
         if (err) return err;
         if (keep_x) sh->x_fmt = pl.bf16 ? BCNN_B200_SHADOW_IM2COL_BF16 : BCNN_B200_SHADOW_IM2COL_F32;
-        return run_fwd(geom_im2col(d), pl, shadow, wpack, bias, act, dst, accumulate, st);
+        return run_fwd(geom_im2col(d), pl, shadow, wpack, bias, act, dst, accumulate, st, stats);
     }
     taps.n = kk;
     for (int t = 0; t < kk; ++t) taps.idx[t] = (short)(dgrad ? kk - 1 - t : t);
@@ -948,7 +1028,7 @@ int launch_fwd(const bcnn_b200_conv_desc *d, bool dgrad, const float *src, const
         if (keep_x) sh->x_fmt = pl.bf16 ? BCNN_B200_SHADOW_NHWC_BF16 : BCNN_B200_SHADOW_NHWC_F32;
         operand = shadow;
     }
-    return run_fwd(g, pl, operand, wpack, bias, act, dst, accumulate, st);
+    return run_fwd(g, pl, operand, wpack, bias, act, dst, accumulate, st, stats);
 }
 
 
@@ -1321,7 +1401,7 @@ size_t conv_tma_workspace_bytes(const bcnn_b200_conv_desc *d) {
         const FwdRoute r = route_fwd(d, dgrad != 0, &pl);
         size_t b = 0;
         if (r == ROUTE_STRIDED_DGRAD) b = strided_dgrad_bytes(d);
-        else if (r != ROUTE_NONE) b = pl.shadow_bytes + pl.wpack_bytes;
+        else if (r != ROUTE_NONE) b = pl.shadow_bytes + pl.wpack_bytes + (dgrad ? 0 : pl.stat_bytes);
         if (b > need) need = b;
     }
     WgPlan wp;
@@ -1357,6 +1437,18 @@ int conv_tma_forward(const bcnn_b200_conv_desc *d, const float *x, const float *
                      int act, float *y, void *workspace, size_t workspace_bytes,
                      bcnn_b200_conv_shadows *sh, cudaStream_t st) {
     return launch_fwd(d, false, x, w, bias, act, y, 0, workspace, workspace_bytes, sh, st);
+}
+
+// fprop without bias / activation that also leaves the batch-norm partial sums of y in the workspace:
+// *stat_partial stays nullptr when the workspace is too small for them (the caller then runs the
+// stand-alone statistics kernel over y).
+int conv_tma_forward_stats(const bcnn_b200_conv_desc *d, const float *x, const float *w, float *y,
+                           void *workspace, size_t workspace_bytes, bcnn_b200_conv_shadows *sh,
+                           const float **stat_partial, int *stat_rows, cudaStream_t st) {
+    *stat_partial = nullptr;
+    *stat_rows = 0;
+    return launch_fwd(d, false, x, w, nullptr, 0, y, 0, workspace, workspace_bytes, sh, st, stat_partial,
+                      stat_rows);
 }
 
 int conv_tma_backward_data(const bcnn_b200_conv_desc *d, const float *w, const float *dy, float *dx,

@@ -149,14 +149,28 @@ void bcnn_forward_conv_layer_gpu(bcnn_net *net, bcnn_node *node) {
                                                   ctx->conv_math, sh, stream));
     } else {
         float *raw = param->bn_workspace_gpu ? param->bn_workspace_gpu : dst->data_gpu;
-        bcnn_cuda_check(bcnn_b200_conv_forward_sh(&param->desc, src->data_gpu, weights->data_gpu,
-                                                  NULL, BCNN_ACT_NONE, raw, ctx->workspace_gpu,
-                                                  ctx->workspace_bytes, ctx->conv_math, sh,
-                                                  stream));
-        bcnn_forward_batchnorm_gpu(net, raw, dst, &t[node->src[3]], &t[node->src[4]],
-                                   &t[node->src[5]], biases, &param->saved_mean,
-                                   &param->saved_variance, param->reduce_scratch_gpu, net->mode,
-                                   fused_act);
+        if (net->mode == BCNN_MODE_TRAIN) {
+            /* batch statistics come out of the convolution epilogue; one pass normalises */
+            bcnn_tensor *run_mean = &t[node->src[3]], *run_var = &t[node->src[4]];
+            bcnn_cuda_check(bcnn_b200_conv_forward_bn_stats(
+                &param->desc, src->data_gpu, weights->data_gpu, raw, ctx->workspace_gpu,
+                ctx->workspace_bytes, ctx->conv_math, sh, param->saved_mean.data_gpu,
+                param->saved_variance.data_gpu, run_mean->data_gpu, run_var->data_gpu,
+                param->reduce_scratch_gpu, stream));
+            bcnn_cuda_check(bcnn_b200_bn_apply(raw, dst->data_gpu, param->saved_mean.data_gpu,
+                                               param->saved_variance.data_gpu,
+                                               t[node->src[5]].data_gpu, biases->data_gpu, dst->n,
+                                               dst->c, dst->h * dst->w, fused_act, stream));
+        } else {
+            bcnn_cuda_check(bcnn_b200_conv_forward_sh(&param->desc, src->data_gpu,
+                                                      weights->data_gpu, NULL, BCNN_ACT_NONE, raw,
+                                                      ctx->workspace_gpu, ctx->workspace_bytes,
+                                                      ctx->conv_math, sh, stream));
+            bcnn_forward_batchnorm_gpu(net, raw, dst, &t[node->src[3]], &t[node->src[4]],
+                                       &t[node->src[5]], biases, &param->saved_mean,
+                                       &param->saved_variance, param->reduce_scratch_gpu,
+                                       net->mode, fused_act);
+        }
     }
     if (act == BCNN_ACT_PRELU) {
         bcnn_tensor *slopes = &t[node->src[3 + 3 * param->batch_norm]];

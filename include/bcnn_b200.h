@@ -227,6 +227,20 @@ BCNN_B200_API int bcnn_b200_conv_forward_sh(const bcnn_b200_conv_desc *d, const 
                                             float *y, void *workspace,
                                             size_t workspace_bytes, int math,
                                             bcnn_b200_conv_shadows *sh, void *stream);
+/* Convolution feeding a TRAIN-mode batch normalisation: y = W (*) x (no bias, no
+ * activation) and the statistics bcnn_b200_bn_stats would compute over y (saved mean /
+ * biased variance, running update), taken from the FP32 accumulators in the convolution
+ * epilogue so that y is not read back: the first of the reference's seven passes over
+ * the tensor (bcnn_forward_batchnorm_cpu, src/layers/bcnn_batchnorm_layer.c:196-242,
+ * called from bcnn_conv_layer.c:470) disappears. Shapes the TMA kernel does not cover
+ * run convolution and bcnn_b200_bn_stats back to back. `scratch` as bcnn_b200_bn_stats. */
+BCNN_B200_API int bcnn_b200_conv_forward_bn_stats(const bcnn_b200_conv_desc *d,
+                                                  const float *x, const float *w, float *y,
+                                                  void *workspace, size_t workspace_bytes,
+                                                  int math, bcnn_b200_conv_shadows *sh,
+                                                  float *saved_mean, float *saved_var,
+                                                  float *run_mean, float *run_var,
+                                                  float *scratch, void *stream);
 BCNN_B200_API int bcnn_b200_conv_backward_data_sh(const bcnn_b200_conv_desc *d,
                                                   const float *w, const float *dy,
                                                   float *dx, int accumulate,

@@ -452,6 +452,51 @@ def test_conv_shadow_storage_matches_plain_entry_points(case):
     assert np.array_equal(gw2.download(np.float32, wt.shape), plain[1])
 
 
+@pytest.mark.parametrize("math", [capi.MATH_TC, capi.MATH_FP32])
+@pytest.mark.parametrize("case", [
+    (8, 64, 14, 14, 256, 1, 1, 0, 1),    # DIRECT 1x1, 196 positions: ragged 128-row tiles
+    (8, 64, 28, 28, 320, 1, 1, 0, 1),    # two channel tiles of 160
+    (16, 32, 7, 7, 48, 3, 1, 1, 1),      # several images per tile, 48 channels (ragged chunk)
+    (6, 32, 30, 30, 64, 3, 2, 1, 1),     # stride 2, tiles past the right / bottom edge
+    (32, 3, 32, 32, 32, 7, 2, 3, 1),     # thin first layer (im2col route)
+    (4, 32, 12, 12, 32, 3, 1, 1, 2),     # groups: not on the TMA kernel -> unfused statistics
+])
+def test_conv_forward_bn_stats_matches_separate_kernels(case, math):
+    """Batch-norm statistics fused into the convolution epilogue == statistics of the stored
+    output (float64 reference over the very tensor the call wrote), output == plain fprop."""
+    lib = capi.b200()
+    batch, cin, h, w, cout, k, s, pad, groups = case
+    d = capi.ConvDesc.make(*case)
+    r = rng(sum(case) + math)
+    x = f32(r.uniform(-1, 1, size=(batch, cin, h, w)) + 0.25)
+    wt = f32(r.uniform(-1, 1, size=(cout, cin // groups, k, k)) / np.sqrt(cin * k * k))
+    ws_bytes = lib.bcnn_b200_conv_workspace_bytes(d, math)
+    ws = capi.DeviceBuffer(nbytes=max(ws_bytes, 4))
+    dxv, dwt = dev(x), dev(wt)
+    ysz = batch * cout * d.ho * d.wo
+    y_plain, y_fused = dev_zeros(ysz), dev_zeros(ysz)
+    check(lib.bcnn_b200_conv_forward(d, dxv.ptr, dwt.ptr, None, 0, y_plain.ptr, ws.ptr, ws_bytes,
+                                     math, None))
+    run0 = f32(r.uniform(-1, 1, size=cout)), f32(r.uniform(0.5, 1.5, size=cout))
+    mean, var, rmean, rvar = dev_zeros(cout), dev_zeros(cout), dev(run0[0]), dev(run0[1])
+    scratch = dev_zeros(lib.bcnn_b200_bn_scratch_floats(cout))
+    for _ in range(2):  # twice: the tickets of the reduction must re-arm
+        rmean, rvar = dev(run0[0]), dev(run0[1])
+        check(lib.bcnn_b200_conv_forward_bn_stats(d, dxv.ptr, dwt.ptr, y_fused.ptr, ws.ptr, ws_bytes,
+                                                  math, None, mean.ptr, var.ptr, rmean.ptr, rvar.ptr,
+                                                  scratch.ptr, None))
+    y = y_fused.download(np.float32, (batch, cout, d.ho, d.wo))
+    assert np.array_equal(y, y_plain.download(np.float32, y.shape))
+    y64 = y.astype(np.float64)
+    m_ref = y64.mean(axis=(0, 2, 3))
+    v_ref = (y64 ** 2).mean(axis=(0, 2, 3)) - m_ref ** 2
+    got_m, got_v = mean.download(np.float32, (cout,)), var.download(np.float32, (cout,))
+    assert_close(got_m, f32(m_ref), 1e-5, "fused mean")
+    assert np.abs(got_v - v_ref).max() <= 2e-5 * np.abs((y64 ** 2).mean(axis=(0, 2, 3))).max()
+    assert_close(rmean.download(np.float32, (cout,)), f32(0.9 * run0[0] + 0.1 * got_m), 1e-6, "run mean")
+    assert_close(rvar.download(np.float32, (cout,)), f32(0.9 * run0[1] + 0.1 * got_v), 1e-6, "run var")
+
+
 # ------------------------------------------------------------------ depthwise
 @pytest.mark.parametrize("n,c,h,w,k,s,pad", [(2, 32, 28, 28, 3, 1, 1), (2, 16, 28, 28, 3, 2, 1),
                                              (1, 7, 9, 11, 3, 1, 0), (2, 4, 12, 12, 5, 1, 2)])
