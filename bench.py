@@ -395,15 +395,17 @@ def run_own_arm(args):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         ms_total, ms_e2e = float(t[0]), float(t[1])
 
+    # per-node breakdown of one step (CUDA events around every node). Every rank runs it: the
+    # step carries the gradient all-reduce, which all ranks must enter.
+    lib.bcnn_b200_profile(net.handle, 1)
+    net.train_step()
+    barrier()
     result = None
     if rank == 0:
         peaks = measured_peaks()
         imgs = args.batch * world * args.steps
         value = imgs / (ms_total * 1e-3)
         e2e = imgs / (ms_e2e * 1e-3)
-        # per-node breakdown of one step (CUDA events around every node)
-        lib.bcnn_b200_profile(net.handle, 1)
-        net.train_step()
         by_type = {}
         names = {0: "conv(+bn+act)", 2: "depthwise", 3: "activation", 4: "fullc", 5: "maxpool",
                  6: "avgpool", 7: "softmax", 9: "batchnorm", 12: "eltwise", 16: "cost"}
@@ -482,6 +484,9 @@ def main():
     ap.add_argument("--no-rooflines", dest="rooflines", action="store_false")
     ap.add_argument("--no-cpu-baseline", dest="cpu_baseline", action="store_false")
     args = ap.parse_args()
+    # a wedged collective must not hold the box: dump every thread's stack and exit
+    import faulthandler
+    faulthandler.dump_traceback_later(int(os.environ.get("BCNN_B200_BENCH_WATCHDOG_S", "1500")), exit=True)
     args.warmup = max(args.warmup, 3) if args.impl == "own" else args.warmup
     if args.impl == "reference":
         return run_reference_arm(args)
