@@ -107,6 +107,7 @@ def bind_b200_ext(lib: C.CDLL) -> None:
         "bcnn_b200_sync": (None, [vp]),
         "bcnn_b200_upload_tensor": (i, [vp, i]),
         "bcnn_b200_upload_inputs": (sz, [vp]),
+        "bcnn_b200_prefetch_inputs": (sz, [vp]),
         "bcnn_b200_get_loss": (f, [vp]),
         "bcnn_b200_train_step": (f, [vp, i, i]),
         "bcnn_b200_profile": (None, [vp, i]),
@@ -329,8 +330,22 @@ class Net:
         return float(self.lib.bcnn_b200_get_loss(self.handle))
 
     def train_step(self, upload_inputs=False, fetch_loss=False) -> float:
+        """upload_inputs: False / True (upload, then step) / 2 (input pipeline, see
+        bcnn_b200_net.h: consumes the staged batch, uploads the mirrors for the next call)."""
         return float(self.lib.bcnn_b200_train_step(self.handle, int(upload_inputs),
                                                    int(fetch_loss)))
+
+    def set_host(self, name, array: np.ndarray) -> None:
+        """Fill a tensor's pinned host mirror only (the input pipeline uploads it)."""
+        idx = name if isinstance(name, int) else self.tensor_index(name)
+        t = self._tensor(idx)
+        arr = np.ascontiguousarray(array, dtype=np.float32).reshape(-1)
+        if arr.size != t.n * t.c * t.h * t.w or not t.data:
+            raise ValueError(f"tensor {name!r}: bad size or no host mirror")
+        C.memmove(t.data, arr.ctypes.data, arr.size * 4)
+
+    def prefetch_inputs(self) -> int:
+        return int(self.lib.bcnn_b200_prefetch_inputs(self.handle))
 
     def num_nodes(self) -> int:
         return self.lib.bcnn_b200_num_nodes(self.handle)

@@ -84,6 +84,13 @@ void bcnn_end_net(bcnn_net **net) {
         free(ctx->consumers);
         bcnn_b200_free(ctx->workspace_gpu);
         bcnn_b200_free(ctx->dy_shadow_gpu);
+        if (ctx->stage_gpu) {
+            for (int i = 0; i <= p->num_inputs; ++i) bcnn_b200_free(ctx->stage_gpu[i]);
+            free(ctx->stage_gpu);
+        }
+        bcnn_b200_event_destroy(ctx->evt_uploaded);
+        bcnn_b200_event_destroy(ctx->evt_consumed);
+        bcnn_b200_stream_destroy(ctx->copy_stream);
         bcnn_b200_stream_destroy(ctx->stream);
         free(ctx);
     }
@@ -350,6 +357,8 @@ void *bcnn_b200_get_stream(bcnn_net *net) { return bcnn_stream(net); }
 
 void bcnn_b200_sync(bcnn_net *net) {
     bcnn_dp_sync(net);
+    if (bcnn_ctx(net)->copy_stream)
+        bcnn_cuda_check(bcnn_b200_stream_sync(bcnn_ctx(net)->copy_stream));
     bcnn_cuda_check(bcnn_b200_stream_sync(bcnn_stream(net)));
 }
 
@@ -394,12 +403,80 @@ float bcnn_b200_get_loss(bcnn_net *net) {
     return count ? loss / count : 0.f;
 }
 
+/* ---- input pipeline: double-buffered uploads on a copy stream ---- */
+static bcnn_tensor *pipeline_tensor(bcnn_net *net, int i) {
+    return &net->tensors[i < net->num_inputs ? net->inputs[i] : 1]; /* inputs[], then the label */
+}
+
+/* Queue the upload of the host mirrors into the staging buffers. The copy waits for the last
+ * step that read those buffers (they were the live inputs of the previous step), nothing else:
+ * it overlaps whatever the compute stream is running. */
+static size_t pipeline_prefetch(bcnn_net *net) {
+    bcnn_cuda_context *ctx = bcnn_ctx(net);
+    size_t queued = 0;
+    if (!ctx->copy_stream) {
+        ctx->copy_stream = bcnn_b200_stream_create();
+        ctx->evt_uploaded = bcnn_b200_event_create();
+        ctx->evt_consumed = bcnn_b200_event_create();
+        ctx->stage_gpu = (float **)calloc((size_t)net->num_inputs + 1, sizeof(float *));
+        if (!ctx->copy_stream || !ctx->evt_uploaded || !ctx->evt_consumed || !ctx->stage_gpu) {
+            fprintf(stderr, "[ERROR] input pipeline: cannot create stream / events\n");
+            exit(BCNN_CUDA_FAILED_ALLOC);
+        }
+        bcnn_cuda_check(bcnn_b200_event_record(ctx->evt_consumed, ctx->stream));
+    }
+    bcnn_cuda_check(bcnn_b200_stream_wait_event(ctx->copy_stream, ctx->evt_consumed));
+    for (int i = 0; i <= net->num_inputs; ++i) {
+        bcnn_tensor *t = pipeline_tensor(net, i);
+        size_t bytes = (size_t)bcnn_tensor_size(t) * sizeof(float);
+        if (!t->data || !t->data_gpu || bytes == 0) continue;
+        if (!ctx->stage_gpu[i]) {
+            ctx->stage_gpu[i] = (float *)bcnn_b200_malloc(bytes);
+            if (!ctx->stage_gpu[i]) exit(BCNN_CUDA_FAILED_ALLOC);
+        }
+        bcnn_cuda_check(bcnn_b200_memcpy_h2d(ctx->stage_gpu[i], t->data, bytes, ctx->copy_stream));
+        queued += bytes;
+    }
+    bcnn_cuda_check(bcnn_b200_event_record(ctx->evt_uploaded, ctx->copy_stream));
+    ctx->stage_valid = 1;
+    return queued;
+}
+
+size_t bcnn_b200_prefetch_inputs(bcnn_net *net) {
+    size_t queued = pipeline_prefetch(net);
+    bcnn_cuda_check(bcnn_b200_stream_sync(bcnn_ctx(net)->copy_stream));
+    return queued;
+}
+
+/* Make the staged batch the live one: swap the device buffers once the copy has landed. */
+static void pipeline_swap_in(bcnn_net *net) {
+    bcnn_cuda_context *ctx = bcnn_ctx(net);
+    if (!ctx->stage_valid) pipeline_prefetch(net); /* first step: nothing was staged yet */
+    bcnn_cuda_check(bcnn_b200_stream_wait_event(ctx->stream, ctx->evt_uploaded));
+    for (int i = 0; i <= net->num_inputs; ++i) {
+        bcnn_tensor *t = pipeline_tensor(net, i);
+        if (!ctx->stage_gpu[i]) continue;
+        float *live = t->data_gpu;
+        t->data_gpu = ctx->stage_gpu[i];
+        ctx->stage_gpu[i] = live;
+    }
+    ctx->stage_valid = 0;
+    /* completes when every earlier step has: from then on the old live buffers are free */
+    bcnn_cuda_check(bcnn_b200_event_record(ctx->evt_consumed, ctx->stream));
+}
+
 float bcnn_b200_train_step(bcnn_net *net, int upload_inputs, int fetch_loss) {
-    if (upload_inputs) bcnn_b200_upload_inputs(net);
+    if (upload_inputs == 2) pipeline_swap_in(net);
+    else if (upload_inputs) bcnn_b200_upload_inputs(net);
     bcnn_forward(net);
     bcnn_backward(net);
     bcnn_update(net);
-    return fetch_loss ? bcnn_b200_get_loss(net) : 0.f;
+    if (upload_inputs == 2) pipeline_prefetch(net);
+    float loss = fetch_loss ? bcnn_b200_get_loss(net) : 0.f;
+    /* the host mirrors may be refilled once the call returns */
+    if (upload_inputs == 2 && fetch_loss)
+        bcnn_cuda_check(bcnn_b200_stream_sync(bcnn_ctx(net)->copy_stream));
+    return loss;
 }
 
 int bcnn_b200_num_nodes(bcnn_net *net) { return net->num_nodes; }

@@ -24,6 +24,13 @@ typedef struct bcnn_cuda_context {
     float *workspace_gpu; /* conv workspace shared by all conv nodes */
     /* --- B200 extensions --- */
     size_t workspace_bytes;   /* max over conv nodes, sized at construction */
+    /* input pipeline (bcnn_b200_train_step, upload_inputs == 2): the next batch travels to a
+     * second set of device buffers on copy_stream while the current step computes */
+    void *copy_stream;
+    void *evt_uploaded;       /* copy -> compute: staged batch is on the device */
+    void *evt_consumed;       /* compute -> copy: last step reading the staging buffers is done */
+    float **stage_gpu;        /* per uploaded tensor (inputs[], then the label) */
+    int stage_valid;
     void *dy_shadow_gpu;      /* NHWC shadow of the output gradient of the conv node running
                                  backward (shared by its wgrad and dgrad), max over nodes */
     size_t dy_shadow_bytes;

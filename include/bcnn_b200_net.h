@@ -44,8 +44,20 @@ BCNN_B200_API size_t bcnn_b200_upload_inputs(bcnn_net *net);
 BCNN_B200_API float bcnn_b200_get_loss(bcnn_net *net);
 /* One training step = optional input upload + bcnn_forward + bcnn_backward +
  * bcnn_update, the body of bcnn_train_on_batch (src/bcnn_net.c:452-463) without the
- * file loader. Returns the loss when fetch_loss != 0 (which synchronises), else 0. */
+ * file loader. Returns the loss when fetch_loss != 0 (which synchronises), else 0.
+ * upload_inputs: 0 = inputs already on the device; 1 = upload the host mirrors on the
+ * compute stream, then step (bcnn_loader_next's synchronous cudaMemcpy, src/bcnn_data.c:
+ * 402-427, made asynchronous); 2 = input pipeline: the step consumes the batch staged by
+ * the previous call (the first call stages its own) and the batch now in the host mirrors
+ * is uploaded to a second set of device buffers on a copy stream while the step computes,
+ * to be consumed by the next call -- fill the mirrors with batch i+1 before step i. With
+ * fetch_loss the mirrors may be refilled when the call returns; without it after
+ * bcnn_b200_sync. */
 BCNN_B200_API float bcnn_b200_train_step(bcnn_net *net, int upload_inputs, int fetch_loss);
+/* Prologue of the input pipeline: stage the batch now in the host mirrors (batch 0) for the
+ * first bcnn_b200_train_step(net, 2, ...). Returns the bytes uploaded; the mirrors may be
+ * refilled on return. */
+BCNN_B200_API size_t bcnn_b200_prefetch_inputs(bcnn_net *net);
 
 /* Per-node CUDA-event timers: when enabled, bcnn_forward / bcnn_backward bracket every
  * node with events on the net's stream; read the last step's durations per node. */

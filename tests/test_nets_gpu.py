@@ -141,6 +141,38 @@ def test_residual_fix_mode_accumulates_branch_gradients():
     assert_close(prev_off, prev_on + out_on * mask, 1e-5, "branch gradients accumulate")
 
 
+def test_input_pipeline_matches_upload_then_step():
+    """bcnn_b200_train_step(upload_inputs=2): batch i+1 travels on the copy stream while step i
+    computes; losses and final parameters are bit-identical to upload-then-step."""
+    batches = [(configs.synth_input((4, 3, 20, 20), seed=40 + i),
+                configs.synth_labels((4, 10, 1, 1), first_sample=3 * i)) for i in range(4)]
+    runs = {}
+    for mode in ("sequential", "pipelined"):
+        net = capi.Net()
+        netcases.chain_convnet(net, batch=4)
+        net.compile()
+        configs.init_params(net, seed=9)
+        losses = []
+        if mode == "pipelined":
+            net.set_host("input", batches[0][0])
+            net.set_host("label", batches[0][1])
+            net.prefetch_inputs()
+        for i in range(len(batches)):
+            nxt = batches[min(i + 1, len(batches) - 1)] if mode == "pipelined" else batches[i]
+            net.set_host("input", nxt[0])
+            net.set_host("label", nxt[1])
+            losses.append(net.train_step(upload_inputs=2 if mode == "pipelined" else True,
+                                         fetch_loss=True))
+        net.sync()
+        params = {name: net.get(idx) for idx, name, _ in configs.param_tensors(net)}
+        net.close()
+        runs[mode] = (losses, params)
+    assert runs["sequential"][0] == runs["pipelined"][0], "per-step losses differ"
+    assert len(set(runs["sequential"][0])) > 1, "batches must differ for the test to bite"
+    for name, w in runs["sequential"][1].items():
+        assert np.array_equal(w, runs["pipelined"][1][name]), name
+
+
 def test_valid_and_predict_modes_follow_reference_semantics():
     """VALID normalises with the running statistics; PREDICT applies y = gamma*x + beta."""
     results = {}

@@ -1,3 +1,3 @@
-mkdir -p gpurun_out/r1h
-BCNN_B200_BENCH_WATCHDOG_S=150 timeout 200 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29511 bench.py --gpus 2 --steps 10 --warmup 3 > gpurun_out/r1h/bench_n2.json 2> gpurun_out/r1h/bench_n2.err
-echo "bench rc=$?"; head -c 900 gpurun_out/r1h/bench_n2.json; tail -5 gpurun_out/r1h/bench_n2.err
+mkdir -p gpurun_out/r1f
+timeout 900 python -m pytest tests -m gpu -x -q > gpurun_out/r1f/gpu_tests.log 2>&1; tail -15 gpurun_out/r1f/gpu_tests.log
+timeout 600 python bench.py > gpurun_out/r1f/bench_n1.json 2> gpurun_out/r1f/bench_n1.err; head -c 400 gpurun_out/r1f/bench_n1.json
