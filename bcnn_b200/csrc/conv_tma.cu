@@ -66,6 +66,22 @@ __device__ __forceinline__ void tma_load_4d(uint32_t dst_smem, const CUtensorMap
         "[%0], [%1, {%2, %3, %4, %5}], [%6];"
         :: "r"(dst_smem), "l"(map), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(bar) : "memory");
 }
+// Shared -> global tensor stores of the bulk async-group kind (3-D map: position, channel, image).
+__device__ __forceinline__ void tma_store_3d(const CUtensorMap *map, uint32_t src_smem, int c0, int c1, int c2) {
+    asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.tile.bulk_group [%0, {%2, %3, %4}], [%1];"
+                 :: "l"(map), "r"(src_smem), "r"(c0), "r"(c1), "r"(c2) : "memory");
+}
+__device__ __forceinline__ void tma_reduce_add_3d(const CUtensorMap *map, uint32_t src_smem, int c0, int c1,
+                                                  int c2) {
+    asm volatile("cp.reduce.async.bulk.tensor.3d.global.shared::cta.add.tile.bulk_group [%0, {%2, %3, %4}], [%1];"
+                 :: "l"(map), "r"(src_smem), "r"(c0), "r"(c1), "r"(c2) : "memory");
+}
+__device__ __forceinline__ void bulk_commit_group() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+// every earlier bulk group of this thread has finished READING its shared-memory source
+__device__ __forceinline__ void bulk_wait_read_all() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+__device__ __forceinline__ void named_bar_sync(int id, int threads) {
+    asm volatile("bar.sync %0, %1;" :: "r"(id), "r"(threads) : "memory");
+}
 __device__ __forceinline__ void prefetch_tensormap(const CUtensorMap *map) {
     asm volatile("prefetch.tensormap [%0];" :: "l"(map) : "memory");
 }
@@ -142,6 +158,22 @@ bool make_map_nchw(CUtensorMap *map, const float *base, int w, int h, int c, int
                     box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
                     mn_major ? CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B : CU_TENSOR_MAP_SWIZZLE_128B,
                     CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    return r == CUDA_SUCCESS;
+}
+
+// Map over an NCHW fp32 result seen as (position, channel, image), the plane as one row (plane % 4
+// == 0): the store box is box_pos consecutive positions x 16 channels x box_n images, no swizzle.
+// Elements of a box that fall outside the tensor are not written.
+bool make_map_out(CUtensorMap *map, float *base, int plane, int c, int n, int box_pos, int box_n) {
+    EncodeTiledFn fn = encode_fn();
+    if (!fn) return false;
+    cuuint64_t dims[3] = {(cuuint64_t)plane, (cuuint64_t)c, (cuuint64_t)n};
+    cuuint64_t strides[2] = {(cuuint64_t)plane * 4, (cuuint64_t)plane * c * 4};
+    cuuint32_t box[3] = {(cuuint32_t)box_pos, 16, (cuuint32_t)box_n};
+    cuuint32_t estr[3] = {1, 1, 1};
+    CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, base, dims, strides, box, estr,
+                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
+                    CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     return r == CUDA_SUCCESS;
 }
 
@@ -303,6 +335,11 @@ struct FwdParams {
     const float *bias;
     const uint8_t *wpack;
     int act, accumulate;
+    // tstore: the epilogue stages each 32-channel chunk in shared memory and a bulk tensor store
+    // (reduce-add when accumulating) writes it through tm_dst; the tile is tile_pos consecutive
+    // positions of the plane (x tn images). 0: per-thread stores (scattered dgrad classes, planes
+    // whose size is not a multiple of 4 elements).
+    int tstore, tile_pos;
     int src_c, dst_c, batch;
     int out_w, out_h;     // output plane as the kernel sees it (DIRECT: (H*W, 1))
     int ksh, ksw, pad_h, pad_w, stride;   // tap window (rows x columns) and its leading pads
@@ -322,9 +359,10 @@ struct FwdParams {
 
 constexpr int FWD_EPI_WARPS = 8;
 constexpr int FWD_THREADS = 64 + 32 * FWD_EPI_WARPS;
-// fused batch-norm statistics: per epilogue warp the running sums of its <= 4 column chunks
-constexpr int STAT_ACC_FLOATS = 4 * 2 * 32;
-constexpr int STAT_PAD_BYTES = FWD_EPI_WARPS * STAT_ACC_FLOATS * 4;
+// output staging of the bulk-store epilogue: per half of the epilogue warps one chunk of 128
+// positions x 32 channels, laid out [16-channel sub-box][image][channel][position]
+constexpr int OUT_STAGE_BYTES = TILE_M * 32 * 4;
+constexpr int FWD_EXTRA_SMEM = 1024 + 256 + 2 * OUT_STAGE_BYTES;   // alignment slack, barriers, staging
 
 struct TileCoord { int tile_n, m_tile, img, w0, h0; };
 
@@ -381,7 +419,8 @@ __device__ __forceinline__ void store_chunk_any(const uint32_t (&v)[32], float *
 // MMAs of tile i+1.
 template <bool NHWC, bool BF16>
 __global__ void __launch_bounds__(FWD_THREADS, 1)
-conv_tma_fwd_kernel(const __grid_constant__ CUtensorMap tm_src, const FwdParams p) {
+conv_tma_fwd_kernel(const __grid_constant__ CUtensorMap tm_src, const __grid_constant__ CUtensorMap tm_dst,
+                    const FwdParams p) {
     constexpr int KC = BF16 ? 64 : 32;   // channels per 128-byte k-block row
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     uint8_t *smem = reinterpret_cast<uint8_t *>(
@@ -406,6 +445,7 @@ conv_tma_fwd_kernel(const __grid_constant__ CUtensorMap tm_src, const FwdParams 
         mbar_init(smem_u32(acc_empty + 1), FWD_EPI_WARPS);
         fence_barrier_init();
         prefetch_tensormap(&tm_src);
+        if (p.tstore) prefetch_tensormap(&tm_dst);
     }
     if (warp == 1) tmem_alloc(smem_u32(tmem_slot), tmem_cols);
     tc_fence_before();
@@ -487,12 +527,12 @@ conv_tma_fwd_kernel(const __grid_constant__ CUtensorMap tm_src, const FwdParams 
         const int ew = warp - 2;
         const int q = warp & 3;
         const int half = ew >> 2;
-        // fused statistics: running sums of this warp, [chunk of the warp][sum | sum of squares][lane]
-        float *stat_acc = reinterpret_cast<float *>(smem + (size_t)S * stage_bytes + 256) + ew * STAT_ACC_FLOATS;
-        if (p.stat_partial != nullptr) {
-#pragma unroll
-            for (int i = 0; i < STAT_ACC_FLOATS / 32; ++i) stat_acc[i * 32 + lane] = 0.f;
-        }
+        // fused statistics: running sums of this warp's <= 4 column chunks (lane = channel)
+        float acc1[4] = {0.f, 0.f, 0.f, 0.f}, acc2[4] = {0.f, 0.f, 0.f, 0.f};
+        // bulk-store epilogue: staging buffer of this half, position of this thread's row in it
+        const int hw = ew & 3;   // warp within the half
+        float *stage = reinterpret_cast<float *>(smem + (size_t)S * stage_bytes + 256 + (size_t)half * OUT_STAGE_BYTES);
+        const int sub_stride = p.tn * 16 * p.tile_pos;   // floats between the two 16-channel sub-boxes
         const uint32_t plane = (uint32_t)p.dst_plane;
         const int chunks32 = (n_tile + 31) / 32;
         // position of this thread's tile row relative to the tile origin
@@ -506,6 +546,8 @@ conv_tma_fwd_kernel(const __grid_constant__ CUtensorMap tm_src, const FwdParams 
             const int wci = q / p.rows;
             rw = wci * 32 + lane; rh = q - wci * p.rows; rn = 0;
         }
+        const bool in_box = NHWC ? (rn < p.tn) : (rh == 0);
+        const int row_off = NHWC ? rn * 16 * p.tile_pos + rh * p.tw + rw : rw;
         uint32_t local = 0;
         for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++local) {
             const TileCoord c = decode_tile<NHWC>(p, tile);
@@ -519,6 +561,77 @@ conv_tma_fwd_kernel(const __grid_constant__ CUtensorMap tm_src, const FwdParams 
             __syncwarp();
             tc_fence_after();
             const uint32_t d_tmem = tmem_base + buf * acc_cols + ((uint32_t)(q * 32) << 16);
+            if (p.tstore) {
+                const int pos0 = NHWC ? c.h0 * p.dst_w + c.w0 : c.w0;
+#pragma unroll
+                for (int ci = 0; ci < 4; ++ci) {
+                    const int ck = half + 2 * ci;
+                    if (ck < chunks32) {
+                        uint32_t v[32];
+                        tmem_ld32(d_tmem + (uint32_t)(ck * 32), v);
+                        const int ch0 = c.tile_n * n_tile + ck * 32;
+                        if (p.bias != nullptr || p.act != ACT_NONE) {
+#pragma unroll
+                            for (int j = 0; j < 32; ++j) {
+                                float val = __uint_as_float(v[j]);
+                                if (p.bias != nullptr && ch0 + j < p.dst_c) val += __ldg(p.bias + ch0 + j);
+                                if (p.act == ACT_RELU) val = fmaxf(val, 0.f);
+                                else if (p.act == ACT_LRELU) val = val > 0 ? val : 0.1f * val;
+                                else val = act_fwd(val, p.act, 0.f);
+                                v[j] = __float_as_uint(val);
+                            }
+                        }
+                        // the previous bulk store of this half has finished reading the staging buffer
+                        if (hw == 0 && lane == 0) bulk_wait_read_all();
+                        named_bar_sync(1 + half, 128);
+                        if (in_box) {
+                            float *sp = stage + row_off;
+#pragma unroll
+                            for (int j = 0; j < 32; ++j)
+                                sp[(j >> 4) * sub_stride + (j & 15) * p.tile_pos] = __uint_as_float(v[j]);
+                        }
+                        fence_proxy_async();
+                        named_bar_sync(1 + half, 128);
+                        if (hw == 0 && lane == 0) {
+                            const int nch = n_tile - ck * 32;   // channels of this chunk inside the tile
+                            const uint32_t s0 = smem_u32(stage);
+                            if (p.accumulate) {
+                                tma_reduce_add_3d(&tm_dst, s0, pos0, ch0, c.img);
+                                if (nch > 16) tma_reduce_add_3d(&tm_dst, s0 + sub_stride * 4, pos0, ch0 + 16, c.img);
+                            } else {
+                                tma_store_3d(&tm_dst, s0, pos0, ch0, c.img);
+                                if (nch > 16) tma_store_3d(&tm_dst, s0 + sub_stride * 4, pos0, ch0 + 16, c.img);
+                            }
+                            bulk_commit_group();
+                        }
+                        if (p.stat_partial != nullptr) {
+                            // Per-channel sum / sum of squares over this warp's 32 positions: a
+                            // transposing butterfly (31 shuffles per quantity) leaves channel
+                            // ch0 + lane in lane `lane`; it runs while the bulk store drains.
+                            float s1[32], s2[32];
+#pragma unroll
+                            for (int j = 0; j < 32; ++j) {
+                                const float x = valid ? __uint_as_float(v[j]) : 0.f;
+                                s1[j] = x;
+                                s2[j] = x * x;
+                            }
+#pragma unroll
+                            for (int off = 16; off >= 1; off >>= 1) {
+                                const bool hi = (lane & off) != 0;
+#pragma unroll
+                                for (int i = 0; i < off; ++i) {
+                                    const float k1 = hi ? s1[i + off] : s1[i], g1 = hi ? s1[i] : s1[i + off];
+                                    const float k2 = hi ? s2[i + off] : s2[i], g2 = hi ? s2[i] : s2[i + off];
+                                    s1[i] = k1 + __shfl_xor_sync(0xffffffffu, g1, off);
+                                    s2[i] = k2 + __shfl_xor_sync(0xffffffffu, g2, off);
+                                }
+                            }
+                            acc1[ci] += s1[0];
+                            acc2[ci] += s2[0];
+                        }
+                    }
+                }
+            } else
             for (int ck = half; ck < chunks32; ck += 2) {
                 uint32_t v[32];
                 tmem_ld32(d_tmem + (uint32_t)(ck * 32), v);
@@ -547,33 +660,6 @@ conv_tma_fwd_kernel(const __grid_constant__ CUtensorMap tm_src, const FwdParams 
                         }
                     }
                 }
-                if (p.stat_partial != nullptr) {
-                    // Per-channel sum / sum of squares over this warp's 32 positions: a transposing
-                    // butterfly (31 shuffles per quantity) leaves channel ch0 + lane in lane `lane`;
-                    // the warp keeps running sums over all its tiles (a CTA sees one channel tile:
-                    // the grid is a multiple of n_tiles) in a private shared-memory row.
-                    float s1[32], s2[32];
-#pragma unroll
-                    for (int j = 0; j < 32; ++j) {
-                        const float x = valid ? __uint_as_float(v[j]) : 0.f;
-                        s1[j] = x;
-                        s2[j] = x * x;
-                    }
-#pragma unroll
-                    for (int off = 16; off >= 1; off >>= 1) {
-                        const bool hi = (lane & off) != 0;
-#pragma unroll
-                        for (int i = 0; i < off; ++i) {
-                            const float k1 = hi ? s1[i + off] : s1[i], g1 = hi ? s1[i] : s1[i + off];
-                            const float k2 = hi ? s2[i + off] : s2[i], g2 = hi ? s2[i] : s2[i + off];
-                            s1[i] = k1 + __shfl_xor_sync(0xffffffffu, g1, off);
-                            s2[i] = k2 + __shfl_xor_sync(0xffffffffu, g2, off);
-                        }
-                    }
-                    float *acc = stat_acc + (ck >> 1) * 64 + lane;
-                    acc[0] += s1[0];
-                    acc[32] += s2[0];
-                }
             }
             // all of this warp's tcgen05.ld have completed (wait::ld inside tmem_ld32)
             tc_fence_before();
@@ -584,14 +670,18 @@ conv_tma_fwd_kernel(const __grid_constant__ CUtensorMap tm_src, const FwdParams 
             // row = (CTA index among those of this channel tile) * 4 + lane quarter
             const uint32_t tile_n = blockIdx.x % (uint32_t)p.n_tiles;
             const size_t row = (size_t)(blockIdx.x / (uint32_t)p.n_tiles) * 4 + (size_t)q;
-            for (int ck = half; ck < chunks32; ck += 2) {
+#pragma unroll
+            for (int ci = 0; ci < 4; ++ci) {
+                const int ck = half + 2 * ci;
                 const int ch = (int)tile_n * n_tile + ck * 32 + lane;
-                if (lane < n_tile - ck * 32 && ch < p.dst_c) {
-                    p.stat_partial[(row * 2 + 0) * p.dst_c + ch] = stat_acc[(ck >> 1) * 64 + lane];
-                    p.stat_partial[(row * 2 + 1) * p.dst_c + ch] = stat_acc[(ck >> 1) * 64 + 32 + lane];
+                if (ck < chunks32 && lane < n_tile - ck * 32 && ch < p.dst_c) {
+                    p.stat_partial[(row * 2 + 0) * p.dst_c + ch] = acc1[ci];
+                    p.stat_partial[(row * 2 + 1) * p.dst_c + ch] = acc2[ci];
                 }
             }
         }
+        // shared memory must outlive the bulk stores that read it
+        if (p.tstore && hw == 0 && lane == 0) bulk_wait_read_all();
     }
     tc_fence_before();
     __syncthreads();
@@ -618,6 +708,8 @@ struct FwdPlan {
     int tiles_w, tiles_h, tiles_b;
     uint32_t a_bytes;
     size_t shadow_bytes, wpack_bytes, smem_bytes;
+    bool tstore;             // bulk tensor-store epilogue (tile = tile_pos consecutive positions)
+    int tile_pos;
     int stat_rows;           // rows of the fused batch-norm partials: 4 per position tile
     size_t stat_bytes;
 };
@@ -683,6 +775,8 @@ bool plan_fwd(const FwdGeom &g, FwdPlan *pl) {
         pl->tiles_b = g.batch;
         pl->a_bytes = A_STAGE_BYTES;
         pl->shadow_bytes = 0;
+        pl->tile_pos = pl->wc * 32;
+        pl->tstore = g.o_s == 1 && g.dst_plane % 4 == 0;
     } else {
         pl->view_w = g.sw; pl->view_h = g.sh;
         pl->out_w = g.dw; pl->out_h = g.dh;
@@ -695,8 +789,19 @@ bool plan_fwd(const FwdGeom &g, FwdPlan *pl) {
         if (th_max < 1) th_max = 1;
         while (th_max * g.stride > 256) --th_max;
         int th = g.dh < th_max ? g.dh : th_max;
-        const int tiles_h = ceil_div(g.dh, th);
+        int tiles_h = ceil_div(g.dh, th);
         th = ceil_div(g.dh, tiles_h);
+        // bulk-store epilogue: a tile must be a run of consecutive plane positions whose length is a
+        // multiple of 4 elements (16 bytes): full-width rows, th a multiple of 4 / gcd(tw, 4)
+        if (tiles_w == 1 && tiles_h > 1 && (tw * th) % 4 != 0) {
+            const int m = (tw % 2 == 0) ? 2 : 4;
+            int up = ceil_div(th, m) * m;
+            if (up > th_max) up = (th / m) * m;
+            if (up >= m) {
+                th = up;
+                tiles_h = ceil_div(g.dh, th);
+            }
+        }
         int tn = 1;
         if (tiles_w == 1 && tiles_h == 1) {
             tn = 128 / (tw * th);
@@ -707,20 +812,25 @@ bool plan_fwd(const FwdGeom &g, FwdPlan *pl) {
         pl->tiles_w = tiles_w; pl->tiles_h = tiles_h; pl->tiles_b = ceil_div(g.batch, tn);
         pl->a_bytes = (uint32_t)(tw * th * tn * 128);
         pl->shadow_bytes = align256((size_t)g.batch * g.src_c * g.sh * g.sw * (pl->bf16 ? 2 : 4));
+        pl->tile_pos = tw * th;
+        const bool contiguous = tiles_w == 1 || (th == 1 && g.dw % tw == 0);
+        pl->tstore = g.o_s == 1 && g.dst_plane % 4 == 0 && g.dst_w == g.dw && contiguous &&
+                     pl->tile_pos % 4 == 0 && !env_off("BCNN_B200_NO_TSTORE");
     }
+    if (env_off("BCNN_B200_NO_TSTORE")) pl->tstore = false;
     const int stage = A_STAGE_BYTES + n * BLOCK_K * 4;
-    int stages = (200 * 1024) / stage;  // persistent: one CTA per SM owns the shared memory
+    int stages = (227 * 1024 - FWD_EXTRA_SMEM) / stage;  // persistent: one CTA per SM owns the shared memory
     if (stages > 8) stages = 8;
     if (stages < 2) stages = 2;
     pl->stages = stages;
     pl->wpack_bytes = align256((size_t)pl->n_tiles * pl->k_blocks * n * BLOCK_K * sizeof(float));
-    pl->smem_bytes = (size_t)stages * stage + 1024 + 256;
+    pl->smem_bytes = (size_t)stages * stage + FWD_EXTRA_SMEM;
     const long long total = (long long)pl->n_tiles * pl->tiles_w * pl->tiles_h * pl->tiles_b;
     if (total >= (1LL << 31)) return false;
     // fused statistics: grid = a multiple of n_tiles (0 rows: more channel tiles than SMs, no fusion)
     const long long per_tile = sm_count() / pl->n_tiles;
     const long long m_tiles = total / pl->n_tiles;
-    pl->stat_rows = (int)(4 * (per_tile < m_tiles ? per_tile : m_tiles));
+    pl->stat_rows = pl->tstore ? (int)(4 * (per_tile < m_tiles ? per_tile : m_tiles)) : 0;
     pl->stat_bytes = align256((size_t)pl->stat_rows * 2 * g.dst_c * sizeof(float));
     return true;
 }
@@ -836,7 +946,8 @@ FwdRoute route_fwd(const bcnn_b200_conv_desc *d, bool dgrad, FwdPlan *pl) {
 }
 
 template <bool NHWC, bool BF16>
-int launch_fwd_kernel(const CUtensorMap &tm, const FwdParams &p, size_t smem, cudaStream_t st, int grid_override) {
+int launch_fwd_kernel(const CUtensorMap &tm, const CUtensorMap &tm_dst, const FwdParams &p, size_t smem,
+                      cudaStream_t st, int grid_override) {
     static bool attr_set = false;
     if (!attr_set) {
         cudaError_t e = cudaFuncSetAttribute(conv_tma_fwd_kernel<NHWC, BF16>,
@@ -846,7 +957,7 @@ int launch_fwd_kernel(const CUtensorMap &tm, const FwdParams &p, size_t smem, cu
     }
     int grid = p.total_tiles < sm_count() ? p.total_tiles : sm_count();
     if (grid_override > 0) grid = grid_override;
-    conv_tma_fwd_kernel<NHWC, BF16><<<grid, FWD_THREADS, smem, st>>>(tm, p);
+    conv_tma_fwd_kernel<NHWC, BF16><<<grid, FWD_THREADS, smem, st>>>(tm, tm_dst, p);
     return launched();
 }
 
@@ -881,11 +992,17 @@ int run_fwd(const FwdGeom &g, const FwdPlan &pl, const void *src, const uint8_t 
     p.d_tiles_h = FastDiv((uint32_t)pl.tiles_h);
     p.d_tw = FastDiv((uint32_t)pl.tw);
     p.d_th = FastDiv((uint32_t)pl.th);
-    const size_t smem = pl.smem_bytes + (stat_partial ? STAT_PAD_BYTES : 0);
+    p.tstore = pl.tstore ? 1 : 0;
+    p.tile_pos = pl.tile_pos;
+    CUtensorMap tm_dst = tm;   // placeholder when the epilogue stores from registers
+    if (pl.tstore &&
+        !make_map_out(&tm_dst, dst, g.dst_plane, g.dst_c, g.batch, pl.tile_pos, pl.nhwc ? pl.tn : 1))
+        return (int)cudaErrorInvalidValue;
+    const size_t smem = pl.smem_bytes;
     const int grid = stat_partial ? stat_grid(pl) : 0;
-    if (!pl.nhwc) return launch_fwd_kernel<false, false>(tm, p, smem, st, grid);
-    return pl.bf16 ? launch_fwd_kernel<true, true>(tm, p, smem, st, grid)
-                   : launch_fwd_kernel<true, false>(tm, p, smem, st, grid);
+    if (!pl.nhwc) return launch_fwd_kernel<false, false>(tm, tm_dst, p, smem, st, grid);
+    return pl.bf16 ? launch_fwd_kernel<true, true>(tm, tm_dst, p, smem, st, grid)
+                   : launch_fwd_kernel<true, false>(tm, tm_dst, p, smem, st, grid);
 }
 
 int launch_pack(const float *w, uint8_t *wpack, bool dgrad, int cout, int cin, int kk, const FwdPlan &pl,
