@@ -79,6 +79,8 @@ __device__ __forceinline__ void tma_reduce_add_3d(const CUtensorMap *map, uint32
 __device__ __forceinline__ void bulk_commit_group() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
 // every earlier bulk group of this thread has finished READING its shared-memory source
 __device__ __forceinline__ void bulk_wait_read_all() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+// at most one bulk group (the most recent) of this thread may still be reading shared memory
+__device__ __forceinline__ void bulk_wait_read_le1() { asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory"); }
 __device__ __forceinline__ void named_bar_sync(int id, int threads) {
     asm volatile("bar.sync %0, %1;" :: "r"(id), "r"(threads) : "memory");
 }
@@ -532,7 +534,8 @@ conv_tma_fwd_kernel(const __grid_constant__ CUtensorMap tm_src, const __grid_con
         // bulk-store epilogue: staging buffer of this half, position of this thread's row in it
         const int hw = ew & 3;   // warp within the half
         float *stage = reinterpret_cast<float *>(smem + (size_t)S * stage_bytes + 256 + (size_t)half * OUT_STAGE_BYTES);
-        const int sub_stride = p.tn * 16 * p.tile_pos;   // floats between the two 16-channel sub-boxes
+        const int sub_stride = p.tn * 16 * p.tile_pos;   // floats of one 16-channel sub-box
+        uint32_t stores = 0;                              // bulk stores issued by this half so far
         const uint32_t plane = (uint32_t)p.dst_plane;
         const int chunks32 = (n_tile + 31) / 32;
         // position of this thread's tile row relative to the tile origin
@@ -581,28 +584,32 @@ conv_tma_fwd_kernel(const __grid_constant__ CUtensorMap tm_src, const __grid_con
                                 v[j] = __float_as_uint(val);
                             }
                         }
-                        // the previous bulk store of this half has finished reading the staging buffer
-                        if (hw == 0 && lane == 0) bulk_wait_read_all();
-                        named_bar_sync(1 + half, 128);
-                        if (in_box) {
-                            float *sp = stage + row_off;
+                        // two 16-channel sub-boxes per chunk, ping-ponging between the two halves of
+                        // the staging buffer: a sub-box is rewritten once the bulk store issued two
+                        // stores ago has finished reading it, so the store of one sub-box drains
+                        // while the warps fill the other
+                        const int nsub = (n_tile - ck * 32) > 16 ? 2 : 1;
 #pragma unroll
-                            for (int j = 0; j < 32; ++j)
-                                sp[(j >> 4) * sub_stride + (j & 15) * p.tile_pos] = __uint_as_float(v[j]);
-                        }
-                        fence_proxy_async();
-                        named_bar_sync(1 + half, 128);
-                        if (hw == 0 && lane == 0) {
-                            const int nch = n_tile - ck * 32;   // channels of this chunk inside the tile
-                            const uint32_t s0 = smem_u32(stage);
-                            if (p.accumulate) {
-                                tma_reduce_add_3d(&tm_dst, s0, pos0, ch0, c.img);
-                                if (nch > 16) tma_reduce_add_3d(&tm_dst, s0 + sub_stride * 4, pos0, ch0 + 16, c.img);
-                            } else {
-                                tma_store_3d(&tm_dst, s0, pos0, ch0, c.img);
-                                if (nch > 16) tma_store_3d(&tm_dst, s0 + sub_stride * 4, pos0, ch0 + 16, c.img);
+                        for (int sub = 0; sub < 2; ++sub) {
+                            if (sub < nsub) {
+                                float *sb = stage + (stores & 1) * sub_stride;
+                                if (hw == 0 && lane == 0) bulk_wait_read_le1();
+                                named_bar_sync(1 + half, 128);
+                                if (in_box) {
+                                    float *sp = sb + row_off;
+#pragma unroll
+                                    for (int j = 0; j < 16; ++j)
+                                        sp[j * p.tile_pos] = __uint_as_float(v[sub * 16 + j]);
+                                }
+                                fence_proxy_async();
+                                named_bar_sync(1 + half, 128);
+                                if (hw == 0 && lane == 0) {
+                                    if (p.accumulate) tma_reduce_add_3d(&tm_dst, smem_u32(sb), pos0, ch0 + sub * 16, c.img);
+                                    else tma_store_3d(&tm_dst, smem_u32(sb), pos0, ch0 + sub * 16, c.img);
+                                    bulk_commit_group();
+                                }
+                                ++stores;
                             }
-                            bulk_commit_group();
                         }
                         if (p.stat_partial != nullptr) {
                             // Per-channel sum / sum of squares over this warp's 32 positions: a
