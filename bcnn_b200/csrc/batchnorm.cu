@@ -12,6 +12,8 @@
 //             E[x^2] - mean^2, running = 0.9 running + 0.1 batch)
 //   backward: src/layers/bcnn_batchnorm_layer.c:263-332 + src/kernels/bcnn_mat.c:692-727
 //             (eps 1e-5, var*sqrt(var) + 1e-5 in the variance term)
+#include <cstdlib>
+
 #include "common.cuh"
 #include "conv_impl.cuh"
 
@@ -428,6 +430,110 @@ bn_bwd_apply_kernel(const float *__restrict__ x, const float *__restrict__ y,
     }
 }
 
+
+// ---- lean float4 streams with per-channel constants tabulated in shared memory ------------
+// The generic kernels above rebuild 1/sqrt(var + eps) and friends for every float4 (~140
+// instructions per warp-level float4: issue-bound at 60 % of HBM); here each CTA tabulates them
+// once per channel, the stream costs one 16-byte shared-memory read per float4 and the activation
+// is a template parameter. Same arithmetic, same rounding order as the generic kernels.
+template <int ACT>   // ACT_NONE, ACT_RELU or ACT_LRELU
+__global__ void __launch_bounds__(256)
+bn_apply_fast_kernel(const float *__restrict__ x, float *__restrict__ y, const float *__restrict__ mean,
+                     const float *__restrict__ var, const float *__restrict__ gamma,
+                     const float *__restrict__ beta, uint32_t n4, int c, FastDiv div_hw4, FastDiv div_c) {
+    extern __shared__ float4 bn_tab[];   // {mean, 1/sqrt(var + 1e-6), gamma, beta}
+    for (int i = threadIdx.x; i < c; i += 256)
+        bn_tab[i] = make_float4(__ldg(mean + i), 1.0f / sqrtf(__ldg(var + i) + 0.000001f), __ldg(gamma + i),
+                                __ldg(beta + i));
+    __syncthreads();
+    const uint32_t gstride = gridDim.x * 256u;
+    constexpr int UNROLL = 4;   // independent 16-byte loads in flight per thread
+    for (uint32_t j0 = blockIdx.x * 256u + threadIdx.x; j0 < n4; j0 += gstride * UNROLL) {
+        float4 v[UNROLL];
+#pragma unroll
+        for (int u = 0; u < UNROLL; ++u) {
+            const uint32_t j = j0 + u * gstride;
+            if (j < n4) v[u] = ld_stream4(x + ((size_t)j << 2));
+        }
+#pragma unroll
+        for (int u = 0; u < UNROLL; ++u) {
+            const uint32_t j = j0 + u * gstride;
+            if (j < n4) {
+                uint32_t q, ch;
+                div_c.divmod(div_hw4.div(j), q, ch);
+                const float4 t = bn_tab[ch];
+                float4 r;
+                r.x = bn_affine(v[u].x, t.x, t.y, t.z, t.w);
+                r.y = bn_affine(v[u].y, t.x, t.y, t.z, t.w);
+                r.z = bn_affine(v[u].z, t.x, t.y, t.z, t.w);
+                r.w = bn_affine(v[u].w, t.x, t.y, t.z, t.w);
+                if (ACT == ACT_RELU) {
+                    r.x *= (float)(r.x > 0); r.y *= (float)(r.y > 0); r.z *= (float)(r.z > 0); r.w *= (float)(r.w > 0);
+                } else if (ACT == ACT_LRELU) {
+                    r.x = r.x > 0 ? r.x : 0.1f * r.x; r.y = r.y > 0 ? r.y : 0.1f * r.y;
+                    r.z = r.z > 0 ? r.z : 0.1f * r.z; r.w = r.w > 0 ? r.w : 0.1f * r.w;
+                }
+                st_stream4(y + ((size_t)j << 2), r);
+            }
+        }
+    }
+}
+
+// REMASK: ReLU / leaky-ReLU mask rebuilt from x (beta known); otherwise no activation.
+template <bool REMASK>
+__global__ void __launch_bounds__(256)
+bn_bwd_apply_fast_kernel(const float *__restrict__ x, const float *dy, float *dx,
+                         const float *__restrict__ mean, const float *__restrict__ var,
+                         const float *__restrict__ gamma, const float *__restrict__ beta,
+                         const float *__restrict__ d_mean, const float *__restrict__ d_var, uint32_t n4,
+                         int c, int count, float neg, FastDiv div_hw4, FastDiv div_c) {
+    extern __shared__ float4 bn_tab[];   // [c] {mean, k1, k2, k3}, then [c] {1/sqrt(var + 1e-6), gamma, beta, -}
+    const float inv_count = 1.0f / (float)count;
+    for (int i = threadIdx.x; i < c; i += 256) {
+        const float v = __ldg(var + i), g = __ldg(gamma + i);
+        bn_tab[i] = make_float4(__ldg(mean + i), g / sqrtf(v + 0.00001f), __ldg(d_var + i) * 2.0f * inv_count,
+                                __ldg(d_mean + i) * inv_count);
+        if (REMASK) bn_tab[c + i] = make_float4(1.0f / sqrtf(v + 0.000001f), g, __ldg(beta + i), 0.f);
+    }
+    __syncthreads();
+    const uint32_t gstride = gridDim.x * 256u;
+    constexpr int UNROLL = 2;
+    for (uint32_t j0 = blockIdx.x * 256u + threadIdx.x; j0 < n4; j0 += gstride * UNROLL) {
+        float4 xv[UNROLL], gv[UNROLL];
+#pragma unroll
+        for (int u = 0; u < UNROLL; ++u) {
+            const uint32_t j = j0 + u * gstride;
+            if (j < n4) {
+                xv[u] = ld_stream4(x + ((size_t)j << 2));
+                gv[u] = reinterpret_cast<const float4 *>(dy)[j];   // dx may alias dy: coherent load
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < UNROLL; ++u) {
+            const uint32_t j = j0 + u * gstride;
+            if (j < n4) {
+                uint32_t q, ch;
+                div_c.divmod(div_hw4.div(j), q, ch);
+                const float4 t = bn_tab[ch];
+                float4 g = gv[u];
+                if (REMASK) {
+                    const float4 r = bn_tab[c + ch];
+                    g.x *= relu_factor(bn_affine(xv[u].x, t.x, r.x, r.y, r.z), neg);
+                    g.y *= relu_factor(bn_affine(xv[u].y, t.x, r.x, r.y, r.z), neg);
+                    g.z *= relu_factor(bn_affine(xv[u].z, t.x, r.x, r.y, r.z), neg);
+                    g.w *= relu_factor(bn_affine(xv[u].w, t.x, r.x, r.y, r.z), neg);
+                }
+                float4 o;
+                o.x = g.x * t.y + t.z * (xv[u].x - t.x) + t.w;
+                o.y = g.y * t.y + t.z * (xv[u].y - t.x) + t.w;
+                o.z = g.z * t.y + t.z * (xv[u].z - t.x) + t.w;
+                o.w = g.w * t.y + t.z * (xv[u].w - t.x) + t.w;
+                reinterpret_cast<float4 *>(dx)[j] = o;
+            }
+        }
+    }
+}
+
 }  // namespace
 
 extern "C" int bcnn_b200_bn_stats(const float *x, int n, int c, int hw, float *saved_mean,
@@ -466,6 +572,22 @@ extern "C" int bcnn_b200_bn_apply(const float *x, float *y, const float *mean, c
     size_t total = (size_t)n * c * hw;
     if (total == 0) return 0;
     bool vec = (hw % 4) == 0 && aligned16(x) && aligned16(y);
+    static const bool lean = !getenv("BCNN_B200_NO_LEAN_BN");
+    if (lean && vec && x != y && c <= 3072 && total / 4 < (1ull << 31) &&
+        (act == ACT_NONE || act == ACT_RELU || act == ACT_LRELU)) {
+        const uint32_t n4 = (uint32_t)(total / 4);
+        const int grid = stream_grid(ceil_div_sz(n4, 4), 256);
+        const size_t smem = (size_t)c * sizeof(float4);
+        const FastDiv dhw4(hw / 4), dc(c);
+        cudaStream_t st = as_stream(stream);
+        if (act == ACT_RELU)
+            bn_apply_fast_kernel<ACT_RELU><<<grid, 256, smem, st>>>(x, y, mean, var, gamma, beta, n4, c, dhw4, dc);
+        else if (act == ACT_LRELU)
+            bn_apply_fast_kernel<ACT_LRELU><<<grid, 256, smem, st>>>(x, y, mean, var, gamma, beta, n4, c, dhw4, dc);
+        else
+            bn_apply_fast_kernel<ACT_NONE><<<grid, 256, smem, st>>>(x, y, mean, var, gamma, beta, n4, c, dhw4, dc);
+        return launched();
+    }
     bn_apply_kernel<true><<<stream_grid(vec ? total / 4 : total, 256), 256, 0, as_stream(stream)>>>(
         x, y, mean, var, gamma, beta, total, act, FastDiv(hw), FastDiv(c), vec);
     return launched();
@@ -503,6 +625,21 @@ extern "C" int bcnn_b200_bn_backward(const float *x, const float *y, float *dy, 
     if (err) return err;
     bool vec = (hw % 4) == 0 && aligned16(x) && aligned16(dy) && aligned16(dx_out) &&
                (y == nullptr || aligned16(y));
+    const bool remask = beta != nullptr && (act == ACT_RELU || act == ACT_LRELU);
+    static const bool lean = !getenv("BCNN_B200_NO_LEAN_BN");
+    if (lean && vec && c <= 1536 && total / 4 < (1ull << 31) && (remask || act == ACT_NONE)) {
+        const uint32_t n4 = (uint32_t)(total / 4);
+        const int grid = stream_grid(ceil_div_sz(n4, 2), 256);
+        const FastDiv dhw4(hw / 4), dc(c);
+        const float neg = act == ACT_LRELU ? 0.1f : 0.f;
+        if (remask)
+            bn_bwd_apply_fast_kernel<true><<<grid, 256, (size_t)2 * c * sizeof(float4), st>>>(
+                x, dy, dx_out, mean, var, gamma, beta, d_mean, d_var, n4, c, n * hw, neg, dhw4, dc);
+        else
+            bn_bwd_apply_fast_kernel<false><<<grid, 256, (size_t)c * sizeof(float4), st>>>(
+                x, dy, dx_out, mean, var, gamma, beta, d_mean, d_var, n4, c, n * hw, neg, dhw4, dc);
+        return launched();
+    }
     bn_bwd_apply_kernel<<<stream_grid(vec ? total / 4 : total, 256), 256, 0, st>>>(
         x, y, dy, dx_out, mean, var, gamma, beta, d_mean, d_var, total, n * hw, act, FastDiv(hw),
         FastDiv(c), vec);
