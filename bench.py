@@ -222,87 +222,144 @@ def event_time_ms(lib, stream, fn, iters):
     return ms
 
 
-def kernel_rooflines(lib, stream, math, peaks, batch):
-    """Algorithmic bytes / flops per launch over the measured launch time, for
-    one representative ResNet-50 shape per kernel class."""
+# (cin, h, cout, k, stride, pad, operand type of the kernel, share-of-step note)
+CONV_ROOFLINE_SHAPES = (
+    (64, 56, 256, 1, 1, 0, "tf32"),    # DIRECT 1x1: conv_tma_fwd_kernel<0,0>, the kernel with the largest step share
+    (256, 56, 64, 1, 1, 0, "tf32"),
+    (256, 14, 1024, 1, 1, 0, "tf32"),
+    (64, 56, 64, 3, 1, 1, "bf16"),     # NHWC-shadow route, kind::f16
+    (256, 14, 256, 3, 1, 1, "bf16"),
+    (512, 7, 512, 3, 1, 1, "bf16"),    # the compute-bound end of the net
+)
+
+
+def ncu_traffic():
+    """DRAM bytes per launch from the committed `ncu --set full` captures (profiles/), keyed by
+    roofline entry name; made by tools/ncu_rooflines.sh + tools/ncu_traffic.py."""
+    p = ROOT / "profiles" / "ncu_traffic.json"
+    return json.loads(p.read_text()) if p.exists() else {}
+
+
+def kernel_rooflines(lib, stream, math, peaks, batch, only=""):
+    """Algorithmic bytes / flops per launch over the measured launch time, at the
+    bench batch, for the kernel classes of the path. Convolutions are reported against the roof
+    that bounds the shape: with FP32 NCHW tensors in HBM most ResNet-50 layers sit left of the
+    ridge, so their bound is "hbm" (algorithmic bytes = read x and W once, write y once);
+    `tc_frac` is always given beside it. Convolution entries time the whole C-ABI call (weight
+    pack, NHWC shadow of the shadow-route shapes, main kernel, split-K reduction)."""
     from bcnn_b200 import capi
     out = []
     n = batch
+    traffic = ncu_traffic()
 
     def buf(elems):
         return capi.DeviceBuffer(nbytes=int(elems) * 4)
 
+    def want(name):
+        return only in name
+
     # --- batchnorm on [n, 256, 56, 56] (largest BN class of the net)
     c, hw = 256, 56 * 56
     E = n * c * hw
-    x, y, dy = buf(E), buf(E), buf(E)
-    prm = [buf(c) for _ in range(9)]
-    scratch = buf(lib.bcnn_b200_bn_scratch_floats(c))
-    lib.bcnn_b200_fill_f32(prm[3].ptr, c, 1.0, stream)  # var
-    lib.bcnn_b200_fill_f32(prm[4].ptr, c, 1.0, stream)  # gamma
-    ms = event_time_ms(lib, stream, lambda: (
-        lib.bcnn_b200_bn_stats(x.ptr, n, c, hw, prm[0].ptr, prm[1].ptr, prm[2].ptr, prm[3].ptr,
-                               scratch.ptr, stream),
-        lib.bcnn_b200_bn_apply(x.ptr, y.ptr, prm[0].ptr, prm[1].ptr, prm[4].ptr, prm[5].ptr, n, c,
-                               hw, 2, stream)), 5)
-    out.append(dict(kernel="bn_forward_train(stats+apply+relu)", shape=[n, c, 56, 56], bound="hbm",
-                    bytes=12 * E, ms=ms))
-    ms = event_time_ms(lib, stream, lambda: lib.bcnn_b200_bn_backward(
-        x.ptr, y.ptr, dy.ptr, dy.ptr, prm[0].ptr, prm[3].ptr, prm[4].ptr, prm[5].ptr, prm[6].ptr,
-        prm[7].ptr, prm[8].ptr, prm[2].ptr, n, c, hw, 2, scratch.ptr, stream), 5)
-    out.append(dict(kernel="bn_backward(reduce+apply, relu fused)", shape=[n, c, 56, 56],
-                    bound="hbm", bytes=20 * E, ms=ms))
+    if any(want(k) for k in ("bn_forward_train(stats+apply+relu)", "bn_backward(reduce+apply, relu fused)",
+                             "bn_apply+relu (statistics from the conv epilogue)", "eltwise_add_relu")):
+        x, y, dy = buf(E), buf(E), buf(E)
+        prm = [buf(c) for _ in range(9)]
+        scratch = buf(lib.bcnn_b200_bn_scratch_floats(c))
+        lib.bcnn_b200_fill_f32(prm[3].ptr, c, 1.0, stream)  # var
+        lib.bcnn_b200_fill_f32(prm[4].ptr, c, 1.0, stream)  # gamma
+        if want("bn_forward_train(stats+apply+relu)"):
+            ms = event_time_ms(lib, stream, lambda: (
+                lib.bcnn_b200_bn_stats(x.ptr, n, c, hw, prm[0].ptr, prm[1].ptr, prm[2].ptr, prm[3].ptr,
+                                       scratch.ptr, stream),
+                lib.bcnn_b200_bn_apply(x.ptr, y.ptr, prm[0].ptr, prm[1].ptr, prm[4].ptr, prm[5].ptr, n,
+                                       c, hw, 2, stream)), 5)
+            out.append(dict(kernel="bn_forward_train(stats+apply+relu)", shape=[n, c, 56, 56],
+                            bound="hbm", bytes=12 * E, ms=ms))
+        if want("bn_apply+relu (statistics from the conv epilogue)"):
+            ms = event_time_ms(lib, stream, lambda: lib.bcnn_b200_bn_apply(
+                x.ptr, y.ptr, prm[0].ptr, prm[1].ptr, prm[4].ptr, prm[5].ptr, n, c, hw, 2, stream), 5)
+            out.append(dict(kernel="bn_apply+relu (statistics from the conv epilogue)",
+                            shape=[n, c, 56, 56], bound="hbm", bytes=8 * E, ms=ms))
+        if want("bn_backward(reduce+apply, relu fused)"):
+            ms = event_time_ms(lib, stream, lambda: lib.bcnn_b200_bn_backward(
+                x.ptr, y.ptr, dy.ptr, dy.ptr, prm[0].ptr, prm[3].ptr, prm[4].ptr, prm[5].ptr,
+                prm[6].ptr, prm[7].ptr, prm[8].ptr, prm[2].ptr, n, c, hw, 2, scratch.ptr, stream), 5)
+            out.append(dict(kernel="bn_backward(reduce+apply, relu fused)", shape=[n, c, 56, 56],
+                            bound="hbm", bytes=20 * E, ms=ms))
+        if want("eltwise_add_relu"):
+            ms = event_time_ms(lib, stream, lambda: lib.bcnn_b200_eltwise_forward(
+                x.ptr, dy.ptr, y.ptr, E, E, 2, stream), 5)
+            out.append(dict(kernel="eltwise_add_relu", shape=[n, c, 56, 56], bound="hbm",
+                            bytes=12 * E, ms=ms))
+        for b in (x, y, dy, scratch, *prm):
+            b.free()
     # --- max pool 3x3 s2 on [n, 64, 112, 112]
-    Ei, Eo = n * 64 * 112 * 112, n * 64 * 56 * 56
-    px, py, pi = buf(Ei), buf(Eo), buf(Eo)
-    ms = event_time_ms(lib, stream, lambda: lib.bcnn_b200_maxpool_forward(
-        px.ptr, py.ptr, pi.ptr, n, 64, 112, 112, 3, 2, 56, 56, stream), 5)
-    out.append(dict(kernel="maxpool_forward k3s2", shape=[n, 64, 112, 112], bound="hbm",
-                    bytes=4 * Ei + 8 * Eo, ms=ms))
-    ms = event_time_ms(lib, stream, lambda: lib.bcnn_b200_maxpool_backward(
-        px.ptr, py.ptr, pi.ptr, n, 64, 112, 112, 3, 2, 56, 56, stream), 5)
-    out.append(dict(kernel="maxpool_backward k3s2", shape=[n, 64, 112, 112], bound="hbm",
-                    bytes=8 * Eo + 8 * Ei, ms=ms))
-    # --- residual add + relu on [n, 256, 56, 56]
-    ms = event_time_ms(lib, stream, lambda: lib.bcnn_b200_eltwise_forward(
-        x.ptr, dy.ptr, y.ptr, E, E, 2, stream), 5)
-    out.append(dict(kernel="eltwise_add_relu", shape=[n, c, 56, 56], bound="hbm", bytes=12 * E,
-                    ms=ms))
-    for b in (x, y, dy, px, py, pi, scratch, *prm):
-        b.free()
-    # --- convolution: 3x3 64->64 @56x56 and 1x1 256->64 @56x56, 3x3 512 @7x7
-    for (cin, hh, cout, k, s, pad) in ((64, 56, 64, 3, 1, 1), (256, 56, 64, 1, 1, 0),
-                                       (512, 7, 512, 3, 1, 1)):
+    if want("maxpool_forward k3s2") or want("maxpool_backward k3s2"):
+        Ei, Eo = n * 64 * 112 * 112, n * 64 * 56 * 56
+        px, py, pi = buf(Ei), buf(Eo), buf(Eo)
+        ms = event_time_ms(lib, stream, lambda: lib.bcnn_b200_maxpool_forward(
+            px.ptr, py.ptr, pi.ptr, n, 64, 112, 112, 3, 2, 56, 56, stream), 5)
+        out.append(dict(kernel="maxpool_forward k3s2", shape=[n, 64, 112, 112], bound="hbm",
+                        bytes=4 * Ei + 8 * Eo, ms=ms))
+        ms = event_time_ms(lib, stream, lambda: lib.bcnn_b200_maxpool_backward(
+            px.ptr, py.ptr, pi.ptr, n, 64, 112, 112, 3, 2, 56, 56, stream), 5)
+        out.append(dict(kernel="maxpool_backward k3s2", shape=[n, 64, 112, 112], bound="hbm",
+                        bytes=8 * Eo + 8 * Ei, ms=ms))
+        for b in (px, py, pi):
+            b.free()
+    # --- convolution
+    for (cin, hh, cout, k, s, pad, kind) in CONV_ROOFLINE_SHAPES:
+        tag = f"{k}x{k} {cin}->{cout} @{hh}"
+        if not any(want(f"conv_{nm} {tag}") for nm in ("fprop", "dgrad", "wgrad")):
+            continue
         d = capi.ConvDesc.make(n, cin, hh, hh, cout, k, s, pad, 1)
         ws_bytes = lib.bcnn_b200_conv_workspace_bytes(d, math)
         ws = capi.DeviceBuffer(nbytes=max(ws_bytes, 4))
-        cx, cw = buf(n * cin * hh * hh), buf(cout * cin * k * k)
-        cy, cgw = buf(n * cout * d.ho * d.wo), buf(cout * cin * k * k)
+        ex, ey, ew = n * cin * hh * hh, n * cout * d.ho * d.wo, cout * cin * k * k
+        cx, cw, cy, cgw = buf(ex), buf(ew), buf(ey), buf(ew)
         flops = 2.0 * n * cout * d.ho * d.wo * cin * k * k
-        for name, call in (
+        for name, call, nbytes in (
             ("fprop", lambda: lib.bcnn_b200_conv_forward(d, cx.ptr, cw.ptr, None, 0, cy.ptr, ws.ptr,
-                                                         ws_bytes, math, stream)),
+                                                         ws_bytes, math, stream), 4 * (ex + ew + ey)),
             ("dgrad", lambda: lib.bcnn_b200_conv_backward_data(d, cw.ptr, cy.ptr, cx.ptr, 0, ws.ptr,
-                                                               ws_bytes, math, stream)),
+                                                               ws_bytes, math, stream), 4 * (ex + ew + ey)),
             ("wgrad", lambda: lib.bcnn_b200_conv_backward_weights(d, cx.ptr, cy.ptr, cgw.ptr, ws.ptr,
-                                                                  ws_bytes, math, stream))):
+                                                                  ws_bytes, math, stream),
+             4 * (ex + ey + 2 * ew))):
+            if not want(f"conv_{name} {tag}"):
+                continue
             ms = event_time_ms(lib, stream, call, 3)
-            out.append(dict(kernel=f"conv_{name} {k}x{k} {cin}->{cout} @{hh}", bound="tensor",
-                            shape=[n, cin, hh, hh], flops=flops, ms=ms))
+            out.append(dict(kernel=f"conv_{name} {tag}", shape=[n, cin, hh, hh], flops=flops,
+                            bytes=nbytes, ms=ms, kind=kind))
         for b in (ws, cx, cw, cy, cgw):
             b.free()
     res = []
     for r in out:
-        if r["bound"] == "hbm":
+        t = traffic.get(r["kernel"], {})
+        dram = t.get("dram_bytes")
+        if "flops" not in r:
             ach = r["bytes"] / (r["ms"] * 1e-3) / 1e9
             res.append(dict(kernel=r["kernel"], shape=r["shape"], bound="hbm", achieved=ach,
                             peak=peaks["hbm"], unit="GB/s", frac=ach / peaks["hbm"],
-                            ms_per_launch=r["ms"], traffic=None))
+                            ms_per_launch=r["ms"], traffic=dram))
+            continue
+        # tensor peak of the operand type: the measured BF16 GEMM peak, halved for kind::tf32
+        tc_peak = peaks["tc_burst"] * (0.5 if r["kind"] == "tf32" else 1.0)
+        t_hbm = r["bytes"] / (peaks["hbm"] * 1e9)
+        t_tc = r["flops"] / (tc_peak * 1e12)
+        tf = r["flops"] / (r["ms"] * 1e-3) / 1e12
+        gb = r["bytes"] / (r["ms"] * 1e-3) / 1e9
+        e = dict(kernel=r["kernel"], shape=r["shape"], ms_per_launch=r["ms"], traffic=dram,
+                 operands=r["kind"], tflops=tf, tc_peak=tc_peak, tc_frac=tf / tc_peak,
+                 algorithmic_gbs=gb, hbm_frac=gb / peaks["hbm"])
+        if t_hbm >= t_tc:
+            e.update(bound="hbm", achieved=gb, peak=peaks["hbm"], unit="GB/s", frac=gb / peaks["hbm"])
         else:
-            ach = r["flops"] / (r["ms"] * 1e-3) / 1e12
-            res.append(dict(kernel=r["kernel"], shape=r["shape"], bound="tensor", achieved=ach,
-                            peak=peaks["tc_burst"], unit="TFLOP/s", frac=ach / peaks["tc_burst"],
-                            ms_per_launch=r["ms"], traffic=None))
+            e.update(bound="tensor", achieved=tf, peak=tc_peak, unit="TFLOP/s", frac=tf / tc_peak)
+        if t.get("tensor_pipe_pct") is not None:
+            e["ncu_tensor_pipe_pct"] = t["tensor_pipe_pct"]
+        res.append(e)
     return res
 
 
@@ -424,12 +481,10 @@ def run_own_arm(args):
         breakdown = {k: dict(fwd_ms=round(v[0], 3), bwd_ms=round(v[1], 3)) for k, v in by_type.items()}
         dp_bytes = lib.bcnn_b200_dp_bytes_per_step(net.handle)
         net.close()
-        roofs = kernel_rooflines(lib, None, math, peaks, min(args.batch, 64)) if args.rooflines else []
-        conv = [r for r in roofs if r["bound"] == "tensor"]
-        dominant = None
-        if conv:
-            # the convolution kernels carry the bulk of the step; report the largest-FLOP shape
-            dominant = max(conv, key=lambda r: r["ms_per_launch"])
+        roofs = kernel_rooflines(lib, None, math, peaks, args.batch) if args.rooflines else []
+        # headline: conv_tma_fwd_kernel (fprop + dgrad) has the largest share of the step in the
+        # ncu launch list (profiles/); its heaviest ResNet-50 shape is the 1x1 64->256 @56 fprop
+        dominant = next((r for r in roofs if r["kernel"].startswith("conv_fprop 1x1 64->256")), None)
         cpu = None
         if world == 1 and args.cpu_baseline:
             r = time_reference(args.workload, args.res, steps=1, warmup=0, budget_s=20.0)
