@@ -65,7 +65,7 @@ extern "C" int bcnn_b200_conv_forward_sh(const bcnn_b200_conv_desc *d, const flo
         return conv_tma_forward(d, x, w, bias, act, y, workspace, workspace_bytes, sh, st);
     if (math == BCNN_B200_MATH_TC && conv_tc_supports_fprop(d))
         return conv_tc_forward(d, x, w, bias, act, y, workspace, workspace_bytes, st);
-    return conv_simt_forward(d, x, w, bias, act, y, st);
+    return conv_simt_forward(d, x, w, bias, act, y, workspace, workspace_bytes, st);
 }
 
 extern "C" int bcnn_b200_conv_forward_bn_stats(const bcnn_b200_conv_desc *d, const float *x,
@@ -107,7 +107,7 @@ extern "C" int bcnn_b200_conv_backward_data_sh(const bcnn_b200_conv_desc *d, con
         return conv_tma_backward_data(d, w, dy, dx, accumulate, workspace, workspace_bytes, sh, st);
     if (math == BCNN_B200_MATH_TC && conv_tc_supports_dgrad(d))
         return conv_tc_backward_data(d, w, dy, dx, accumulate, workspace, workspace_bytes, st);
-    return conv_simt_backward_data(d, w, dy, dx, accumulate, st);
+    return conv_simt_backward_data(d, w, dy, dx, accumulate, workspace, workspace_bytes, st);
 }
 
 extern "C" int bcnn_b200_conv_backward_weights_sh(const bcnn_b200_conv_desc *d, const float *x,

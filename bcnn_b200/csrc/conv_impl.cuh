@@ -10,9 +10,11 @@ namespace b200 {
 // FP32 SIMT path (conv_simt.cu) -- covers every shape.
 size_t conv_simt_workspace_bytes(const bcnn_b200_conv_desc *d);
 int conv_simt_forward(const bcnn_b200_conv_desc *d, const float *x, const float *w,
-                      const float *bias, int act, float *y, cudaStream_t st);
+                      const float *bias, int act, float *y, void *workspace, size_t workspace_bytes,
+                      cudaStream_t st);
 int conv_simt_backward_data(const bcnn_b200_conv_desc *d, const float *w, const float *dy,
-                            float *dx, int accumulate, cudaStream_t st);
+                            float *dx, int accumulate, void *workspace, size_t workspace_bytes,
+                            cudaStream_t st);
 int conv_simt_backward_weights(const bcnn_b200_conv_desc *d, const float *x, const float *dy,
                                float *gw, void *workspace, size_t workspace_bytes,
                                cudaStream_t st);

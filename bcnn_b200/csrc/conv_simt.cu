@@ -276,6 +276,21 @@ igemm_kernel(const ConvP p) {
             const int chans = (MODE == FPROP) ? p.cout : p.cin;
             const int ch = (MODE == FPROP) ? g * p.cout_g + m : g * p.cin_g + m;
             const float bv = (MODE == FPROP && p.bias) ? __ldg(p.bias + ch) : 0.f;
+            if (p.splits > 1) {
+                // split-K: raw partial sums into slab `split`; splitk_finish_kernel folds the slabs
+                // in split order and applies bias / activation / accumulation
+                float *slab = p.out + (size_t)split * p.out_split_stride;
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                    const int n = n0 + (j < 4 ? tx * 4 + j : 64 + tx * 4 + (j - 4));
+                    if (n >= p.N) continue;
+                    uint32_t bj, pj;
+                    if (MODE == FPROP) p.d_howo.divmod(n, bj, pj);
+                    else p.d_hw.divmod(n, bj, pj);
+                    slab[((size_t)bj * chans + ch) * plane + pj] = acc[i][j];
+                }
+                continue;
+            }
 #pragma unroll
             for (int half = 0; half < 2; ++half) {
                 const int n = n0 + half * 64 + tx * 4;
@@ -324,6 +339,65 @@ splitk_reduce_kernel(float *__restrict__ gw, const float *__restrict__ partial, 
         for (int k = 0; k < splits; ++k) s += __ldg(partial + (size_t)k * n + i);
         gw[i] += s;
     }
+}
+
+// out[i] = act(sum_s partial[s][i] + bias[channel])  (fprop)  or  out[i] (+)= sum_s partial[s][i]
+// (dgrad), slabs folded in split order.
+__global__ void __launch_bounds__(256)
+splitk_finish_kernel(float *__restrict__ out, const float *__restrict__ partial, size_t n, int splits,
+                     const float *__restrict__ bias, int act, int accumulate, FastDiv d_plane,
+                     FastDiv d_chans) {
+    size_t gstride = (size_t)gridDim.x * blockDim.x;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gstride) {
+        float s = 0.f;
+        for (int k = 0; k < splits; ++k) s += __ldg(partial + (size_t)k * n + i);
+        if (bias) {
+            uint32_t q, ch;
+            d_chans.divmod(d_plane.div((uint32_t)i), q, ch);
+            s += __ldg(bias + ch);
+        }
+        s = act_fwd(s, act, 0.f);
+        out[i] = accumulate ? out[i] + s : s;
+    }
+}
+
+// Split-K for fprop / dgrad launches whose tile grid would leave most SMs idle (fully-connected
+// layers: a few tiles with a K of thousands): enough splits for about two CTAs per SM, at least
+// 128 reduction steps each.
+int fwd_splits(int M, int N, int K, int groups) {
+    const int bm = M > 64 ? 128 : (M > 32 ? 64 : 32);
+    const long long tiles = (long long)ceil_div(M, bm) * ceil_div(N, BN) * groups;
+    if (tiles * 2 > sm_count() || K < 512) return 1;
+    long long want = (2LL * sm_count() + tiles - 1) / tiles;
+    if (want > K / 128) want = K / 128;
+    if (want > 32) want = 32;
+    return want < 1 ? 1 : (int)want;
+}
+
+template <int MODE>
+int launch(ConvP &p, cudaStream_t st);
+
+// Runs an fprop / dgrad launch, through split-K partial slabs in `workspace` when that pays.
+template <int MODE>
+int launch_fwd_like(ConvP &p, float *out, size_t out_elems, int plane, int chans, void *workspace,
+                    size_t workspace_bytes, cudaStream_t st) {
+    const int s = out_elems < (1ull << 31) ? fwd_splits(p.M, p.N, p.K, p.groups) : 1;
+    if (s <= 1 || workspace == nullptr || workspace_bytes < (size_t)s * out_elems * sizeof(float)) {
+        p.out = out;
+        return launch<MODE>(p, st);
+    }
+    const float *bias = p.bias;
+    const int act = p.act, accumulate = p.accumulate;
+    p.out = reinterpret_cast<float *>(workspace);
+    p.splits = s;
+    p.out_split_stride = out_elems;
+    p.kchunk = ceil_div(ceil_div(p.K, s), BK) * BK;
+    int err = launch<MODE>(p, st);
+    if (err) return err;
+    splitk_finish_kernel<<<stream_grid(out_elems, 256), 256, 0, st>>>(
+        out, reinterpret_cast<const float *>(workspace), out_elems, s, bias, act, accumulate,
+        FastDiv((uint32_t)plane), FastDiv((uint32_t)chans));
+    return launched();
 }
 
 void fill_geom(ConvP &p, const bcnn_b200_conv_desc *d) {
@@ -380,28 +454,38 @@ int wgrad_splits(const bcnn_b200_conv_desc *d) {
 namespace b200 {
 
 size_t conv_simt_workspace_bytes(const bcnn_b200_conv_desc *d) {
+    size_t need = 0;
     int s = wgrad_splits(d);
-    if (s <= 1) return 0;
-    size_t wsize = (size_t)d->cout * (d->cin / d->groups) * d->ksize * d->ksize;
-    return (size_t)s * wsize * sizeof(float);
+    if (s > 1) need = (size_t)s * d->cout * (d->cin / d->groups) * d->ksize * d->ksize * sizeof(float);
+    const int kk = d->ksize * d->ksize, cin_g = d->cin / d->groups, cout_g = d->cout / d->groups;
+    s = fwd_splits(cout_g, d->batch * d->ho * d->wo, cin_g * kk, d->groups);
+    size_t b = s > 1 ? (size_t)s * d->batch * d->cout * d->ho * d->wo * sizeof(float) : 0;
+    if (b > need) need = b;
+    s = fwd_splits(cin_g, d->batch * d->h * d->w, cout_g * kk, d->groups);
+    b = s > 1 ? (size_t)s * d->batch * d->cin * d->h * d->w * sizeof(float) : 0;
+    return b > need ? b : need;
 }
 
 int conv_simt_forward(const bcnn_b200_conv_desc *d, const float *x, const float *w,
-                      const float *bias, int act, float *y, cudaStream_t st) {
+                      const float *bias, int act, float *y, void *workspace, size_t workspace_bytes,
+                      cudaStream_t st) {
     ConvP p;
     fill_geom(p, d);
-    p.x = x; p.w = w; p.out = y; p.bias = bias; p.act = act;
+    p.x = x; p.w = w; p.bias = bias; p.act = act;
     p.M = p.cout_g; p.N = d->batch * p.howo; p.K = p.cin_g * p.kk;
-    return launch<FPROP>(p, st);
+    return launch_fwd_like<FPROP>(p, y, (size_t)d->batch * d->cout * p.howo, p.howo, d->cout, workspace,
+                                  workspace_bytes, st);
 }
 
 int conv_simt_backward_data(const bcnn_b200_conv_desc *d, const float *w, const float *dy,
-                            float *dx, int accumulate, cudaStream_t st) {
+                            float *dx, int accumulate, void *workspace, size_t workspace_bytes,
+                            cudaStream_t st) {
     ConvP p;
     fill_geom(p, d);
-    p.w = w; p.dy = dy; p.out = dx; p.accumulate = accumulate;
+    p.w = w; p.dy = dy; p.accumulate = accumulate;
     p.M = p.cin_g; p.N = d->batch * p.hw; p.K = p.cout_g * p.kk;
-    return launch<DGRAD>(p, st);
+    return launch_fwd_like<DGRAD>(p, dx, (size_t)d->batch * d->cin * p.hw, p.hw, d->cin, workspace,
+                                  workspace_bytes, st);
 }
 
 int conv_simt_backward_weights(const bcnn_b200_conv_desc *d, const float *x, const float *dy,

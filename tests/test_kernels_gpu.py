@@ -293,6 +293,9 @@ CONV_CASES = [
     (2, 32, 12, 12, 32, 2, 2, 0, 1),   # k2 s2: one tap per class
     (2, 32, 9, 9, 16, 1, 2, 0, 1),     # 1x1 s2 on an odd plane: three empty classes
     (2, 64, 28, 28, 64, 3, 2, 1, 1),   # resnet stride-2 3x3 at a size with several tiles
+    # fully-connected layers (1x1 plane): a handful of tiles with a long K -> split-K fprop / dgrad
+    (64, 1024, 1, 1, 100, 1, 1, 0, 1),
+    (16, 640, 2, 2, 24, 1, 1, 0, 1),
 ]
 
 
