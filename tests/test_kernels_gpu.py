@@ -502,7 +502,11 @@ def test_conv_forward_bn_stats_matches_separate_kernels(case, math):
 
 # ------------------------------------------------------------------ depthwise
 @pytest.mark.parametrize("n,c,h,w,k,s,pad", [(2, 32, 28, 28, 3, 1, 1), (2, 16, 28, 28, 3, 2, 1),
-                                             (1, 7, 9, 11, 3, 1, 0), (2, 4, 12, 12, 5, 1, 2)])
+                                             (1, 7, 9, 11, 3, 1, 0), (2, 4, 12, 12, 5, 1, 2),
+                                             # 3x3 fast paths: ragged groups of four, odd planes
+                                             (2, 8, 15, 13, 3, 2, 1), (1, 5, 10, 10, 3, 1, 1),
+                                             (2, 4, 12, 12, 3, 1, 2), (3, 6, 14, 14, 3, 2, 1),
+                                             (2, 8, 7, 7, 3, 1, 1), (2, 6, 11, 12, 3, 2, 0)])
 def test_depthwise(n, c, h, w, k, s, pad):
     lib, orc = capi.b200(), oracle()
     r = rng(n + c * 13 + h)
