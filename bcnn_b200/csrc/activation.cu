@@ -4,6 +4,8 @@
 //
 // Arithmetic follows reference src/layers/bcnn_activation_layer.c:90-226 (all ten
 // activations; the reference's own .cu covers six) and src/kernels/bcnn_mat.c:761-811.
+#include <cstdlib>
+
 #include "common.cuh"
 
 using namespace b200;
@@ -202,13 +204,16 @@ eltwise_fwd_kernel(const float *__restrict__ a, const float *__restrict__ b, flo
 __global__ void __launch_bounds__(256)
 eltwise_bwd_kernel(const float *__restrict__ y, float *__restrict__ dy, float *__restrict__ da,
                    float *__restrict__ db, size_t n, size_t n_add, int act, bool vec, bool acc_a,
-                   bool acc_b) {
+                   bool acc_b, bool reverse) {
     size_t gstride = (size_t)gridDim.x * blockDim.x;
     size_t tid = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     size_t done = 0;
     if (vec) {
         size_t n4 = n >> 2;
-        for (size_t j = tid; j < n4; j += gstride) {
+        for (size_t i = tid; i < n4; i += gstride) {
+            // descending: dy was just written by an ascending convolution (its tail is in L2) and
+            // the head written last here is what the next per-channel reduction reads first
+            const size_t j = reverse ? n4 - 1 - i : i;
             float4 g = reinterpret_cast<float4 *>(dy)[j];
             if (act != ACT_NONE) {
                 float4 v = reinterpret_cast<const float4 *>(y)[j];
@@ -341,6 +346,6 @@ extern "C" int bcnn_b200_eltwise_backward(const float *y, float *dy, float *da, 
     bool vec = aligned16(y) && aligned16(dy) && aligned16(da) && aligned16(db) && (n_add % 4) == 0;
     eltwise_bwd_kernel<<<stream_grid(vec ? sz / 4 + 1 : sz, 256), 256, 0, as_stream(stream)>>>(
         y, dy, da, db, (size_t)sz, (size_t)n_add, act, vec, (accumulate_flags & 1) != 0,
-        (accumulate_flags & 2) != 0);
+        (accumulate_flags & 2) != 0, getenv("BCNN_B200_NO_REVERSE") == nullptr);
     return launched();
 }

@@ -26,6 +26,19 @@ constexpr int MAX_SPLITS = 64;   // scratch layout assumes this (bcnn_b200_bn_sc
 
 inline bool aligned16(const void *p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
 
+// The lean elementwise streams walk their tensor from the END: the producer (a convolution or a
+// per-channel reduction, both ascending) has just left the tail of the tensor in the 126 MB L2, and
+// what these streams write last -- the head -- is what the next ascending consumer reads first.
+inline bool reverse_streams() {
+    static const bool on = !getenv("BCNN_B200_NO_REVERSE");
+    return on;
+}
+
+inline bool l2_hints() {
+    static const bool on = !getenv("BCNN_B200_NO_L2_HINTS");
+    return on;
+}
+
 inline int reduce_splits(int n, int c) {
     int target = 2 * sm_count();
     int s = ceil_div(target, c);
@@ -440,8 +453,10 @@ template <int ACT>   // ACT_NONE, ACT_RELU or ACT_LRELU
 __global__ void __launch_bounds__(256)
 bn_apply_fast_kernel(const float *__restrict__ x, float *__restrict__ y, const float *__restrict__ mean,
                      const float *__restrict__ var, const float *__restrict__ gamma,
-                     const float *__restrict__ beta, uint32_t n4, int c, FastDiv div_hw4, FastDiv div_c) {
+                     const float *__restrict__ beta, uint32_t n4, int c, FastDiv div_hw4, FastDiv div_c,
+                     bool reverse, bool hints) {
     extern __shared__ float4 bn_tab[];   // {mean, 1/sqrt(var + 1e-6), gamma, beta}
+    const uint64_t pol_in = l2_policy_evict_first(), pol_out = l2_policy_evict_last();
     for (int i = threadIdx.x; i < c; i += 256)
         bn_tab[i] = make_float4(__ldg(mean + i), 1.0f / sqrtf(__ldg(var + i) + 0.000001f), __ldg(gamma + i),
                                 __ldg(beta + i));
@@ -452,13 +467,17 @@ bn_apply_fast_kernel(const float *__restrict__ x, float *__restrict__ y, const f
         float4 v[UNROLL];
 #pragma unroll
         for (int u = 0; u < UNROLL; ++u) {
-            const uint32_t j = j0 + u * gstride;
-            if (j < n4) v[u] = ld_stream4(x + ((size_t)j << 2));
+            const uint32_t i = j0 + u * gstride;
+            if (i < n4) {
+                const float *src = x + ((size_t)(reverse ? n4 - 1 - i : i) << 2);
+                v[u] = hints ? ld_stream4_hint(src, pol_in) : ld_stream4(src);
+            }
         }
 #pragma unroll
         for (int u = 0; u < UNROLL; ++u) {
-            const uint32_t j = j0 + u * gstride;
-            if (j < n4) {
+            const uint32_t i = j0 + u * gstride;
+            if (i < n4) {
+                const uint32_t j = reverse ? n4 - 1 - i : i;
                 uint32_t q, ch;
                 div_c.divmod(div_hw4.div(j), q, ch);
                 const float4 t = bn_tab[ch];
@@ -473,7 +492,8 @@ bn_apply_fast_kernel(const float *__restrict__ x, float *__restrict__ y, const f
                     r.x = r.x > 0 ? r.x : 0.1f * r.x; r.y = r.y > 0 ? r.y : 0.1f * r.y;
                     r.z = r.z > 0 ? r.z : 0.1f * r.z; r.w = r.w > 0 ? r.w : 0.1f * r.w;
                 }
-                st_stream4(y + ((size_t)j << 2), r);
+                if (hints) st_stream4_hint(y + ((size_t)j << 2), r, pol_out);
+                else st_stream4(y + ((size_t)j << 2), r);
             }
         }
     }
@@ -486,7 +506,9 @@ bn_bwd_apply_fast_kernel(const float *__restrict__ x, const float *dy, float *dx
                          const float *__restrict__ mean, const float *__restrict__ var,
                          const float *__restrict__ gamma, const float *__restrict__ beta,
                          const float *__restrict__ d_mean, const float *__restrict__ d_var, uint32_t n4,
-                         int c, int count, float neg, FastDiv div_hw4, FastDiv div_c) {
+                         int c, int count, float neg, FastDiv div_hw4, FastDiv div_c, bool reverse,
+                         bool hints) {
+    const uint64_t pol_in = l2_policy_evict_first(), pol_out = l2_policy_evict_last();
     extern __shared__ float4 bn_tab[];   // [c] {mean, k1, k2, k3}, then [c] {1/sqrt(var + 1e-6), gamma, beta, -}
     const float inv_count = 1.0f / (float)count;
     for (int i = threadIdx.x; i < c; i += 256) {
@@ -502,16 +524,24 @@ bn_bwd_apply_fast_kernel(const float *__restrict__ x, const float *dy, float *dx
         float4 xv[UNROLL], gv[UNROLL];
 #pragma unroll
         for (int u = 0; u < UNROLL; ++u) {
-            const uint32_t j = j0 + u * gstride;
-            if (j < n4) {
-                xv[u] = ld_stream4(x + ((size_t)j << 2));
-                gv[u] = reinterpret_cast<const float4 *>(dy)[j];   // dx may alias dy: coherent load
+            const uint32_t i = j0 + u * gstride;
+            if (i < n4) {
+                const uint32_t j = reverse ? n4 - 1 - i : i;
+                // dx may alias dy: coherent load for dy
+                if (hints) {
+                    xv[u] = ld_stream4_hint(x + ((size_t)j << 2), pol_in);
+                    gv[u] = ld4_hint(dy + ((size_t)j << 2), pol_in);
+                } else {
+                    xv[u] = ld_stream4(x + ((size_t)j << 2));
+                    gv[u] = reinterpret_cast<const float4 *>(dy)[j];
+                }
             }
         }
 #pragma unroll
         for (int u = 0; u < UNROLL; ++u) {
-            const uint32_t j = j0 + u * gstride;
-            if (j < n4) {
+            const uint32_t i = j0 + u * gstride;
+            if (i < n4) {
+                const uint32_t j = reverse ? n4 - 1 - i : i;
                 uint32_t q, ch;
                 div_c.divmod(div_hw4.div(j), q, ch);
                 const float4 t = bn_tab[ch];
@@ -528,7 +558,8 @@ bn_bwd_apply_fast_kernel(const float *__restrict__ x, const float *dy, float *dx
                 o.y = g.y * t.y + t.z * (xv[u].y - t.x) + t.w;
                 o.z = g.z * t.y + t.z * (xv[u].z - t.x) + t.w;
                 o.w = g.w * t.y + t.z * (xv[u].w - t.x) + t.w;
-                reinterpret_cast<float4 *>(dx)[j] = o;
+                if (hints) st_stream4_hint(dx + ((size_t)j << 2), o, pol_out);
+                else reinterpret_cast<float4 *>(dx)[j] = o;
             }
         }
     }
@@ -580,12 +611,13 @@ extern "C" int bcnn_b200_bn_apply(const float *x, float *y, const float *mean, c
         const size_t smem = (size_t)c * sizeof(float4);
         const FastDiv dhw4(hw / 4), dc(c);
         cudaStream_t st = as_stream(stream);
+        const bool rev = reverse_streams();
         if (act == ACT_RELU)
-            bn_apply_fast_kernel<ACT_RELU><<<grid, 256, smem, st>>>(x, y, mean, var, gamma, beta, n4, c, dhw4, dc);
+            bn_apply_fast_kernel<ACT_RELU><<<grid, 256, smem, st>>>(x, y, mean, var, gamma, beta, n4, c, dhw4, dc, rev, l2_hints());
         else if (act == ACT_LRELU)
-            bn_apply_fast_kernel<ACT_LRELU><<<grid, 256, smem, st>>>(x, y, mean, var, gamma, beta, n4, c, dhw4, dc);
+            bn_apply_fast_kernel<ACT_LRELU><<<grid, 256, smem, st>>>(x, y, mean, var, gamma, beta, n4, c, dhw4, dc, rev, l2_hints());
         else
-            bn_apply_fast_kernel<ACT_NONE><<<grid, 256, smem, st>>>(x, y, mean, var, gamma, beta, n4, c, dhw4, dc);
+            bn_apply_fast_kernel<ACT_NONE><<<grid, 256, smem, st>>>(x, y, mean, var, gamma, beta, n4, c, dhw4, dc, rev, l2_hints());
         return launched();
     }
     bn_apply_kernel<true><<<stream_grid(vec ? total / 4 : total, 256), 256, 0, as_stream(stream)>>>(
@@ -632,12 +664,13 @@ extern "C" int bcnn_b200_bn_backward(const float *x, const float *y, float *dy, 
         const int grid = stream_grid(ceil_div_sz(n4, 2), 256);
         const FastDiv dhw4(hw / 4), dc(c);
         const float neg = act == ACT_LRELU ? 0.1f : 0.f;
+        const bool rev = reverse_streams();
         if (remask)
             bn_bwd_apply_fast_kernel<true><<<grid, 256, (size_t)2 * c * sizeof(float4), st>>>(
-                x, dy, dx_out, mean, var, gamma, beta, d_mean, d_var, n4, c, n * hw, neg, dhw4, dc);
+                x, dy, dx_out, mean, var, gamma, beta, d_mean, d_var, n4, c, n * hw, neg, dhw4, dc, rev, l2_hints());
         else
             bn_bwd_apply_fast_kernel<false><<<grid, 256, (size_t)c * sizeof(float4), st>>>(
-                x, dy, dx_out, mean, var, gamma, beta, d_mean, d_var, n4, c, n * hw, neg, dhw4, dc);
+                x, dy, dx_out, mean, var, gamma, beta, d_mean, d_var, n4, c, n * hw, neg, dhw4, dc, rev, l2_hints());
         return launched();
     }
     bn_bwd_apply_kernel<<<stream_grid(vec ? total / 4 : total, 256), 256, 0, st>>>(

@@ -100,6 +100,36 @@ __device__ __forceinline__ void st_stream4(float *p, float4 v) {
                  :: "l"(p), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
 }
 
+// The same with L2 eviction priorities: read-once operands leave L2 first, results that the next
+// kernel consumes stay last (a stream then keeps its freshly written tail / head in the 126 MB L2
+// instead of the operands it will never touch again).
+__device__ __forceinline__ uint64_t l2_policy_evict_first() {
+    uint64_t p;
+    asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(p));
+    return p;
+}
+__device__ __forceinline__ uint64_t l2_policy_evict_last() {
+    uint64_t p;
+    asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(p));
+    return p;
+}
+__device__ __forceinline__ float4 ld_stream4_hint(const float *p, uint64_t policy) {
+    float4 r;
+    asm volatile("ld.global.nc.L1::no_allocate.L2::cache_hint.v4.f32 {%0,%1,%2,%3}, [%4], %5;"
+                 : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w) : "l"(p), "l"(policy));
+    return r;
+}
+__device__ __forceinline__ float4 ld4_hint(const float *p, uint64_t policy) {   // coherent flavour
+    float4 r;
+    asm volatile("ld.global.L1::no_allocate.L2::cache_hint.v4.f32 {%0,%1,%2,%3}, [%4], %5;"
+                 : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w) : "l"(p), "l"(policy) : "memory");
+    return r;
+}
+__device__ __forceinline__ void st_stream4_hint(float *p, float4 v, uint64_t policy) {
+    asm volatile("st.global.L1::no_allocate.L2::cache_hint.v4.f32 [%0], {%1,%2,%3,%4}, %5;"
+                 :: "l"(p), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w), "l"(policy) : "memory");
+}
+
 // Activation forward, arithmetic of bcnn_forward_activation_cpu
 // (reference src/layers/bcnn_activation_layer.c:90-146): transcendentals go through
 // double exp/log and are rounded to float where the reference casts.

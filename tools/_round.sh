@@ -1,4 +1,6 @@
-mkdir -p gpurun_out/r1o
-timeout 300 python -m pytest tests -m gpu -x -q > gpurun_out/r1o/gpu_tests.log 2>&1; tail -4 gpurun_out/r1o/gpu_tests.log
-timeout 200 python tools/dw_sweep.py 64 > gpurun_out/r1o/dw_sweep_b64.txt 2>&1; cat gpurun_out/r1o/dw_sweep_b64.txt
-timeout 200 python bench.py --workload mobilenet --batch 64 --res 224 --no-rooflines --no-cpu-baseline > gpurun_out/r1o/bench_mobilenet.json 2>> gpurun_out/r1o/bench.err; cut -c1-200 gpurun_out/r1o/bench_mobilenet.json
+mkdir -p gpurun_out/r1p
+timeout 300 python -m pytest tests -m gpu -x -q > gpurun_out/r1p/gpu_tests.log 2>&1; tail -3 gpurun_out/r1p/gpu_tests.log
+for i in 1 2; do
+timeout 300 python bench.py --no-cpu-baseline --no-rooflines > gpurun_out/r1p/bench_n1.json 2> gpurun_out/r1p/bench_n1.err; head -c 250 gpurun_out/r1p/bench_n1.json; echo
+BCNN_B200_NO_L2_HINTS=1 timeout 300 python bench.py --no-cpu-baseline --no-rooflines > gpurun_out/r1p/bench_n1_nohint.json 2> gpurun_out/r1p/bench_n1.err; head -c 250 gpurun_out/r1p/bench_n1_nohint.json; echo
+done
