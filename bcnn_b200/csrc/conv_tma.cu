@@ -1353,9 +1353,19 @@ bool plan_wgrad(const bcnn_b200_conv_desc *desc, WgPlan *pl) {
     pl->nhwc = !direct;
     if (!direct && (nhwc_disabled() || d->cin_phys % 4 != 0 || d->cout % 4 != 0 || d->stride > 4))
         return false;
+    // N tile (input channels): up to 128 columns leave room for two co-resident CTAs per SM; layers
+    // on small planes with many channels are bound by L2 -> SM operand traffic instead (every dY
+    // tile is re-read per N tile, every X tile per M tile), so they take 256-column tiles
+    static int wg_nmax = 0;
+    if (!wg_nmax) {
+        const char *e = getenv("BCNN_B200_WG_NMAX");
+        wg_nmax = e ? atoi(e) : 256;
+        if (wg_nmax != 128 && wg_nmax != 256) wg_nmax = 256;
+    }
+    const int nmax = d->cin >= 256 ? wg_nmax : 128;
     int n = d->cin;
-    if (n > 128) {
-        int tiles = ceil_div(n, 128);
+    if (n > nmax) {
+        int tiles = ceil_div(n, nmax);
         n = ceil_div(ceil_div(n, tiles), 16) * 16;
     } else {
         n = ceil_div(n, 16) * 16;
