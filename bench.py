@@ -188,8 +188,8 @@ def run_reference_arm(args):
                per_gpu_batch=args.batch, global_batch=args.batch * args.gpus)
     r = time_reference(args.workload, args.res, args.steps, args.warmup, budget_s=150.0)
     if r is None:
-        print(json.dumps({"impl": "reference", "unavailable":
-                          "oracle/_ref/libbcnn_ref.so missing (reference CPU library not built)"}))
+        emit(json.dumps({"impl": "reference", "unavailable":
+                         "oracle/_ref/libbcnn_ref.so missing (reference CPU library not built)"}))
         return 0
     cfg["cpu_sample_batch"] = r["batch"]
     line = {"impl": "reference", "metric": METRIC, "value": r["value"], "unit": UNIT,
@@ -201,7 +201,7 @@ def run_reference_arm(args):
             "e2e": {"value": r["value"], "unit": UNIT, "h2d_bytes_per_step": 0,
                     "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
-    print(json.dumps(line))
+    emit(json.dumps(line))
     return 0
 
 
@@ -520,13 +520,42 @@ def run_own_arm(args):
             result["rooflines"] = roofs
         if cpu:
             result["cpu_baseline"] = cpu
-        print(json.dumps(result))
+        emit(json.dumps(result))
     else:
         net.close()
     if dist:
         dist.barrier()
         dist.destroy_process_group()
     return 0
+
+
+class JsonOnlyStdout:
+    """Everything libraries print to file descriptor 1 (NCCL's version banner, ...) goes to stderr;
+    the JSON line is the only thing written to the real stdout."""
+
+    def __enter__(self):
+        sys.stdout.flush()
+        self.real = os.dup(1)
+        os.dup2(2, 1)
+        return self
+
+    def emit(self, line: str):
+        os.write(self.real, (line + "\n").encode())
+
+    def __exit__(self, *exc):
+        sys.stdout.flush()
+        os.dup2(self.real, 1)
+        os.close(self.real)
+
+
+OUT = None
+
+
+def emit(line: str):
+    if OUT is not None:
+        OUT.emit(line)
+    else:
+        print(line, flush=True)
 
 
 def main():
@@ -548,9 +577,11 @@ def main():
     import faulthandler
     faulthandler.dump_traceback_later(int(os.environ.get("BCNN_B200_BENCH_WATCHDOG_S", "1500")), exit=True)
     args.warmup = max(args.warmup, 3) if args.impl == "own" else args.warmup
-    if args.impl == "reference":
-        return run_reference_arm(args)
-    return run_own_arm(args)
+    global OUT
+    with JsonOnlyStdout() as OUT:
+        if args.impl == "reference":
+            return run_reference_arm(args)
+        return run_own_arm(args)
 
 
 if __name__ == "__main__":
