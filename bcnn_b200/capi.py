@@ -88,6 +88,8 @@ def bind_bcnn_api(lib: C.CDLL, tensor_type) -> None:
         "bcnn_add_fullc_layer": (i, [vp, i, i, i, i, s, s]),
         "bcnn_add_softmax_layer": (i, [vp, s, s]),
         "bcnn_add_eltwise_layer": (i, [vp, i, s, s, s]),
+        "bcnn_add_concat_layer": (i, [vp, i, C.POINTER(C.c_char_p), s]),
+        "bcnn_add_upsample_layer": (i, [vp, i, s, s]),
         "bcnn_add_cost_layer": (i, [vp, i, i, f, s, s, s]),
     }
     for name, (res, args) in sigs.items():
@@ -238,6 +240,15 @@ class Net:
     def eltwise(self, act, src1, src2, dst):
         self._check(self.lib.bcnn_add_eltwise_layer(self.handle, ACT[act], _b(src1),
                                                     _b(src2), _b(dst)), f"eltwise {dst}")
+
+    def concat(self, srcs, dst):
+        arr = (C.c_char_p * len(srcs))(*[_b(x) for x in srcs])
+        self._check(self.lib.bcnn_add_concat_layer(self.handle, len(srcs), arr, _b(dst)),
+                    f"concat {dst}")
+
+    def upsample(self, size, src, dst):
+        self._check(self.lib.bcnn_add_upsample_layer(self.handle, size, _b(src), _b(dst)),
+                    f"upsample {dst}")
 
     def cost(self, src, dst="cost", metric=METRIC_ERROR_RATE, scale=1.0):
         self._check(self.lib.bcnn_add_cost_layer(self.handle, LOSS_EUCLIDEAN, metric, scale,
@@ -435,6 +446,10 @@ def bind_kernel_abi(lib: C.CDLL) -> None:
         "bcnn_b200_cost_forward": (i, [vp, vp, vp, vp, i, i, i, vp]),
         "bcnn_b200_eltwise_forward": (i, [vp, vp, vp, i, i, i, vp]),
         "bcnn_b200_eltwise_backward": (i, [vp, vp, vp, vp, i, i, i, i, vp]),
+        "bcnn_b200_concat_forward": (i, [vp, vp, i, i, i, i, vp]),
+        "bcnn_b200_concat_backward": (i, [vp, vp, i, i, i, i, i, vp]),
+        "bcnn_b200_upsample_forward": (i, [vp, vp, i, i, i, i, i, vp]),
+        "bcnn_b200_upsample_backward": (i, [vp, vp, i, i, i, i, i, i, vp]),
     }
     for name, (res, args) in sigs.items():
         fn = getattr(lib, name)

@@ -81,6 +81,11 @@ def mobilenet(net, batch=1, res=224, classes=1000):
 
 
 def yolo_tiny(net, batch=1, res=416):
+    """YOLOv3-tiny (examples/yolo/yolov3-tiny.cfg) with both heads: trunk, coarse head at res/32,
+    route -> 1x1 conv -> upsample x2 -> concat with the 256-channel trunk tensor at res/16 -> fine
+    head. The yolo loss layers stay out of scope (host-side in the reference): for
+    training the fine head carries a euclidean cost, the coarse head's output has no consumer and
+    so receives a zero gradient (its convolutions still run forward and backward)."""
     net.set_input_shape(res, res, 3, batch)
     prev = "input"
     for i, c in enumerate([16, 32, 64, 128, 256, 512]):
@@ -90,7 +95,12 @@ def yolo_tiny(net, batch=1, res=416):
     net.conv(1024, 3, 1, 1, 1, 1, "lrelu", prev, "conv6")
     net.conv(256, 1, 1, 0, 1, 1, "lrelu", "conv6", "conv7")
     net.conv(512, 3, 1, 1, 1, 1, "lrelu", "conv7", "conv8")
-    net.conv(255, 1, 1, 0, 1, 0, "none", "conv8", "head")
+    net.conv(255, 1, 1, 0, 1, 0, "none", "conv8", "head1")
+    net.conv(128, 1, 1, 0, 1, 1, "lrelu", "conv7", "conv9")     # route -4
+    net.upsample(2, "conv9", "up")
+    net.concat(["up", "conv4"], "route")                         # route -1, 8
+    net.conv(256, 3, 1, 1, 1, 1, "lrelu", "route", "conv10")
+    net.conv(255, 1, 1, 0, 1, 0, "none", "conv10", "head")
     if net.mode != capi.MODE_PREDICT:
         net.cost("head", "cost", metric=capi.METRIC_SSE)
         net.sgd(0.001, 0.9, 0.0005)

@@ -259,6 +259,89 @@ eltwise_bwd_kernel(const float *__restrict__ y, float *__restrict__ dy, float *_
     }
 }
 
+
+// ---- concat / upsample (YOLO second head glue) ---------------------------
+// Channel concatenation is a strided block copy: image j of a source ([block] = C_src * H * W
+// floats) lands at dst + j * dst_pitch + offset. The backward pass adds (or, for the first writer
+// of the step, stores) the matching slice of the output gradient.
+__global__ void __launch_bounds__(256)
+block_copy_kernel(const float *__restrict__ in, float *__restrict__ out, uint32_t total4, uint32_t block4,
+                  size_t in_pitch, size_t out_pitch, bool accumulate, FastDiv d_block4) {
+    const uint32_t gstride = gridDim.x * 256u;
+    for (uint32_t i = blockIdx.x * 256u + threadIdx.x; i < total4; i += gstride) {
+        uint32_t j, r;
+        d_block4.divmod(i, j, r);
+        const float4 v = __ldg(reinterpret_cast<const float4 *>(in + (size_t)j * in_pitch) + r);
+        float4 *dst = reinterpret_cast<float4 *>(out + (size_t)j * out_pitch) + r;
+        if (accumulate) {
+            const float4 o = *dst;
+            *dst = make_float4(o.x + v.x, o.y + v.y, o.z + v.z, o.w + v.w);
+        } else {
+            *dst = v;
+        }
+    }
+}
+__global__ void __launch_bounds__(256)
+block_copy_scalar_kernel(const float *__restrict__ in, float *__restrict__ out, size_t total, uint32_t block,
+                         size_t in_pitch, size_t out_pitch, bool accumulate, FastDiv d_block) {
+    const size_t gstride = (size_t)gridDim.x * 256;
+    for (size_t i = (size_t)blockIdx.x * 256 + threadIdx.x; i < total; i += gstride) {
+        uint32_t j, r;
+        d_block.divmod((uint32_t)i, j, r);
+        const float v = __ldg(in + (size_t)j * in_pitch + r);
+        float *dst = out + (size_t)j * out_pitch + r;
+        *dst = accumulate ? *dst + v : v;
+    }
+}
+
+int launch_block_copy(const float *in, float *out, int n, int block, size_t in_pitch, size_t out_pitch,
+                      bool accumulate, cudaStream_t st) {
+    if (n <= 0 || block <= 0) return 0;
+    const size_t total = (size_t)n * block;
+    if (total >= (1ull << 32)) return (int)cudaErrorInvalidValue;
+    const bool vec = (block & 3) == 0 && (in_pitch & 3) == 0 && (out_pitch & 3) == 0 && aligned16(in) &&
+                     aligned16(out);
+    if (vec)
+        block_copy_kernel<<<stream_grid(total / 4, 256), 256, 0, st>>>(
+            in, out, (uint32_t)(total / 4), (uint32_t)(block / 4), in_pitch, out_pitch, accumulate,
+            FastDiv((uint32_t)(block / 4)));
+    else
+        block_copy_scalar_kernel<<<stream_grid(total, 256), 256, 0, st>>>(
+            in, out, total, (uint32_t)block, in_pitch, out_pitch, accumulate, FastDiv((uint32_t)block));
+    return launched();
+}
+
+// Nearest-neighbour upsampling by an integer factor: one thread per OUTPUT element forward (rows
+// of the output are contiguous), one thread per INPUT element backward, which sums its size x size
+// block of the output gradient in the reference's raster order on top of the existing value.
+__global__ void __launch_bounds__(256)
+upsample_fwd_kernel(const float *__restrict__ x, float *__restrict__ y, size_t total, int h, int w,
+                    FastDiv d_wo, FastDiv d_ho, FastDiv d_size) {
+    const size_t gstride = (size_t)gridDim.x * 256;
+    for (size_t o = (size_t)blockIdx.x * 256 + threadIdx.x; o < total; o += gstride) {
+        uint32_t t, i, plane, j;
+        d_wo.divmod((uint32_t)o, t, i);
+        d_ho.divmod(t, plane, j);
+        y[o] = __ldg(x + ((size_t)plane * h + d_size.div(j)) * w + d_size.div(i));
+    }
+}
+__global__ void __launch_bounds__(256)
+upsample_bwd_kernel(const float *__restrict__ dy, float *__restrict__ dx, size_t total, int h, int w,
+                    int size, bool accumulate, FastDiv d_w, FastDiv d_h) {
+    const size_t gstride = (size_t)gridDim.x * 256;
+    const int wo = w * size;
+    for (size_t e = (size_t)blockIdx.x * 256 + threadIdx.x; e < total; e += gstride) {
+        uint32_t t, iw, plane, ih;
+        d_w.divmod((uint32_t)e, t, iw);
+        d_h.divmod(t, plane, ih);
+        const float *g = dy + ((size_t)plane * h * size + (size_t)ih * size) * wo + (size_t)iw * size;
+        float acc = accumulate ? dx[e] : 0.f;
+        for (int a = 0; a < size; ++a)
+            for (int b = 0; b < size; ++b) acc += __ldg(g + (size_t)a * wo + b);
+        dx[e] = acc;
+    }
+}
+
 }  // namespace
 
 extern "C" int bcnn_b200_activation_forward(float *x, int sz, int act, const float *slope, int hw,
@@ -347,5 +430,38 @@ extern "C" int bcnn_b200_eltwise_backward(const float *y, float *dy, float *da, 
     eltwise_bwd_kernel<<<stream_grid(vec ? sz / 4 + 1 : sz, 256), 256, 0, as_stream(stream)>>>(
         y, dy, da, db, (size_t)sz, (size_t)n_add, act, vec, (accumulate_flags & 1) != 0,
         (accumulate_flags & 2) != 0, getenv("BCNN_B200_NO_REVERSE") == nullptr);
+    return launched();
+}
+
+extern "C" int bcnn_b200_concat_forward(const float *src, float *dst, int n, int src_sz, int dst_sz,
+                                        int dst_offset, void *stream) {
+    return launch_block_copy(src, dst + dst_offset, n, src_sz, (size_t)src_sz, (size_t)dst_sz, false,
+                             as_stream(stream));
+}
+
+extern "C" int bcnn_b200_concat_backward(const float *dst_grad, float *src_grad, int n, int src_sz,
+                                         int dst_sz, int dst_offset, int accumulate, void *stream) {
+    return launch_block_copy(dst_grad + dst_offset, src_grad, n, src_sz, (size_t)dst_sz, (size_t)src_sz,
+                             accumulate != 0, as_stream(stream));
+}
+
+extern "C" int bcnn_b200_upsample_forward(const float *x, float *y, int n, int c, int h, int w, int size,
+                                          void *stream) {
+    const size_t total = (size_t)n * c * h * w * size * size;
+    if (total == 0) return 0;
+    if (size < 1 || total >= (1ull << 32)) return (int)cudaErrorInvalidValue;
+    upsample_fwd_kernel<<<stream_grid(total, 256), 256, 0, as_stream(stream)>>>(
+        x, y, total, h, w, FastDiv((uint32_t)(w * size)), FastDiv((uint32_t)(h * size)),
+        FastDiv((uint32_t)size));
+    return launched();
+}
+
+extern "C" int bcnn_b200_upsample_backward(const float *dy, float *dx, int n, int c, int h, int w,
+                                           int size, int accumulate, void *stream) {
+    const size_t total = (size_t)n * c * h * w;
+    if (total == 0) return 0;
+    if (size < 1 || total * size * size >= (1ull << 32)) return (int)cudaErrorInvalidValue;
+    upsample_bwd_kernel<<<stream_grid(total, 256), 256, 0, as_stream(stream)>>>(
+        dy, dx, total, h, w, size, accumulate != 0, FastDiv((uint32_t)w), FastDiv((uint32_t)h));
     return launched();
 }

@@ -125,7 +125,10 @@ void bcnn_dp_after_node_backward(bcnn_net *net, bcnn_node *node) {
     int queued = 0;
     for (int i = 1; i < node->num_src; ++i) { /* src[0] is the activation input */
         bcnn_tensor *t = &net->tensors[node->src[i]];
-        if (node->type == BCNN_LAYER_COST || node->type == BCNN_LAYER_ELTWISE) break;
+        /* these nodes' further sources are activations, not parameters */
+        if (node->type == BCNN_LAYER_COST || node->type == BCNN_LAYER_ELTWISE ||
+            node->type == BCNN_LAYER_CONCAT)
+            break;
         if (!t->has_grad || !t->grad_data_gpu) continue;
         if (!queued) {
             bcnn_cuda_check(bcnn_b200_event_record(dp->evt_ready, bcnn_stream(net)));

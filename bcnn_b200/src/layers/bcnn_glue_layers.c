@@ -176,3 +176,117 @@ void bcnn_backward_eltwise_layer(bcnn_net *net, bcnn_node *node) {
         dst->data_gpu, dst->grad_data_gpu, t[node->src[0]].grad_data_gpu,
         t[node->src[1]].grad_data_gpu, sz, n_add, param->activation, flags, bcnn_stream(net)));
 }
+
+/* ------------------------------- concat ------------------------------- */
+/* src/layers/bcnn_concat_layer.c:34-142: channel concatenation of num_src tensors with equal
+ * spatial size; backward adds the output-gradient slices into the sources' gradients. */
+
+bcnn_status bcnn_add_concat_layer(bcnn_net *net, int num_src, char *const *src_ids,
+                                  const char *dst_id) {
+    bcnn_node node = {0};
+    BCNN_CHECK_AND_LOG(net->log_ctx, net->num_nodes >= 1, BCNN_INVALID_PARAMETER,
+                       "Concat layer can't be the first layer of the network\n");
+    BCNN_CHECK_AND_LOG(net->log_ctx, num_src >= 1, BCNN_INVALID_PARAMETER,
+                       "Concat layer: no input\n");
+    for (int i = 0; i < num_src; ++i) {
+        int tid = bcnn_get_tensor_index_by_name(net, src_ids[i]);
+        BCNN_CHECK_AND_LOG(net->log_ctx, tid >= 0, BCNN_INVALID_PARAMETER,
+                           "Concat layer: invalid input node name %s\n", src_ids[i]);
+        BCNN_CHECK_STATUS(bcnn_node_add_input(net, &node, tid));
+    }
+    const bcnn_tensor *first = &net->tensors[node.src[0]];
+    int out_c = first->c;
+    for (int i = 1; i < node.num_src; ++i) {
+        const bcnn_tensor *t = &net->tensors[node.src[i]];
+        BCNN_CHECK_AND_LOG(net->log_ctx, t->w == first->w && t->h == first->h && t->n == first->n,
+                           BCNN_INVALID_PARAMETER,
+                           "Concat layer: inconsistent sizes between node %s (%dx%d) and node %s "
+                           "(%dx%d)\n", src_ids[0], first->w, first->h, src_ids[i], t->w, t->h);
+        out_c += t->c;
+    }
+    const int n = first->n, h = first->h, w = first->w;
+    BCNN_CHECK_STATUS(bcnn_net_add_dst_tensor(net, &node, n, out_c, h, w, dst_id));
+    node.type = BCNN_LAYER_CONCAT;
+    node.forward = bcnn_forward_concat_layer;
+    node.backward = bcnn_backward_concat_layer;
+    BCNN_CHECK_STATUS(bcnn_net_add_node(net, node));
+    return BCNN_SUCCESS;
+}
+
+void bcnn_forward_concat_layer(bcnn_net *net, bcnn_node *node) {
+    bcnn_tensor *dst = &net->tensors[node->dst[0]];
+    const int dst_sz = dst->c * dst->h * dst->w;
+    int offset = 0;
+    for (int i = 0; i < node->num_src; ++i) {
+        bcnn_tensor *src = &net->tensors[node->src[i]];
+        const int src_sz = src->c * src->h * src->w;
+        bcnn_cuda_check(bcnn_b200_concat_forward(src->data_gpu, dst->data_gpu, src->n, src_sz, dst_sz,
+                                                 offset, bcnn_stream(net)));
+        offset += src_sz;
+    }
+}
+
+void bcnn_backward_concat_layer(bcnn_net *net, bcnn_node *node) {
+    bcnn_tensor *dst = &net->tensors[node->dst[0]];
+    const int dst_sz = dst->c * dst->h * dst->w;
+    int offset = 0;
+    for (int i = 0; i < node->num_src; ++i) {
+        bcnn_tensor *src = &net->tensors[node->src[i]];
+        const int src_sz = src->c * src->h * src->w;
+        if (src->grad_data_gpu)
+            bcnn_cuda_check(bcnn_b200_concat_backward(
+                dst->grad_data_gpu, src->grad_data_gpu, src->n, src_sz, dst_sz, offset,
+                bcnn_net_grad_accumulate(net, node->src[i]), bcnn_stream(net)));
+        offset += src_sz;
+    }
+}
+
+/* ------------------------------ upsample ------------------------------ */
+/* src/layers/bcnn_upsample_layer.c:33-142: nearest-neighbour upsampling by `size`. */
+
+static void bcnn_release_param_upsample_layer(bcnn_node *node) { (void)node; }
+
+bcnn_status bcnn_add_upsample_layer(bcnn_net *net, int size, const char *src_id,
+                                    const char *dst_id) {
+    bcnn_node node = {0};
+    BCNN_CHECK_AND_LOG(net->log_ctx, size >= 1, BCNN_INVALID_PARAMETER,
+                       "Upsample layer: invalid factor %d\n", size);
+    int src = 0;
+    if (net->num_nodes > 0) {
+        src = bcnn_get_tensor_index_by_name(net, src_id);
+        BCNN_CHECK_AND_LOG(net->log_ctx, src >= 0, BCNN_INVALID_PARAMETER,
+                           "Upsample layer: invalid input node name %s\n", src_id);
+    }
+    BCNN_CHECK_STATUS(bcnn_node_add_input(net, &node, src));
+    const bcnn_tensor *s = &net->tensors[src];
+    const int n = s->n, c = s->c, h = s->h, w = s->w;
+    BCNN_CHECK_STATUS(bcnn_net_add_dst_tensor(net, &node, n, c, h * size, w * size, dst_id));
+    node.type = BCNN_LAYER_UPSAMPLE;
+    node.param_size = sizeof(bcnn_upsample_param);
+    bcnn_upsample_param *param = (bcnn_upsample_param *)calloc(1, node.param_size);
+    BCNN_CHECK(param != NULL, BCNN_FAILED_ALLOC);
+    param->size = size;
+    node.param = param;
+    node.forward = bcnn_forward_upsample_layer;
+    node.backward = bcnn_backward_upsample_layer;
+    node.release_param = bcnn_release_param_upsample_layer;
+    BCNN_CHECK_STATUS(bcnn_net_add_node(net, node));
+    return BCNN_SUCCESS;
+}
+
+void bcnn_forward_upsample_layer(bcnn_net *net, bcnn_node *node) {
+    bcnn_upsample_param *param = (bcnn_upsample_param *)node->param;
+    bcnn_tensor *src = &net->tensors[node->src[0]], *dst = &net->tensors[node->dst[0]];
+    bcnn_cuda_check(bcnn_b200_upsample_forward(src->data_gpu, dst->data_gpu, src->n, src->c, src->h,
+                                               src->w, param->size, bcnn_stream(net)));
+}
+
+void bcnn_backward_upsample_layer(bcnn_net *net, bcnn_node *node) {
+    bcnn_upsample_param *param = (bcnn_upsample_param *)node->param;
+    bcnn_tensor *src = &net->tensors[node->src[0]], *dst = &net->tensors[node->dst[0]];
+    if (!src->grad_data_gpu) return;
+    bcnn_cuda_check(bcnn_b200_upsample_backward(dst->grad_data_gpu, src->grad_data_gpu, src->n, src->c,
+                                                src->h, src->w, param->size,
+                                                bcnn_net_grad_accumulate(net, node->src[0]),
+                                                bcnn_stream(net)));
+}

@@ -22,6 +22,14 @@ typedef struct bcnn_eltwise_param {
     int min_dim[3];
 } bcnn_eltwise_param;
 
+typedef struct bcnn_upsample_param {
+    int size;
+} bcnn_upsample_param;
+
+void bcnn_forward_concat_layer(bcnn_net *net, bcnn_node *node);
+void bcnn_backward_concat_layer(bcnn_net *net, bcnn_node *node);
+void bcnn_forward_upsample_layer(bcnn_net *net, bcnn_node *node);
+void bcnn_backward_upsample_layer(bcnn_net *net, bcnn_node *node);
 void bcnn_forward_softmax_layer(bcnn_net *net, bcnn_node *node);
 void bcnn_backward_softmax_layer(bcnn_net *net, bcnn_node *node);
 void bcnn_forward_cost_layer(bcnn_net *net, bcnn_node *node);

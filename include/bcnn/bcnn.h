@@ -175,6 +175,12 @@ BCNN_API bcnn_status bcnn_add_softmax_layer(bcnn_net *net, const char *src_id,
 BCNN_API bcnn_status bcnn_add_eltwise_layer(bcnn_net *net, bcnn_activation activation,
                                             const char *src_id1, const char *src_id2,
                                             const char *dst_id);
+/* Concatenation along the channel axis (reference inc/bcnn/bcnn.h:956) and nearest upsampling
+ * by an integer factor (:999): the glue of YOLOv3-tiny's second head. */
+BCNN_API bcnn_status bcnn_add_concat_layer(bcnn_net *net, int num_src, char *const *src_ids,
+                                           const char *dst_id);
+BCNN_API bcnn_status bcnn_add_upsample_layer(bcnn_net *net, int size, const char *src_id,
+                                             const char *dst_id);
 BCNN_API bcnn_status bcnn_add_cost_layer(bcnn_net *net, bcnn_loss loss,
                                          bcnn_loss_metric loss_metric, float scale,
                                          const char *src_id, const char *label_id,

@@ -306,6 +306,27 @@ BCNN_B200_API int bcnn_b200_eltwise_backward(const float *y, float *dy, float *d
                                              float *db, int sz, int n_add, int act,
                                              int accumulate_flags, void *stream);
 
+/* ---- concat / upsample (the second YOLO head's glue) ---------------------- */
+/* Channel concatenation of one source into the output: image j (src_sz = C_src*H*W floats)
+ * goes to dst + j * dst_sz + dst_offset.  replaces the bcnn_cuda_copy_f32 loop of
+ * bcnn_forward_concat_layer_gpu, src/layers/bcnn_concat_layer.c:146-160 (CPU :107-121). */
+BCNN_B200_API int bcnn_b200_concat_forward(const float *src, float *dst, int n, int src_sz,
+                                           int dst_sz, int dst_offset, void *stream);
+/* src_grad (+)= the matching slice of dst_grad (bcnn_axpy loop, :123-142); accumulate == 0
+ * stores instead (first backward writer of the step). */
+BCNN_B200_API int bcnn_b200_concat_backward(const float *dst_grad, float *src_grad, int n,
+                                            int src_sz, int dst_sz, int dst_offset,
+                                            int accumulate, void *stream);
+/* y[n, c, j, i] = x[n, c, j / size, i / size]   (src/layers/bcnn_upsample_layer.c:86-109;
+ * replaces bcnn_cuda_upsample_kernel, bcnn_upsample_layer.cu). */
+BCNN_B200_API int bcnn_b200_upsample_forward(const float *x, float *y, int n, int c, int h,
+                                             int w, int size, void *stream);
+/* dx[n, c, y, x] (+)= sum of the size x size block of dy, summed in the raster order of
+ * bcnn_backward_upsample_layer_cpu (:119-142). */
+BCNN_B200_API int bcnn_b200_upsample_backward(const float *dy, float *dx, int n, int c, int h,
+                                              int w, int size, int accumulate, void *stream);
+
+
 #ifdef __cplusplus
 }
 #endif

@@ -641,3 +641,49 @@ void orc_softmax_forward(const float *x, float *y, int n, int c, int hw) {
 void orc_eltwise_add(const float *a, const float *b, float *y, int sz) {
     for (int i = 0; i < sz; ++i) y[i] = a[i] + b[i];
 }
+
+/* ------------------------------------------------------------------ */
+/* Concat / upsample (YOLO second head glue)                            */
+/* ------------------------------------------------------------------ */
+
+/* bcnn_forward_concat_layer_cpu, src/layers/bcnn_concat_layer.c:107-121: image j of the source
+ * (src_sz floats) is copied to dst + dst_offset + j * dst_sz. */
+void orc_concat_forward(const float *src, float *dst, int n, int src_sz, int dst_sz, int dst_offset) {
+    for (int j = 0; j < n; ++j)
+        for (int i = 0; i < src_sz; ++i)
+            dst[(size_t)dst_offset + (size_t)j * dst_sz + i] = src[(size_t)j * src_sz + i];
+}
+
+/* bcnn_backward_concat_layer_cpu, :123-142: src_grad += slice of dst_grad (bcnn_axpy, alpha 1). */
+void orc_concat_backward(const float *dst_grad, float *src_grad, int n, int src_sz, int dst_sz,
+                         int dst_offset) {
+    for (int j = 0; j < n; ++j)
+        for (int i = 0; i < src_sz; ++i)
+            src_grad[(size_t)j * src_sz + i] += dst_grad[(size_t)dst_offset + (size_t)j * dst_sz + i];
+}
+
+/* bcnn_forward_upsample_layer_cpu, src/layers/bcnn_upsample_layer.c:86-109. */
+void orc_upsample_forward(const float *x, float *y, int n, int c, int h, int w, int size) {
+    for (int b = 0; b < n; ++b)
+        for (int k = 0; k < c; ++k)
+            for (int j = 0; j < h * size; ++j)
+                for (int i = 0; i < w * size; ++i) {
+                    size_t src_id = (size_t)b * w * h * c + (size_t)k * w * h + (size_t)(j / size) * w + i / size;
+                    size_t dst_id = (size_t)b * w * h * c * size * size + (size_t)k * w * h * size * size +
+                                    (size_t)j * w * size + i;
+                    y[dst_id] = x[src_id];
+                }
+}
+
+/* bcnn_backward_upsample_layer_cpu, :119-142: the same walk, dx[src] += dy[dst] one at a time. */
+void orc_upsample_backward(const float *dy, float *dx, int n, int c, int h, int w, int size) {
+    for (int b = 0; b < n; ++b)
+        for (int k = 0; k < c; ++k)
+            for (int j = 0; j < h * size; ++j)
+                for (int i = 0; i < w * size; ++i) {
+                    size_t src_id = (size_t)b * w * h * c + (size_t)k * w * h + (size_t)(j / size) * w + i / size;
+                    size_t dst_id = (size_t)b * w * h * c * size * size + (size_t)k * w * h * size * size +
+                                    (size_t)j * w * size + i;
+                    dx[src_id] += dy[dst_id];
+                }
+}

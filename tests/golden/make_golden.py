@@ -2,7 +2,7 @@
 (oracle/_ref/libbcnn_ref.so, built from /root/reference by oracle/Makefile) through its own
 public API on the seeded synthetic cases of tests/netcases.py.
 
-    python tests/golden/make_golden.py
+    python tests/golden/make_golden.py [case ...]     (default: every case of netcases.CASES)
 
 The reference ships no golden vectors of its own, so these files are
 the pin: they record what the reference computes, never hand-edited. Large tensors are
@@ -21,7 +21,7 @@ import netcases  # noqa: E402
 from helpers import GOLDEN, ref_net  # noqa: E402
 
 SUB = 4096
-FULL_CASES = {"chain_b4", "resnet_small_b4"}  # small enough to keep every tensor whole
+FULL_CASES = {"chain_b4", "resnet_small_b4", "yolo_two_heads_b2"}  # small enough to keep every tensor whole
 
 
 def subsample(a: np.ndarray) -> np.ndarray:
@@ -35,7 +35,7 @@ def subsample(a: np.ndarray) -> np.ndarray:
 def main():
     from bcnn_b200 import configs
     from helpers import rel_err
-    for name in netcases.CASES:
+    for name in (sys.argv[1:] or netcases.CASES):
         net = ref_net(threads=1)
         out = netcases.run_case(net, name)
         net.close()

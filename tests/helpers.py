@@ -77,6 +77,10 @@ def oracle() -> C.CDLL:
         "orc_fc_backward": (None, [vp, vp, vp, vp, vp, vp, i, i, i]),
         "orc_softmax_forward": (None, [vp, vp, i, i, i]),
         "orc_eltwise_add": (None, [vp, vp, vp, i]),
+        "orc_concat_forward": (None, [vp, vp, i, i, i, i]),
+        "orc_concat_backward": (None, [vp, vp, i, i, i, i]),
+        "orc_upsample_forward": (None, [vp, vp, i, i, i, i, i]),
+        "orc_upsample_backward": (None, [vp, vp, i, i, i, i, i]),
     }
     for name, (res, args) in sigs.items():
         fn = getattr(lib, name)

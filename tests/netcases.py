@@ -36,12 +36,36 @@ def chain_convnet(net, batch=4):
     return dict(classes=10, out="softmax")
 
 
+def yolo_two_heads(net, batch=2):
+    """YOLOv3-tiny's head topology at oracle-friendly size (examples/yolo/yolov3-tiny.cfg): a
+    trunk of conv+BN+leaky / max-pool stages, a coarse head, and a second head fed by a 1x1
+    conv -> upsample x2 -> concat with an earlier trunk tensor. The yolo loss itself stays out of
+    scope: the fine head carries the euclidean cost, and the coarse branch
+    reaches it through the upsample / concat route, so both glue layers see gradients."""
+    net.set_input_shape(32, 32, 3, batch)
+    net.conv(8, 3, 1, 1, 1, 1, "lrelu", "input", "c0")
+    net.maxpool(2, 2, capi.PAD_SAME, "c0", "p0")          # 16x16
+    net.conv(16, 3, 1, 1, 1, 1, "lrelu", "p0", "c1")      # route source (16 ch @16)
+    net.maxpool(2, 2, capi.PAD_SAME, "c1", "p1")          # 8x8
+    net.conv(32, 3, 1, 1, 1, 1, "lrelu", "p1", "c2")
+    net.conv(16, 1, 1, 0, 1, 1, "lrelu", "c2", "c3")      # trunk end @8
+    net.conv(8, 1, 1, 0, 1, 1, "lrelu", "c3", "r0")       # second head: 1x1 reduce
+    net.upsample(2, "r0", "up")                           # 16x16
+    net.concat(["up", "c1"], "cat")                       # 8 + 16 channels
+    net.conv(24, 3, 1, 1, 1, 1, "lrelu", "cat", "c4")
+    net.conv(18, 1, 1, 0, 1, 0, "none", "c4", "head")
+    net.cost("head", "cost", metric=capi.METRIC_SSE)
+    net.sgd(0.001, 0.9, 0.0005)
+    return dict(classes=None, out="head")
+
+
 CASES = {
     # name: (builder, kwargs, steps)
     "mnist_b8": (configs.mnist, dict(batch=8), 3),
     "cifar_b4": (configs.cifar, dict(batch=4), 3),
     "chain_b4": (chain_convnet, dict(batch=4), 2),
     "resnet_small_b4": (small_resnet, dict(batch=4), 2),
+    "yolo_two_heads_b2": (yolo_two_heads, dict(batch=2), 2),
 }
 
 

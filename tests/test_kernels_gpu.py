@@ -500,6 +500,55 @@ def test_conv_forward_bn_stats_matches_separate_kernels(case, math):
     assert_close(rvar.download(np.float32, (cout,)), f32(0.9 * run0[1] + 0.1 * got_v), 1e-6, "run var")
 
 
+# ------------------------------------------------------------------ concat / upsample
+@pytest.mark.parametrize("n,c1,c2,h,w", [(3, 5, 4, 10, 10), (2, 3, 7, 13, 13), (1, 256, 128, 26, 26)])
+def test_concat_bit_exact(n, c1, c2, h, w):
+    lib, orc = capi.b200(), oracle()
+    r = rng(n + c1 + h)
+    a, b = f32(r.uniform(-1, 1, size=(n, c1, h, w))), f32(r.uniform(-1, 1, size=(n, c2, h, w)))
+    sa, sb, sd = c1 * h * w, c2 * h * w, (c1 + c2) * h * w
+    want = np.zeros((n, c1 + c2, h, w), np.float32)
+    orc.orc_concat_forward(p(a), p(want), n, sa, sd, 0)
+    orc.orc_concat_forward(p(b), p(want), n, sb, sd, sa)
+    da, db, dd = dev(a), dev(b), dev_zeros(want.size)
+    check(lib.bcnn_b200_concat_forward(da.ptr, dd.ptr, n, sa, sd, 0, None))
+    check(lib.bcnn_b200_concat_forward(db.ptr, dd.ptr, n, sb, sd, sa, None))
+    assert np.array_equal(dd.download(np.float32, want.shape), want)
+    assert np.array_equal(want, np.concatenate([a, b], axis=1))
+    g = f32(r.uniform(-1, 1, size=want.shape))
+    g0 = f32(r.uniform(-1, 1, size=b.shape))
+    ref_acc, ref_new = g0.copy(), np.zeros_like(b)
+    orc.orc_concat_backward(p(g), p(ref_acc), n, sb, sd, sa)
+    orc.orc_concat_backward(p(g), p(ref_new), n, sb, sd, sa)
+    dg, dgb = dev(g), dev(g0)
+    check(lib.bcnn_b200_concat_backward(dg.ptr, dgb.ptr, n, sb, sd, sa, 1, None))
+    assert np.array_equal(dgb.download(np.float32, b.shape), ref_acc)
+    check(lib.bcnn_b200_concat_backward(dg.ptr, dgb.ptr, n, sb, sd, sa, 0, None))
+    assert np.array_equal(dgb.download(np.float32, b.shape), ref_new)
+
+
+@pytest.mark.parametrize("n,c,h,w,size", [(3, 5, 5, 5, 2), (2, 4, 7, 9, 3), (1, 128, 13, 13, 2), (2, 3, 6, 6, 1)])
+def test_upsample_bit_exact(n, c, h, w, size):
+    lib, orc = capi.b200(), oracle()
+    r = rng(n * 7 + c + size)
+    x = f32(r.uniform(-1, 1, size=(n, c, h, w)))
+    want = np.zeros((n, c, h * size, w * size), np.float32)
+    orc.orc_upsample_forward(p(x), p(want), n, c, h, w, size)
+    dx, dy = dev(x), dev_zeros(want.size)
+    check(lib.bcnn_b200_upsample_forward(dx.ptr, dy.ptr, n, c, h, w, size, None))
+    assert np.array_equal(dy.download(np.float32, want.shape), want)
+    g = f32(r.uniform(-1, 1, size=want.shape))
+    g0 = f32(r.uniform(-1, 1, size=x.shape))
+    ref_acc, ref_new = g0.copy(), np.zeros_like(x)
+    orc.orc_upsample_backward(p(g), p(ref_acc), n, c, h, w, size)
+    orc.orc_upsample_backward(p(g), p(ref_new), n, c, h, w, size)
+    dg, dgx = dev(g), dev(g0)
+    check(lib.bcnn_b200_upsample_backward(dg.ptr, dgx.ptr, n, c, h, w, size, 1, None))
+    assert np.array_equal(dgx.download(np.float32, x.shape), ref_acc)   # same summation order
+    check(lib.bcnn_b200_upsample_backward(dg.ptr, dgx.ptr, n, c, h, w, size, 0, None))
+    assert np.array_equal(dgx.download(np.float32, x.shape), ref_new)
+
+
 # ------------------------------------------------------------------ depthwise
 @pytest.mark.parametrize("n,c,h,w,k,s,pad", [(2, 32, 28, 28, 3, 1, 1), (2, 16, 28, 28, 3, 2, 1),
                                              (1, 7, 9, 11, 3, 1, 0), (2, 4, 12, 12, 5, 1, 2),

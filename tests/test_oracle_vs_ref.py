@@ -217,6 +217,41 @@ def test_avgpool_depthwise_fc_softmax():
     net.close()
 
 
+def test_concat_upsample_bit_exact():
+    """YOLO second-head glue: upsample x2 and channel concat, forward and backward."""
+    orc = oracle()
+
+    def build(m):
+        m.conv(5, 3, 2, 1, 1, 0, "lrelu", "pre", "small")      # 10x10 -> 5x5
+        m.upsample(2, "small", "up")                             # back to 10x10
+        m.concat(["up", "pre"], "out")                           # 5 + 4 channels
+    net = _single_layer(build, (10, 10, 4, 3), seed=21)
+    pre, small, up, out = (net.get(k) for k in ("pre", "small", "up", "out"))
+    mine = np.zeros_like(up)
+    orc.orc_upsample_forward(p(small), p(mine), 3, 5, 5, 5, 2)
+    assert np.array_equal(mine, up)
+    cat = np.zeros_like(out)
+    orc.orc_concat_forward(p(up), p(cat), 3, 5 * 100, 9 * 100, 0)
+    orc.orc_concat_forward(p(pre), p(cat), 3, 4 * 100, 9 * 100, 5 * 100)
+    assert np.array_equal(cat, out)
+    dy = f32(rng(6).uniform(-1, 1, size=out.shape))
+    net.set("out", dy, grad=True)
+    # run only the two glue nodes backward: their source gradients start from zero
+    net.set("up", np.zeros_like(up), grad=True)
+    net.set("pre", np.zeros_like(pre), grad=True)
+    net.set("small", np.zeros_like(small), grad=True)
+    net.backward()
+    g_up = np.zeros_like(up)
+    orc.orc_concat_backward(p(dy), p(g_up), 3, 5 * 100, 9 * 100, 0)
+    assert np.array_equal(g_up, net.get("up", grad=True))
+    g_small = np.zeros_like(small)
+    orc.orc_upsample_backward(p(g_up), p(g_small), 3, 5, 5, 5, 2)
+    # small.grad is then run through the conv's leaky-ReLU backward in place by the reference
+    fac = np.where(small > 0, 1.0, 0.1).astype(np.float32)
+    assert_close(g_small * fac, net.get("small", grad=True), 1e-6, "upsample bwd (+ lrelu')")
+    net.close()
+
+
 def test_sgd_update_bit_exact():
     lib, orc = ref_lib(), oracle()
     lib.bcnn_sgd_update_cpu.argtypes = [C.c_void_p] * 4 + [C.c_int] * 3 + [C.c_float] * 3

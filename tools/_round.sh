@@ -1,6 +1,3 @@
-mkdir -p gpurun_out/r1t
-nvidia-smi -L | head -4
-for N in 2 4; do
-BCNN_B200_BENCH_WATCHDOG_S=200 timeout 260 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 2951$N bench.py --gpus $N --steps 10 --warmup 3 > gpurun_out/r1t/bench_n$N.json 2> gpurun_out/r1t/bench_n$N.err
-echo "N=$N rc=$?"; head -c 330 gpurun_out/r1t/bench_n$N.json; echo
-done
+mkdir -p gpurun_out/r1u
+timeout 300 python -m pytest tests -m gpu -x -q > gpurun_out/r1u/gpu_tests.log 2>&1; tail -6 gpurun_out/r1u/gpu_tests.log
+timeout 200 python bench.py --workload yolo_tiny --batch 8 --res 416 --no-rooflines --no-cpu-baseline > gpurun_out/r1u/bench_yolo.json 2>> gpurun_out/r1u/bench.err; cut -c1-200 gpurun_out/r1u/bench_yolo.json; tail -3 gpurun_out/r1u/bench.err
