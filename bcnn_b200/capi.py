@@ -91,6 +91,11 @@ def bind_bcnn_api(lib: C.CDLL, tensor_type) -> None:
         "bcnn_add_concat_layer": (i, [vp, i, C.POINTER(C.c_char_p), s]),
         "bcnn_add_upsample_layer": (i, [vp, i, s, s]),
         "bcnn_add_cost_layer": (i, [vp, i, i, f, s, s, s]),
+        "bcnn_set_adam_optimizer": (None, [vp, f, f, f]),
+        "bcnn_load_weights": (i, [vp, s]),
+        "bcnn_save_weights": (i, [vp, s]),
+        # internal but exported by both libraries (reference src/bcnn_net.h:75)
+        "bcnn_net_set_param": (None, [vp, s, s]),
     }
     for name, (res, args) in sigs.items():
         fn = getattr(lib, name)
@@ -257,6 +262,26 @@ class Net:
     def sgd(self, lr, momentum, decay=0.0):
         self.lib.bcnn_set_sgd_optimizer(self.handle, lr, momentum)
         self.lib.bcnn_set_weight_regularizer(self.handle, decay)
+
+    def set_param(self, name: str, value) -> None:
+        """A solver key as the cfg reader sets it (optimizer=adam, beta1=..., decay=...)."""
+        self.lib.bcnn_net_set_param(self.handle, _b(name), _b(str(value)))
+
+    def adam(self, lr, beta1=0.9, beta2=0.999, decay=0.0):
+        """Adam the only way the reference reaches it: the setter for the rates,
+        the cfg key for the switch. Call before adding layers on the reference (it allocates the
+        moments at layer creation)."""
+        self.lib.bcnn_set_adam_optimizer(self.handle, lr, beta1, beta2)
+        self.lib.bcnn_set_weight_regularizer(self.handle, decay)
+        self.set_param("optimizer", "adam")
+
+    def save_weights(self, path) -> None:
+        self._check(self.lib.bcnn_save_weights(self.handle, _b(str(path))), "bcnn_save_weights")
+
+    def load_weights(self, path) -> int:
+        """Returns the bcnn_status (0 = BCNN_SUCCESS); does not raise, so tests can probe the
+        error paths."""
+        return int(self.lib.bcnn_load_weights(self.handle, _b(str(path))))
 
     def compile(self):
         self._check(self.lib.bcnn_compile_net(self.handle), "bcnn_compile_net")

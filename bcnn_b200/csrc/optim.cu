@@ -1,9 +1,11 @@
-// optim.cu -- fused SGD-momentum update, softmax and euclidean cost for sm_100a.
+// optim.cu -- fused SGD-momentum and Adam updates, softmax and euclidean cost for sm_100a.
 //
 // SGD: the reference spends five BLAS-1 launches per parameter tensor
 // (bcnn_sgd_update_gpu, src/bcnn_learner.c:86-103: axpy, scal, axpy, axpy, scal);
 // here it is one read-modify-write pass over (w, g): 16 B/element instead of 40.
 // Momentum stays in the gradient buffer exactly as in the reference.
+// Adam: nine BLAS-1 passes over (w, g, m, v) in bcnn_adam_update_cpu / _gpu
+// (src/bcnn_learner.c:106-164) become one pass: 32 B/element instead of 96.
 #include <float.h>
 
 #include "common.cuh"
@@ -45,6 +47,57 @@ sgd_kernel(float *__restrict__ w, float *__restrict__ g, size_t n, float wd_scal
         w[j] = __fadd_rn(w[j], __fmul_rn(step, gv));
         g[j] = gv * g_scale;
     }
+}
+
+// One Adam step for one element, in the operation order and with the roundings of
+// bcnn_adam_update_cpu (src/bcnn_learner.c:118-129): axpy, axpby, vmul, axpby, pow(.,0.5),
+// add_scalar(1e-7), vdiv, axpy, zero-fill. sqrt stands for powf(v, 0.5f) (correctly rounded
+// here; glibc's powf is within 0.82 ulp of it). `guard`: the elements bcnn_vdiv handles in its
+// scalar tail (n % 8, src/kernels/bcnn_mat.c:277-310 with AVX) get 0 instead of a quotient
+// when the denominator is <= 1e-5; the vector body divides unconditionally.
+__device__ __forceinline__ void adam_element(float &w, float &g, float &m, float &v, float wd_scale,
+                                             float one_minus_b1, float b1, float one_minus_b2,
+                                             float b2, float alpha, bool guard) {
+    g = __fadd_rn(g, __fmul_rn(wd_scale, w));
+    m = __fadd_rn(__fmul_rn(g, one_minus_b1), __fmul_rn(m, b1));
+    const float g2 = __fmul_rn(g, g);
+    v = __fadd_rn(__fmul_rn(g2, one_minus_b2), __fmul_rn(v, b2));
+    const float den = __fadd_rn(__fsqrt_rn(v), 0.0000001f);
+    const float q = (guard && !(fabsf(den) > 0.00001f)) ? 0.0f : __fdiv_rn(m, den);
+    w = __fadd_rn(w, __fmul_rn(alpha, q));
+    g = 0.0f;
+}
+
+__global__ void __launch_bounds__(256)
+adam_kernel(float *__restrict__ w, float *__restrict__ g, float *__restrict__ m,
+            float *__restrict__ v, size_t n, float wd_scale, float one_minus_b1, float b1,
+            float one_minus_b2, float b2, float alpha, bool vec) {
+    const size_t gstride = (size_t)gridDim.x * blockDim.x;
+    const size_t tid = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const size_t tail = n & ~(size_t)7;  // first element of bcnn_vdiv's scalar tail
+    size_t done = 0;
+    if (vec) {
+        const size_t n4 = n >> 2;
+        for (size_t j = tid; j < n4; j += gstride) {
+            float4 wv = reinterpret_cast<float4 *>(w)[j];
+            float4 gv = reinterpret_cast<float4 *>(g)[j];
+            float4 mv = reinterpret_cast<float4 *>(m)[j];
+            float4 vv = reinterpret_cast<float4 *>(v)[j];
+            const bool guard = (j << 2) >= tail;  // tail is a multiple of 4: whole vector or none
+            adam_element(wv.x, gv.x, mv.x, vv.x, wd_scale, one_minus_b1, b1, one_minus_b2, b2, alpha, guard);
+            adam_element(wv.y, gv.y, mv.y, vv.y, wd_scale, one_minus_b1, b1, one_minus_b2, b2, alpha, guard);
+            adam_element(wv.z, gv.z, mv.z, vv.z, wd_scale, one_minus_b1, b1, one_minus_b2, b2, alpha, guard);
+            adam_element(wv.w, gv.w, mv.w, vv.w, wd_scale, one_minus_b1, b1, one_minus_b2, b2, alpha, guard);
+            reinterpret_cast<float4 *>(w)[j] = wv;
+            reinterpret_cast<float4 *>(g)[j] = gv;
+            reinterpret_cast<float4 *>(m)[j] = mv;
+            reinterpret_cast<float4 *>(v)[j] = vv;
+        }
+        done = n4 << 2;
+    }
+    for (size_t j = done + tid; j < n; j += gstride)
+        adam_element(w[j], g[j], m[j], v[j], wd_scale, one_minus_b1, b1, one_minus_b2, b2, alpha,
+                     j >= tail);
 }
 
 // One warp per (sample, spatial position): softmax over channels in the
@@ -130,6 +183,16 @@ extern "C" int bcnn_b200_sgd_update(float *w, float *g, size_t n, float wd_scale
     bool vec = aligned16(w) && aligned16(g);
     sgd_kernel<<<stream_grid(vec ? n / 4 + 1 : n, 256), 256, 0, as_stream(stream)>>>(
         w, g, n, wd_scale, step, g_scale, vec);
+    return launched();
+}
+
+extern "C" int bcnn_b200_adam_update(float *w, float *g, float *m, float *v, size_t n,
+                                     float wd_scale, float beta1, float beta2, float alpha,
+                                     void *stream) {
+    if (n == 0) return 0;
+    bool vec = aligned16(w) && aligned16(g) && aligned16(m) && aligned16(v);
+    adam_kernel<<<stream_grid(vec ? n / 4 + 1 : n, 256), 256, 0, as_stream(stream)>>>(
+        w, g, m, v, n, wd_scale, 1.0f - beta1, beta1, 1.0f - beta2, beta2, alpha, vec);
     return launched();
 }
 

@@ -1,9 +1,11 @@
 /*
  * bcnn_learner.c -- learning-rate schedules, optimizer setters and the update loop.
  * Behaviour of jnbraun/bcnn src/bcnn_learner.c:29-65 (schedules), :67-103 (SGD with the
- * momentum kept in the gradient buffer), :167-225 (bcnn_update and the setters, including
- * the quirk that bcnn_set_adam_optimizer never switches `optimizer`).
- * The five BLAS-1 launches of bcnn_sgd_update_gpu are one fused kernel per tensor here.
+ * momentum kept in the gradient buffer), :106-164 (Adam), :167-225 (bcnn_update and the
+ * setters, including the quirk that bcnn_set_adam_optimizer never switches `optimizer`,
+ * Adam is reached through bcnn_net_set_param("optimizer", "adam") only).
+ * The five BLAS-1 launches of bcnn_sgd_update_gpu and the nine of bcnn_adam_update_gpu are
+ * one fused kernel per tensor here.
  */
 #include "bcnn_learner.h"
 
@@ -56,6 +58,62 @@ void bcnn_sgd_update_gpu(bcnn_net *net, float *weights, float *biases, float *we
                                              decay * batch_size, step, g_scale, stream));
 }
 
+/* Host side of bcnn_adam_update_gpu (reference :134-164). The bias branch is the SGD bias
+ * branch (axpy + scal by `momentum`); the weight branch is one fused kernel. `iter` is what the
+ * layers pass: learner->seen, i.e. samples, not steps. */
+void bcnn_adam_update_gpu(bcnn_net *net, float *weights, float *biases, float *weights_grad,
+                          float *biases_grad, float *adam_m, float *adam_v, int weights_size,
+                          int biases_size, int batch_size, int iter, float beta1, float beta2,
+                          float learning_rate, float momentum, float decay) {
+    const float mu_correction = sqrtf(1.0f - powf(beta2, (float)iter + 1)) /
+                                (1.0f - powf(beta1, (float)iter + 1));
+    if (biases && biases_grad)
+        bcnn_sgd_update_gpu(net, NULL, biases, NULL, biases_grad, 0, biases_size, batch_size,
+                            learning_rate, momentum, 0.0f);
+    if (weights && weights_grad && adam_m && adam_v) {
+        const float alpha = -learning_rate / batch_size * mu_correction;
+        bcnn_cuda_check(bcnn_b200_adam_update(weights, weights_grad, adam_m, adam_v,
+                                              (size_t)weights_size, decay * batch_size, beta1,
+                                              beta2, alpha, bcnn_stream(net)));
+    }
+}
+
+static float *zeroed_device_floats(bcnn_net *net, size_t n) {
+    float *p = (float *)bcnn_b200_malloc(n * sizeof(float));
+    if (p) bcnn_cuda_check(bcnn_b200_fill_f32(p, n, 0.0f, bcnn_stream(net)));
+    return p;
+}
+
+/* The optimizer switch every parametrised layer's update runs (reference
+ * bcnn_conv_layer.c:810-855, bcnn_depthwise_conv_layer.c:563-608, bcnn_fc_layer.c:301-346).
+ * The reference allocates the Adam moments when the layer is created and crashes on NULL
+ * moments if the optimizer is switched afterwards; here they appear, zeroed, on the first
+ * Adam step, which gives the same numbers in the first case and working code in the second. */
+void bcnn_optimizer_step_gpu(bcnn_net *net, bcnn_tensor *weights, bcnn_tensor *biases,
+                             float **adam_m_gpu, float **adam_v_gpu) {
+    bcnn_learner *ln = net->learner;
+    const int w_sz = bcnn_tensor_size(weights), b_sz = bcnn_tensor_size(biases);
+    const int batch = bcnn_net_global_batch(net);
+    switch (ln->optimizer) {
+        case BCNN_OPTIM_ADAM:
+            if (!*adam_m_gpu) *adam_m_gpu = zeroed_device_floats(net, (size_t)w_sz);
+            if (!*adam_v_gpu) *adam_v_gpu = zeroed_device_floats(net, (size_t)w_sz);
+            if (!*adam_m_gpu || !*adam_v_gpu) bcnn_cuda_check(2 /* cudaErrorMemoryAllocation */);
+            bcnn_adam_update_gpu(net, weights->data_gpu, biases->data_gpu, weights->grad_data_gpu,
+                                 biases->grad_data_gpu, *adam_m_gpu, *adam_v_gpu, w_sz, b_sz,
+                                 batch, ln->seen, ln->beta1, ln->beta2, ln->learning_rate,
+                                 ln->momentum, ln->decay);
+            break;
+        case BCNN_OPTIM_SGD:
+            bcnn_sgd_update_gpu(net, weights->data_gpu, biases->data_gpu, weights->grad_data_gpu,
+                                biases->grad_data_gpu, w_sz, b_sz, batch, ln->learning_rate,
+                                ln->momentum, ln->decay);
+            break;
+        default:
+            break;
+    }
+}
+
 void bcnn_update(bcnn_net *net) {
     update_learning_rate(net);
     bcnn_dp_before_update(net);
@@ -97,4 +155,39 @@ void bcnn_set_sgd_optimizer(bcnn_net *net, float learning_rate, float momentum) 
 
 void bcnn_set_weight_regularizer(bcnn_net *net, float weight_decay) {
     learner_of(net)->decay = weight_decay;
+}
+
+/* The learner keys of the reference's bcnn_net_set_param (src/bcnn_net.c:506-553), looked up in
+ * tables; like the reference, keys are ignored while the net has no learner (PREDICT). */
+void bcnn_net_set_param(bcnn_net *net, const char *name, const char *val) {
+    static const struct { const char *text; bcnn_lr_decay decay; } policies[] = {
+        {"sigmoid", BCNN_LR_DECAY_SIGMOID}, {"constant", BCNN_LR_DECAY_CONSTANT},
+        {"exp", BCNN_LR_DECAY_EXP},         {"inv", BCNN_LR_DECAY_INV},
+        {"step", BCNN_LR_DECAY_STEP},       {"poly", BCNN_LR_DECAY_POLY}};
+    bcnn_learner *ln = net ? net->learner : NULL;
+    if (!ln || !name || !val) return;
+    if (!strcmp(name, "learning_policy") || !strcmp(name, "decay_type")) {
+        ln->decay_type = BCNN_LR_DECAY_CONSTANT; /* unknown text falls back to constant */
+        for (size_t i = 0; i < sizeof(policies) / sizeof(policies[0]); ++i)
+            if (!strcmp(val, policies[i].text)) ln->decay_type = policies[i].decay;
+    } else if (!strcmp(name, "optimizer")) {
+        if (!strcmp(val, "sgd")) ln->optimizer = BCNN_OPTIM_SGD;
+        if (!strcmp(val, "adam")) ln->optimizer = BCNN_OPTIM_ADAM;
+    } else if (!strcmp(name, "max_batches")) {
+        ln->max_batches = atoi(val);
+    } else if (!strcmp(name, "step")) {
+        ln->step = atoi(val);
+    } else if (!strcmp(name, "learning_rate")) {
+        ln->base_learning_rate = ln->learning_rate = (float)atof(val);
+    } else if (!strcmp(name, "beta1")) {
+        ln->beta1 = (float)atof(val);
+    } else if (!strcmp(name, "beta2")) {
+        ln->beta2 = (float)atof(val);
+    } else if (!strcmp(name, "decay")) {
+        ln->decay = (float)atof(val);
+    } else if (!strcmp(name, "momentum")) {
+        ln->momentum = (float)atof(val);
+    } else if (!strcmp(name, "gamma")) {
+        ln->gamma = (float)atof(val);
+    }
 }

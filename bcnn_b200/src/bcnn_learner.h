@@ -32,6 +32,16 @@ extern "C" {
 void bcnn_sgd_update_gpu(bcnn_net *net, float *weights, float *biases, float *weights_grad,
                          float *biases_grad, int weights_size, int biases_size, int batch_size,
                          float learning_rate, float momentum, float decay);
+/* Device Adam step; argument meaning of reference bcnn_adam_update_gpu (src/bcnn_learner.c:
+ * 134-164) plus the net. */
+void bcnn_adam_update_gpu(bcnn_net *net, float *weights, float *biases, float *weights_grad,
+                          float *biases_grad, float *adam_m, float *adam_v, int weights_size,
+                          int biases_size, int batch_size, int iter, float beta1, float beta2,
+                          float learning_rate, float momentum, float decay);
+/* SGD or Adam step of one (weights, biases) pair, by net->learner->optimizer; the Adam moment
+ * buffers are created on first use. */
+void bcnn_optimizer_step_gpu(bcnn_net *net, bcnn_tensor *weights, bcnn_tensor *biases,
+                             float **adam_m_gpu, float **adam_v_gpu);
 #ifdef __cplusplus
 }
 #endif

@@ -239,16 +239,9 @@ void bcnn_backward_conv_layer(bcnn_net *net, bcnn_node *node) {
 /* bcnn_update_conv_layer (reference :810-855): only W and the bias / beta are stepped;
  * gamma ("scales") receives gradients that no update ever applies. */
 void bcnn_update_conv_layer(bcnn_net *net, bcnn_node *node) {
-    bcnn_tensor *weights = &net->tensors[node->src[1]];
-    bcnn_tensor *biases = &net->tensors[node->src[2]];
-    if (net->learner->optimizer != BCNN_OPTIM_SGD) {
-        BCNN_WARNING(net->log_ctx, "Only the SGD optimizer is implemented on the B200 path\n");
-        return;
-    }
-    bcnn_sgd_update_gpu(net, weights->data_gpu, biases->data_gpu, weights->grad_data_gpu,
-                        biases->grad_data_gpu, bcnn_tensor_size(weights), bcnn_tensor_size(biases),
-                        bcnn_net_global_batch(net), net->learner->learning_rate,
-                        net->learner->momentum, net->learner->decay);
+    bcnn_conv_param *param = (bcnn_conv_param *)node->param;
+    bcnn_optimizer_step_gpu(net, &net->tensors[node->src[1]], &net->tensors[node->src[2]],
+                            &param->adam_m_gpu, &param->adam_v_gpu);
 }
 
 void bcnn_release_param_conv_layer(bcnn_node *node) {
@@ -258,5 +251,7 @@ void bcnn_release_param_conv_layer(bcnn_node *node) {
     bcnn_b200_free(param->bn_workspace_gpu);
     bcnn_b200_free(param->shadows.x);
     bcnn_b200_free(param->reduce_scratch_gpu);
+    bcnn_b200_free(param->adam_m_gpu);
+    bcnn_b200_free(param->adam_v_gpu);
     /* conv_workspace_gpu belongs to the net */
 }

@@ -82,16 +82,14 @@ void bcnn_backward_fullc_layer(bcnn_net *net, bcnn_node *node) {
 }
 
 void bcnn_update_fullc_layer(bcnn_net *net, bcnn_node *node) {
-    bcnn_tensor *weights = &net->tensors[node->src[1]];
-    bcnn_tensor *biases = &net->tensors[node->src[2]];
-    if (net->learner->optimizer != BCNN_OPTIM_SGD) return;
-    bcnn_sgd_update_gpu(net, weights->data_gpu, biases->data_gpu, weights->grad_data_gpu,
-                        biases->grad_data_gpu, bcnn_tensor_size(weights), bcnn_tensor_size(biases),
-                        bcnn_net_global_batch(net), net->learner->learning_rate,
-                        net->learner->momentum, net->learner->decay);
+    bcnn_fullc_param *param = (bcnn_fullc_param *)node->param;
+    bcnn_optimizer_step_gpu(net, &net->tensors[node->src[1]], &net->tensors[node->src[2]],
+                            &param->adam_m_gpu, &param->adam_v_gpu);
 }
 
 void bcnn_release_param_fullc_layer(bcnn_node *node) {
     bcnn_fullc_param *param = (bcnn_fullc_param *)node->param;
     bcnn_b200_free(param->reduce_scratch_gpu);
+    bcnn_b200_free(param->adam_m_gpu);
+    bcnn_b200_free(param->adam_v_gpu);
 }

@@ -136,6 +136,14 @@ BCNN_API void bcnn_set_learning_rate_policy(bcnn_net *net, bcnn_lr_decay decay_t
                                             int max_batches, int step);
 BCNN_API void bcnn_set_weight_regularizer(bcnn_net *net, float weight_decay);
 
+/* -- weight files (reference inc/bcnn/bcnn.h:421, :448; src/bcnn_net.c:597-681, :1485-1558) --
+ * bcnn_save_weights writes the reference's .bcnnmodel layout byte for byte.
+ * bcnn_load_weights reads .bcnnmodel and Darknet *.weights files; in BCNN_MODE_PREDICT it
+ * folds the batch-norm running statistics into scales / bias as the reference's CPU build
+ * does. A truncated file returns BCNN_INVALID_MODEL (the reference logs and returns success). */
+BCNN_API bcnn_status bcnn_load_weights(bcnn_net *net, const char *model_path);
+BCNN_API bcnn_status bcnn_save_weights(bcnn_net *net, const char *filename);
+
 /* -- the three loops -- */
 BCNN_API void bcnn_forward(bcnn_net *net);
 BCNN_API void bcnn_backward(bcnn_net *net);

@@ -277,6 +277,15 @@ BCNN_B200_API size_t bcnn_b200_depthwise_scratch_floats(int n, int c, int ksize)
  * momentum (momentum / world_size under data parallelism). */
 BCNN_B200_API int bcnn_b200_sgd_update(float *w, float *g, size_t n, float wd_scale,
                                        float step, float g_scale, void *stream);
+/* One fused pass of bcnn_adam_update_gpu's weight branch (src/bcnn_learner.c:148-161; the CPU
+ * arithmetic of :118-129 is the parity target):
+ *   g += wd_scale * w;  m = (1-beta1) g + beta1 m;  v = (1-beta2) g^2 + beta2 v;
+ *   w += alpha * m / (sqrt(v) + 1e-7);  g = 0
+ * with wd_scale = decay*batch and alpha = -lr/batch * sqrt(1-beta2^(t+1)) / (1-beta1^(t+1))
+ * computed by the caller (t = samples seen). Biases take bcnn_b200_sgd_update. */
+BCNN_B200_API int bcnn_b200_adam_update(float *w, float *g, float *m, float *v, size_t n,
+                                        float wd_scale, float beta1, float beta2, float alpha,
+                                        void *stream);
 
 /* ---- glue kernels ---------------------------------------- */
 /* softmax over channels at each spatial position, log-sum-exp form of

@@ -27,6 +27,14 @@ BCNN_B200_API int bcnn_b200_get_conv_math(bcnn_net *net);
  *   OFF: batch-correct residual add, and data gradients accumulate into tensors that have
  *        more than one consumer. ResNet-style training needs OFF to be meaningful. */
 BCNN_B200_API void bcnn_b200_set_reference_quirks(bcnn_net *net, int on);
+/* Solver parameters by name, as the reference's cfg reader sets them: the learner branch of
+ * bcnn_net_set_param (src/bcnn_net.h:75, src/bcnn_net.c:506-553; internal but non-static there,
+ * same name and meaning here). Keys: max_batches, learning_policy | decay_type
+ * (sigmoid|constant|exp|inv|step|poly), optimizer (sgd|adam), step, learning_rate, beta1,
+ * beta2, decay, momentum, gamma. This is the only way to reach Adam, in the reference too:
+ * bcnn_set_adam_optimizer never switches the optimizer. Shape keys and
+ * augmentation keys are the cfg parser's business and are ignored. */
+BCNN_B200_API void bcnn_net_set_param(bcnn_net *net, const char *name, const char *val);
 /* The CUDA stream (cudaStream_t) every kernel of this net is launched on. */
 BCNN_B200_API void *bcnn_b200_get_stream(bcnn_net *net);
 /* Block the host until the net's stream (and its comm stream) are idle. */

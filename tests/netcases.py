@@ -118,3 +118,22 @@ def _pool_indexes(net, node):
     n = net.lib.bcnn_b200_maxpool_indexes(net.handle, node, buf.ctypes.data)
     assert n == buf.size
     return buf
+
+
+def model_io_net(net, batch=2):
+    """Every node kind that owns records in a weight file: conv+BN (3x3/s1, the
+    reference's Winograd route in PREDICT), plain conv, standalone batchnorm, depthwise, 1x1
+    conv+BN, and a fully-connected layer with a non-square weight matrix (Darknet transpose)."""
+    net.set_input_shape(12, 12, 3, batch)
+    net.conv(8, 3, 1, 1, 1, 1, "lrelu", "input", "c1")
+    net.maxpool(2, 2, capi.PAD_SAME, "c1", "p1")
+    net.conv(8, 3, 2, 1, 1, 0, "relu", "p1", "c2")
+    net.batchnorm("c2", "bn2")
+    net.depthwise(3, 1, 1, "relu", "bn2", "dw")
+    net.conv(12, 1, 1, 0, 1, 1, "none", "dw", "c3")
+    net.fullc(10, "none", "c3", "fc")
+    net.softmax("fc", "softmax")
+    if net.mode != capi.MODE_PREDICT:
+        net.cost("softmax", "cost")
+        net.sgd(0.01, 0.9, 0.0005)
+    return dict(classes=10, out="softmax")
