@@ -571,6 +571,35 @@ void orc_sgd_update(float *w, float *b, float *gw, float *gb, int wsz, int bsz,
     }
 }
 
+/* bcnn_adam_update_cpu, src/bcnn_learner.c:106-132, pass by pass. `iter` is what the layers
+ * hand in: learner->seen, samples not steps (bcnn_conv_layer.c:831). The division is bcnn_vdiv
+ * as the default (AVX) build compiles it, src/kernels/bcnn_mat.c:277-310: the 8-wide body
+ * divides unconditionally, the n % 8 scalar tail yields 0 when |denominator| <= 1e-5. */
+void orc_adam_update(float *w, float *b, float *gw, float *gb, float *m, float *v, int wsz,
+                     int bsz, int batch, int iter, float beta1, float beta2, float lr,
+                     float momentum, float decay) {
+    float mu = sqrtf(1.0f - powf(beta2, (float)iter + 1)) / (1.0f - powf(beta1, (float)iter + 1));
+    if (b && gb) {
+        float a = -lr / batch;
+        for (int i = 0; i < bsz; ++i) b[i] += a * gb[i];
+        for (int i = 0; i < bsz; ++i) gb[i] *= momentum;
+    }
+    if (w && gw) {
+        float d = decay * batch, a = -lr / batch * mu;
+        int body = wsz / 8 * 8;
+        for (int i = 0; i < wsz; ++i) gw[i] += d * w[i];
+        for (int i = 0; i < wsz; ++i) m[i] = (1.0f - beta1) * gw[i] + beta1 * m[i];
+        for (int i = 0; i < wsz; ++i) gw[i] = gw[i] * gw[i];
+        for (int i = 0; i < wsz; ++i) v[i] = (1.0f - beta2) * gw[i] + beta2 * v[i];
+        for (int i = 0; i < wsz; ++i) gw[i] = powf(v[i], 0.5f);
+        for (int i = 0; i < wsz; ++i) gw[i] += 0.0000001f;
+        for (int i = 0; i < body; ++i) gw[i] = m[i] / gw[i];
+        for (int i = body; i < wsz; ++i) gw[i] = fabsf(gw[i]) > 0.00001f ? m[i] / gw[i] : 0.0f;
+        for (int i = 0; i < wsz; ++i) w[i] += a * gw[i];
+        memset(gw, 0, (size_t)wsz * sizeof(float));
+    }
+}
+
 /* ------------------------------------------------------------------ */
 /* Glue: fc, softmax, eltwise                                           */
 /* ------------------------------------------------------------------ */

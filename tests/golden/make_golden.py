@@ -3,6 +3,7 @@
 public API on the seeded synthetic cases of tests/netcases.py.
 
     python tests/golden/make_golden.py [case ...]     (default: every case of netcases.CASES)
+    python tests/golden/make_golden.py model_io       (weight-file fixtures, see make_model_io)
 
 The reference ships no golden vectors of its own, so these files are
 the pin: they record what the reference computes, never hand-edited. Large tensors are
@@ -21,7 +22,7 @@ import netcases  # noqa: E402
 from helpers import GOLDEN, ref_net  # noqa: E402
 
 SUB = 4096
-FULL_CASES = {"chain_b4", "resnet_small_b4", "yolo_two_heads_b2"}  # small enough to keep every tensor whole
+FULL_CASES = {"chain_b4", "resnet_small_b4", "yolo_two_heads_b2", "chain_adam_b4"}  # small enough to keep every tensor whole
 
 
 def subsample(a: np.ndarray) -> np.ndarray:
@@ -32,7 +33,65 @@ def subsample(a: np.ndarray) -> np.ndarray:
     return flat[idx].copy()
 
 
+def make_model_io():
+    """Weight-file fixtures, all written or read by the reference itself:
+      model_io.bcnnmodel  bcnn_save_weights of netcases.model_io_net with seeded parameters
+      model_io.weights    a Darknet-layout file of the same net (written by the numpy restatement,
+                          minor version 1001 so the reader transposes the fc matrix)
+      model_io.npz        layout (json); saved/<tensor> the values that were saved;
+                          train/<tensor>, predict/<tensor> what bcnn_load_weights leaves in a
+                          TRAIN / PREDICT net (PREDICT: batch-norm folded); darknet/<tensor> the
+                          same for the Darknet file in PREDICT mode; input + predict_out: one
+                          PREDICT forward of the reference after loading model_io.bcnnmodel."""
+    import dataclasses
+    import json
+    sys.path.insert(0, str(ROOT / "oracle"))
+    import bcnn_model_oracle as mo
+    from bcnn_b200 import capi, configs
+
+    def built(mode):
+        net = ref_net(mode=mode, threads=1)
+        info = netcases.model_io_net(net)
+        net.compile()
+        return net, info
+
+    def params(net, prefix):
+        return {f"{prefix}/{name}": net.get(idx).ravel()
+                for idx, name, _ in configs.param_tensors(net)}
+
+    packed = {}
+    src, _ = built(capi.MODE_VALID)  # VALID: init_params randomises the running statistics
+    configs.init_params(src, seed=11)
+    src.save_weights(GOLDEN / "model_io.bcnnmodel")
+    packed.update(params(src, "saved"))
+    layout = mo.net_layout(src)
+    packed["layout"] = np.array(json.dumps([dataclasses.asdict(n) for n in layout]))
+    rng = np.random.default_rng(12)
+    values = {name: rng.uniform(0.5, 1.5, size=size).astype(np.float32)
+              for name, size in mo.all_names(layout)}
+    mo.write_darknet(GOLDEN / "model_io.weights", layout, values, major=0, minor=1001)
+    for mode, tag, path in ((capi.MODE_TRAIN, "train", "model_io.bcnnmodel"),
+                            (capi.MODE_PREDICT, "predict", "model_io.bcnnmodel"),
+                            (capi.MODE_PREDICT, "darknet", "model_io.weights")):
+        net, info = built(mode)
+        assert net.load_weights(GOLDEN / path) == 0
+        packed.update(params(net, tag))
+        if tag == "predict":
+            x = configs.synth_input(net.shape("input"), seed=21)
+            net.set("input", x)
+            net.forward()
+            packed["input"] = x
+            packed["predict_out"] = net.get(info["out"])
+        net.close()
+    np.savez_compressed(GOLDEN / "model_io.npz", **packed)
+    print(f"model_io: {len(packed)} arrays, "
+          f"{(GOLDEN / 'model_io.bcnnmodel').stat().st_size} + "
+          f"{(GOLDEN / 'model_io.weights').stat().st_size} file bytes")
+
+
 def main():
+    if sys.argv[1:] == ["model_io"]:
+        return make_model_io()
     from bcnn_b200 import configs
     from helpers import rel_err
     for name in (sys.argv[1:] or netcases.CASES):

@@ -59,6 +59,15 @@ def yolo_two_heads(net, batch=2):
     return dict(classes=None, out="head")
 
 
+def chain_adam(net, batch=4):
+    """chain_convnet trained with Adam, reached the only way the reference reaches it (SURVEY.md
+    H7): rates through bcnn_set_adam_optimizer, the switch through the cfg key, both BEFORE the
+    layers exist (the reference allocates the moments at layer creation). chain_convnet's own
+    bcnn_set_sgd_optimizer call then only sets lr 0.01 / bias momentum 0.9; decay 5e-4."""
+    net.adam(0.004, 0.9, 0.999)
+    return chain_convnet(net, batch)
+
+
 CASES = {
     # name: (builder, kwargs, steps)
     "mnist_b8": (configs.mnist, dict(batch=8), 3),
@@ -66,6 +75,7 @@ CASES = {
     "chain_b4": (chain_convnet, dict(batch=4), 2),
     "resnet_small_b4": (small_resnet, dict(batch=4), 2),
     "yolo_two_heads_b2": (yolo_two_heads, dict(batch=2), 2),
+    "chain_adam_b4": (chain_adam, dict(batch=4), 3),
 }
 
 

@@ -1,0 +1,239 @@
+"""Weight files: bcnn_save_weights / bcnn_load_weights of libbcnn_b200.so against
+the reference's own files and loads.
+
+Fixtures (tests/golden/make_golden.py model_io, all produced by the compiled reference):
+model_io.bcnnmodel (its bcnn_save_weights), model_io.weights (Darknet layout, fc transposed on
+load), model_io.npz (what its bcnn_load_weights leaves in TRAIN / PREDICT nets, and one PREDICT
+forward after the load).
+
+CPU suite: the numpy restatement oracle/bcnn_model_oracle.py is pinned against those fixtures and,
+when oracle/_ref is present, against the reference run live on fresh seeds.
+GPU suite: the B200 library must write the same bytes, load the same values (bit-exact: this is
+byte work, including the PREDICT batch-norm fold, which is float arithmetic in a fixed order) and
+reproduce the reference's PREDICT forward within 2e-5 of the output's max (FP32 convolutions in
+a different summation order; the reference runs its 3x3/s1 convolution through Winograd there).
+"""
+import json
+import sys
+
+import numpy as np
+import pytest
+
+import netcases
+from bcnn_b200 import capi, configs
+from helpers import GOLDEN, ROOT, assert_close, ref_available, ref_net
+
+sys.path.insert(0, str(ROOT / "oracle"))
+import bcnn_model_oracle as mo  # noqa: E402
+
+MODEL = GOLDEN / "model_io.bcnnmodel"
+DARKNET = GOLDEN / "model_io.weights"
+
+
+@pytest.fixture(scope="module")
+def golden():
+    return dict(np.load(GOLDEN / "model_io.npz"))
+
+
+def golden_layout(golden):
+    nodes = []
+    for d in json.loads(str(golden["layout"])):
+        roles = {k: (v[0], int(v[1])) for k, v in d["roles"].items()}
+        nodes.append(mo.Node(d["kind"], roles, d["rows"], d["cols"]))
+    return nodes
+
+
+def group(golden, prefix):
+    return {k[len(prefix) + 1:]: v for k, v in golden.items() if k.startswith(prefix + "/")}
+
+
+def assert_same_bits(got, want, what):
+    assert set(want) <= set(got), f"{what}: missing {set(want) - set(got)}"
+    for name, w in want.items():
+        g = np.asarray(got[name], dtype=np.float32).reshape(-1)
+        assert np.array_equal(g.view(np.uint32), w.reshape(-1).view(np.uint32)), f"{what}: {name}"
+
+
+def params(net):
+    return {name: net.get(idx).ravel() for idx, name, _ in configs.param_tensors(net)}
+
+
+def build(net):
+    info = netcases.model_io_net(net)
+    net.compile()
+    return info
+
+
+# ------------------------------------------------------------------ CPU: the restatement is pinned
+def test_restatement_writes_the_reference_bytes(golden, tmp_path):
+    blob = mo.write_bcnn(tmp_path / "w.bcnnmodel", golden_layout(golden), group(golden, "saved"))
+    assert blob == MODEL.read_bytes()
+    assert blob[:4] == b"BCNN" and np.frombuffer(blob, "<u4", 3, 4).tolist() == [0, 2, 0]
+
+
+def test_restatement_reads_like_the_reference_train(golden):
+    got = mo.read(MODEL, golden_layout(golden))
+    assert_same_bits(got, group(golden, "train"), "TRAIN load")
+    assert_same_bits(got, group(golden, "saved"), "round trip")
+
+
+def test_restatement_folds_like_the_reference_predict(golden):
+    got = mo.read(MODEL, golden_layout(golden), predict=True)
+    want = group(golden, "predict")
+    assert_same_bits(got, want, "PREDICT load (batch-norm fold)")
+    # the fold really changed something, and only scales / biases of batch-normalised nodes
+    saved = group(golden, "saved")
+    changed = {k for k in want if not np.array_equal(want[k], saved[k])}
+    assert changed and all(k.endswith("_scales") or k.endswith("_b") for k in changed), changed
+
+
+def test_restatement_reads_darknet_like_the_reference(golden):
+    got = mo.read(DARKNET, golden_layout(golden), predict=True)
+    assert_same_bits(got, group(golden, "darknet"), "Darknet load")
+
+
+def test_restatement_rejects_what_the_reference_rejects(golden, tmp_path):
+    layout = golden_layout(golden)
+    bad = tmp_path / "bad.bcnnmodel"
+    bad.write_bytes(b"XXXX" + MODEL.read_bytes()[4:])
+    with pytest.raises(ValueError, match="BCNN_INVALID_MODEL"):
+        mo.read(bad, layout)
+    onnx = tmp_path / "net.onnx"
+    onnx.write_bytes(MODEL.read_bytes())
+    with pytest.raises(ValueError, match="BCNN_INVALID_MODEL"):
+        mo.read(onnx, layout)
+
+
+@pytest.mark.skipif(not ref_available(), reason="oracle/_ref was not built / did not travel")
+@pytest.mark.parametrize("seed", [1, 2])
+def test_restatement_against_the_live_reference(seed, tmp_path):
+    src = ref_net(mode=capi.MODE_VALID)
+    build(src)
+    configs.init_params(src, seed=seed)
+    path = tmp_path / "live.bcnnmodel"
+    src.save_weights(path)
+    layout = mo.net_layout(src)
+    assert mo.write_bcnn(tmp_path / "mine.bcnnmodel", layout, params(src)) == path.read_bytes()
+    for mode in (capi.MODE_TRAIN, capi.MODE_PREDICT):
+        net = ref_net(mode=mode)
+        build(net)
+        assert net.load_weights(path) == 0
+        assert_same_bits(mo.read(path, layout, predict=mode == capi.MODE_PREDICT), params(net),
+                         f"live load, mode {mode}")
+        net.close()
+    # Darknet header variants: 64-bit `seen` (0.2), 32-bit `seen` (0.1), transposing reader
+    rng = np.random.default_rng(seed)
+    values = {n: rng.uniform(0.5, 1.5, size=s).astype(np.float32) for n, s in mo.all_names(layout)}
+    for major, minor in ((0, 2), (0, 1), (0, 1001)):
+        dk = tmp_path / f"v{major}_{minor}.weights"
+        mo.write_darknet(dk, layout, values, major=major, minor=minor)
+        net = ref_net(mode=capi.MODE_PREDICT)
+        build(net)
+        assert net.load_weights(dk) == 0
+        assert_same_bits(mo.read(dk, layout, predict=True), params(net), f"darknet {major}.{minor}")
+        net.close()
+    src.close()
+
+
+# ------------------------------------------------------------------ GPU: the product
+@pytest.mark.gpu
+def test_layout_of_the_b200_net_is_the_reference_layout(golden):
+    net = capi.Net(mode=capi.MODE_TRAIN)
+    build(net)
+    assert mo.net_layout(net) == golden_layout(golden)
+    net.close()
+
+
+@pytest.mark.gpu
+def test_save_writes_the_reference_bytes(golden, tmp_path):
+    net = capi.Net(mode=capi.MODE_VALID)
+    build(net)
+    configs.init_params(net, seed=11)  # the seed the fixture was saved with
+    assert_same_bits(params(net), group(golden, "saved"), "seeded parameters")
+    net.save_weights(tmp_path / "b200.bcnnmodel")
+    assert (tmp_path / "b200.bcnnmodel").read_bytes() == MODEL.read_bytes()
+    net.close()
+
+
+@pytest.mark.gpu
+def test_load_train_is_bit_exact(golden):
+    net = capi.Net(mode=capi.MODE_TRAIN)
+    build(net)
+    assert net.load_weights(MODEL) == 0
+    assert_same_bits(params(net), group(golden, "train"), "TRAIN load")
+    net.close()
+
+
+@pytest.mark.gpu
+def test_load_predict_folds_and_forward_matches_reference(golden):
+    net = capi.Net(mode=capi.MODE_PREDICT)
+    info = build(net)
+    assert net.load_weights(MODEL) == 0
+    assert_same_bits(params(net), group(golden, "predict"), "PREDICT load (batch-norm fold)")
+    net.set("input", golden["input"])
+    net.forward()
+    out = net.get(info["out"])
+    assert out.shape == golden["predict_out"].shape
+    assert_close(out, golden["predict_out"], 2e-5, "PREDICT forward after load")
+    assert np.allclose(out.reshape(out.shape[0], -1).sum(axis=1), 1.0, atol=1e-5)
+    net.close()
+
+
+@pytest.mark.gpu
+def test_load_darknet_is_bit_exact(golden):
+    net = capi.Net(mode=capi.MODE_PREDICT)
+    build(net)
+    assert net.load_weights(DARKNET) == 0
+    assert_same_bits(params(net), group(golden, "darknet"), "Darknet load")
+    net.close()
+
+
+@pytest.mark.gpu
+def test_load_error_statuses(tmp_path):
+    invalid_parameter, invalid_model = 1, 3  # bcnn_status
+    net = capi.Net(mode=capi.MODE_TRAIN)
+    build(net)
+    blob = MODEL.read_bytes()
+    assert net.load_weights(tmp_path / "missing.bcnnmodel") == invalid_parameter
+    (tmp_path / "bad.bcnnmodel").write_bytes(b"XXXX" + blob[4:])
+    assert net.load_weights(tmp_path / "bad.bcnnmodel") == invalid_model
+    (tmp_path / "net.onnx").write_bytes(blob)
+    assert net.load_weights(tmp_path / "net.onnx") == invalid_model
+    # truncated: documented deviation (the reference logs and returns success); whatever was read
+    # before the cut is loaded, as in the reference
+    (tmp_path / "short.bcnnmodel").write_bytes(blob[:16 + 4 * 8 + 4 * 100])
+    assert net.load_weights(tmp_path / "short.bcnnmodel") == invalid_model
+    with pytest.raises(RuntimeError):
+        net.save_weights(tmp_path / "no_such_dir" / "x.bcnnmodel")
+    net.close()
+
+
+@pytest.mark.gpu
+def test_trained_weights_survive_a_save_load_round_trip(tmp_path):
+    """Size-independent property: train, save, load into a fresh net => identical parameters,
+    identical next forward."""
+    net = capi.Net(mode=capi.MODE_TRAIN)
+    info = build(net)
+    configs.init_params(net, seed=5)
+    x = configs.synth_input(net.shape("input"), seed=6)
+    y = configs.synth_labels(net.shape("label"))
+    for _ in range(2):
+        net.set("input", x)
+        net.set("label", y)
+        net.forward()
+        net.backward()
+        net.update()
+    path = tmp_path / "trained.bcnnmodel"
+    net.save_weights(path)
+    assert path.stat().st_size == MODEL.stat().st_size
+    twin = capi.Net(mode=capi.MODE_TRAIN)
+    build(twin)
+    assert twin.load_weights(path) == 0
+    assert_same_bits(params(twin), params(net), "round trip")
+    for n in (net, twin):
+        n.set_mode(capi.MODE_VALID)
+        n.set("input", x)
+        n.forward()
+    assert np.array_equal(net.get(info["out"]), twin.get(info["out"]))
+    net.close()
+    twin.close()

@@ -265,3 +265,29 @@ def test_sgd_update_bit_exact():
         orc.orc_sgd_update(p(b[0]), p(b[1]), p(b[2]), p(b[3]), n, 7, 64, 0.003, 0.9, 0.0005)
         for u, v in zip(a, b):
             assert np.array_equal(u, v)
+
+
+def test_adam_update_bit_exact():
+    """orc_adam_update against the reference's bcnn_adam_update_cpu (src/bcnn_learner.c:106-132):
+    three consecutive steps (moments carried over), sizes with and without an n % 8 tail, and
+    vanishing second moments so the tail's division guard (bcnn_vdiv) is taken."""
+    lib, orc = ref_lib(), oracle()
+    lib.bcnn_adam_update_cpu.argtypes = [C.c_void_p] * 6 + [C.c_int] * 4 + [C.c_float] * 5
+    r = rng(9)
+    for n in (5, 16, 1003):
+        state = [f32(r.normal(size=n)), f32(r.normal(size=7)), None, None,
+                 np.zeros(n, np.float32), np.zeros(n, np.float32)]
+        a = [None if x is None else x.copy() for x in state]
+        b = [None if x is None else x.copy() for x in state]
+        for step in range(3):
+            g = f32(r.normal(scale=1e-2, size=n))
+            if step == 0:
+                g[-3:] = 0.0  # zero moments in the scalar tail: guarded quotient
+                g[0] = 1e-9   # tiny moments in the vector body: unguarded quotient
+            gb = f32(r.normal(size=7))
+            for side, fn in ((a, lib.bcnn_adam_update_cpu), (b, orc.orc_adam_update)):
+                side[2], side[3] = g.copy(), gb.copy()
+                fn(p(side[0]), p(side[1]), p(side[2]), p(side[3]), p(side[4]), p(side[5]), n, 7,
+                   16, 16 * (step + 1), 0.9, 0.999, 0.002, 0.9, 0.0005)
+            for u, v in zip(a, b):
+                assert np.array_equal(u.view(np.uint32), v.view(np.uint32)), (n, step)
