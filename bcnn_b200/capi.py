@@ -92,6 +92,9 @@ def bind_bcnn_api(lib: C.CDLL, tensor_type) -> None:
         "bcnn_add_upsample_layer": (i, [vp, i, s, s]),
         "bcnn_add_cost_layer": (i, [vp, i, i, f, s, s, s]),
         "bcnn_set_adam_optimizer": (None, [vp, f, f, f]),
+        "bcnn_train_on_batch": (f, [vp]),
+        "bcnn_predict_on_batch": (f, [vp, C.POINTER(C.POINTER(tensor_type))]),
+        "bcnn_add_input": (i, [vp, i, i, i, s]),
         "bcnn_load_weights": (i, [vp, s]),
         "bcnn_save_weights": (i, [vp, s]),
         # internal but exported by both libraries (reference src/bcnn_net.h:75)
@@ -289,6 +292,24 @@ class Net:
     def set_mode(self, mode):
         self.lib.bcnn_set_mode(self.handle, mode)
         self.mode = mode
+
+    def add_input(self, w, h, c, name):
+        self._check(self.lib.bcnn_add_input(self.handle, w, h, c, _b(name)), f"add_input {name}")
+
+    def train_on_batch(self) -> float:
+        """bcnn_train_on_batch. On the B200 flavour the batch is taken from the host mirrors
+        (fill them with set_host); the CPU reference needs a file loader and cannot run this."""
+        return float(self.lib.bcnn_train_on_batch(self.handle))
+
+    def predict_on_batch(self):
+        """bcnn_predict_on_batch -> (loss, output array)."""
+        ttype = TensorB200 if self.flavour == "b200" else TensorCPU
+        out = C.POINTER(ttype)()
+        loss = float(self.lib.bcnn_predict_on_batch(self.handle, C.byref(out)))
+        t = out.contents
+        size = t.n * t.c * t.h * t.w
+        arr = np.ctypeslib.as_array(t.data, shape=(size,)).reshape(t.n, t.c, t.h, t.w).copy()
+        return loss, arr
 
     # -- the three loops --
     def forward(self):

@@ -5,7 +5,8 @@
  * Mirrors the behaviour of jnbraun/bcnn src/bcnn_net.c:61-463 for the functions on the
  * path (bcnn_init_net :61, bcnn_net_add_node/_tensor :236-258, bcnn_set_input_shape :280,
  * bcnn_compile_net :356, bcnn_reset_gradients :361, getters :377-408, bcnn_forward :410,
- * bcnn_backward :424). The cfg parser, weight files and data loaders of that file are out
+ * bcnn_backward :424, bcnn_train_on_batch / bcnn_predict_on_batch :452-483, bcnn_add_input
+ * :260). Weight files: bcnn_model.c. The cfg parser and data loaders of that file are out
  * of scope. Everything runs on one CUDA stream per net; nothing synchronises unless a
  * getter needs host data.
  */
@@ -477,6 +478,50 @@ float bcnn_b200_train_step(bcnn_net *net, int upload_inputs, int fetch_loss) {
     if (upload_inputs == 2 && fetch_loss)
         bcnn_cuda_check(bcnn_b200_stream_sync(bcnn_ctx(net)->copy_stream));
     return loss;
+}
+
+/* bcnn_train_on_batch (reference src/bcnn_net.c:452-463): next batch, forward, backward,
+ * update, loss. The reference pulls the batch from its file loader (bcnn_loader_next,
+ * src/bcnn_data.c:402-427: decode, augment, synchronous cudaMemcpy) -- out of scope here, and a
+ * NULL dereference there when no loader is set. Here the batch is what the caller left in the
+ * pinned host mirrors of the inputs and the label; it is uploaded on the compute stream. Use
+ * bcnn_b200_train_step(net, 2, ...) for the overlapped input pipeline. */
+float bcnn_train_on_batch(bcnn_net *net) { return bcnn_b200_train_step(net, 1, 1); }
+
+/* bcnn_predict_on_batch (reference :465-483): forward on the batch in the host mirrors; *out is
+ * the last node's output, or the cost node's prediction input, with its host copy refreshed. */
+float bcnn_predict_on_batch(bcnn_net *net, bcnn_tensor **out) {
+    if (out) *out = NULL;
+    if (net->num_nodes < 1) return 0.f;
+    bcnn_b200_upload_inputs(net);
+    bcnn_forward(net);
+    const bcnn_node *last = &net->nodes[net->num_nodes - 1];
+    const int out_id = last->type == BCNN_LAYER_COST ? last->src[0] : last->dst[0];
+    if (out) *out = bcnn_get_tensor_by_index(net, out_id);
+    return bcnn_b200_get_loss(net);
+}
+
+/* bcnn_add_input (reference :260-278): one more input tensor [batch, c, h, w] without
+ * gradient, registered in net->inputs[] so the upload calls and the input pipeline carry it.
+ * Call it after bcnn_set_input_shape (it takes the batch size from the net) and before the
+ * first pipelined step. */
+bcnn_status bcnn_add_input(bcnn_net *net, int w, int h, int c, const char *name) {
+    BCNN_CHECK_AND_LOG(net->log_ctx, w > 0 && h > 0 && c > 0 && net->batch_size > 0 && name,
+                       BCNN_INVALID_PARAMETER, "bcnn_add_input: invalid shape or name\n");
+    BCNN_CHECK_AND_LOG(net->log_ctx, bcnn_ctx(net)->stage_gpu == NULL, BCNN_INVALID_PARAMETER,
+                       "bcnn_add_input: the input pipeline is already running\n");
+    bcnn_tensor input = {0};
+    bcnn_tensor_set_shape(&input, net->batch_size, c, h, w, 0);
+    BCNN_CHECK_STATUS(bcnn_tensor_allocate(&input, net->mode));
+    BCNN_CHECK_STATUS(bcnn_tensor_ensure_host(&input));
+    input.name = bcnn_strdup_(name);
+    BCNN_CHECK_STATUS(bcnn_net_add_tensor(net, input));
+    int *grown = (int *)realloc(net->inputs, (size_t)(net->num_inputs + 1) * sizeof(int));
+    BCNN_CHECK_AND_LOG(net->log_ctx, grown != NULL, BCNN_FAILED_ALLOC,
+                       "Internal allocation error\n");
+    net->inputs = grown;
+    net->inputs[net->num_inputs++] = net->num_tensors - 1;
+    return BCNN_SUCCESS;
 }
 
 int bcnn_b200_num_nodes(bcnn_net *net) { return net->num_nodes; }

@@ -123,6 +123,9 @@ BCNN_API int bcnn_get_num_threads(bcnn_net *net);
 BCNN_API void bcnn_set_input_shape(bcnn_net *net, int width, int height,
                                    int channels, int batch_size);
 BCNN_API int bcnn_get_batch_size(bcnn_net *net);
+/* One more input tensor (reference inc/bcnn/bcnn.h:368, src/bcnn_net.c:260-278). */
+BCNN_API bcnn_status bcnn_add_input(bcnn_net *net, int width, int height, int channels,
+                                    const char *name);
 BCNN_API bcnn_status bcnn_compile_net(bcnn_net *net);
 BCNN_API bcnn_status bcnn_set_mode(bcnn_net *net, bcnn_mode mode);
 
@@ -148,6 +151,12 @@ BCNN_API bcnn_status bcnn_save_weights(bcnn_net *net, const char *filename);
 BCNN_API void bcnn_forward(bcnn_net *net);
 BCNN_API void bcnn_backward(bcnn_net *net);
 BCNN_API void bcnn_update(bcnn_net *net);
+/* The train / predict calls of the reference (inc/bcnn/bcnn.h:683, :699; src/bcnn_net.c:
+ * 452-483) without its file loader: the batch is taken from the pinned host mirrors of the
+ * input tensors and the label (bcnn_get_tensor_by_name(net, "input")->data, ...), uploaded,
+ * and the loss (mean over the cost nodes) is read back. */
+BCNN_API float bcnn_train_on_batch(bcnn_net *net);
+BCNN_API float bcnn_predict_on_batch(bcnn_net *net, bcnn_tensor **out);
 
 /* -- tensor access (refreshes the host mirrors of data and grad) -- */
 BCNN_API int bcnn_get_tensor_index_by_name(bcnn_net *net, const char *name);

@@ -202,3 +202,74 @@ def test_valid_and_predict_modes_follow_reference_semantics():
                            None, mode)
         orc.orc_activation_forward(p(raw), raw.size, None, 144, 8, capi.ACT["relu"])
         assert_close(y, raw, 2e-5, f"mode {mode}")
+
+
+def test_train_and_predict_on_batch_are_the_three_loops():
+    """bcnn_train_on_batch = upload + forward + backward + update + loss; bcnn_predict_on_batch =
+    upload + forward + output (reference src/bcnn_net.c:452-483, minus the file loader)."""
+    nets = []
+    for _ in range(2):
+        net = capi.Net()
+        info = netcases.chain_convnet(net, batch=4)
+        net.compile()
+        configs.init_params(net, seed=9)
+        nets.append(net)
+    a, b = nets
+    x = configs.synth_input(a.shape("input"), seed=10)
+    y = configs.synth_labels(a.shape("label"))
+    for step in range(2):
+        a.set_host("input", x + step)
+        a.set_host("label", y)
+        loss_a = a.train_on_batch()
+        b.set("input", x + step)
+        b.set("label", y)
+        b.forward()
+        b.backward()
+        b.update()
+        assert loss_a == b.loss()
+    for idx, name, _ in configs.param_tensors(a):
+        assert np.array_equal(a.get(idx), b.get(idx)), name
+    for n in (a, b):
+        n.set_mode(capi.MODE_VALID)
+    a.set_host("input", x)
+    loss, out = a.predict_on_batch()
+    b.set("input", x)
+    b.forward()
+    assert np.array_equal(out, b.get(info["out"])) and loss == b.loss()
+    assert out.shape == a.shape(info["out"])
+    a.close()
+    b.close()
+
+
+def _two_input_net(net, batch=2):
+    """A second input tensor (bcnn_add_input) joining the trunk through a concat."""
+    net.set_input_shape(8, 8, 3, batch)
+    net.add_input(8, 8, 2, "aux")
+    net.conv(4, 3, 1, 1, 1, 0, "relu", "input", "c_main")
+    net.conv(4, 3, 1, 1, 1, 0, "relu", "aux", "c_aux")
+    net.concat(["c_main", "c_aux"], "cat")
+    net.conv(6, 1, 1, 0, 1, 0, "none", "cat", "head")
+    net.cost("head", "cost", metric=capi.METRIC_SSE)
+    net.sgd(0.01, 0.9, 0.0005)
+    net.compile()
+
+
+@pytest.mark.skipif(not ref_available(), reason="oracle/_ref was not built / did not travel")
+def test_second_input_tensor_matches_live_reference():
+    outs = []
+    for net in (capi.Net(), ref_net()):
+        _two_input_net(net)
+        configs.init_params(net, seed=4)
+        net.set("input", configs.synth_input(net.shape("input"), seed=5))
+        net.set("aux", configs.synth_input(net.shape("aux"), seed=6))
+        net.set("label", configs.synth_input(net.shape("label"), seed=7))
+        net.forward()
+        net.backward()
+        net.update()
+        outs.append({k: net.get(k) for k in ("head", "c_aux")} |
+                    {"g:" + k: net.get(k, grad=True) for k in ("cat", "aux_w")} |
+                    {"w:" + k: net.get(k) for k in ("aux_w", "input_w", "cat_w")})
+        assert net.tensor_index("aux") == 2  # right after input (0) and label (1), as upstream
+        net.close()
+    for k in outs[1]:
+        assert_close(outs[0][k], outs[1][k], 2e-5, f"two-input net {k}")
