@@ -95,6 +95,9 @@ def bind_bcnn_api(lib: C.CDLL, tensor_type) -> None:
         "bcnn_train_on_batch": (f, [vp]),
         "bcnn_predict_on_batch": (f, [vp, C.POINTER(C.POINTER(tensor_type))]),
         "bcnn_add_input": (i, [vp, i, i, i, s]),
+        "bcnn_load_net": (i, [vp, s, s]),
+        "bcnn_add_yolo_layer": (i, [vp, i, i, i, i, C.POINTER(C.c_int), C.POINTER(C.c_float), s, s]),
+        "bcnn_get_batch_size": (i, [vp]),
         "bcnn_load_weights": (i, [vp, s]),
         "bcnn_save_weights": (i, [vp, s]),
         # internal but exported by both libraries (reference src/bcnn_net.h:75)
@@ -277,6 +280,36 @@ class Net:
         self.lib.bcnn_set_adam_optimizer(self.handle, lr, beta1, beta2)
         self.lib.bcnn_set_weight_regularizer(self.handle, decay)
         self.set_param("optimizer", "adam")
+
+    def load_net(self, cfg_path, model_path=None) -> int:
+        """bcnn_load_net: build the graph from a .cfg / .conf file (Darknet dialect when the model
+        is a *.weights file) and load the model. Returns the bcnn_status."""
+        model = _b(str(model_path)) if model_path is not None else None
+        return int(self.lib.bcnn_load_net(self.handle, _b(str(cfg_path)), model))
+
+    def yolo(self, mask, anchors, classes, src, dst, coords=4):
+        m = (C.c_int * len(mask))(*mask)
+        a = (C.c_float * len(anchors))(*anchors)
+        self._check(self.lib.bcnn_add_yolo_layer(self.handle, len(mask), classes, coords,
+                                                 len(anchors) // 2, m, a, _b(src), _b(dst)),
+                    f"yolo {dst}")
+
+    def structure(self) -> dict:
+        """Graph as plain data: nodes [type, src indices, dst indices], tensors [name, n, c, h, w]."""
+        lib, h = self.lib, self.handle
+        nodes = []
+        for i in range(lib.bcnn_b200_num_nodes(h)):
+            src, dst = [], []
+            while lib.bcnn_b200_node_src(h, i, len(src)) >= 0:
+                src.append(lib.bcnn_b200_node_src(h, i, len(src)))
+            while lib.bcnn_b200_node_dst(h, i, len(dst)) >= 0:
+                dst.append(lib.bcnn_b200_node_dst(h, i, len(dst)))
+            nodes.append([lib.bcnn_b200_node_type(h, i), src, dst])
+        tensors = []
+        for i in range(lib.bcnn_b200_num_tensors(h)):
+            t = self._tensor(i)
+            tensors.append([t.name.decode(), t.n, t.c, t.h, t.w])
+        return dict(nodes=nodes, tensors=tensors, batch=int(lib.bcnn_get_batch_size(h)))
 
     def save_weights(self, path) -> None:
         self._check(self.lib.bcnn_save_weights(self.handle, _b(str(path))), "bcnn_save_weights")

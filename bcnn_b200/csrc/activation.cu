@@ -445,6 +445,36 @@ extern "C" int bcnn_b200_concat_backward(const float *dst_grad, float *src_grad,
                              accumulate != 0, as_stream(stream));
 }
 
+// YOLOv3 head, inference part of bcnn_forward_yolo_layer_cpu (src/layers/bcnn_yolo.c:226-250):
+// y = x with the logistic function on the box-centre offsets (entries 0, 1) and on objectness +
+// class scores (entries coords ..) of every anchor group; the size entries pass through. The
+// reference does this on the host after a D2H copy of the head (:418-431); here it is one pass
+// over the tensor on the device (8 B / element).
+__global__ void __launch_bounds__(256)
+yolo_activate_kernel(const float *__restrict__ x, float *__restrict__ y, size_t total, FastDiv d_hw,
+                     FastDiv d_group, int coords) {
+    const size_t gstride = (size_t)gridDim.x * 256;
+    for (size_t o = (size_t)blockIdx.x * 256 + threadIdx.x; o < total; o += gstride) {
+        uint32_t plane, pos, grp, entry;
+        d_hw.divmod((uint32_t)o, plane, pos);     // plane = batch * channels + channel
+        d_group.divmod(plane, grp, entry);        // channels is a multiple of the group size
+        float v = __ldg(x + o);
+        if (entry < 2u || entry >= (uint32_t)coords) v = act_fwd(v, ACT_LOGISTIC, 0.f);
+        y[o] = v;
+    }
+}
+
+extern "C" int bcnn_b200_yolo_activate(const float *x, float *y, int n, int boxes_per_cell,
+                                       int classes, int coords, int hw, void *stream) {
+    const size_t group = (size_t)coords + classes + 1;
+    const size_t total = (size_t)n * boxes_per_cell * group * hw;
+    if (total == 0) return 0;
+    if (coords < 2 || total >= (1ull << 32)) return (int)cudaErrorInvalidValue;
+    yolo_activate_kernel<<<stream_grid(total, 256), 256, 0, as_stream(stream)>>>(
+        x, y, total, FastDiv((uint32_t)hw), FastDiv((uint32_t)group), coords);
+    return launched();
+}
+
 extern "C" int bcnn_b200_upsample_forward(const float *x, float *y, int n, int c, int h, int w, int size,
                                           void *stream) {
     const size_t total = (size_t)n * c * h * w * size * size;

@@ -157,15 +157,31 @@ void bcnn_set_weight_regularizer(bcnn_net *net, float weight_decay) {
     learner_of(net)->decay = weight_decay;
 }
 
-/* The learner keys of the reference's bcnn_net_set_param (src/bcnn_net.c:506-553), looked up in
- * tables; like the reference, keys are ignored while the net has no learner (PREDICT). */
+/* The shape and learner keys of the reference's bcnn_net_set_param (src/bcnn_net.c:506-553);
+ * like the reference, solver keys are ignored while the net has no learner (PREDICT) and the
+ * data-augmentation keys (no loader here) always. */
 void bcnn_net_set_param(bcnn_net *net, const char *name, const char *val) {
     static const struct { const char *text; bcnn_lr_decay decay; } policies[] = {
         {"sigmoid", BCNN_LR_DECAY_SIGMOID}, {"constant", BCNN_LR_DECAY_CONSTANT},
         {"exp", BCNN_LR_DECAY_EXP},         {"inv", BCNN_LR_DECAY_INV},
         {"step", BCNN_LR_DECAY_STEP},       {"poly", BCNN_LR_DECAY_POLY}};
-    bcnn_learner *ln = net ? net->learner : NULL;
-    if (!ln || !name || !val) return;
+    if (!net || !name || !val) return;
+    /* input shape and batch (:507-518); these do not need a learner */
+    if (!strcmp(name, "input_width") || !strcmp(name, "width")) {
+        net->tensors[0].w = atoi(val);
+        return;
+    } else if (!strcmp(name, "input_height") || !strcmp(name, "height")) {
+        net->tensors[0].h = atoi(val);
+        return;
+    } else if (!strcmp(name, "input_channels") || !strcmp(name, "channels")) {
+        net->tensors[0].c = atoi(val);
+        return;
+    } else if (!strcmp(name, "batch_size") || !strcmp(name, "batch")) {
+        net->batch_size = net->tensors[0].n = atoi(val);
+        return;
+    }
+    bcnn_learner *ln = net->learner;
+    if (!ln) return;
     if (!strcmp(name, "learning_policy") || !strcmp(name, "decay_type")) {
         ln->decay_type = BCNN_LR_DECAY_CONSTANT; /* unknown text falls back to constant */
         for (size_t i = 0; i < sizeof(policies) / sizeof(policies[0]); ++i)

@@ -144,6 +144,12 @@ BCNN_API void bcnn_set_weight_regularizer(bcnn_net *net, float weight_decay);
  * bcnn_load_weights reads .bcnnmodel and Darknet *.weights files; in BCNN_MODE_PREDICT it
  * folds the batch-norm running statistics into scales / bias as the reference's CPU build
  * does. A truncated file returns BCNN_INVALID_MODEL (the reference logs and returns success). */
+/* Build the net from a .cfg / .conf file (bcnn dialect, or Darknet when model_path ends in
+ * .weights), then load model_path if given (reference inc/bcnn/bcnn.h:437,
+ * src/bcnn_net.c:1114-1218). Sections for layers this path does not have ([deconv], [lrn],
+ * [dropout]) fail with BCNN_INVALID_PARAMETER. */
+BCNN_API bcnn_status bcnn_load_net(bcnn_net *net, const char *config_path,
+                                   const char *model_path);
 BCNN_API bcnn_status bcnn_load_weights(bcnn_net *net, const char *model_path);
 BCNN_API bcnn_status bcnn_save_weights(bcnn_net *net, const char *filename);
 
@@ -198,6 +204,13 @@ BCNN_API bcnn_status bcnn_add_concat_layer(bcnn_net *net, int num_src, char *con
                                            const char *dst_id);
 BCNN_API bcnn_status bcnn_add_upsample_layer(bcnn_net *net, int size, const char *src_id,
                                              const char *dst_id);
+/* YOLOv3 output layer (reference inc/bcnn/bcnn.h:1039, src/layers/bcnn_yolo.c:15-107).
+ * PREDICT / VALID: the head activation runs on the device. The detection loss of TRAIN mode is
+ * host code in the reference even in its CUDA build (:418-431) and is not part of this path:
+ * the constructor returns BCNN_INVALID_PARAMETER for a TRAIN-mode net. */
+BCNN_API bcnn_status bcnn_add_yolo_layer(bcnn_net *net, int num_boxes_per_cell, int classes,
+                                         int coords, int total, int *mask, float *anchors,
+                                         const char *src_id, const char *dst_id);
 BCNN_API bcnn_status bcnn_add_cost_layer(bcnn_net *net, bcnn_loss loss,
                                          bcnn_loss_metric loss_metric, float scale,
                                          const char *src_id, const char *label_id,

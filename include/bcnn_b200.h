@@ -326,6 +326,12 @@ BCNN_B200_API int bcnn_b200_concat_forward(const float *src, float *dst, int n, 
 BCNN_B200_API int bcnn_b200_concat_backward(const float *dst_grad, float *src_grad, int n,
                                             int src_sz, int dst_sz, int dst_offset,
                                             int accumulate, void *stream);
+/* YOLOv3 head activation, the inference part of bcnn_forward_yolo_layer_cpu
+ * (src/layers/bcnn_yolo.c:226-250): x, y are [n, boxes_per_cell * (coords + classes + 1), hw];
+ * per anchor group the logistic function is applied to entries 0, 1 (centre offsets) and
+ * coords .. coords + classes (objectness, class scores); entries 2 .. coords-1 are copied. */
+BCNN_B200_API int bcnn_b200_yolo_activate(const float *x, float *y, int n, int boxes_per_cell,
+                                          int classes, int coords, int hw, void *stream);
 /* y[n, c, j, i] = x[n, c, j / size, i / size]   (src/layers/bcnn_upsample_layer.c:86-109;
  * replaces bcnn_cuda_upsample_kernel, bcnn_upsample_layer.cu). */
 BCNN_B200_API int bcnn_b200_upsample_forward(const float *x, float *y, int n, int c, int h,

@@ -32,8 +32,9 @@ BCNN_B200_API void bcnn_b200_set_reference_quirks(bcnn_net *net, int on);
  * same name and meaning here). Keys: max_batches, learning_policy | decay_type
  * (sigmoid|constant|exp|inv|step|poly), optimizer (sgd|adam), step, learning_rate, beta1,
  * beta2, decay, momentum, gamma. This is the only way to reach Adam, in the reference too:
- * bcnn_set_adam_optimizer never switches the optimizer. Shape keys and
- * augmentation keys are the cfg parser's business and are ignored. */
+ * bcnn_set_adam_optimizer never switches the optimizer. Also the shape keys
+ * input_width | width, input_height | height, input_channels | channels, batch_size | batch.
+ * Augmentation keys belong to the file loader and are ignored. */
 BCNN_B200_API void bcnn_net_set_param(bcnn_net *net, const char *name, const char *val);
 /* The CUDA stream (cudaStream_t) every kernel of this net is launched on. */
 BCNN_B200_API void *bcnn_b200_get_stream(bcnn_net *net);

@@ -600,6 +600,21 @@ void orc_adam_update(float *w, float *b, float *gw, float *gb, float *m, float *
     }
 }
 
+/* Inference part of bcnn_forward_yolo_layer_cpu, src/layers/bcnn_yolo.c:226-250: copy, then per
+ * sample and anchor group the logistic function (bcnn_activation_layer.c: 1/(1+exp(-x)), exp in
+ * double) on entries 0..1 and coords..coords+classes; entry_index of :207-215 spelled out. */
+void orc_yolo_forward(const float *x, float *y, int n, int num, int classes, int coords, int hw) {
+    int group = coords + classes + 1, chw = num * group * hw;
+    memcpy(y, x, (size_t)n * chw * sizeof(float));
+    for (int b = 0; b < n; ++b)
+        for (int a = 0; a < num; ++a) {
+            float *p = y + (size_t)b * chw + (size_t)a * hw * group;
+            for (int i = 0; i < 2 * hw; ++i) p[i] = 1.0f / (1.0f + (float)exp(-p[i]));
+            p += (size_t)coords * hw;
+            for (int i = 0; i < (1 + classes) * hw; ++i) p[i] = 1.0f / (1.0f + (float)exp(-p[i]));
+        }
+}
+
 /* ------------------------------------------------------------------ */
 /* Glue: fc, softmax, eltwise                                           */
 /* ------------------------------------------------------------------ */

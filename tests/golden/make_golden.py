@@ -4,6 +4,7 @@ public API on the seeded synthetic cases of tests/netcases.py.
 
     python tests/golden/make_golden.py [case ...]     (default: every case of netcases.CASES)
     python tests/golden/make_golden.py model_io       (weight-file fixtures, see make_model_io)
+    python tests/golden/make_golden.py cfg            (config-file fixtures, see make_cfg)
 
 The reference ships no golden vectors of its own, so these files are
 the pin: they record what the reference computes, never hand-edited. Large tensors are
@@ -89,7 +90,64 @@ def make_model_io():
           f"{(GOLDEN / 'model_io.weights').stat().st_size} file bytes")
 
 
+def make_cfg():
+    """Config-file fixtures under tests/golden/cfg/ (the two cfg files are hand-written test
+    inputs; everything else is what the reference makes of them):
+      mini_bcnn.json / mini_yolo.json  graph built by the reference's bcnn_load_net
+                                       (capi.Net.structure: node types, src / dst indices,
+                                       tensor names and shapes, batch size)
+      mini_yolo.weights                Darknet weights for mini_yolo.cfg, seeded values written by
+                                       the numpy restatement in the order the reference reads
+      mini_yolo.npz                    input and the tensors of one PREDICT forward of the
+                                       reference after bcnn_load_net(cfg, weights)."""
+    import json
+    sys.path.insert(0, str(ROOT / "oracle"))
+    import bcnn_model_oracle as mo
+    from bcnn_b200 import capi, configs
+    cfg_dir = GOLDEN / "cfg"
+    weights = cfg_dir / "mini_yolo.weights"
+
+    net = ref_net(mode=capi.MODE_TRAIN, threads=1)
+    assert net.load_net(cfg_dir / "mini_bcnn.conf") == 0
+    (cfg_dir / "mini_bcnn.json").write_text(json.dumps(net.structure()))
+    net.close()
+
+    # the layout comes from a graph-only load (a model path that does not exist yet selects the
+    # Darknet dialect and fails after the graph is built)
+    probe = ref_net(mode=capi.MODE_PREDICT, threads=1)
+    if weights.exists():
+        weights.unlink()
+    assert probe.load_net(cfg_dir / "mini_yolo.cfg", weights) == 1
+    layout = mo.net_layout(probe)
+    rng = np.random.default_rng(17)
+    span = {"weights": (-0.25, 0.25), "bias": (-0.1, 0.1), "scales": (0.5, 1.5),
+            "mean": (-0.2, 0.2), "var": (0.5, 1.5), "slopes": (0.05, 0.3)}
+    values = {}
+    for node in layout:
+        for role, (name, size) in node.roles.items():
+            lo, hi = span[role]
+            values[name] = rng.uniform(lo, hi, size=size).astype(np.float32)
+    mo.write_darknet(weights, layout, values, major=0, minor=2, seen=12800)
+    probe.close()
+
+    net = ref_net(mode=capi.MODE_PREDICT, threads=1)
+    assert net.load_net(cfg_dir / "mini_yolo.cfg", weights) == 0
+    (cfg_dir / "mini_yolo.json").write_text(json.dumps(net.structure()))
+    net.compile()
+    x = configs.synth_input(net.shape("input"), seed=23)
+    net.set("input", x)
+    net.forward()
+    packed = {"input": x}
+    for name in ("lid1", "lid7", "lid9", "lid10", "lid14", "lid16", "lid17"):
+        packed[name] = net.get(name)
+    np.savez_compressed(cfg_dir / "mini_yolo.npz", **packed)
+    net.close()
+    print("cfg:", sorted(p.name for p in cfg_dir.iterdir()))
+
+
 def main():
+    if sys.argv[1:] == ["cfg"]:
+        return make_cfg()
     if sys.argv[1:] == ["model_io"]:
         return make_model_io()
     from bcnn_b200 import configs

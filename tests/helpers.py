@@ -74,6 +74,7 @@ def oracle() -> C.CDLL:
         "orc_depthwise_backward": (None, [vp, vp, vp, vp, vp] + [i] * 7),
         "orc_sgd_update": (None, [vp, vp, vp, vp, i, i, i, f, f, f]),
         "orc_adam_update": (None, [vp] * 6 + [i] * 4 + [f] * 5),
+        "orc_yolo_forward": (None, [vp, vp, i, i, i, i, i]),
         "orc_fc_forward": (None, [vp, vp, vp, vp, i, i, i, i]),
         "orc_fc_backward": (None, [vp, vp, vp, vp, vp, vp, i, i, i]),
         "orc_softmax_forward": (None, [vp, vp, i, i, i]),

@@ -1,4 +1,4 @@
-"""Development aid: run the kernel-free GPU-marked tests (weight files) against the host stub.
+"""Development aid: run the kernel-free GPU-marked tests (weight files, config files) against the host stub.
 Usage: python tools/hoststub/run_host_tests.py [extra pytest args]"""
 import ctypes as C
 import sys
@@ -14,6 +14,8 @@ stub = C.CDLL(str(Path(__file__).parent / "libbcnn_hoststub.so"), mode=C.RTLD_LO
 capi.bind_bcnn_api(stub, capi.TensorB200)
 capi.bind_b200_ext(stub)
 capi._B200 = stub
-sys.exit(pytest.main([str(ROOT / "tests" / "test_model_io.py"), "-q", "-m", "gpu", "-k",
-                      "layout or save_writes or load_train or darknet or error_statuses",
+sys.exit(pytest.main([str(ROOT / "tests" / "test_model_io.py"), str(ROOT / "tests" / "test_cfg.py"),
+                      "-q", "-m", "gpu", "-k",
+                      "layout or save_writes or load_train or load_darknet or error_statuses or "
+                      "darknet_dialect_builds or refuses_train",
                       *sys.argv[1:]]))
