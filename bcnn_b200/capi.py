@@ -40,6 +40,12 @@ class TensorB200(C.Structure):
                 ("data_gpu", C.c_void_p), ("grad_data_gpu", C.c_void_p)]
 
 
+class Detection(C.Structure):  # bcnn_output_detection
+    _fields_ = [("num_classes", C.c_int), ("x", C.c_float), ("y", C.c_float), ("w", C.c_float),
+                ("h", C.c_float), ("prob", C.POINTER(C.c_float)), ("mask", C.POINTER(C.c_float)),
+                ("objectness", C.c_float)]
+
+
 class TensorCPU(C.Structure):  # reference built without BCNN_USE_CUDA
     _fields_ = [("n", C.c_int), ("c", C.c_int), ("h", C.c_int), ("w", C.c_int),
                 ("has_grad", C.c_int), ("name", C.c_char_p),
@@ -96,6 +102,7 @@ def bind_bcnn_api(lib: C.CDLL, tensor_type) -> None:
         "bcnn_predict_on_batch": (f, [vp, C.POINTER(C.POINTER(tensor_type))]),
         "bcnn_add_input": (i, [vp, i, i, i, s]),
         "bcnn_load_net": (i, [vp, s, s]),
+        "bcnn_yolo_get_detections": (C.POINTER(Detection), [vp, i, i, i, i, i, f, i, C.POINTER(C.c_int)]),
         "bcnn_add_yolo_layer": (i, [vp, i, i, i, i, C.POINTER(C.c_int), C.POINTER(C.c_float), s, s]),
         "bcnn_get_batch_size": (i, [vp]),
         "bcnn_load_weights": (i, [vp, s]),
@@ -293,6 +300,28 @@ class Net:
         self._check(self.lib.bcnn_add_yolo_layer(self.handle, len(mask), classes, coords,
                                                  len(anchors) // 2, m, a, _b(src), _b(dst)),
                     f"yolo {dst}")
+
+    def yolo_detections(self, batch, width, height, thresh, relative=True) -> np.ndarray:
+        """bcnn_yolo_get_detections as an array [num_dets, 5 + classes]: x, y, w, h, objectness,
+        class probabilities (rows in the order the library returns them)."""
+        count = C.c_int(0)
+        _, _, net_h, net_w = self.shape("input")
+        dets = self.lib.bcnn_yolo_get_detections(self.handle, batch, width, height, net_w, net_h,
+                                                 thresh, int(relative), C.byref(count))
+        rows = []
+        libc = C.CDLL(None)
+        libc.free.argtypes = [C.c_void_p]
+        for k in range(count.value):
+            d = dets[k]
+            rows.append([d.x, d.y, d.w, d.h, d.objectness] + [d.prob[j] for j in range(d.num_classes)])
+            libc.free(C.cast(d.prob, C.c_void_p))
+            if d.mask:
+                libc.free(C.cast(d.mask, C.c_void_p))
+        if count.value:
+            libc.free(C.cast(dets, C.c_void_p))
+        if not rows:
+            return np.zeros((0, 5), np.float32)
+        return np.array(rows, dtype=np.float32).reshape(count.value, -1)
 
     def structure(self) -> dict:
         """Graph as plain data: nodes [type, src indices, dst indices], tensors [name, n, c, h, w]."""

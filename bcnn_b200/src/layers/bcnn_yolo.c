@@ -7,10 +7,13 @@
  * class scores) is one device kernel here; the reference copies the head to the host for it even
  * in its CUDA build (:418-431). The TRAIN-mode detection loss (:251-416) is host code in the
  * reference and outside this path: a TRAIN-mode net refuses the layer instead of
- * silently training without a loss. Box decoding / NMS (bcnn_yolo_get_detections, :470-639) is
- * the caller's post-processing and is not provided.
+ * silently training without a loss. bcnn_yolo_get_detections (:470-639: box decoding, letterbox
+ * correction, objectness NMS) is host post-processing in the reference and is host code here
+ * too, on the heads' host mirrors after one D2H refresh per head.
  */
 #include "bcnn_yolo.h"
+
+#include <math.h>
 
 #include "bcnn_tensor.h"
 
@@ -98,4 +101,136 @@ void bcnn_release_param_yolo_layer(bcnn_node *node) {
     free(param->cost);
     free(param->mask);
     bcnn_tensor_destroy(&param->biases);
+}
+
+/* ---- detections: host post-processing, semantics of reference :470-639 ---- */
+typedef struct { float x, y, w, h; } yolo_box;
+
+static float span_overlap(float c1, float e1, float c2, float e2) {
+    const float lo1 = c1 - e1 / 2, lo2 = c2 - e2 / 2, hi1 = c1 + e1 / 2, hi2 = c2 + e2 / 2;
+    return (hi1 < hi2 ? hi1 : hi2) - (lo1 > lo2 ? lo1 : lo2);
+}
+
+static float yolo_iou(yolo_box a, yolo_box b) {
+    const float w = span_overlap(a.x, a.w, b.x, b.w), h = span_overlap(a.y, a.h, b.y, b.h);
+    const float inter = (w < 0 || h < 0) ? 0 : w * h;
+    const float uni = a.w * a.h + b.w * b.h - inter;
+    return inter / uni;
+}
+
+static int by_objectness_desc(const void *pa, const void *pb) {
+    const float diff = ((const bcnn_output_detection *)pa)->objectness -
+                       ((const bcnn_output_detection *)pb)->objectness;
+    return diff < 0 ? 1 : (diff > 0 ? -1 : 0);
+}
+
+/* Visit every (cell, anchor) of every yolo head whose objectness exceeds `thresh`, in the
+ * reference's order (heads in node order, cells row-major, anchors innermost). With dets == NULL
+ * it only counts. */
+static int yolo_collect(bcnn_net *net, int batch, float thresh, bcnn_output_detection *dets) {
+    int count = 0;
+    for (int k = 0; k < net->num_nodes; ++k) {
+        if (net->nodes[k].type != BCNN_LAYER_YOLOV3) continue;
+        const bcnn_yolo_param *param = (const bcnn_yolo_param *)net->nodes[k].param;
+        const bcnn_tensor *dst = &net->tensors[net->nodes[k].dst[0]];
+        const int hw = dst->w * dst->h, group = param->coords + param->classes + 1;
+        const float *head = dst->data + (size_t)batch * dst->c * hw;
+        for (int cell = 0; cell < hw; ++cell)
+            for (int a = 0; a < param->num; ++a) {
+                const float *entry = head + (size_t)a * group * hw + cell; /* stride hw per entry */
+                const float objectness = entry[(size_t)param->coords * hw];
+                if (!(objectness > thresh)) continue;
+                if (dets) {
+                    bcnn_output_detection *d = &dets[count];
+                    const int col = cell % dst->w, row = cell / dst->w, anchor = param->mask[a];
+                    d->x = (col + entry[0]) / dst->w;
+                    d->y = (row + entry[hw]) / dst->h;
+                    d->w = expf(entry[2 * (size_t)hw]) * param->biases.data[2 * anchor] /
+                           net->tensors[0].w;
+                    d->h = expf(entry[3 * (size_t)hw]) * param->biases.data[2 * anchor + 1] /
+                           net->tensors[0].h;
+                    d->objectness = objectness;
+                    d->num_classes = param->classes;
+                    for (int j = 0; j < param->classes; ++j) {
+                        const float prob = objectness * entry[(size_t)(param->coords + 1 + j) * hw];
+                        d->prob[j] = prob > thresh ? prob : 0;
+                    }
+                }
+                ++count;
+            }
+    }
+    return count;
+}
+
+bcnn_output_detection *bcnn_yolo_get_detections(bcnn_net *net, int batch, int w, int h, int netw,
+                                                int neth, float thresh, int relative,
+                                                int *num_dets) {
+    *num_dets = 0;
+    int num_classes = 0, max_classes = 0, extra_coords = 0;
+    for (int k = 0; k < net->num_nodes; ++k) { /* one D2H refresh per head */
+        if (net->nodes[k].type != BCNN_LAYER_YOLOV3) continue;
+        const bcnn_yolo_param *param = (const bcnn_yolo_param *)net->nodes[k].param;
+        if (!bcnn_get_tensor_by_index(net, net->nodes[k].dst[0])) return NULL;
+        if (batch < 0 || batch >= net->tensors[net->nodes[k].dst[0]].n) return NULL;
+        num_classes = param->classes; /* the last head's, as the reference */
+        if (param->classes > max_classes) max_classes = param->classes;
+        if (param->coords - 4 > extra_coords) extra_coords = param->coords - 4;
+    }
+    const int count = yolo_collect(net, batch, thresh, NULL);
+    if (count == 0) return NULL;
+    bcnn_output_detection *dets =
+        (bcnn_output_detection *)calloc((size_t)count, sizeof(bcnn_output_detection));
+    if (!dets) return NULL;
+    for (int i = 0; i < count; ++i) { /* owned by the caller, released with free() */
+        dets[i].prob = (float *)calloc((size_t)(max_classes > 0 ? max_classes : 1), sizeof(float));
+        if (extra_coords > 0) dets[i].mask = (float *)calloc((size_t)extra_coords, sizeof(float));
+    }
+    yolo_collect(net, batch, thresh, dets);
+
+    /* undo the letterbox the image was fitted into the net input with (:470-496) */
+    int new_w, new_h;
+    if (((float)netw / w) < ((float)neth / h)) {
+        new_w = netw;
+        new_h = (h * netw) / w;
+    } else {
+        new_h = neth;
+        new_w = (w * neth) / h;
+    }
+    for (int i = 0; i < count; ++i) {
+        dets[i].x = (dets[i].x - (netw - new_w) / 2. / netw) / ((float)new_w / netw);
+        dets[i].y = (dets[i].y - (neth - new_h) / 2. / neth) / ((float)new_h / neth);
+        dets[i].w *= (float)netw / new_w;
+        dets[i].h *= (float)neth / new_h;
+        if (!relative) {
+            dets[i].x *= w;
+            dets[i].w *= w;
+            dets[i].y *= h;
+            dets[i].h *= h;
+        }
+    }
+
+    /* greedy NMS on objectness at IoU 0.45 (:511-546); suppressed boxes keep their slot with
+     * objectness and class scores zeroed */
+    int live = count; /* boxes with zero objectness (possible for thresh < 0) go to the back */
+    for (int i = 0; i < live; ++i)
+        if (dets[i].objectness == 0) {
+            const bcnn_output_detection tmp = dets[i];
+            dets[i--] = dets[--live];
+            dets[live] = tmp;
+        }
+    qsort(dets, (size_t)live, sizeof(bcnn_output_detection), by_objectness_desc);
+    for (int i = 0; i < live; ++i) {
+        if (dets[i].objectness == 0) continue;
+        const yolo_box a = {dets[i].x, dets[i].y, dets[i].w, dets[i].h};
+        for (int j = i + 1; j < live; ++j) {
+            if (dets[j].objectness == 0) continue;
+            const yolo_box b = {dets[j].x, dets[j].y, dets[j].w, dets[j].h};
+            if (yolo_iou(a, b) > 0.45f) {
+                dets[j].objectness = 0;
+                for (int c = 0; c < num_classes; ++c) dets[j].prob[c] = 0;
+            }
+        }
+    }
+    *num_dets = count;
+    return dets;
 }

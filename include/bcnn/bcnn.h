@@ -101,6 +101,15 @@ typedef enum bcnn_filler_type {
 
 typedef void (*bcnn_log_callback)(const char *fmt, ...);
 
+/* One detection of bcnn_yolo_get_detections (reference inc/bcnn/bcnn.h:260-266). */
+typedef struct bcnn_output_detection {
+    int num_classes;
+    float x, y, w, h;
+    float *prob;
+    float *mask;
+    float objectness;
+} bcnn_output_detection;
+
 /* NCHW float32 tensor. Element count is an int (< 2^31). */
 struct bcnn_tensor {
     int n, c, h, w;
@@ -211,6 +220,14 @@ BCNN_API bcnn_status bcnn_add_upsample_layer(bcnn_net *net, int size, const char
 BCNN_API bcnn_status bcnn_add_yolo_layer(bcnn_net *net, int num_boxes_per_cell, int classes,
                                          int coords, int total, int *mask, float *anchors,
                                          const char *src_id, const char *dst_id);
+/* Boxes above `thresh` of sample `batch` from every yolo head, letterbox-corrected for a
+ * width x height image and NMS-filtered (reference inc/bcnn/bcnn.h:718, src/layers/bcnn_yolo.c:
+ * 548-639). Host post-processing after one device -> host copy per head. The caller frees
+ * dets[i].prob, dets[i].mask and the array. NULL and *num_dets = 0 when nothing passes. */
+BCNN_API bcnn_output_detection *bcnn_yolo_get_detections(bcnn_net *net, int batch, int width,
+                                                         int height, int netw, int neth,
+                                                         float thresh, int relative,
+                                                         int *num_dets);
 BCNN_API bcnn_status bcnn_add_cost_layer(bcnn_net *net, bcnn_loss loss,
                                          bcnn_loss_metric loss_metric, float scale,
                                          const char *src_id, const char *label_id,

@@ -99,7 +99,9 @@ def make_cfg():
       mini_yolo.weights                Darknet weights for mini_yolo.cfg, seeded values written by
                                        the numpy restatement in the order the reference reads
       mini_yolo.npz                    input and the tensors of one PREDICT forward of the
-                                       reference after bcnn_load_net(cfg, weights)."""
+                                       reference after bcnn_load_net(cfg, weights), and its
+                                       bcnn_yolo_get_detections per sample (thresh 0.5, 640x480
+                                       frame, relative) as [num_dets, x y w h objectness p0 p1]."""
     import json
     sys.path.insert(0, str(ROOT / "oracle"))
     import bcnn_model_oracle as mo
@@ -140,6 +142,8 @@ def make_cfg():
     packed = {"input": x}
     for name in ("lid1", "lid7", "lid9", "lid10", "lid14", "lid16", "lid17"):
         packed[name] = net.get(name)
+    for b in range(2):  # bcnn_yolo_get_detections of a 640x480 frame (chatty on stderr)
+        packed[f"dets_b{b}"] = net.yolo_detections(b, 640, 480, 0.5, relative=True)
     np.savez_compressed(cfg_dir / "mini_yolo.npz", **packed)
     net.close()
     print("cfg:", sorted(p.name for p in cfg_dir.iterdir()))
