@@ -551,6 +551,7 @@ def bind_kernel_abi(lib: C.CDLL) -> None:
         "bcnn_b200_depthwise_scratch_floats": (sz, [i, i, i]),
         "bcnn_b200_sgd_update": (i, [vp, vp, sz, f, f, f, vp]),
         "bcnn_b200_adam_update": (i, [vp, vp, vp, vp, sz, f, f, f, f, vp]),
+        "bcnn_b200_yolo_activate": (i, [vp, vp, i, i, i, i, i, vp]),
         "bcnn_b200_softmax_forward": (i, [vp, vp, i, i, i, vp]),
         "bcnn_b200_cost_forward": (i, [vp, vp, vp, vp, i, i, i, vp]),
         "bcnn_b200_eltwise_forward": (i, [vp, vp, vp, i, i, i, vp]),
