@@ -83,8 +83,8 @@ def mobilenet(net, batch=1, res=224, classes=1000):
 def yolo_tiny(net, batch=1, res=416):
     """YOLOv3-tiny (examples/yolo/yolov3-tiny.cfg) with both heads: trunk, coarse head at res/32,
     route -> 1x1 conv -> upsample x2 -> concat with the 256-channel trunk tensor at res/16 -> fine
-    head. The yolo loss layers stay out of scope (host-side in the reference): for
-    training the fine head carries a euclidean cost, the coarse head's output has no consumer and
+    head. PREDICT nets end in the two yolo layers; the yolo loss stays out of scope (SURVEY.md 8f:
+    host-side in the reference): for training the fine head carries a euclidean cost, the coarse head's output has no consumer and
     so receives a zero gradient (its convolutions still run forward and backward)."""
     net.set_input_shape(res, res, 3, batch)
     prev = "input"
@@ -104,7 +104,13 @@ def yolo_tiny(net, batch=1, res=416):
     if net.mode != capi.MODE_PREDICT:
         net.cost("head", "cost", metric=capi.METRIC_SSE)
         net.sgd(0.001, 0.9, 0.0005)
-    return dict(classes=None, out="head")
+        return dict(classes=None, out="head")
+    # inference: the two [yolo] layers of the cfg (80 classes, 6 anchors, masks 3-5 and 0-2);
+    # the fine one is added last, as in the cfg, so bcnn_predict_on_batch returns it
+    anchors = [10, 14, 23, 27, 37, 58, 81, 82, 135, 169, 344, 319]
+    net.yolo([3, 4, 5], anchors, 80, "head1", "yolo1")
+    net.yolo([0, 1, 2], anchors, 80, "head", "yolo2")
+    return dict(classes=None, out="yolo2")
 
 
 def resnet50(net, batch=256, res=224, classes=1000, widths=(64, 128, 256, 512),
