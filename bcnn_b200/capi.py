@@ -123,6 +123,8 @@ def bind_b200_ext(lib: C.CDLL) -> None:
         "bcnn_b200_set_conv_math": (None, [vp, i]),
         "bcnn_b200_get_conv_math": (i, [vp]),
         "bcnn_b200_set_reference_quirks": (None, [vp, i]),
+        "bcnn_b200_set_graphs": (None, [vp, i]),
+        "bcnn_b200_get_graphs": (i, [vp]),
         "bcnn_b200_get_stream": (vp, [vp]),
         "bcnn_b200_sync": (None, [vp]),
         "bcnn_b200_upload_tensor": (i, [vp, i]),
@@ -438,6 +440,13 @@ class Net:
     # -- B200-only helpers --
     def set_conv_math(self, math: int):
         self.lib.bcnn_b200_set_conv_math(self.handle, math)
+
+    def set_graphs(self, on: bool):
+        self.lib.bcnn_b200_set_graphs(self.handle, int(on))
+
+    def graphs(self) -> int:
+        """0 = off, 1 = on, 2 = on and the forward graph is live."""
+        return int(self.lib.bcnn_b200_get_graphs(self.handle))
 
     def set_reference_quirks(self, on: bool):
         self.lib.bcnn_b200_set_reference_quirks(self.handle, int(on))

@@ -99,6 +99,32 @@ float bcnn_b200_event_elapsed_ms(void *a, void *b) {
     cudaEventElapsedTime(&ms, (cudaEvent_t)a, (cudaEvent_t)b);
     return ms;
 }
+// ---- CUDA graphs: capture what a stream is given between begin and end, replay it later ----
+int bcnn_b200_graph_begin(void *s) {
+    return (int)cudaStreamBeginCapture(as_stream(s), cudaStreamCaptureModeThreadLocal);
+}
+// Ends the capture and instantiates the graph. Returns the executable graph, or nullptr when the
+// capture was invalidated or empty (the captured work was NOT executed either way).
+void *bcnn_b200_graph_end(void *s) {
+    cudaGraph_t graph = nullptr;
+    cudaGraphExec_t exec = nullptr;
+    cudaError_t err = cudaStreamEndCapture(as_stream(s), &graph);
+    if (err == cudaSuccess && graph) err = cudaGraphInstantiate(&exec, graph, 0);
+    if (graph) cudaGraphDestroy(graph);
+    if (err != cudaSuccess) {
+        cudaGetLastError();  // clear the sticky capture error: the caller falls back to eager launches
+        return nullptr;
+    }
+    return (void *)exec;
+}
+int bcnn_b200_graph_launch(void *exec, void *s) {
+    ++g_launch_count;
+    return (int)cudaGraphLaunch((cudaGraphExec_t)exec, as_stream(s));
+}
+void bcnn_b200_graph_destroy(void *exec) {
+    if (exec) cudaGraphExecDestroy((cudaGraphExec_t)exec);
+}
+
 const char *bcnn_b200_error_string(int err) { return cudaGetErrorString((cudaError_t)err); }
 
 uint64_t bcnn_b200_launch_count(void) { return (uint64_t)g_launch_count; }

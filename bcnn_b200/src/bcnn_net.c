@@ -16,6 +16,8 @@
 #include "bcnn_tensor.h"
 #include <bcnn_b200_net.h>
 
+static void forward_graph_drop(bcnn_cuda_context *ctx);
+
 bcnn_status bcnn_net_create_cuda_context(bcnn_net *net) {
     bcnn_cuda_context *ctx = (bcnn_cuda_context *)calloc(1, sizeof(bcnn_cuda_context));
     BCNN_CHECK(ctx != NULL, BCNN_FAILED_ALLOC);
@@ -26,6 +28,8 @@ bcnn_status bcnn_net_create_cuda_context(bcnn_net *net) {
         free(ctx);
         return BCNN_CUDA_FAILED_ALLOC;
     }
+    const char *graphs = getenv("BCNN_B200_GRAPHS");
+    ctx->graphs = !(graphs && graphs[0] == '0');
     const char *math = getenv("BCNN_B200_CONV_MATH");
     ctx->conv_math = (math && (math[0] == 't' || math[0] == 'T' || math[0] == '1'))
                          ? BCNN_B200_MATH_TC
@@ -83,6 +87,7 @@ void bcnn_end_net(bcnn_net **net) {
         free(ctx->profile_events);
         free(ctx->grad_fresh);
         free(ctx->consumers);
+        bcnn_b200_graph_destroy(ctx->fwd_graph);
         bcnn_b200_free(ctx->workspace_gpu);
         bcnn_b200_free(ctx->dy_shadow_gpu);
         if (ctx->stage_gpu) {
@@ -138,12 +143,14 @@ int bcnn_get_batch_size(bcnn_net *net) { return net->batch_size; }
 bcnn_status bcnn_set_mode(bcnn_net *net, bcnn_mode mode) {
     /* TRAIN <-> VALID switches are free; gradient buffers exist only if the net was
      * created in TRAIN / VALID mode (as in the reference, bcnn_tensor.c:111). */
+    if (net->mode != mode) forward_graph_drop(bcnn_ctx(net));
     net->mode = mode;
     return BCNN_SUCCESS;
 }
 
 bcnn_status bcnn_compile_net(bcnn_net *net) {
     bcnn_cuda_context *ctx = bcnn_ctx(net);
+    forward_graph_drop(ctx); /* buffers are reallocated below */
     /* (re)allocate the input tensor, with an eager pinned host mirror the caller fills */
     BCNN_CHECK_STATUS(bcnn_tensor_allocate(&net->tensors[0], net->mode));
     BCNN_CHECK_STATUS(bcnn_tensor_ensure_host(&net->tensors[0]));
@@ -247,8 +254,7 @@ static inline void profile_mark(bcnn_net *net, int node, int slot) {
         bcnn_cuda_check(bcnn_b200_event_record(ctx->profile_events[4 * node + slot], ctx->stream));
 }
 
-void bcnn_forward(bcnn_net *net) {
-    grad_state_sync(net);
+static void forward_nodes(bcnn_net *net) {
     for (int i = 0; i < net->num_nodes; ++i) {
         bcnn_node *node = &net->nodes[i];
         profile_mark(net, i, 0);
@@ -256,6 +262,67 @@ void bcnn_forward(bcnn_net *net) {
         node->forward(net, node);
         profile_mark(net, i, 1);
     }
+}
+
+static void forward_graph_drop(bcnn_cuda_context *ctx) {
+    bcnn_b200_graph_destroy(ctx->fwd_graph);
+    ctx->fwd_graph = NULL;
+    ctx->fwd_graph_warm = 0;
+}
+
+/* PREDICT-mode forward through a CUDA graph; see bcnn_cuda_context.graphs. Returns 1 when the
+ * step was run (replayed), 0 when the caller has to run it eagerly. */
+static int forward_graph(bcnn_net *net) {
+    bcnn_cuda_context *ctx = bcnn_ctx(net);
+    if (!ctx->graphs || net->mode != BCNN_MODE_PREDICT || ctx->profile || net->num_nodes == 0)
+        return 0;
+    const int same = ctx->fwd_graph_nodes == net->num_nodes &&
+                     ctx->fwd_graph_tensors == net->num_tensors &&
+                     ctx->fwd_graph_math == ctx->conv_math &&
+                     ctx->fwd_graph_input == (const void *)net->tensors[0].data_gpu;
+    if (!same) {
+        forward_graph_drop(ctx);
+        ctx->fwd_graph_nodes = net->num_nodes;
+        ctx->fwd_graph_tensors = net->num_tensors;
+        ctx->fwd_graph_math = ctx->conv_math;
+        ctx->fwd_graph_input = net->tensors[0].data_gpu;
+    }
+    if (!ctx->fwd_graph) {
+        if (!ctx->fwd_graph_warm) { /* first forward of this configuration: eager */
+            ctx->fwd_graph_warm = 1;
+            return 0;
+        }
+        if (bcnn_b200_graph_begin(ctx->stream) != 0) {
+            ctx->graphs = 0;
+            return 0;
+        }
+        forward_nodes(net);
+        ctx->fwd_graph = bcnn_b200_graph_end(ctx->stream);
+        if (!ctx->fwd_graph) { /* capture refused: stay eager for the rest of this net's life */
+            BCNN_WARNING(net->log_ctx, "CUDA graph capture of the forward pass failed; running eagerly\n");
+            ctx->graphs = 0;
+            return 0;
+        }
+    }
+    bcnn_cuda_check(bcnn_b200_graph_launch(ctx->fwd_graph, ctx->stream));
+    return 1;
+}
+
+void bcnn_forward(bcnn_net *net) {
+    grad_state_sync(net);
+    if (forward_graph(net)) return;
+    forward_nodes(net);
+}
+
+void bcnn_b200_set_graphs(bcnn_net *net, int on) {
+    bcnn_cuda_context *ctx = bcnn_ctx(net);
+    ctx->graphs = on != 0;
+    if (!on) forward_graph_drop(ctx);
+}
+
+int bcnn_b200_get_graphs(bcnn_net *net) {
+    bcnn_cuda_context *ctx = bcnn_ctx(net);
+    return !ctx->graphs ? 0 : (ctx->fwd_graph ? 2 : 1);
 }
 
 void bcnn_backward(bcnn_net *net) {
@@ -352,7 +419,10 @@ float bcnn_net_grad_post_scale(bcnn_net *net, float momentum) {
 /* ---------------- extension API (include/bcnn_b200_net.h) ---------------- */
 
 void bcnn_b200_set_conv_math(bcnn_net *net, int math) { bcnn_ctx(net)->conv_math = math; }
-void bcnn_b200_set_reference_quirks(bcnn_net *net, int on) { bcnn_ctx(net)->reference_quirks = on; }
+void bcnn_b200_set_reference_quirks(bcnn_net *net, int on) {
+    if (bcnn_ctx(net)->reference_quirks != on) forward_graph_drop(bcnn_ctx(net));
+    bcnn_ctx(net)->reference_quirks = on;
+}
 int bcnn_b200_get_conv_math(bcnn_net *net) { return bcnn_ctx(net)->conv_math; }
 void *bcnn_b200_get_stream(bcnn_net *net) { return bcnn_stream(net); }
 

@@ -49,6 +49,16 @@ typedef struct bcnn_cuda_context {
      * overwrites (no fill, no read), later writers accumulate: same values, two memory
      * passes fewer per activation. grad_fresh[t] != 0 <=> tensor t's gradient holds a partial
      * sum of the current step. */
+    /* PREDICT-mode forward as a CUDA graph (batch-1 inference is launch-bound: ~60 kernels of
+     * a few microseconds each). State machine: the first forward of a configuration runs eagerly
+     * (one-time initialisation inside the launchers), the second is captured and replayed, every
+     * later one is a single cudaGraphLaunch. The key (nodes, tensors, math, input buffer)
+     * invalidates the graph when the net changes. graphs: 1 = on (default), 0 = off. */
+    int graphs;
+    void *fwd_graph;
+    int fwd_graph_warm;
+    int fwd_graph_nodes, fwd_graph_tensors, fwd_graph_math;
+    const void *fwd_graph_input;
     unsigned char *grad_fresh;
     int *consumers; /* activation consumers per tensor (bcnn_net_num_consumers) */
     int grad_state_tensors, grad_state_nodes;

@@ -88,6 +88,14 @@ BCNN_B200_API void bcnn_b200_event_destroy(void *event);
 BCNN_B200_API int bcnn_b200_event_record(void *event, void *stream);
 BCNN_B200_API int bcnn_b200_stream_wait_event(void *stream, void *event);
 BCNN_B200_API float bcnn_b200_event_elapsed_ms(void *start, void *stop);
+/* CUDA graphs (no counterpart in the reference, whose CUDA path launches every kernel from the
+ * host on the default stream): record the work queued on `stream` between begin and end, then
+ * replay it with one launch. graph_end returns NULL when the capture failed; captured work is
+ * not executed until the graph is launched. */
+BCNN_B200_API int bcnn_b200_graph_begin(void *stream);
+BCNN_B200_API void *bcnn_b200_graph_end(void *stream);
+BCNN_B200_API int bcnn_b200_graph_launch(void *graph_exec, void *stream);
+BCNN_B200_API void bcnn_b200_graph_destroy(void *graph_exec);
 BCNN_B200_API const char *bcnn_b200_error_string(int err);
 /* number of kernels this library has launched in this process (bench.py's
  * gpu_launches claim) */

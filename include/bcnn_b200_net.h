@@ -36,6 +36,13 @@ BCNN_B200_API void bcnn_b200_set_reference_quirks(bcnn_net *net, int on);
  * input_width | width, input_height | height, input_channels | channels, batch_size | batch.
  * Augmentation keys belong to the file loader and are ignored. */
 BCNN_B200_API void bcnn_net_set_param(bcnn_net *net, const char *name, const char *val);
+/* CUDA-graph replay of the PREDICT-mode forward (default on; env BCNN_B200_GRAPHS=0 or
+ * on = 0 turns it off). The first bcnn_forward of a configuration launches its kernels one by
+ * one, the second is captured, later ones are one graph launch; the graph is rebuilt when
+ * nodes / tensors / conv math / the input buffer change. Results are identical to the eager
+ * path (same kernels, same order). get: 0 = off, 1 = on, 2 = on and a graph is live. */
+BCNN_B200_API void bcnn_b200_set_graphs(bcnn_net *net, int on);
+BCNN_B200_API int bcnn_b200_get_graphs(bcnn_net *net);
 /* The CUDA stream (cudaStream_t) every kernel of this net is launched on. */
 BCNN_B200_API void *bcnn_b200_get_stream(bcnn_net *net);
 /* Block the host until the net's stream (and its comm stream) are idle. */

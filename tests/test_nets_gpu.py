@@ -273,3 +273,42 @@ def test_second_input_tensor_matches_live_reference():
         net.close()
     for k in outs[1]:
         assert_close(outs[0][k], outs[1][k], 2e-5, f"two-input net {k}")
+
+
+@pytest.mark.parametrize("math", [capi.MATH_FP32, capi.MATH_TC])
+def test_predict_forward_graph_replay_is_the_eager_forward(math):
+    """PREDICT-mode bcnn_forward: 1st call eager, 2nd captured into a CUDA graph, later calls one
+    graph launch (bcnn_b200_set_graphs). Same kernels in the same order, so every output must be
+    bit-identical to a graph-free twin, for fresh inputs on every call; changing the conv math or
+    recompiling rebuilds the graph."""
+    nets = []
+    for graphs in (True, False):
+        net = capi.Net(mode=capi.MODE_PREDICT)
+        net.set_graphs(graphs)
+        net.set_conv_math(math)
+        info = configs.yolo_tiny(net, batch=2, res=64)
+        net.compile()
+        configs.init_params(net, seed=3)
+        nets.append(net)
+    fast, eager = nets
+    assert fast.graphs() == 1 and eager.graphs() == 0
+    for step in range(5):
+        x = configs.synth_input(fast.shape("input"), seed=50 + step)
+        for net in nets:
+            net.set("input", x)
+            net.forward()
+        assert fast.graphs() == (2 if step >= 1 else 1)
+        for name in ("conv0", "route", "yolo1", info["out"]):
+            assert np.array_equal(fast.get(name), eager.get(name)), (step, name)
+    before = fast.get(info["out"])
+    fast.set_conv_math(capi.MATH_FP32 if math == capi.MATH_TC else capi.MATH_TC)
+    fast.forward()                      # new configuration: eager again, graph dropped
+    assert fast.graphs() == 1
+    fast.set_conv_math(math)
+    for _ in range(3):
+        fast.forward()
+    assert fast.graphs() == 2 and np.array_equal(fast.get(info["out"]), before)
+    fast.compile()                      # reallocates the input and the workspace
+    assert fast.graphs() == 1
+    for net in nets:
+        net.close()
