@@ -216,3 +216,19 @@ def init_params(net, seed=2024, randomize_bn=True):
         else:
             val = np.zeros(size)
         net.set(idx, val.astype(np.float32))
+
+
+def synth_yolo_labels(n, boxes_per_image=3, classes=80, seed=12345):
+    """Detection labels in the reference's layout (src/layers/bcnn_yolo.c:69-72, 282-290):
+    [n, 1, 1, 250] = up to 50 boxes x (x, y, w, h, class), centre and size relative to the image,
+    the list ends at the first x == 0. Boxes stay inside (0.05, 0.95): a box centred exactly on
+    the right / bottom edge indexes one cell past the grid in the reference."""
+    rng = np.random.default_rng(seed)
+    counts = boxes_per_image if hasattr(boxes_per_image, "__len__") else [boxes_per_image] * n
+    lab = np.zeros((n, 1, 1, 250), np.float32)
+    for b in range(n):
+        for t in range(min(int(counts[b]), 50)):
+            lab[b, 0, 0, 5 * t:5 * t + 5] = [rng.uniform(0.05, 0.95), rng.uniform(0.05, 0.95),
+                                             rng.uniform(0.05, 0.6), rng.uniform(0.05, 0.6),
+                                             rng.integers(0, classes)]
+    return lab

@@ -14,6 +14,7 @@
 
 #include "bcnn_dp.h"
 #include "bcnn_tensor.h"
+#include "bcnn_yolo.h"
 #include <bcnn_b200_net.h>
 
 static void forward_graph_drop(bcnn_cuda_context *ctx);
@@ -463,6 +464,15 @@ float bcnn_b200_get_loss(bcnn_net *net) {
     int count = 0;
     void *stream = bcnn_stream(net);
     for (int i = 0; i < net->num_nodes; ++i) {
+        if (net->nodes[i].type == BCNN_LAYER_YOLOV3) { /* host-side loss (reference :437-443) */
+            const bcnn_yolo_param *yolo = (const bcnn_yolo_param *)net->nodes[i].param;
+            if (yolo->cost) {
+                bcnn_cuda_check(bcnn_b200_stream_sync(stream));
+                loss += yolo->cost[0];
+                ++count;
+            }
+            continue;
+        }
         if (net->nodes[i].type != BCNN_LAYER_COST) continue;
         float v = 0.f;
         bcnn_cuda_check(bcnn_b200_memcpy_d2h(&v, net->tensors[net->nodes[i].dst[0]].data_gpu,

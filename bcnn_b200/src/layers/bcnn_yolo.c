@@ -2,20 +2,26 @@
  * bcnn_yolo.c -- YOLOv3 output node, inference side.
  *
  * Node layout and checks of jnbraun/bcnn src/layers/bcnn_yolo.c:15-107: src[0] = the head's
- * [N, num*(coords+classes+1), H, W] map, dst[0] the same shape, param = mask + anchor sizes. The
- * forward of PREDICT / VALID mode (:226-250: copy, logistic on centre offsets, objectness and
- * class scores) is one device kernel here; the reference copies the head to the host for it even
- * in its CUDA build (:418-431). The TRAIN-mode detection loss (:251-416) is host code in the
- * reference and outside this path: a TRAIN-mode net refuses the layer instead of
- * silently training without a loss. bcnn_yolo_get_detections (:470-639: box decoding, letterbox
- * correction, objectness NMS) is host post-processing in the reference and is host code here
- * too, on the heads' host mirrors after one D2H refresh per head.
+ * [N, num*(coords+classes+1), H, W] map, dst[0] the same shape, param = mask + anchor sizes.
+ *   * forward, every mode (:226-250: copy, logistic on centre offsets, objectness and class
+ *     scores): one device kernel; the reference copies the head to the host for it even in its
+ *     CUDA build (:418-431).
+ *   * TRAIN: the detection loss (:251-416) is host code in the reference, also in its CUDA build
+ *     (D2H of the head, loss on the CPU, H2D of the gradient), and it is host code here: a few
+ *     thousand cells against at most 50 boxes per image is branchy scalar work worth microseconds.
+ *     bcnn_yolo_loss_host works on the host mirrors of the activated head, the label and the
+ *     gradient; the forward brackets it with the two copies. Float operations are the reference's,
+ *     in its order, so the gradient is bit-identical for identical head tensors.
+ *   * bcnn_yolo_get_detections (:470-639: box decoding, letterbox correction, objectness NMS) is
+ *     host post-processing in the reference and is host code here too, on the heads' host mirrors
+ *     after one D2H refresh per head.
  */
 #include "bcnn_yolo.h"
 
 #include <math.h>
 
 #include "bcnn_tensor.h"
+#include <bcnn_b200_net.h>
 
 bcnn_status bcnn_add_yolo_layer(bcnn_net *net, int num_boxes_per_cell, int classes, int coords,
                                 int total, int *mask, float *anchors, const char *src_id,
@@ -23,8 +29,6 @@ bcnn_status bcnn_add_yolo_layer(bcnn_net *net, int num_boxes_per_cell, int class
     bcnn_node node = {0};
     BCNN_CHECK_AND_LOG(net->log_ctx, net->num_nodes >= 1, BCNN_INVALID_PARAMETER,
                        "Yolo layer can't be the first layer of the network\n");
-    BCNN_CHECK_AND_LOG(net->log_ctx, net->mode != BCNN_MODE_TRAIN, BCNN_INVALID_PARAMETER,
-                       "Yolo layer: the detection loss (TRAIN mode) is not part of the B200 path\n");
     int src = bcnn_net_find_src(net, src_id);
     BCNN_CHECK_AND_LOG(net->log_ctx, src >= 0, BCNN_INVALID_PARAMETER,
                        "Yolo layer: invalid input node name %s\n", src_id);
@@ -66,7 +70,7 @@ bcnn_status bcnn_add_yolo_layer(bcnn_net *net, int num_boxes_per_cell, int class
     node.backward = bcnn_backward_yolo_layer;
     node.release_param = bcnn_release_param_yolo_layer;
 
-    /* VALID: the label holds up to 50 boxes x (x, y, w, h, class) per sample (:69-74) */
+    /* TRAIN / VALID: the label holds up to 50 boxes x (x, y, w, h, class) per sample (:69-74) */
     if (net->mode != BCNN_MODE_PREDICT && net->tensors[1].data_gpu == NULL) {
         bcnn_tensor_set_shape(&net->tensors[1], n, 1, 1, BCNN_DETECTION_MAX_BOXES * 5, 0);
         BCNN_CHECK_STATUS(bcnn_tensor_allocate(&net->tensors[1], net->mode));
@@ -79,12 +83,165 @@ bcnn_status bcnn_add_yolo_layer(bcnn_net *net, int num_boxes_per_cell, int class
     return BCNN_SUCCESS;
 }
 
+typedef struct { float x, y, w, h; } yolo_box;
+
+static float span_overlap(float c1, float e1, float c2, float e2) {
+    const float lo1 = c1 - e1 / 2, lo2 = c2 - e2 / 2, hi1 = c1 + e1 / 2, hi2 = c2 + e2 / 2;
+    return (hi1 < hi2 ? hi1 : hi2) - (lo1 > lo2 ? lo1 : lo2);
+}
+
+static float yolo_iou(yolo_box a, yolo_box b) {
+    const float w = span_overlap(a.x, a.w, b.x, b.w), h = span_overlap(a.y, a.h, b.y, b.h);
+    const float inter = (w < 0 || h < 0) ? 0 : w * h;
+    const float uni = a.w * a.h + b.w * b.h - inter;
+    return inter / uni;
+}
+
+/* Box predicted at cell (col, row) by the anchor of size (aw, ah); `e` points at the cell's
+ * first entry, entries are `hw` floats apart (get_yolo_box, reference :137-146). */
+static yolo_box decode_box(const float *e, int hw, float aw, float ah, int col, int row, int lw,
+                           int lh, int netw, int neth) {
+    yolo_box b;
+    b.x = (col + e[0]) / lw;
+    b.y = (row + e[hw]) / lh;
+    b.w = expf(e[2 * (size_t)hw]) * aw / netw;
+    b.h = expf(e[3 * (size_t)hw]) * ah / neth;
+    return b;
+}
+
+/* The truth boxes of one sample: x, y, w, h, class per box, the list ends at x == 0. */
+static int truth_at(const float *label, int t, int stride, yolo_box *box) {
+    const float *f = label + (size_t)t * stride;
+    box->x = f[0]; box->y = f[1]; box->w = f[2]; box->h = f[3];
+    return f[0] != 0;
+}
+
+/* Detection loss of one yolo node on the host mirrors (reference :251-416): fills dst->grad_data
+ * (the gradient of the loss w.r.t. the activated head) and param->cost. Two sweeps per sample:
+ * every predicted box pays for its objectness unless it overlaps some truth by more than 0.5;
+ * every truth box then claims the cell it falls in, for the anchor that fits its size best when
+ * that anchor belongs to this head, and sets box, objectness and class targets there. */
+void bcnn_yolo_loss_host(bcnn_net *net, bcnn_node *node) {
+    bcnn_yolo_param *param = (bcnn_yolo_param *)node->param;
+    const bcnn_tensor *dst = &net->tensors[node->dst[0]], *label = &net->tensors[1];
+    const int lw = dst->w, lh = dst->h, hw = lw * lh, coords = param->coords;
+    const int group = coords + param->classes + 1, chw = param->num * group * hw;
+    const int netw = net->tensors[0].w, neth = net->tensors[0].h;
+    const float *anchors = param->biases.data;
+    const float *out = dst->data;
+    float *delta = dst->grad_data;
+    memset(delta, 0, (size_t)dst->n * chw * sizeof(float));
+    float sum_iou = 0, sum_class = 0, sum_obj = 0, sum_anyobj = 0, recall50 = 0, recall75 = 0;
+    int count = 0;
+    for (int b = 0; b < dst->n; ++b) {
+        const float *truths = label->data + (size_t)b * param->truths;
+        const size_t base = (size_t)b * chw;
+        for (int row = 0; row < lh; ++row)
+            for (int col = 0; col < lw; ++col)
+                for (int a = 0; a < param->num; ++a) {
+                    const size_t cell = base + (size_t)a * group * hw + (size_t)row * lw + col;
+                    const int anchor = param->mask[a];
+                    const yolo_box pred = decode_box(out + cell, hw, anchors[2 * anchor],
+                                                     anchors[2 * anchor + 1], col, row, lw, lh,
+                                                     netw, neth);
+                    float best_iou = 0;
+                    yolo_box truth;
+                    for (int t = 0; t < param->max_boxes && truth_at(truths, t, coords + 1, &truth); ++t) {
+                        const float iou = yolo_iou(pred, truth);
+                        if (iou > best_iou) best_iou = iou;
+                    }
+                    const size_t obj = cell + (size_t)coords * hw;
+                    delta[obj] = out[obj] - 0;
+                    if (best_iou > 0.5) delta[obj] = 0;
+                    sum_anyobj += out[obj];
+                }
+        yolo_box truth;
+        for (int t = 0; t < param->max_boxes && truth_at(truths, t, coords + 1, &truth); ++t) {
+            const int col = (int)(truth.x * lw), row = (int)(truth.y * lh);
+            if (col < 0 || col >= lw || row < 0 || row >= lh) continue; /* the reference writes out of bounds here */
+            yolo_box centred = truth;
+            centred.x = centred.y = 0;
+            float best_iou = 0;
+            int best = 0;
+            for (int n = 0; n < param->total; ++n) {
+                const yolo_box prior = {0, 0, anchors[2 * n] / netw, anchors[2 * n + 1] / neth};
+                const float iou = yolo_iou(prior, centred);
+                if (iou > best_iou) { best_iou = iou; best = n; }
+            }
+            int a = -1;
+            for (int k = 0; k < param->num && a < 0; ++k)
+                if (param->mask[k] == best) a = k;
+            if (a < 0) continue; /* another head owns this anchor */
+            const size_t cell = base + (size_t)a * group * hw + (size_t)row * lw + col;
+            const float aw = anchors[2 * best], ah = anchors[2 * best + 1];
+            const float iou = yolo_iou(decode_box(out + cell, hw, aw, ah, col, row, lw, lh, netw, neth),
+                                       truth);
+            const float scale = (2 - truth.w * truth.h);
+            const float target[4] = {truth.x * lw - col, truth.y * lh - row,
+                                     logf(truth.w * netw / aw), logf(truth.h * neth / ah)};
+            for (int e = 0; e < 4; ++e)
+                delta[cell + (size_t)e * hw] = -scale * (target[e] - out[cell + (size_t)e * hw]);
+            const size_t obj = cell + (size_t)coords * hw;
+            sum_obj += out[obj];
+            delta[obj] = out[obj] - 1;
+            const int cls = (int)truths[(size_t)t * (coords + 1) + coords];
+            const size_t first_class = obj + hw;
+            if (delta[first_class]) { /* cell already claimed: only this class is pushed up */
+                delta[first_class + (size_t)hw * cls] = out[first_class + (size_t)hw * cls] - 1;
+                sum_class += out[first_class + (size_t)hw * cls];
+            } else {
+                for (int n = 0; n < param->classes; ++n) {
+                    delta[first_class + (size_t)hw * n] = out[first_class + (size_t)hw * n] - ((n == cls) ? 1 : 0);
+                    if (n == cls) sum_class += out[first_class + (size_t)hw * n];
+                }
+            }
+            ++count;
+            if (iou > 0.5f) recall50 += 1;
+            if (iou > 0.75f) recall75 += 1;
+            sum_iou += iou;
+        }
+    }
+    double sq = 0; /* the reference sums in float lanes; the cost is a report, not an operand */
+    for (size_t i = 0; i < (size_t)dst->n * chw; ++i) sq += (double)delta[i] * delta[i];
+    *param->cost = powf(sqrtf((float)sq), 2);
+    BCNN_INFO(net->log_ctx,
+              "Yolo Avg IOU: %f Class: %f Obj: %f No Obj: %f .5R: %f, .75R: %f num_boxes: %d "
+              "cost: %f\n", sum_iou / count, sum_class / count, sum_obj / count,
+              sum_anyobj / ((float)hw * param->num * dst->n), recall50 / count, recall75 / count,
+              count, *param->cost);
+}
+
+/* The host round trip of a TRAIN forward on its own: dst.data (device) -> host, loss, gradient ->
+ * dst.grad (device). Returns the node's cost, or -1 when `node_index` is not a yolo node with a
+ * gradient buffer. */
+static float yolo_loss_round_trip(bcnn_net *net, bcnn_node *node) {
+    bcnn_tensor *dst = &net->tensors[node->dst[0]];
+    void *stream = bcnn_stream(net);
+    const size_t bytes = (size_t)bcnn_tensor_size(dst) * sizeof(float);
+    if (!dst->grad_data_gpu || bcnn_tensor_ensure_host(dst) != BCNN_SUCCESS || !net->tensors[1].data)
+        return -1.f;
+    bcnn_cuda_check(bcnn_b200_memcpy_d2h(dst->data, dst->data_gpu, bytes, stream));
+    bcnn_cuda_check(bcnn_b200_stream_sync(stream));
+    bcnn_yolo_loss_host(net, node);
+    bcnn_cuda_check(bcnn_b200_memcpy_h2d(dst->grad_data_gpu, dst->grad_data, bytes, stream));
+    return *((bcnn_yolo_param *)node->param)->cost;
+}
+
+float bcnn_b200_yolo_loss(bcnn_net *net, int node_index) {
+    if (node_index < 0 || node_index >= net->num_nodes ||
+        net->nodes[node_index].type != BCNN_LAYER_YOLOV3)
+        return -1.f;
+    return yolo_loss_round_trip(net, &net->nodes[node_index]);
+}
+
 void bcnn_forward_yolo_layer(bcnn_net *net, bcnn_node *node) {
     bcnn_yolo_param *param = (bcnn_yolo_param *)node->param;
     bcnn_tensor *src = &net->tensors[node->src[0]], *dst = &net->tensors[node->dst[0]];
+    void *stream = bcnn_stream(net);
     bcnn_cuda_check(bcnn_b200_yolo_activate(src->data_gpu, dst->data_gpu, src->n, param->num,
-                                            param->classes, param->coords, src->h * src->w,
-                                            bcnn_stream(net)));
+                                            param->classes, param->coords, src->h * src->w, stream));
+    /* the reference's own TRAIN data flow (:418-431): head to the host, loss there, gradient back */
+    if (net->mode == BCNN_MODE_TRAIN) (void)yolo_loss_round_trip(net, node);
 }
 
 /* src.grad += dst.grad (reference :432-447) */
@@ -104,20 +261,6 @@ void bcnn_release_param_yolo_layer(bcnn_node *node) {
 }
 
 /* ---- detections: host post-processing, semantics of reference :470-639 ---- */
-typedef struct { float x, y, w, h; } yolo_box;
-
-static float span_overlap(float c1, float e1, float c2, float e2) {
-    const float lo1 = c1 - e1 / 2, lo2 = c2 - e2 / 2, hi1 = c1 + e1 / 2, hi2 = c2 + e2 / 2;
-    return (hi1 < hi2 ? hi1 : hi2) - (lo1 > lo2 ? lo1 : lo2);
-}
-
-static float yolo_iou(yolo_box a, yolo_box b) {
-    const float w = span_overlap(a.x, a.w, b.x, b.w), h = span_overlap(a.y, a.h, b.y, b.h);
-    const float inter = (w < 0 || h < 0) ? 0 : w * h;
-    const float uni = a.w * a.h + b.w * b.h - inter;
-    return inter / uni;
-}
-
 static int by_objectness_desc(const void *pa, const void *pb) {
     const float diff = ((const bcnn_output_detection *)pa)->objectness -
                        ((const bcnn_output_detection *)pb)->objectness;

@@ -27,6 +27,9 @@ typedef struct bcnn_yolo_param {
 void bcnn_forward_yolo_layer(bcnn_net *net, bcnn_node *node);
 void bcnn_backward_yolo_layer(bcnn_net *net, bcnn_node *node);
 void bcnn_release_param_yolo_layer(bcnn_node *node);
+/* TRAIN-mode detection loss on the host mirrors of dst (activated head, in), the label (in) and
+ * dst's gradient (out); param->cost receives the loss. */
+void bcnn_yolo_loss_host(bcnn_net *net, bcnn_node *node);
 
 #ifdef __cplusplus
 }

@@ -214,9 +214,9 @@ BCNN_API bcnn_status bcnn_add_concat_layer(bcnn_net *net, int num_src, char *con
 BCNN_API bcnn_status bcnn_add_upsample_layer(bcnn_net *net, int size, const char *src_id,
                                              const char *dst_id);
 /* YOLOv3 output layer (reference inc/bcnn/bcnn.h:1039, src/layers/bcnn_yolo.c:15-107).
- * PREDICT / VALID: the head activation runs on the device. The detection loss of TRAIN mode is
- * host code in the reference even in its CUDA build (:418-431) and is not part of this path:
- * the constructor returns BCNN_INVALID_PARAMETER for a TRAIN-mode net. */
+ * The head activation runs on the device in every mode. The detection loss of TRAIN mode is host
+ * code in the reference even in its CUDA build (:418-431) and is host code here: head to the
+ * host, loss against the [N,1,1,250] box label, gradient back. */
 BCNN_API bcnn_status bcnn_add_yolo_layer(bcnn_net *net, int num_boxes_per_cell, int classes,
                                          int coords, int total, int *mask, float *anchors,
                                          const char *src_id, const char *dst_id);

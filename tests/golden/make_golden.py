@@ -101,7 +101,10 @@ def make_cfg():
       mini_yolo.npz                    input and the tensors of one PREDICT forward of the
                                        reference after bcnn_load_net(cfg, weights), and its
                                        bcnn_yolo_get_detections per sample (thresh 0.5, 640x480
-                                       frame, relative) as [num_dets, x y w h objectness p0 p1]."""
+                                       frame, relative) as [num_dets, x y w h objectness p0 p1].
+      mini_yolo_train.npz              the same files in TRAIN mode: box labels, the heads, the
+                                       gradient its yolo loss leaves on them, gradients after
+                                       bcnn_backward and weights after one bcnn_update."""
     import json
     sys.path.insert(0, str(ROOT / "oracle"))
     import bcnn_model_oracle as mo
@@ -145,6 +148,30 @@ def make_cfg():
     for b in range(2):  # bcnn_yolo_get_detections of a 640x480 frame (chatty on stderr)
         packed[f"dets_b{b}"] = net.yolo_detections(b, 640, 480, 0.5, relative=True)
     np.savez_compressed(cfg_dir / "mini_yolo.npz", **packed)
+    net.close()
+    # TRAIN mode on the same files: one step with box labels through the reference's yolo loss
+    net = ref_net(mode=capi.MODE_TRAIN, threads=1)
+    assert net.load_net(cfg_dir / "mini_yolo.cfg", weights) == 0
+    net.compile()
+    x = configs.synth_input(net.shape("input"), seed=29)
+    lab = configs.synth_yolo_labels(2, [4, 7], classes=2, seed=31)
+    lab[0, 0, 0, 5:9] = lab[0, 0, 0, 0:4]          # two truths in one cell: the "claimed" branch
+    net.set("input", x)
+    net.set("label", lab)
+    net.forward()
+    train = {"input": x, "label": lab}
+    for name in ("lid9", "lid10", "lid16", "lid17"):
+        train["data/" + name] = net.get(name)
+    for name in ("lid10", "lid17"):
+        train["loss_grad/" + name] = net.get(name, grad=True)
+    net.backward()
+    for name in ("lid9", "lid16", "lid14", "lid7", "lid1", "lid8_w", "lid15_w", "lid11_w", "lid0_w",
+                 "lid8_b", "lid4_scales"):
+        train["grad/" + name] = net.get(name, grad=True)
+    net.update()
+    for name in ("lid8_w", "lid15_w", "lid0_w", "lid8_b"):
+        train["updated/" + name] = net.get(name)
+    np.savez_compressed(cfg_dir / "mini_yolo_train.npz", **train)
     net.close()
     print("cfg:", sorted(p.name for p in cfg_dir.iterdir()))
 
