@@ -83,9 +83,9 @@ def mobilenet(net, batch=1, res=224, classes=1000):
 def yolo_tiny(net, batch=1, res=416):
     """YOLOv3-tiny (examples/yolo/yolov3-tiny.cfg) with both heads: trunk, coarse head at res/32,
     route -> 1x1 conv -> upsample x2 -> concat with the 256-channel trunk tensor at res/16 -> fine
-    head. PREDICT nets end in the two yolo layers; the yolo loss stays out of scope (SURVEY.md 8f:
-    host-side in the reference): for training the fine head carries a euclidean cost, the coarse head's output has no consumer and
-    so receives a zero gradient (its convolutions still run forward and backward)."""
+    head, each ending in its yolo layer (head activation on the device; in TRAIN mode the detection
+    loss on the host, as in the reference). Profiles older than round 1l trained this net with a
+    euclidean cost on the fine head instead."""
     net.set_input_shape(res, res, 3, batch)
     prev = "input"
     for i, c in enumerate([16, 32, 64, 128, 256, 512]):
@@ -101,15 +101,14 @@ def yolo_tiny(net, batch=1, res=416):
     net.concat(["up", "conv4"], "route")                         # route -1, 8
     net.conv(256, 3, 1, 1, 1, 1, "lrelu", "route", "conv10")
     net.conv(255, 1, 1, 0, 1, 0, "none", "conv10", "head")
-    if net.mode != capi.MODE_PREDICT:
-        net.cost("head", "cost", metric=capi.METRIC_SSE)
-        net.sgd(0.001, 0.9, 0.0005)
-        return dict(classes=None, out="head")
-    # inference: the two [yolo] layers of the cfg (80 classes, 6 anchors, masks 3-5 and 0-2);
-    # the fine one is added last, as in the cfg, so bcnn_predict_on_batch returns it
+    # the two [yolo] layers of the cfg (80 classes, 6 anchors, masks 3-5 and 0-2); the fine one is
+    # added last, as in the cfg, so bcnn_predict_on_batch returns it. In TRAIN mode they carry the
+    # detection loss against [N,1,1,250] box labels (synth_labels makes 3 boxes per image).
     anchors = [10, 14, 23, 27, 37, 58, 81, 82, 135, 169, 344, 319]
     net.yolo([3, 4, 5], anchors, 80, "head1", "yolo1")
     net.yolo([0, 1, 2], anchors, 80, "head", "yolo2")
+    if net.mode != capi.MODE_PREDICT:
+        net.sgd(0.001, 0.9, 0.0005)
     return dict(classes=None, out="yolo2")
 
 
@@ -160,6 +159,8 @@ def synth_labels(shape, first_sample=0):
     """One-hot [N, classes, 1, 1] (class = global sample index mod classes); for a dense
     target (yolo head stand-in) small uniform values."""
     n, c, h, w = shape
+    if (c, h, w) == (1, 1, 250):  # detection labels of a net that ends in yolo layers
+        return synth_yolo_labels(n, 3, classes=80, seed=777 + first_sample)
     if h * w == 1:
         y = np.zeros(shape, dtype=np.float32)
         for i in range(n):
