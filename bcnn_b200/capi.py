@@ -123,7 +123,7 @@ def bind_b200_ext(lib: C.CDLL) -> None:
         "bcnn_b200_set_conv_math": (None, [vp, i]),
         "bcnn_b200_get_conv_math": (i, [vp]),
         "bcnn_b200_set_reference_quirks": (None, [vp, i]),
-        "bcnn_b200_yolo_loss": (f, [vp, i]),
+        "bcnn_b200_yolo_loss_on_host": (f, [vp, i]),
         "bcnn_b200_set_graphs": (None, [vp, i]),
         "bcnn_b200_get_graphs": (i, [vp]),
         "bcnn_b200_get_stream": (vp, [vp]),
@@ -562,6 +562,8 @@ def bind_kernel_abi(lib: C.CDLL) -> None:
         "bcnn_b200_sgd_update": (i, [vp, vp, sz, f, f, f, vp]),
         "bcnn_b200_adam_update": (i, [vp, vp, vp, vp, sz, f, f, f, f, vp]),
         "bcnn_b200_yolo_activate": (i, [vp, vp, i, i, i, i, i, vp]),
+        "bcnn_b200_yolo_cost_scratch_floats": (i, []),
+        "bcnn_b200_yolo_loss_forward": (i, [vp, vp, vp, vp, vp, vp] + [i] * 10 + [vp]),
         "bcnn_b200_softmax_forward": (i, [vp, vp, i, i, i, vp]),
         "bcnn_b200_cost_forward": (i, [vp, vp, vp, vp, i, i, i, vp]),
         "bcnn_b200_eltwise_forward": (i, [vp, vp, vp, i, i, i, vp]),

@@ -464,13 +464,9 @@ float bcnn_b200_get_loss(bcnn_net *net) {
     int count = 0;
     void *stream = bcnn_stream(net);
     for (int i = 0; i < net->num_nodes; ++i) {
-        if (net->nodes[i].type == BCNN_LAYER_YOLOV3) { /* host-side loss (reference :437-443) */
-            const bcnn_yolo_param *yolo = (const bcnn_yolo_param *)net->nodes[i].param;
-            if (yolo->cost) {
-                bcnn_cuda_check(bcnn_b200_stream_sync(stream));
-                loss += yolo->cost[0];
-                ++count;
-            }
+        if (net->nodes[i].type == BCNN_LAYER_YOLOV3) { /* reference :437-443 */
+            loss += bcnn_yolo_cost(net, &net->nodes[i]);
+            ++count;
             continue;
         }
         if (net->nodes[i].type != BCNN_LAYER_COST) continue;

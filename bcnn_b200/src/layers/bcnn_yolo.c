@@ -7,11 +7,12 @@
  *     scores): one device kernel; the reference copies the head to the host for it even in its
  *     CUDA build (:418-431).
  *   * TRAIN: the detection loss (:251-416) is host code in the reference, also in its CUDA build
- *     (D2H of the head, loss on the CPU, H2D of the gradient), and it is host code here: a few
- *     thousand cells against at most 50 boxes per image is branchy scalar work worth microseconds.
- *     bcnn_yolo_loss_host works on the host mirrors of the activated head, the label and the
- *     gradient; the forward brackets it with the two copies. Float operations are the reference's,
- *     in its order, so the gradient is bit-identical for identical head tensors.
+ *     (D2H of the head, loss on the CPU, H2D of the gradient: a pipeline stall in every step).
+ *     Here it is three kernels on the net's stream (csrc/yolo.cu) and nothing leaves the device
+ *     until somebody asks for the loss. bcnn_yolo_loss_host keeps the reference's loops as host
+ *     code on the host mirrors -- bit-identical to the reference for identical head tensors --
+ *     and serves as the cross-check of the kernels (bcnn_b200_yolo_loss_on_host); the forward
+ *     pass never calls it.
  *   * bcnn_yolo_get_detections (:470-639: box decoding, letterbox correction, objectness NMS) is
  *     host post-processing in the reference and is host code here too, on the heads' host mirrors
  *     after one D2H refresh per head.
@@ -65,6 +66,13 @@ bcnn_status bcnn_add_yolo_layer(bcnn_net *net, int num_boxes_per_cell, int class
     for (int i = 0; i < total * 2; ++i) param->biases.data[i] = anchors ? anchors[i] : 0.5f;
     bcnn_cuda_check(bcnn_b200_memcpy_h2d(param->biases.data_gpu, param->biases.data,
                                          (size_t)total * 2 * sizeof(float), bcnn_stream(net)));
+    bcnn_cuda_check(bcnn_b200_stream_sync(bcnn_stream(net)));
+    param->mask_gpu = (int *)bcnn_b200_malloc((size_t)num_boxes_per_cell * sizeof(int));
+    param->cost_gpu =
+        (float *)bcnn_b200_malloc((size_t)bcnn_b200_yolo_cost_scratch_floats() * sizeof(float));
+    BCNN_CHECK(param->mask_gpu != NULL && param->cost_gpu != NULL, BCNN_CUDA_FAILED_ALLOC);
+    bcnn_cuda_check(bcnn_b200_memcpy_h2d(param->mask_gpu, param->mask,
+                                         (size_t)num_boxes_per_cell * sizeof(int), bcnn_stream(net)));
     bcnn_cuda_check(bcnn_b200_stream_sync(bcnn_stream(net)));
     node.forward = bcnn_forward_yolo_layer;
     node.backward = bcnn_backward_yolo_layer;
@@ -211,9 +219,9 @@ void bcnn_yolo_loss_host(bcnn_net *net, bcnn_node *node) {
               count, *param->cost);
 }
 
-/* The host round trip of a TRAIN forward on its own: dst.data (device) -> host, loss, gradient ->
- * dst.grad (device). Returns the node's cost, or -1 when `node_index` is not a yolo node with a
- * gradient buffer. */
+/* The reference's TRAIN data flow (:418-431) as a cross-check of the kernels: dst.data (device)
+ * -> host, loss on the host, gradient -> dst.grad (device). Returns the cost, or -1 when the node
+ * has no gradient buffer. */
 static float yolo_loss_round_trip(bcnn_net *net, bcnn_node *node) {
     bcnn_tensor *dst = &net->tensors[node->dst[0]];
     void *stream = bcnn_stream(net);
@@ -227,7 +235,7 @@ static float yolo_loss_round_trip(bcnn_net *net, bcnn_node *node) {
     return *((bcnn_yolo_param *)node->param)->cost;
 }
 
-float bcnn_b200_yolo_loss(bcnn_net *net, int node_index) {
+float bcnn_b200_yolo_loss_on_host(bcnn_net *net, int node_index) {
     if (node_index < 0 || node_index >= net->num_nodes ||
         net->nodes[node_index].type != BCNN_LAYER_YOLOV3)
         return -1.f;
@@ -240,8 +248,23 @@ void bcnn_forward_yolo_layer(bcnn_net *net, bcnn_node *node) {
     void *stream = bcnn_stream(net);
     bcnn_cuda_check(bcnn_b200_yolo_activate(src->data_gpu, dst->data_gpu, src->n, param->num,
                                             param->classes, param->coords, src->h * src->w, stream));
-    /* the reference's own TRAIN data flow (:418-431): head to the host, loss there, gradient back */
-    if (net->mode == BCNN_MODE_TRAIN) (void)yolo_loss_round_trip(net, node);
+    if (net->mode != BCNN_MODE_TRAIN || !dst->grad_data_gpu || !net->tensors[1].data_gpu) return;
+    bcnn_cuda_check(bcnn_b200_yolo_loss_forward(
+        dst->data_gpu, net->tensors[1].data_gpu, param->biases.data_gpu, param->mask_gpu,
+        dst->grad_data_gpu, param->cost_gpu, dst->n, param->num, param->classes, param->coords,
+        dst->w, dst->h, net->tensors[0].w, net->tensors[0].h, param->total, param->max_boxes,
+        stream));
+}
+
+/* This step's loss of a yolo node: one float from the device (synchronises the stream). */
+float bcnn_yolo_cost(bcnn_net *net, bcnn_node *node) {
+    bcnn_yolo_param *param = (bcnn_yolo_param *)node->param;
+    if (net->mode == BCNN_MODE_TRAIN && param->cost_gpu) {
+        bcnn_cuda_check(bcnn_b200_memcpy_d2h(param->cost, param->cost_gpu, sizeof(float),
+                                             bcnn_stream(net)));
+        bcnn_cuda_check(bcnn_b200_stream_sync(bcnn_stream(net)));
+    }
+    return *param->cost;
 }
 
 /* src.grad += dst.grad (reference :432-447) */
@@ -257,6 +280,8 @@ void bcnn_release_param_yolo_layer(bcnn_node *node) {
     bcnn_yolo_param *param = (bcnn_yolo_param *)node->param;
     free(param->cost);
     free(param->mask);
+    bcnn_b200_free(param->mask_gpu);
+    bcnn_b200_free(param->cost_gpu);
     bcnn_tensor_destroy(&param->biases);
 }
 

@@ -340,6 +340,20 @@ BCNN_B200_API int bcnn_b200_concat_backward(const float *dst_grad, float *src_gr
  * coords .. coords + classes (objectness, class scores); entries 2 .. coords-1 are copied. */
 BCNN_B200_API int bcnn_b200_yolo_activate(const float *x, float *y, int n, int boxes_per_cell,
                                           int classes, int coords, int hw, void *stream);
+/* YOLOv3 detection loss, the TRAIN part of bcnn_forward_yolo_layer_cpu (src/layers/bcnn_yolo.c:
+ * 251-416), on the device: `out` is the activated head, `label` the [n, max_boxes * (coords + 1)]
+ * truth list (x, y, w, h, class per box, ended by x == 0), `anchors` 2 * total_anchors sizes,
+ * `mask` the boxes_per_cell anchor indices of this head; `delta` receives d(loss)/d(out) (every
+ * entry written), cost_scratch[0] the loss (sum of squared delta entries); cost_scratch holds
+ * bcnn_b200_yolo_cost_scratch_floats() floats. The reference does this on the host after a
+ * device -> host copy of the head (:418-431). */
+BCNN_B200_API int bcnn_b200_yolo_cost_scratch_floats(void);
+BCNN_B200_API int bcnn_b200_yolo_loss_forward(const float *out, const float *label,
+                                              const float *anchors, const int *mask, float *delta,
+                                              float *cost_scratch, int n, int boxes_per_cell,
+                                              int classes, int coords, int lw, int lh, int netw,
+                                              int neth, int total_anchors, int max_boxes,
+                                              void *stream);
 /* y[n, c, j, i] = x[n, c, j / size, i / size]   (src/layers/bcnn_upsample_layer.c:86-109;
  * replaces bcnn_cuda_upsample_kernel, bcnn_upsample_layer.cu). */
 BCNN_B200_API int bcnn_b200_upsample_forward(const float *x, float *y, int n, int c, int h,

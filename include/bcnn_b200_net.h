@@ -95,11 +95,11 @@ BCNN_B200_API int bcnn_b200_maxpool_indexes(bcnn_net *net, int node, int *host_o
 BCNN_B200_API int bcnn_b200_bn_saved_stats(bcnn_net *net, int node, float *mean_out,
                                            float *var_out);
 
-/* Runs the TRAIN-mode detection loss of yolo node `node` on the head tensor now in its dst
- * buffer (device -> host, loss on the host, gradient -> device) and returns the node's cost;
- * -1 when `node` is not a yolo node of a net with gradients. bcnn_forward does this itself in
- * TRAIN mode; the tests use it to check the loss on the reference's own head tensors. */
-BCNN_B200_API float bcnn_b200_yolo_loss(bcnn_net *net, int node);
+/* Cross-check of the yolo loss kernels: evaluates the detection loss of yolo node `node` with
+ * the reference's host loops on the head tensor now in its dst buffer (device -> host, loss,
+ * gradient -> device) and returns the cost; -1 when `node` is not a yolo node of a net with
+ * gradients. bcnn_forward never takes this route: in TRAIN mode the loss runs on the device. */
+BCNN_B200_API float bcnn_b200_yolo_loss_on_host(bcnn_net *net, int node);
 
 /* ---- data parallelism (one process per GPU, NCCL all-reduce of weight grads) ---- */
 #define BCNN_B200_DP_ID_BYTES 128
