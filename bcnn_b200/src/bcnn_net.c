@@ -88,7 +88,7 @@ void bcnn_end_net(bcnn_net **net) {
         free(ctx->profile_events);
         free(ctx->grad_fresh);
         free(ctx->consumers);
-        bcnn_b200_graph_destroy(ctx->fwd_graph);
+        forward_graph_drop(ctx);
         bcnn_b200_free(ctx->workspace_gpu);
         bcnn_b200_free(ctx->dy_shadow_gpu);
         if (ctx->stage_gpu) {
@@ -269,6 +269,23 @@ static void forward_graph_drop(bcnn_cuda_context *ctx) {
     bcnn_b200_graph_destroy(ctx->fwd_graph);
     ctx->fwd_graph = NULL;
     ctx->fwd_graph_warm = 0;
+    for (int i = 0; i < 2; ++i) {
+        bcnn_b200_graph_destroy(ctx->step_graph[i].exec);
+        ctx->step_graph[i].exec = NULL;
+    }
+    ctx->step_graph_warm = 0;
+}
+
+/* Same configuration as the one the live graphs were recorded for? Otherwise drop them. */
+static void graph_key_check(bcnn_net *net) {
+    bcnn_cuda_context *ctx = bcnn_ctx(net);
+    if (ctx->fwd_graph_nodes == net->num_nodes && ctx->fwd_graph_tensors == net->num_tensors &&
+        ctx->fwd_graph_math == ctx->conv_math)
+        return;
+    forward_graph_drop(ctx);
+    ctx->fwd_graph_nodes = net->num_nodes;
+    ctx->fwd_graph_tensors = net->num_tensors;
+    ctx->fwd_graph_math = ctx->conv_math;
 }
 
 /* PREDICT-mode forward through a CUDA graph; see bcnn_cuda_context.graphs. Returns 1 when the
@@ -277,15 +294,9 @@ static int forward_graph(bcnn_net *net) {
     bcnn_cuda_context *ctx = bcnn_ctx(net);
     if (!ctx->graphs || net->mode != BCNN_MODE_PREDICT || ctx->profile || net->num_nodes == 0)
         return 0;
-    const int same = ctx->fwd_graph_nodes == net->num_nodes &&
-                     ctx->fwd_graph_tensors == net->num_tensors &&
-                     ctx->fwd_graph_math == ctx->conv_math &&
-                     ctx->fwd_graph_input == (const void *)net->tensors[0].data_gpu;
-    if (!same) {
+    graph_key_check(net);
+    if (ctx->fwd_graph_input != (const void *)net->tensors[0].data_gpu) {
         forward_graph_drop(ctx);
-        ctx->fwd_graph_nodes = net->num_nodes;
-        ctx->fwd_graph_tensors = net->num_tensors;
-        ctx->fwd_graph_math = ctx->conv_math;
         ctx->fwd_graph_input = net->tensors[0].data_gpu;
     }
     if (!ctx->fwd_graph) {
@@ -323,7 +334,8 @@ void bcnn_b200_set_graphs(bcnn_net *net, int on) {
 
 int bcnn_b200_get_graphs(bcnn_net *net) {
     bcnn_cuda_context *ctx = bcnn_ctx(net);
-    return !ctx->graphs ? 0 : (ctx->fwd_graph ? 2 : 1);
+    const int live = ctx->fwd_graph || ctx->step_graph[0].exec || ctx->step_graph[1].exec;
+    return !ctx->graphs ? 0 : (live ? 2 : 1);
 }
 
 void bcnn_backward(bcnn_net *net) {
@@ -542,11 +554,56 @@ static void pipeline_swap_in(bcnn_net *net) {
     bcnn_cuda_check(bcnn_b200_event_record(ctx->evt_consumed, ctx->stream));
 }
 
+/* forward + backward of a training step through a CUDA graph; see bcnn_cuda_context.step_graph.
+ * Returns 1 when the two passes were run (replayed), 0 when the caller runs them eagerly. */
+static int train_graph(bcnn_net *net) {
+    bcnn_cuda_context *ctx = bcnn_ctx(net);
+    if (!ctx->graphs || net->mode != BCNN_MODE_TRAIN || ctx->profile || ctx->dp ||
+        net->num_inputs != 1 || net->num_nodes == 0)
+        return 0;
+    graph_key_check(net);
+    if (!ctx->step_graph_warm) { /* first step of this configuration: eager (lazy allocations) */
+        ctx->step_graph_warm = 1;
+        return 0;
+    }
+    const void *input = net->tensors[0].data_gpu, *label = net->tensors[1].data_gpu;
+    int slot = -1;
+    for (int i = 0; i < 2; ++i)
+        if (ctx->step_graph[i].exec && ctx->step_graph[i].input == input &&
+            ctx->step_graph[i].label == label)
+            slot = i;
+    if (slot < 0) {
+        slot = ctx->step_graph_next;
+        ctx->step_graph_next ^= 1;
+        bcnn_b200_graph_destroy(ctx->step_graph[slot].exec);
+        ctx->step_graph[slot].exec = NULL;
+        grad_state_sync(net);
+        if (bcnn_b200_graph_begin(ctx->stream) != 0) {
+            ctx->graphs = 0;
+            return 0;
+        }
+        forward_nodes(net);
+        bcnn_backward(net);
+        ctx->step_graph[slot].exec = bcnn_b200_graph_end(ctx->stream);
+        if (!ctx->step_graph[slot].exec) {
+            BCNN_WARNING(net->log_ctx, "CUDA graph capture of the training step failed; running eagerly\n");
+            ctx->graphs = 0;
+            return 0;
+        }
+        ctx->step_graph[slot].input = input;
+        ctx->step_graph[slot].label = label;
+    }
+    bcnn_cuda_check(bcnn_b200_graph_launch(ctx->step_graph[slot].exec, ctx->stream));
+    return 1;
+}
+
 float bcnn_b200_train_step(bcnn_net *net, int upload_inputs, int fetch_loss) {
     if (upload_inputs == 2) pipeline_swap_in(net);
     else if (upload_inputs) bcnn_b200_upload_inputs(net);
-    bcnn_forward(net);
-    bcnn_backward(net);
+    if (!train_graph(net)) {
+        bcnn_forward(net);
+        bcnn_backward(net);
+    }
     bcnn_update(net);
     if (upload_inputs == 2) pipeline_prefetch(net);
     float loss = fetch_loss ? bcnn_b200_get_loss(net) : 0.f;

@@ -55,6 +55,14 @@ typedef struct bcnn_cuda_context {
      * later one is a single cudaGraphLaunch. The key (nodes, tensors, math, input buffer)
      * invalidates the graph when the net changes. graphs: 1 = on (default), 0 = off. */
     int graphs;
+    /* TRAIN: forward + backward of bcnn_b200_train_step / bcnn_train_on_batch as a graph (small
+     * nets -- the reference's own mnist / cifar examples -- are launch-bound: ~100 kernels in
+     * well under a millisecond). The update stays eager: its scalars (learning-rate schedule,
+     * Adam bias correction) change every step. Two slots, keyed by the input / label buffers,
+     * because the input pipeline alternates two sets of them. Not used with data parallelism
+     * (the all-reduce lives on a second stream), per-node profiling or extra inputs. */
+    struct { void *exec; const void *input, *label; } step_graph[2];
+    int step_graph_warm, step_graph_next;
     void *fwd_graph;
     int fwd_graph_warm;
     int fwd_graph_nodes, fwd_graph_tensors, fwd_graph_math;

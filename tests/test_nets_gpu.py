@@ -312,3 +312,56 @@ def test_predict_forward_graph_replay_is_the_eager_forward(math):
     assert fast.graphs() == 1
     for net in nets:
         net.close()
+
+
+@pytest.mark.parametrize("case,math", [("mnist", capi.MATH_FP32), ("chain", capi.MATH_FP32),
+                                       ("chain", capi.MATH_TC), ("resnet", capi.MATH_TC)])
+def test_train_step_graph_replay_is_the_eager_step(case, math):
+    """bcnn_b200_train_step: 1st step eager, then forward + backward are captured per input
+    buffer (the input pipeline alternates two) and replayed; the update stays eager. Losses and
+    every parameter must be bit-identical to a graph-free twin over upload-then-step and
+    pipelined steps, with a fresh batch every step."""
+    def build(net):
+        if case == "mnist":
+            return configs.mnist(net, batch=8)
+        if case == "chain":
+            return netcases.chain_convnet(net, batch=4)
+        net.set_reference_quirks(False)
+        return netcases.small_resnet(net, batch=4)
+
+    nets = []
+    for graphs in (True, False):
+        net = capi.Net()
+        net.set_graphs(graphs)
+        net.set_conv_math(math)
+        build(net)
+        net.compile()
+        configs.init_params(net, seed=21)
+        nets.append(net)
+    fast, eager = nets
+    y = configs.synth_labels(fast.shape("label"))
+    batches = [configs.synth_input(fast.shape("input"), seed=70 + i) for i in range(9)]
+    for step in range(4):                      # upload, then step (one input buffer)
+        losses = []
+        for net in nets:
+            net.set_host("input", batches[step])
+            net.set_host("label", y)
+            losses.append(net.train_step(upload_inputs=True, fetch_loss=True))
+        assert losses[0] == losses[1], (step, losses)
+    assert fast.graphs() == 2 and eager.graphs() == 0
+    for net in nets:                           # pipelined: two input buffers alternate
+        net.set_host("input", batches[4])
+        net.prefetch_inputs()
+    for step in range(4, 8):
+        losses = []
+        for net in nets:
+            net.set_host("input", batches[step + 1])
+            losses.append(net.train_step(upload_inputs=2, fetch_loss=True))
+        assert losses[0] == losses[1], (step, losses)
+    for idx, name, _ in configs.param_tensors(fast):
+        assert np.array_equal(fast.get(idx), eager.get(idx)), name
+    fast.forward()                             # the plain loops still work beside the graphs
+    eager.forward()
+    assert np.array_equal(fast.get("cost"), eager.get("cost"))
+    for net in nets:
+        net.close()
