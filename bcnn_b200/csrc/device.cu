@@ -117,8 +117,10 @@ void *bcnn_b200_graph_end(void *s) {
     }
     return (void *)exec;
 }
-int bcnn_b200_graph_launch(void *exec, void *s) {
-    ++g_launch_count;
+// `kernels` = the launches that were recorded into the graph: a replay executes that many kernels,
+// and bcnn_b200_launch_count() keeps counting kernels, not graph launches.
+int bcnn_b200_graph_launch(void *exec, unsigned long long kernels, void *s) {
+    g_launch_count += kernels;
     return (int)cudaGraphLaunch((cudaGraphExec_t)exec, as_stream(s));
 }
 void bcnn_b200_graph_destroy(void *exec) {

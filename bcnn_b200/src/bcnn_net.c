@@ -299,7 +299,9 @@ static int forward_graph(bcnn_net *net) {
         forward_graph_drop(ctx);
         ctx->fwd_graph_input = net->tensors[0].data_gpu;
     }
+    int recorded_now = 0; /* the capture itself already counted its launches once */
     if (!ctx->fwd_graph) {
+        recorded_now = 1;
         if (!ctx->fwd_graph_warm) { /* first forward of this configuration: eager */
             ctx->fwd_graph_warm = 1;
             return 0;
@@ -308,7 +310,9 @@ static int forward_graph(bcnn_net *net) {
             ctx->graphs = 0;
             return 0;
         }
+        const unsigned long long before = bcnn_b200_launch_count();
         forward_nodes(net);
+        ctx->fwd_graph_kernels = bcnn_b200_launch_count() - before;
         ctx->fwd_graph = bcnn_b200_graph_end(ctx->stream);
         if (!ctx->fwd_graph) { /* capture refused: stay eager for the rest of this net's life */
             BCNN_WARNING(net->log_ctx, "CUDA graph capture of the forward pass failed; running eagerly\n");
@@ -316,7 +320,8 @@ static int forward_graph(bcnn_net *net) {
             return 0;
         }
     }
-    bcnn_cuda_check(bcnn_b200_graph_launch(ctx->fwd_graph, ctx->stream));
+    bcnn_cuda_check(bcnn_b200_graph_launch(ctx->fwd_graph, recorded_now ? 0 : ctx->fwd_graph_kernels,
+                                           ctx->stream));
     return 1;
 }
 
@@ -567,7 +572,7 @@ static int train_graph(bcnn_net *net) {
         return 0;
     }
     const void *input = net->tensors[0].data_gpu, *label = net->tensors[1].data_gpu;
-    int slot = -1;
+    int slot = -1, recorded_now = 0;
     for (int i = 0; i < 2; ++i)
         if (ctx->step_graph[i].exec && ctx->step_graph[i].input == input &&
             ctx->step_graph[i].label == label)
@@ -582,8 +587,10 @@ static int train_graph(bcnn_net *net) {
             ctx->graphs = 0;
             return 0;
         }
+        const unsigned long long before = bcnn_b200_launch_count();
         forward_nodes(net);
         bcnn_backward(net);
+        ctx->step_graph[slot].kernels = bcnn_b200_launch_count() - before;
         ctx->step_graph[slot].exec = bcnn_b200_graph_end(ctx->stream);
         if (!ctx->step_graph[slot].exec) {
             BCNN_WARNING(net->log_ctx, "CUDA graph capture of the training step failed; running eagerly\n");
@@ -592,8 +599,10 @@ static int train_graph(bcnn_net *net) {
         }
         ctx->step_graph[slot].input = input;
         ctx->step_graph[slot].label = label;
+        recorded_now = 1;
     }
-    bcnn_cuda_check(bcnn_b200_graph_launch(ctx->step_graph[slot].exec, ctx->stream));
+    bcnn_cuda_check(bcnn_b200_graph_launch(ctx->step_graph[slot].exec,
+                                           recorded_now ? 0 : ctx->step_graph[slot].kernels, ctx->stream));
     return 1;
 }
 

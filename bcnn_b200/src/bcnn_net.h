@@ -61,7 +61,8 @@ typedef struct bcnn_cuda_context {
      * Adam bias correction) change every step. Two slots, keyed by the input / label buffers,
      * because the input pipeline alternates two sets of them. Not used with data parallelism
      * (the all-reduce lives on a second stream), per-node profiling or extra inputs. */
-    struct { void *exec; const void *input, *label; } step_graph[2];
+    struct { void *exec; const void *input, *label; unsigned long long kernels; } step_graph[2];
+    unsigned long long fwd_graph_kernels;
     int step_graph_warm, step_graph_next;
     void *fwd_graph;
     int fwd_graph_warm;

@@ -440,6 +440,8 @@ def run_own_arm(args):
     # (inputs + labels) from the pinned host mirrors on the copy stream while it computes on the
     # batch staged by the previous step, and reads its loss back. The prologue stages batch 0.
     net.prefetch_inputs()
+    for _ in range(args.warmup):  # the pipelined mode has its own warm-up: it alternates two input
+        net.train_step(upload_inputs=2, fetch_loss=True)  # buffers, each with its own step graph
     barrier()
     lib.bcnn_b200_event_record(e0, stream)
     loss = 0.0

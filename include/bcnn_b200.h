@@ -94,7 +94,9 @@ BCNN_B200_API float bcnn_b200_event_elapsed_ms(void *start, void *stop);
  * not executed until the graph is launched. */
 BCNN_B200_API int bcnn_b200_graph_begin(void *stream);
 BCNN_B200_API void *bcnn_b200_graph_end(void *stream);
-BCNN_B200_API int bcnn_b200_graph_launch(void *graph_exec, void *stream);
+/* kernels: how many launches the graph holds (added to bcnn_b200_launch_count per replay). */
+BCNN_B200_API int bcnn_b200_graph_launch(void *graph_exec, unsigned long long kernels,
+                                         void *stream);
 BCNN_B200_API void bcnn_b200_graph_destroy(void *graph_exec);
 BCNN_B200_API const char *bcnn_b200_error_string(int err);
 /* number of kernels this library has launched in this process (bench.py's

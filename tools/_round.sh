@@ -1,3 +1,3 @@
-mkdir -p gpurun_out/r1n
-timeout 240 python -m pytest tests -m gpu -x -q > gpurun_out/r1n/gpu_tests.log 2>&1; echo "tests rc=$?" >> gpurun_out/r1n/gpu_tests.log; tail -25 gpurun_out/r1n/gpu_tests.log
-timeout 200 python bench.py --workload yolo_tiny --batch 8 --res 416 --no-rooflines > gpurun_out/r1n/bench_yolo_b8.json 2> gpurun_out/r1n/bench_yolo.err; echo "rc=$?"; cut -c1-330 gpurun_out/r1n/bench_yolo_b8.json; grep -v "Yolo Avg" gpurun_out/r1n/bench_yolo.err | tail -3
+mkdir -p gpurun_out/r1p
+timeout 300 python bench.py > gpurun_out/r1p/bench_n1.json 2> gpurun_out/r1p/bench_n1.err; echo "bench rc=$?"; cut -c1-260 gpurun_out/r1p/bench_n1.json; grep -o '"e2e": {[^}]*}' gpurun_out/r1p/bench_n1.json; grep -o '"gpu_launches": [0-9]*' gpurun_out/r1p/bench_n1.json; tail -3 gpurun_out/r1p/bench_n1.err
+timeout 60 python -c "import __graft_entry__ as g; g.smoke()" 2>&1 | tail -2

@@ -39,7 +39,7 @@ int bcnn_b200_stream_wait_event(void *, void *) { return 0; }
 float bcnn_b200_event_elapsed_ms(void *, void *) { return 0.f; }
 int bcnn_b200_graph_begin(void *) { return 1; }  // no capture on the host: the runtime stays eager
 void *bcnn_b200_graph_end(void *) { return nullptr; }
-int bcnn_b200_graph_launch(void *, void *) { return 1; }
+int bcnn_b200_graph_launch(void *, unsigned long long, void *) { return 1; }
 void bcnn_b200_graph_destroy(void *) {}
 const char *bcnn_b200_error_string(int) { return "host stub: no device"; }
 uint64_t bcnn_b200_launch_count(void) { return b200::g_launch_count; }
