@@ -1,7 +1,9 @@
 """Development check of the C host runtime without a GPU: drives tools/hoststub/libbcnn_hoststub.so
 (real bcnn_b200/src/**/*.c, host-memory device stub) and the compiled reference side by side.
 Covers what needs no kernels: weight files (save bytes, load, PREDICT fold, Darknet layout and
-transpose, error statuses) and the optimizer dispatch (SGD / Adam from injected gradients).
+transpose, error statuses), the optimizer dispatch (SGD / Adam from injected gradients), config
+files (graphs and error statuses in both dialects), bcnn_yolo_get_detections and the host
+restatement of the yolo loss on the reference's own head tensors.
 Usage: tools/hoststub/build.sh && python tools/hoststub/check_host_logic.py"""
 import ctypes as C
 import sys
@@ -124,4 +126,78 @@ for opt in ("sgd", "adam"):
                 assert np.array_equal(po[k], pr[k]), (opt, step, k)
     print(f"update[{opt}]: worst max-abs / max over 3 steps = {worst:.3e}")
     assert worst < 2e-6
+
+# --- config files: same graph, same status, both dialects ---
+import contextlib
+import os
+
+CFG = ROOT / "tests" / "golden" / "cfg"
+
+
+@contextlib.contextmanager
+def quiet():  # the reference's yolo code prints to stderr
+    devnull, saved = os.open(os.devnull, os.O_WRONLY), os.dup(2)
+    os.dup2(devnull, 2)
+    try:
+        yield
+    finally:
+        os.dup2(saved, 2)
+        os.close(devnull)
+        os.close(saved)
+
+
+def pair(mode):
+    return capi.Net(mode=mode, lib=stub), helpers.ref_net(mode=mode)
+
+
+for mode, cfg, model in ((capi.MODE_TRAIN, "mini_bcnn.conf", None),
+                         (capi.MODE_PREDICT, "mini_yolo.cfg", CFG / "mini_yolo.weights"),
+                         (capi.MODE_TRAIN, "mini_yolo.cfg", CFG / "mini_yolo.weights"),
+                         (capi.MODE_PREDICT, "mini_yolo.cfg", tmp / "absent.weights")):
+    a, b = pair(mode)
+    sa, sb = a.load_net(CFG / cfg, model), b.load_net(CFG / cfg, model)
+    assert sa == sb and a.structure() == b.structure(), (cfg, mode, sa, sb)
+    if sa == 0 and model is not None:  # without a model the weights are each library's rand() draws
+        same(params(a), params(b), f"{cfg} parameters after load_net")
+print("load_net: graphs, statuses and loaded parameters identical to the reference (bcnn + Darknet)")
+
+# --- detections and yolo loss on the reference's own head tensors ---
+g = dict(np.load(CFG / "mini_yolo_train.npz"))
+heads = dict(np.load(CFG / "mini_yolo.npz"))
+a, b = pair(capi.MODE_PREDICT)
+for n in (a, b):
+    assert n.load_net(CFG / "mini_yolo.cfg", CFG / "mini_yolo.weights") == 0
+    n.compile()
+    n.set("lid10", heads["lid10"])
+    n.set("lid17", heads["lid17"])
+for thresh, (w, h), rel in ((0.5, (640, 480), True), (0.3, (300, 500), False), (-1.0, (64, 48), True),
+                            (0.9999, (10, 10), True)):
+    for sample in range(2):
+        with quiet():
+            da = a.yolo_detections(sample, w, h, thresh, rel)
+            db = b.yolo_detections(sample, w, h, thresh, rel)
+        assert da.shape == db.shape and np.array_equal(da.view(np.uint32), db.view(np.uint32))
+print("yolo detections: boxes, scores and NMS order bit-identical to the reference")
+
+a = capi.Net(mode=capi.MODE_TRAIN, lib=stub)
+assert a.load_net(CFG / "mini_yolo.cfg", CFG / "mini_yolo.weights") == 0
+a.compile()
+for label in (g["label"], configs.synth_yolo_labels(2, [50, 0], classes=2, seed=5)):
+    b = helpers.ref_net(mode=capi.MODE_TRAIN)
+    assert b.load_net(CFG / "mini_yolo.cfg", CFG / "mini_yolo.weights") == 0
+    b.compile()
+    b.set("input", g["input"])
+    b.set("label", label)
+    with quiet():
+        b.forward()
+    a.set("label", label)
+    nodes = [i for i, (kind, _, _) in enumerate(a.structure()["nodes"]) if kind == 14]
+    for node, name in zip(nodes, ("lid10", "lid17")):
+        a.set(name, b.get(name))
+        cost = stub.bcnn_b200_yolo_loss_on_host(a.handle, node)
+        want = b.get(name, grad=True)
+        got = a.get(name, grad=True)
+        assert np.array_equal(got.view(np.uint32), want.view(np.uint32)), name
+        assert abs(cost - float((want.astype(np.float64) ** 2).sum())) <= 1e-5 * cost
+print("yolo loss (host loops): gradient bit-identical to the reference")
 print("OK")
