@@ -351,6 +351,12 @@ class Net:
         error paths."""
         return int(self.lib.bcnn_load_weights(self.handle, _b(str(path))))
 
+    def lr_policy(self, decay_type: int, gamma=0.0, scale=0.0, power=0.0, max_batches=0, step=0):
+        """bcnn_set_learning_rate_policy; decay_type: 0 constant, 1 step, 2 inv, 3 exp, 4 poly,
+        5 sigmoid (bcnn_lr_decay)."""
+        self.lib.bcnn_set_learning_rate_policy(self.handle, decay_type, gamma, scale, power,
+                                               max_batches, step)
+
     def compile(self):
         self._check(self.lib.bcnn_compile_net(self.handle), "bcnn_compile_net")
 

@@ -43,7 +43,7 @@ def test_host_logic_matches_the_reference(stub):
                           capture_output=True, text=True, timeout=300)
     assert proc.returncode == 0, proc.stdout[-2000:] + proc.stderr[-2000:]
     for line in ("save: byte-identical", "PREDICT fold bit-identical", "Darknet files",
-                 "update[adam]", "load_net: graphs", "yolo detections", "yolo loss (host loops)", "OK"):
+                 "update[adam]", "learning-rate policies", "load_net: graphs", "yolo detections", "yolo loss (host loops)", "OK"):
         assert line in proc.stdout, line
 
 

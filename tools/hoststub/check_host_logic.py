@@ -127,6 +127,28 @@ for opt in ("sgd", "adam"):
     print(f"update[{opt}]: worst max-abs / max over 3 steps = {worst:.3e}")
     assert worst < 2e-6
 
+# --- learning-rate schedules (bcnn_set_learning_rate_policy): five SGD steps per policy ---
+policies = {"step": (1, dict(scale=0.5, step=2)), "inv": (2, dict(gamma=0.3, power=0.75)),
+            "exp": (3, dict(gamma=0.9)), "poly": (4, dict(power=2.0, max_batches=8)),
+            "sigmoid": (5, dict(gamma=0.7, step=3)), "constant": (0, {})}
+for name, (kind, kw) in policies.items():
+    ours6, ref6 = nets(capi.MODE_TRAIN)
+    for n in (ours6, ref6):
+        n.lr_policy(kind, **kw)
+        configs.init_params(n, seed=8)
+    for step in range(5):
+        rng = np.random.default_rng(300 + step)
+        for idx, pname, shape in configs.param_tensors(ours6):
+            if not ours6._tensor(idx).grad_data:
+                continue
+            g = rng.normal(0, 1e-2, size=shape).astype(np.float32)
+            for n in (ours6, ref6):
+                n.set(idx, n.get(idx, grad=True) + g, grad=True)
+        ours6.update()
+        ref6.update()
+    same(params(ours6), params(ref6), f"lr policy {name}")
+print("update: learning-rate policies (step / inv / exp / poly / sigmoid / constant) bit-identical")
+
 # --- config files: same graph, same status, both dialects ---
 import contextlib
 import os
