@@ -114,13 +114,22 @@ void bcnn_optimizer_step_gpu(bcnn_net *net, bcnn_tensor *weights, bcnn_tensor *b
     }
 }
 
-void bcnn_update(bcnn_net *net) {
-    update_learning_rate(net);
-    bcnn_dp_before_update(net);
+/* The two halves of bcnn_update (reference :167-175): the host bookkeeping (samples seen,
+ * learning-rate schedule) and the per-node update kernels. The step graph of
+ * bcnn_b200_train_step records the kernels and replays them; the bookkeeping runs every step. */
+void bcnn_update_schedule(bcnn_net *net) { update_learning_rate(net); }
+
+void bcnn_update_nodes(bcnn_net *net) {
     for (int i = 0; i < net->num_nodes; ++i) {
         bcnn_node *node = &net->nodes[i];
         if (node->update) node->update(net, node);
     }
+}
+
+void bcnn_update(bcnn_net *net) {
+    bcnn_update_schedule(net);
+    bcnn_dp_before_update(net);
+    bcnn_update_nodes(net);
 }
 
 static bcnn_learner *learner_of(bcnn_net *net) {

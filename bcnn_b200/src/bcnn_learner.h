@@ -32,6 +32,10 @@ extern "C" {
 void bcnn_sgd_update_gpu(bcnn_net *net, float *weights, float *biases, float *weights_grad,
                          float *biases_grad, int weights_size, int biases_size, int batch_size,
                          float learning_rate, float momentum, float decay);
+/* bcnn_update = bcnn_update_schedule (host: samples seen, learning-rate policy) + the
+ * data-parallel join + bcnn_update_nodes (the per-node update kernels). */
+void bcnn_update_schedule(bcnn_net *net);
+void bcnn_update_nodes(bcnn_net *net);
 /* Device Adam step; argument meaning of reference bcnn_adam_update_gpu (src/bcnn_learner.c:
  * 134-164) plus the net. */
 void bcnn_adam_update_gpu(bcnn_net *net, float *weights, float *biases, float *weights_grad,

@@ -559,8 +559,9 @@ static void pipeline_swap_in(bcnn_net *net) {
     bcnn_cuda_check(bcnn_b200_event_record(ctx->evt_consumed, ctx->stream));
 }
 
-/* forward + backward of a training step through a CUDA graph; see bcnn_cuda_context.step_graph.
- * Returns 1 when the two passes were run (replayed), 0 when the caller runs them eagerly. */
+/* forward + backward (+ the update kernels) of a training step through a CUDA graph; see
+ * bcnn_cuda_context.step_graph. Returns 0 when the caller runs the step eagerly, 1 when forward
+ * and backward were replayed, 2 when the update kernels were replayed with them. */
 static int train_graph(bcnn_net *net) {
     bcnn_cuda_context *ctx = bcnn_ctx(net);
     if (!ctx->graphs || net->mode != BCNN_MODE_TRAIN || ctx->profile || ctx->dp ||
@@ -572,10 +573,16 @@ static int train_graph(bcnn_net *net) {
         return 0;
     }
     const void *input = net->tensors[0].data_gpu, *label = net->tensors[1].data_gpu;
+    const bcnn_learner *ln = net->learner;
+    const int with_update = ln && ln->optimizer == BCNN_OPTIM_SGD &&
+                            ln->decay_type == BCNN_LR_DECAY_CONSTANT;
     int slot = -1, recorded_now = 0;
     for (int i = 0; i < 2; ++i)
         if (ctx->step_graph[i].exec && ctx->step_graph[i].input == input &&
-            ctx->step_graph[i].label == label)
+            ctx->step_graph[i].label == label && ctx->step_graph[i].with_update == with_update &&
+            (!with_update || (ctx->step_graph[i].lr == ln->learning_rate &&
+                              ctx->step_graph[i].momentum == ln->momentum &&
+                              ctx->step_graph[i].decay == ln->decay)))
             slot = i;
     if (slot < 0) {
         slot = ctx->step_graph_next;
@@ -590,6 +597,7 @@ static int train_graph(bcnn_net *net) {
         const unsigned long long before = bcnn_b200_launch_count();
         forward_nodes(net);
         bcnn_backward(net);
+        if (with_update) bcnn_update_nodes(net);
         ctx->step_graph[slot].kernels = bcnn_b200_launch_count() - before;
         ctx->step_graph[slot].exec = bcnn_b200_graph_end(ctx->stream);
         if (!ctx->step_graph[slot].exec) {
@@ -599,21 +607,29 @@ static int train_graph(bcnn_net *net) {
         }
         ctx->step_graph[slot].input = input;
         ctx->step_graph[slot].label = label;
+        ctx->step_graph[slot].with_update = with_update;
+        if (with_update) {
+            ctx->step_graph[slot].lr = ln->learning_rate;
+            ctx->step_graph[slot].momentum = ln->momentum;
+            ctx->step_graph[slot].decay = ln->decay;
+        }
         recorded_now = 1;
     }
     bcnn_cuda_check(bcnn_b200_graph_launch(ctx->step_graph[slot].exec,
                                            recorded_now ? 0 : ctx->step_graph[slot].kernels, ctx->stream));
-    return 1;
+    return with_update ? 2 : 1;
 }
 
 float bcnn_b200_train_step(bcnn_net *net, int upload_inputs, int fetch_loss) {
     if (upload_inputs == 2) pipeline_swap_in(net);
     else if (upload_inputs) bcnn_b200_upload_inputs(net);
-    if (!train_graph(net)) {
+    const int replayed = train_graph(net);
+    if (!replayed) {
         bcnn_forward(net);
         bcnn_backward(net);
     }
-    bcnn_update(net);
+    if (replayed == 2) bcnn_update_schedule(net); /* the kernels ran inside the graph */
+    else bcnn_update(net);
     if (upload_inputs == 2) pipeline_prefetch(net);
     float loss = fetch_loss ? bcnn_b200_get_loss(net) : 0.f;
     /* the host mirrors may be refilled once the call returns */

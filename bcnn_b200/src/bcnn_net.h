@@ -57,11 +57,21 @@ typedef struct bcnn_cuda_context {
     int graphs;
     /* TRAIN: forward + backward of bcnn_b200_train_step / bcnn_train_on_batch as a graph (small
      * nets -- the reference's own mnist / cifar examples -- are launch-bound: ~100 kernels in
-     * well under a millisecond). The update stays eager: its scalars (learning-rate schedule,
-     * Adam bias correction) change every step. Two slots, keyed by the input / label buffers,
+     * well under a millisecond). The update kernels join the graph when their scalars cannot
+     * change (SGD with a constant learning rate); otherwise (schedules, Adam's bias correction)
+     * the update stays eager. Two slots, keyed by the input / label buffers,
      * because the input pipeline alternates two sets of them. Not used with data parallelism
      * (the all-reduce lives on a second stream), per-node profiling or extra inputs. */
-    struct { void *exec; const void *input, *label; unsigned long long kernels; } step_graph[2];
+    struct {
+        void *exec;
+        const void *input, *label;
+        unsigned long long kernels;
+        /* with_update: the SGD update kernels are part of the graph (constant learning rate
+         * only: their scalars are then the same every step); lr / momentum / decay are the
+         * values they were recorded with and part of the key */
+        int with_update;
+        float lr, momentum, decay;
+    } step_graph[2];
     unsigned long long fwd_graph_kernels;
     int step_graph_warm, step_graph_next;
     void *fwd_graph;

@@ -360,6 +360,20 @@ def test_train_step_graph_replay_is_the_eager_step(case, math):
         assert losses[0] == losses[1], (step, losses)
     for idx, name, _ in configs.param_tensors(fast):
         assert np.array_equal(fast.get(idx), eager.get(idx)), name
+    # the SGD update kernels ride in the graph while the learning rate is constant: a new rate
+    # must re-record them, a schedule must take them out again
+    for phase, change in enumerate((lambda n: n.sgd(0.02, 0.8, 0.001),
+                                    lambda n: n.lr_policy(1, scale=0.5, step=1))):
+        for net in nets:
+            change(net)
+        for step in range(3):
+            losses = []
+            for net in nets:
+                net.set_host("input", batches[step])
+                losses.append(net.train_step(upload_inputs=True, fetch_loss=True))
+            assert losses[0] == losses[1], (phase, step, losses)
+        for idx, name, _ in configs.param_tensors(fast):
+            assert np.array_equal(fast.get(idx), eager.get(idx)), (phase, name)
     fast.forward()                             # the plain loops still work beside the graphs
     eager.forward()
     assert np.array_equal(fast.get("cost"), eager.get("cost"))
