@@ -1,3 +1,4 @@
-mkdir -p gpurun_out/r1r
-timeout 120 python -m pytest tests/test_dp.py -m gpu -x -q 2>&1 | tail -3
-timeout 200 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29517 bench.py --gpus 2 --steps 5 --warmup 3 --no-rooflines --no-cpu-baseline > gpurun_out/r1r/bench_n2.json 2> gpurun_out/r1r/bench_n2.err; echo "rc=$?"; cut -c1-200 gpurun_out/r1r/bench_n2.json; grep -o '"e2e": {[^}]*}' gpurun_out/r1r/bench_n2.json; tail -3 gpurun_out/r1r/bench_n2.err
+mkdir -p gpurun_out/r1s
+timeout 120 python -m pytest tests -m gpu -x -q > gpurun_out/r1s/gpu_tests.log 2>&1; echo "tests rc=$?" >> gpurun_out/r1s/gpu_tests.log; tail -8 gpurun_out/r1s/gpu_tests.log
+timeout 40 python bench.py --workload mnist --batch 64 --res 28 --no-rooflines --no-cpu-baseline --steps 50 --warmup 5 2>/dev/null | cut -c1-130 | tee gpurun_out/r1s/bench_mnist.txt
+timeout 40 python bench.py --workload cifar --batch 128 --res 32 --no-rooflines --no-cpu-baseline --steps 50 --warmup 5 2>/dev/null | cut -c1-130 | tee gpurun_out/r1s/bench_cifar.txt
