@@ -36,11 +36,16 @@ BCNN_B200_API void bcnn_b200_set_reference_quirks(bcnn_net *net, int on);
  * input_width | width, input_height | height, input_channels | channels, batch_size | batch.
  * Augmentation keys belong to the file loader and are ignored. */
 BCNN_B200_API void bcnn_net_set_param(bcnn_net *net, const char *name, const char *val);
-/* CUDA-graph replay of the PREDICT-mode forward (default on; env BCNN_B200_GRAPHS=0 or
- * on = 0 turns it off). The first bcnn_forward of a configuration launches its kernels one by
- * one, the second is captured, later ones are one graph launch; the graph is rebuilt when
- * nodes / tensors / conv math / the input buffer change. Results are identical to the eager
- * path (same kernels, same order). get: 0 = off, 1 = on, 2 = on and a graph is live. */
+/* CUDA-graph replay (default on; env BCNN_B200_GRAPHS=0 or on = 0 turns it off).
+ *   PREDICT: the first bcnn_forward of a configuration launches its kernels one by one, the
+ *     second is captured, later ones are one graph launch.
+ *   TRAIN: bcnn_b200_train_step / bcnn_train_on_batch do the same with forward + backward (one
+ *     graph per input buffer of the pipeline) and add the SGD update kernels while the learning
+ *     rate is constant. Plain bcnn_forward / bcnn_backward calls are never captured in TRAIN
+ *     mode; data-parallel nets, nets being profiled and nets with extra inputs run eagerly.
+ * Graphs are rebuilt when nodes / tensors / conv math / buffers / solver scalars change.
+ * Results are identical to the eager path (same kernels, same order).
+ * get: 0 = off, 1 = on, 2 = on and a graph is live. */
 BCNN_B200_API void bcnn_b200_set_graphs(bcnn_net *net, int on);
 BCNN_B200_API int bcnn_b200_get_graphs(bcnn_net *net);
 /* The CUDA stream (cudaStream_t) every kernel of this net is launched on. */
