@@ -172,7 +172,7 @@ static int for_each_token(const char *val, int max, void (*each)(const char *, i
     return n > max ? max : n;
 }
 
-typedef struct { layer_desc *d; int section; char names[CFG_MAX_SRCS][32]; } route_ctx;
+typedef struct { layer_desc *d; int section; char names[CFG_MAX_SRCS][256]; } route_ctx;
 
 static void take_anchor(const char *tok, int i, void *arg) { ((layer_desc *)arg)->anchors[i] = (float)atof(tok); }
 static void take_mask(const char *tok, int i, void *arg) { ((layer_desc *)arg)->anchors_mask[i] = atoi(tok); }
@@ -369,6 +369,8 @@ static bcnn_status add_layer(bcnn_net *net, const char *name, const layer_desc *
             return bcnn_add_eltwise_layer(net, (bcnn_activation)d->a, d->src_id[0], d->src_id[1],
                                           dst);
         case SEC_YOLO:
+            BCNN_CHECK_AND_LOG(net->log_ctx, d->num_anchors <= CFG_MAX_ANCHORS, BCNN_INVALID_PARAMETER,
+                               "Yolo layer: more than %d anchors\n", CFG_MAX_ANCHORS);
             return bcnn_add_yolo_layer(net, d->boxes_per_cell, d->num_classes, d->num_coords,
                                        d->num_anchors, (int *)d->anchors_mask,
                                        d->num_anchor_values ? (float *)d->anchors : NULL, src, dst);

@@ -36,6 +36,9 @@ bcnn_status bcnn_add_yolo_layer(bcnn_net *net, int num_boxes_per_cell, int class
     BCNN_CHECK_AND_LOG(net->log_ctx,
                        num_boxes_per_cell > 0 && classes >= 0 && coords >= 2 && total > 0 && mask,
                        BCNN_INVALID_PARAMETER, "Yolo layer: invalid box / class / anchor counts\n");
+    for (int k = 0; k < num_boxes_per_cell; ++k) /* the kernels index the anchor table with these */
+        BCNN_CHECK_AND_LOG(net->log_ctx, mask[k] >= 0 && mask[k] < total, BCNN_INVALID_PARAMETER,
+                           "Yolo layer: mask entry %d outside the %d anchors\n", mask[k], total);
     BCNN_CHECK_STATUS(bcnn_node_add_input(net, &node, src));
     const int n = net->tensors[src].n, c = net->tensors[src].c, h = net->tensors[src].h,
               w = net->tensors[src].w;
