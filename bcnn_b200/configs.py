@@ -6,9 +6,8 @@ calls a bcnn user would write:
   cifar      -- reference examples/cifar10/cifar10_example.c:32-63 simple_net (configs[1])
   mobilenet  -- MobileNet-v1 224 as bcnn layers (configs[2]; no cfg ships with the
                 reference, synthesised per SURVEY.md section 8 / Appendix A)
-  yolo_tiny  -- trunk + first head of examples/yolo/yolov3-tiny.cfg (configs[3]); the yolo
-                loss layer is host logic in the reference and out of scope, so training
-                runs end in a euclidean cost on the head's 255-channel map
+  yolo_tiny  -- examples/yolo/yolov3-tiny.cfg (configs[3]): trunk, both heads, both yolo layers
+                (detection loss against box labels in TRAIN mode)
   resnet50   -- ResNet-50 v1.5 224 as bcnn layers (configs[4], the headline workload)
 
 Synthetic inputs follow SURVEY.md 8d: FP32 uniform [-1,1) images, one-hot labels with

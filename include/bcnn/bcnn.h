@@ -5,9 +5,9 @@
  * and every function signature below is binary compatible with jnbraun/bcnn's
  * inc/bcnn/bcnn.h (enums :90-235, bcnn_tensor :242-255, functions :285-1043), so
  * a program written against bcnn links against libbcnn_b200.so unchanged for the
- * layer hot path. Only the functions that path needs are provided; the rest of
- * the reference API (file loaders, augmentation, cfg parser, yolo, ...) is out of
- * scope -- see DESIGN.md.
+ * layer hot path and for the files either side of it (weight files, cfg files,
+ * yolo detections). The rest of the reference API (file loaders, augmentation,
+ * deconv / dropout / lrn layers, ...) is out of scope -- see DESIGN.md.
  *
  * This library is always the CUDA flavour: BCNN_USE_CUDA is forced on, so
  * bcnn_tensor carries data_gpu / grad_data_gpu. Host mirrors of layer outputs
