@@ -22,36 +22,36 @@ from . import capi
 from .capi import PAD_SAME
 
 
-def mnist(net, batch=64):
+def mnist(net, batch=64, act="relu"):
     net.set_input_shape(28, 28, 1, batch)
-    net.conv(32, 3, 1, 1, 1, 0, "relu", "input", "conv1")
+    net.conv(32, 3, 1, 1, 1, 0, act, "input", "conv1")
     net.batchnorm("conv1", "bn1")
     net.maxpool(2, 2, PAD_SAME, "bn1", "pool1")
-    net.conv(32, 3, 1, 1, 1, 0, "relu", "pool1", "conv2")
+    net.conv(32, 3, 1, 1, 1, 0, act, "pool1", "conv2")
     net.batchnorm("conv2", "bn2")
     net.maxpool(2, 2, PAD_SAME, "bn2", "pool2")
-    net.fullc(256, "relu", "pool2", "fc1")
+    net.fullc(256, act, "pool2", "fc1")
     net.batchnorm("fc1", "bn3")
-    net.fullc(10, "relu", "bn3", "fc2")
+    net.fullc(10, act, "bn3", "fc2")
     net.softmax("fc2", "softmax")
     net.cost("softmax", "cost")
     net.sgd(0.003, 0.9, 0.0005)  # mnist_example.c:136-139
     return dict(classes=10, out="softmax")
 
 
-def cifar(net, batch=128):
+def cifar(net, batch=128, act="relu"):
     net.set_input_shape(32, 32, 3, batch)
-    net.conv(32, 3, 1, 1, 1, 1, "relu", "input", "conv1_1")
-    net.conv(32, 3, 1, 1, 1, 1, "relu", "conv1_1", "conv1_2")
-    net.conv(32, 3, 1, 1, 1, 1, "relu", "conv1_2", "conv1_3")
+    net.conv(32, 3, 1, 1, 1, 1, act, "input", "conv1_1")
+    net.conv(32, 3, 1, 1, 1, 1, act, "conv1_1", "conv1_2")
+    net.conv(32, 3, 1, 1, 1, 1, act, "conv1_2", "conv1_3")
     net.maxpool(2, 2, PAD_SAME, "conv1_3", "pool1")
-    net.conv(64, 3, 1, 1, 1, 1, "relu", "pool1", "conv2_1")
-    net.conv(64, 3, 1, 1, 1, 1, "relu", "conv2_1", "conv2_2")
-    net.conv(64, 3, 1, 1, 1, 1, "relu", "conv2_2", "conv2_3")
+    net.conv(64, 3, 1, 1, 1, 1, act, "pool1", "conv2_1")
+    net.conv(64, 3, 1, 1, 1, 1, act, "conv2_1", "conv2_2")
+    net.conv(64, 3, 1, 1, 1, 1, act, "conv2_2", "conv2_3")
     net.maxpool(2, 2, PAD_SAME, "conv2_3", "pool2")
-    net.fullc(512, "relu", "pool2", "fc1")
+    net.fullc(512, act, "pool2", "fc1")
     net.batchnorm("fc1", "bn3")
-    net.fullc(10, "relu", "bn3", "fc2")
+    net.fullc(10, act, "bn3", "fc2")
     net.softmax("fc2", "softmax")
     net.cost("softmax", "cost")
     # the example's "adam" call leaves the optimizer on SGD, momentum 0.9, lr 0.005
@@ -139,6 +139,32 @@ def resnet50(net, batch=256, res=224, classes=1000, widths=(64, 128, 256, 512),
         net.cost("softmax", "cost")
         net.sgd(0.005, 0.9, 0.0005)
     return dict(classes=classes, out="softmax")
+
+
+def yolov3_tiny_cfg(batch=1, width=416, height=416):
+    """The text of a Darknet-dialect YOLOv3-tiny config, generated from the layer list (the
+    reference ships the same network as examples/yolo/yolov3-tiny.cfg; tests/test_baseline_parity
+    checks on the CPU that both files make the reference build the identical graph). Keys the
+    reference's reader ignores (augmentation, burn-in, thresholds) are left out."""
+    def conv(filters, size, bn=1, act="leaky"):
+        head = "[convolutional]\n" + ("batch_normalize=1\n" if bn else "")
+        return head + f"filters={filters}\nsize={size}\nstride=1\npad=1\nactivation={act}\n"
+
+    def yolo(mask):
+        return ("[yolo]\nmask = %s\nanchors = 10,14,  23,27,  37,58,  81,82,  135,169,  344,319\n"
+                "classes=80\nnum=6\n" % ",".join(str(m) for m in mask))
+
+    sections = [f"[net]\nbatch={batch}\nsubdivisions=1\nwidth={width}\nheight={height}\nchannels=3\n"
+                "momentum=0.9\ndecay=0.0005\nlearning_rate=0.001\nmax_batches = 500200\n"
+                "policy=steps\nsteps=400000,450000\nscales=.1,.1\n"]
+    for i, c in enumerate([16, 32, 64, 128, 256, 512]):
+        sections.append(conv(c, 3))
+        sections.append(f"[maxpool]\nsize=2\nstride={2 if i < 5 else 1}\n")
+    sections += [conv(1024, 3), conv(256, 1), conv(512, 3), conv(255, 1, bn=0, act="linear"),
+                 yolo([3, 4, 5]), "[route]\nlayers = -4\n", conv(128, 1), "[upsample]\nstride=2\n",
+                 "[route]\nlayers = -1, 8\n", conv(256, 3), conv(255, 1, bn=0, act="linear"),
+                 yolo([0, 1, 2])]
+    return "\n".join(sections)
 
 
 BUILDERS = dict(mnist=mnist, cifar=cifar, mobilenet=mobilenet, yolo_tiny=yolo_tiny,

@@ -76,6 +76,13 @@ CASES = {
     "resnet_small_b4": (small_resnet, dict(batch=4), 2),
     "yolo_two_heads_b2": (yolo_two_heads, dict(batch=2), 2),
     "chain_adam_b4": (chain_adam, dict(batch=4), 3),
+    # BASELINE.json sizes (C1, C2): live-reference comparisons only, no committed golden
+    "mnist_b64": (configs.mnist, dict(batch=64), 3),
+    "cifar_b128": (configs.cifar, dict(batch=128), 3),
+    # the same nets with tanh instead of ReLU: no mask bits to flip, so the gradients of the
+    # tensor-core path can be held to the kernel tolerance through the whole backward chain
+    "mnist_tanh_b64": (configs.mnist, dict(batch=64, act="tanh"), 2),
+    "cifar_tanh_b128": (configs.cifar, dict(batch=128, act="tanh"), 2),
 }
 
 
@@ -119,6 +126,29 @@ def run_case(net, name, seed=7, collect_steps=True):
         if t.grad_data:
             out[f"final/grad/{idx}:{nm}"] = net.get(idx, grad=True)
     return out
+
+
+def live_reference_case(name, seed, threads=4):
+    """run_case on the compiled reference (oracle/_ref), plus under "sens:<key>" the reference's
+    own response to a 1-ulp (2e-7 relative) input perturbation: the noise floor of each tensor."""
+    from helpers import ref_net, rel_err
+
+    ref = ref_net(threads=threads)
+    want = run_case(ref, name, seed=seed)
+    ref.close()
+    clean = configs.synth_input
+    configs.synth_input = lambda shape, seed=12345: (
+        clean(shape, seed) * np.float32(1 + 2e-7)).astype(np.float32)
+    try:
+        ref = ref_net(threads=threads)
+        pert = run_case(ref, name, seed=seed)
+        ref.close()
+    finally:
+        configs.synth_input = clean
+    for k in list(want):
+        if "/argmax/" not in k and np.abs(want[k]).max(initial=0.0) > 0:
+            want["sens:" + k] = np.float32(max(rel_err(pert[k], want[k])))
+    return want
 
 
 def _pool_indexes(net, node):

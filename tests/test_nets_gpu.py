@@ -92,21 +92,7 @@ def test_net_matches_golden_tensor_core(name):
 @pytest.mark.parametrize("name", ["mnist_b8", "chain_b4"])
 def test_net_matches_live_reference(name):
     """Same calls, same seed (different from the golden's), both libraries in one process."""
-    ref = ref_net()
-    want = netcases.run_case(ref, name, seed=31)
-    ref.close()
-    clean = configs.synth_input
-    configs.synth_input = lambda shape, seed=12345: (
-        clean(shape, seed) * np.float32(1 + 2e-7)).astype(np.float32)
-    try:
-        ref = ref_net()
-        pert = netcases.run_case(ref, name, seed=31)
-        ref.close()
-    finally:
-        configs.synth_input = clean
-    for k in list(want):
-        if "/argmax/" not in k and np.abs(want[k]).max(initial=0.0) > 0:
-            want["sens:" + k] = np.float32(max(rel_err(pert[k], want[k])))
+    want = netcases.live_reference_case(name, 31, threads=1)
     net = capi.Net()
     out = netcases.run_case(net, name, seed=31)
     net.close()
