@@ -123,6 +123,7 @@ def bind_b200_ext(lib: C.CDLL) -> None:
         "bcnn_b200_set_conv_math": (None, [vp, i]),
         "bcnn_b200_get_conv_math": (i, [vp]),
         "bcnn_b200_set_reference_quirks": (None, [vp, i]),
+        "bcnn_b200_get_reference_quirks": (i, [vp]),
         "bcnn_b200_yolo_loss_on_host": (f, [vp, i]),
         "bcnn_b200_set_graphs": (None, [vp, i]),
         "bcnn_b200_get_graphs": (i, [vp]),

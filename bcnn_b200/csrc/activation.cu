@@ -91,7 +91,7 @@ prelu_bwd_kernel(const float *__restrict__ y, float *__restrict__ dy,
         }
     }
     block_sum<1, 256>(acc, red);
-    if (threadIdx.x == 0) g_slope[ch] += acc[0];
+    if (threadIdx.x == 0 && g_slope != nullptr) g_slope[ch] += acc[0];
 }
 
 // ---- y[n,c,:] += b[c] ----------------------------------------------------------

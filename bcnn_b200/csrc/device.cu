@@ -40,7 +40,10 @@ void *bcnn_b200_malloc(size_t bytes) {
                 cudaGetErrorString(cudaGetLastError()));
         return nullptr;
     }
+    // the net's streams are non-blocking (no implicit ordering with the legacy stream this
+    // memset runs on): finish it before anyone can launch work on the buffer
     cudaMemset(p, 0, bytes);
+    cudaStreamSynchronize(0);
     return p;
 }
 

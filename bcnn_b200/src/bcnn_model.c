@@ -84,7 +84,11 @@ static void plan_node(bcnn_net *net, bcnn_node *node, int format, int loading, m
                 p->fold_var = v;
             }
             if (format == MODEL_FMT_DARKNET) plan_add(p, w, bcnn_tensor_size(w));
-            if (loading && cp && cp->activation == BCNN_ACT_PRELU) {
+            /* The reference's saver never writes the slopes its reader expects (:597-681 vs
+             * :1305-1321), so it cannot read back its own conv+PReLU files. Here both walks carry
+             * them: a file written by this library loads in this library AND in the reference. */
+            (void)loading;
+            if (cp && cp->activation == BCNN_ACT_PRELU) {
                 bcnn_tensor *slopes = &t[node->src[3 + 3 * cp->batch_norm]];
                 plan_add(p, slopes, bcnn_tensor_size(slopes));
             }

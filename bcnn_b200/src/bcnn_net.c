@@ -19,6 +19,10 @@
 
 static void forward_graph_drop(bcnn_cuda_context *ctx);
 
+static void *g_current_stream = NULL;
+void *bcnn_b200_current_stream(void) { return g_current_stream; }
+void bcnn_b200_set_current_stream(void *stream) { g_current_stream = stream; }
+
 bcnn_status bcnn_net_create_cuda_context(bcnn_net *net) {
     bcnn_cuda_context *ctx = (bcnn_cuda_context *)calloc(1, sizeof(bcnn_cuda_context));
     BCNN_CHECK(ctx != NULL, BCNN_FAILED_ALLOC);
@@ -31,11 +35,17 @@ bcnn_status bcnn_net_create_cuda_context(bcnn_net *net) {
     }
     const char *graphs = getenv("BCNN_B200_GRAPHS");
     ctx->graphs = !(graphs && graphs[0] == '0');
+    /* Tensor-core math is the default; BCNN_B200_CONV_MATH=fp32 (or bcnn_b200_set_conv_math)
+     * selects the FP32 SIMT verification path. */
     const char *math = getenv("BCNN_B200_CONV_MATH");
-    ctx->conv_math = (math && (math[0] == 't' || math[0] == 'T' || math[0] == '1'))
-                         ? BCNN_B200_MATH_TC
-                         : BCNN_B200_MATH_FP32;
-    ctx->reference_quirks = 1;
+    ctx->conv_math = (math && (math[0] == 'f' || math[0] == 'F' || math[0] == '0'))
+                         ? BCNN_B200_MATH_FP32
+                         : BCNN_B200_MATH_TC;
+    /* Batch-correct residual semantics by default; the reference's two residual bugs (H2, H3) are
+     * replicated only on request (parity tests): BCNN_B200_REFERENCE_QUIRKS=1 or
+     * bcnn_b200_set_reference_quirks(net, 1). */
+    const char *quirks = getenv("BCNN_B200_REFERENCE_QUIRKS");
+    ctx->reference_quirks = (quirks && quirks[0] && quirks[0] != '0') ? 1 : 0;
     net->cuda_ctx = ctx;
     return BCNN_SUCCESS;
 }
@@ -256,6 +266,7 @@ static inline void profile_mark(bcnn_net *net, int node, int slot) {
 }
 
 static void forward_nodes(bcnn_net *net) {
+    g_current_stream = bcnn_stream(net);
     for (int i = 0; i < net->num_nodes; ++i) {
         bcnn_node *node = &net->nodes[i];
         profile_mark(net, i, 0);
@@ -344,6 +355,7 @@ int bcnn_b200_get_graphs(bcnn_net *net) {
 }
 
 void bcnn_backward(bcnn_net *net) {
+    g_current_stream = bcnn_stream(net);
     for (int i = net->num_nodes - 1; i >= 0; --i) {
         bcnn_node *node = &net->nodes[i];
         profile_mark(net, i, 2);
@@ -441,6 +453,7 @@ void bcnn_b200_set_reference_quirks(bcnn_net *net, int on) {
     if (bcnn_ctx(net)->reference_quirks != on) forward_graph_drop(bcnn_ctx(net));
     bcnn_ctx(net)->reference_quirks = on;
 }
+int bcnn_b200_get_reference_quirks(bcnn_net *net) { return bcnn_ctx(net)->reference_quirks; }
 int bcnn_b200_get_conv_math(bcnn_net *net) { return bcnn_ctx(net)->conv_math; }
 void *bcnn_b200_get_stream(bcnn_net *net) { return bcnn_stream(net); }
 

@@ -7,6 +7,8 @@
  */
 #include "bcnn_activation_layer.h"
 
+#include <bcnn_b200_net.h>
+
 #include "bcnn_learner.h"
 #include "bcnn_tensor.h"
 
@@ -37,12 +39,13 @@ bcnn_status bcnn_add_activation_layer(bcnn_net *net, bcnn_activation type, const
     return BCNN_SUCCESS;
 }
 
-void bcnn_forward_activation_gpu(bcnn_net *net, float *x, int sz, bcnn_activation a) {
-    bcnn_cuda_check(bcnn_b200_activation_forward(x, sz, a, NULL, 1, 1, bcnn_stream(net)));
+void bcnn_forward_activation_gpu(float *x, int sz, bcnn_activation a) {
+    bcnn_cuda_check(bcnn_b200_activation_forward(x, sz, a, NULL, 1, 1, bcnn_b200_current_stream()));
 }
 
-void bcnn_backward_activation_gpu(bcnn_net *net, float *x, float *dx, int sz, bcnn_activation a) {
-    bcnn_cuda_check(bcnn_b200_activation_backward(x, dx, sz, a, NULL, NULL, 1, 1, bcnn_stream(net)));
+void bcnn_backward_activation_gpu(float *x, float *dx, int sz, bcnn_activation a) {
+    bcnn_cuda_check(bcnn_b200_activation_backward(x, dx, sz, a, NULL, NULL, 1, 1,
+                                                  bcnn_b200_current_stream()));
 }
 
 void bcnn_forward_activation_layer_gpu(bcnn_net *net, bcnn_node *node) {

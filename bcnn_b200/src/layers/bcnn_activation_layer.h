@@ -1,7 +1,7 @@
 /*
  * bcnn_activation_layer.h -- standalone (in-place) activation node; entry points of
- * jnbraun/bcnn src/layers/bcnn_activation_layer.h:37-52, with the net prepended to the
- * raw-pointer helpers (for the stream) and PReLU slopes accepted on the device path.
+ * jnbraun/bcnn src/layers/bcnn_activation_layer.h:37-52 with their signatures; PReLU slopes
+ * are accepted on the device path of the node.
  */
 #ifndef BCNN_ACTIVATION_LAYER_H
 #define BCNN_ACTIVATION_LAYER_H
@@ -21,8 +21,10 @@ void bcnn_backward_activation_layer(bcnn_net *net, bcnn_node *node);
 void bcnn_update_activation_layer(bcnn_net *net, bcnn_node *node);
 void bcnn_forward_activation_layer_gpu(bcnn_net *net, bcnn_node *node);
 void bcnn_backward_activation_layer_gpu(bcnn_net *net, bcnn_node *node);
-void bcnn_forward_activation_gpu(bcnn_net *net, float *x, int sz, bcnn_activation a);
-void bcnn_backward_activation_gpu(bcnn_net *net, float *x, float *dx, int sz, bcnn_activation a);
+/* reference signatures (src/layers/bcnn_activation_layer.h:48-51); kernels go to the
+ * process-current stream (bcnn_b200_current_stream) */
+void bcnn_forward_activation_gpu(float *x, int sz, bcnn_activation a);
+void bcnn_backward_activation_gpu(float *x, float *dx, int sz, bcnn_activation a);
 
 #ifdef __cplusplus
 }

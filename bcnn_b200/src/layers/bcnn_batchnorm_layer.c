@@ -11,6 +11,8 @@
  */
 #include "bcnn_batchnorm_layer.h"
 
+#include <bcnn_b200_net.h>
+
 #include "bcnn_tensor.h"
 
 bcnn_status bcnn_add_batchnorm_layer(bcnn_net *net, const char *src_id, const char *dst_id) {
@@ -54,11 +56,11 @@ bcnn_status bcnn_add_batchnorm_layer(bcnn_net *net, const char *src_id, const ch
     return BCNN_SUCCESS;
 }
 
-void bcnn_forward_batchnorm_gpu(bcnn_net *net, const float *x_gpu, bcnn_tensor *dst,
-                                bcnn_tensor *bn_mean, bcnn_tensor *bn_var, bcnn_tensor *bn_scales,
-                                bcnn_tensor *biases, bcnn_tensor *saved_mean,
-                                bcnn_tensor *saved_var, float *scratch_gpu, bcnn_mode mode,
-                                bcnn_activation act) {
+void bcnn_b200_forward_batchnorm(bcnn_net *net, const float *x_gpu, bcnn_tensor *dst,
+                                 bcnn_tensor *bn_mean, bcnn_tensor *bn_var, bcnn_tensor *bn_scales,
+                                 bcnn_tensor *biases, bcnn_tensor *saved_mean,
+                                 bcnn_tensor *saved_var, float *scratch_gpu, bcnn_mode mode,
+                                 bcnn_activation act) {
     void *stream = bcnn_stream(net);
     const int n = dst->n, c = dst->c, hw = dst->h * dst->w;
     if (mode == BCNN_MODE_PREDICT) { /* statistics were folded into scales / biases */
@@ -78,11 +80,11 @@ void bcnn_forward_batchnorm_gpu(bcnn_net *net, const float *x_gpu, bcnn_tensor *
                                        biases->data_gpu, n, c, hw, act, stream));
 }
 
-void bcnn_backward_batchnorm_gpu(bcnn_net *net, const float *x_gpu, const float *y_gpu,
-                                 bcnn_tensor *dst, bcnn_tensor *bn_mean, bcnn_tensor *bn_var,
-                                 bcnn_tensor *bn_scales, bcnn_tensor *biases,
-                                 bcnn_tensor *saved_mean, bcnn_tensor *saved_var,
-                                 float *scratch_gpu, bcnn_mode mode, bcnn_activation act) {
+void bcnn_b200_backward_batchnorm(bcnn_net *net, const float *x_gpu, const float *y_gpu,
+                                  bcnn_tensor *dst, bcnn_tensor *bn_mean, bcnn_tensor *bn_var,
+                                  bcnn_tensor *bn_scales, bcnn_tensor *biases,
+                                  bcnn_tensor *saved_mean, bcnn_tensor *saved_var,
+                                  float *scratch_gpu, bcnn_mode mode, bcnn_activation act) {
     const int n = dst->n, c = dst->c, hw = dst->h * dst->w;
     /* outside TRAIN the reference differentiates through the running statistics
      * (bcnn_batchnorm_layer.c:308-311) */
@@ -94,10 +96,76 @@ void bcnn_backward_batchnorm_gpu(bcnn_net *net, const float *x_gpu, const float 
         saved_var->grad_data_gpu, n, c, hw, act, scratch_gpu, bcnn_stream(net)));
 }
 
+/* ---- reference-signature entry points (see the header) ---- */
+static float *compat_scratch(int c) {
+    static float *buf = NULL;
+    static size_t floats = 0;
+    const size_t need = bcnn_b200_bn_scratch_floats(c);
+    if (need > floats) {
+        bcnn_b200_stream_sync(bcnn_b200_current_stream());
+        bcnn_b200_free(buf);
+        buf = (float *)bcnn_b200_malloc(need * sizeof(float));
+        floats = buf ? need : 0;
+    }
+    return buf;
+}
+
+void bcnn_forward_batchnorm_gpu(bcnn_tensor *src, bcnn_tensor *dst, bcnn_tensor *bn_mean,
+                                bcnn_tensor *bn_var, bcnn_tensor *bn_scales, bcnn_tensor *biases,
+                                bcnn_tensor *saved_mean, bcnn_tensor *saved_var, float *x_norm_gpu,
+                                float *workspace_gpu, bcnn_mode mode) {
+    (void)x_norm_gpu;
+    void *stream = bcnn_b200_current_stream();
+    const int n = dst->n, c = dst->c, hw = dst->h * dst->w;
+    const float *x = src->data_gpu;
+    if (workspace_gpu && workspace_gpu != src->data_gpu && mode == BCNN_MODE_TRAIN) {
+        bcnn_cuda_check(bcnn_b200_memcpy_d2d(workspace_gpu, src->data_gpu,
+                                             (size_t)n * c * hw * sizeof(float), stream));
+        x = workspace_gpu;
+    }
+    if (mode == BCNN_MODE_PREDICT) {
+        bcnn_cuda_check(bcnn_b200_scale_bias(x, dst->data_gpu, bn_scales->data_gpu, biases->data_gpu,
+                                             n, c, hw, BCNN_ACT_NONE, stream));
+        return;
+    }
+    const float *mean = bn_mean->data_gpu, *var = bn_var->data_gpu;
+    if (mode == BCNN_MODE_TRAIN) {
+        float *scratch = compat_scratch(c);
+        if (!scratch) bcnn_cuda_check(2 /* cudaErrorMemoryAllocation */);
+        bcnn_cuda_check(bcnn_b200_bn_stats(x, n, c, hw, saved_mean->data_gpu, saved_var->data_gpu,
+                                           bn_mean->data_gpu, bn_var->data_gpu, scratch, stream));
+        mean = saved_mean->data_gpu;
+        var = saved_var->data_gpu;
+    }
+    bcnn_cuda_check(bcnn_b200_bn_apply(x, dst->data_gpu, mean, var, bn_scales->data_gpu,
+                                       biases->data_gpu, n, c, hw, BCNN_ACT_NONE, stream));
+}
+
+void bcnn_backward_batchnorm_gpu(bcnn_tensor *src, bcnn_tensor *dst, bcnn_tensor *bn_mean,
+                                 bcnn_tensor *bn_var, bcnn_tensor *bn_scales, bcnn_tensor *biases,
+                                 bcnn_tensor *saved_mean, bcnn_tensor *saved_var, float *x_norm_gpu,
+                                 float *workspace_gpu, bcnn_mode mode) {
+    (void)x_norm_gpu;
+    void *stream = bcnn_b200_current_stream();
+    const int n = dst->n, c = dst->c, hw = dst->h * dst->w;
+    const float *x = workspace_gpu ? workspace_gpu : src->data_gpu;
+    const float *mean = (mode == BCNN_MODE_TRAIN) ? saved_mean->data_gpu : bn_mean->data_gpu;
+    const float *var = (mode == BCNN_MODE_TRAIN) ? saved_var->data_gpu : bn_var->data_gpu;
+    float *scratch = compat_scratch(c);
+    if (!scratch) bcnn_cuda_check(2 /* cudaErrorMemoryAllocation */);
+    bcnn_cuda_check(bcnn_b200_bn_backward(
+        x, NULL, dst->grad_data_gpu, dst->grad_data_gpu, mean, var, bn_scales->data_gpu, NULL,
+        bn_scales->grad_data_gpu, biases->grad_data_gpu, saved_mean->grad_data_gpu,
+        saved_var->grad_data_gpu, n, c, hw, BCNN_ACT_NONE, scratch, stream));
+    if (src->grad_data_gpu && src->grad_data_gpu != dst->grad_data_gpu)
+        bcnn_cuda_check(bcnn_b200_memcpy_d2d(src->grad_data_gpu, dst->grad_data_gpu,
+                                             (size_t)n * c * hw * sizeof(float), stream));
+}
+
 void bcnn_forward_batchnorm_layer_gpu(bcnn_net *net, bcnn_node *node) {
     bcnn_batchnorm_param *param = (bcnn_batchnorm_param *)node->param;
     bcnn_tensor *t = net->tensors;
-    bcnn_forward_batchnorm_gpu(net, t[node->src[0]].data_gpu, &t[node->dst[0]], &t[node->src[1]],
+    bcnn_b200_forward_batchnorm(net, t[node->src[0]].data_gpu, &t[node->dst[0]], &t[node->src[1]],
                                &t[node->src[2]], &t[node->src[3]], &t[node->src[4]],
                                &param->saved_mean, &param->saved_variance,
                                param->reduce_scratch_gpu, net->mode, BCNN_ACT_NONE);
@@ -107,7 +175,7 @@ void bcnn_backward_batchnorm_layer_gpu(bcnn_net *net, bcnn_node *node) {
     bcnn_batchnorm_param *param = (bcnn_batchnorm_param *)node->param;
     bcnn_tensor *t = net->tensors;
     bcnn_tensor *src = &t[node->src[0]], *dst = &t[node->dst[0]];
-    bcnn_backward_batchnorm_gpu(net, src->data_gpu, NULL, dst, &t[node->src[1]], &t[node->src[2]],
+    bcnn_b200_backward_batchnorm(net, src->data_gpu, NULL, dst, &t[node->src[1]], &t[node->src[2]],
                                 &t[node->src[3]], &t[node->src[4]], &param->saved_mean,
                                 &param->saved_variance, param->reduce_scratch_gpu, net->mode,
                                 BCNN_ACT_NONE);

@@ -166,7 +166,7 @@ void bcnn_forward_conv_layer_gpu(bcnn_net *net, bcnn_node *node) {
                                                       weights->data_gpu, NULL, BCNN_ACT_NONE, raw,
                                                       ctx->workspace_gpu, ctx->workspace_bytes,
                                                       ctx->conv_math, sh, stream));
-            bcnn_forward_batchnorm_gpu(net, raw, dst, &t[node->src[3]], &t[node->src[4]],
+            bcnn_b200_forward_batchnorm(net, raw, dst, &t[node->src[3]], &t[node->src[4]],
                                        &t[node->src[5]], biases, &param->saved_mean,
                                        &param->saved_variance, param->reduce_scratch_gpu,
                                        net->mode, fused_act);
@@ -197,7 +197,7 @@ void bcnn_backward_conv_layer_gpu(bcnn_net *net, bcnn_node *node) {
         act = BCNN_ACT_NONE;
     }
     if (param->batch_norm) {
-        bcnn_backward_batchnorm_gpu(net, param->bn_workspace_gpu, dst->data_gpu, dst,
+        bcnn_b200_backward_batchnorm(net, param->bn_workspace_gpu, dst->data_gpu, dst,
                                     &t[node->src[3]], &t[node->src[4]], &t[node->src[5]], biases,
                                     &param->saved_mean, &param->saved_variance,
                                     param->reduce_scratch_gpu, net->mode, act);

@@ -34,6 +34,8 @@ bcnn_status bcnn_add_maxpool_layer(bcnn_net *net, int size, int stride, bcnn_pad
     const int ho = pooled_extent(s->h, size, stride, padding);
     const int wo = pooled_extent(s->w, size, stride, padding);
     const int n = s->n, c = s->c, h = s->h, w = s->w;
+    BCNN_CHECK_AND_LOG(net->log_ctx, ho > 0 && wo > 0, BCNN_INVALID_PARAMETER,
+                       "Maxpool layer: empty output\n");
     BCNN_CHECK_STATUS(bcnn_net_add_dst_tensor(net, &node, n, c, ho, wo, dst_id));
 
     node.type = BCNN_LAYER_MAXPOOL;

@@ -1,7 +1,7 @@
 /*
  * bcnn_b200.h -- kernel-level C ABI of libbcnn_b200.so.
  *
- * These are the entry points the C layer files (bcnn_b200/src/layers/*.c) call
+ * These are the entry points the C layer files (the .c files under bcnn_b200/src/layers) call
  * where jnbraun/bcnn's layer files call its bcnn_cuda_* helpers, cuBLAS and
  * cuDNN.  Plain pointers and sizes only: device pointers are raw `float *` /
  * `int *` into cudaMalloc'd memory, `stream` is a cudaStream_t passed as

@@ -17,16 +17,20 @@
 extern "C" {
 #endif
 
-/* Convolution arithmetic for every conv node of `net` (BCNN_B200_MATH_*). Default FP32. */
+/* Convolution arithmetic for every conv node of `net` (BCNN_B200_MATH_*). Default: tensor cores
+ * (BCNN_B200_MATH_TC); env BCNN_B200_CONV_MATH=fp32 or this call select the FP32 SIMT
+ * verification path. */
 BCNN_B200_API void bcnn_b200_set_conv_math(bcnn_net *net, int math);
 BCNN_B200_API int bcnn_b200_get_conv_math(bcnn_net *net);
-/* Reference-quirk mode (default ON = results identical to bcnn's CPU path):
+/* Reference-quirk mode (default OFF; env BCNN_B200_REFERENCE_QUIRKS=1 or this call turn it ON =
+ * results identical to bcnn's CPU path, which the parity tests need):
  *   ON : the residual add touches only sample 0 of the second input (bcnn_eltwise_layer.c
  *        :119-121) and a convolution's data gradient always overwrites src.grad
  *        (bcnn_conv_layer.c:567-578), even when src feeds several nodes;
  *   OFF: batch-correct residual add, and data gradients accumulate into tensors that have
  *        more than one consumer. ResNet-style training needs OFF to be meaningful. */
 BCNN_B200_API void bcnn_b200_set_reference_quirks(bcnn_net *net, int on);
+BCNN_B200_API int bcnn_b200_get_reference_quirks(bcnn_net *net);
 /* Solver parameters by name, as the reference's cfg reader sets them: the learner branch of
  * bcnn_net_set_param (src/bcnn_net.h:75, src/bcnn_net.c:506-553; internal but non-static there,
  * same name and meaning here). Keys: max_batches, learning_policy | decay_type
@@ -50,6 +54,13 @@ BCNN_B200_API void bcnn_b200_set_graphs(bcnn_net *net, int on);
 BCNN_B200_API int bcnn_b200_get_graphs(bcnn_net *net);
 /* The CUDA stream (cudaStream_t) every kernel of this net is launched on. */
 BCNN_B200_API void *bcnn_b200_get_stream(bcnn_net *net);
+/* The process-current stream: what the entry points that keep the reference's net-less
+ * signatures (bcnn_forward_activation_gpu, bcnn_forward_batchnorm_gpu, bcnn_cuda_*) launch on.
+ * bcnn_forward / bcnn_backward / bcnn_update set it to their net's stream for the duration of the
+ * loop; outside of them it is whatever was set last (initially NULL = the legacy default stream,
+ * which is what the reference's CUDA path uses everywhere). */
+BCNN_B200_API void *bcnn_b200_current_stream(void);
+BCNN_B200_API void bcnn_b200_set_current_stream(void *stream);
 /* Block the host until the net's stream (and its comm stream) are idle. */
 BCNN_B200_API void bcnn_b200_sync(bcnn_net *net);
 

@@ -1,3 +1,4 @@
+import os
 import sys
 from pathlib import Path
 
@@ -8,6 +9,15 @@ if str(ROOT) not in sys.path:
     sys.path.insert(0, str(ROOT))
 if str(ROOT / "tests") not in sys.path:
     sys.path.insert(0, str(ROOT / "tests"))
+
+
+# The suite is a PARITY suite against the reference's CPU path, so a net made without further
+# calls is the verification configuration: FP32 SIMT convolutions and the reference's residual
+# semantics (H2 / H3). The library's own defaults (tensor-core math, batch-correct residuals) are
+# asserted in tests/test_nets_gpu.py::test_library_defaults; tests of the tensor-core path select
+# it explicitly.
+os.environ.setdefault("BCNN_B200_CONV_MATH", "fp32")
+os.environ.setdefault("BCNN_B200_REFERENCE_QUIRKS", "1")
 
 
 def pytest_configure(config):

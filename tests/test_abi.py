@@ -58,6 +58,7 @@ def test_library_exports_every_declared_symbol(header, name):
     "bcnn_backward_avgpool_layer_gpu", "bcnn_forward_activation_layer",
     "bcnn_backward_activation_layer", "bcnn_update_activation_layer",
     "bcnn_forward_activation_gpu", "bcnn_backward_activation_gpu",
+    "bcnn_b200_forward_batchnorm", "bcnn_b200_backward_batchnorm",
     "bcnn_forward_depthwise_conv_layer", "bcnn_backward_depthwise_conv_layer",
     "bcnn_update_depthwise_conv_layer", "bcnn_release_param_depthwise_conv_layer",
     "bcnn_sgd_update_gpu", "bcnn_net_add_node", "bcnn_net_add_tensor", "bcnn_node_add_input",

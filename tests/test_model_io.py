@@ -209,6 +209,37 @@ def test_load_error_statuses(tmp_path):
 
 
 @pytest.mark.gpu
+def test_conv_with_fused_prelu_survives_a_save_load_round_trip(tmp_path):
+    """The reference's saver drops the slopes its reader expects (bcnn_net.c:597-681 vs :1305-1321);
+    here both walks carry them, so the file round-trips (and is what the reference's reader wants)."""
+    def make(mode):
+        net = capi.Net(mode=mode)
+        net.set_input_shape(8, 8, 3, 2)
+        net.conv(4, 3, 1, 1, 1, 1, "prelu", "input", "c1")
+        net.conv(6, 1, 1, 0, 1, 0, "prelu", "c1", "c2")
+        net.compile()
+        return net
+    src = make(capi.MODE_VALID)
+    configs.init_params(src, seed=8)
+    path = tmp_path / "prelu.bcnnmodel"
+    src.save_weights(path)
+    want = params(src)
+    assert any("prelu" in k for k in want)
+    floats = sum(v.size for v in want.values())
+    assert path.stat().st_size == 16 + 4 * floats
+    twin = make(capi.MODE_VALID)
+    assert twin.load_weights(path) == 0
+    assert_same_bits(params(twin), want, "conv + PReLU round trip")
+    x = configs.synth_input(src.shape("input"), seed=9)
+    for n in (src, twin):
+        n.set("input", x)
+        n.forward()
+    assert np.array_equal(src.get("c2"), twin.get("c2"))
+    src.close()
+    twin.close()
+
+
+@pytest.mark.gpu
 def test_trained_weights_survive_a_save_load_round_trip(tmp_path):
     """Size-independent property: train, save, load into a fresh net => identical parameters,
     identical next forward."""

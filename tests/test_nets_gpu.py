@@ -99,6 +99,23 @@ def test_net_matches_live_reference(name):
     _compare(out, want, 2e-5, 1e-4, f"{name} fp32 vs live reference")
 
 
+def test_library_defaults(monkeypatch):
+    """Without the test session's environment a net computes on the tensor cores with
+    batch-correct residual semantics; the FP32 path and the reference quirks are opt-in."""
+    monkeypatch.delenv("BCNN_B200_CONV_MATH")
+    monkeypatch.delenv("BCNN_B200_REFERENCE_QUIRKS")
+    net = capi.Net()
+    assert net.lib.bcnn_b200_get_conv_math(net.handle) == capi.MATH_TC
+    assert net.lib.bcnn_b200_get_reference_quirks(net.handle) == 0
+    net.close()
+    monkeypatch.setenv("BCNN_B200_CONV_MATH", "fp32")
+    monkeypatch.setenv("BCNN_B200_REFERENCE_QUIRKS", "1")
+    net = capi.Net()
+    assert net.lib.bcnn_b200_get_conv_math(net.handle) == capi.MATH_FP32
+    assert net.lib.bcnn_b200_get_reference_quirks(net.handle) == 1
+    net.close()
+
+
 def test_residual_fix_mode_accumulates_branch_gradients():
     """reference_quirks OFF: the block input's gradient is the sum of both branches.
     Checked on the last (identity-shortcut) block at batch 1, where everything downstream
