@@ -579,6 +579,19 @@ def bind_kernel_abi(lib: C.CDLL) -> None:
         "bcnn_b200_concat_backward": (i, [vp, vp, i, i, i, i, i, vp]),
         "bcnn_b200_upsample_forward": (i, [vp, vp, i, i, i, i, i, vp]),
         "bcnn_b200_upsample_backward": (i, [vp, vp, i, i, i, i, i, i, vp]),
+        # BF16 NHWC resident kernels (csrc/nhwc_bf16.cu)
+        "bcnn_b200_f32nchw_to_bf16nhwc": (i, [vp, vp, i, i, i, vp]),
+        "bcnn_b200_bf16nhwc_to_f32nchw": (i, [vp, vp, i, i, i, vp]),
+        "bcnn_b200_nhwc_scratch_floats": (sz, [i]),
+        "bcnn_b200_bn_apply_nhwc": (i, [vp, vp, vp, vp, vp, vp, sz, i, i, vp]),
+        "bcnn_b200_bn_backward_nhwc": (i, [vp] * 11 + [sz, i, i, vp, vp]),
+        "bcnn_b200_actbwd_grad_bias_nhwc": (i, [vp, vp, vp, i, sz, i, vp, vp]),
+        "bcnn_b200_eltwise_forward_bf16": (i, [vp, vp, vp, sz, sz, i, vp]),
+        "bcnn_b200_eltwise_backward_bf16": (i, [vp, vp, vp, vp, sz, sz, i, i, vp]),
+        "bcnn_b200_maxpool_forward_nhwc": (i, [vp, vp, vp, i, i, i, i, i, i, i, i, vp]),
+        "bcnn_b200_maxpool_backward_nhwc": (i, [vp, vp, vp, i, i, i, i, i, i, i, i, i, vp]),
+        "bcnn_b200_avgpool_forward_nhwc": (i, [vp, vp, i, i, i, vp]),
+        "bcnn_b200_avgpool_backward_nhwc": (i, [vp, vp, i, i, i, i, vp]),
     }
     for name, (res, args) in sigs.items():
         fn = getattr(lib, name)

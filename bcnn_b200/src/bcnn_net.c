@@ -80,6 +80,7 @@ void bcnn_end_net(bcnn_net **net) {
     if (ctx) {
         bcnn_b200_stream_sync(ctx->stream);
         bcnn_dp_release(p);
+        if (g_current_stream == ctx->stream) g_current_stream = NULL; /* about to be destroyed */
     }
     for (int i = 0; i < p->num_nodes; ++i) {
         bcnn_node *node = &p->nodes[i];

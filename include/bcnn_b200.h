@@ -366,6 +366,59 @@ BCNN_B200_API int bcnn_b200_upsample_backward(const float *dy, float *dx, int n,
                                               int w, int size, int accumulate, void *stream);
 
 
+/* ---- BF16 NHWC resident tensors (BCNN_B200_MATH_TC_BF16; csrc/nhwc_bf16.cu) -------------- */
+/* In this mode a convolution writes its result once as BF16 NHWC from the tensor-core epilogue and
+ * the layers between two convolutions work on that format: half the bytes of the FP32 NCHW
+ * kernels above and no transposition pass in front of the next convolution's TMA loads. Element
+ * (n, h, w, c) lives at ((n * H + h) * W + w) * C + c, C % 8 == 0, buffers 16-byte aligned;
+ * `positions` = N * H * W. Same formulas as the FP32 entry points they shadow (cited there),
+ * evaluated in FP32 on BF16-rounded storage: the 2e-2 tolerance class. No reference counterpart
+ * (the reference has no reduced-precision path). */
+/* layout / precision converters: what materialises the FP32 NCHW tensors bcnn_get_tensor_by_index
+ * hands out (reference inc/bcnn/bcnn.h:242-255) and brings FP32 producers' outputs in. c % 2 == 0. */
+BCNN_B200_API int bcnn_b200_f32nchw_to_bf16nhwc(const float *in, void *out, int n, int c, int hw,
+                                                void *stream);
+BCNN_B200_API int bcnn_b200_bf16nhwc_to_f32nchw(const void *in, float *out, int n, int c, int hw,
+                                                void *stream);
+/* floats of scratch the two reductions below need for `c` channels */
+BCNN_B200_API size_t bcnn_b200_nhwc_scratch_floats(int c);
+/* y = act(gamma (x - mean) / sqrt(var + 1e-6) + beta); mean == NULL: y = act(gamma x + beta)
+ * (PREDICT). act: NONE, RELU or LRELU. x may alias y. Shadows bcnn_b200_bn_apply / _scale_bias. */
+BCNN_B200_API int bcnn_b200_bn_apply_nhwc(const void *x, void *y, const float *mean, const float *var,
+                                          const float *gamma, const float *beta, size_t positions,
+                                          int c, int act, void *stream);
+/* Backward of (activation o batchnorm): shadows bcnn_b200_bn_backward with the mask rebuilt from x
+ * (beta required). dx may alias dy. g_gamma / g_beta accumulate (FP32); d_mean / d_var written. */
+BCNN_B200_API int bcnn_b200_bn_backward_nhwc(const void *x, void *dy, void *dx, const float *mean,
+                                             const float *var, const float *gamma, const float *beta,
+                                             float *g_gamma, float *g_beta, float *d_mean,
+                                             float *d_var, size_t positions, int c, int act,
+                                             float *scratch, void *stream);
+/* dy *= act'(y) in place; g_bias[c] += sum dy. Shadows bcnn_b200_actbwd_grad_bias. */
+BCNN_B200_API int bcnn_b200_actbwd_grad_bias_nhwc(float *g_bias, void *dy, const void *y, int act,
+                                                  size_t positions, int c, float *scratch,
+                                                  void *stream);
+/* residual add; shadows bcnn_b200_eltwise_forward / _backward (sz, n_add in elements, % 8 == 0) */
+BCNN_B200_API int bcnn_b200_eltwise_forward_bf16(const void *a, const void *b, void *y, size_t sz,
+                                                 size_t n_add, int act, void *stream);
+BCNN_B200_API int bcnn_b200_eltwise_backward_bf16(const void *y, void *dy, void *da, void *db,
+                                                  size_t sz, size_t n_add, int act,
+                                                  int accumulate_flags, void *stream);
+/* max pooling with the reference's rule (first max wins, bottom / right padding only); the index
+ * buffer is laid out like y (NHWC), its values are the reference's flat NCHW indices (-1: empty
+ * window). Shadows bcnn_b200_maxpool_forward / _backward; accumulate == 0 overwrites dx. */
+BCNN_B200_API int bcnn_b200_maxpool_forward_nhwc(const void *x, void *y, int *indexes, int n, int c,
+                                                 int h, int w, int ksize, int stride, int ho, int wo,
+                                                 void *stream);
+BCNN_B200_API int bcnn_b200_maxpool_backward_nhwc(void *dx, const void *dy, const int *indexes, int n,
+                                                  int c, int h, int w, int ksize, int stride, int ho,
+                                                  int wo, int accumulate, void *stream);
+/* global average pooling: y is FP32 [n, c]; dx (+)= dy / hw. Shadows bcnn_b200_avgpool_*. */
+BCNN_B200_API int bcnn_b200_avgpool_forward_nhwc(const void *x, float *y, int n, int c, int hw,
+                                                 void *stream);
+BCNN_B200_API int bcnn_b200_avgpool_backward_nhwc(void *dx, const float *dy, int n, int c, int hw,
+                                                  int accumulate, void *stream);
+
 #ifdef __cplusplus
 }
 #endif

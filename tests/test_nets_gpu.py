@@ -65,7 +65,7 @@ def _compare(out, golden, tol_s0, tol_final, what, noise=None, grad_l2_tol=None)
     print(f"[{what}] {checked} tensors checked, worst err/tol {worst[0]:.2f} at {worst[1]}")
 
 
-@pytest.mark.parametrize("name", list(netcases.CASES))
+@pytest.mark.parametrize("name", [n for n in netcases.CASES if (GOLDEN / f"{n}.npz").exists()])
 def test_net_matches_golden_fp32(name):
     golden = dict(np.load(GOLDEN / f"{name}.npz"))
     net = capi.Net()

@@ -8,6 +8,7 @@ import test_baseline_parity_gpu as T
 from bcnn_b200 import capi, configs
 from helpers import ref_net, rel_err
 batch = int(sys.argv[1]) if len(sys.argv) > 1 else 8
+quirks = int(sys.argv[2]) if len(sys.argv) > 2 else 1
 tmp = T._yolo_files(tempfile.mkdtemp())
 (tmp / "tiny_bN.cfg").write_text(configs.yolov3_tiny_cfg(batch=batch))
 x = configs.synth_input((batch, 3, 416, 416), seed=25)
@@ -17,7 +18,7 @@ for make in (lambda: ref_net(mode=capi.MODE_TRAIN, threads=8), lambda: capi.Net(
     net = make()
     assert net.load_net(tmp / "tiny_bN.cfg", tmp / "tiny.weights") == 0
     if net.flavour == "b200":
-        net.set_reference_quirks(True); net.set_conv_math(capi.MATH_FP32)
+        net.set_reference_quirks(bool(quirks)); net.set_conv_math(capi.MATH_FP32)
     net.compile(); net.set("input", x); net.set("label", label); net.forward(); net.backward()
     nets.append(net)
 ref, net = nets
