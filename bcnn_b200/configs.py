@@ -141,12 +141,16 @@ def resnet50(net, batch=256, res=224, classes=1000, widths=(64, 128, 256, 512),
     return dict(classes=classes, out="softmax")
 
 
-def yolov3_tiny_cfg(batch=1, width=416, height=416):
+def yolov3_tiny_cfg(batch=1, width=416, height=416, max_filters=None):
     """The text of a Darknet-dialect YOLOv3-tiny config, generated from the layer list (the
     reference ships the same network as examples/yolo/yolov3-tiny.cfg; tests/test_baseline_parity
     checks on the CPU that both files make the reference build the identical graph). Keys the
-    reference's reader ignores (augmentation, burn-in, thresholds) are left out."""
+    reference's reader ignores (augmentation, burn-in, thresholds) are left out.
+    max_filters caps the layer widths: with 384 every backward GEMM of the reference stays inside
+    the range its transposed-operand blocking handles (SURVEY hazard H12)."""
     def conv(filters, size, bn=1, act="leaky"):
+        if max_filters:
+            filters = min(filters, max_filters)
         head = "[convolutional]\n" + ("batch_normalize=1\n" if bn else "")
         return head + f"filters={filters}\nsize={size}\nstride=1\npad=1\nactivation={act}\n"
 

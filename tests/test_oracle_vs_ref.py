@@ -291,3 +291,56 @@ def test_adam_update_bit_exact():
                    16, 16 * (step + 1), 0.9, 0.999, 0.002, 0.9, 0.0005)
             for u, v in zip(a, b):
                 assert np.array_equal(u.view(np.uint32), v.view(np.uint32)), (n, step)
+
+
+def _ref_conv_backward(cin, cout, k, hw, batch=2, seed=1):
+    """dgrad / wgrad of one convolution through the reference's public API (a 1x1 convolution in
+    front gives its source tensor a gradient buffer), and the oracle's on the same inputs."""
+    orc = oracle()
+    net = ref_net(mode=capi.MODE_TRAIN, threads=1)
+    net.set_input_shape(hw, hw, 3, batch)
+    net.conv(cin, 1, 1, 0, 1, 0, "none", "input", "c0")
+    net.conv(cout, k, 1, k // 2, 1, 0, "none", "c0", "c1")
+    net.compile()
+    r = rng(seed)
+    net.set("input", f32(r.uniform(-1, 1, (batch, 3, hw, hw))))
+    net.forward()
+    c0, w = net.get("c0").copy(), net.get("c0_w").copy()
+    dy = f32(r.uniform(-1, 1, (batch, cout, hw, hw)))
+    gw0 = net.get("c0_w", grad=True).copy()
+    net.set("c1", dy, grad=True)
+    net.backward()
+    dx_ref, gw_ref = net.get("c0", grad=True).copy(), net.get("c0_w", grad=True).copy()
+    net.close()
+    gw, dx = gw0.copy(), np.zeros_like(c0)
+    orc.orc_conv_backward(p(c0), p(w), p(dy), p(gw), p(dx), batch, cin, hw, hw, cout, k, 1, k // 2, 1)
+    # float64 evaluation of the definition (1x1 only): dx[n,ci,p] = sum_co W[co,ci] dy[n,co,p]
+    exact = None
+    if k == 1:
+        exact = np.einsum("oi,nop->nip", w.reshape(cout, cin).astype(np.float64),
+                          dy.reshape(batch, cout, -1).astype(np.float64)).reshape(c0.shape)
+    return dx_ref, gw_ref, dx, gw, exact
+
+
+def test_reference_transposed_gemm_blocking_h12():
+    """Hazard H12: `sgemm` (the transposed-operand driver behind bcnn_gemm, src/kernels/bcnn_mat.c
+    :2588-2625) addresses K block l of a transposed A as `&A[... + l * KC]` and N block j of a
+    transposed B as `&B[... + j * NC]`, without the column increment. Inside the first block
+    (K <= KC = 384, N <= NC = 4096) the reference is right and the oracle matches it bit for bit;
+    past it the reference's convolution backward is wrong (not merely different): its data gradient
+    for Cout > 384, its weight gradient for Cin * k * k > 4096. The oracle restates the intended
+    arithmetic; the float64 evaluation of the definition says which side is correct."""
+    def err(a, b):
+        return float(np.abs(a - b).max() / np.abs(b).max())
+    dx_ref, gw_ref, dx, gw, exact = _ref_conv_backward(16, 384, 1, 8)
+    assert np.array_equal(dx_ref, dx) and np.array_equal(gw_ref, gw)
+    assert err(dx, exact) < 1e-6
+    dx_ref, gw_ref, dx, gw, exact = _ref_conv_backward(16, 385, 1, 8)     # K block 1 has one row
+    assert np.array_equal(gw_ref, gw)
+    assert err(dx, exact) < 1e-6 and err(dx_ref, exact) > 1e-3
+    dx_ref, gw_ref, dx, gw, exact = _ref_conv_backward(16, 512, 1, 8)     # YOLOv3-tiny's 256 -> 512 class
+    assert err(dx, exact) < 1e-6 and err(dx_ref, exact) > 0.3
+    dx_ref, gw_ref, dx, gw, _ = _ref_conv_backward(455, 32, 3, 8)         # Cin k k = 4095: in range
+    assert np.array_equal(dx_ref, dx) and err(gw, gw_ref) < 1e-5
+    dx_ref, gw_ref, dx, gw, _ = _ref_conv_backward(500, 32, 3, 8)         # Cin k k = 4500 > NC
+    assert np.array_equal(dx_ref, dx) and err(gw, gw_ref) > 0.3
