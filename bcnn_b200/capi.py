@@ -592,6 +592,15 @@ def bind_kernel_abi(lib: C.CDLL) -> None:
         "bcnn_b200_maxpool_backward_nhwc": (i, [vp, vp, vp, i, i, i, i, i, i, i, i, i, vp]),
         "bcnn_b200_avgpool_forward_nhwc": (i, [vp, vp, i, i, i, vp]),
         "bcnn_b200_avgpool_backward_nhwc": (i, [vp, vp, i, i, i, i, vp]),
+        "bcnn_b200_bn_stats_nhwc": (i, [vp, sz, i, vp, vp, vp, vp, vp, vp, vp]),
+        # convolution on resident BF16 NHWC tensors (csrc/conv_tma.cu)
+        "bcnn_b200_conv_nhwc_supported": (i, [dp]),
+        "bcnn_b200_conv_nhwc_workspace_bytes": (sz, [dp]),
+        "bcnn_b200_conv_nhwc_x_keep_bytes": (sz, [dp]),
+        "bcnn_b200_conv_forward_nhwc": (i, [dp, vp, vp, vp, i, vp, vp, sz, shp, vp]),
+        "bcnn_b200_conv_forward_bn_stats_nhwc": (i, [dp, vp, vp, vp, vp, sz, shp, vp, vp, vp, vp, vp, vp, vp]),
+        "bcnn_b200_conv_backward_data_nhwc": (i, [dp, vp, vp, vp, i, vp, sz, vp]),
+        "bcnn_b200_conv_backward_weights_nhwc": (i, [dp, vp, vp, vp, vp, sz, shp, vp]),
     }
     for name, (res, args) in sigs.items():
         fn = getattr(lib, name)

@@ -121,3 +121,48 @@ extern "C" int bcnn_b200_conv_backward_weights_sh(const bcnn_b200_conv_desc *d, 
         return conv_tc_backward_weights(d, x, dy, gw, workspace, workspace_bytes, st);
     return conv_simt_backward_weights(d, x, dy, gw, workspace, workspace_bytes, st);
 }
+
+// ---------------------------------------------------------------- resident BF16 NHWC activations
+extern "C" int bcnn_b200_conv_nhwc_supported(const bcnn_b200_conv_desc *d) { return conv_nhwc_supported(d); }
+extern "C" size_t bcnn_b200_conv_nhwc_workspace_bytes(const bcnn_b200_conv_desc *d) {
+    return conv_nhwc_workspace_bytes(d);
+}
+extern "C" size_t bcnn_b200_conv_nhwc_x_keep_bytes(const bcnn_b200_conv_desc *d) {
+    return conv_nhwc_x_keep_bytes(d);
+}
+extern "C" int bcnn_b200_conv_forward_nhwc(const bcnn_b200_conv_desc *d, const void *x, const float *w,
+                                           const float *bias, int act, void *y, void *workspace,
+                                           size_t workspace_bytes, bcnn_b200_conv_shadows *sh,
+                                           void *stream) {
+    return conv_nhwc_forward(d, x, w, bias, act, y, workspace, workspace_bytes, sh, nullptr, nullptr,
+                             as_stream(stream));
+}
+extern "C" int bcnn_b200_conv_forward_bn_stats_nhwc(const bcnn_b200_conv_desc *d, const void *x,
+                                                    const float *w, void *y, void *workspace,
+                                                    size_t workspace_bytes, bcnn_b200_conv_shadows *sh,
+                                                    float *saved_mean, float *saved_var, float *run_mean,
+                                                    float *run_var, float *nhwc_scratch, float *scratch,
+                                                    void *stream) {
+    cudaStream_t st = as_stream(stream);
+    const float *partial = nullptr;
+    int rows = 0;
+    int err = conv_nhwc_forward(d, x, w, nullptr, 0, y, workspace, workspace_bytes, sh, &partial, &rows, st);
+    if (err) return err;
+    const size_t positions = (size_t)d->batch * d->ho * d->wo;
+    if (partial)
+        return bn_stats_from_partials(partial, rows, d->cout, (double)positions, saved_mean, saved_var,
+                                      run_mean, run_var, scratch, st);
+    return bcnn_b200_bn_stats_nhwc(y, positions, d->cout, saved_mean, saved_var, run_mean, run_var,
+                                   nhwc_scratch, scratch, stream);
+}
+extern "C" int bcnn_b200_conv_backward_data_nhwc(const bcnn_b200_conv_desc *d, const float *w,
+                                                 const void *dy, void *dx, int accumulate,
+                                                 void *workspace, size_t workspace_bytes, void *stream) {
+    return conv_nhwc_backward_data(d, w, dy, dx, accumulate, workspace, workspace_bytes, as_stream(stream));
+}
+extern "C" int bcnn_b200_conv_backward_weights_nhwc(const bcnn_b200_conv_desc *d, const void *x,
+                                                    const void *dy, float *gw, void *workspace,
+                                                    size_t workspace_bytes, bcnn_b200_conv_shadows *sh,
+                                                    void *stream) {
+    return conv_nhwc_backward_weights(d, x, dy, gw, workspace, workspace_bytes, sh, as_stream(stream));
+}

@@ -57,6 +57,22 @@ int conv_tma_backward_weights(const bcnn_b200_conv_desc *d, const float *x, cons
                               float *gw, void *workspace, size_t workspace_bytes,
                               bcnn_b200_conv_shadows *sh, cudaStream_t st);
 
+// Resident BF16 NHWC activations (conv_tma.cu): source and result are BF16 NHWC tensors, the thin
+// first layer reads its FP32 NCHW input through an im2col buffer. Bit mask of the passes covered:
+// 1 fprop, 2 dgrad, 4 wgrad.
+int conv_nhwc_supported(const bcnn_b200_conv_desc *d);
+size_t conv_nhwc_workspace_bytes(const bcnn_b200_conv_desc *d);
+size_t conv_nhwc_x_keep_bytes(const bcnn_b200_conv_desc *d);
+int conv_nhwc_forward(const bcnn_b200_conv_desc *d, const void *x, const float *w, const float *bias,
+                      int act, void *y16, void *workspace, size_t workspace_bytes,
+                      bcnn_b200_conv_shadows *sh, const float **stat_partial, int *stat_rows,
+                      cudaStream_t st);
+int conv_nhwc_backward_data(const bcnn_b200_conv_desc *d, const float *w, const void *dy16, void *dx16,
+                            int accumulate, void *workspace, size_t workspace_bytes, cudaStream_t st);
+int conv_nhwc_backward_weights(const bcnn_b200_conv_desc *d, const void *x, const void *dy16, float *gw,
+                               void *workspace, size_t workspace_bytes, bcnn_b200_conv_shadows *sh,
+                               cudaStream_t st);
+
 // batchnorm.cu: TRAIN statistics from the per-tile partial sums a convolution epilogue left
 // (partial[(row * 2 + {0: sum, 1: sum of squares}) * c + channel]), folded in a fixed order.
 int bn_stats_from_partials(const float *partial, int rows, int c, double count, float *saved_mean,

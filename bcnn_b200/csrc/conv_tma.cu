@@ -76,6 +76,17 @@ __device__ __forceinline__ void tma_reduce_add_3d(const CUtensorMap *map, uint32
     asm volatile("cp.reduce.async.bulk.tensor.3d.global.shared::cta.add.tile.bulk_group [%0, {%2, %3, %4}], [%1];"
                  :: "l"(map), "r"(src_smem), "r"(c0), "r"(c1), "r"(c2) : "memory");
 }
+// 4-D flavours: BF16 NHWC results seen as (channel, w, h, image)
+__device__ __forceinline__ void tma_store_4d(const CUtensorMap *map, uint32_t src_smem, int c0, int c1, int c2,
+                                             int c3) {
+    asm volatile("cp.async.bulk.tensor.4d.global.shared::cta.tile.bulk_group [%0, {%2, %3, %4, %5}], [%1];"
+                 :: "l"(map), "r"(src_smem), "r"(c0), "r"(c1), "r"(c2), "r"(c3) : "memory");
+}
+__device__ __forceinline__ void tma_reduce_add_4d(const CUtensorMap *map, uint32_t src_smem, int c0, int c1,
+                                                  int c2, int c3) {
+    asm volatile("cp.reduce.async.bulk.tensor.4d.global.shared::cta.add.tile.bulk_group [%0, {%2, %3, %4, %5}], [%1];"
+                 :: "l"(map), "r"(src_smem), "r"(c0), "r"(c1), "r"(c2), "r"(c3) : "memory");
+}
 __device__ __forceinline__ void bulk_commit_group() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
 // every earlier bulk group of this thread has finished READING its shared-memory source
 __device__ __forceinline__ void bulk_wait_read_all() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
@@ -175,6 +186,22 @@ bool make_map_out(CUtensorMap *map, float *base, int plane, int c, int n, int bo
     cuuint32_t estr[3] = {1, 1, 1};
     CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, base, dims, strides, box, estr,
                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
+                    CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    return r == CUDA_SUCCESS;
+}
+
+// Map over a BF16 NHWC result seen as (c, w, h, n): the store box is 64 channels x tw x th x tn
+// positions, SWIZZLE_128B (row r of the staged tile is 128 bytes whose 16-byte chunks are XOR-ed
+// with r & 7). Elements of a box that fall outside the tensor are not written.
+bool make_map_out16(CUtensorMap *map, void *base, int c, int w, int h, int n, int tw, int th, int tn) {
+    EncodeTiledFn fn = encode_fn();
+    if (!fn) return false;
+    cuuint64_t dims[4] = {(cuuint64_t)c, (cuuint64_t)w, (cuuint64_t)h, (cuuint64_t)n};
+    cuuint64_t strides[3] = {(cuuint64_t)c * 2, (cuuint64_t)w * c * 2, (cuuint64_t)w * h * c * 2};
+    cuuint32_t box[4] = {64, (cuuint32_t)tw, (cuuint32_t)th, (cuuint32_t)tn};
+    cuuint32_t estr[4] = {1, 1, 1, 1};
+    CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, base, dims, strides, box, estr,
+                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
                     CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     return r == CUDA_SUCCESS;
 }
@@ -342,6 +369,11 @@ struct FwdParams {
     // positions of the plane (x tn images). 0: per-thread stores (scattered dgrad classes, planes
     // whose size is not a multiple of 4 elements).
     int tstore, tile_pos;
+    // out16: the result is a BF16 NHWC tensor (resident activations). 1: each half of the epilogue
+    // warps stages 128 positions x 64 channels (128-byte rows, SWIZZLE_128B) and one bulk tensor
+    // store (reduce-add when accumulating) writes the box through the 4-D map tm_dst; 2: per-thread
+    // 16-byte stores (scattered strided-dgrad classes, channel tiles that are not 64-aligned).
+    int out16;
     int src_c, dst_c, batch;
     int out_w, out_h;     // output plane as the kernel sees it (DIRECT: (H*W, 1))
     int ksh, ksw, pad_h, pad_w, stride;   // tap window (rows x columns) and its leading pads
@@ -431,7 +463,8 @@ conv_tma_fwd_kernel(const __grid_constant__ CUtensorMap tm_src, const __grid_con
     const int n_tile = p.n_tile;
     const int b_stage_bytes = n_tile * BLOCK_K * 4;
     const int stage_bytes = A_STAGE_BYTES + b_stage_bytes;
-    uint64_t *bars = reinterpret_cast<uint64_t *>(smem + (size_t)S * stage_bytes);
+    // [S stages][2 output staging buffers (1 KiB aligned)][barriers]
+    uint64_t *bars = reinterpret_cast<uint64_t *>(smem + (size_t)S * stage_bytes + 2 * OUT_STAGE_BYTES);
     uint64_t *full = bars, *empty = bars + S, *acc_full = bars + 2 * S, *acc_empty = bars + 2 * S + 2;
     uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bars + 2 * S + 4);
 
@@ -447,7 +480,7 @@ conv_tma_fwd_kernel(const __grid_constant__ CUtensorMap tm_src, const __grid_con
         mbar_init(smem_u32(acc_empty + 1), FWD_EPI_WARPS);
         fence_barrier_init();
         prefetch_tensormap(&tm_src);
-        if (p.tstore) prefetch_tensormap(&tm_dst);
+        if (p.tstore || p.out16 == 1) prefetch_tensormap(&tm_dst);
     }
     if (warp == 1) tmem_alloc(smem_u32(tmem_slot), tmem_cols);
     tc_fence_before();
@@ -533,7 +566,7 @@ conv_tma_fwd_kernel(const __grid_constant__ CUtensorMap tm_src, const __grid_con
         float acc1[4] = {0.f, 0.f, 0.f, 0.f}, acc2[4] = {0.f, 0.f, 0.f, 0.f};
         // bulk-store epilogue: staging buffer of this half, position of this thread's row in it
         const int hw = ew & 3;   // warp within the half
-        float *stage = reinterpret_cast<float *>(smem + (size_t)S * stage_bytes + 256 + (size_t)half * OUT_STAGE_BYTES);
+        float *stage = reinterpret_cast<float *>(smem + (size_t)S * stage_bytes + (size_t)half * OUT_STAGE_BYTES);
         const int sub_stride = p.tn * 16 * p.tile_pos;   // floats of one 16-channel sub-box
         uint32_t stores = 0;                              // bulk stores issued by this half so far
         const uint32_t plane = (uint32_t)p.dst_plane;
@@ -564,7 +597,113 @@ conv_tma_fwd_kernel(const __grid_constant__ CUtensorMap tm_src, const __grid_con
             __syncwarp();
             tc_fence_after();
             const uint32_t d_tmem = tmem_base + buf * acc_cols + ((uint32_t)(q * 32) << 16);
-            if (p.tstore) {
+            if (p.out16) {
+                // BF16 NHWC result: this half owns the 64-channel groups gi = half, half + 2
+                __nv_bfloat16 *dst16 = reinterpret_cast<__nv_bfloat16 *>(p.dst) +
+                                       ((size_t)img * plane + (size_t)(oh * p.o_s + p.o_oy) * p.dst_w +
+                                        (size_t)(ow * p.o_s + p.o_ox)) * (size_t)p.dst_c;
+                uint8_t *sb = reinterpret_cast<uint8_t *>(stage);
+                const int r = q * 32 + lane;
+#pragma unroll
+                for (int gj = 0; gj < 2; ++gj) {
+                    const int gi = half + 2 * gj;
+                    if (gi * 64 >= n_tile) break;
+                    uint32_t pk[2][16];
+#pragma unroll
+                    for (int sc = 0; sc < 2; ++sc) {
+                        const int ck = 2 * gi + sc;
+                        const int ch0 = c.tile_n * n_tile + ck * 32;
+                        if (ck < chunks32) {
+                            uint32_t v[32];
+                            tmem_ld32(d_tmem + (uint32_t)(ck * 32), v);
+                            if (p.bias != nullptr || p.act != ACT_NONE) {
+#pragma unroll
+                                for (int j = 0; j < 32; ++j) {
+                                    float val = __uint_as_float(v[j]);
+                                    if (p.bias != nullptr && ch0 + j < p.dst_c) val += __ldg(p.bias + ch0 + j);
+                                    if (p.act == ACT_RELU) val = fmaxf(val, 0.f);
+                                    else if (p.act == ACT_LRELU) val = val > 0 ? val : 0.1f * val;
+                                    else val = act_fwd(val, p.act, 0.f);
+                                    v[j] = __float_as_uint(val);
+                                }
+                            }
+#pragma unroll
+                            for (int j = 0; j < 16; ++j)
+                                pk[sc][j] = pack_bf16x2(__uint_as_float(v[2 * j]), __uint_as_float(v[2 * j + 1]));
+                            if (p.stat_partial != nullptr) {
+                                float s1[32], s2[32];
+#pragma unroll
+                                for (int j = 0; j < 32; ++j) {
+                                    const float x = valid ? __uint_as_float(v[j]) : 0.f;
+                                    s1[j] = x;
+                                    s2[j] = x * x;
+                                }
+#pragma unroll
+                                for (int off = 16; off >= 1; off >>= 1) {
+                                    const bool hi = (lane & off) != 0;
+#pragma unroll
+                                    for (int i = 0; i < off; ++i) {
+                                        const float k1 = hi ? s1[i + off] : s1[i], g1 = hi ? s1[i] : s1[i + off];
+                                        const float k2 = hi ? s2[i + off] : s2[i], g2 = hi ? s2[i] : s2[i + off];
+                                        s1[i] = k1 + __shfl_xor_sync(0xffffffffu, g1, off);
+                                        s2[i] = k2 + __shfl_xor_sync(0xffffffffu, g2, off);
+                                    }
+                                }
+                                acc1[gj * 2 + sc] += s1[0];
+                                acc2[gj * 2 + sc] += s2[0];
+                            }
+                        } else {
+#pragma unroll
+                            for (int j = 0; j < 16; ++j) pk[sc][j] = 0u;
+                        }
+                    }
+                    const int ch0 = c.tile_n * n_tile + gi * 64;
+                    if (p.out16 == 1) {
+                        // the bulk store issued from this buffer one group ago has read it
+                        if (hw == 0 && lane == 0) bulk_wait_read_all();
+                        named_bar_sync(1 + half, 128);
+                        if (in_box) {
+                            uint8_t *row = sb + (size_t)r * 128;
+#pragma unroll
+                            for (int k8 = 0; k8 < 8; ++k8) {
+                                const uint32_t *w4 = &pk[k8 >> 2][(k8 & 3) * 4];
+                                *reinterpret_cast<uint4 *>(row + ((k8 ^ (r & 7)) << 4)) =
+                                    make_uint4(w4[0], w4[1], w4[2], w4[3]);
+                            }
+                        }
+                        fence_proxy_async();
+                        named_bar_sync(1 + half, 128);
+                        if (hw == 0 && lane == 0) {
+                            if (p.accumulate) tma_reduce_add_4d(&tm_dst, smem_u32(sb), ch0, c.w0, c.h0, c.img);
+                            else tma_store_4d(&tm_dst, smem_u32(sb), ch0, c.w0, c.h0, c.img);
+                            bulk_commit_group();
+                        }
+                    } else if (valid) {
+#pragma unroll
+                        for (int k8 = 0; k8 < 8; ++k8) {
+                            if (ch0 + k8 * 8 < p.dst_c && gi * 64 + k8 * 8 < n_tile) {
+                                const uint32_t *w4 = &pk[k8 >> 2][(k8 & 3) * 4];
+                                uint4 o = make_uint4(w4[0], w4[1], w4[2], w4[3]);
+                                uint4 *gp = reinterpret_cast<uint4 *>(dst16 + ch0 + k8 * 8);
+                                if (p.accumulate) {
+                                    const uint4 old = *gp;
+                                    const uint32_t ov[4] = {old.x, old.y, old.z, old.w};
+                                    uint32_t nv[4] = {o.x, o.y, o.z, o.w};
+#pragma unroll
+                                    for (int e = 0; e < 4; ++e) {
+                                        const float lo = __uint_as_float(ov[e] << 16) + __uint_as_float(nv[e] << 16);
+                                        const float hi2 = __uint_as_float(ov[e] & 0xffff0000u) +
+                                                          __uint_as_float(nv[e] & 0xffff0000u);
+                                        nv[e] = pack_bf16x2(lo, hi2);
+                                    }
+                                    o = make_uint4(nv[0], nv[1], nv[2], nv[3]);
+                                }
+                                *gp = o;
+                            }
+                        }
+                    }
+                }
+            } else if (p.tstore) {
                 const int pos0 = NHWC ? c.h0 * p.dst_w + c.w0 : c.w0;
 #pragma unroll
                 for (int ci = 0; ci < 4; ++ci) {
@@ -679,7 +818,8 @@ conv_tma_fwd_kernel(const __grid_constant__ CUtensorMap tm_src, const __grid_con
             const size_t row = (size_t)(blockIdx.x / (uint32_t)p.n_tiles) * 4 + (size_t)q;
 #pragma unroll
             for (int ci = 0; ci < 4; ++ci) {
-                const int ck = half + 2 * ci;
+                // out16: this half owns the 64-channel groups half, half + 2 (two chunks each)
+                const int ck = p.out16 ? 2 * (half + 2 * (ci >> 1)) + (ci & 1) : half + 2 * ci;
                 const int ch = (int)tile_n * n_tile + ck * 32 + lane;
                 if (ck < chunks32 && lane < n_tile - ck * 32 && ch < p.dst_c) {
                     p.stat_partial[(row * 2 + 0) * p.dst_c + ch] = acc1[ci];
@@ -688,7 +828,7 @@ conv_tma_fwd_kernel(const __grid_constant__ CUtensorMap tm_src, const __grid_con
             }
         }
         // shared memory must outlive the bulk stores that read it
-        if (p.tstore && hw == 0 && lane == 0) bulk_wait_read_all();
+        if ((p.tstore || p.out16 == 1) && hw == 0 && lane == 0) bulk_wait_read_all();
     }
     tc_fence_before();
     __syncthreads();
@@ -704,6 +844,9 @@ struct FwdGeom {
     int ksh, ksw, pad_h, pad_w, stride;
     int o_s, o_oy, o_ox, dst_w, dst_plane;
     bool direct;   // source may be read in place through the NCHW map
+    // resident activations: the source already is a BF16 NHWC tensor (no shadow to make) and the
+    // result is written as BF16 NHWC (dst_h = dst_plane / dst_w rows of dst_w positions)
+    bool resident = false;
 };
 
 struct FwdPlan {
@@ -716,6 +859,7 @@ struct FwdPlan {
     uint32_t a_bytes;
     size_t shadow_bytes, wpack_bytes, smem_bytes;
     bool tstore;             // bulk tensor-store epilogue (tile = tile_pos consecutive positions)
+    int out16;               // BF16 NHWC result: 1 bulk tensor store, 2 per-thread stores (FwdParams)
     int tile_pos;
     int stat_rows;           // rows of the fused batch-norm partials: 4 per position tile
     size_t stat_bytes;
@@ -751,7 +895,8 @@ bool plan_fwd(const FwdGeom &g, FwdPlan *pl) {
     pl->nhwc = !direct;
     if (!direct && (nhwc_disabled() || g.src_c % 4 != 0 || g.stride > 4)) return false;
     if (g.ksh * g.ksw > 64) return false;   // TapMap capacity
-    pl->bf16 = !direct && shadow_bf16() && g.src_c % 8 == 0;
+    if (g.resident && (g.src_c % 8 != 0 || g.dst_c % 8 != 0)) return false;   // 16-byte channel vectors
+    pl->bf16 = !direct && (g.resident || shadow_bf16()) && g.src_c % 8 == 0;
     const int kc = pl->bf16 ? 64 : 32;       // channels per 128-byte k-block row
     static int nmax = 0;
     if (!nmax) {
@@ -766,6 +911,8 @@ bool plan_fwd(const FwdGeom &g, FwdPlan *pl) {
     } else {
         n = ceil_div(n, 16) * 16;
     }
+    // resident results are stored in boxes of 64 channels: several channel tiles must not overlap
+    if (g.resident && ceil_div(g.dst_c, n) > 1 && n % 64 != 0) n = ceil_div(n, 64) * 64;
     pl->n_tile = n;
     pl->n_tiles = ceil_div(g.dst_c, n);
     pl->kc_blocks = ceil_div(g.src_c, kc);
@@ -825,6 +972,13 @@ bool plan_fwd(const FwdGeom &g, FwdPlan *pl) {
                      pl->tile_pos % 4 == 0 && !env_off("BCNN_B200_NO_TSTORE");
     }
     if (env_off("BCNN_B200_NO_TSTORE")) pl->tstore = false;
+    pl->out16 = 0;
+    if (g.resident) {
+        if (direct) return false;
+        pl->shadow_bytes = 0;
+        pl->out16 = (g.o_s == 1 && g.dst_w == g.dw && g.dst_c % 64 == 0 && !env_off("BCNN_B200_NO_TSTORE")) ? 1 : 2;
+        pl->tstore = false;
+    }
     const int stage = A_STAGE_BYTES + n * BLOCK_K * 4;
     int stages = (227 * 1024 - FWD_EXTRA_SMEM) / stage;  // persistent: one CTA per SM owns the shared memory
     if (stages > 8) stages = 8;
@@ -837,7 +991,7 @@ bool plan_fwd(const FwdGeom &g, FwdPlan *pl) {
     // fused statistics: grid = a multiple of n_tiles (0 rows: more channel tiles than SMs, no fusion)
     const long long per_tile = sm_count() / pl->n_tiles;
     const long long m_tiles = total / pl->n_tiles;
-    pl->stat_rows = pl->tstore ? (int)(4 * (per_tile < m_tiles ? per_tile : m_tiles)) : 0;
+    pl->stat_rows = (pl->tstore || pl->out16) ? (int)(4 * (per_tile < m_tiles ? per_tile : m_tiles)) : 0;
     pl->stat_bytes = align256((size_t)pl->stat_rows * 2 * g.dst_c * sizeof(float));
     return true;
 }
@@ -970,7 +1124,8 @@ int launch_fwd_kernel(const CUtensorMap &tm, const CUtensorMap &tm_dst, const Fw
 
 // src: the NCHW tensor (DIRECT plans) or the NHWC-shaped shadow (all others).
 int run_fwd(const FwdGeom &g, const FwdPlan &pl, const void *src, const uint8_t *wpack, const float *bias,
-            int act, float *dst, int accumulate, cudaStream_t st, float *stat_partial = nullptr) {
+            int act, void *dst_any, int accumulate, cudaStream_t st, float *stat_partial = nullptr) {
+    float *dst = reinterpret_cast<float *>(dst_any);
     CUtensorMap tm;
     if (pl.nhwc) {
         if (!make_map_nhwc(&tm, src, g.src_c, g.sw, g.sh, g.batch, pl.tw, pl.th, pl.tn, g.stride, false,
@@ -1000,10 +1155,14 @@ int run_fwd(const FwdGeom &g, const FwdPlan &pl, const void *src, const uint8_t 
     p.d_tw = FastDiv((uint32_t)pl.tw);
     p.d_th = FastDiv((uint32_t)pl.th);
     p.tstore = pl.tstore ? 1 : 0;
+    p.out16 = pl.out16;
     p.tile_pos = pl.tile_pos;
     CUtensorMap tm_dst = tm;   // placeholder when the epilogue stores from registers
     if (pl.tstore &&
         !make_map_out(&tm_dst, dst, g.dst_plane, g.dst_c, g.batch, pl.tile_pos, pl.nhwc ? pl.tn : 1))
+        return (int)cudaErrorInvalidValue;
+    if (pl.out16 == 1 && !make_map_out16(&tm_dst, dst_any, g.dst_c, g.dst_w, g.dst_plane / g.dst_w, g.batch,
+                                         pl.tw, pl.th, pl.tn))
         return (int)cudaErrorInvalidValue;
     const size_t smem = pl.smem_bytes;
     const int grid = stat_partial ? stat_grid(pl) : 0;
@@ -1155,6 +1314,182 @@ int launch_fwd(const bcnn_b200_conv_desc *d, bool dgrad, const float *src, const
     return run_fwd(g, pl, operand, wpack, bias, act, dst, accumulate, st, stats);
 }
 
+
+// ------------------------------------------------------------------ resident (BF16 NHWC) fprop / dgrad
+// Source and result are BF16 NHWC tensors: no shadow is made, the TMA reads the activation tensor
+// itself and the epilogue writes the result once in the layout the next layer's loads want.
+FwdGeom geom_resident(const bcnn_b200_conv_desc *d, bool dgrad) {
+    FwdGeom g = geom_plain(d, dgrad);
+    g.direct = false;
+    g.resident = true;
+    const long long positions = (long long)d->batch * d->h * d->w;
+    if (d->ksize == 1 && d->stride == 1 && d->pad == 0 && positions < (1LL << 31)) {
+        // 1x1: the batch is one row of N*H*W positions, so every tile has 128 full rows whatever
+        // the plane size (7x7 planes would fill 98 of 128 otherwise)
+        g.batch = 1;
+        g.sh = g.dh = 1;
+        g.sw = g.dw = g.dst_w = g.dst_plane = (int)positions;
+    }
+    return g;
+}
+
+bool resident_desc_ok(const bcnn_b200_conv_desc *d) {
+    return !tma_disabled() && encode_fn() && d->groups == 1 && d->cout % 8 == 0 && d->ksize <= 8 &&
+           (d->cin % 8 == 0 || im2col_shape(d));
+}
+
+FwdRoute route_fwd_resident(const bcnn_b200_conv_desc *d, bool dgrad, FwdPlan *pl) {
+    if (!resident_desc_ok(d)) return ROUTE_NONE;
+    if (dgrad) {
+        if (d->cin % 8 != 0) return ROUTE_NONE;
+        if (d->stride != 1) {
+            if (!strided_dgrad_shape(d)) return ROUTE_NONE;
+            for (int ph = 0; ph < d->stride; ++ph)
+                for (int pw = 0; pw < d->stride; ++pw) {
+                    const ClassAxis ah = class_axis(ph, d->stride, d->pad, d->ksize, d->h);
+                    const ClassAxis aw = class_axis(pw, d->stride, d->pad, d->ksize, d->w);
+                    if (ah.n == 0 || aw.n == 0 || ah.extent == 0 || aw.extent == 0) continue;
+                    FwdGeom g = geom_dgrad_class(d, ah, aw, ph, pw);
+                    g.resident = true;
+                    if (!plan_fwd(g, pl)) return ROUTE_NONE;
+                }
+            return ROUTE_STRIDED_DGRAD;
+        }
+        if (d->pad > d->ksize - 1) return ROUTE_NONE;
+        return plan_fwd(geom_resident(d, true), pl) ? ROUTE_PLAIN : ROUTE_NONE;
+    }
+    if (im2col_shape(d)) {
+        FwdGeom g = geom_im2col(d);
+        g.resident = true;
+        return plan_fwd(g, pl) ? ROUTE_IM2COL : ROUTE_NONE;
+    }
+    return plan_fwd(geom_resident(d, false), pl) ? ROUTE_PLAIN : ROUTE_NONE;
+}
+
+size_t im2col_bytes(const bcnn_b200_conv_desc *d) {
+    return align256((size_t)d->batch * d->ho * d->wo * im2col_kp(d) * 2);
+}
+
+size_t strided_dgrad_pack_bytes_resident(const bcnn_b200_conv_desc *d) {
+    size_t packs = 0;
+    for (int ph = 0; ph < d->stride; ++ph)
+        for (int pw = 0; pw < d->stride; ++pw) {
+            const ClassAxis ah = class_axis(ph, d->stride, d->pad, d->ksize, d->h);
+            const ClassAxis aw = class_axis(pw, d->stride, d->pad, d->ksize, d->w);
+            if (ah.n == 0 || aw.n == 0 || ah.extent == 0 || aw.extent == 0) continue;
+            FwdGeom g = geom_dgrad_class(d, ah, aw, ph, pw);
+            g.resident = true;
+            FwdPlan pl;
+            if (!plan_fwd(g, &pl)) return 0;
+            packs += pl.wpack_bytes;
+        }
+    return packs;
+}
+
+// fprop: x is the BF16 NHWC activation, or the FP32 NCHW input of a thin first layer (im2col route)
+int launch_fwd_resident(const bcnn_b200_conv_desc *d, const void *x, const float *w, const float *bias,
+                        int act, void *y16, void *workspace, size_t workspace_bytes,
+                        bcnn_b200_conv_shadows *sh, cudaStream_t st, const float **stat_partial,
+                        int *stat_rows) {
+    FwdPlan pl;
+    const FwdRoute route = route_fwd_resident(d, false, &pl);
+    if (route == ROUTE_NONE) return (int)cudaErrorInvalidValue;
+    if ((reinterpret_cast<uintptr_t>(x) & 15) != 0 || (reinterpret_cast<uintptr_t>(y16) & 15) != 0 ||
+        (reinterpret_cast<uintptr_t>(workspace) & 255) != 0)
+        return (int)cudaErrorMisalignedAddress;
+    uint8_t *ws = reinterpret_cast<uint8_t *>(workspace);
+    size_t off = 0;
+    const void *operand = x;
+    const int kk = d->ksize * d->ksize;
+    TapMap taps;
+    if (route == ROUTE_IM2COL) {
+        const size_t cb = im2col_bytes(d);
+        void *col = ws;
+        const bool keep = sh && sh->x && sh->x_bytes >= cb && (reinterpret_cast<uintptr_t>(sh->x) & 255) == 0;
+        if (keep) col = sh->x;
+        else off += cb;
+        if (workspace == nullptr || workspace_bytes < off + pl.wpack_bytes) return (int)cudaErrorInvalidValue;
+        int err = launch_im2col(d, reinterpret_cast<const float *>(x), col, true, st);
+        if (err) return err;
+        if (keep) sh->x_fmt = BCNN_B200_SHADOW_IM2COL_BF16;
+        operand = col;
+        taps.n = 1; taps.idx[0] = 0;
+    } else {
+        taps.n = kk;
+        for (int t = 0; t < kk; ++t) taps.idx[t] = (short)t;
+    }
+    if (workspace == nullptr || workspace_bytes < off + pl.wpack_bytes) return (int)cudaErrorInvalidValue;
+    uint8_t *wpack = ws + off;
+    off += pl.wpack_bytes;
+    float *stats = nullptr;
+    if (stat_partial && pl.stat_rows > 0 && workspace_bytes >= off + pl.stat_bytes) {
+        stats = reinterpret_cast<float *>(ws + off);
+        *stat_partial = stats;
+        *stat_rows = pl.stat_rows;
+    }
+    int err = route == ROUTE_IM2COL ? launch_pack(w, wpack, false, d->cout, d->cin * kk, 1, pl, taps, st)
+                                    : launch_pack(w, wpack, false, d->cout, d->cin, kk, pl, taps, st);
+    if (err) return err;
+    FwdGeom g = route == ROUTE_IM2COL ? geom_im2col(d) : geom_resident(d, false);
+    g.resident = true;
+    return run_fwd(g, pl, operand, wpack, bias, act, y16, 0, st, stats);
+}
+
+int launch_dgrad_resident(const bcnn_b200_conv_desc *d, const float *w, const void *dy16, void *dx16,
+                          int accumulate, void *workspace, size_t workspace_bytes, cudaStream_t st) {
+    FwdPlan pl;
+    const FwdRoute route = route_fwd_resident(d, true, &pl);
+    if (route == ROUTE_NONE) return (int)cudaErrorInvalidValue;
+    if ((reinterpret_cast<uintptr_t>(dy16) & 15) != 0 || (reinterpret_cast<uintptr_t>(dx16) & 15) != 0 ||
+        (reinterpret_cast<uintptr_t>(workspace) & 255) != 0)
+        return (int)cudaErrorMisalignedAddress;
+    uint8_t *ws = reinterpret_cast<uint8_t *>(workspace);
+    const int kk = d->ksize * d->ksize;
+    if (route == ROUTE_PLAIN) {
+        if (workspace == nullptr || workspace_bytes < pl.wpack_bytes) return (int)cudaErrorInvalidValue;
+        TapMap taps;
+        taps.n = kk;
+        for (int t = 0; t < kk; ++t) taps.idx[t] = (short)(kk - 1 - t);
+        int err = launch_pack(w, ws, true, d->cout, d->cin, kk, pl, taps, st);
+        if (err) return err;
+        return run_fwd(geom_resident(d, true), pl, dy16, ws, nullptr, 0, dx16, accumulate, st);
+    }
+    // strided: one stride-1 launch per class of input positions, scattered into dx
+    if (workspace == nullptr || workspace_bytes < strided_dgrad_pack_bytes_resident(d))
+        return (int)cudaErrorInvalidValue;
+    const int s = d->stride;
+    bool holes = false;
+    for (int ph = 0; ph < s; ++ph)
+        for (int pw = 0; pw < s; ++pw)
+            if (class_axis(ph, s, d->pad, d->ksize, d->h).n == 0 || class_axis(pw, s, d->pad, d->ksize, d->w).n == 0)
+                holes = true;
+    if (holes && !accumulate) {
+        cudaError_t e = cudaMemsetAsync(dx16, 0, (size_t)d->batch * d->cin * d->h * d->w * 2, st);
+        if (e != cudaSuccess) return (int)e;
+    }
+    size_t off = 0;
+    for (int ph = 0; ph < s; ++ph)
+        for (int pw = 0; pw < s; ++pw) {
+            const ClassAxis ah = class_axis(ph, s, d->pad, d->ksize, d->h);
+            const ClassAxis aw = class_axis(pw, s, d->pad, d->ksize, d->w);
+            if (ah.n == 0 || aw.n == 0 || ah.extent == 0 || aw.extent == 0) continue;
+            FwdGeom g = geom_dgrad_class(d, ah, aw, ph, pw);
+            g.resident = true;
+            if (!plan_fwd(g, &pl)) return (int)cudaErrorInvalidValue;
+            uint8_t *wpack = ws + off;
+            off += pl.wpack_bytes;
+            TapMap taps;
+            taps.n = ah.n * aw.n;
+            for (int th = 0; th < ah.n; ++th)
+                for (int tw = 0; tw < aw.n; ++tw)
+                    taps.idx[th * aw.n + tw] = (short)((ah.kfirst - s * th) * d->ksize + (aw.kfirst - s * tw));
+            int err = launch_pack(w, wpack, true, d->cout, d->cin, kk, pl, taps, st);
+            if (err) return err;
+            err = run_fwd(g, pl, dy16, wpack, nullptr, 0, dx16, accumulate, st);
+            if (err) return err;
+        }
+    return 0;
+}
 
 // ------------------------------------------------------------------ wgrad
 struct WgParams {
@@ -1327,7 +1662,9 @@ struct WgEff {
     int batch, cin, cin_phys, h, w, cout, ho, wo, ksize, stride, pad;
     bool im2col;
 };
-WgEff wg_effective(const bcnn_b200_conv_desc *d) {
+// resident: x and dy are BF16 NHWC tensors (or the kept im2col buffer); 1x1 problems are flattened
+// to one row of N*H*W positions, so a k-block is 64 consecutive positions whatever the plane size
+WgEff wg_effective(const bcnn_b200_conv_desc *d, bool resident = false) {
     WgEff e;
     e.batch = d->batch; e.cout = d->cout; e.ho = d->ho; e.wo = d->wo;
     e.im2col = im2col_shape(d);
@@ -1338,17 +1675,24 @@ WgEff wg_effective(const bcnn_b200_conv_desc *d) {
         e.cin = e.cin_phys = d->cin; e.h = d->h; e.w = d->w;
         e.ksize = d->ksize; e.stride = d->stride; e.pad = d->pad;
     }
+    const long long positions = (long long)e.batch * e.ho * e.wo;
+    if (resident && e.ksize == 1 && e.stride == 1 && e.pad == 0 && positions < (1LL << 31)) {
+        e.batch = 1;
+        e.h = e.ho = 1;
+        e.w = e.wo = (int)positions;
+    }
     return e;
 }
 
-bool plan_wgrad(const bcnn_b200_conv_desc *desc, WgPlan *pl) {
+bool plan_wgrad(const bcnn_b200_conv_desc *desc, WgPlan *pl, bool resident = false) {
     if (tma_disabled() || !encode_fn()) return false;
     if (desc->groups != 1) return false;
-    const WgEff e = wg_effective(desc);
+    const WgEff e = wg_effective(desc, resident);
     const WgEff *d = &e;
     if (d->cin < 16 || d->cout < 32) return false;
     if ((long long)d->batch * d->ho * d->wo < 512) return false;  // tiny reductions (fc-shaped)
-    const bool direct = !d->im2col && d->ksize == 1 && d->stride == 1 && d->pad == 0 &&
+    if (resident && (d->cin_phys % 8 != 0 || d->cout % 8 != 0)) return false;
+    const bool direct = !resident && !d->im2col && d->ksize == 1 && d->stride == 1 && d->pad == 0 &&
                         (d->h * d->w) % 4 == 0;
     pl->nhwc = !direct;
     if (!direct && (nhwc_disabled() || d->cin_phys % 4 != 0 || d->cout % 4 != 0 || d->stride > 4))
@@ -1373,7 +1717,7 @@ bool plan_wgrad(const bcnn_b200_conv_desc *desc, WgPlan *pl) {
     pl->n_tile = n;
     pl->ci_tiles = ceil_div(d->cin, n);
     pl->co_tiles = ceil_div(d->cout, TILE_M);
-    pl->bf16 = !direct && shadow_bf16() && d->cin_phys % 8 == 0 && d->cout % 8 == 0;
+    pl->bf16 = !direct && (resident || shadow_bf16()) && d->cin_phys % 8 == 0 && d->cout % 8 == 0;
     pl->nb = ceil_div(n, pl->bf16 ? 64 : 32);
     if (direct) {
         pl->view_w = d->h * d->w; pl->view_h = 1;
@@ -1405,6 +1749,10 @@ bool plan_wgrad(const bcnn_b200_conv_desc *desc, WgPlan *pl) {
         pl->stage_bytes = (uint32_t)(a_atoms + pl->nb) * pl->atom_bytes;
         pl->shadow_x_bytes = align256((size_t)d->batch * d->cin_phys * d->h * d->w * es);
         pl->shadow_dy_bytes = align256((size_t)d->batch * d->cout * d->ho * d->wo * es);
+        if (resident) {   // the tensors themselves are the operands; only a thin first layer's
+            pl->shadow_dy_bytes = 0;   // im2col buffer may have to be rebuilt
+            if (!d->im2col) pl->shadow_x_bytes = 0;
+        }
     }
     const long long kb_total = (long long)d->batch * pl->blocks_h * pl->blocks_w;
     if (kb_total >= (1LL << 31)) return false;
@@ -1591,12 +1939,14 @@ int conv_tma_backward_data(const bcnn_b200_conv_desc *d, const float *w, const f
     return launch_fwd(d, true, dy, w, nullptr, 0, dx, accumulate, workspace, workspace_bytes, sh, st);
 }
 
-int conv_tma_backward_weights(const bcnn_b200_conv_desc *desc, const float *x, const float *dy, float *gw,
-                              void *workspace, size_t workspace_bytes, bcnn_b200_conv_shadows *sh,
-                              cudaStream_t st) {
+static int backward_weights_impl(const bcnn_b200_conv_desc *desc, const void *x_any, const void *dy_any,
+                                 float *gw, void *workspace, size_t workspace_bytes,
+                                 bcnn_b200_conv_shadows *sh, bool resident, cudaStream_t st) {
+    const float *x = reinterpret_cast<const float *>(x_any);
+    const float *dy = reinterpret_cast<const float *>(dy_any);
     WgPlan pl;
-    if (!plan_wgrad(desc, &pl)) return (int)cudaErrorInvalidValue;
-    const WgEff e = wg_effective(desc);
+    if (!plan_wgrad(desc, &pl, resident)) return (int)cudaErrorInvalidValue;
+    const WgEff e = wg_effective(desc, resident);
     const WgEff *d = &e;
     const size_t need = pl.shadow_x_bytes + pl.shadow_dy_bytes + pl.partial_bytes;
     if (need > 0 && (workspace == nullptr || workspace_bytes < need)) return (int)cudaErrorInvalidValue;
@@ -1613,16 +1963,22 @@ int conv_tma_backward_weights(const bcnn_b200_conv_desc *desc, const float *x, c
         // x: the shadow (or im2col buffer) the forward pass of this layer kept, when its format fits
         const int x_fmt = d->im2col ? (pl.bf16 ? BCNN_B200_SHADOW_IM2COL_BF16 : BCNN_B200_SHADOW_IM2COL_F32)
                                     : (pl.bf16 ? BCNN_B200_SHADOW_NHWC_BF16 : BCNN_B200_SHADOW_NHWC_F32);
-        if (sh && sh->x && sh->x_fmt == x_fmt && sh->x_bytes >= pl.shadow_x_bytes) {
+        if (resident && !d->im2col) {
+            x_shadow = x_any;
+        } else if (sh && sh->x && sh->x_fmt == x_fmt && sh->x_bytes >= pl.shadow_x_bytes) {
             x_shadow = sh->x;
         } else {
             err = d->im2col ? launch_im2col(desc, x, ws, pl.bf16, st)
                             : launch_transpose(x, ws, d->batch, d->cin, d->h * d->w, pl.bf16, st);
             if (err) return err;
         }
-        err = dy_shadow(dy, d->batch, d->cout, d->ho * d->wo, pl.bf16, pl.shadow_dy_bytes, sh,
-                        ws + pl.shadow_x_bytes, &dy_sh, st);
-        if (err) return err;
+        if (resident) {
+            dy_sh = dy_any;
+        } else {
+            err = dy_shadow(dy, d->batch, d->cout, d->ho * d->wo, pl.bf16, pl.shadow_dy_bytes, sh,
+                            ws + pl.shadow_x_bytes, &dy_sh, st);
+            if (err) return err;
+        }
         if (!make_map_nhwc(&tm_dy, dy_sh, d->cout, d->wo, d->ho, d->batch, pl.bw, pl.bh, 1, 1, true,
                            pl.bf16) ||
             !make_map_nhwc(&tm_x, x_shadow, d->cin_phys, d->w, d->h, d->batch, pl.bw, pl.bh, 1, d->stride,
@@ -1655,6 +2011,64 @@ int conv_tma_backward_weights(const bcnn_b200_conv_desc *desc, const float *x, c
         return launched();
     }
     return 0;
+}
+
+int conv_tma_backward_weights(const bcnn_b200_conv_desc *desc, const float *x, const float *dy, float *gw,
+                              void *workspace, size_t workspace_bytes, bcnn_b200_conv_shadows *sh,
+                              cudaStream_t st) {
+    return backward_weights_impl(desc, x, dy, gw, workspace, workspace_bytes, sh, false, st);
+}
+
+// ---- resident (BF16 NHWC) entry points
+int conv_nhwc_supported(const bcnn_b200_conv_desc *d) {
+    FwdPlan pl;
+    WgPlan wp;
+    int mask = 0;
+    if (route_fwd_resident(d, false, &pl) != ROUTE_NONE) mask |= 1;
+    if (route_fwd_resident(d, true, &pl) != ROUTE_NONE) mask |= 2;
+    if (resident_desc_ok(d) && plan_wgrad(d, &wp, true)) mask |= 4;
+    return mask;
+}
+
+size_t conv_nhwc_workspace_bytes(const bcnn_b200_conv_desc *d) {
+    size_t need = 0;
+    FwdPlan pl;
+    FwdRoute r = route_fwd_resident(d, false, &pl);
+    if (r != ROUTE_NONE) need = (r == ROUTE_IM2COL ? im2col_bytes(d) : 0) + pl.wpack_bytes + pl.stat_bytes;
+    r = route_fwd_resident(d, true, &pl);
+    size_t b = r == ROUTE_STRIDED_DGRAD ? strided_dgrad_pack_bytes_resident(d) : (r == ROUTE_PLAIN ? pl.wpack_bytes : 0);
+    if (b > need) need = b;
+    WgPlan wp;
+    if (resident_desc_ok(d) && plan_wgrad(d, &wp, true)) {
+        b = wp.shadow_x_bytes + wp.partial_bytes;
+        if (b > need) need = b;
+    }
+    return need;
+}
+
+size_t conv_nhwc_x_keep_bytes(const bcnn_b200_conv_desc *d) {
+    FwdPlan pl;
+    return route_fwd_resident(d, false, &pl) == ROUTE_IM2COL ? im2col_bytes(d) : 0;
+}
+
+int conv_nhwc_forward(const bcnn_b200_conv_desc *d, const void *x, const float *w, const float *bias, int act,
+                      void *y16, void *workspace, size_t workspace_bytes, bcnn_b200_conv_shadows *sh,
+                      const float **stat_partial, int *stat_rows, cudaStream_t st) {
+    if (stat_partial) { *stat_partial = nullptr; *stat_rows = 0; }
+    return launch_fwd_resident(d, x, w, bias, act, y16, workspace, workspace_bytes, sh, st, stat_partial,
+                               stat_rows);
+}
+
+int conv_nhwc_backward_data(const bcnn_b200_conv_desc *d, const float *w, const void *dy16, void *dx16,
+                            int accumulate, void *workspace, size_t workspace_bytes, cudaStream_t st) {
+    return launch_dgrad_resident(d, w, dy16, dx16, accumulate, workspace, workspace_bytes, st);
+}
+
+int conv_nhwc_backward_weights(const bcnn_b200_conv_desc *d, const void *x, const void *dy16, float *gw,
+                               void *workspace, size_t workspace_bytes, bcnn_b200_conv_shadows *sh,
+                               cudaStream_t st) {
+    if (!resident_desc_ok(d)) return (int)cudaErrorInvalidValue;
+    return backward_weights_impl(d, x, dy16, gw, workspace, workspace_bytes, sh, true, st);
 }
 
 }  // namespace b200

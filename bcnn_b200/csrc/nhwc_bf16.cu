@@ -24,6 +24,7 @@
 #include <float.h>
 
 #include "common.cuh"
+#include "conv_impl.cuh"
 
 using namespace b200;
 
@@ -170,6 +171,7 @@ bn_apply_nhwc_kernel(const __nv_bfloat16 *__restrict__ x, __nv_bfloat16 *__restr
 // ------------------------------------------------------------------ per-channel backward reductions
 // MODE 0 (batch norm): dy' = dy * relu'(fma(x, a, b));  S1 = sum dy',  S2 = sum dy' * (x - mean)
 // MODE 1 (bias):       dy' = dy * act'(y), written back; S1 = sum dy'
+// MODE 2 (statistics): S1 = sum x, S2 = sum x * x (dy unused)
 // Block = lanes x cgb threads (cgb channel groups, lanes position lanes); partial[(block * 2 + k) * C + ch]
 template <int MODE>
 __global__ void __launch_bounds__(256)
@@ -206,7 +208,7 @@ reduce_nhwc_kernel(const __nv_bfloat16 *__restrict__ x, __nv_bfloat16 *dy,
                 const size_t p = p0 + u * step;
                 if (p < P) {
                     xv[u] = ld_stream_u4(x + p * C + ch0);
-                    gv[u] = MODE == 0 ? ld_stream_u4(dy + p * C + ch0) : ld_u4(dy + p * C + ch0);
+                    if (MODE != 2) gv[u] = MODE == 0 ? ld_stream_u4(dy + p * C + ch0) : ld_u4(dy + p * C + ch0);
                 }
             }
 #pragma unroll
@@ -215,8 +217,14 @@ reduce_nhwc_kernel(const __nv_bfloat16 *__restrict__ x, __nv_bfloat16 *dy,
                 if (p < P) {
                     float xf[8], gf[8];
                     unpack8(xv[u], xf);
-                    unpack8(gv[u], gf);
-                    if (MODE == 0) {
+                    if (MODE != 2) unpack8(gv[u], gf);
+                    if (MODE == 2) {
+#pragma unroll
+                        for (int j = 0; j < 8; ++j) {
+                            s1[j] += xf[j];
+                            s2[j] += xf[j] * xf[j];
+                        }
+                    } else if (MODE == 0) {
 #pragma unroll
                         for (int j = 0; j < 8; ++j) {
                             float d = gf[j];
@@ -568,6 +576,22 @@ extern "C" int bcnn_b200_bf16nhwc_to_f32nchw(const void *in, float *out, int n, 
 }
 
 extern "C" size_t bcnn_b200_nhwc_scratch_floats(int c) { return (size_t)2 * 2 * sm_count() * c + 64; }
+
+extern "C" int bcnn_b200_bn_stats_nhwc(const void *x, size_t positions, int c, float *saved_mean,
+                                       float *saved_var, float *run_mean, float *run_var,
+                                       float *nhwc_scratch, float *scratch, void *stream) {
+    if (positions == 0 || c == 0) return 0;
+    if (c % 8) return (int)cudaErrorInvalidValue;
+    cudaStream_t st = as_stream(stream);
+    const ReducePlan r = plan_reduce(positions, c);
+    reduce_nhwc_kernel<2><<<dim3(r.gx, r.gy), 256, r.smem, st>>>(
+        reinterpret_cast<const __nv_bfloat16 *>(x), nullptr, nullptr, nullptr, nullptr, nullptr, ACT_NONE,
+        positions, c, r.cgb, r.lanes, nhwc_scratch);
+    int err = launched();
+    if (err) return err;
+    return b200::bn_stats_from_partials(nhwc_scratch, r.gx, c, (double)positions, saved_mean, saved_var,
+                                        run_mean, run_var, scratch, st);
+}
 
 extern "C" int bcnn_b200_bn_apply_nhwc(const void *x, void *y, const float *mean, const float *var,
                                        const float *gamma, const float *beta, size_t positions, int c,

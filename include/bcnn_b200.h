@@ -28,9 +28,14 @@ extern "C" {
 /* Convolution arithmetic selection (per net, see bcnn_b200_set_conv_math). */
 enum {
     BCNN_B200_MATH_FP32 = 0, /* FP32 SIMT implicit GEMM: 1e-5 verification path */
-    BCNN_B200_MATH_TC = 1    /* BF16 tcgen05 implicit GEMM, FP32 accumulate in TMEM:
+    BCNN_B200_MATH_TC = 1,   /* BF16 / TF32 tcgen05 implicit GEMM, FP32 accumulate in TMEM:
                                 2e-2 path; falls back per layer to FP32 for shapes
                                 it does not cover (never to the CPU) */
+    BCNN_B200_MATH_TC_BF16 = 2 /* the same tensor-core kernels with RESIDENT activations:
+                                between two convolutions tensors and their gradients live
+                                as BF16 NHWC (see the block at the end of this header);
+                                FP32 NCHW copies are made when somebody asks for them.
+                                Kernel-level entry points treat it as MATH_TC. */
 };
 
 /* Geometry of one convolution; shared by fprop / dgrad / wgrad. */
@@ -382,6 +387,12 @@ BCNN_B200_API int bcnn_b200_bf16nhwc_to_f32nchw(const void *in, float *out, int 
                                                 void *stream);
 /* floats of scratch the two reductions below need for `c` channels */
 BCNN_B200_API size_t bcnn_b200_nhwc_scratch_floats(int c);
+/* TRAIN statistics of a BF16 NHWC tensor: what bcnn_b200_bn_stats computes (biased variance,
+ * running = 0.9 running + 0.1 batch). nhwc_scratch: bcnn_b200_nhwc_scratch_floats(c) floats,
+ * scratch: bcnn_b200_bn_scratch_floats(c) floats. */
+BCNN_B200_API int bcnn_b200_bn_stats_nhwc(const void *x, size_t positions, int c, float *saved_mean,
+                                          float *saved_var, float *run_mean, float *run_var,
+                                          float *nhwc_scratch, float *scratch, void *stream);
 /* y = act(gamma (x - mean) / sqrt(var + 1e-6) + beta); mean == NULL: y = act(gamma x + beta)
  * (PREDICT). act: NONE, RELU or LRELU. x may alias y. Shadows bcnn_b200_bn_apply / _scale_bias. */
 BCNN_B200_API int bcnn_b200_bn_apply_nhwc(const void *x, void *y, const float *mean, const float *var,
@@ -418,6 +429,42 @@ BCNN_B200_API int bcnn_b200_avgpool_forward_nhwc(const void *x, float *y, int n,
                                                  void *stream);
 BCNN_B200_API int bcnn_b200_avgpool_backward_nhwc(void *dx, const float *dy, int n, int c, int hw,
                                                   int accumulate, void *stream);
+
+/* Convolution on resident tensors: x, y, dy, dx are BF16 NHWC; weights, bias and the weight
+ * gradient stay FP32 in the reference's [Cout, Cin, k, k] layout. Same three passes and the same
+ * semantics as bcnn_b200_conv_forward / _backward_data / _backward_weights above (reference
+ * src/layers/bcnn_conv_layer.c:367-587), on the tcgen05 + TMA kernels only: the TMA reads the
+ * activation tensor itself (no transposed shadow), the epilogue writes BF16 NHWC through a bulk
+ * tensor store. 1x1 problems see the batch as one row of N*H*W positions.
+ * _supported: bit mask of the passes these kernels cover for `d` (1 fprop, 2 dgrad, 4 wgrad);
+ * needs groups == 1, cout % 8 == 0 and cin % 8 == 0. A thin first layer (cin < 16) is covered too:
+ * its `x` is the FP32 NCHW input, gathered into a BF16 im2col buffer that `sh->x` keeps for wgrad
+ * (_x_keep_bytes = its size). */
+BCNN_B200_API int bcnn_b200_conv_nhwc_supported(const bcnn_b200_conv_desc *d);
+BCNN_B200_API size_t bcnn_b200_conv_nhwc_workspace_bytes(const bcnn_b200_conv_desc *d);
+BCNN_B200_API size_t bcnn_b200_conv_nhwc_x_keep_bytes(const bcnn_b200_conv_desc *d);
+BCNN_B200_API int bcnn_b200_conv_forward_nhwc(const bcnn_b200_conv_desc *d, const void *x,
+                                              const float *w, const float *bias, int act, void *y,
+                                              void *workspace, size_t workspace_bytes,
+                                              bcnn_b200_conv_shadows *sh, void *stream);
+/* shadows bcnn_b200_conv_forward_bn_stats: y is the raw convolution result, statistics come from
+ * the FP32 accumulators in the epilogue (or, when that is not possible, from bcnn_b200_bn_stats_nhwc
+ * over y). */
+BCNN_B200_API int bcnn_b200_conv_forward_bn_stats_nhwc(const bcnn_b200_conv_desc *d, const void *x,
+                                                       const float *w, void *y, void *workspace,
+                                                       size_t workspace_bytes,
+                                                       bcnn_b200_conv_shadows *sh, float *saved_mean,
+                                                       float *saved_var, float *run_mean,
+                                                       float *run_var, float *nhwc_scratch,
+                                                       float *scratch, void *stream);
+BCNN_B200_API int bcnn_b200_conv_backward_data_nhwc(const bcnn_b200_conv_desc *d, const float *w,
+                                                    const void *dy, void *dx, int accumulate,
+                                                    void *workspace, size_t workspace_bytes,
+                                                    void *stream);
+BCNN_B200_API int bcnn_b200_conv_backward_weights_nhwc(const bcnn_b200_conv_desc *d, const void *x,
+                                                       const void *dy, float *gw, void *workspace,
+                                                       size_t workspace_bytes,
+                                                       bcnn_b200_conv_shadows *sh, void *stream);
 
 #ifdef __cplusplus
 }

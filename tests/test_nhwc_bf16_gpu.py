@@ -209,3 +209,140 @@ def test_avgpool_nhwc(shape):
     dg, ddx = dev(g), dev(nhwc_bits(np.full_like(x, 5.0)))
     check(lib.bcnn_b200_avgpool_backward_nhwc(ddx.ptr, dg.ptr, n, c, h * w, 0, None))
     assert_close(nchw_from_bits(ddx.download(np.uint16), shape), dx_ref, BF16_OUT_TOL, "avgpool dx")
+
+
+# ------------------------------------------------------------------ convolution on resident tensors
+# (cin, h, cout, k, stride, pad): every ResNet-50 class plus YOLO / odd shapes
+RESIDENT_CONVS = [
+    (64, 56, 64, 1, 1, 0), (64, 56, 64, 3, 1, 1), (64, 56, 256, 1, 1, 0), (256, 56, 64, 1, 1, 0),
+    (128, 56, 128, 3, 2, 1), (256, 56, 512, 1, 2, 0), (256, 28, 256, 3, 2, 1), (512, 28, 128, 1, 1, 0),
+    (256, 14, 256, 3, 1, 1), (1024, 14, 256, 1, 1, 0), (512, 14, 512, 3, 2, 1), (512, 7, 2048, 1, 1, 0),
+    (2048, 7, 512, 1, 1, 0), (512, 7, 512, 3, 1, 1), (1024, 14, 2048, 1, 2, 0),
+    (16, 26, 32, 3, 1, 1), (32, 13, 72, 3, 1, 1), (24, 9, 40, 1, 1, 0), (128, 13, 256, 3, 1, 1),
+    (64, 20, 384, 3, 1, 1),
+]
+
+
+def _conv_case(shape, batch, seed_extra=0):
+    cin, h, cout, k, s, pad = shape
+    orc = oracle()
+    r = rng(hash(shape) % 2**31 + seed_extra)
+    d = capi.ConvDesc.make(batch, cin, h, h, cout, k, s, pad, 1)
+    x = rounded(f32(r.uniform(-1, 1, size=(batch, cin, h, h))))
+    wt = f32(r.uniform(-1, 1, size=(cout, cin, k, k)) * np.sqrt(3.0 / (cin * k * k)))
+    y = np.zeros((batch, cout, d.ho, d.wo), np.float32)
+    orc.orc_conv_forward(p(x), p(wt), p(y), batch, cin, h, h, cout, k, s, pad, 1)
+    dy = rounded(f32(r.uniform(-1, 1, size=y.shape)))
+    gw0 = f32(r.uniform(-0.1, 0.1, size=wt.shape))
+    gw = gw0.copy()
+    dx = np.zeros_like(x)
+    orc.orc_conv_backward(p(x), p(wt), p(dy), p(gw), p(dx), batch, cin, h, h, cout, k, s, pad, 1)
+    return d, x, wt, y, dy, gw0, gw, dx
+
+
+@pytest.mark.parametrize("shape", RESIDENT_CONVS, ids=lambda s: "x".join(map(str, s)))
+@pytest.mark.parametrize("batch", [2, 5])
+def test_resident_conv_three_passes_vs_oracle(shape, batch):
+    """fprop (+bias +ReLU), dgrad (overwrite and accumulate), wgrad (+=) on BF16 NHWC tensors against
+    the oracle on the same BF16-rounded inputs: 2e-2 tensor-core class (weights are rounded to BF16 by
+    the packing kernel, results to BF16 by the epilogue)."""
+    lib = capi.b200()
+    d, x, wt, y_ref, dy, gw0, gw_ref, dx_ref = _conv_case(shape, batch)
+    mask = lib.bcnn_b200_conv_nhwc_supported(d)
+    assert mask & 1 and mask & 2, f"{shape}: fprop / dgrad not on the resident kernels ({mask})"
+    ws_bytes = lib.bcnn_b200_conv_nhwc_workspace_bytes(d)
+    ws = capi.DeviceBuffer(nbytes=max(ws_bytes, 256))
+    dxb, dwt = dev(nhwc_bits(x)), dev(wt)
+    dyo = dev(np.full(y_ref.size, 0x7fc0, np.uint16))           # NaN-filled: every element must be written
+    check(lib.bcnn_b200_conv_forward_nhwc(d, dxb.ptr, dwt.ptr, None, 0, dyo.ptr, ws.ptr, ws_bytes, None, None))
+    got = nchw_from_bits(dyo.download(np.uint16), y_ref.shape)
+    assert_close(got, y_ref, 2e-2, "fprop")
+    # bias + ReLU in the epilogue
+    bias = f32(rng(3).uniform(-0.5, 0.5, size=d.cout))
+    dbias = dev(bias)
+    check(lib.bcnn_b200_conv_forward_nhwc(d, dxb.ptr, dwt.ptr, dbias.ptr, ACT["relu"], dyo.ptr, ws.ptr,
+                                          ws_bytes, None, None))
+    got = nchw_from_bits(dyo.download(np.uint16), y_ref.shape)
+    assert_close(got, np.maximum(y_ref + bias.reshape(1, -1, 1, 1), 0), 2e-2, "fprop + bias + relu")
+    # dgrad
+    ddy = dev(nhwc_bits(dy))
+    ddx = dev(np.full(x.size, 0x7fc0, np.uint16))
+    check(lib.bcnn_b200_conv_backward_data_nhwc(d, dwt.ptr, ddy.ptr, ddx.ptr, 0, ws.ptr, ws_bytes, None))
+    got = nchw_from_bits(ddx.download(np.uint16), x.shape)
+    assert_close(got, dx_ref, 2e-2, "dgrad (overwrite)")
+    base = rounded(f32(rng(4).uniform(-1, 1, size=x.shape)))
+    ddx = dev(nhwc_bits(base))
+    check(lib.bcnn_b200_conv_backward_data_nhwc(d, dwt.ptr, ddy.ptr, ddx.ptr, 1, ws.ptr, ws_bytes, None))
+    got = nchw_from_bits(ddx.download(np.uint16), x.shape)
+    assert_close(got, dx_ref + base, 2e-2, "dgrad (accumulate)")
+    # wgrad
+    if mask & 4:
+        dgw = dev(gw0)
+        check(lib.bcnn_b200_conv_backward_weights_nhwc(d, dxb.ptr, ddy.ptr, dgw.ptr, ws.ptr, ws_bytes, None, None))
+        assert_close(dgw.download(np.float32, wt.shape), gw_ref, 2e-2, "wgrad (+=)")
+    else:
+        assert batch * d.ho * d.wo < 512 or d.cout < 32 or d.cin < 16, f"{shape}: wgrad not covered"
+
+
+@pytest.mark.parametrize("shape", [(64, 56, 64, 3, 1, 1), (256, 14, 1024, 1, 1, 0), (512, 7, 512, 3, 1, 1),
+                                   (128, 28, 512, 1, 1, 0)], ids=lambda s: "x".join(map(str, s)))
+def test_resident_conv_fused_bn_statistics(shape):
+    """Mean / biased variance / running statistics from the epilogue's FP32 accumulators against the
+    oracle's batch-norm forward over the oracle's convolution result."""
+    lib, orc = capi.b200(), oracle()
+    batch = 4
+    d, x, wt, y_ref, *_ = _conv_case(shape, batch, 7)
+    c, hw = d.cout, d.ho * d.wo
+    rm, rv, sm, sv = (np.zeros(c, np.float32) for _ in range(4))
+    gamma, beta = np.ones(c, np.float32), np.zeros(c, np.float32)
+    yy = y_ref.copy()
+    xn, xc = np.zeros_like(yy), np.zeros_like(yy)
+    orc.orc_bn_forward(p(yy), batch, c, hw, p(rm), p(rv), p(gamma), p(beta), p(sm), p(sv), p(xn), p(xc), 1)
+    ws_bytes = lib.bcnn_b200_conv_nhwc_workspace_bytes(d)
+    ws = capi.DeviceBuffer(nbytes=max(ws_bytes, 256))
+    dxb, dwt, dyo = dev(nhwc_bits(x)), dev(wt), dev_zeros(y_ref.size, 2)
+    dsm, dsv, drm, drv = (dev(np.zeros(c, np.float32)) for _ in range(4))
+    sc1 = capi.DeviceBuffer(nbytes=4 * lib.bcnn_b200_nhwc_scratch_floats(c))
+    sc2 = capi.DeviceBuffer(nbytes=4 * lib.bcnn_b200_bn_scratch_floats(c))
+    check(lib.bcnn_b200_conv_forward_bn_stats_nhwc(d, dxb.ptr, dwt.ptr, dyo.ptr, ws.ptr, ws_bytes, None,
+                                                   dsm.ptr, dsv.ptr, drm.ptr, drv.ptr, sc1.ptr, sc2.ptr, None))
+    assert_close(nchw_from_bits(dyo.download(np.uint16), y_ref.shape), y_ref, 2e-2, "raw result")
+    assert_close(dsm.download(), sm, 2e-2, "saved mean")
+    assert_close(dsv.download(), sv, 2e-2, "saved variance")
+    assert_close(drm.download(), rm, 2e-2, "running mean")
+    assert_close(drv.download(), rv, 2e-2, "running variance")
+    # the stand-alone statistics kernel over the BF16 result agrees with the fused ones
+    dsm2, dsv2, drm2, drv2 = (dev(np.zeros(c, np.float32)) for _ in range(4))
+    check(lib.bcnn_b200_bn_stats_nhwc(dyo.ptr, batch * hw, c, dsm2.ptr, dsv2.ptr, drm2.ptr, drv2.ptr,
+                                      sc1.ptr, sc2.ptr, None))
+    assert_close(dsm2.download(), sm, 2e-2, "stand-alone mean")
+    assert_close(dsv2.download(), sv, 2e-2, "stand-alone variance")
+
+
+def test_resident_thin_first_layer_reads_fp32_nchw():
+    """ResNet-50's stem (3 -> 64, 7x7 / 2) and YOLOv3-tiny's first layer: FP32 NCHW input gathered into a
+    BF16 im2col buffer, BF16 NHWC result; wgrad from the kept buffer."""
+    lib = capi.b200()
+    for shape, batch in (((3, 224, 64, 7, 2, 3), 2), ((3, 64, 16, 3, 1, 1), 2)):
+        d, x, wt, y_ref, dy, gw0, gw_ref, _ = _conv_case(shape, batch, 11)
+        mask = lib.bcnn_b200_conv_nhwc_supported(d)
+        assert mask & 1, shape
+        ws_bytes = lib.bcnn_b200_conv_nhwc_workspace_bytes(d)
+        ws = capi.DeviceBuffer(nbytes=max(ws_bytes, 256))
+        keep = capi.DeviceBuffer(nbytes=lib.bcnn_b200_conv_nhwc_x_keep_bytes(d))
+        sh = capi.ConvShadows()
+        sh.x, sh.x_bytes = keep.ptr, keep.nbytes
+        dxf, dwt, dyo = dev(x), dev(wt), dev_zeros(y_ref.size, 2)
+        check(lib.bcnn_b200_conv_forward_nhwc(d, dxf.ptr, dwt.ptr, None, 0, dyo.ptr, ws.ptr, ws_bytes,
+                                              capi.C.byref(sh), None))
+        assert_close(nchw_from_bits(dyo.download(np.uint16), y_ref.shape), y_ref, 2e-2, f"fprop {shape}")
+        if mask & 4:
+            ddy, dgw = dev(nhwc_bits(dy)), dev(gw0)
+            check(lib.bcnn_b200_conv_backward_weights_nhwc(d, dxf.ptr, ddy.ptr, dgw.ptr, ws.ptr, ws_bytes,
+                                                           capi.C.byref(sh), None))
+            assert_close(dgw.download(np.float32, wt.shape), gw_ref, 2e-2, f"wgrad {shape}")
+            # and without the kept buffer (rebuilt in the workspace)
+            dgw = dev(gw0)
+            check(lib.bcnn_b200_conv_backward_weights_nhwc(d, dxf.ptr, ddy.ptr, dgw.ptr, ws.ptr, ws_bytes,
+                                                           None, None))
+            assert_close(dgw.download(np.float32, wt.shape), gw_ref, 2e-2, f"wgrad rebuilt {shape}")
