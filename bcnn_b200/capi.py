@@ -30,7 +30,7 @@ LOSS_EUCLIDEAN = 0
 METRIC_ERROR_RATE, METRIC_LOGLOSS, METRIC_SSE, METRIC_MSE = 0, 1, 2, 3
 LOG_SILENT = 3
 LAYER_CONV2D, LAYER_MAXPOOL, LAYER_BATCHNORM, LAYER_COST = 0, 5, 9, 16
-MATH_FP32, MATH_TC = 0, 1
+MATH_FP32, MATH_TC, MATH_TC_BF16 = 0, 1, 2   # include/bcnn_b200.h; 2 = resident BF16 NHWC activations
 
 
 class TensorB200(C.Structure):

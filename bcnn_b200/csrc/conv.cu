@@ -19,18 +19,18 @@ extern "C" int bcnn_b200_conv_uses_tensor_cores(const bcnn_b200_conv_desc *d, in
 
 extern "C" size_t bcnn_b200_conv_workspace_bytes(const bcnn_b200_conv_desc *d, int math) {
     size_t a = conv_simt_workspace_bytes(d);
-    size_t b = (math == BCNN_B200_MATH_TC) ? conv_tc_workspace_bytes(d) : 0;
-    size_t c = (math == BCNN_B200_MATH_TC) ? conv_tma_workspace_bytes(d) : 0;
+    size_t b = (math != BCNN_B200_MATH_FP32) ? conv_tc_workspace_bytes(d) : 0;
+    size_t c = (math != BCNN_B200_MATH_FP32) ? conv_tma_workspace_bytes(d) : 0;
     if (b > a) a = b;
     return a > c ? a : c;
 }
 
 extern "C" size_t bcnn_b200_conv_x_shadow_bytes(const bcnn_b200_conv_desc *d, int math) {
-    return math == BCNN_B200_MATH_TC ? conv_tma_x_shadow_bytes(d) : 0;
+    return math != BCNN_B200_MATH_FP32 ? conv_tma_x_shadow_bytes(d) : 0;
 }
 
 extern "C" size_t bcnn_b200_conv_dy_shadow_bytes(const bcnn_b200_conv_desc *d, int math) {
-    return math == BCNN_B200_MATH_TC ? conv_tma_dy_shadow_bytes(d) : 0;
+    return math != BCNN_B200_MATH_FP32 ? conv_tma_dy_shadow_bytes(d) : 0;
 }
 
 extern "C" int bcnn_b200_conv_forward(const bcnn_b200_conv_desc *d, const float *x,
@@ -61,9 +61,9 @@ extern "C" int bcnn_b200_conv_forward_sh(const bcnn_b200_conv_desc *d, const flo
                                          void *workspace, size_t workspace_bytes, int math,
                                          bcnn_b200_conv_shadows *sh, void *stream) {
     cudaStream_t st = as_stream(stream);
-    if (math == BCNN_B200_MATH_TC && conv_tma_supports_fprop(d))
+    if (math != BCNN_B200_MATH_FP32 && conv_tma_supports_fprop(d))
         return conv_tma_forward(d, x, w, bias, act, y, workspace, workspace_bytes, sh, st);
-    if (math == BCNN_B200_MATH_TC && conv_tc_supports_fprop(d))
+    if (math != BCNN_B200_MATH_FP32 && conv_tc_supports_fprop(d))
         return conv_tc_forward(d, x, w, bias, act, y, workspace, workspace_bytes, st);
     return conv_simt_forward(d, x, w, bias, act, y, workspace, workspace_bytes, st);
 }
@@ -80,7 +80,7 @@ extern "C" int bcnn_b200_conv_forward_bn_stats(const bcnn_b200_conv_desc *d, con
         const char *e = getenv("BCNN_B200_NO_FUSED_BN_STATS");
         unfused = (e && e[0] && e[0] != '0') ? 1 : 0;
     }
-    if (!unfused && math == BCNN_B200_MATH_TC && conv_tma_supports_fprop(d)) {
+    if (!unfused && math != BCNN_B200_MATH_FP32 && conv_tma_supports_fprop(d)) {
         const float *partial = nullptr;
         int rows = 0;
         int err = conv_tma_forward_stats(d, x, w, y, workspace, workspace_bytes, sh, &partial, &rows, st);
@@ -103,9 +103,9 @@ extern "C" int bcnn_b200_conv_backward_data_sh(const bcnn_b200_conv_desc *d, con
                                                void *workspace, size_t workspace_bytes, int math,
                                                bcnn_b200_conv_shadows *sh, void *stream) {
     cudaStream_t st = as_stream(stream);
-    if (math == BCNN_B200_MATH_TC && conv_tma_supports_dgrad(d))
+    if (math != BCNN_B200_MATH_FP32 && conv_tma_supports_dgrad(d))
         return conv_tma_backward_data(d, w, dy, dx, accumulate, workspace, workspace_bytes, sh, st);
-    if (math == BCNN_B200_MATH_TC && conv_tc_supports_dgrad(d))
+    if (math != BCNN_B200_MATH_FP32 && conv_tc_supports_dgrad(d))
         return conv_tc_backward_data(d, w, dy, dx, accumulate, workspace, workspace_bytes, st);
     return conv_simt_backward_data(d, w, dy, dx, accumulate, workspace, workspace_bytes, st);
 }
@@ -115,9 +115,9 @@ extern "C" int bcnn_b200_conv_backward_weights_sh(const bcnn_b200_conv_desc *d, 
                                                   size_t workspace_bytes, int math,
                                                   bcnn_b200_conv_shadows *sh, void *stream) {
     cudaStream_t st = as_stream(stream);
-    if (math == BCNN_B200_MATH_TC && conv_tma_supports_wgrad(d))
+    if (math != BCNN_B200_MATH_FP32 && conv_tma_supports_wgrad(d))
         return conv_tma_backward_weights(d, x, dy, gw, workspace, workspace_bytes, sh, st);
-    if (math == BCNN_B200_MATH_TC && conv_tc_supports_wgrad(d))
+    if (math != BCNN_B200_MATH_FP32 && conv_tc_supports_wgrad(d))
         return conv_tc_backward_weights(d, x, dy, gw, workspace, workspace_bytes, st);
     return conv_simt_backward_weights(d, x, dy, gw, workspace, workspace_bytes, st);
 }

@@ -38,9 +38,10 @@ bcnn_status bcnn_net_create_cuda_context(bcnn_net *net) {
     /* Tensor-core math is the default; BCNN_B200_CONV_MATH=fp32 (or bcnn_b200_set_conv_math)
      * selects the FP32 SIMT verification path. */
     const char *math = getenv("BCNN_B200_CONV_MATH");
-    ctx->conv_math = (math && (math[0] == 'f' || math[0] == 'F' || math[0] == '0'))
-                         ? BCNN_B200_MATH_FP32
-                         : BCNN_B200_MATH_TC;
+    ctx->conv_math = BCNN_B200_MATH_TC;
+    if (math && (math[0] == 'f' || math[0] == 'F' || math[0] == '0')) ctx->conv_math = BCNN_B200_MATH_FP32;
+    else if (math && (math[0] == 'r' || math[0] == 'R' || math[0] == 'b' || math[0] == 'B' || math[0] == '2'))
+        ctx->conv_math = BCNN_B200_MATH_TC_BF16; /* "resident" / "bf16" */
     /* Batch-correct residual semantics by default; the reference's two residual bugs (H2, H3) are
      * replicated only on request (parity tests): BCNN_B200_REFERENCE_QUIRKS=1 or
      * bcnn_b200_set_reference_quirks(net, 1). */
@@ -100,6 +101,7 @@ void bcnn_end_net(bcnn_net **net) {
         free(ctx->grad_fresh);
         free(ctx->consumers);
         forward_graph_drop(ctx);
+        bcnn_net_resident_release(p);
         bcnn_b200_free(ctx->workspace_gpu);
         bcnn_b200_free(ctx->dy_shadow_gpu);
         if (ctx->stage_gpu) {
@@ -197,6 +199,9 @@ bcnn_tensor *bcnn_get_tensor_by_index(bcnn_net *net, int index) {
     if (bytes == 0 || !t->data_gpu) return t;
     void *stream = bcnn_stream(net);
     if (bcnn_tensor_ensure_host(t) != BCNN_SUCCESS) return NULL;
+    /* resident mode: the FP32 NCHW buffers are materialised from the BF16 NHWC twins here */
+    (void)bcnn_net_data32_in(net, index);
+    if (t->grad_data_gpu) (void)bcnn_net_grad32_in(net, index);
     bcnn_cuda_check(bcnn_b200_memcpy_d2h(t->data, t->data_gpu, bytes, stream));
     if (t->grad_data_gpu && t->grad_data)
         bcnn_cuda_check(bcnn_b200_memcpy_d2h(t->grad_data, t->grad_data_gpu, bytes, stream));
@@ -234,6 +239,7 @@ static void reset_output_gradients(bcnn_net *net, bcnn_node *node) {
         const int idx = node->dst[i];
         bcnn_tensor *t = &net->tensors[idx];
         if (!t->grad_data_gpu) continue;
+        bcnn_net_grad32_written(net, idx); /* stale either way; a resident writer claims it again */
         if (ctx->consumers[idx] == 0) {
             bcnn_cuda_check(bcnn_b200_fill_f32(t->grad_data_gpu, (size_t)bcnn_tensor_size(t), 0.0f,
                                                bcnn_stream(net)));
@@ -255,9 +261,11 @@ int bcnn_net_grad_accumulate(bcnn_net *net, int index) {
 void bcnn_net_grad_prepare_accumulate(bcnn_net *net, int index) {
     if (bcnn_net_grad_accumulate(net, index)) return;
     bcnn_tensor *t = &net->tensors[index];
-    if (t->grad_data_gpu)
+    if (t->grad_data_gpu) {
         bcnn_cuda_check(bcnn_b200_fill_f32(t->grad_data_gpu, (size_t)bcnn_tensor_size(t), 0.0f,
                                            bcnn_stream(net)));
+        bcnn_net_grad32_written(net, index);
+    }
 }
 
 static inline void profile_mark(bcnn_net *net, int node, int slot) {
@@ -272,7 +280,13 @@ static void forward_nodes(bcnn_net *net) {
         bcnn_node *node = &net->nodes[i];
         profile_mark(net, i, 0);
         if (net->mode == BCNN_MODE_TRAIN) reset_output_gradients(net, node);
-        node->forward(net, node);
+        if (bcnn_net_node_is_resident(net, node)) {
+            node->forward(net, node);
+        } else { /* the node reads and writes the FP32 NCHW buffers */
+            bcnn_net_node_f32_before_forward(net, node);
+            node->forward(net, node);
+            bcnn_net_node_f32_after_forward(net, node);
+        }
         profile_mark(net, i, 1);
     }
 }
@@ -360,7 +374,13 @@ void bcnn_backward(bcnn_net *net) {
     for (int i = net->num_nodes - 1; i >= 0; --i) {
         bcnn_node *node = &net->nodes[i];
         profile_mark(net, i, 2);
-        node->backward(net, node);
+        if (bcnn_net_node_is_resident(net, node)) {
+            node->backward(net, node);
+        } else {
+            bcnn_net_node_f32_before_backward(net, node);
+            node->backward(net, node);
+            bcnn_net_node_f32_after_backward(net, node);
+        }
         profile_mark(net, i, 3);
         bcnn_dp_after_node_backward(net, node); /* no-op without data parallelism */
     }
@@ -449,7 +469,18 @@ float bcnn_net_grad_post_scale(bcnn_net *net, float momentum) {
 
 /* ---------------- extension API (include/bcnn_b200_net.h) ---------------- */
 
-void bcnn_b200_set_conv_math(bcnn_net *net, int math) { bcnn_ctx(net)->conv_math = math; }
+void bcnn_b200_set_conv_math(bcnn_net *net, int math) {
+    bcnn_cuda_context *ctx = bcnn_ctx(net);
+    if (ctx->conv_math == math) return;
+    /* leaving the resident mode: every tensor's current value goes back to the FP32 buffers */
+    for (int i = 0; i < ctx->res_count && i < net->num_tensors; ++i) {
+        (void)bcnn_net_data32_in(net, i);
+        if (net->tensors[i].grad_data_gpu) (void)bcnn_net_grad32_in(net, i);
+        ctx->res[i].data_at = ctx->res[i].grad_at = BCNN_RES_F32;
+    }
+    forward_graph_drop(ctx);
+    ctx->conv_math = math;
+}
 void bcnn_b200_set_reference_quirks(bcnn_net *net, int on) {
     if (bcnn_ctx(net)->reference_quirks != on) forward_graph_drop(bcnn_ctx(net));
     bcnn_ctx(net)->reference_quirks = on;
@@ -473,6 +504,8 @@ bcnn_status bcnn_b200_upload_tensor(bcnn_net *net, int index) {
     if (t->data && t->data_gpu) bcnn_cuda_check(bcnn_b200_memcpy_h2d(t->data_gpu, t->data, bytes, stream));
     if (t->grad_data && t->grad_data_gpu)
         bcnn_cuda_check(bcnn_b200_memcpy_h2d(t->grad_data_gpu, t->grad_data, bytes, stream));
+    bcnn_net_data32_written(net, index);
+    bcnn_net_grad32_written(net, index);
     bcnn_cuda_check(bcnn_b200_stream_sync(stream));
     return BCNN_SUCCESS;
 }
@@ -485,6 +518,7 @@ size_t bcnn_b200_upload_inputs(bcnn_net *net) {
         size_t bytes = (size_t)bcnn_tensor_size(t) * sizeof(float);
         if (!t->data || !t->data_gpu || bytes == 0) continue;
         bcnn_cuda_check(bcnn_b200_memcpy_h2d(t->data_gpu, t->data, bytes, stream));
+        bcnn_net_data32_written(net, i < net->num_inputs ? net->inputs[i] : 1);
         queued += bytes;
     }
     return queued;
@@ -567,6 +601,7 @@ static void pipeline_swap_in(bcnn_net *net) {
         float *live = t->data_gpu;
         t->data_gpu = ctx->stage_gpu[i];
         ctx->stage_gpu[i] = live;
+        bcnn_net_data32_written(net, i < net->num_inputs ? net->inputs[i] : 1);
     }
     ctx->stage_valid = 0;
     /* completes when every earlier step has: from then on the old live buffers are free */

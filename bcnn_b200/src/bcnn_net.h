@@ -81,7 +81,20 @@ typedef struct bcnn_cuda_context {
     unsigned char *grad_fresh;
     int *consumers; /* activation consumers per tensor (bcnn_net_num_consumers) */
     int grad_state_tensors, grad_state_nodes;
+    /* Resident BF16 NHWC activations (conv_math == BCNN_B200_MATH_TC_BF16, bcnn_resident.c):
+     * per tensor a BF16 NHWC twin of data / grad, made on first use, and which copy is current. */
+    struct bcnn_resident *res;
+    int res_count;
+    float *nhwc_scratch_gpu; /* per-channel reduction partials of the NHWC kernels (max over nodes) */
+    size_t nhwc_scratch_floats;
 } bcnn_cuda_context;
+
+/* Where the current value of a tensor's data / gradient lives. */
+enum { BCNN_RES_F32 = 0, BCNN_RES_BF16 = 1, BCNN_RES_BOTH = 2 };
+typedef struct bcnn_resident {
+    void *data16, *grad16;
+    unsigned char data_at, grad_at; /* BCNN_RES_* */
+} bcnn_resident;
 
 struct bcnn_net {
     int batch_size;
@@ -136,6 +149,37 @@ void bcnn_net_require_dy_shadow(bcnn_net *net, size_t bytes);
  * with after an SGD step (momentum, or momentum / world under data parallelism). */
 int bcnn_net_global_batch(bcnn_net *net);
 float bcnn_net_grad_post_scale(bcnn_net *net, float momentum);
+
+/* ---- resident BF16 NHWC activations (bcnn_resident.c) ----
+ * In BCNN_B200_MATH_TC_BF16 the layers between two convolutions keep activations and their
+ * gradients as BF16 NHWC. bcnn_tensor.data_gpu / grad_data_gpu (FP32 NCHW, the reference's
+ * contract, inc/bcnn/bcnn.h:242-255) are brought up to date on demand: by
+ * bcnn_get_tensor_by_index and in front of every node that is not format-aware. */
+int bcnn_net_resident(bcnn_net *net);              /* the net runs in the resident mode */
+int bcnn_net_tensor_can16(bcnn_net *net, int idx); /* shape allows a BF16 NHWC twin (c % 8 == 0) */
+/* current value as BF16 NHWC (converted from FP32 if that copy is the current one) */
+void *bcnn_net_data16_in(bcnn_net *net, int idx);
+void *bcnn_net_grad16_in(bcnn_net *net, int idx);
+/* buffer about to be overwritten with BF16 NHWC content: afterwards it is the only current copy */
+void *bcnn_net_data16_out(bcnn_net *net, int idx);
+void *bcnn_net_grad16_out(bcnn_net *net, int idx);
+/* the BF16 copy was modified in place: the FP32 copy is stale */
+void bcnn_net_grad16_modified(bcnn_net *net, int idx);
+/* current value as FP32 NCHW in data_gpu / grad_data_gpu (converted if needed) */
+float *bcnn_net_data32_in(bcnn_net *net, int idx);
+float *bcnn_net_grad32_in(bcnn_net *net, int idx);
+/* data_gpu / grad_data_gpu was (or is about to be) written directly */
+void bcnn_net_data32_written(bcnn_net *net, int idx);
+void bcnn_net_grad32_written(bcnn_net *net, int idx);
+/* what a node that only knows FP32 NCHW needs before / after its forward and backward */
+void bcnn_net_node_f32_before_forward(bcnn_net *net, bcnn_node *node);
+void bcnn_net_node_f32_after_forward(bcnn_net *net, bcnn_node *node);
+void bcnn_net_node_f32_before_backward(bcnn_net *net, bcnn_node *node);
+void bcnn_net_node_f32_after_backward(bcnn_net *net, bcnn_node *node);
+/* 1 when the node's own forward / backward handle the resident format */
+int bcnn_net_node_is_resident(bcnn_net *net, bcnn_node *node);
+float *bcnn_net_nhwc_scratch(bcnn_net *net, int channels);
+void bcnn_net_resident_release(bcnn_net *net);
 
 #ifdef __cplusplus
 }

@@ -27,6 +27,12 @@ bcnn_status bcnn_add_avgpool_layer(bcnn_net *net, const char *src_id, const char
 
 void bcnn_forward_avgpool_layer_gpu(bcnn_net *net, bcnn_node *node) {
     bcnn_tensor *src = &net->tensors[node->src[0]], *dst = &net->tensors[node->dst[0]];
+    if (bcnn_net_node_is_resident(net, node)) { /* BF16 NHWC in, FP32 [n, c] out */
+        bcnn_cuda_check(bcnn_b200_avgpool_forward_nhwc(bcnn_net_data16_in(net, node->src[0]), dst->data_gpu,
+                                                       src->n, src->c, src->h * src->w, bcnn_stream(net)));
+        bcnn_net_data32_written(net, node->dst[0]);
+        return;
+    }
     bcnn_cuda_check(bcnn_b200_avgpool_forward(src->data_gpu, dst->data_gpu, src->n * src->c,
                                               src->h * src->w, bcnn_stream(net)));
 }
@@ -34,6 +40,15 @@ void bcnn_forward_avgpool_layer_gpu(bcnn_net *net, bcnn_node *node) {
 void bcnn_backward_avgpool_layer_gpu(bcnn_net *net, bcnn_node *node) {
     bcnn_tensor *src = &net->tensors[node->src[0]], *dst = &net->tensors[node->dst[0]];
     if (!src->grad_data_gpu) return;
+    if (bcnn_net_node_is_resident(net, node)) {
+        const float *dy = bcnn_net_grad32_in(net, node->dst[0]);
+        const int accumulate = bcnn_net_grad_accumulate(net, node->src[0]);
+        void *dx16 = accumulate ? bcnn_net_grad16_in(net, node->src[0]) : bcnn_net_grad16_out(net, node->src[0]);
+        bcnn_cuda_check(bcnn_b200_avgpool_backward_nhwc(dx16, dy, src->n, src->c, src->h * src->w,
+                                                        accumulate, bcnn_stream(net)));
+        bcnn_net_grad16_modified(net, node->src[0]);
+        return;
+    }
     bcnn_net_grad_prepare_accumulate(net, node->src[0]); /* the kernel does += */
     bcnn_cuda_check(bcnn_b200_avgpool_backward(src->grad_data_gpu, dst->grad_data_gpu,
                                                src->n * src->c, src->h * src->w,

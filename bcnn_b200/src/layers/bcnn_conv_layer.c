@@ -76,8 +76,10 @@ bcnn_status bcnn_add_convolutional_layer(bcnn_net *net, int n, int size, int str
     BCNN_CHECK_STATUS(bcnn_net_add_dst_tensor(net, &node, batch, n, ho, wo, dst_id));
     bcnn_b200_conv_desc desc = {batch, cin, h, w, n, ho, wo, size, stride, pad, num_groups};
     param->desc = desc;
-    param->workspace_size =
-        bcnn_b200_conv_workspace_bytes(&desc, BCNN_B200_MATH_TC) / sizeof(float);
+    size_t ws_bytes = bcnn_b200_conv_workspace_bytes(&desc, BCNN_B200_MATH_TC);
+    if (bcnn_b200_conv_nhwc_workspace_bytes(&desc) > ws_bytes)
+        ws_bytes = bcnn_b200_conv_nhwc_workspace_bytes(&desc);
+    param->workspace_size = (ws_bytes + sizeof(float) - 1) / sizeof(float);
     bcnn_net_require_workspace(net, param->workspace_size * sizeof(float));
     bcnn_net_require_dy_shadow(net, bcnn_b200_conv_dy_shadow_bytes(&desc, BCNN_B200_MATH_TC));
     param->reduce_scratch_gpu =
@@ -117,9 +119,142 @@ bcnn_status bcnn_add_convolutional_layer(bcnn_net *net, int n, int size, int str
     return BCNN_SUCCESS;
 }
 
+/* Does this node run on the resident (BF16 NHWC) kernels? All of its passes must: fprop, and when
+ * the net trains, wgrad and (if the source has a gradient) dgrad; fused activations are the ones
+ * the NHWC batch-norm kernels know. Decided once per node. */
+int bcnn_conv_layer_is_resident(bcnn_net *net, bcnn_node *node) {
+    bcnn_conv_param *param = (bcnn_conv_param *)node->param;
+    if (param->resident_state == 0) {
+        const bcnn_tensor *src = &net->tensors[node->src[0]];
+        const int mask = bcnn_b200_conv_nhwc_supported(&param->desc);
+        int ok = (mask & 1) != 0;
+        if (net->mode != BCNN_MODE_PREDICT) {
+            ok = ok && (mask & 4);
+            if (src->grad_data_gpu) ok = ok && (mask & 2);
+        }
+        const bcnn_activation a = param->activation;
+        if (a == BCNN_ACT_PRELU) ok = 0;
+        if (param->batch_norm && !(a == BCNN_ACT_NONE || a == BCNN_ACT_RELU || a == BCNN_ACT_LRELU)) ok = 0;
+        param->resident_state = ok ? 1 : -1;
+    }
+    return param->resident_state > 0;
+}
+
+static int conv_reads_fp32_input(const bcnn_conv_param *param) {
+    return bcnn_b200_conv_nhwc_x_keep_bytes(&param->desc) > 0; /* thin first layer: im2col route */
+}
+
+static void conv_forward_resident(bcnn_net *net, bcnn_node *node) {
+    bcnn_conv_param *param = (bcnn_conv_param *)node->param;
+    bcnn_cuda_context *ctx = bcnn_ctx(net);
+    bcnn_tensor *t = net->tensors;
+    bcnn_tensor *dst = &t[node->dst[0]];
+    bcnn_tensor *weights = &t[node->src[1]], *biases = &t[node->src[2]];
+    void *stream = ctx->stream;
+    const size_t positions = (size_t)dst->n * dst->h * dst->w;
+    const void *x;
+    bcnn_b200_conv_shadows *sh = NULL;
+    param->shadows.x_fmt = BCNN_B200_SHADOW_NONE; /* whatever was kept mirrors an older input */
+    if (conv_reads_fp32_input(param)) {
+        x = bcnn_net_data32_in(net, node->src[0]);
+        if (net->mode == BCNN_MODE_TRAIN) { /* keep the im2col buffer for this step's wgrad */
+            sh = &param->shadows;
+            if (!sh->x) {
+                const size_t bytes = bcnn_b200_conv_nhwc_x_keep_bytes(&param->desc);
+                sh->x = bcnn_b200_malloc(bytes);
+                sh->x_bytes = sh->x ? bytes : 0;
+            }
+            sh->x_fmt = BCNN_B200_SHADOW_NONE;
+        }
+    } else {
+        x = bcnn_net_data16_in(net, node->src[0]);
+    }
+    void *y16 = bcnn_net_data16_out(net, node->dst[0]);
+    if (!param->batch_norm) {
+        bcnn_cuda_check(bcnn_b200_conv_forward_nhwc(&param->desc, x, weights->data_gpu, biases->data_gpu,
+                                                    param->activation, y16, ctx->workspace_gpu,
+                                                    ctx->workspace_bytes, sh, stream));
+        return;
+    }
+    const float *gamma = t[node->src[5]].data_gpu;
+    if (net->mode == BCNN_MODE_PREDICT) { /* statistics folded into gamma / beta at load time */
+        bcnn_cuda_check(bcnn_b200_conv_forward_nhwc(&param->desc, x, weights->data_gpu, NULL, BCNN_ACT_NONE,
+                                                    y16, ctx->workspace_gpu, ctx->workspace_bytes, sh,
+                                                    stream));
+        bcnn_cuda_check(bcnn_b200_bn_apply_nhwc(y16, y16, NULL, NULL, gamma, biases->data_gpu, positions,
+                                                dst->c, param->activation, stream));
+        return;
+    }
+    if (!param->bn_raw16_gpu) {
+        param->bn_raw16_gpu = bcnn_b200_malloc(positions * dst->c * 2);
+        if (!param->bn_raw16_gpu) bcnn_cuda_check(2 /* cudaErrorMemoryAllocation */);
+    }
+    const float *mean = t[node->src[3]].data_gpu, *var = t[node->src[4]].data_gpu; /* VALID */
+    if (net->mode == BCNN_MODE_TRAIN) {
+        bcnn_cuda_check(bcnn_b200_conv_forward_bn_stats_nhwc(
+            &param->desc, x, weights->data_gpu, param->bn_raw16_gpu, ctx->workspace_gpu,
+            ctx->workspace_bytes, sh, param->saved_mean.data_gpu, param->saved_variance.data_gpu,
+            t[node->src[3]].data_gpu, t[node->src[4]].data_gpu, bcnn_net_nhwc_scratch(net, dst->c),
+            param->reduce_scratch_gpu, stream));
+        mean = param->saved_mean.data_gpu;
+        var = param->saved_variance.data_gpu;
+    } else {
+        bcnn_cuda_check(bcnn_b200_conv_forward_nhwc(&param->desc, x, weights->data_gpu, NULL, BCNN_ACT_NONE,
+                                                    param->bn_raw16_gpu, ctx->workspace_gpu,
+                                                    ctx->workspace_bytes, sh, stream));
+    }
+    bcnn_cuda_check(bcnn_b200_bn_apply_nhwc(param->bn_raw16_gpu, y16, mean, var, gamma, biases->data_gpu,
+                                            positions, dst->c, param->activation, stream));
+}
+
+static void conv_backward_resident(bcnn_net *net, bcnn_node *node) {
+    bcnn_conv_param *param = (bcnn_conv_param *)node->param;
+    bcnn_cuda_context *ctx = bcnn_ctx(net);
+    bcnn_tensor *t = net->tensors;
+    bcnn_tensor *src = &t[node->src[0]], *dst = &t[node->dst[0]];
+    bcnn_tensor *weights = &t[node->src[1]], *biases = &t[node->src[2]];
+    void *stream = ctx->stream;
+    const size_t positions = (size_t)dst->n * dst->h * dst->w;
+    void *dy16 = bcnn_net_grad16_in(net, node->dst[0]);
+    float *scratch = bcnn_net_nhwc_scratch(net, dst->c);
+    if (param->batch_norm) {
+        const int train = net->mode == BCNN_MODE_TRAIN;
+        const float *mean = train ? param->saved_mean.data_gpu : t[node->src[3]].data_gpu;
+        const float *var = train ? param->saved_variance.data_gpu : t[node->src[4]].data_gpu;
+        bcnn_cuda_check(bcnn_b200_bn_backward_nhwc(
+            param->bn_raw16_gpu, dy16, dy16, mean, var, t[node->src[5]].data_gpu, biases->data_gpu,
+            t[node->src[5]].grad_data_gpu, biases->grad_data_gpu, param->saved_mean.grad_data_gpu,
+            param->saved_variance.grad_data_gpu, positions, dst->c, param->activation, scratch, stream));
+    } else {
+        const void *y16 = param->activation == BCNN_ACT_NONE ? NULL : bcnn_net_data16_in(net, node->dst[0]);
+        bcnn_cuda_check(bcnn_b200_actbwd_grad_bias_nhwc(biases->grad_data_gpu, dy16, y16, param->activation,
+                                                        positions, dst->c, scratch, stream));
+    }
+    bcnn_net_grad16_modified(net, node->dst[0]);
+    const void *x = conv_reads_fp32_input(param) ? (const void *)bcnn_net_data32_in(net, node->src[0])
+                                                 : (const void *)bcnn_net_data16_in(net, node->src[0]);
+    bcnn_cuda_check(bcnn_b200_conv_backward_weights_nhwc(&param->desc, x, dy16, weights->grad_data_gpu,
+                                                         ctx->workspace_gpu, ctx->workspace_bytes,
+                                                         &param->shadows, stream));
+    if (src->grad_data_gpu) {
+        int accumulate = bcnn_net_grad_accumulate(net, node->src[0]);
+        if (ctx->reference_quirks) accumulate = 0;
+        void *dx16 = accumulate ? bcnn_net_grad16_in(net, node->src[0]) : bcnn_net_grad16_out(net, node->src[0]);
+        bcnn_cuda_check(bcnn_b200_conv_backward_data_nhwc(&param->desc, weights->data_gpu, dy16, dx16,
+                                                          accumulate, ctx->workspace_gpu,
+                                                          ctx->workspace_bytes, stream));
+        bcnn_net_grad16_modified(net, node->src[0]);
+    }
+}
+
 void bcnn_forward_conv_layer_gpu(bcnn_net *net, bcnn_node *node) {
     bcnn_conv_param *param = (bcnn_conv_param *)node->param;
     bcnn_cuda_context *ctx = bcnn_ctx(net);
+    if (bcnn_net_node_is_resident(net, node)) {
+        conv_forward_resident(net, node);
+        return;
+    }
+    const int conv_math = ctx->conv_math == BCNN_B200_MATH_FP32 ? BCNN_B200_MATH_FP32 : BCNN_B200_MATH_TC;
     bcnn_tensor *t = net->tensors;
     bcnn_tensor *src = &t[node->src[0]], *dst = &t[node->dst[0]];
     bcnn_tensor *weights = &t[node->src[1]], *biases = &t[node->src[2]];
@@ -130,10 +265,10 @@ void bcnn_forward_conv_layer_gpu(bcnn_net *net, bcnn_node *node) {
     const bcnn_activation fused_act = (act == BCNN_ACT_PRELU) ? BCNN_ACT_NONE : act;
     /* TRAIN: keep the NHWC shadow of the input for this step's wgrad */
     bcnn_b200_conv_shadows *sh = NULL;
-    if (net->mode == BCNN_MODE_TRAIN && ctx->conv_math == BCNN_B200_MATH_TC) {
+    if (net->mode == BCNN_MODE_TRAIN && conv_math == BCNN_B200_MATH_TC) {
         sh = &param->shadows;
         if (!sh->x) {
-            size_t bytes = bcnn_b200_conv_x_shadow_bytes(&param->desc, ctx->conv_math);
+            size_t bytes = bcnn_b200_conv_x_shadow_bytes(&param->desc, conv_math);
             if (bytes) {
                 sh->x = bcnn_b200_malloc(bytes);
                 sh->x_bytes = sh->x ? bytes : 0; /* without storage the passes transpose again */
@@ -146,7 +281,7 @@ void bcnn_forward_conv_layer_gpu(bcnn_net *net, bcnn_node *node) {
         bcnn_cuda_check(bcnn_b200_conv_forward_sh(&param->desc, src->data_gpu, weights->data_gpu,
                                                   biases->data_gpu, fused_act, dst->data_gpu,
                                                   ctx->workspace_gpu, ctx->workspace_bytes,
-                                                  ctx->conv_math, sh, stream));
+                                                  conv_math, sh, stream));
     } else {
         float *raw = param->bn_workspace_gpu ? param->bn_workspace_gpu : dst->data_gpu;
         if (net->mode == BCNN_MODE_TRAIN) {
@@ -154,7 +289,7 @@ void bcnn_forward_conv_layer_gpu(bcnn_net *net, bcnn_node *node) {
             bcnn_tensor *run_mean = &t[node->src[3]], *run_var = &t[node->src[4]];
             bcnn_cuda_check(bcnn_b200_conv_forward_bn_stats(
                 &param->desc, src->data_gpu, weights->data_gpu, raw, ctx->workspace_gpu,
-                ctx->workspace_bytes, ctx->conv_math, sh, param->saved_mean.data_gpu,
+                ctx->workspace_bytes, conv_math, sh, param->saved_mean.data_gpu,
                 param->saved_variance.data_gpu, run_mean->data_gpu, run_var->data_gpu,
                 param->reduce_scratch_gpu, stream));
             bcnn_cuda_check(bcnn_b200_bn_apply(raw, dst->data_gpu, param->saved_mean.data_gpu,
@@ -165,7 +300,7 @@ void bcnn_forward_conv_layer_gpu(bcnn_net *net, bcnn_node *node) {
             bcnn_cuda_check(bcnn_b200_conv_forward_sh(&param->desc, src->data_gpu,
                                                       weights->data_gpu, NULL, BCNN_ACT_NONE, raw,
                                                       ctx->workspace_gpu, ctx->workspace_bytes,
-                                                      ctx->conv_math, sh, stream));
+                                                      conv_math, sh, stream));
             bcnn_b200_forward_batchnorm(net, raw, dst, &t[node->src[3]], &t[node->src[4]],
                                        &t[node->src[5]], biases, &param->saved_mean,
                                        &param->saved_variance, param->reduce_scratch_gpu,
@@ -183,6 +318,11 @@ void bcnn_forward_conv_layer_gpu(bcnn_net *net, bcnn_node *node) {
 void bcnn_backward_conv_layer_gpu(bcnn_net *net, bcnn_node *node) {
     bcnn_conv_param *param = (bcnn_conv_param *)node->param;
     bcnn_cuda_context *ctx = bcnn_ctx(net);
+    if (bcnn_net_node_is_resident(net, node)) {
+        conv_backward_resident(net, node);
+        return;
+    }
+    const int conv_math = ctx->conv_math == BCNN_B200_MATH_FP32 ? BCNN_B200_MATH_FP32 : BCNN_B200_MATH_TC;
     bcnn_tensor *t = net->tensors;
     bcnn_tensor *src = &t[node->src[0]], *dst = &t[node->dst[0]];
     bcnn_tensor *weights = &t[node->src[1]], *biases = &t[node->src[2]];
@@ -214,7 +354,7 @@ void bcnn_backward_conv_layer_gpu(bcnn_net *net, bcnn_node *node) {
     sh->dy_fmt = BCNN_B200_SHADOW_NONE;
     bcnn_cuda_check(bcnn_b200_conv_backward_weights_sh(
         &param->desc, src->data_gpu, dst->grad_data_gpu, weights->grad_data_gpu,
-        ctx->workspace_gpu, ctx->workspace_bytes, ctx->conv_math, sh, stream));
+        ctx->workspace_gpu, ctx->workspace_bytes, conv_math, sh, stream));
     if (src->grad_data_gpu) {
         /* reference semantics: overwrite. With the quirks off, a source read by several
          * nodes (residual branches) accumulates instead: the first backward writer of the
@@ -223,7 +363,7 @@ void bcnn_backward_conv_layer_gpu(bcnn_net *net, bcnn_node *node) {
         if (ctx->reference_quirks) accumulate = 0;
         bcnn_cuda_check(bcnn_b200_conv_backward_data_sh(
             &param->desc, weights->data_gpu, dst->grad_data_gpu, src->grad_data_gpu, accumulate,
-            ctx->workspace_gpu, ctx->workspace_bytes, ctx->conv_math, sh, stream));
+            ctx->workspace_gpu, ctx->workspace_bytes, conv_math, sh, stream));
     }
     sh->dy_fmt = BCNN_B200_SHADOW_NONE;
 }
@@ -249,6 +389,7 @@ void bcnn_release_param_conv_layer(bcnn_node *node) {
     bcnn_tensor_destroy(&param->saved_mean);
     bcnn_tensor_destroy(&param->saved_variance);
     bcnn_b200_free(param->bn_workspace_gpu);
+    bcnn_b200_free(param->bn_raw16_gpu);
     bcnn_b200_free(param->shadows.x);
     bcnn_b200_free(param->reduce_scratch_gpu);
     bcnn_b200_free(param->adam_m_gpu);

@@ -48,6 +48,11 @@ typedef struct bcnn_conv_param {
      * (written by forward, read by wgrad), dy points into the net-level buffer (written by
      * wgrad, read by dgrad of the same backward call) */
     bcnn_b200_conv_shadows shadows;
+    /* resident mode (BCNN_B200_MATH_TC_BF16): raw convolution result of a conv+BN node as BF16
+     * NHWC (the twin of bn_workspace_gpu), and whether this node runs on the resident kernels
+     * (0 = not decided yet, 1 = yes, -1 = no: it takes the FP32-tensor path) */
+    void *bn_raw16_gpu;
+    int resident_state;
 } bcnn_conv_param;
 
 void bcnn_forward_conv_layer(bcnn_net *net, bcnn_node *node);
@@ -55,6 +60,7 @@ void bcnn_backward_conv_layer(bcnn_net *net, bcnn_node *node);
 void bcnn_update_conv_layer(bcnn_net *net, bcnn_node *node);
 void bcnn_release_param_conv_layer(bcnn_node *node);
 void bcnn_forward_conv_layer_gpu(bcnn_net *net, bcnn_node *node);
+int bcnn_conv_layer_is_resident(bcnn_net *net, bcnn_node *node);
 void bcnn_backward_conv_layer_gpu(bcnn_net *net, bcnn_node *node);
 
 #ifdef __cplusplus

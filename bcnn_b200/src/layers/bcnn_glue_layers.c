@@ -158,6 +158,14 @@ void bcnn_forward_eltwise_layer(bcnn_net *net, bcnn_node *node) {
     bcnn_tensor *dst = &t[node->dst[0]];
     const int sz = bcnn_tensor_size(dst);
     const int n_add = bcnn_ctx(net)->reference_quirks ? param->min_dim[0] * dst->h * dst->w : sz;
+    if (bcnn_net_node_is_resident(net, node)) { /* sample 0 is the first C*H*W elements in NHWC too */
+        const void *a16 = bcnn_net_data16_in(net, node->src[0]);
+        const void *b16 = bcnn_net_data16_in(net, node->src[1]);
+        bcnn_cuda_check(bcnn_b200_eltwise_forward_bf16(a16, b16, bcnn_net_data16_out(net, node->dst[0]),
+                                                       (size_t)sz, (size_t)n_add, param->activation,
+                                                       bcnn_stream(net)));
+        return;
+    }
     bcnn_cuda_check(bcnn_b200_eltwise_forward(t[node->src[0]].data_gpu, t[node->src[1]].data_gpu,
                                               dst->data_gpu, sz, n_add, param->activation,
                                               bcnn_stream(net)));
@@ -172,6 +180,22 @@ void bcnn_backward_eltwise_layer(bcnn_net *net, bcnn_node *node) {
     int flags = 0;
     if (t[node->src[0]].grad_data_gpu && bcnn_net_grad_accumulate(net, node->src[0])) flags |= 1;
     if (t[node->src[1]].grad_data_gpu && bcnn_net_grad_accumulate(net, node->src[1])) flags |= 2;
+    if (bcnn_net_node_is_resident(net, node)) {
+        const void *y16 = param->activation == BCNN_ACT_NONE ? NULL : bcnn_net_data16_in(net, node->dst[0]);
+        void *dy16 = bcnn_net_grad16_in(net, node->dst[0]);
+        void *g16[2] = {NULL, NULL};
+        for (int i = 0; i < 2; ++i)
+            if (t[node->src[i]].grad_data_gpu)
+                g16[i] = (flags & (1 << i)) ? bcnn_net_grad16_in(net, node->src[i])
+                                            : bcnn_net_grad16_out(net, node->src[i]);
+        bcnn_cuda_check(bcnn_b200_eltwise_backward_bf16(y16 ? y16 : dy16, dy16, g16[0], g16[1], (size_t)sz,
+                                                        (size_t)n_add, param->activation, flags,
+                                                        bcnn_stream(net)));
+        bcnn_net_grad16_modified(net, node->dst[0]);
+        for (int i = 0; i < 2; ++i)
+            if (g16[i]) bcnn_net_grad16_modified(net, node->src[i]);
+        return;
+    }
     bcnn_cuda_check(bcnn_b200_eltwise_backward(
         dst->data_gpu, dst->grad_data_gpu, t[node->src[0]].grad_data_gpu,
         t[node->src[1]].grad_data_gpu, sz, n_add, param->activation, flags, bcnn_stream(net)));

@@ -60,6 +60,16 @@ bcnn_status bcnn_add_maxpool_layer(bcnn_net *net, int size, int stride, bcnn_pad
 void bcnn_forward_maxpool_layer_gpu(bcnn_net *net, bcnn_node *node) {
     bcnn_maxpool_param *param = (bcnn_maxpool_param *)node->param;
     bcnn_tensor *src = &net->tensors[node->src[0]], *dst = &net->tensors[node->dst[0]];
+    if (bcnn_net_node_is_resident(net, node)) { /* BF16 NHWC in and out; index VALUES stay NCHW-flat */
+        const void *x16 = bcnn_net_data16_in(net, node->src[0]);
+        void *y16 = bcnn_net_data16_out(net, node->dst[0]);
+        bcnn_cuda_check(bcnn_b200_maxpool_forward_nhwc(x16, y16, param->indexes_gpu, src->n, src->c,
+                                                       src->h, src->w, param->size, param->stride,
+                                                       dst->h, dst->w, bcnn_stream(net)));
+        param->indexes_nhwc = 1;
+        return;
+    }
+    param->indexes_nhwc = 0;
     bcnn_cuda_check(bcnn_b200_maxpool_forward(src->data_gpu, dst->data_gpu, param->indexes_gpu,
                                               src->n, src->c, src->h, src->w, param->size,
                                               param->stride, dst->h, dst->w, bcnn_stream(net)));
@@ -69,6 +79,16 @@ void bcnn_backward_maxpool_layer_gpu(bcnn_net *net, bcnn_node *node) {
     bcnn_maxpool_param *param = (bcnn_maxpool_param *)node->param;
     bcnn_tensor *src = &net->tensors[node->src[0]], *dst = &net->tensors[node->dst[0]];
     if (!src->grad_data_gpu) return;
+    if (bcnn_net_node_is_resident(net, node) && param->indexes_nhwc) {
+        const void *dy16 = bcnn_net_grad16_in(net, node->dst[0]);
+        const int accumulate = bcnn_net_grad_accumulate(net, node->src[0]);
+        void *dx16 = accumulate ? bcnn_net_grad16_in(net, node->src[0]) : bcnn_net_grad16_out(net, node->src[0]);
+        bcnn_cuda_check(bcnn_b200_maxpool_backward_nhwc(dx16, dy16, param->indexes_gpu, src->n, src->c,
+                                                        src->h, src->w, param->size, param->stride,
+                                                        dst->h, dst->w, accumulate, bcnn_stream(net)));
+        bcnn_net_grad16_modified(net, node->src[0]);
+        return;
+    }
     bcnn_net_grad_prepare_accumulate(net, node->src[0]); /* the kernel does += */
     bcnn_cuda_check(bcnn_b200_maxpool_backward(src->grad_data_gpu, dst->grad_data_gpu,
                                                param->indexes_gpu, src->n, src->c, src->h, src->w,
@@ -95,9 +115,21 @@ int bcnn_b200_maxpool_indexes(bcnn_net *net, int node_index, int *host_out) {
     bcnn_node *node = &net->nodes[node_index];
     if (node->type != BCNN_LAYER_MAXPOOL) return -1;
     bcnn_maxpool_param *param = (bcnn_maxpool_param *)node->param;
-    int count = bcnn_tensor_size(&net->tensors[node->dst[0]]);
+    const bcnn_tensor *dst = &net->tensors[node->dst[0]];
+    int count = bcnn_tensor_size(dst);
     bcnn_cuda_check(bcnn_b200_memcpy_d2h(host_out, param->indexes_gpu, (size_t)count * sizeof(int),
                                          bcnn_stream(net)));
     bcnn_cuda_check(bcnn_b200_stream_sync(bcnn_stream(net)));
+    if (param->indexes_nhwc) { /* hand the buffer out in the reference's NCHW order */
+        int *tmp = (int *)malloc((size_t)count * sizeof(int));
+        if (!tmp) return -1;
+        memcpy(tmp, host_out, (size_t)count * sizeof(int));
+        const int c = dst->c, hw = dst->h * dst->w;
+        for (int n = 0; n < dst->n; ++n)
+            for (int p = 0; p < hw; ++p)
+                for (int ch = 0; ch < c; ++ch)
+                    host_out[((size_t)n * c + ch) * hw + p] = tmp[((size_t)n * hw + p) * c + ch];
+        free(tmp);
+    }
     return count;
 }

@@ -18,6 +18,7 @@ typedef struct bcnn_maxpool_param {
     bcnn_padding padding;
     int *indexes;     /* host mirror, filled on demand by bcnn_b200_maxpool_indexes */
     int *indexes_gpu;
+    int indexes_nhwc; /* B200: the last forward laid indexes_gpu out like a BF16 NHWC result */
 } bcnn_maxpool_param;
 
 void bcnn_forward_maxpool_layer(bcnn_net *net, bcnn_node *node);

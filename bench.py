@@ -383,7 +383,7 @@ def run_own_arm(args):
         dist_mod.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
         dist = dist_mod
 
-    math = capi.MATH_TC if args.math == "tc" else capi.MATH_FP32
+    math = {"tc": capi.MATH_TC, "fp32": capi.MATH_FP32, "resident": capi.MATH_TC_BF16}[args.math]
     net = capi.Net(mode=capi.MODE_TRAIN)
     net.set_conv_math(math)
     net.set_reference_quirks(False)  # batch-correct residual adds
@@ -571,7 +571,7 @@ def main():
     ap.add_argument("--batch", type=int, default=256, help="per-GPU batch")
     ap.add_argument("--res", type=int, default=224)
     ap.add_argument("--math", default=os.environ.get("BCNN_B200_BENCH_MATH", "tc"),
-                    choices=["tc", "fp32"])
+                    choices=["resident", "tc", "fp32"])
     ap.add_argument("--no-rooflines", dest="rooflines", action="store_false")
     ap.add_argument("--no-cpu-baseline", dest="cpu_baseline", action="store_false")
     args = ap.parse_args()

@@ -39,7 +39,7 @@ def assert_close(a, b, tol=FP32_TOL, what=""):
     assert e_max <= tol and e_l2 <= tol, f"{what}: max-rel {e_max:.3e}, l2-rel {e_l2:.3e} > {tol}"
 
 
-def assert_close_grad(a, b, l2_tol, what="", el_tol=None, outlier_frac=1e-3):
+def assert_close_grad(a, b, l2_tol, what="", el_tol=2e-2, outlier_frac=5e-3):
     """Gradients behind (leaky-)ReLU masks: a pre-activation within rounding noise of zero changes
     sign between two correct FP32 evaluations, which multiplies that element's gradient by 1 vs the
     negative slope, and batch norm spreads the difference thinly over its channel. The max-abs
@@ -50,7 +50,6 @@ def assert_close_grad(a, b, l2_tol, what="", el_tol=None, outlier_frac=1e-3):
     assert np.all(np.isfinite(a)), f"{what}: non-finite values"
     e_max, e_l2 = rel_err(a, b)
     assert e_l2 <= l2_tol, f"{what}: l2-rel {e_l2:.3e} > {l2_tol} (max-rel {e_max:.3e})"
-    el_tol = l2_tol if el_tol is None else el_tol
     far = float(np.mean(np.abs(a - b) > el_tol * max(np.abs(b).max(initial=0.0), 1e-30)))
     assert far <= outlier_frac, f"{what}: {far:.2e} of the elements are off by more than {el_tol} of max"
 

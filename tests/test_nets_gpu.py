@@ -74,18 +74,24 @@ def test_net_matches_golden_fp32(name):
     _compare(out, golden, 2e-5, 1e-4, f"{name} fp32 vs golden")
 
 
+@pytest.mark.parametrize("math", [capi.MATH_TC, capi.MATH_TC_BF16], ids=["tc", "resident"])
 @pytest.mark.parametrize("name", ["chain_b4", "resnet_small_b4"])
-def test_net_matches_golden_tensor_core(name):
+def test_net_matches_golden_tensor_core(name, math):
     golden = dict(np.load(GOLDEN / f"{name}.npz"))
     net = capi.Net()
-    net.set_conv_math(capi.MATH_TC)
+    net.set_conv_math(math)
     out = netcases.run_case(net, name)
     net.close()
     golden = {k: v for k, v in golden.items() if "/argmax/" not in k}
     # TF32 / BF16 operands: 2^-11 .. 2^-9 per element, <= 1e-3 effective after the dot products
     # average it. Forward tensors and the loss are held to 2e-2; gradients of the ReLU nets to
     # an L2-relative 0.15 (see _compare: mask flips at batch 4)
-    _compare(out, golden, 2e-2, 5e-2, f"{name} tc vs golden", noise=1e-3, grad_l2_tol=0.15)
+    # Resident mode additionally rounds every activation and gradient tensor to BF16 (2^-9), which
+    # flips more ReLU masks: at batch 4 gradients reach 0.25 .. 0.4, i.e. this case only checks that
+    # they are sane (a missing or doubled branch contribution is >= 1). The decision-free twin at
+    # batch 64 (test_baseline_parity_gpu.py) holds the same chained arithmetic to 2e-2 in both modes.
+    _compare(out, golden, 2e-2, 5e-2, f"{name} tc vs golden", noise=1e-3 if math == capi.MATH_TC else 4e-3,
+             grad_l2_tol=0.15 if math == capi.MATH_TC else 0.6)
 
 
 @pytest.mark.skipif(not ref_available(), reason="oracle/_ref was not built / did not travel")
