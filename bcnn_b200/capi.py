@@ -141,6 +141,7 @@ def bind_b200_ext(lib: C.CDLL) -> None:
         "bcnn_b200_node_type": (i, [vp, i]),
         "bcnn_b200_node_src": (i, [vp, i, i]),
         "bcnn_b200_node_dst": (i, [vp, i, i]),
+        "bcnn_b200_tensor_dims": (i, [vp, i, C.POINTER(C.c_int)]),
         "bcnn_b200_maxpool_indexes": (i, [vp, i, vp]),
         "bcnn_b200_bn_saved_stats": (i, [vp, i, vp, vp]),
         "bcnn_b200_dp_get_unique_id": (i, [vp]),
@@ -488,6 +489,13 @@ class Net:
 
     def node_type(self, i) -> int:
         return self.lib.bcnn_b200_node_type(self.handle, i)
+
+    def tensor_shape(self, index: int) -> tuple:
+        """(n, c, h, w) of tensor `index` without a device -> host refresh of its buffers."""
+        dims = (C.c_int * 4)()
+        if self.lib.bcnn_b200_tensor_dims(self.handle, index, dims) != 0:
+            raise KeyError(index)
+        return tuple(dims)
 
     def maxpool_indexes(self, node: int) -> np.ndarray:
         dst = self.lib.bcnn_b200_node_dst(self.handle, node, 0)

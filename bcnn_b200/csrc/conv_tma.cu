@@ -396,7 +396,9 @@ constexpr int FWD_THREADS = 64 + 32 * FWD_EPI_WARPS;
 // output staging of the bulk-store epilogue: per half of the epilogue warps one chunk of 128
 // positions x 32 channels, laid out [16-channel sub-box][image][channel][position]
 constexpr int OUT_STAGE_BYTES = TILE_M * 32 * 4;
-constexpr int FWD_EXTRA_SMEM = 1024 + 256 + 2 * OUT_STAGE_BYTES;   // alignment slack, barriers, staging
+constexpr int STAT_SCRATCH_BYTES = 8 * 32 * 36 * 4;   // chunk_col_sums scratch of the 8 epilogue warps
+// alignment slack, barriers, output staging, statistics scratch
+constexpr int FWD_EXTRA_SMEM = 1024 + 256 + 2 * OUT_STAGE_BYTES + STAT_SCRATCH_BYTES;
 
 struct TileCoord { int tile_n, m_tile, img, w0, h0; };
 
@@ -445,6 +447,34 @@ __device__ __forceinline__ void store_chunk_any(const uint32_t (&v)[32], float *
                                                 const float *bias, int nvalid) {
     if (nvalid == 32) store_chunk<ACT, HAS_BIAS, ACCUM, true>(v, d, plane, bias, 32);
     else if (nvalid > 0) store_chunk<ACT, HAS_BIAS, ACCUM, false>(v, d, plane, bias, nvalid);
+}
+
+// Per-channel sum / sum of squares of one 32-column chunk of a warp's 32 accumulator rows
+// (lane = position row, v[j] = channel j): the warp writes its 32 x 32 block to its own scratch
+// (row pitch 36 floats: 16-byte aligned and conflict-free for both accesses) and every lane sums
+// one channel column. 8 vector stores + 32 loads per chunk instead of the 62 shuffles of a
+// transposing butterfly, which bound the epilogue (and with it thin-K layers) on the shuffle pipe.
+constexpr int STAT_PITCH = 36;
+constexpr int STAT_WARP_FLOATS = 32 * STAT_PITCH;
+__device__ __forceinline__ void chunk_col_sums(const uint32_t (&v)[32], bool valid, float *wscr, int lane,
+                                               float &a1, float &a2) {
+    float4 *row = reinterpret_cast<float4 *>(wscr + lane * STAT_PITCH);
+#pragma unroll
+    for (int j = 0; j < 8; ++j)
+        row[j] = valid ? make_float4(__uint_as_float(v[4 * j]), __uint_as_float(v[4 * j + 1]),
+                                     __uint_as_float(v[4 * j + 2]), __uint_as_float(v[4 * j + 3]))
+                       : make_float4(0.f, 0.f, 0.f, 0.f);
+    __syncwarp();
+    float s1[4] = {0.f, 0.f, 0.f, 0.f}, s2[4] = {0.f, 0.f, 0.f, 0.f};   // four independent chains
+#pragma unroll
+    for (int r = 0; r < 32; ++r) {
+        const float x = wscr[r * STAT_PITCH + lane];
+        s1[r & 3] += x;
+        s2[r & 3] = fmaf(x, x, s2[r & 3]);
+    }
+    __syncwarp();
+    a1 += (s1[0] + s1[1]) + (s1[2] + s1[3]);
+    a2 += (s2[0] + s2[1]) + (s2[2] + s2[3]);
 }
 
 // Persistent kernel: every CTA walks tiles blockIdx.x, +gridDim.x, ... (channel tile fastest, so
@@ -567,6 +597,8 @@ conv_tma_fwd_kernel(const __grid_constant__ CUtensorMap tm_src, const __grid_con
         // bulk-store epilogue: staging buffer of this half, position of this thread's row in it
         const int hw = ew & 3;   // warp within the half
         float *stage = reinterpret_cast<float *>(smem + (size_t)S * stage_bytes + (size_t)half * OUT_STAGE_BYTES);
+        float *wscr = reinterpret_cast<float *>(smem + (size_t)S * stage_bytes + 2 * OUT_STAGE_BYTES + 256) +
+                      (size_t)ew * STAT_WARP_FLOATS;
         const int sub_stride = p.tn * 16 * p.tile_pos;   // floats of one 16-channel sub-box
         uint32_t stores = 0;                              // bulk stores issued by this half so far
         const uint32_t plane = (uint32_t)p.dst_plane;
@@ -630,28 +662,6 @@ conv_tma_fwd_kernel(const __grid_constant__ CUtensorMap tm_src, const __grid_con
 #pragma unroll
                             for (int j = 0; j < 16; ++j)
                                 pk[sc][j] = pack_bf16x2(__uint_as_float(v[2 * j]), __uint_as_float(v[2 * j + 1]));
-                            if (p.stat_partial != nullptr) {
-                                float s1[32], s2[32];
-#pragma unroll
-                                for (int j = 0; j < 32; ++j) {
-                                    const float x = valid ? __uint_as_float(v[j]) : 0.f;
-                                    s1[j] = x;
-                                    s2[j] = x * x;
-                                }
-#pragma unroll
-                                for (int off = 16; off >= 1; off >>= 1) {
-                                    const bool hi = (lane & off) != 0;
-#pragma unroll
-                                    for (int i = 0; i < off; ++i) {
-                                        const float k1 = hi ? s1[i + off] : s1[i], g1 = hi ? s1[i] : s1[i + off];
-                                        const float k2 = hi ? s2[i + off] : s2[i], g2 = hi ? s2[i] : s2[i + off];
-                                        s1[i] = k1 + __shfl_xor_sync(0xffffffffu, g1, off);
-                                        s2[i] = k2 + __shfl_xor_sync(0xffffffffu, g2, off);
-                                    }
-                                }
-                                acc1[gj * 2 + sc] += s1[0];
-                                acc2[gj * 2 + sc] += s2[0];
-                            }
                         } else {
 #pragma unroll
                             for (int j = 0; j < 16; ++j) pk[sc][j] = 0u;
@@ -678,7 +688,29 @@ conv_tma_fwd_kernel(const __grid_constant__ CUtensorMap tm_src, const __grid_con
                             else tma_store_4d(&tm_dst, smem_u32(sb), ch0, c.w0, c.h0, c.img);
                             bulk_commit_group();
                         }
-                    } else if (valid) {
+                        // batch-norm statistics of this group while its bulk store drains. (Summing the
+                        // staged BF16 tile instead was measured slower: 0.237 vs 0.191 ms on 1x1 64->256
+                        // @56, gpurun r2j.)
+                        if (p.stat_partial != nullptr) {   // the accumulators are read again: cheaper than
+#pragma unroll                                                // keeping 64 registers alive across the store
+                            for (int sc = 0; sc < 2; ++sc)
+                                if (2 * gi + sc < chunks32) {
+                                    uint32_t v[32];
+                                    tmem_ld32(d_tmem + (uint32_t)((2 * gi + sc) * 32), v);
+                                    chunk_col_sums(v, valid, wscr, lane, acc1[gj * 2 + sc], acc2[gj * 2 + sc]);
+                                }
+                        }
+                    } else {
+                        if (p.stat_partial != nullptr) {   // the accumulators are read again: cheaper than
+#pragma unroll                                                // keeping 64 registers alive across the store
+                            for (int sc = 0; sc < 2; ++sc)
+                                if (2 * gi + sc < chunks32) {
+                                    uint32_t v[32];
+                                    tmem_ld32(d_tmem + (uint32_t)((2 * gi + sc) * 32), v);
+                                    chunk_col_sums(v, valid, wscr, lane, acc1[gj * 2 + sc], acc2[gj * 2 + sc]);
+                                }
+                        }
+                        if (valid)
 #pragma unroll
                         for (int k8 = 0; k8 < 8; ++k8) {
                             if (ch0 + k8 * 8 < p.dst_c && gi * 64 + k8 * 8 < n_tile) {
@@ -750,31 +782,7 @@ conv_tma_fwd_kernel(const __grid_constant__ CUtensorMap tm_src, const __grid_con
                                 ++stores;
                             }
                         }
-                        if (p.stat_partial != nullptr) {
-                            // Per-channel sum / sum of squares over this warp's 32 positions: a
-                            // transposing butterfly (31 shuffles per quantity) leaves channel
-                            // ch0 + lane in lane `lane`; it runs while the bulk store drains.
-                            float s1[32], s2[32];
-#pragma unroll
-                            for (int j = 0; j < 32; ++j) {
-                                const float x = valid ? __uint_as_float(v[j]) : 0.f;
-                                s1[j] = x;
-                                s2[j] = x * x;
-                            }
-#pragma unroll
-                            for (int off = 16; off >= 1; off >>= 1) {
-                                const bool hi = (lane & off) != 0;
-#pragma unroll
-                                for (int i = 0; i < off; ++i) {
-                                    const float k1 = hi ? s1[i + off] : s1[i], g1 = hi ? s1[i] : s1[i + off];
-                                    const float k2 = hi ? s2[i + off] : s2[i], g2 = hi ? s2[i] : s2[i + off];
-                                    s1[i] = k1 + __shfl_xor_sync(0xffffffffu, g1, off);
-                                    s2[i] = k2 + __shfl_xor_sync(0xffffffffu, g2, off);
-                                }
-                            }
-                            acc1[ci] += s1[0];
-                            acc2[ci] += s2[0];
-                        }
+                        if (p.stat_partial != nullptr) chunk_col_sums(v, valid, wscr, lane, acc1[ci], acc2[ci]);
                     }
                 }
             } else
@@ -1840,8 +1848,76 @@ im2col_nhwc_kernel(const float *__restrict__ x, void *__restrict__ col, int cin,
     }
 }
 
+// BF16 flavour through shared memory: one CTA per (image, output row). The ks input rows of every
+// channel are staged once (coalesced, zero-filled outside the image, with the left / right padding
+// columns materialised), then every thread assembles 16-byte chunks of the row's col entries from
+// them: no divisions and no scattered global loads in the inner loop (the gather kernel above spends
+// 0.76 ms on ResNet-50's stem at batch 256, 4x the time its bytes need).
+// smem: rows[cin * ks][wp] floats (wp = w + 2 * pad), then the k -> row / column offset table.
+__global__ void __launch_bounds__(256)
+im2col_rows_bf16_kernel(const float *__restrict__ x, uint4 *__restrict__ col, int cin, int h, int w, int ks,
+                        int stride, int pad, int kdim, int kp8, int ho, int wo) {
+    extern __shared__ float sm[];
+    const int wp = w + 2 * pad;
+    const int nrows = cin * ks;
+    float *rows = sm;
+    // k = 8 q + e -> (ci * ks + kh) * wp + kw, stored [e][q] so that a warp's lanes (consecutive q) hit
+    // consecutive banks
+    int *koff = reinterpret_cast<int *>(sm + (size_t)nrows * wp);
+    const int oh = blockIdx.x % ho, n = blockIdx.x / ho;
+    const int t = threadIdx.x;
+    for (int k = t; k < kp8 * 8; k += 256) {
+        int off = -1;
+        if (k < kdim) {
+            const int ci = k / (ks * ks), r = k - ci * ks * ks, kh = r / ks, kw = r - kh * ks;
+            off = (ci * ks + kh) * wp + kw;
+        }
+        koff[(k & 7) * kp8 + (k >> 3)] = off;
+    }
+    const int ih0 = oh * stride - pad;
+    for (int i = t; i < nrows * wp; i += 256) {
+        const int r = i / wp, cpos = i - r * wp;
+        const int ci = r / ks, kh = r - ci * ks;
+        const int ih = ih0 + kh, iw = cpos - pad;
+        float v = 0.f;
+        if (ih >= 0 && ih < h && iw >= 0 && iw < w) v = __ldg(x + (((size_t)n * cin + ci) * h + ih) * w + iw);
+        rows[i] = v;
+    }
+    __syncthreads();
+    uint4 *out = col + ((size_t)n * ho + oh) * wo * kp8;
+    const int chunks = wo * kp8;
+    for (int i = t; i < chunks; i += 256) {
+        const int ow = i / kp8, q = i - ow * kp8;
+        const int base = ow * stride;
+        float v[8];
+#pragma unroll
+        for (int e = 0; e < 8; ++e) {
+            const int off = koff[e * kp8 + q];
+            v[e] = off >= 0 ? rows[off + base] : 0.f;
+        }
+        out[i] = make_uint4(pack_bf16x2(v[0], v[1]), pack_bf16x2(v[2], v[3]), pack_bf16x2(v[4], v[5]),
+                            pack_bf16x2(v[6], v[7]));
+    }
+}
+
 int launch_im2col(const bcnn_b200_conv_desc *d, const float *x, void *col, bool bf16, cudaStream_t st) {
     const int kk = d->ksize * d->ksize, kp = im2col_kp(d);
+    if (bf16 && !env_off("BCNN_B200_NO_FAST_IM2COL")) {
+        const size_t smem = ((size_t)d->cin * d->ksize * (d->w + 2 * d->pad) + kp) * sizeof(float);
+        if (smem <= 96 * 1024 && (long long)d->batch * d->ho < (1LL << 31)) {
+            static bool attr_set = false;
+            if (!attr_set) {
+                cudaError_t e = cudaFuncSetAttribute(im2col_rows_bf16_kernel,
+                                                     cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024);
+                if (e != cudaSuccess) return (int)e;
+                attr_set = true;
+            }
+            im2col_rows_bf16_kernel<<<d->batch * d->ho, 256, smem, st>>>(
+                x, reinterpret_cast<uint4 *>(col), d->cin, d->h, d->w, d->ksize, d->stride, d->pad, d->cin * kk,
+                kp / 8, d->ho, d->wo);
+            return launched();
+        }
+    }
     const int ept = bf16 ? 8 : 4;
     const size_t total4 = (size_t)d->batch * d->ho * d->wo * (kp / ept);
     if (total4 >= (1ull << 31)) return (int)cudaErrorInvalidValue;

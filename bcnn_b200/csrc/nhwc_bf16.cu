@@ -260,32 +260,53 @@ reduce_nhwc_kernel(const __nv_bfloat16 *__restrict__ x, __nv_bfloat16 *dy,
     }
 }
 
-// Batch-norm backward, per channel: fold the block partials in block order, then
+// Fold the per-block partial rows of a reduction: block = 32 channels x 32 row lanes, lane ty sums
+// rows ty, ty + 32, ... (coalesced over channels), shared memory folds the 32 lanes in lane order.
+// Deterministic: the order depends only on the row count.
+__device__ __forceinline__ void fold_partials(const float *__restrict__ partial, int blocks, int C, int ch,
+                                              float &s1, float &s2, float (*red)[32][33]) {
+    const int tx = threadIdx.x, ty = threadIdx.y;
+    float a = 0.f, b = 0.f;
+    if (ch < C)
+        for (int r = ty; r < blocks; r += 32) {
+            a += __ldcs(partial + ((size_t)r * 2 + 0) * C + ch);
+            b += __ldcs(partial + ((size_t)r * 2 + 1) * C + ch);
+        }
+    red[0][ty][tx] = a;
+    red[1][ty][tx] = b;
+    __syncthreads();
+    s1 = s2 = 0.f;
+    if (ty == 0) {
+#pragma unroll
+        for (int l = 0; l < 32; ++l) { s1 += red[0][l][tx]; s2 += red[1][l][tx]; }
+    }
+}
+
+// Batch-norm backward, per channel: fold the block partials, then
 //   g_beta += S1;  g_gamma += S2 / sqrt(var + 1e-6)                    (bcnn_grad_bias / _scales)
 //   d_mean = gamma S1 (-1 / sqrt(var + 1e-5));  d_var = gamma S2 (-0.5 / (var sqrt(var) + 1e-5))
-__global__ void __launch_bounds__(128)
+__global__ void __launch_bounds__(1024)
 bn_bwd_finalize_nhwc_kernel(const float *__restrict__ partial, int blocks, int C,
                             const float *__restrict__ var, const float *__restrict__ gamma,
                             float *g_gamma, float *g_beta, float *d_mean, float *d_var) {
-    const int ch = blockIdx.x * 128 + threadIdx.x;
-    if (ch >= C) return;
-    float s1 = 0.f, s2 = 0.f;
-    for (int r = 0; r < blocks; ++r) {
-        s1 += __ldcs(partial + ((size_t)r * 2 + 0) * C + ch);
-        s2 += __ldcs(partial + ((size_t)r * 2 + 1) * C + ch);
-    }
+    __shared__ float red[2][32][33];
+    const int ch = blockIdx.x * 32 + threadIdx.x;
+    float s1, s2;
+    fold_partials(partial, blocks, C, ch, s1, s2, red);
+    if (threadIdx.y != 0 || ch >= C) return;
     const float v = var[ch], g = gamma[ch];
     if (g_beta) g_beta[ch] += s1;
     if (g_gamma) g_gamma[ch] += s2 / sqrtf(v + 0.000001f);
     d_mean[ch] = (g * s1) * (-1.0f / sqrtf(v + 0.00001f));
     d_var[ch] = (g * s2) * (-0.5f / (v * sqrtf(v) + 0.00001f));
 }
-__global__ void __launch_bounds__(128)
+__global__ void __launch_bounds__(1024)
 bias_bwd_finalize_nhwc_kernel(const float *__restrict__ partial, int blocks, int C, float *g_bias) {
-    const int ch = blockIdx.x * 128 + threadIdx.x;
-    if (ch >= C) return;
-    float s1 = 0.f;
-    for (int r = 0; r < blocks; ++r) s1 += __ldcs(partial + ((size_t)r * 2) * C + ch);
+    __shared__ float red[2][32][33];
+    const int ch = blockIdx.x * 32 + threadIdx.x;
+    float s1, s2;
+    fold_partials(partial, blocks, C, ch, s1, s2, red);
+    if (threadIdx.y != 0 || ch >= C) return;
     g_bias[ch] += s1;
 }
 
@@ -418,6 +439,8 @@ eltwise_bwd_bf16_kernel(const __nv_bfloat16 *__restrict__ y, __nv_bfloat16 *dy, 
 // column) scan order from -FLT_MAX, so the first maximum wins; idx = flat NCHW index of the
 // winner, -1 when nothing beat -FLT_MAX (bcnn_maxpool_layer.c:145-191). The index BUFFER is laid
 // out like y (NHWC); its VALUES are NCHW-flat, as the reference's.
+// KT: compile-time window size (2, 3) so that every tap is loaded before the first compare; 0 = any
+template <int KT>
 __global__ void __launch_bounds__(256)
 maxpool_fwd_nhwc_kernel(const __nv_bfloat16 *__restrict__ x, __nv_bfloat16 *__restrict__ y,
                         int *__restrict__ idx, int N, int C, int H, int W, int k, int s, int Ho, int Wo,
@@ -433,6 +456,26 @@ maxpool_fwd_nhwc_kernel(const __nv_bfloat16 *__restrict__ x, __nv_bfloat16 *__re
         int arg[8];
 #pragma unroll
         for (int j = 0; j < 8; ++j) { best[j] = -FLT_MAX; arg[j] = -1; }
+        if (KT > 0) {
+            uint4 v[KT > 0 ? KT * KT : 1];
+#pragma unroll
+            for (int t = 0; t < KT * KT; ++t) {
+                const int ih = oh * s + t / KT, iw = ow * s + t % KT;
+                if (ih < H && iw < W) v[t] = ld_stream_u4(x + (((size_t)n * H + ih) * W + iw) * C + g * 8);
+            }
+#pragma unroll
+            for (int t = 0; t < KT * KT; ++t) {
+                const int ih = oh * s + t / KT, iw = ow * s + t % KT;
+                if (ih < H && iw < W) {
+                    float f[8];
+                    unpack8(v[t], f);
+                    const int base = ((n * C + g * 8) * H + ih) * W + iw;   // channel j adds j * H * W
+#pragma unroll
+                    for (int j = 0; j < 8; ++j)
+                        if (f[j] > best[j]) { best[j] = f[j]; arg[j] = base + j * H * W; }
+                }
+            }
+        } else
         for (int kh = 0; kh < k; ++kh) {
             const int ih = oh * s + kh;
             if (ih >= H) break;
@@ -476,6 +519,34 @@ maxpool_bwd_nhwc_kernel(__nv_bfloat16 *dx, const __nv_bfloat16 *__restrict__ dy,
         int oh0 = ih - k + 1; oh0 = oh0 > 0 ? (oh0 + s - 1) / s : 0;
         int ow0 = iw - k + 1; ow0 = ow0 > 0 ? (ow0 + s - 1) / s : 0;
         const int oh1 = min(ih / s, Ho - 1), ow1 = min(iw / s, Wo - 1);
+        if (k <= 2 * s) {
+            // an element sits in at most 2 x 2 windows: issue every load before the first use
+            int4 i0[4], i1[4];
+            uint4 dv[4];
+            bool live[4];
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                const int oh = oh0 + (q >> 1), ow = ow0 + (q & 1);
+                live[q] = oh <= oh1 && ow <= ow1;
+                if (live[q]) {
+                    const size_t o = ((((size_t)n * Ho + oh) * Wo + ow) * C + g * 8);
+                    i0[q] = __ldg(reinterpret_cast<const int4 *>(idx + o));
+                    i1[q] = __ldg(reinterpret_cast<const int4 *>(idx + o) + 1);
+                    dv[q] = ld_stream_u4(dy + o);
+                }
+            }
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                if (live[q]) {
+                    float f[8];
+                    unpack8(dv[q], f);
+                    const int id[8] = {i0[q].x, i0[q].y, i0[q].z, i0[q].w, i1[q].x, i1[q].y, i1[q].z, i1[q].w};
+#pragma unroll
+                    for (int j = 0; j < 8; ++j)
+                        if (id[j] == base + j * H * W) acc[j] += f[j];
+                }
+            }
+        } else
         for (int oh = oh0; oh <= oh1; ++oh)
             for (int ow = ow0; ow <= ow1; ++ow) {
                 const size_t o = ((((size_t)n * Ho + oh) * Wo + ow) * C + g * 8);
@@ -635,8 +706,8 @@ extern "C" int bcnn_b200_bn_backward_nhwc(const void *x, void *dy, void *dx, con
                                                                  positions, c, r.cgb, r.lanes, scratch);
     int err = launched();
     if (err) return err;
-    bn_bwd_finalize_nhwc_kernel<<<ceil_div(c, 128), 128, 0, st>>>(scratch, r.gx, c, var, gamma, g_gamma,
-                                                                   g_beta, d_mean, d_var);
+    bn_bwd_finalize_nhwc_kernel<<<ceil_div(c, 32), dim3(32, 32), 0, st>>>(scratch, r.gx, c, var, gamma, g_gamma,
+                                                                            g_beta, d_mean, d_var);
     err = launched();
     if (err) return err;
     const int cg = c / 8;
@@ -660,7 +731,7 @@ extern "C" int bcnn_b200_actbwd_grad_bias_nhwc(float *g_bias, void *dy, const vo
                                                                  positions, c, r.cgb, r.lanes, scratch);
     int err = launched();
     if (err) return err;
-    bias_bwd_finalize_nhwc_kernel<<<ceil_div(c, 128), 128, 0, st>>>(scratch, r.gx, c, g_bias);
+    bias_bwd_finalize_nhwc_kernel<<<ceil_div(c, 32), dim3(32, 32), 0, st>>>(scratch, r.gx, c, g_bias);
     return launched();
 }
 
@@ -689,9 +760,16 @@ extern "C" int bcnn_b200_maxpool_forward_nhwc(const void *x, void *y, int *index
     const size_t vectors = (size_t)n * ho * wo * (c / 8);
     if (vectors == 0) return 0;
     if (c % 8 || (size_t)n * c * h * w >= (1ull << 31)) return (int)cudaErrorInvalidValue;
-    maxpool_fwd_nhwc_kernel<<<stream_grid(vectors, 256), 256, 0, as_stream(stream)>>>(
-        reinterpret_cast<const __nv_bfloat16 *>(x), reinterpret_cast<__nv_bfloat16 *>(y), indexes, n, c, h, w,
-        ksize, stride, ho, wo, vectors, c / 8);
+    const int grid = stream_grid(vectors, 256);
+    const __nv_bfloat16 *xb = reinterpret_cast<const __nv_bfloat16 *>(x);
+    __nv_bfloat16 *yb = reinterpret_cast<__nv_bfloat16 *>(y);
+    cudaStream_t st = as_stream(stream);
+    if (ksize == 2)
+        maxpool_fwd_nhwc_kernel<2><<<grid, 256, 0, st>>>(xb, yb, indexes, n, c, h, w, ksize, stride, ho, wo, vectors, c / 8);
+    else if (ksize == 3)
+        maxpool_fwd_nhwc_kernel<3><<<grid, 256, 0, st>>>(xb, yb, indexes, n, c, h, w, ksize, stride, ho, wo, vectors, c / 8);
+    else
+        maxpool_fwd_nhwc_kernel<0><<<grid, 256, 0, st>>>(xb, yb, indexes, n, c, h, w, ksize, stride, ho, wo, vectors, c / 8);
     return launched();
 }
 extern "C" int bcnn_b200_maxpool_backward_nhwc(void *dx, const void *dy, const int *indexes, int n, int c,

@@ -744,3 +744,9 @@ int bcnn_b200_node_dst(bcnn_net *net, int node, int i) {
     if (node < 0 || node >= net->num_nodes || i < 0 || i >= net->nodes[node].num_dst) return -1;
     return net->nodes[node].dst[i];
 }
+int bcnn_b200_tensor_dims(bcnn_net *net, int index, int *dims) {
+    if (index < 0 || index >= net->num_tensors || !dims) return -1;
+    const bcnn_tensor *t = &net->tensors[index];
+    dims[0] = t->n; dims[1] = t->c; dims[2] = t->h; dims[3] = t->w;
+    return 0;
+}

@@ -103,6 +103,9 @@ BCNN_B200_API int bcnn_b200_num_tensors(bcnn_net *net);
 BCNN_B200_API int bcnn_b200_node_type(bcnn_net *net, int node);
 BCNN_B200_API int bcnn_b200_node_src(bcnn_net *net, int node, int i); /* -1 if out of range */
 BCNN_B200_API int bcnn_b200_node_dst(bcnn_net *net, int node, int i);
+/* dims[4] = {n, c, h, w} of tensor `index` without touching its buffers (bcnn_get_tensor_by_index
+ * refreshes the host copies, a full device -> host transfer). Returns 0, or -1 for a bad index. */
+BCNN_B200_API int bcnn_b200_tensor_dims(bcnn_net *net, int index, int *dims);
 /* Copies the max-pool argmax of node `node` (param->indexes_gpu) into host_out
  * (count = size of the node's dst tensor). Returns the count or -1. */
 BCNN_B200_API int bcnn_b200_maxpool_indexes(bcnn_net *net, int node, int *host_out);

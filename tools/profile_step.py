@@ -10,10 +10,10 @@ from bcnn_b200 import capi, configs
 workload = sys.argv[1] if len(sys.argv) > 1 else "resnet50"
 batch = int(sys.argv[2]) if len(sys.argv) > 2 else 64
 steps = int(sys.argv[3]) if len(sys.argv) > 3 else 2
-math = sys.argv[4] if len(sys.argv) > 4 else "tc"
+math = sys.argv[4] if len(sys.argv) > 4 else "resident"
 lib = capi.b200()
 net = capi.Net(mode=capi.MODE_TRAIN)
-net.set_conv_math(capi.MATH_TC if math == "tc" else capi.MATH_FP32)
+net.set_conv_math({"tc": capi.MATH_TC, "fp32": capi.MATH_FP32, "resident": capi.MATH_TC_BF16}[math])
 net.set_reference_quirks(False)
 if workload in ("mnist", "cifar"):
     configs.BUILDERS[workload](net, batch=batch)
