@@ -601,6 +601,7 @@ def bind_kernel_abi(lib: C.CDLL) -> None:
         "bcnn_b200_avgpool_forward_nhwc": (i, [vp, vp, i, i, i, vp]),
         "bcnn_b200_avgpool_backward_nhwc": (i, [vp, vp, i, i, i, i, vp]),
         "bcnn_b200_bn_stats_nhwc": (i, [vp, sz, i, vp, vp, vp, vp, vp, vp, vp]),
+        "bcnn_b200_bn_add_act_nhwc": (i, [vp] * 11 + [sz, i, i, vp]),
         # convolution on resident BF16 NHWC tensors (csrc/conv_tma.cu)
         "bcnn_b200_conv_nhwc_supported": (i, [dp]),
         "bcnn_b200_conv_nhwc_workspace_bytes": (sz, [dp]),

@@ -361,6 +361,61 @@ bn_bwd_apply_nhwc_kernel(const __nv_bfloat16 *__restrict__ x, const __nv_bfloat1
     }
 }
 
+// ------------------------------------------------------------------ batch norm + residual add
+// y = act(bn_a(xa) + bn_b(xb)) in one pass: the block's last convolution (and its projection
+// shortcut) never materialise their normalised outputs. Per operand: KIND 0 plain tensor, 1 batch
+// norm (a = gamma / sqrt(var + 1e-6), b = beta - mean a), 2 folded scale / shift (PREDICT).
+struct BnOperand { const __nv_bfloat16 *x; const float *mean, *var, *gamma, *beta; int kind; };
+__device__ __forceinline__ void bn_coeffs(const BnOperand &o, int ch0, float (&a)[8], float (&b)[8]) {
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+        if (o.kind == 0) { a[j] = 1.f; b[j] = 0.f; continue; }
+        const float g = __ldg(o.gamma + ch0 + j), be = __ldg(o.beta + ch0 + j);
+        if (o.kind == 1) {
+            a[j] = g / sqrtf(__ldg(o.var + ch0 + j) + 0.000001f);
+            b[j] = be - __ldg(o.mean + ch0 + j) * a[j];
+        } else {
+            a[j] = g; b[j] = be;
+        }
+    }
+}
+__global__ void __launch_bounds__(256)
+bn_add_act_nhwc_kernel(const BnOperand oa, const BnOperand ob, __nv_bfloat16 *__restrict__ y, size_t vectors,
+                       int cg, int act) {
+    const size_t stride = (size_t)gridDim.x * 256;
+    const size_t first = (size_t)blockIdx.x * 256 + threadIdx.x;
+    const int ch0 = (int)(first % (size_t)cg) * 8;
+    float aa[8], ab[8], ba[8], bb[8];
+    bn_coeffs(oa, ch0, aa, ab);
+    bn_coeffs(ob, ch0, ba, bb);
+    constexpr int UNROLL = 4;
+    for (size_t i0 = first; i0 < vectors; i0 += stride * UNROLL) {
+        uint4 va[UNROLL], vb[UNROLL];
+#pragma unroll
+        for (int u = 0; u < UNROLL; ++u) {
+            const size_t i = i0 + u * stride;
+            if (i < vectors) { va[u] = ld_stream_u4(oa.x + i * 8); vb[u] = ld_stream_u4(ob.x + i * 8); }
+        }
+#pragma unroll
+        for (int u = 0; u < UNROLL; ++u) {
+            const size_t i = i0 + u * stride;
+            if (i < vectors) {
+                float fa[8], fb[8];
+                unpack8(va[u], fa);
+                unpack8(vb[u], fb);
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                    // each branch rounded to BF16 like the tensor the unfused path would have stored
+                    const float ta = oa.kind ? __uint_as_float(pack2(fmaf(fa[j], aa[j], ab[j]), 0.f) << 16) : fa[j];
+                    const float tb = ob.kind ? __uint_as_float(pack2(fmaf(fb[j], ba[j], bb[j]), 0.f) << 16) : fb[j];
+                    fa[j] = apply_act(ta + tb, act);
+                }
+                st_u4(y + i * 8, pack8(fa));
+            }
+        }
+    }
+}
+
 // ------------------------------------------------------------------ residual add
 __global__ void __launch_bounds__(256)
 eltwise_fwd_bf16_kernel(const __nv_bfloat16 *__restrict__ a, const __nv_bfloat16 *__restrict__ b,
@@ -732,6 +787,24 @@ extern "C" int bcnn_b200_actbwd_grad_bias_nhwc(float *g_bias, void *dy, const vo
     int err = launched();
     if (err) return err;
     bias_bwd_finalize_nhwc_kernel<<<ceil_div(c, 32), dim3(32, 32), 0, st>>>(scratch, r.gx, c, g_bias);
+    return launched();
+}
+
+extern "C" int bcnn_b200_bn_add_act_nhwc(const void *xa, const float *mean_a, const float *var_a,
+                                         const float *gamma_a, const float *beta_a, const void *xb,
+                                         const float *mean_b, const float *var_b, const float *gamma_b,
+                                         const float *beta_b, void *y, size_t positions, int c, int act,
+                                         void *stream) {
+    if (positions == 0 || c == 0) return 0;
+    if (c % 8) return (int)cudaErrorInvalidValue;
+    BnOperand oa{reinterpret_cast<const __nv_bfloat16 *>(xa), mean_a, var_a, gamma_a, beta_a,
+                 gamma_a ? (mean_a ? 1 : 2) : 0};
+    BnOperand ob{reinterpret_cast<const __nv_bfloat16 *>(xb), mean_b, var_b, gamma_b, beta_b,
+                 gamma_b ? (mean_b ? 1 : 2) : 0};
+    const int cg = c / 8;
+    const size_t vectors = positions * cg;
+    bn_add_act_nhwc_kernel<<<fixed_group_grid(vectors, cg, 256, 4), 256, 0, as_stream(stream)>>>(
+        oa, ob, reinterpret_cast<__nv_bfloat16 *>(y), vectors, cg, act);
     return launched();
 }
 

@@ -90,10 +90,22 @@ typedef struct bcnn_cuda_context {
 } bcnn_cuda_context;
 
 /* Where the current value of a tensor's data / gradient lives. */
-enum { BCNN_RES_F32 = 0, BCNN_RES_BF16 = 1, BCNN_RES_BOTH = 2 };
+enum {
+    BCNN_RES_F32 = 0,
+    BCNN_RES_BF16 = 1,
+    BCNN_RES_BOTH = 2,
+    /* data only: the tensor is the not-yet-applied batch norm of its producer's raw convolution
+     * result (the residual add that consumes it applies the normalisation itself); anybody else
+     * who asks for it gets it materialised first (bcnn_conv_layer_materialize) */
+    BCNN_RES_DEFERRED = 3
+};
 typedef struct bcnn_resident {
     void *data16, *grad16;
     unsigned char data_at, grad_at; /* BCNN_RES_* */
+    int producer;   /* BCNN_RES_DEFERRED: index of the producing node */
+    /* backward: this tensor's incoming gradient was not written; it is the (masked) gradient of
+     * tensor grad_alias - 1, left there by the residual add that consumes this tensor. 0 = none. */
+    int grad_alias;
 } bcnn_resident;
 
 struct bcnn_net {
@@ -179,6 +191,11 @@ void bcnn_net_node_f32_after_backward(bcnn_net *net, bcnn_node *node);
 /* 1 when the node's own forward / backward handle the resident format */
 int bcnn_net_node_is_resident(bcnn_net *net, bcnn_node *node);
 float *bcnn_net_nhwc_scratch(bcnn_net *net, int channels);
+/* The resident residual-add node `consumer` is the only reader of tensor idx (1), so the batch norm
+ * of the convolution producing idx may be applied inside that add and idx's gradient read from the
+ * add's output gradient; 0 otherwise. *consumer_out receives the node index. */
+int bcnn_net_sole_eltwise_consumer(bcnn_net *net, int idx, int *consumer_out);
+bcnn_resident *bcnn_net_res(bcnn_net *net, int idx);
 void bcnn_net_resident_release(bcnn_net *net);
 
 #ifdef __cplusplus

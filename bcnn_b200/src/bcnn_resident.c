@@ -43,6 +43,32 @@ static bcnn_resident *res_of(bcnn_net *net, int idx) {
     return &ctx->res[idx];
 }
 
+bcnn_resident *bcnn_net_res(bcnn_net *net, int idx) { return res_of(net, idx); }
+
+int bcnn_net_sole_eltwise_consumer(bcnn_net *net, int idx, int *consumer_out) {
+    bcnn_cuda_context *ctx = bcnn_ctx(net);
+    if (!bcnn_net_resident(net) || ctx->reference_quirks) return 0;
+    int found = -1;
+    for (int i = 0; i < net->num_nodes; ++i) {
+        const bcnn_node *node = &net->nodes[i];
+        for (int j = 0; j < node->num_src; ++j) {
+            if (node->src[j] != idx) continue;
+            if (found >= 0 || node->type != BCNN_LAYER_ELTWISE || j > 1) return 0;
+            found = i;
+        }
+    }
+    if (found < 0 || !bcnn_net_tensor_can16(net, net->nodes[found].dst[0])) return 0;
+    if (net->nodes[found].src[0] == net->nodes[found].src[1]) return 0;
+    if (consumer_out) *consumer_out = found;
+    return 1;
+}
+
+static void materialize_deferred(bcnn_net *net, int idx) {
+    bcnn_resident *r = res_of(net, idx);
+    if (r->data_at != BCNN_RES_DEFERRED) return;
+    bcnn_conv_layer_materialize(net, &net->nodes[r->producer]); /* leaves data_at = BCNN_RES_BF16 */
+}
+
 int bcnn_net_tensor_can16(bcnn_net *net, int idx) {
     const bcnn_tensor *t = &net->tensors[idx];
     return t->c % 8 == 0 && bcnn_tensor_size(t) > 0 && t->data_gpu != NULL;
@@ -68,6 +94,7 @@ static void to32(bcnn_net *net, const void *src, float *dst, const bcnn_tensor *
 }
 
 void *bcnn_net_data16_in(bcnn_net *net, int idx) {
+    materialize_deferred(net, idx);
     bcnn_resident *r = res_of(net, idx);
     void *p = twin(net, &r->data16, idx);
     if (r->data_at == BCNN_RES_F32) {
@@ -104,6 +131,7 @@ void bcnn_net_grad16_modified(bcnn_net *net, int idx) { res_of(net, idx)->grad_a
 float *bcnn_net_data32_in(bcnn_net *net, int idx) {
     bcnn_tensor *t = &net->tensors[idx];
     if (idx < bcnn_ctx(net)->res_count) {
+        materialize_deferred(net, idx);
         bcnn_resident *r = &bcnn_ctx(net)->res[idx];
         if (r->data_at == BCNN_RES_BF16 && t->data_gpu) {
             to32(net, r->data16, t->data_gpu, t);

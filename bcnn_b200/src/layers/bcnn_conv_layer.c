@@ -144,6 +144,59 @@ static int conv_reads_fp32_input(const bcnn_conv_param *param) {
     return bcnn_b200_conv_nhwc_x_keep_bytes(&param->desc) > 0; /* thin first layer: im2col route */
 }
 
+void bcnn_conv_layer_bn_operand(bcnn_net *net, bcnn_node *node, const void **raw, const float **mean,
+                                const float **var, const float **gamma, const float **beta) {
+    bcnn_conv_param *param = (bcnn_conv_param *)node->param;
+    bcnn_tensor *t = net->tensors;
+    *raw = param->bn_raw16_gpu;
+    *gamma = t[node->src[5]].data_gpu;
+    *beta = t[node->src[2]].data_gpu;
+    if (net->mode == BCNN_MODE_TRAIN) {
+        *mean = param->saved_mean.data_gpu;
+        *var = param->saved_variance.data_gpu;
+    } else if (net->mode == BCNN_MODE_PREDICT) { /* folded at load time */
+        *mean = *var = NULL;
+    } else {
+        *mean = t[node->src[3]].data_gpu;
+        *var = t[node->src[4]].data_gpu;
+    }
+}
+
+void bcnn_conv_layer_materialize(bcnn_net *net, bcnn_node *node) {
+    bcnn_conv_param *param = (bcnn_conv_param *)node->param;
+    bcnn_tensor *dst = &net->tensors[node->dst[0]];
+    const void *raw;
+    const float *mean, *var, *gamma, *beta;
+    bcnn_conv_layer_bn_operand(net, node, &raw, &mean, &var, &gamma, &beta);
+    void *y16 = bcnn_net_data16_out(net, node->dst[0]); /* state: BF16 current */
+    bcnn_cuda_check(bcnn_b200_bn_apply_nhwc(raw, y16, mean, var, gamma, beta,
+                                            (size_t)dst->n * dst->h * dst->w, dst->c, param->activation,
+                                            bcnn_stream(net)));
+}
+
+/* conv + BN without activation whose only reader is a resident residual add: that add applies the
+ * normalisation (forward) and this node reads its incoming gradient from the add's output gradient
+ * (backward). The node index of the add, or -1. */
+static int conv_fused_into_eltwise(bcnn_net *net, bcnn_node *node) {
+    bcnn_conv_param *param = (bcnn_conv_param *)node->param;
+    int consumer = -1;
+    if (!param->batch_norm || param->activation != BCNN_ACT_NONE) return -1;
+    if (!bcnn_net_sole_eltwise_consumer(net, node->dst[0], &consumer)) return -1;
+    return consumer;
+}
+
+int bcnn_conv_layer_takes_grad_alias(bcnn_net *net, int idx) {
+    for (int i = 0; i < net->num_nodes; ++i) {
+        bcnn_node *node = &net->nodes[i];
+        if (node->num_dst < 1 || node->dst[0] != idx) continue;
+        if (node->type != BCNN_LAYER_CONV2D) return 0;
+        const bcnn_conv_param *param = (const bcnn_conv_param *)node->param;
+        return param->batch_norm && param->activation == BCNN_ACT_NONE && net->mode == BCNN_MODE_TRAIN &&
+               bcnn_conv_layer_is_resident(net, node);
+    }
+    return 0;
+}
+
 static void conv_forward_resident(bcnn_net *net, bcnn_node *node) {
     bcnn_conv_param *param = (bcnn_conv_param *)node->param;
     bcnn_cuda_context *ctx = bcnn_ctx(net);
@@ -169,6 +222,7 @@ static void conv_forward_resident(bcnn_net *net, bcnn_node *node) {
     } else {
         x = bcnn_net_data16_in(net, node->src[0]);
     }
+    const int deferred = conv_fused_into_eltwise(net, node) >= 0;
     void *y16 = bcnn_net_data16_out(net, node->dst[0]);
     if (!param->batch_norm) {
         bcnn_cuda_check(bcnn_b200_conv_forward_nhwc(&param->desc, x, weights->data_gpu, biases->data_gpu,
@@ -177,7 +231,7 @@ static void conv_forward_resident(bcnn_net *net, bcnn_node *node) {
         return;
     }
     const float *gamma = t[node->src[5]].data_gpu;
-    if (net->mode == BCNN_MODE_PREDICT) { /* statistics folded into gamma / beta at load time */
+    if (net->mode == BCNN_MODE_PREDICT && !deferred) { /* statistics folded into gamma / beta at load time */
         bcnn_cuda_check(bcnn_b200_conv_forward_nhwc(&param->desc, x, weights->data_gpu, NULL, BCNN_ACT_NONE,
                                                     y16, ctx->workspace_gpu, ctx->workspace_bytes, sh,
                                                     stream));
@@ -203,6 +257,12 @@ static void conv_forward_resident(bcnn_net *net, bcnn_node *node) {
                                                     param->bn_raw16_gpu, ctx->workspace_gpu,
                                                     ctx->workspace_bytes, sh, stream));
     }
+    if (deferred) { /* the residual add normalises; anybody else asking gets bcnn_conv_layer_materialize */
+        bcnn_resident *r = bcnn_net_res(net, node->dst[0]);
+        r->data_at = BCNN_RES_DEFERRED;
+        r->producer = (int)(node - net->nodes);
+        return;
+    }
     bcnn_cuda_check(bcnn_b200_bn_apply_nhwc(param->bn_raw16_gpu, y16, mean, var, gamma, biases->data_gpu,
                                             positions, dst->c, param->activation, stream));
 }
@@ -215,14 +275,26 @@ static void conv_backward_resident(bcnn_net *net, bcnn_node *node) {
     bcnn_tensor *weights = &t[node->src[1]], *biases = &t[node->src[2]];
     void *stream = ctx->stream;
     const size_t positions = (size_t)dst->n * dst->h * dst->w;
-    void *dy16 = bcnn_net_grad16_in(net, node->dst[0]);
+    /* incoming gradient: this tensor's own twin, or (fused residual add) the add's masked output
+     * gradient; the batch-norm backward then writes its result into the own twin, so both tensors
+     * read back as in the reference (in-place results, src/layers/bcnn_conv_layer.c:516-528) */
+    bcnn_resident *rd = bcnn_net_res(net, node->dst[0]);
+    void *dy16;
+    void *dy_in;
+    if (rd->grad_alias > 0) {
+        dy_in = bcnn_net_grad16_in(net, rd->grad_alias - 1);
+        dy16 = bcnn_net_grad16_out(net, node->dst[0]);
+        rd->grad_alias = 0;
+    } else {
+        dy16 = dy_in = bcnn_net_grad16_in(net, node->dst[0]);
+    }
     float *scratch = bcnn_net_nhwc_scratch(net, dst->c);
     if (param->batch_norm) {
         const int train = net->mode == BCNN_MODE_TRAIN;
         const float *mean = train ? param->saved_mean.data_gpu : t[node->src[3]].data_gpu;
         const float *var = train ? param->saved_variance.data_gpu : t[node->src[4]].data_gpu;
         bcnn_cuda_check(bcnn_b200_bn_backward_nhwc(
-            param->bn_raw16_gpu, dy16, dy16, mean, var, t[node->src[5]].data_gpu, biases->data_gpu,
+            param->bn_raw16_gpu, dy_in, dy16, mean, var, t[node->src[5]].data_gpu, biases->data_gpu,
             t[node->src[5]].grad_data_gpu, biases->grad_data_gpu, param->saved_mean.grad_data_gpu,
             param->saved_variance.grad_data_gpu, positions, dst->c, param->activation, scratch, stream));
     } else {

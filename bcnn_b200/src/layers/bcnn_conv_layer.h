@@ -61,6 +61,14 @@ void bcnn_update_conv_layer(bcnn_net *net, bcnn_node *node);
 void bcnn_release_param_conv_layer(bcnn_node *node);
 void bcnn_forward_conv_layer_gpu(bcnn_net *net, bcnn_node *node);
 int bcnn_conv_layer_is_resident(bcnn_net *net, bcnn_node *node);
+/* resident mode: apply the deferred batch norm of this node (raw result -> dst's BF16 twin) */
+void bcnn_conv_layer_materialize(bcnn_net *net, bcnn_node *node);
+/* resident mode: tensor idx is the output of a resident conv + BN node without activation, i.e. one
+ * whose backward can take its incoming gradient from a residual add's output gradient */
+int bcnn_conv_layer_takes_grad_alias(bcnn_net *net, int idx);
+/* resident mode: mean / variance the batch norm of this node normalises with in the net's mode */
+void bcnn_conv_layer_bn_operand(bcnn_net *net, bcnn_node *node, const void **raw, const float **mean,
+                                const float **var, const float **gamma, const float **beta);
 void bcnn_backward_conv_layer_gpu(bcnn_net *net, bcnn_node *node);
 
 #ifdef __cplusplus

@@ -16,6 +16,7 @@
  */
 #include "bcnn_glue_layers.h"
 
+#include "bcnn_conv_layer.h"
 #include "bcnn_tensor.h"
 
 /* ------------------------------- softmax ------------------------------- */
@@ -159,11 +160,33 @@ void bcnn_forward_eltwise_layer(bcnn_net *net, bcnn_node *node) {
     const int sz = bcnn_tensor_size(dst);
     const int n_add = bcnn_ctx(net)->reference_quirks ? param->min_dim[0] * dst->h * dst->w : sz;
     if (bcnn_net_node_is_resident(net, node)) { /* sample 0 is the first C*H*W elements in NHWC too */
-        const void *a16 = bcnn_net_data16_in(net, node->src[0]);
-        const void *b16 = bcnn_net_data16_in(net, node->src[1]);
-        bcnn_cuda_check(bcnn_b200_eltwise_forward_bf16(a16, b16, bcnn_net_data16_out(net, node->dst[0]),
-                                                       (size_t)sz, (size_t)n_add, param->activation,
-                                                       bcnn_stream(net)));
+        /* operands whose batch norm was left to this node (conv + BN without activation read by
+         * nobody else, see bcnn_conv_layer.c): normalise, add and activate in one pass */
+        const void *x16[2];
+        const float *mean[2] = {NULL, NULL}, *var[2] = {NULL, NULL}, *gamma[2] = {NULL, NULL},
+                    *beta[2] = {NULL, NULL};
+        int fused = 0;
+        for (int i = 0; i < 2; ++i) {
+            bcnn_resident *r = bcnn_net_res(net, node->src[i]);
+            const bcnn_activation a = param->activation;
+            if (r->data_at == BCNN_RES_DEFERRED && n_add == sz &&
+                (a == BCNN_ACT_NONE || a == BCNN_ACT_RELU || a == BCNN_ACT_LRELU)) {
+                bcnn_conv_layer_bn_operand(net, &net->nodes[r->producer], &x16[i], &mean[i], &var[i],
+                                           &gamma[i], &beta[i]);
+                fused = 1;
+            } else {
+                x16[i] = bcnn_net_data16_in(net, node->src[i]);
+            }
+        }
+        void *y16 = bcnn_net_data16_out(net, node->dst[0]);
+        if (fused)
+            bcnn_cuda_check(bcnn_b200_bn_add_act_nhwc(x16[0], mean[0], var[0], gamma[0], beta[0], x16[1],
+                                                      mean[1], var[1], gamma[1], beta[1], y16,
+                                                      (size_t)dst->n * dst->h * dst->w, dst->c,
+                                                      param->activation, bcnn_stream(net)));
+        else
+            bcnn_cuda_check(bcnn_b200_eltwise_forward_bf16(x16[0], x16[1], y16, (size_t)sz, (size_t)n_add,
+                                                           param->activation, bcnn_stream(net)));
         return;
     }
     bcnn_cuda_check(bcnn_b200_eltwise_forward(t[node->src[0]].data_gpu, t[node->src[1]].data_gpu,
@@ -184,10 +207,22 @@ void bcnn_backward_eltwise_layer(bcnn_net *net, bcnn_node *node) {
         const void *y16 = param->activation == BCNN_ACT_NONE ? NULL : bcnn_net_data16_in(net, node->dst[0]);
         void *dy16 = bcnn_net_grad16_in(net, node->dst[0]);
         void *g16[2] = {NULL, NULL};
-        for (int i = 0; i < 2; ++i)
-            if (t[node->src[i]].grad_data_gpu)
-                g16[i] = (flags & (1 << i)) ? bcnn_net_grad16_in(net, node->src[i])
-                                            : bcnn_net_grad16_out(net, node->src[i]);
+        for (int i = 0; i < 2; ++i) {
+            if (!t[node->src[i]].grad_data_gpu) continue;
+            /* a source only this node reads, produced by a conv + BN without activation: its
+             * gradient IS the masked dy this node leaves in dst.grad -- the producer reads it there
+             * (bcnn_resident.grad_alias) instead of from a copy written here */
+            int consumer = -1;
+            bcnn_resident *r = bcnn_net_res(net, node->src[i]);
+            if (!(flags & (1 << i)) && n_add == sz && r->producer >= 0 && r->producer < net->num_nodes &&
+                bcnn_net_sole_eltwise_consumer(net, node->src[i], &consumer) &&
+                &net->nodes[consumer] == node && bcnn_conv_layer_takes_grad_alias(net, node->src[i])) {
+                r->grad_alias = node->dst[0] + 1;
+                continue;
+            }
+            g16[i] = (flags & (1 << i)) ? bcnn_net_grad16_in(net, node->src[i])
+                                        : bcnn_net_grad16_out(net, node->src[i]);
+        }
         bcnn_cuda_check(bcnn_b200_eltwise_backward_bf16(y16 ? y16 : dy16, dy16, g16[0], g16[1], (size_t)sz,
                                                         (size_t)n_add, param->activation, flags,
                                                         bcnn_stream(net)));

@@ -409,6 +409,18 @@ BCNN_B200_API int bcnn_b200_bn_backward_nhwc(const void *x, void *dy, void *dx, 
 BCNN_B200_API int bcnn_b200_actbwd_grad_bias_nhwc(float *g_bias, void *dy, const void *y, int act,
                                                   size_t positions, int c, float *scratch,
                                                   void *stream);
+/* y = act(bn_a(xa) + bn_b(xb)): batch-norm apply of one or both operands fused with the residual
+ * add (bcnn_forward_batchnorm_cpu's normalise + scale + shift, src/layers/bcnn_batchnorm_layer.c
+ * :170-194, then bcnn_eltwise_layer.c:111-127) so that the block's last convolution and its
+ * projection shortcut never store their normalised outputs. Per operand: gamma == NULL: plain
+ * tensor; mean != NULL: gamma (x - mean) / sqrt(var + 1e-6) + beta; mean == NULL: gamma x + beta
+ * (PREDICT, folded statistics). Each branch is rounded to BF16 before the add, like the tensor the
+ * unfused path stores. act: NONE, RELU, LRELU. */
+BCNN_B200_API int bcnn_b200_bn_add_act_nhwc(const void *xa, const float *mean_a, const float *var_a,
+                                            const float *gamma_a, const float *beta_a,
+                                            const void *xb, const float *mean_b, const float *var_b,
+                                            const float *gamma_b, const float *beta_b, void *y,
+                                            size_t positions, int c, int act, void *stream);
 /* residual add; shadows bcnn_b200_eltwise_forward / _backward (sz, n_add in elements, % 8 == 0) */
 BCNN_B200_API int bcnn_b200_eltwise_forward_bf16(const void *a, const void *b, void *y, size_t sz,
                                                  size_t n_add, int act, void *stream);

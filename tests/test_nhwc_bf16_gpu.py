@@ -346,3 +346,40 @@ def test_resident_thin_first_layer_reads_fp32_nchw():
             check(lib.bcnn_b200_conv_backward_weights_nhwc(d, dxf.ptr, ddy.ptr, dgw.ptr, ws.ptr, ws_bytes,
                                                            None, None))
             assert_close(dgw.download(np.float32, wt.shape), gw_ref, 2e-2, f"wgrad rebuilt {shape}")
+
+
+@pytest.mark.parametrize("shape", [(3, 64, 14, 14), (2, 256, 7, 7), (4, 8, 5, 3)])
+@pytest.mark.parametrize("kinds", ["bn+plain", "bn+bn", "plain+bn", "fold+plain"])
+def test_fused_bn_residual_add_matches_the_unfused_kernels(shape, kinds):
+    """bn_add_act (normalise one or both operands, add, ReLU in one pass) against bn_apply_nhwc on each
+    operand followed by eltwise_forward_bf16: bit-identical, since every branch is rounded to BF16
+    exactly where the unfused path stores it."""
+    lib = capi.b200()
+    n, c, h, w = shape
+    pos = n * h * w
+    r = rng(len(kinds) + sum(shape))
+    ka, kb = kinds.split("+")
+    ops = []
+    for kind in (ka, kb):
+        x = dev(nhwc_bits(rounded(f32(r.normal(0.1, 1.0, size=shape)))))
+        prm = dict(mean=dev(f32(r.normal(0, 0.3, size=c))), var=dev(f32(r.uniform(0.5, 2.0, size=c))),
+                   gamma=dev(f32(r.uniform(0.5, 1.5, size=c))), beta=dev(f32(r.uniform(-0.3, 0.3, size=c))))
+        ops.append((kind, x, prm))
+    args, branches = [], []
+    for kind, x, prm in ops:
+        if kind == "plain":
+            args += [x.ptr, None, None, None, None]
+            branches.append(x)
+        else:
+            mean, var = (prm["mean"].ptr, prm["var"].ptr) if kind == "bn" else (None, None)
+            args += [x.ptr, mean, var, prm["gamma"].ptr, prm["beta"].ptr]
+            y = dev_zeros(x.nbytes // 2, 2)
+            check(lib.bcnn_b200_bn_apply_nhwc(x.ptr, y.ptr, mean, var, prm["gamma"].ptr, prm["beta"].ptr, pos, c,
+                                              ACT["none"], None))
+            branches.append(y)
+    want = dev_zeros(pos * c, 2)
+    check(lib.bcnn_b200_eltwise_forward_bf16(branches[0].ptr, branches[1].ptr, want.ptr, pos * c, pos * c,
+                                             ACT["relu"], None))
+    got = dev_zeros(pos * c, 2)
+    check(lib.bcnn_b200_bn_add_act_nhwc(*args, got.ptr, pos, c, ACT["relu"], None))
+    assert np.array_equal(got.download(np.uint16), want.download(np.uint16))
