@@ -141,6 +141,19 @@ def resnet50(net, batch=256, res=224, classes=1000, widths=(64, 128, 256, 512),
     return dict(classes=classes, out="softmax")
 
 
+# every convolution shape of ResNet-50 v1.5 at 224 x 224:
+# (cin, h, cout, k, stride, pad, how many nodes of the net have it)
+RESNET50_CONV_SHAPES = [
+    (3, 224, 64, 7, 2, 3, 1),
+    (64, 56, 64, 1, 1, 0, 1), (64, 56, 64, 3, 1, 1, 3), (64, 56, 256, 1, 1, 0, 4), (256, 56, 64, 1, 1, 0, 2),
+    (256, 56, 128, 1, 1, 0, 1), (128, 56, 128, 3, 2, 1, 1), (128, 28, 512, 1, 1, 0, 4), (256, 56, 512, 1, 2, 0, 1),
+    (512, 28, 128, 1, 1, 0, 3), (128, 28, 128, 3, 1, 1, 3), (512, 28, 256, 1, 1, 0, 1), (256, 28, 256, 3, 2, 1, 1),
+    (256, 14, 1024, 1, 1, 0, 6), (512, 28, 1024, 1, 2, 0, 1), (1024, 14, 256, 1, 1, 0, 5), (256, 14, 256, 3, 1, 1, 5),
+    (1024, 14, 512, 1, 1, 0, 1), (512, 14, 512, 3, 2, 1, 1), (512, 7, 2048, 1, 1, 0, 3), (1024, 14, 2048, 1, 2, 0, 1),
+    (2048, 7, 512, 1, 1, 0, 2), (512, 7, 512, 3, 1, 1, 2),
+]
+
+
 def yolov3_tiny_cfg(batch=1, width=416, height=416, max_filters=None):
     """The text of a Darknet-dialect YOLOv3-tiny config, generated from the layer list (the
     reference ships the same network as examples/yolo/yolov3-tiny.cfg; tests/test_baseline_parity

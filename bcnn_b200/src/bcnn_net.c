@@ -35,13 +35,14 @@ bcnn_status bcnn_net_create_cuda_context(bcnn_net *net) {
     }
     const char *graphs = getenv("BCNN_B200_GRAPHS");
     ctx->graphs = !(graphs && graphs[0] == '0');
-    /* Tensor-core math is the default; BCNN_B200_CONV_MATH=fp32 (or bcnn_b200_set_conv_math)
-     * selects the FP32 SIMT verification path. */
+    /* Default: tensor-core math with resident BF16 NHWC activations (BCNN_B200_MATH_TC_BF16).
+     * BCNN_B200_CONV_MATH=tc keeps FP32 NCHW tensors between the layers (tensor-core convolutions on
+     * transposed shadows), =fp32 selects the FP32 SIMT verification path; bcnn_b200_set_conv_math
+     * does the same per net. */
     const char *math = getenv("BCNN_B200_CONV_MATH");
-    ctx->conv_math = BCNN_B200_MATH_TC;
+    ctx->conv_math = BCNN_B200_MATH_TC_BF16;
     if (math && (math[0] == 'f' || math[0] == 'F' || math[0] == '0')) ctx->conv_math = BCNN_B200_MATH_FP32;
-    else if (math && (math[0] == 'r' || math[0] == 'R' || math[0] == 'b' || math[0] == 'B' || math[0] == '2'))
-        ctx->conv_math = BCNN_B200_MATH_TC_BF16; /* "resident" / "bf16" */
+    else if (math && (math[0] == 't' || math[0] == 'T' || math[0] == '1')) ctx->conv_math = BCNN_B200_MATH_TC;
     /* Batch-correct residual semantics by default; the reference's two residual bugs (H2, H3) are
      * replicated only on request (parity tests): BCNN_B200_REFERENCE_QUIRKS=1 or
      * bcnn_b200_set_reference_quirks(net, 1). */

@@ -106,10 +106,15 @@ def test_net_matches_live_reference(name):
 
 
 def test_library_defaults(monkeypatch):
-    """Without the test session's environment a net computes on the tensor cores with
-    batch-correct residual semantics; the FP32 path and the reference quirks are opt-in."""
+    """Without the test session's environment a net computes on the tensor cores with resident BF16
+    NHWC activations and batch-correct residual semantics; the FP32-tensor tensor-core mode, the FP32
+    path and the reference quirks are opt-in."""
     monkeypatch.delenv("BCNN_B200_CONV_MATH")
     monkeypatch.delenv("BCNN_B200_REFERENCE_QUIRKS")
+    net = capi.Net()
+    assert net.lib.bcnn_b200_get_conv_math(net.handle) == capi.MATH_TC_BF16
+    net.close()
+    monkeypatch.setenv("BCNN_B200_CONV_MATH", "tc")
     net = capi.Net()
     assert net.lib.bcnn_b200_get_conv_math(net.handle) == capi.MATH_TC
     assert net.lib.bcnn_b200_get_reference_quirks(net.handle) == 0
