@@ -149,6 +149,8 @@ def bind_b200_ext(lib: C.CDLL) -> None:
         "bcnn_b200_dp_shutdown": (None, [vp]),
         "bcnn_b200_dp_world": (i, [vp]),
         "bcnn_b200_dp_bytes_per_step": (sz, [vp]),
+        "bcnn_b200_dp_groups_per_step": (i, [vp]),
+        "bcnn_b200_dp_allreduce_probe_ms": (f, [vp, i]),
         "bcnn_b200_set_device": (i, [i]),
         "bcnn_b200_device_count": (i, []),
         "bcnn_b200_sm_count": (i, []),

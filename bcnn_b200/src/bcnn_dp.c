@@ -39,6 +39,13 @@ static struct {
     fn_errstr errstr;
 } nccl;
 
+/* Gradients are all-reduced in buckets: tensors of consecutive nodes (in backward order) are
+ * collected until BUCKET_BYTES are pending, then issued as ONE NCCL group (NCCL aggregates the
+ * collectives of a group into a single launch) behind one event. ResNet-50: 102 MB in 5 launches
+ * instead of one per node. */
+#define BUCKET_BYTES ((size_t)25 << 20)
+#define BUCKET_MAX_TENSORS 256
+
 struct bcnn_dp_state {
     int rank, world;
     void *comm;
@@ -46,6 +53,11 @@ struct bcnn_dp_state {
     void *evt_ready; /* compute -> comm */
     void *evt_done;  /* comm -> compute */
     size_t bytes_per_step, bytes_this_step;
+    float *pending[BUCKET_MAX_TENSORS];
+    size_t pending_count[BUCKET_MAX_TENSORS];
+    int num_pending;
+    size_t pending_bytes;
+    int groups_per_step, groups_this_step;
 };
 
 static int nccl_bind(void) {
@@ -119,38 +131,89 @@ size_t bcnn_b200_dp_bytes_per_step(bcnn_net *net) {
     return dp ? dp->bytes_per_step : 0;
 }
 
+static void flush_bucket(bcnn_net *net, struct bcnn_dp_state *dp) {
+    if (dp->num_pending == 0) return;
+    /* everything enqueued on the compute stream so far (the backward passes that produced the
+     * pending gradients) precedes the transfer; under stream capture this forks the comm stream
+     * into the graph */
+    bcnn_cuda_check(bcnn_b200_event_record(dp->evt_ready, bcnn_stream(net)));
+    bcnn_cuda_check(bcnn_b200_stream_wait_event(dp->comm_stream, dp->evt_ready));
+    nccl_check(nccl.group_start());
+    for (int i = 0; i < dp->num_pending; ++i)
+        nccl_check(nccl.allreduce(dp->pending[i], dp->pending[i], dp->pending_count[i], NCCL_FLOAT32,
+                                  NCCL_SUM, dp->comm, dp->comm_stream));
+    nccl_check(nccl.group_end());
+    dp->num_pending = 0;
+    dp->pending_bytes = 0;
+    dp->groups_this_step++;
+}
+
+/* Parameter gradients an optimizer step consumes: W and bias / beta of the nodes that have an
+ * update function (src[1], src[2]; the PReLU slopes of an activation node are src[1]). Batch-norm
+ * scale gradients are written by backward but never applied: they stay local. */
 void bcnn_dp_after_node_backward(bcnn_net *net, bcnn_node *node) {
     struct bcnn_dp_state *dp = bcnn_ctx(net)->dp;
     if (!dp) return;
-    int queued = 0;
-    for (int i = 1; i < node->num_src; ++i) { /* src[0] is the activation input */
-        bcnn_tensor *t = &net->tensors[node->src[i]];
-        /* these nodes' further sources are activations, not parameters */
-        if (node->type == BCNN_LAYER_COST || node->type == BCNN_LAYER_ELTWISE ||
-            node->type == BCNN_LAYER_CONCAT)
-            break;
-        if (!t->has_grad || !t->grad_data_gpu) continue;
-        if (!queued) {
-            bcnn_cuda_check(bcnn_b200_event_record(dp->evt_ready, bcnn_stream(net)));
-            bcnn_cuda_check(bcnn_b200_stream_wait_event(dp->comm_stream, dp->evt_ready));
-            nccl_check(nccl.group_start());
-            queued = 1;
+    if (node->update) {
+        const int last = node->type == BCNN_LAYER_ACTIVATION ? 1 : 2;
+        for (int i = 1; i <= last && i < node->num_src; ++i) {
+            bcnn_tensor *t = &net->tensors[node->src[i]];
+            if (!t->has_grad || !t->grad_data_gpu) continue;
+            const size_t count = (size_t)bcnn_tensor_size(t);
+            if (dp->num_pending == BUCKET_MAX_TENSORS) flush_bucket(net, dp);
+            dp->pending[dp->num_pending] = t->grad_data_gpu;
+            dp->pending_count[dp->num_pending++] = count;
+            dp->pending_bytes += count * sizeof(float);
+            dp->bytes_this_step += count * sizeof(float);
         }
-        size_t count = (size_t)bcnn_tensor_size(t);
-        nccl_check(nccl.allreduce(t->grad_data_gpu, t->grad_data_gpu, count, NCCL_FLOAT32, NCCL_SUM,
-                                  dp->comm, dp->comm_stream));
-        dp->bytes_this_step += count * sizeof(float);
     }
-    if (queued) nccl_check(nccl.group_end());
+    /* a full bucket goes out now and overlaps the rest of backward; the remainder when the first
+     * node's backward is done */
+    if (dp->pending_bytes >= BUCKET_BYTES || node == &net->nodes[0]) flush_bucket(net, dp);
 }
 
+/* Join: the compute stream waits for every transfer issued so far. Idempotent. */
 void bcnn_dp_before_update(bcnn_net *net) {
     struct bcnn_dp_state *dp = bcnn_ctx(net)->dp;
     if (!dp) return;
+    flush_bucket(net, dp);
     bcnn_cuda_check(bcnn_b200_event_record(dp->evt_done, dp->comm_stream));
     bcnn_cuda_check(bcnn_b200_stream_wait_event(bcnn_stream(net), dp->evt_done));
-    dp->bytes_per_step = dp->bytes_this_step;
+    if (dp->bytes_this_step) {
+        dp->bytes_per_step = dp->bytes_this_step;
+        dp->groups_per_step = dp->groups_this_step;
+    }
     dp->bytes_this_step = 0;
+    dp->groups_this_step = 0;
+}
+
+int bcnn_b200_dp_groups_per_step(bcnn_net *net) {
+    struct bcnn_dp_state *dp = bcnn_ctx(net)->dp;
+    return dp ? dp->groups_per_step : 0;
+}
+
+/* Time of `iters` all-reduces of the whole gradient set (the step's buckets, back to back on the
+ * comm stream, nothing else running): milliseconds per set, for the bus-bandwidth figure of the
+ * bench line. The gradient buffers are summed over and over: call it after the measurements. */
+float bcnn_b200_dp_allreduce_probe_ms(bcnn_net *net, int iters) {
+    struct bcnn_dp_state *dp = bcnn_ctx(net)->dp;
+    if (!dp || iters < 1) return 0.f;
+    bcnn_b200_sync(net);
+    void *e0 = bcnn_b200_event_create(), *e1 = bcnn_b200_event_create();
+    float ms = 0.f;
+    for (int it = -1; it < iters; ++it) { /* one untimed round first */
+        if (it == 0) bcnn_cuda_check(bcnn_b200_event_record(e0, dp->comm_stream));
+        for (int i = net->num_nodes - 1; i >= 0; --i) bcnn_dp_after_node_backward(net, &net->nodes[i]);
+        flush_bucket(net, dp);
+    }
+    bcnn_cuda_check(bcnn_b200_event_record(e1, dp->comm_stream));
+    bcnn_cuda_check(bcnn_b200_stream_sync(dp->comm_stream));
+    ms = bcnn_b200_event_elapsed_ms(e0, e1) / (float)iters;
+    bcnn_b200_event_destroy(e0);
+    bcnn_b200_event_destroy(e1);
+    dp->bytes_this_step = 0;
+    dp->groups_this_step = 0;
+    return ms;
 }
 
 void bcnn_dp_sync(bcnn_net *net) {

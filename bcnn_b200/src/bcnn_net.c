@@ -614,9 +614,17 @@ static void pipeline_swap_in(bcnn_net *net) {
  * and backward were replayed, 2 when the update kernels were replayed with them. */
 static int train_graph(bcnn_net *net) {
     bcnn_cuda_context *ctx = bcnn_ctx(net);
-    if (!ctx->graphs || net->mode != BCNN_MODE_TRAIN || ctx->profile || ctx->dp ||
-        net->num_inputs != 1 || net->num_nodes == 0)
+    if (!ctx->graphs || net->mode != BCNN_MODE_TRAIN || ctx->profile || net->num_inputs != 1 ||
+        net->num_nodes == 0)
         return 0;
+    if (ctx->dp) { /* the comm stream forks into the capture; BCNN_B200_DP_GRAPH=0 keeps DP eager */
+        static int dp_graph = -1;
+        if (dp_graph < 0) {
+            const char *e = getenv("BCNN_B200_DP_GRAPH");
+            dp_graph = !(e && e[0] == '0');
+        }
+        if (!dp_graph) return 0;
+    }
     graph_key_check(net);
     if (!ctx->step_graph_warm) { /* first step of this configuration: eager (lazy allocations) */
         ctx->step_graph_warm = 1;
@@ -647,6 +655,10 @@ static int train_graph(bcnn_net *net) {
         const unsigned long long before = bcnn_b200_launch_count();
         forward_nodes(net);
         bcnn_backward(net);
+        /* data parallelism: the gradient all-reduces forked onto the comm stream during backward
+         * re-join the captured stream here, so the graph is closed whether or not the update
+         * kernels are part of it */
+        bcnn_dp_before_update(net);
         if (with_update) bcnn_update_nodes(net);
         ctx->step_graph[slot].kernels = bcnn_b200_launch_count() - before;
         ctx->step_graph[slot].exec = bcnn_b200_graph_end(ctx->stream);

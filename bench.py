@@ -493,6 +493,12 @@ def run_own_arm(args):
     lib.bcnn_b200_profile(net.handle, 1)
     net.train_step()
     barrier()
+    # all-reduce of the whole gradient set alone on the comm stream (collective: every rank), for the
+    # bus-bandwidth figure; it clobbers the gradient buffers, so it runs after everything else
+    dp_bytes = lib.bcnn_b200_dp_bytes_per_step(net.handle)
+    dp_groups = lib.bcnn_b200_dp_groups_per_step(net.handle)
+    allreduce_ms = lib.bcnn_b200_dp_allreduce_probe_ms(net.handle, 5) if world > 1 else 0.0
+    barrier()
     result = None
     if rank == 0:
         peaks = measured_peaks()
@@ -510,7 +516,6 @@ def run_own_arm(args):
             a[0] += fwd.value; a[1] += bwd.value
         lib.bcnn_b200_profile(net.handle, 0)
         breakdown = {k: dict(fwd_ms=round(v[0], 3), bwd_ms=round(v[1], 3)) for k, v in by_type.items()}
-        dp_bytes = lib.bcnn_b200_dp_bytes_per_step(net.handle)
         net.close()
         classes, per_shape, hbm_classes, conv_tc_util = [], [], [], None
         if args.rooflines and math == capi.MATH_TC_BF16 and args.workload == "resnet50":
@@ -554,6 +559,14 @@ def run_own_arm(args):
             "loss": loss,
             "step_breakdown_ms": breakdown,
             "allreduce_bytes_per_step": int(dp_bytes),
+            "allreduce": None if world == 1 else {
+                "bytes_per_step": int(dp_bytes), "nccl_groups_per_step": int(dp_groups),
+                "ms_alone": allreduce_ms,
+                "busbw_gbs": (2.0 * (world - 1) / world) * dp_bytes / (allreduce_ms * 1e-3) / 1e9
+                if allreduce_ms > 0 else None,
+                "note": "gradients of weights and biases in ~25 MB buckets, one aggregated NCCL group "
+                        "each, issued during backward on a second stream inside the step's CUDA graph; "
+                        "ms_alone / busbw: the same buckets back to back with nothing else running"},
             "peaks": peaks,
         }
         if dominant:

@@ -133,8 +133,14 @@ BCNN_B200_API int bcnn_b200_dp_init(bcnn_net *net, int rank, int world,
                                     const char id[BCNN_B200_DP_ID_BYTES]);
 BCNN_B200_API void bcnn_b200_dp_shutdown(bcnn_net *net);
 BCNN_B200_API int bcnn_b200_dp_world(bcnn_net *net);
-/* Bytes all-reduced per step (sum over parameter gradient tensors). */
+/* Bytes all-reduced per step (sum over the parameter gradient tensors an update consumes: weights
+ * and bias / beta; batch-norm scale gradients are never applied, SURVEY.md H6, and stay local). */
 BCNN_B200_API size_t bcnn_b200_dp_bytes_per_step(bcnn_net *net);
+/* NCCL launches per step: gradients travel in ~25 MB buckets, one aggregated group each. */
+BCNN_B200_API int bcnn_b200_dp_groups_per_step(bcnn_net *net);
+/* Milliseconds per all-reduce of the whole gradient set with nothing else running (bench.py's
+ * bus-bandwidth figure). Sums the gradient buffers repeatedly: call it after the measurements. */
+BCNN_B200_API float bcnn_b200_dp_allreduce_probe_ms(bcnn_net *net, int iters);
 
 #ifdef __cplusplus
 }
