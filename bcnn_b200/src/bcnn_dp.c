@@ -18,6 +18,8 @@
 
 #include <bcnn_b200_net.h>
 
+#include "bcnn_tensor.h"
+
 typedef struct { char internal[128]; } nccl_uid;
 typedef int (*fn_get_uid)(nccl_uid *);
 typedef int (*fn_init_rank)(void **comm, int nranks, nccl_uid id, int rank);
@@ -58,6 +60,9 @@ struct bcnn_dp_state {
     int num_pending;
     size_t pending_bytes;
     int groups_per_step, groups_this_step;
+    /* set while a step graph is recorded / replayed: backward does not issue transfers (NCCL calls
+     * stay out of the graph), bcnn_dp_allreduce_all issues them behind the replay */
+    int defer;
 };
 
 static int nccl_bind(void) {
@@ -151,9 +156,55 @@ static void flush_bucket(bcnn_net *net, struct bcnn_dp_state *dp) {
 /* Parameter gradients an optimizer step consumes: W and bias / beta of the nodes that have an
  * update function (src[1], src[2]; the PReLU slopes of an activation node are src[1]). Batch-norm
  * scale gradients are written by backward but never applied: they stay local. */
+void bcnn_dp_set_deferred(bcnn_net *net, int on) {
+    struct bcnn_dp_state *dp = bcnn_ctx(net)->dp;
+    if (dp) dp->defer = on;
+}
+
+static void collect_node(bcnn_net *net, struct bcnn_dp_state *dp, bcnn_node *node);
+
 void bcnn_dp_after_node_backward(bcnn_net *net, bcnn_node *node) {
     struct bcnn_dp_state *dp = bcnn_ctx(net)->dp;
+    if (!dp || dp->defer) return;
+    collect_node(net, dp, node);
+}
+
+/* Every gradient bucket of the step, behind whatever the compute stream holds (a replayed step
+ * graph): same buckets in the same order as the overlapped path. */
+void bcnn_dp_allreduce_range(bcnn_net *net, int first, int end) {
+    struct bcnn_dp_state *dp = bcnn_ctx(net)->dp;
     if (!dp) return;
+    /* one group for the whole range (fewer, larger messages) */
+    dp->defer = 2;
+    for (int i = end - 1; i >= first; --i) collect_node(net, dp, &net->nodes[i]);
+    dp->defer = 0;
+    flush_bucket(net, dp);
+}
+
+void bcnn_dp_allreduce_all(bcnn_net *net) { bcnn_dp_allreduce_range(net, 0, net->num_nodes); }
+
+/* Where to cut the backward pass of a replayed step in two: the node index `split` such that the
+ * nodes below it hold at most ~8 % of the gradient bytes (ResNet-50: the stem and the first two
+ * stages -- most of the backward TIME, because their activations are the large ones). */
+int bcnn_dp_backward_split(bcnn_net *net) {
+    size_t total = 0, below = 0;
+    for (int i = 0; i < net->num_nodes; ++i) {
+        const bcnn_node *node = &net->nodes[i];
+        if (!node->update) continue;
+        for (int j = 1; j <= 2 && j < node->num_src; ++j) total += (size_t)bcnn_tensor_size(&net->tensors[node->src[j]]);
+    }
+    int split = 0;
+    for (int i = 0; i < net->num_nodes; ++i) {
+        const bcnn_node *node = &net->nodes[i];
+        if (node->update)
+            for (int j = 1; j <= 2 && j < node->num_src; ++j) below += (size_t)bcnn_tensor_size(&net->tensors[node->src[j]]);
+        if (below * 12 > total) break;
+        split = i + 1;
+    }
+    return split < net->num_nodes ? split : 0;
+}
+
+static void collect_node(bcnn_net *net, struct bcnn_dp_state *dp, bcnn_node *node) {
     if (node->update) {
         const int last = node->type == BCNN_LAYER_ACTIVATION ? 1 : 2;
         for (int i = 1; i <= last && i < node->num_src; ++i) {
@@ -169,6 +220,7 @@ void bcnn_dp_after_node_backward(bcnn_net *net, bcnn_node *node) {
     }
     /* a full bucket goes out now and overlaps the rest of backward; the remainder when the first
      * node's backward is done */
+    if (dp->defer == 2) return;
     if (dp->pending_bytes >= BUCKET_BYTES || node == &net->nodes[0]) flush_bucket(net, dp);
 }
 
@@ -203,8 +255,7 @@ float bcnn_b200_dp_allreduce_probe_ms(bcnn_net *net, int iters) {
     float ms = 0.f;
     for (int it = -1; it < iters; ++it) { /* one untimed round first */
         if (it == 0) bcnn_cuda_check(bcnn_b200_event_record(e0, dp->comm_stream));
-        for (int i = net->num_nodes - 1; i >= 0; --i) bcnn_dp_after_node_backward(net, &net->nodes[i]);
-        flush_bucket(net, dp);
+        bcnn_dp_allreduce_all(net);
     }
     bcnn_cuda_check(bcnn_b200_event_record(e1, dp->comm_stream));
     bcnn_cuda_check(bcnn_b200_stream_sync(dp->comm_stream));

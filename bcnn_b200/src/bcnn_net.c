@@ -299,7 +299,11 @@ static void forward_graph_drop(bcnn_cuda_context *ctx) {
     for (int i = 0; i < 2; ++i) {
         bcnn_b200_graph_destroy(ctx->step_graph[i].exec);
         ctx->step_graph[i].exec = NULL;
+        bcnn_b200_graph_destroy(ctx->step_graph[i].exec_tail);
+        ctx->step_graph[i].exec_tail = NULL;
     }
+    bcnn_b200_graph_destroy(ctx->update_graph.exec);
+    ctx->update_graph.exec = NULL;
     ctx->step_graph_warm = 0;
 }
 
@@ -370,9 +374,14 @@ int bcnn_b200_get_graphs(bcnn_net *net) {
     return !ctx->graphs ? 0 : (live ? 2 : 1);
 }
 
-void bcnn_backward(bcnn_net *net) {
+static void backward_range(bcnn_net *net, int first, int end);
+
+void bcnn_backward(bcnn_net *net) { backward_range(net, 0, net->num_nodes); }
+
+/* backward of nodes end - 1 .. first */
+static void backward_range(bcnn_net *net, int first, int end) {
     g_current_stream = bcnn_stream(net);
-    for (int i = net->num_nodes - 1; i >= 0; --i) {
+    for (int i = end - 1; i >= first; --i) {
         bcnn_node *node = &net->nodes[i];
         profile_mark(net, i, 2);
         if (bcnn_net_node_is_resident(net, node)) {
@@ -617,7 +626,13 @@ static int train_graph(bcnn_net *net) {
     if (!ctx->graphs || net->mode != BCNN_MODE_TRAIN || ctx->profile || net->num_inputs != 1 ||
         net->num_nodes == 0)
         return 0;
-    if (ctx->dp) { /* the comm stream forks into the capture; BCNN_B200_DP_GRAPH=0 keeps DP eager */
+    if (ctx->dp) {
+        /* Data parallelism: forward + backward are replayed as one graph and the gradient buckets
+         * are all-reduced behind it (4 NCCL launches for ResNet-50, ~0.45 ms on NVLink), then the
+         * update runs eagerly. Capturing the NCCL calls on a forked comm stream inside the graph
+         * deadlocked both ranks on this stack (gpurun r2n), and the eager step it replaced cost
+         * 1.8 ms of launch overhead per step -- more than the overlap was worth.
+         * BCNN_B200_DP_GRAPH=0: fully eager steps with the transfers overlapping backward. */
         static int dp_graph = -1;
         if (dp_graph < 0) {
             const char *e = getenv("BCNN_B200_DP_GRAPH");
@@ -633,7 +648,7 @@ static int train_graph(bcnn_net *net) {
     const void *input = net->tensors[0].data_gpu, *label = net->tensors[1].data_gpu;
     const bcnn_learner *ln = net->learner;
     const int with_update = ln && ln->optimizer == BCNN_OPTIM_SGD &&
-                            ln->decay_type == BCNN_LR_DECAY_CONSTANT;
+                            ln->decay_type == BCNN_LR_DECAY_CONSTANT && !ctx->dp;
     int slot = -1, recorded_now = 0;
     for (int i = 0; i < 2; ++i)
         if (ctx->step_graph[i].exec && ctx->step_graph[i].input == input &&
@@ -653,15 +668,33 @@ static int train_graph(bcnn_net *net) {
             return 0;
         }
         const unsigned long long before = bcnn_b200_launch_count();
+        bcnn_dp_set_deferred(net, 1); /* no NCCL call inside the capture */
+        const int split = ctx->dp ? bcnn_dp_backward_split(net) : 0;
+        bcnn_b200_graph_destroy(ctx->step_graph[slot].exec_tail);
+        ctx->step_graph[slot].exec_tail = NULL;
+        ctx->step_graph[slot].split = split;
         forward_nodes(net);
-        bcnn_backward(net);
-        /* data parallelism: the gradient all-reduces forked onto the comm stream during backward
-         * re-join the captured stream here, so the graph is closed whether or not the update
-         * kernels are part of it */
-        bcnn_dp_before_update(net);
+        backward_range(net, split, net->num_nodes);
+        if (split > 0) { /* data parallelism: the rest of backward is a second graph */
+            ctx->step_graph[slot].kernels = bcnn_b200_launch_count() - before;
+            ctx->step_graph[slot].exec = bcnn_b200_graph_end(ctx->stream);
+            if (ctx->step_graph[slot].exec && bcnn_b200_graph_begin(ctx->stream) == 0) {
+                const unsigned long long before_tail = bcnn_b200_launch_count();
+                backward_range(net, 0, split);
+                ctx->step_graph[slot].kernels_tail = bcnn_b200_launch_count() - before_tail;
+                ctx->step_graph[slot].exec_tail = bcnn_b200_graph_end(ctx->stream);
+            }
+            if (!ctx->step_graph[slot].exec_tail) { /* half a step is no step: run eagerly */
+                bcnn_b200_graph_destroy(ctx->step_graph[slot].exec);
+                ctx->step_graph[slot].exec = NULL;
+            }
+            bcnn_dp_set_deferred(net, 0);
+        } else {
+        bcnn_dp_set_deferred(net, 0);
         if (with_update) bcnn_update_nodes(net);
         ctx->step_graph[slot].kernels = bcnn_b200_launch_count() - before;
         ctx->step_graph[slot].exec = bcnn_b200_graph_end(ctx->stream);
+        }
         if (!ctx->step_graph[slot].exec) {
             BCNN_WARNING(net->log_ctx, "CUDA graph capture of the training step failed; running eagerly\n");
             ctx->graphs = 0;
@@ -679,6 +712,45 @@ static int train_graph(bcnn_net *net) {
     }
     bcnn_cuda_check(bcnn_b200_graph_launch(ctx->step_graph[slot].exec,
                                            recorded_now ? 0 : ctx->step_graph[slot].kernels, ctx->stream));
+    if (ctx->dp) {
+        /* gradients of the nodes whose backward is done travel while the tail graph (the stem and
+         * the early stages: few parameters, most of the backward time) runs */
+        const int split = ctx->step_graph[slot].split;
+        bcnn_dp_allreduce_range(net, split, net->num_nodes);
+        if (ctx->step_graph[slot].exec_tail) {
+            bcnn_cuda_check(bcnn_b200_graph_launch(ctx->step_graph[slot].exec_tail,
+                                                   recorded_now ? 0 : ctx->step_graph[slot].kernels_tail,
+                                                   ctx->stream));
+            bcnn_dp_allreduce_range(net, 0, split);
+        }
+        /* constant learning rate: the update kernels replay as a second graph behind the join */
+        if (ln && ln->optimizer == BCNN_OPTIM_SGD && ln->decay_type == BCNN_LR_DECAY_CONSTANT) {
+            bcnn_dp_before_update(net);
+            if (ctx->update_graph.exec &&
+                (ctx->update_graph.lr != ln->learning_rate || ctx->update_graph.momentum != ln->momentum ||
+                 ctx->update_graph.decay != ln->decay)) {
+                bcnn_b200_graph_destroy(ctx->update_graph.exec);
+                ctx->update_graph.exec = NULL;
+            }
+            int fresh = 0;
+            if (!ctx->update_graph.exec && bcnn_b200_graph_begin(ctx->stream) == 0) {
+                const unsigned long long before = bcnn_b200_launch_count();
+                bcnn_update_nodes(net);
+                ctx->update_graph.kernels = bcnn_b200_launch_count() - before;
+                ctx->update_graph.exec = bcnn_b200_graph_end(ctx->stream);
+                ctx->update_graph.lr = ln->learning_rate;
+                ctx->update_graph.momentum = ln->momentum;
+                ctx->update_graph.decay = ln->decay;
+                fresh = 1;
+            }
+            if (ctx->update_graph.exec) {
+                bcnn_cuda_check(bcnn_b200_graph_launch(ctx->update_graph.exec,
+                                                       fresh ? 0 : ctx->update_graph.kernels, ctx->stream));
+                return 2;
+            }
+        }
+        return 1; /* bcnn_update joins the transfers and steps eagerly */
+    }
     return with_update ? 2 : 1;
 }
 

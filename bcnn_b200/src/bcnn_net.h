@@ -60,10 +60,15 @@ typedef struct bcnn_cuda_context {
      * well under a millisecond). The update kernels join the graph when their scalars cannot
      * change (SGD with a constant learning rate); otherwise (schedules, Adam's bias correction)
      * the update stays eager. Two slots, keyed by the input / label buffers,
-     * because the input pipeline alternates two sets of them. Not used with data parallelism
-     * (the all-reduce lives on a second stream), per-node profiling or extra inputs. */
+     * because the input pipeline alternates two sets of them. Not used with per-node profiling
+     * or extra inputs. Data parallelism: NCCL calls stay outside the graphs (see train_graph). */
     struct {
         void *exec;
+        /* data parallelism: the backward pass of the first `split` nodes as a second graph, so that
+         * the gradients of everything above it travel while it runs (bcnn_net.c:train_graph) */
+        void *exec_tail;
+        unsigned long long kernels_tail;
+        int split;
         const void *input, *label;
         unsigned long long kernels;
         /* with_update: the SGD update kernels are part of the graph (constant learning rate
@@ -72,6 +77,12 @@ typedef struct bcnn_cuda_context {
         int with_update;
         float lr, momentum, decay;
     } step_graph[2];
+    /* data parallelism: the update kernels as their own graph, replayed behind the all-reduce */
+    struct {
+        void *exec;
+        unsigned long long kernels;
+        float lr, momentum, decay;
+    } update_graph;
     unsigned long long fwd_graph_kernels;
     int step_graph_warm, step_graph_next;
     void *fwd_graph;

@@ -565,8 +565,9 @@ def run_own_arm(args):
                 "busbw_gbs": (2.0 * (world - 1) / world) * dp_bytes / (allreduce_ms * 1e-3) / 1e9
                 if allreduce_ms > 0 else None,
                 "note": "gradients of weights and biases in ~25 MB buckets, one aggregated NCCL group "
-                        "each, issued during backward on a second stream inside the step's CUDA graph; "
-                        "ms_alone / busbw: the same buckets back to back with nothing else running"},
+                        "each, issued on a second stream behind the replayed forward + backward graph "
+                        "(BCNN_B200_DP_GRAPH=0: eager steps, transfers overlap backward); ms_alone / "
+                        "busbw: the same buckets back to back with nothing else running"},
             "peaks": peaks,
         }
         if dominant:
