@@ -414,8 +414,8 @@ BCNN_B200_API int bcnn_b200_actbwd_grad_bias_nhwc(float *g_bias, void *dy, const
  * :170-194, then bcnn_eltwise_layer.c:111-127) so that the block's last convolution and its
  * projection shortcut never store their normalised outputs. Per operand: gamma == NULL: plain
  * tensor; mean != NULL: gamma (x - mean) / sqrt(var + 1e-6) + beta; mean == NULL: gamma x + beta
- * (PREDICT, folded statistics). Each branch is rounded to BF16 before the add, like the tensor the
- * unfused path stores. act: NONE, RELU, LRELU. */
+ * (PREDICT, folded statistics). The branches are added in FP32 and the sum rounded once (the unfused
+ * path rounds each branch to BF16 first). act: NONE, RELU, LRELU. */
 BCNN_B200_API int bcnn_b200_bn_add_act_nhwc(const void *xa, const float *mean_a, const float *var_a,
                                             const float *gamma_a, const float *beta_a,
                                             const void *xb, const float *mean_b, const float *var_b,

@@ -352,8 +352,8 @@ def test_resident_thin_first_layer_reads_fp32_nchw():
 @pytest.mark.parametrize("kinds", ["bn+plain", "bn+bn", "plain+bn", "fold+plain"])
 def test_fused_bn_residual_add_matches_the_unfused_kernels(shape, kinds):
     """bn_add_act (normalise one or both operands, add, ReLU in one pass) against bn_apply_nhwc on each
-    operand followed by eltwise_forward_bf16: bit-identical, since every branch is rounded to BF16
-    exactly where the unfused path stores it."""
+    operand followed by eltwise_forward_bf16: within the rounding the unfused path adds by storing
+    each normalised branch as BF16 (1e-2 = 2.5 ulp of the output format)."""
     lib = capi.b200()
     n, c, h, w = shape
     pos = n * h * w
@@ -382,4 +382,5 @@ def test_fused_bn_residual_add_matches_the_unfused_kernels(shape, kinds):
                                              ACT["relu"], None))
     got = dev_zeros(pos * c, 2)
     check(lib.bcnn_b200_bn_add_act_nhwc(*args, got.ptr, pos, c, ACT["relu"], None))
-    assert np.array_equal(got.download(np.uint16), want.download(np.uint16))
+    assert_close(nchw_from_bits(got.download(np.uint16), shape), nchw_from_bits(want.download(np.uint16), shape),
+                 BF16_OUT_TOL, "fused vs unfused")
