@@ -374,6 +374,8 @@ struct FwdParams {
     // store (reduce-add when accumulating) writes the box through the 4-D map tm_dst; 2: per-thread
     // 16-byte stores (scattered strided-dgrad classes, channel tiles that are not 64-aligned).
     int out16;
+    int narrow;      // n_tile <= 64: both epilogue halves share the single 64-channel group
+    int dbg_shift;   // experiment (BCNN_B200_DBG_ROWSHIFT): A tile loaded one position early, descriptor one row late
     int src_c, dst_c, batch;
     int out_w, out_h;     // output plane as the kernel sees it (DIRECT: (H*W, 1))
     int ksh, ksw, pad_h, pad_w, stride;   // tap window (rows x columns) and its leading pads
@@ -537,7 +539,7 @@ conv_tma_fwd_kernel(const __grid_constant__ CUtensorMap tm_src, const __grid_con
                             mbar_expect_tx(fb, tx_bytes);
                             if (NHWC) {
                                 tma_load_4d(smem_u32(a_stage), &tm_src, cb * KC,
-                                            c.w0 * p.stride + kw - p.pad_w,
+                                            c.w0 * p.stride + kw - p.pad_w - (p.dbg_shift ? 1 : 0),
                                             c.h0 * p.stride + kh - p.pad_h, c.img, fb);
                             } else {
                                 for (int a = 0; a < 4; ++a) {  // atom a = (column chunk, row) of the tile
@@ -575,8 +577,12 @@ conv_tma_fwd_kernel(const __grid_constant__ CUtensorMap tm_src, const __grid_con
                     for (int g = 0; g < BLOCK_K / UMMA_K; ++g) {
                         // DIRECT A: K-group g = 8 channel rows = 1 KiB further inside every 4 KiB atom
                         // NHWC A / B: 8 fp32 = 32 bytes further along the 128-byte K row
-                        const uint64_t da = NHWC ? make_desc_sw128(a_addr) + (uint64_t)(2 * g)
-                                                 : make_desc_mn_sw128(a_addr + g * 1024, ATOM_BYTES, 512);
+                        uint64_t da = NHWC ? make_desc_sw128(a_addr) + (uint64_t)(2 * g)
+                                           : make_desc_mn_sw128(a_addr + g * 1024, ATOM_BYTES, 512);
+                        if (NHWC && p.dbg_shift) {   // start one 128-byte row into the tile
+                            da = make_desc_sw128(a_addr + 128) + (uint64_t)(2 * g);
+                            if (p.dbg_shift == 1) da |= (uint64_t)1 << 49;   // matrix base offset = (addr >> 7) & 7
+                        }
                         const uint64_t db = make_desc_sw128(b_addr) + (uint64_t)(2 * g);
                         if (BF16) umma_bf16(d_tmem, da, db, idesc, (kb > 0 || g > 0) ? 1u : 0u);
                         else umma_tf32(d_tmem, da, db, idesc, (kb > 0 || g > 0) ? 1u : 0u);
@@ -636,6 +642,83 @@ conv_tma_fwd_kernel(const __grid_constant__ CUtensorMap tm_src, const __grid_con
                                         (size_t)(ow * p.o_s + p.o_ox)) * (size_t)p.dst_c;
                 uint8_t *sb = reinterpret_cast<uint8_t *>(stage);
                 const int r = q * 32 + lane;
+                if (p.narrow) {
+                    // Narrow tiles (one 64-channel group): both halves work on it, half h on the 32-
+                    // channel chunk h, through ONE staging buffer and one store -- with the group left
+                    // to a single half the epilogue chain of thin layers (the stem, 64-channel 1x1 /
+                    // 3x3, every dgrad into 64 channels) took 2 us per tile with four warps idle.
+                    const int ck = half;
+                    const int ch0 = c.tile_n * n_tile + ck * 32;
+                    uint32_t pkn[16];
+                    if (ck < chunks32) {
+                        uint32_t v[32];
+                        tmem_ld32(d_tmem + (uint32_t)(ck * 32), v);
+                        if (p.bias != nullptr || p.act != ACT_NONE) {
+#pragma unroll
+                            for (int j = 0; j < 32; ++j) {
+                                float val = __uint_as_float(v[j]);
+                                if (p.bias != nullptr && ch0 + j < p.dst_c) val += __ldg(p.bias + ch0 + j);
+                                if (p.act == ACT_RELU) val = fmaxf(val, 0.f);
+                                else if (p.act == ACT_LRELU) val = val > 0 ? val : 0.1f * val;
+                                else val = act_fwd(val, p.act, 0.f);
+                                v[j] = __float_as_uint(val);
+                            }
+                        }
+#pragma unroll
+                        for (int j = 0; j < 16; ++j)
+                            pkn[j] = pack_bf16x2(__uint_as_float(v[2 * j]), __uint_as_float(v[2 * j + 1]));
+                    } else {
+#pragma unroll
+                        for (int j = 0; j < 16; ++j) pkn[j] = 0u;
+                    }
+                    if (p.out16 == 1) {
+                        uint8_t *sbn = smem + (size_t)S * stage_bytes;   // the first staging buffer
+                        if (ew == 0 && lane == 0) bulk_wait_read_all();
+                        named_bar_sync(3, 256);
+                        if (in_box) {
+                            uint8_t *row = sbn + (size_t)r * 128;
+#pragma unroll
+                            for (int j = 0; j < 4; ++j)
+                                *reinterpret_cast<uint4 *>(row + (((half * 4 + j) ^ (r & 7)) << 4)) =
+                                    make_uint4(pkn[4 * j], pkn[4 * j + 1], pkn[4 * j + 2], pkn[4 * j + 3]);
+                        }
+                        fence_proxy_async();
+                        named_bar_sync(3, 256);
+                        if (ew == 0 && lane == 0) {
+                            const int g0 = c.tile_n * n_tile;
+                            if (p.accumulate) tma_reduce_add_4d(&tm_dst, smem_u32(sbn), g0, c.w0, c.h0, c.img);
+                            else tma_store_4d(&tm_dst, smem_u32(sbn), g0, c.w0, c.h0, c.img);
+                            bulk_commit_group();
+                        }
+                    } else if (valid && ck < chunks32) {
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) {
+                            if (ch0 + j * 8 < p.dst_c && ck * 32 + j * 8 < n_tile) {
+                                uint4 o = make_uint4(pkn[4 * j], pkn[4 * j + 1], pkn[4 * j + 2], pkn[4 * j + 3]);
+                                uint4 *gp = reinterpret_cast<uint4 *>(dst16 + ch0 + j * 8);
+                                if (p.accumulate) {
+                                    const uint4 old = *gp;
+                                    const uint32_t ov[4] = {old.x, old.y, old.z, old.w};
+                                    uint32_t nv[4] = {o.x, o.y, o.z, o.w};
+#pragma unroll
+                                    for (int e = 0; e < 4; ++e) {
+                                        const float lo = __uint_as_float(ov[e] << 16) + __uint_as_float(nv[e] << 16);
+                                        const float hi2 = __uint_as_float(ov[e] & 0xffff0000u) +
+                                                          __uint_as_float(nv[e] & 0xffff0000u);
+                                        nv[e] = pack_bf16x2(lo, hi2);
+                                    }
+                                    o = make_uint4(nv[0], nv[1], nv[2], nv[3]);
+                                }
+                                *gp = o;
+                            }
+                        }
+                    }
+                    if (p.stat_partial != nullptr && ck < chunks32) {
+                        uint32_t v[32];
+                        tmem_ld32(d_tmem + (uint32_t)(ck * 32), v);
+                        chunk_col_sums(v, valid, wscr, lane, acc1[0], acc2[0]);
+                    }
+                } else
 #pragma unroll
                 for (int gj = 0; gj < 2; ++gj) {
                     const int gi = half + 2 * gj;
@@ -826,8 +909,10 @@ conv_tma_fwd_kernel(const __grid_constant__ CUtensorMap tm_src, const __grid_con
             const size_t row = (size_t)(blockIdx.x / (uint32_t)p.n_tiles) * 4 + (size_t)q;
 #pragma unroll
             for (int ci = 0; ci < 4; ++ci) {
-                // out16: this half owns the 64-channel groups half, half + 2 (two chunks each)
-                const int ck = p.out16 ? 2 * (half + 2 * (ci >> 1)) + (ci & 1) : half + 2 * ci;
+                // out16: this half owns the 64-channel groups half, half + 2 (two chunks each); narrow
+                // tiles (n_tile <= 64): chunk `half`, kept in slot 0
+                int ck = p.out16 ? 2 * (half + 2 * (ci >> 1)) + (ci & 1) : half + 2 * ci;
+                if (p.out16 && p.narrow) ck = ci == 0 ? half : chunks32;
                 const int ch = (int)tile_n * n_tile + ck * 32 + lane;
                 if (ck < chunks32 && lane < n_tile - ck * 32 && ch < p.dst_c) {
                     p.stat_partial[(row * 2 + 0) * p.dst_c + ch] = acc1[ci];
@@ -1164,6 +1249,11 @@ int run_fwd(const FwdGeom &g, const FwdPlan &pl, const void *src, const uint8_t 
     p.d_th = FastDiv((uint32_t)pl.th);
     p.tstore = pl.tstore ? 1 : 0;
     p.out16 = pl.out16;
+    p.narrow = (pl.out16 && pl.n_tile <= 64 && !env_off("BCNN_B200_NO_NARROW")) ? 1 : 0;
+    {
+        const char *e = getenv("BCNN_B200_DBG_ROWSHIFT");
+        p.dbg_shift = (e && pl.nhwc && g.ksh == 1 && g.sh == 1) ? atoi(e) : 0;
+    }
     p.tile_pos = pl.tile_pos;
     CUtensorMap tm_dst = tm;   // placeholder when the epilogue stores from registers
     if (pl.tstore &&
@@ -1866,7 +1956,7 @@ im2col_rows_bf16_kernel(const float *__restrict__ x, uint4 *__restrict__ col, in
     int *koff = reinterpret_cast<int *>(sm + (size_t)nrows * wp);
     const int oh = blockIdx.x % ho, n = blockIdx.x / ho;
     const int t = threadIdx.x;
-    for (int k = t; k < kp8 * 8; k += 256) {
+    for (int k = t; k < kp8 * 8; k += (int)blockDim.x) {
         int off = -1;
         if (k < kdim) {
             const int ci = k / (ks * ks), r = k - ci * ks * ks, kh = r / ks, kw = r - kh * ks;
@@ -1875,7 +1965,7 @@ im2col_rows_bf16_kernel(const float *__restrict__ x, uint4 *__restrict__ col, in
         koff[(k & 7) * kp8 + (k >> 3)] = off;
     }
     const int ih0 = oh * stride - pad;
-    for (int i = t; i < nrows * wp; i += 256) {
+    for (int i = t; i < nrows * wp; i += (int)blockDim.x) {
         const int r = i / wp, cpos = i - r * wp;
         const int ci = r / ks, kh = r - ci * ks;
         const int ih = ih0 + kh, iw = cpos - pad;
@@ -1885,18 +1975,22 @@ im2col_rows_bf16_kernel(const float *__restrict__ x, uint4 *__restrict__ col, in
     }
     __syncthreads();
     uint4 *out = col + ((size_t)n * ho + oh) * wo * kp8;
-    const int chunks = wo * kp8;
-    for (int i = t; i < chunks; i += 256) {
-        const int ow = i / kp8, q = i - ow * kp8;
-        const int base = ow * stride;
-        float v[8];
+    // thread t owns chunk q = t % kp8 of every col row it writes (the block is a multiple of kp8 wide):
+    // its 8 patch offsets live in registers, the loop walks output columns
+    const int lanes = (int)blockDim.x / kp8;       // output columns per pass
+    const int q = t % kp8, ow0 = t / kp8;
+    if (ow0 < lanes) {
+        int off[8];
 #pragma unroll
-        for (int e = 0; e < 8; ++e) {
-            const int off = koff[e * kp8 + q];
-            v[e] = off >= 0 ? rows[off + base] : 0.f;
+        for (int e = 0; e < 8; ++e) off[e] = koff[e * kp8 + q];
+        for (int ow = ow0; ow < wo; ow += lanes) {
+            const int base = ow * stride;
+            float v[8];
+#pragma unroll
+            for (int e = 0; e < 8; ++e) v[e] = off[e] >= 0 ? rows[off[e] + base] : 0.f;
+            out[(size_t)ow * kp8 + q] = make_uint4(pack_bf16x2(v[0], v[1]), pack_bf16x2(v[2], v[3]),
+                                                   pack_bf16x2(v[4], v[5]), pack_bf16x2(v[6], v[7]));
         }
-        out[i] = make_uint4(pack_bf16x2(v[0], v[1]), pack_bf16x2(v[2], v[3]), pack_bf16x2(v[4], v[5]),
-                            pack_bf16x2(v[6], v[7]));
     }
 }
 
@@ -1912,7 +2006,10 @@ int launch_im2col(const bcnn_b200_conv_desc *d, const float *x, void *col, bool 
                 if (e != cudaSuccess) return (int)e;
                 attr_set = true;
             }
-            im2col_rows_bf16_kernel<<<d->batch * d->ho, 256, smem, st>>>(
+            const int kp8 = kp / 8;
+            const int threads = kp8 <= 256 ? (256 / kp8) * kp8 : 256;
+            if (kp8 > 256) return (int)cudaErrorInvalidValue;
+            im2col_rows_bf16_kernel<<<d->batch * d->ho, threads, smem, st>>>(
                 x, reinterpret_cast<uint4 *>(col), d->cin, d->h, d->w, d->ksize, d->stride, d->pad, d->cin * kk,
                 kp / 8, d->ho, d->wo);
             return launched();

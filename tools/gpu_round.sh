@@ -1,36 +1,58 @@
 #!/bin/bash
-# One gpurun call: GPU parity suite, bench line, per-layer conv sweep, ncu launch list and
-# full captures of the dominant kernels.  Usage (on the GPU box): bash tools/gpu_round.sh TAG [parts]
-# parts: any of t(ests) b(ench) s(weep) l(aunch list) n(cu full)   default: tbsln
+# One gpurun call that produces the round's evidence: GPU parity suite, smoke, bench line, per-layer
+# convolution sweep, per-node profile, ncu launch list of one eager step and `ncu --set full` captures
+# of the dominant kernels.   Usage (on the GPU box): bash tools/gpu_round.sh TAG [parts]
+# parts: any of t(ests) b(ench) s(weep) p(er-node) l(aunch list) n(cu full)   default: tbspln
 TAG=${1:-rX}
-PARTS=${2:-tbsln}
+PARTS=${2:-tbspln}
 OUT=gpurun_out/$TAG
 mkdir -p $OUT
 nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm,power.draw --format=csv > $OUT/smi.txt 2>&1
 if [[ $PARTS == *t* ]]; then
-  timeout 900 python -m pytest tests -m gpu -x -q > $OUT/gpu_tests.log 2>&1
+  timeout 1500 python -m pytest tests -m gpu -q > $OUT/gpu_tests.log 2>&1
   echo "tests rc=$?" >> $OUT/gpu_tests.log
   tail -3 $OUT/gpu_tests.log
+  timeout 300 python -c "import __graft_entry__ as g; g.smoke()" > $OUT/smoke.log 2>&1
+  tail -1 $OUT/smoke.log
 fi
 if [[ $PARTS == *b* ]]; then
   timeout 900 python bench.py > $OUT/bench_n1.json 2> $OUT/bench_n1.err
-  echo "bench rc=$?"; head -c 600 $OUT/bench_n1.json; echo
+  echo "bench rc=$?"; head -c 300 $OUT/bench_n1.json; echo
 fi
 if [[ $PARTS == *s* ]]; then
-  timeout 600 python tools/conv_sweep.py 256 5 > $OUT/conv_sweep_b256.txt 2>&1
-  tail -4 $OUT/conv_sweep_b256.txt
+  timeout 600 python tools/resident_sweep.py 256 5 "" sdw > $OUT/resident_sweep_b256.txt 2>&1
+  tail -5 $OUT/resident_sweep_b256.txt
+fi
+if [[ $PARTS == *p* ]]; then
+  timeout 300 python tools/node_profile.py resnet50 256 resident > $OUT/nodes_resident_b256.txt 2>&1
+  tail -1 $OUT/nodes_resident_b256.txt
 fi
 if [[ $PARTS == *l* ]]; then
-  timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none --csv \
-     --log-file $OUT/launches.csv python tools/profile_step.py resnet50 64 2 > $OUT/launches.log 2>&1
-  python tools/summarize_launches.py $OUT/launches.csv > $OUT/launches_resnet50_b64.md 2>&1
-  head -20 $OUT/launches_resnet50_b64.md
+  BCNN_B200_GRAPHS=0 timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none --csv \
+     --log-file $OUT/launches.csv python tools/profile_step.py resnet50 256 2 resident > $OUT/launches.log 2>&1
+  N=$(python -c "
+import csv
+rows=[r for r in csv.DictReader(l for l in open('$OUT/launches.csv') if l.startswith('\"')) if r.get('Metric Name')=='gpu__time_duration.sum']
+print(len(rows)//2)")
+  python tools/summarize_launches.py $OUT/launches.csv $N > $OUT/launches_resident_b256.md 2>&1
+  head -16 $OUT/launches_resident_b256.md
 fi
 if [[ $PARTS == *n* ]]; then
-  for K in conv_tma_fwd_kernel conv_tma_wgrad_kernel bn_bwd_apply_kernel bn_apply_kernel; do
-    timeout 600 ncu --set full --clock-control none --import-source on -k regex:$K -s 20 -c 2 \
-       -f -o $OUT/full_$K python tools/profile_step.py resnet50 64 1 > $OUT/full_$K.log 2>&1
-    echo "ncu $K rc=$?"
-  done
+  # one launch of the main kernel of a roofline entry per capture: "entry name|shape|pass|kernel regex"
+  while IFS='|' read -r NAME SHAPE PASS KERN; do
+    STEM=$(echo "$NAME" | tr ' /<>@,+-' '_________' | tr -s '_')
+    timeout 400 ncu --set full --clock-control none --import-source on -k regex:$KERN -s 3 -c 1 -f \
+       -o $OUT/full_$STEM python tools/resident_sweep.py 256 2 "$SHAPE" $PASS > $OUT/full_$STEM.log 2>&1
+    echo "ncu $NAME rc=$?"
+    echo "$NAME=$OUT/full_$STEM.ncu-rep" >> $OUT/ncu_entries.txt
+  done <<'EOF'
+conv_fprop 1x1/1 64->256 @56|64,56,256,1,1,0|s|conv_tma_fwd
+conv_fprop 3x3/1 64->64 @56|64,56,64,3,1,1|s|conv_tma_fwd
+conv_fprop 3x3/1 256->256 @14|256,14,256,3,1,1|s|conv_tma_fwd
+conv_dgrad 1x1/1 256->64 @56|256,56,64,1,1,0|d|conv_tma_fwd
+conv_wgrad 3x3/1 256->256 @14|256,14,256,3,1,1|w|conv_tma_wgrad
+conv_wgrad 1x1/1 64->256 @56|64,56,256,1,1,0|w|conv_tma_wgrad
+conv_wgrad 3x3/1 64->64 @56|64,56,64,3,1,1|w|conv_tma_wgrad
+EOF
 fi
-ls -la $OUT
+ls -la $OUT | head -40
