@@ -374,6 +374,15 @@ struct FwdParams {
     // store (reduce-add when accumulating) writes the box through the 4-D map tm_dst; 2: per-thread
     // 16-byte stores (scattered strided-dgrad classes, channel tiles that are not 64-aligned).
     int out16;
+    // halo mode (resident, stride 1, k > 1): the input patch of a tile -- (th + ksh - 1) rows of
+    // vw = tw + ksw - 1 columns -- is loaded ONCE per 64-channel block and the taps are MMAs whose A
+    // descriptor starts kh * vw + kw rows into it (tile row m = vh * vw + vcol; columns >= tw are
+    // junk the epilogue skips). Activation tiles (A ring, sa slots) and weight tap tiles (B ring, sb
+    // slots) travel through separate rings; b_resident: every weight tile of the layer fits the B ring
+    // and is loaded once per CTA.
+    int halo, vw, sa, sb, b_resident;
+    uint32_t a_slot_bytes, ring_bytes;   // ring_bytes: everything in front of the staging buffers
+    FastDiv d_vw;
     int narrow;      // n_tile <= 64: both epilogue halves share the single 64-channel group
     int dbg_shift;   // experiment (BCNN_B200_DBG_ROWSHIFT): A tile loaded one position early, descriptor one row late
     int src_c, dst_c, batch;
@@ -400,7 +409,8 @@ constexpr int FWD_THREADS = 64 + 32 * FWD_EPI_WARPS;
 constexpr int OUT_STAGE_BYTES = TILE_M * 32 * 4;
 constexpr int STAT_SCRATCH_BYTES = 8 * 32 * 36 * 4;   // chunk_col_sums scratch of the 8 epilogue warps
 // alignment slack, barriers, output staging, statistics scratch
-constexpr int FWD_EXTRA_SMEM = 1024 + 256 + 2 * OUT_STAGE_BYTES + STAT_SCRATCH_BYTES;
+constexpr int FWD_BAR_BYTES = 512;
+constexpr int FWD_EXTRA_SMEM = 1024 + FWD_BAR_BYTES + 2 * OUT_STAGE_BYTES + STAT_SCRATCH_BYTES;
 
 struct TileCoord { int tile_n, m_tile, img, w0, h0; };
 
@@ -495,17 +505,21 @@ conv_tma_fwd_kernel(const __grid_constant__ CUtensorMap tm_src, const __grid_con
     const int n_tile = p.n_tile;
     const int b_stage_bytes = n_tile * BLOCK_K * 4;
     const int stage_bytes = A_STAGE_BYTES + b_stage_bytes;
-    // [S stages][2 output staging buffers (1 KiB aligned)][barriers]
-    uint64_t *bars = reinterpret_cast<uint64_t *>(smem + (size_t)S * stage_bytes + 2 * OUT_STAGE_BYTES);
-    uint64_t *full = bars, *empty = bars + S, *acc_full = bars + 2 * S, *acc_empty = bars + 2 * S + 2;
-    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bars + 2 * S + 4);
+    // [operand ring(s)][2 output staging buffers (1 KiB aligned)][barriers][statistics scratch]
+    const size_t ring = p.ring_bytes;
+    uint64_t *bars = reinterpret_cast<uint64_t *>(smem + ring + 2 * OUT_STAGE_BYTES);
+    // plain: full[S], empty[S]; halo: fullA[sa], emptyA[sa], fullB[sb], emptyB[sb]
+    const int nring = p.halo ? 2 * (p.sa + p.sb) : 2 * S;
+    uint64_t *full = bars, *empty = bars + S, *acc_full = bars + nring, *acc_empty = bars + nring + 2;
+    uint64_t *full_a = bars, *empty_a = bars + p.sa, *full_b = bars + 2 * p.sa, *empty_b = bars + 2 * p.sa + p.sb;
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bars + nring + 4);
 
     const int t = threadIdx.x, warp = t >> 5, lane = t & 31;
     const uint32_t acc_cols = n_tile <= 32 ? 32 : (n_tile <= 64 ? 64 : (n_tile <= 128 ? 128 : 256));
     const uint32_t tmem_cols = 2 * acc_cols;
 
     if (t == 0) {
-        for (int i = 0; i < 2 * S; ++i) mbar_init(smem_u32(bars + i), 1);
+        for (int i = 0; i < nring; ++i) mbar_init(smem_u32(bars + i), 1);
         mbar_init(smem_u32(acc_full), 1);
         mbar_init(smem_u32(acc_full + 1), 1);
         mbar_init(smem_u32(acc_empty), FWD_EPI_WARPS);
@@ -525,6 +539,33 @@ conv_tma_fwd_kernel(const __grid_constant__ CUtensorMap tm_src, const __grid_con
             // ---------------- TMA producer
             uint32_t it = 0;
             const uint32_t tx_bytes = p.a_bytes + (uint32_t)b_stage_bytes;
+            if (NHWC && p.halo) {
+                uint8_t *ring_b = smem + (size_t)p.sa * p.a_slot_bytes;
+                uint32_t ita = 0, itb = 0;
+                const int taps = p.ksh * p.ksw;
+                bool b_loaded = false;
+                for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+                    const TileCoord c = decode_tile<NHWC>(p, tile);
+                    const uint8_t *wtile = p.wpack + (size_t)c.tile_n * p.k_blocks * b_stage_bytes;
+                    for (int cb = 0; cb < p.kc_blocks; ++cb, ++ita) {
+                        const uint32_t sa = ita % (uint32_t)p.sa;
+                        mbar_wait(smem_u32(empty_a + sa), ((ita / (uint32_t)p.sa) & 1) ^ 1);
+                        mbar_expect_tx(smem_u32(full_a + sa), p.a_bytes);
+                        tma_load_4d(smem_u32(smem + (size_t)sa * p.a_slot_bytes), &tm_src, cb * KC,
+                                    c.w0 - p.pad_w, c.h0 - p.pad_h, c.img, smem_u32(full_a + sa));
+                        if (p.b_resident && b_loaded) continue;
+                        for (int tap = 0; tap < taps; ++tap, ++itb) {
+                            const uint32_t sb = itb % (uint32_t)p.sb;
+                            mbar_wait(smem_u32(empty_b + sb), ((itb / (uint32_t)p.sb) & 1) ^ 1);
+                            mbar_expect_tx(smem_u32(full_b + sb), (uint32_t)b_stage_bytes);
+                            bulk_copy_g2s(smem_u32(ring_b + (size_t)sb * b_stage_bytes),
+                                          wtile + (size_t)(tap * p.kc_blocks + cb) * b_stage_bytes,
+                                          (uint32_t)b_stage_bytes, smem_u32(full_b + sb));
+                        }
+                    }
+                    b_loaded = true;
+                }
+            } else
             for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
                 const TileCoord c = decode_tile<NHWC>(p, tile);
                 const uint8_t *wtile = p.wpack + (size_t)c.tile_n * p.k_blocks * b_stage_bytes;
@@ -561,12 +602,50 @@ conv_tma_fwd_kernel(const __grid_constant__ CUtensorMap tm_src, const __grid_con
             // ---------------- MMA issuer
             const uint32_t idesc = BF16 ? make_idesc_bf16(TILE_M, n_tile, 0, 0)
                                         : make_idesc_tf32(TILE_M, n_tile, NHWC ? 0 : 1, 0);
-            uint32_t it = 0, local = 0;
+            uint32_t it = 0, itb_ = 0, local = 0;
             for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++local) {
                 const uint32_t buf = local & 1, use = local >> 1;
                 mbar_wait(smem_u32(acc_empty + buf), (use & 1) ^ 1);  // epilogue drained this buffer
                 tc_fence_after();
                 const uint32_t d_tmem = tmem_base + buf * acc_cols;
+                if (NHWC && p.halo) {
+                    // (function-local state of the halo rings lives in it = A counter, itb_ = B counter)
+                    const int taps = p.ksh * p.ksw;
+                    const uint32_t ring_b = smem_u32(smem + (size_t)p.sa * p.a_slot_bytes);
+                    for (int cb = 0; cb < p.kc_blocks; ++cb, ++it) {
+                        const uint32_t sa = it % (uint32_t)p.sa;
+                        mbar_wait(smem_u32(full_a + sa), (it / (uint32_t)p.sa) & 1);
+                        tc_fence_after();
+                        const uint32_t a_base = smem_u32(smem + (size_t)sa * p.a_slot_bytes);
+                        for (int tap = 0; tap < taps; ++tap) {
+                            uint32_t sb;
+                            if (p.b_resident) {
+                                sb = (uint32_t)(cb * taps + tap);
+                                if (local == 0) {   // first tile of this CTA: the tile arrives now
+                                    mbar_wait(smem_u32(full_b + sb), 0);
+                                    tc_fence_after();
+                                }
+                            } else {
+                                sb = itb_ % (uint32_t)p.sb;
+                                mbar_wait(smem_u32(full_b + sb), (itb_ / (uint32_t)p.sb) & 1);
+                                tc_fence_after();
+                            }
+                            const int kh = tap / p.ksw, kw = tap - kh * p.ksw;
+                            const uint32_t a_addr = a_base + (uint32_t)(kh * p.vw + kw) * 128u;
+                            const uint32_t b_addr = ring_b + sb * (uint32_t)b_stage_bytes;
+#pragma unroll
+                            for (int g = 0; g < BLOCK_K / UMMA_K; ++g)
+                                umma_bf16(d_tmem, make_desc_sw128(a_addr) + (uint64_t)(2 * g),
+                                          make_desc_sw128(b_addr) + (uint64_t)(2 * g), idesc,
+                                          (cb > 0 || tap > 0 || g > 0) ? 1u : 0u);
+                            if (!p.b_resident) {
+                                umma_commit(smem_u32(empty_b + sb));
+                                ++itb_;
+                            }
+                        }
+                        umma_commit(smem_u32(empty_a + sa));
+                    }
+                } else
                 for (int kb = 0; kb < p.k_blocks; ++kb, ++it) {
                     const uint32_t s = it % (uint32_t)S;
                     mbar_wait(smem_u32(full + s), (it / (uint32_t)S) & 1);
@@ -602,8 +681,8 @@ conv_tma_fwd_kernel(const __grid_constant__ CUtensorMap tm_src, const __grid_con
         float acc1[4] = {0.f, 0.f, 0.f, 0.f}, acc2[4] = {0.f, 0.f, 0.f, 0.f};
         // bulk-store epilogue: staging buffer of this half, position of this thread's row in it
         const int hw = ew & 3;   // warp within the half
-        float *stage = reinterpret_cast<float *>(smem + (size_t)S * stage_bytes + (size_t)half * OUT_STAGE_BYTES);
-        float *wscr = reinterpret_cast<float *>(smem + (size_t)S * stage_bytes + 2 * OUT_STAGE_BYTES + 256) +
+        float *stage = reinterpret_cast<float *>(smem + ring + (size_t)half * OUT_STAGE_BYTES);
+        float *wscr = reinterpret_cast<float *>(smem + ring + 2 * OUT_STAGE_BYTES + FWD_BAR_BYTES) +
                       (size_t)ew * STAT_WARP_FLOATS;
         const int sub_stride = p.tn * 16 * p.tile_pos;   // floats of one 16-channel sub-box
         uint32_t stores = 0;                              // bulk stores issued by this half so far
@@ -611,7 +690,11 @@ conv_tma_fwd_kernel(const __grid_constant__ CUtensorMap tm_src, const __grid_con
         const int chunks32 = (n_tile + 31) / 32;
         // position of this thread's tile row relative to the tile origin
         int rw, rh, rn;
-        if (NHWC) {
+        if (NHWC && p.halo) {   // virtual rows of vw columns; columns >= tw and rows >= th are junk
+            uint32_t m = (uint32_t)(q * 32 + lane), h_, w_;
+            p.d_vw.divmod(m, h_, w_);
+            rw = (int)w_; rh = (int)h_; rn = 0;
+        } else if (NHWC) {
             uint32_t m = (uint32_t)(q * 32 + lane), t2, w_, n_, h_;
             p.d_tw.divmod(m, t2, w_);
             p.d_th.divmod(t2, n_, h_);
@@ -620,7 +703,7 @@ conv_tma_fwd_kernel(const __grid_constant__ CUtensorMap tm_src, const __grid_con
             const int wci = q / p.rows;
             rw = wci * 32 + lane; rh = q - wci * p.rows; rn = 0;
         }
-        const bool in_box = NHWC ? (rn < p.tn) : (rh == 0);
+        const bool in_box = (NHWC && p.halo) ? (rw < p.tw && rh < p.th) : (NHWC ? (rn < p.tn) : (rh == 0));
         const int row_off = NHWC ? rn * 16 * p.tile_pos + rh * p.tw + rw : rw;
         uint32_t local = 0;
         for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++local) {
@@ -628,7 +711,7 @@ conv_tma_fwd_kernel(const __grid_constant__ CUtensorMap tm_src, const __grid_con
             const uint32_t buf = local & 1, use = local >> 1;
             const int ow = c.w0 + rw, oh = c.h0 + rh, img = c.img + rn;
             bool valid = ow < p.out_w && oh < p.out_h && img < p.batch;
-            if (NHWC) valid = valid && rn < p.tn;
+            if (NHWC) valid = valid && in_box;
             float *dst = p.dst + (size_t)img * p.dst_c * plane +
                          (size_t)(oh * p.o_s + p.o_oy) * p.dst_w + (ow * p.o_s + p.o_ox);
             if (lane == 0) mbar_wait(smem_u32(acc_full + buf), use & 1);
@@ -641,7 +724,8 @@ conv_tma_fwd_kernel(const __grid_constant__ CUtensorMap tm_src, const __grid_con
                                        ((size_t)img * plane + (size_t)(oh * p.o_s + p.o_oy) * p.dst_w +
                                         (size_t)(ow * p.o_s + p.o_ox)) * (size_t)p.dst_c;
                 uint8_t *sb = reinterpret_cast<uint8_t *>(stage);
-                const int r = q * 32 + lane;
+                // row of the staged box: halo tiles drop their junk columns (box rows are tw wide)
+                const int r = p.halo ? rh * p.tw + rw : q * 32 + lane;
                 if (p.narrow) {
                     // Narrow tiles (one 64-channel group): both halves work on it, half h on the 32-
                     // channel chunk h, through ONE staging buffer and one store -- with the group left
@@ -672,7 +756,7 @@ conv_tma_fwd_kernel(const __grid_constant__ CUtensorMap tm_src, const __grid_con
                         for (int j = 0; j < 16; ++j) pkn[j] = 0u;
                     }
                     if (p.out16 == 1) {
-                        uint8_t *sbn = smem + (size_t)S * stage_bytes;   // the first staging buffer
+                        uint8_t *sbn = smem + ring;   // the first staging buffer
                         if (ew == 0 && lane == 0) bulk_wait_read_all();
                         named_bar_sync(3, 256);
                         if (in_box) {
@@ -953,6 +1037,9 @@ struct FwdPlan {
     size_t shadow_bytes, wpack_bytes, smem_bytes;
     bool tstore;             // bulk tensor-store epilogue (tile = tile_pos consecutive positions)
     int out16;               // BF16 NHWC result: 1 bulk tensor store, 2 per-thread stores (FwdParams)
+    bool halo;               // halo tiles (FwdParams.halo)
+    int vw, ph, sa, sb, b_resident;
+    uint32_t a_slot_bytes, ring_bytes;
     int tile_pos;
     int stat_rows;           // rows of the fused batch-norm partials: 4 per position tile
     size_t stat_bytes;
@@ -1079,6 +1166,73 @@ bool plan_fwd(const FwdGeom &g, FwdPlan *pl) {
     pl->stages = stages;
     pl->wpack_bytes = align256((size_t)pl->n_tiles * pl->k_blocks * n * BLOCK_K * sizeof(float));
     pl->smem_bytes = (size_t)stages * stage + FWD_EXTRA_SMEM;
+    pl->ring_bytes = (uint32_t)((size_t)stages * stage);
+    pl->halo = false;
+    pl->vw = pl->ph = pl->sa = pl->sb = pl->b_resident = 0;
+    pl->a_slot_bytes = 0;
+    // Halo tiles: resident 3x3-class layers (any k > 1 at stride 1, BF16), see FwdParams.halo.
+    // EXPERIMENTAL, opt-in (BCNN_B200_HALO=1): parity-green (tests/test_nhwc_bf16_gpu.py passes with
+    // it), L2 -> SM traffic halves (ncu: 1.45 GB -> 0.74 GB on 3x3 64->64 @56, 0.23 GB with resident
+    // weights), but the kernel is 25-30 % SLOWER than the per-tap route on every ResNet-50 3x3 shape
+    // (0.20 vs 0.19 ms, 0.134 vs 0.103, 0.090 vs 0.072; gpurun r2w) whatever the ring depths: the
+    // per-tap route was not bound by that traffic after all. Kept for the next round's profiling.
+    static const bool halo_on = [] { const char *e = getenv("BCNN_B200_HALO"); return e && e[0] == '1'; }();
+    if (halo_on && g.resident && pl->bf16 && g.stride == 1 && g.o_s == 1 && g.ksh * g.ksw > 1 &&
+        g.ksw - 1 + 8 <= 128 && !env_off("BCNN_B200_NO_HALO")) {
+        int tw = g.dw;
+        if (tw + g.ksw - 1 > 128) {   // wide planes: balanced column segments
+            const int segs = ceil_div(g.dw, 128 - (g.ksw - 1));
+            tw = ceil_div(g.dw, segs);
+        }
+        const int vw = tw + g.ksw - 1;
+        int th = 128 / vw;
+        if (th > g.dh) th = g.dh;
+        if (th >= 1) {
+            const int tiles_h = ceil_div(g.dh, th);
+            th = ceil_div(g.dh, tiles_h);
+        }
+        // one image per tile: small planes (7 x 7) fill the 128 MMA rows better when the plain route
+        // stacks several images into a tile
+        const char *e_nmax = getenv("BCNN_B200_HALO_NMAX");
+        const int halo_nmax = e_nmax ? atoi(e_nmax) : 256;
+        if (th >= 1 && th * vw >= 96 && n <= halo_nmax) {
+            const int ph = th + g.ksh - 1;
+            const int reach = 128 + (g.ksh - 1) * vw + g.ksw - 1;   // rows the descriptors may touch
+            const int rows = vw * ph > reach ? vw * ph : reach;
+            const uint32_t a_slot = (uint32_t)((rows * 128 + 1023) & ~1023);
+            const uint32_t b_slot = (uint32_t)n * 128u;
+            // ring split: the activation patches need depth (a patch is one tile's worth of MMAs, its
+            // load latency must hide behind the tiles in front of it), the weight tap tiles need at
+            // least four slots; weights stay resident when everything still fits
+            const long long avail = 227 * 1024 - FWD_EXTRA_SMEM;
+            const int taps_all = g.ksh * g.ksw * pl->kc_blocks;
+            const char *e_sa = getenv("BCNN_B200_HALO_SA"), *e_sb = getenv("BCNN_B200_HALO_SB");
+            int sa = e_sa ? atoi(e_sa) : 3;
+            bool resident_b = pl->n_tiles == 1 && (long long)sa * a_slot + (long long)taps_all * b_slot <= avail &&
+                              !env_off("BCNN_B200_HALO_NO_RESIDENT_B");
+            int sb = resident_b ? taps_all : (int)((avail - (long long)sa * a_slot) / b_slot);
+            if (!resident_b && sb > 8) sb = 8;
+            if (e_sb && !resident_b) sb = atoi(e_sb);
+            while (!resident_b && sb < 4 && sa > 2) {   // trade activation depth for weight depth
+                --sa;
+                sb = (int)((avail - (long long)sa * a_slot) / b_slot);
+            }
+            if ((long long)sa * a_slot + (long long)sb * b_slot > avail) sb = 0;
+            // the box must fit the TMA limits and the rings must hold a few tap tiles
+            if (sb >= 3 && vw <= 256 && ph <= 256 && 2 * (sa + sb) + 5 <= FWD_BAR_BYTES / 8) {
+                pl->halo = true;
+                pl->vw = vw; pl->ph = ph; pl->sa = sa; pl->sb = sb; pl->b_resident = resident_b ? 1 : 0;
+                pl->a_slot_bytes = a_slot;
+                pl->tw = tw; pl->th = th; pl->tn = 1;
+                pl->tiles_w = ceil_div(g.dw, tw); pl->tiles_h = ceil_div(g.dh, th); pl->tiles_b = g.batch;
+                pl->a_bytes = (uint32_t)(vw * ph * 128);
+                pl->tile_pos = tw * th;
+                pl->ring_bytes = (uint32_t)(sa * a_slot + sb * b_slot);
+                pl->smem_bytes = (size_t)pl->ring_bytes + FWD_EXTRA_SMEM;
+                pl->out16 = (g.dst_w == g.dw && g.dst_c % 64 == 0 && !env_off("BCNN_B200_NO_TSTORE")) ? 1 : 2;
+            }
+        }
+    }
     const long long total = (long long)pl->n_tiles * pl->tiles_w * pl->tiles_h * pl->tiles_b;
     if (total >= (1LL << 31)) return false;
     // fused statistics: grid = a multiple of n_tiles (0 rows: more channel tiles than SMs, no fusion)
@@ -1221,8 +1375,8 @@ int run_fwd(const FwdGeom &g, const FwdPlan &pl, const void *src, const uint8_t 
     float *dst = reinterpret_cast<float *>(dst_any);
     CUtensorMap tm;
     if (pl.nhwc) {
-        if (!make_map_nhwc(&tm, src, g.src_c, g.sw, g.sh, g.batch, pl.tw, pl.th, pl.tn, g.stride, false,
-                           pl.bf16))
+        const int bw = pl.halo ? pl.vw : pl.tw, bh = pl.halo ? pl.ph : pl.th;
+        if (!make_map_nhwc(&tm, src, g.src_c, g.sw, g.sh, g.batch, bw, bh, pl.tn, g.stride, false, pl.bf16))
             return (int)cudaErrorInvalidValue;
     } else if (!make_map_nchw(&tm, reinterpret_cast<const float *>(src), pl.view_w, pl.view_h, g.src_c,
                               g.batch, BLOCK_K, true)) {
@@ -1250,6 +1404,10 @@ int run_fwd(const FwdGeom &g, const FwdPlan &pl, const void *src, const uint8_t 
     p.tstore = pl.tstore ? 1 : 0;
     p.out16 = pl.out16;
     p.narrow = (pl.out16 && pl.n_tile <= 64 && !env_off("BCNN_B200_NO_NARROW")) ? 1 : 0;
+    p.halo = pl.halo ? 1 : 0;
+    p.vw = pl.vw; p.sa = pl.sa; p.sb = pl.sb; p.b_resident = pl.b_resident;
+    p.a_slot_bytes = pl.a_slot_bytes; p.ring_bytes = pl.ring_bytes;
+    p.d_vw = FastDiv((uint32_t)(pl.vw > 0 ? pl.vw : 1));
     {
         const char *e = getenv("BCNN_B200_DBG_ROWSHIFT");
         p.dbg_shift = (e && pl.nhwc && g.ksh == 1 && g.sh == 1) ? atoi(e) : 0;
