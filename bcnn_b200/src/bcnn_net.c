@@ -43,6 +43,7 @@ bcnn_status bcnn_net_create_cuda_context(bcnn_net *net) {
     ctx->conv_math = BCNN_B200_MATH_TC_BF16;
     if (math && (math[0] == 'f' || math[0] == 'F' || math[0] == '0')) ctx->conv_math = BCNN_B200_MATH_FP32;
     else if (math && (math[0] == 't' || math[0] == 'T' || math[0] == '1')) ctx->conv_math = BCNN_B200_MATH_TC;
+    ctx->conv_math_explicit = math && math[0];
     /* Batch-correct residual semantics by default; the reference's two residual bugs (H2, H3) are
      * replicated only on request (parity tests): BCNN_B200_REFERENCE_QUIRKS=1 or
      * bcnn_b200_set_reference_quirks(net, 1). */
@@ -163,8 +164,36 @@ bcnn_status bcnn_set_mode(bcnn_net *net, bcnn_mode mode) {
     return BCNN_SUCCESS;
 }
 
+/* Resident tensors pay when the layers between convolutions know the format. A net with nodes that
+ * only read FP32 NCHW activations at full spatial size (depthwise convolution, stand-alone batch
+ * norm / activation, concat, upsample, yolo: MobileNet, YOLOv3-tiny, the mnist example) would convert
+ * around every one of them, so unless the caller chose a mode such a net stays on FP32-tensor
+ * tensor-core math (the round-1 layout). */
+static void choose_default_math(bcnn_net *net) {
+    bcnn_cuda_context *ctx = bcnn_ctx(net);
+    if (ctx->conv_math_explicit || ctx->conv_math != BCNN_B200_MATH_TC_BF16) return;
+    for (int i = 0; i < net->num_nodes; ++i) {
+        const bcnn_node *node = &net->nodes[i];
+        const bcnn_tensor *src = node->num_src > 0 ? &net->tensors[node->src[0]] : NULL;
+        const int spatial = src && src->h * src->w > 1;
+        switch (node->type) {
+            case BCNN_LAYER_CONV2D:
+            case BCNN_LAYER_MAXPOOL:
+            case BCNN_LAYER_AVGPOOL:
+            case BCNN_LAYER_ELTWISE:
+                break;
+            default:
+                if (spatial) {
+                    ctx->conv_math = BCNN_B200_MATH_TC;
+                    return;
+                }
+        }
+    }
+}
+
 bcnn_status bcnn_compile_net(bcnn_net *net) {
     bcnn_cuda_context *ctx = bcnn_ctx(net);
+    choose_default_math(net);
     forward_graph_drop(ctx); /* buffers are reallocated below */
     /* (re)allocate the input tensor, with an eager pinned host mirror the caller fills */
     BCNN_CHECK_STATUS(bcnn_tensor_allocate(&net->tensors[0], net->mode));
@@ -481,6 +510,7 @@ float bcnn_net_grad_post_scale(bcnn_net *net, float momentum) {
 
 void bcnn_b200_set_conv_math(bcnn_net *net, int math) {
     bcnn_cuda_context *ctx = bcnn_ctx(net);
+    ctx->conv_math_explicit = 1;
     if (ctx->conv_math == math) return;
     /* leaving the resident mode: every tensor's current value goes back to the FP32 buffers */
     for (int i = 0; i < ctx->res_count && i < net->num_tensors; ++i) {

@@ -36,6 +36,7 @@ typedef struct bcnn_cuda_context {
     size_t dy_shadow_bytes;
     void *stream;             /* compute stream (cudaStream_t) */
     int conv_math;            /* BCNN_B200_MATH_* */
+    int conv_math_explicit;   /* chosen by the caller / environment: bcnn_compile_net keeps it */
     int reference_quirks;     /* see bcnn_b200_set_reference_quirks; default 1 */
     struct bcnn_dp_state *dp; /* NULL unless bcnn_b200_dp_init succeeded */
     /* per-node CUDA-event timers (the reference only has commented-out bh_timer calls in

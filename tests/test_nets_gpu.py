@@ -113,6 +113,17 @@ def test_library_defaults(monkeypatch):
     monkeypatch.delenv("BCNN_B200_REFERENCE_QUIRKS")
     net = capi.Net()
     assert net.lib.bcnn_b200_get_conv_math(net.handle) == capi.MATH_TC_BF16
+    # ... which bcnn_compile_net keeps for nets whose layers between convolutions know the format
+    # (ResNet-style: conv, pooling, residual add) and drops for nets that would convert around
+    # format-unaware nodes (here: stand-alone batch norm)
+    netcases.small_resnet(net, batch=2)
+    net.compile()
+    assert net.lib.bcnn_b200_get_conv_math(net.handle) == capi.MATH_TC_BF16
+    net.close()
+    net = capi.Net()
+    configs.mnist(net, batch=2)
+    net.compile()
+    assert net.lib.bcnn_b200_get_conv_math(net.handle) == capi.MATH_TC
     net.close()
     monkeypatch.setenv("BCNN_B200_CONV_MATH", "tc")
     net = capi.Net()
