@@ -384,6 +384,7 @@ struct FwdParams {
     uint32_t a_slot_bytes, ring_bytes;   // ring_bytes: everything in front of the staging buffers
     FastDiv d_vw;
     int narrow;      // n_tile <= 64: both epilogue halves share the single 64-channel group
+    int dbg;         // timing decomposition (BCNN_B200_DBG_EPI bit mask; results are garbage)
     int dbg_shift;   // experiment (BCNN_B200_DBG_ROWSHIFT): A tile loaded one position early, descriptor one row late
     int src_c, dst_c, batch;
     int out_w, out_h;     // output plane as the kernel sees it (DIRECT: (H*W, 1))
@@ -577,6 +578,7 @@ conv_tma_fwd_kernel(const __grid_constant__ CUtensorMap tm_src, const __grid_con
                             mbar_wait(smem_u32(empty + s), ((it / (uint32_t)S) & 1) ^ 1);
                             const uint32_t fb = smem_u32(full + s);
                             uint8_t *a_stage = smem + (size_t)s * stage_bytes;
+                            if (p.dbg & 32) { mbar_arrive(fb); continue; }
                             mbar_expect_tx(fb, tx_bytes);
                             if (NHWC) {
                                 tma_load_4d(smem_u32(a_stage), &tm_src, cb * KC,
@@ -663,6 +665,7 @@ conv_tma_fwd_kernel(const __grid_constant__ CUtensorMap tm_src, const __grid_con
                             if (p.dbg_shift == 1) da |= (uint64_t)1 << 49;   // matrix base offset = (addr >> 7) & 7
                         }
                         const uint64_t db = make_desc_sw128(b_addr) + (uint64_t)(2 * g);
+                        if (p.dbg & 16) continue;
                         if (BF16) umma_bf16(d_tmem, da, db, idesc, (kb > 0 || g > 0) ? 1u : 0u);
                         else umma_tf32(d_tmem, da, db, idesc, (kb > 0 || g > 0) ? 1u : 0u);
                     }
@@ -755,7 +758,8 @@ conv_tma_fwd_kernel(const __grid_constant__ CUtensorMap tm_src, const __grid_con
 #pragma unroll
                         for (int j = 0; j < 16; ++j) pkn[j] = 0u;
                     }
-                    if (p.out16 == 1) {
+                    if (p.out16 == 1 && (p.dbg & 8)) {
+                    } else if (p.out16 == 1) {
                         uint8_t *sbn = smem + ring;   // the first staging buffer
                         if (ew == 0 && lane == 0) bulk_wait_read_all();
                         named_bar_sync(3, 256);
@@ -797,7 +801,7 @@ conv_tma_fwd_kernel(const __grid_constant__ CUtensorMap tm_src, const __grid_con
                             }
                         }
                     }
-                    if (p.stat_partial != nullptr && ck < chunks32) {
+                    if (p.stat_partial != nullptr && ck < chunks32 && !(p.dbg & 1)) {
                         uint32_t v[32];
                         tmem_ld32(d_tmem + (uint32_t)(ck * 32), v);
                         chunk_col_sums(v, valid, wscr, lane, acc1[0], acc2[0]);
@@ -835,7 +839,17 @@ conv_tma_fwd_kernel(const __grid_constant__ CUtensorMap tm_src, const __grid_con
                         }
                     }
                     const int ch0 = c.tile_n * n_tile + gi * 64;
-                    if (p.out16 == 1) {
+                    if (p.out16 == 1 && (p.dbg & 8)) {
+                        if (p.stat_partial != nullptr && !(p.dbg & 1)) {
+#pragma unroll
+                            for (int sc = 0; sc < 2; ++sc)
+                                if (2 * gi + sc < chunks32) {
+                                    uint32_t v[32];
+                                    tmem_ld32(d_tmem + (uint32_t)((2 * gi + sc) * 32), v);
+                                    chunk_col_sums(v, valid, wscr, lane, acc1[gj * 2 + sc], acc2[gj * 2 + sc]);
+                                }
+                        }
+                    } else if (p.out16 == 1) {
                         // the bulk store issued from this buffer one group ago has read it
                         if (hw == 0 && lane == 0) bulk_wait_read_all();
                         named_bar_sync(1 + half, 128);
@@ -858,13 +872,19 @@ conv_tma_fwd_kernel(const __grid_constant__ CUtensorMap tm_src, const __grid_con
                         // batch-norm statistics of this group while its bulk store drains. (Summing the
                         // staged BF16 tile instead was measured slower: 0.237 vs 0.191 ms on 1x1 64->256
                         // @56, gpurun r2j.)
-                        if (p.stat_partial != nullptr) {   // the accumulators are read again: cheaper than
+                        if (p.stat_partial != nullptr && !(p.dbg & 1)) {   // the accumulators are read again: cheaper than
 #pragma unroll                                                // keeping 64 registers alive across the store
                             for (int sc = 0; sc < 2; ++sc)
                                 if (2 * gi + sc < chunks32) {
                                     uint32_t v[32];
-                                    tmem_ld32(d_tmem + (uint32_t)((2 * gi + sc) * 32), v);
-                                    chunk_col_sums(v, valid, wscr, lane, acc1[gj * 2 + sc], acc2[gj * 2 + sc]);
+                                    if (p.dbg & 2) {
+#pragma unroll
+                                        for (int j = 0; j < 32; ++j) v[j] = pk[sc][j & 15];
+                                    } else {
+                                        tmem_ld32(d_tmem + (uint32_t)((2 * gi + sc) * 32), v);
+                                    }
+                                    if (p.dbg & 4) { acc1[gj * 2 + sc] += __uint_as_float(v[0]) + __uint_as_float(v[31]); }
+                                    else chunk_col_sums(v, valid, wscr, lane, acc1[gj * 2 + sc], acc2[gj * 2 + sc]);
                                 }
                         }
                     } else {
@@ -1411,6 +1431,8 @@ int run_fwd(const FwdGeom &g, const FwdPlan &pl, const void *src, const uint8_t 
     {
         const char *e = getenv("BCNN_B200_DBG_ROWSHIFT");
         p.dbg_shift = (e && pl.nhwc && g.ksh == 1 && g.sh == 1) ? atoi(e) : 0;
+        const char *e2 = getenv("BCNN_B200_DBG_EPI");
+        p.dbg = e2 ? atoi(e2) : 0;
     }
     p.tile_pos = pl.tile_pos;
     CUtensorMap tm_dst = tm;   // placeholder when the epilogue stores from registers

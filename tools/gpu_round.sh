@@ -41,10 +41,16 @@ if [[ $PARTS == *n* ]]; then
   # one launch of the main kernel of a roofline entry per capture: "entry name|shape|pass|kernel regex"
   while IFS='|' read -r NAME SHAPE PASS KERN; do
     STEM=$(echo "$NAME" | tr ' /<>@,+-' '_________' | tr -s '_')
+    # the .ncu-rep files (~35 MB each) stay on the box: gpurun brings back at most 64 MiB, so only
+    # the raw-page metrics of each capture travel
+    mkdir -p /tmp/ncu_$TAG
     timeout 400 ncu --set full --clock-control none --import-source on -k regex:$KERN -s 3 -c 1 -f \
-       -o $OUT/full_$STEM python tools/resident_sweep.py 256 2 "$SHAPE" $PASS > $OUT/full_$STEM.log 2>&1
+       -o /tmp/ncu_$TAG/full_$STEM python tools/resident_sweep.py 256 2 "$SHAPE" $PASS > $OUT/full_$STEM.log 2>&1
     echo "ncu $NAME rc=$?"
-    echo "$NAME=$OUT/full_$STEM.ncu-rep" >> $OUT/ncu_entries.txt
+    echo "## $NAME" >> $OUT/ncu_full_metrics.txt
+    python tools/ncu_metrics.py /tmp/ncu_$TAG/full_$STEM.ncu-rep >> $OUT/ncu_full_metrics.txt 2>&1
+    # the traffic entry bench.py reads (merged into profiles/ncu_traffic.json back home)
+    python tools/ncu_traffic.py $OUT/ncu_traffic.json "$NAME=/tmp/ncu_$TAG/full_$STEM.ncu-rep" > /dev/null 2>&1
   done <<'EOF'
 conv_fprop 1x1/1 64->256 @56|64,56,256,1,1,0|s|conv_tma_fwd
 conv_fprop 3x3/1 64->64 @56|64,56,64,3,1,1|s|conv_tma_fwd
@@ -55,4 +61,5 @@ conv_wgrad 1x1/1 64->256 @56|64,56,256,1,1,0|w|conv_tma_wgrad
 conv_wgrad 3x3/1 64->64 @56|64,56,64,3,1,1|w|conv_tma_wgrad
 EOF
 fi
+find $OUT -size +8M -delete
 ls -la $OUT | head -40
