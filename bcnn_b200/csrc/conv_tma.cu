@@ -385,7 +385,11 @@ struct FwdParams {
     FastDiv d_vw;
     int narrow;      // n_tile <= 64: both epilogue halves share the single 64-channel group
     int dbg;         // timing decomposition (BCNN_B200_DBG_EPI bit mask; results are garbage)
-    int dbg_shift;   // experiment (BCNN_B200_DBG_ROWSHIFT): A tile loaded one position early, descriptor one row late
+    // stats_frag: fused statistics of BF16 results through fragment-shaped TMEM loads and shuffles
+    // (frag_col_sums) instead of the shared-memory transpose; then the scratch of the transpose holds
+    // a second output staging buffer per epilogue half (stage_bufs == 2: a store drains while the
+    // next group is staged)
+    int stats_frag, stage_bufs;
     int src_c, dst_c, batch;
     int out_w, out_h;     // output plane as the kernel sees it (DIRECT: (H*W, 1))
     int ksh, ksw, pad_h, pad_w, stride;   // tap window (rows x columns) and its leading pads
@@ -431,6 +435,10 @@ __device__ __forceinline__ TileCoord decode_tile(const FwdParams &p, int tile) {
     }
     return c;
 }
+
+// Rare activations (everything but none / ReLU / leaky ReLU) in the epilogues: one out-of-line copy of the
+// reference's arithmetic instead of 32 inlined copies per call site (the kernel was 2 MB of SASS).
+__device__ __noinline__ float act_fwd_rare(float x, int act) { return act_fwd(x, act, 0.f); }
 
 // Epilogue store of one 32-column chunk held in registers (lane = position, j = channel).
 // FULL: all 32 channels exist, so the loop carries no per-element predicate.
@@ -490,6 +498,70 @@ __device__ __forceinline__ void chunk_col_sums(const uint32_t (&v)[32], bool val
     a2 += (s2[0] + s2[1]) + (s2[2] + s2[3]);
 }
 
+// Register-only flavour of the same sums (resident epilogues): the warp's 32 accumulator rows x 8*NB
+// columns are read a second time in the m16n8 fragment shape (tmem_ld_frag*), where a thread holds 4
+// rows of 2 columns per 8-column block: 3 adds per column in the thread, then a halving butterfly
+// over the 8 threads that share a column pair (lane bits 4, 3, 2): 7 * NB / 4 shuffles per quantity
+// instead of a 32 x 32 trip through shared memory per chunk, which bound thin-K layers on the
+// shared-memory pipe (profiles/r2_epilogue_decomposition.txt: 90 of 210 us on 1x1 64->256 @56).
+// vmask: ballot of the rows that exist. Results: NB == 8: s[c] / q[c] = column 2 * lane + c (c = 0, 1);
+// NB == 4: s[0] / q[0] = column frag32_col(lane).
+template <int N>
+__device__ __forceinline__ void halve_across(float (&v)[N], bool upper, int lane_mask) {
+#pragma unroll
+    for (int j = 0; j < N / 2; ++j) {
+        const float send = upper ? v[j] : v[j + N / 2];
+        const float keep = upper ? v[j + N / 2] : v[j];
+        v[j] = keep + __shfl_xor_sync(0xffffffffu, send, lane_mask);
+    }
+}
+__device__ __forceinline__ int frag32_col(int lane) {
+    return ((lane >> 4) & 1) * 16 + ((lane >> 3) & 1) * 8 + (lane & 3) * 2 + ((lane >> 2) & 1);
+}
+template <int NB>
+__device__ __forceinline__ void frag_col_sums(const uint32_t (&lo)[4 * NB], const uint32_t (&hi)[4 * NB],
+                                              uint32_t vmask, int lane, float *s_out, float *q_out) {
+    float s[2 * NB], q[2 * NB];
+    const int r = lane >> 2;
+    if (vmask == 0xffffffffu) {
+#pragma unroll
+        for (int i = 0; i < 2 * NB; ++i) {
+            const int b = i >> 1, c = i & 1;
+            const float x0 = __uint_as_float(lo[4 * b + c]), x1 = __uint_as_float(lo[4 * b + 2 + c]);
+            const float x2 = __uint_as_float(hi[4 * b + c]), x3 = __uint_as_float(hi[4 * b + 2 + c]);
+            s[i] = (x0 + x1) + (x2 + x3);
+            q[i] = fmaf(x0, x0, x1 * x1) + fmaf(x2, x2, x3 * x3);
+        }
+    } else {
+        const bool m0 = (vmask >> r) & 1u, m1 = (vmask >> (r + 8)) & 1u;
+        const bool m2 = (vmask >> (r + 16)) & 1u, m3 = (vmask >> (r + 24)) & 1u;
+#pragma unroll
+        for (int i = 0; i < 2 * NB; ++i) {
+            const int b = i >> 1, c = i & 1;
+            const float x0 = m0 ? __uint_as_float(lo[4 * b + c]) : 0.f;
+            const float x1 = m1 ? __uint_as_float(lo[4 * b + 2 + c]) : 0.f;
+            const float x2 = m2 ? __uint_as_float(hi[4 * b + c]) : 0.f;
+            const float x3 = m3 ? __uint_as_float(hi[4 * b + 2 + c]) : 0.f;
+            s[i] = (x0 + x1) + (x2 + x3);
+            q[i] = fmaf(x0, x0, x1 * x1) + fmaf(x2, x2, x3 * x3);
+        }
+    }
+    halve_across(s, (lane & 16) != 0, 16);
+    halve_across(q, (lane & 16) != 0, 16);
+    float s2[NB], q2[NB];
+#pragma unroll
+    for (int i = 0; i < NB; ++i) { s2[i] = s[i]; q2[i] = q[i]; }
+    halve_across(s2, (lane & 8) != 0, 8);
+    halve_across(q2, (lane & 8) != 0, 8);
+    float s3[NB / 2], q3[NB / 2];
+#pragma unroll
+    for (int i = 0; i < NB / 2; ++i) { s3[i] = s2[i]; q3[i] = q2[i]; }
+    halve_across(s3, (lane & 4) != 0, 4);
+    halve_across(q3, (lane & 4) != 0, 4);
+#pragma unroll
+    for (int i = 0; i < NB / 4; ++i) { s_out[i] += s3[i]; q_out[i] += q3[i]; }
+}
+
 // Persistent kernel: every CTA walks tiles blockIdx.x, +gridDim.x, ... (channel tile fastest, so
 // CTAs working at the same time share an activation tile through L2). The TMA producer runs
 // ahead across tile boundaries; two TMEM accumulators let the epilogue of tile i overlap the
@@ -506,9 +578,10 @@ conv_tma_fwd_kernel(const __grid_constant__ CUtensorMap tm_src, const __grid_con
     const int n_tile = p.n_tile;
     const int b_stage_bytes = n_tile * BLOCK_K * 4;
     const int stage_bytes = A_STAGE_BYTES + b_stage_bytes;
-    // [operand ring(s)][2 output staging buffers (1 KiB aligned)][barriers][statistics scratch]
+    // [operand ring(s)][2 output staging buffers (1 KiB aligned)][statistics scratch, or staging
+    // buffers 2 and 3][barriers]
     const size_t ring = p.ring_bytes;
-    uint64_t *bars = reinterpret_cast<uint64_t *>(smem + ring + 2 * OUT_STAGE_BYTES);
+    uint64_t *bars = reinterpret_cast<uint64_t *>(smem + ring + 2 * OUT_STAGE_BYTES + STAT_SCRATCH_BYTES);
     // plain: full[S], empty[S]; halo: fullA[sa], emptyA[sa], fullB[sb], emptyB[sb]
     const int nring = p.halo ? 2 * (p.sa + p.sb) : 2 * S;
     uint64_t *full = bars, *empty = bars + S, *acc_full = bars + nring, *acc_empty = bars + nring + 2;
@@ -535,143 +608,163 @@ conv_tma_fwd_kernel(const __grid_constant__ CUtensorMap tm_src, const __grid_con
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
 
+    // The two single-thread roles below keep their loop state in running counters (ring slot, phase
+    // bit, byte offsets): with `it % S`, `it / S` and per-tap divisions the issue loop cost ~700 cycles
+    // per k-block (SASS: two MUFU.RCP division chains), more than the MMAs of a k-block take, and
+    // bounded every layer with more than a few k-blocks per tile.
     if (warp == 0) {
         if (lane == 0) {
             // ---------------- TMA producer
-            uint32_t it = 0;
             const uint32_t tx_bytes = p.a_bytes + (uint32_t)b_stage_bytes;
+            const uint32_t smem0 = smem_u32(smem);
             if (NHWC && p.halo) {
-                uint8_t *ring_b = smem + (size_t)p.sa * p.a_slot_bytes;
-                uint32_t ita = 0, itb = 0;
+                const uint32_t ring_b = smem0 + (uint32_t)p.sa * p.a_slot_bytes;
+                const uint32_t fa0 = smem_u32(full_a), ea0 = smem_u32(empty_a);
+                const uint32_t fb0 = smem_u32(full_b), eb0 = smem_u32(empty_b);
+                uint32_t sa = 0, pa = 1, sb = 0, pb = 1;   // ring slots and the parity an empty slot shows
                 const int taps = p.ksh * p.ksw;
                 bool b_loaded = false;
                 for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
                     const TileCoord c = decode_tile<NHWC>(p, tile);
                     const uint8_t *wtile = p.wpack + (size_t)c.tile_n * p.k_blocks * b_stage_bytes;
-                    for (int cb = 0; cb < p.kc_blocks; ++cb, ++ita) {
-                        const uint32_t sa = ita % (uint32_t)p.sa;
-                        mbar_wait(smem_u32(empty_a + sa), ((ita / (uint32_t)p.sa) & 1) ^ 1);
-                        mbar_expect_tx(smem_u32(full_a + sa), p.a_bytes);
-                        tma_load_4d(smem_u32(smem + (size_t)sa * p.a_slot_bytes), &tm_src, cb * KC,
-                                    c.w0 - p.pad_w, c.h0 - p.pad_h, c.img, smem_u32(full_a + sa));
+                    for (int cb = 0; cb < p.kc_blocks; ++cb) {
+                        mbar_wait(ea0 + 8 * sa, pa);
+                        mbar_expect_tx(fa0 + 8 * sa, p.a_bytes);
+                        tma_load_4d(smem0 + sa * p.a_slot_bytes, &tm_src, cb * KC, c.w0 - p.pad_w,
+                                    c.h0 - p.pad_h, c.img, fa0 + 8 * sa);
+                        if (++sa == (uint32_t)p.sa) { sa = 0; pa ^= 1; }
                         if (p.b_resident && b_loaded) continue;
-                        for (int tap = 0; tap < taps; ++tap, ++itb) {
-                            const uint32_t sb = itb % (uint32_t)p.sb;
-                            mbar_wait(smem_u32(empty_b + sb), ((itb / (uint32_t)p.sb) & 1) ^ 1);
-                            mbar_expect_tx(smem_u32(full_b + sb), (uint32_t)b_stage_bytes);
-                            bulk_copy_g2s(smem_u32(ring_b + (size_t)sb * b_stage_bytes),
-                                          wtile + (size_t)(tap * p.kc_blocks + cb) * b_stage_bytes,
-                                          (uint32_t)b_stage_bytes, smem_u32(full_b + sb));
+                        // tap tiles of this channel block: k-block index tap * kc_blocks + cb
+                        const uint8_t *wk = wtile + (size_t)cb * b_stage_bytes;
+                        for (int tap = 0; tap < taps; ++tap, wk += (size_t)p.kc_blocks * b_stage_bytes) {
+                            mbar_wait(eb0 + 8 * sb, pb);
+                            mbar_expect_tx(fb0 + 8 * sb, (uint32_t)b_stage_bytes);
+                            bulk_copy_g2s(ring_b + sb * (uint32_t)b_stage_bytes, wk, (uint32_t)b_stage_bytes,
+                                          fb0 + 8 * sb);
+                            if (++sb == (uint32_t)p.sb) { sb = 0; pb ^= 1; }
                         }
                     }
                     b_loaded = true;
                 }
-            } else
-            for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
-                const TileCoord c = decode_tile<NHWC>(p, tile);
-                const uint8_t *wtile = p.wpack + (size_t)c.tile_n * p.k_blocks * b_stage_bytes;
-                int kb = 0;
-                for (int kh = 0; kh < p.ksh; ++kh) {
-                    for (int kw = 0; kw < p.ksw; ++kw) {
-                        for (int cb = 0; cb < p.kc_blocks; ++cb, ++kb, ++it) {
-                            const uint32_t s = it % (uint32_t)S;
-                            mbar_wait(smem_u32(empty + s), ((it / (uint32_t)S) & 1) ^ 1);
-                            const uint32_t fb = smem_u32(full + s);
-                            uint8_t *a_stage = smem + (size_t)s * stage_bytes;
-                            if (p.dbg & 32) { mbar_arrive(fb); continue; }
-                            mbar_expect_tx(fb, tx_bytes);
-                            if (NHWC) {
-                                tma_load_4d(smem_u32(a_stage), &tm_src, cb * KC,
-                                            c.w0 * p.stride + kw - p.pad_w - (p.dbg_shift ? 1 : 0),
-                                            c.h0 * p.stride + kh - p.pad_h, c.img, fb);
-                            } else {
-                                for (int a = 0; a < 4; ++a) {  // atom a = (column chunk, row) of the tile
-                                    const int wci = a / p.rows, r = a - wci * p.rows;
-                                    tma_load_4d(smem_u32(a_stage + a * ATOM_BYTES), &tm_src,
-                                                c.w0 + wci * 32 + kw - p.pad_w, c.h0 + r + kh - p.pad_h,
-                                                cb * BLOCK_K, c.img, fb);
+            } else {
+                const uint32_t f0 = smem_u32(full), e0 = smem_u32(empty);
+                uint32_t s = 0, ph = 1;
+                for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+                    const TileCoord c = decode_tile<NHWC>(p, tile);
+                    const uint8_t *wk = p.wpack + (size_t)c.tile_n * p.k_blocks * b_stage_bytes;
+                    const int x0 = c.w0 * (NHWC ? p.stride : 1) - p.pad_w;
+                    const int y0 = c.h0 * (NHWC ? p.stride : 1) - p.pad_h;
+                    for (int kh = 0; kh < p.ksh; ++kh) {
+                        for (int kw = 0; kw < p.ksw; ++kw) {
+                            for (int cb = 0; cb < p.kc_blocks; ++cb, wk += b_stage_bytes) {
+                                mbar_wait(e0 + 8 * s, ph);
+                                const uint32_t fb = f0 + 8 * s;
+                                const uint32_t a_stage = smem0 + s * (uint32_t)stage_bytes;
+                                if (++s == (uint32_t)S) { s = 0; ph ^= 1; }
+                                if (p.dbg & 32) { mbar_arrive(fb); continue; }
+                                mbar_expect_tx(fb, tx_bytes);
+                                if (NHWC) {
+                                    tma_load_4d(a_stage, &tm_src, cb * KC, x0 + kw, y0 + kh, c.img, fb);
+                                } else {
+                                    for (int a = 0; a < 4; ++a) {  // atom a = (column chunk, row) of the tile
+                                        const int wci = a / p.rows, r = a - wci * p.rows;
+                                        tma_load_4d(a_stage + a * ATOM_BYTES, &tm_src, x0 + wci * 32 + kw,
+                                                    y0 + r + kh, cb * BLOCK_K, c.img, fb);
+                                    }
                                 }
+                                bulk_copy_g2s(a_stage + A_STAGE_BYTES, wk, (uint32_t)b_stage_bytes, fb);
                             }
-                            bulk_copy_g2s(smem_u32(a_stage + A_STAGE_BYTES),
-                                          wtile + (size_t)kb * b_stage_bytes, (uint32_t)b_stage_bytes, fb);
                         }
                     }
                 }
             }
         }
     } else if (warp == 1) {
-        if (lane == 0) {
-            // ---------------- MMA issuer
-            const uint32_t idesc = BF16 ? make_idesc_bf16(TILE_M, n_tile, 0, 0)
-                                        : make_idesc_tf32(TILE_M, n_tile, NHWC ? 0 : 1, 0);
-            uint32_t it = 0, itb_ = 0, local = 0;
+        // ---------------- MMA issuer: the whole warp walks the loop (uniform state), one elected lane issues
+        const uint32_t idesc = BF16 ? make_idesc_bf16(TILE_M, n_tile, 0, 0)
+                                    : make_idesc_tf32(TILE_M, n_tile, NHWC ? 0 : 1, 0);
+        const uint64_t desc_k = make_desc_sw128(0);   // K-major SWIZZLE_128B descriptor without its address
+        const uint32_t smem0 = smem_u32(smem);
+        const uint32_t accf0 = smem_u32(acc_full), acce0 = smem_u32(acc_empty);
+        uint32_t local = 0;
+        if (NHWC && p.halo) {
+            const uint32_t ring_b = smem0 + (uint32_t)p.sa * p.a_slot_bytes;
+            const uint32_t fa0 = smem_u32(full_a), ea0 = smem_u32(empty_a);
+            const uint32_t fb0 = smem_u32(full_b), eb0 = smem_u32(empty_b);
+            uint32_t sa = 0, pa = 0, sb = 0, pb = 0;   // ring slots and the parity a filled slot shows
+            const uint32_t row_step = (uint32_t)(p.vw - p.ksw) * 128u;   // from the last tap of a row to the next row
             for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++local) {
                 const uint32_t buf = local & 1, use = local >> 1;
-                mbar_wait(smem_u32(acc_empty + buf), (use & 1) ^ 1);  // epilogue drained this buffer
+                mbar_wait(acce0 + 8 * buf, (use & 1) ^ 1);  // epilogue drained this buffer
                 tc_fence_after();
                 const uint32_t d_tmem = tmem_base + buf * acc_cols;
-                if (NHWC && p.halo) {
-                    // (function-local state of the halo rings lives in it = A counter, itb_ = B counter)
-                    const int taps = p.ksh * p.ksw;
-                    const uint32_t ring_b = smem_u32(smem + (size_t)p.sa * p.a_slot_bytes);
-                    for (int cb = 0; cb < p.kc_blocks; ++cb, ++it) {
-                        const uint32_t sa = it % (uint32_t)p.sa;
-                        mbar_wait(smem_u32(full_a + sa), (it / (uint32_t)p.sa) & 1);
-                        tc_fence_after();
-                        const uint32_t a_base = smem_u32(smem + (size_t)sa * p.a_slot_bytes);
-                        for (int tap = 0; tap < taps; ++tap) {
-                            uint32_t sb;
-                            if (p.b_resident) {
-                                sb = (uint32_t)(cb * taps + tap);
-                                if (local == 0) {   // first tile of this CTA: the tile arrives now
-                                    mbar_wait(smem_u32(full_b + sb), 0);
-                                    tc_fence_after();
-                                }
-                            } else {
-                                sb = itb_ % (uint32_t)p.sb;
-                                mbar_wait(smem_u32(full_b + sb), (itb_ / (uint32_t)p.sb) & 1);
+                uint32_t first = 0;   // 0 until the first MMA of the tile went out
+                for (int cb = 0; cb < p.kc_blocks; ++cb) {
+                    mbar_wait(fa0 + 8 * sa, pa);
+                    tc_fence_after();
+                    uint32_t a_addr = smem0 + sa * p.a_slot_bytes;   // row kh * vw + kw of the patch
+                    uint32_t rb = (uint32_t)cb * (uint32_t)(p.ksh * p.ksw);   // resident weights: slot of (cb, tap 0)
+                    for (int kh = 0; kh < p.ksh; ++kh, a_addr += row_step) {
+                        for (int kw = 0; kw < p.ksw; ++kw, a_addr += 128u, ++rb) {
+                            const uint32_t slot = p.b_resident ? rb : sb;
+                            if (!p.b_resident || local == 0) {   // resident tiles arrive during the first tile
+                                mbar_wait(fb0 + 8 * slot, p.b_resident ? 0u : pb);
                                 tc_fence_after();
                             }
-                            const int kh = tap / p.ksw, kw = tap - kh * p.ksw;
-                            const uint32_t a_addr = a_base + (uint32_t)(kh * p.vw + kw) * 128u;
-                            const uint32_t b_addr = ring_b + sb * (uint32_t)b_stage_bytes;
+                            const uint64_t da = desc_k | (uint64_t)((a_addr & 0x3FFFF) >> 4);
+                            const uint64_t db = desc_k | (uint64_t)(((ring_b + slot * (uint32_t)b_stage_bytes) & 0x3FFFF) >> 4);
+                            if (elect_one()) {
 #pragma unroll
-                            for (int g = 0; g < BLOCK_K / UMMA_K; ++g)
-                                umma_bf16(d_tmem, make_desc_sw128(a_addr) + (uint64_t)(2 * g),
-                                          make_desc_sw128(b_addr) + (uint64_t)(2 * g), idesc,
-                                          (cb > 0 || tap > 0 || g > 0) ? 1u : 0u);
-                            if (!p.b_resident) {
-                                umma_commit(smem_u32(empty_b + sb));
-                                ++itb_;
+                                for (int g = 0; g < BLOCK_K / UMMA_K; ++g)
+                                    umma_bf16(d_tmem, da + (uint64_t)(2 * g), db + (uint64_t)(2 * g), idesc,
+                                              first | (uint32_t)g);
+                                if (!p.b_resident) umma_commit(eb0 + 8 * sb);
                             }
+                            __syncwarp();
+                            first = 1;
+                            if (!p.b_resident && ++sb == (uint32_t)p.sb) { sb = 0; pb ^= 1; }
                         }
-                        umma_commit(smem_u32(empty_a + sa));
                     }
-                } else
-                for (int kb = 0; kb < p.k_blocks; ++kb, ++it) {
-                    const uint32_t s = it % (uint32_t)S;
-                    mbar_wait(smem_u32(full + s), (it / (uint32_t)S) & 1);
-                    tc_fence_after();
-                    const uint32_t a_addr = smem_u32(smem + (size_t)s * stage_bytes);
-                    const uint32_t b_addr = a_addr + A_STAGE_BYTES;
-#pragma unroll
-                    for (int g = 0; g < BLOCK_K / UMMA_K; ++g) {
-                        // DIRECT A: K-group g = 8 channel rows = 1 KiB further inside every 4 KiB atom
-                        // NHWC A / B: 8 fp32 = 32 bytes further along the 128-byte K row
-                        uint64_t da = NHWC ? make_desc_sw128(a_addr) + (uint64_t)(2 * g)
-                                           : make_desc_mn_sw128(a_addr + g * 1024, ATOM_BYTES, 512);
-                        if (NHWC && p.dbg_shift) {   // start one 128-byte row into the tile
-                            da = make_desc_sw128(a_addr + 128) + (uint64_t)(2 * g);
-                            if (p.dbg_shift == 1) da |= (uint64_t)1 << 49;   // matrix base offset = (addr >> 7) & 7
-                        }
-                        const uint64_t db = make_desc_sw128(b_addr) + (uint64_t)(2 * g);
-                        if (p.dbg & 16) continue;
-                        if (BF16) umma_bf16(d_tmem, da, db, idesc, (kb > 0 || g > 0) ? 1u : 0u);
-                        else umma_tf32(d_tmem, da, db, idesc, (kb > 0 || g > 0) ? 1u : 0u);
-                    }
-                    umma_commit(smem_u32(empty + s));
+                    if (elect_one()) umma_commit(ea0 + 8 * sa);
+                    __syncwarp();
+                    if (++sa == (uint32_t)p.sa) { sa = 0; pa ^= 1; }
                 }
-                umma_commit(smem_u32(acc_full + buf));
+                if (elect_one()) umma_commit(accf0 + 8 * buf);
+                __syncwarp();
+            }
+        } else {
+            const uint32_t f0 = smem_u32(full), e0 = smem_u32(empty);
+            uint32_t s = 0, ph = 0;
+            for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++local) {
+                const uint32_t buf = local & 1, use = local >> 1;
+                mbar_wait(acce0 + 8 * buf, (use & 1) ^ 1);  // epilogue drained this buffer
+                tc_fence_after();
+                const uint32_t d_tmem = tmem_base + buf * acc_cols;
+                for (int kb = 0; kb < p.k_blocks; ++kb) {
+                    mbar_wait(f0 + 8 * s, ph);
+                    tc_fence_after();
+                    const uint32_t a_addr = smem0 + s * (uint32_t)stage_bytes;
+                    const uint32_t b_addr = a_addr + A_STAGE_BYTES;
+                    const uint64_t db = desc_k | (uint64_t)((b_addr & 0x3FFFF) >> 4);
+                    if (!(p.dbg & 16) && elect_one()) {
+#pragma unroll
+                        for (int g = 0; g < BLOCK_K / UMMA_K; ++g) {
+                            // DIRECT A: K-group g = 8 channel rows = 1 KiB further inside every 4 KiB atom
+                            // NHWC A / B: 8 fp32 (16 bf16) = 32 bytes further along the 128-byte K row
+                            const uint64_t da = NHWC ? (desc_k | (uint64_t)((a_addr & 0x3FFFF) >> 4)) + (uint64_t)(2 * g)
+                                                     : make_desc_mn_sw128(a_addr + g * 1024, ATOM_BYTES, 512);
+                            if (BF16) umma_bf16(d_tmem, da, db + (uint64_t)(2 * g), idesc, (kb > 0 || g > 0) ? 1u : 0u);
+                            else umma_tf32(d_tmem, da, db + (uint64_t)(2 * g), idesc, (kb > 0 || g > 0) ? 1u : 0u);
+                        }
+                    }
+                    if (p.dbg & 64) {   // (timing experiment, with bit 16: plain arrive instead of a commit)
+                        if (elect_one()) mbar_arrive(e0 + 8 * s);
+                    } else if (elect_one()) umma_commit(e0 + 8 * s);
+                    __syncwarp();
+                    if (++s == (uint32_t)S) { s = 0; ph ^= 1; }
+                }
+                if (elect_one()) umma_commit(accf0 + 8 * buf);
+                __syncwarp();
             }
         }
     } else {
@@ -685,8 +778,7 @@ conv_tma_fwd_kernel(const __grid_constant__ CUtensorMap tm_src, const __grid_con
         // bulk-store epilogue: staging buffer of this half, position of this thread's row in it
         const int hw = ew & 3;   // warp within the half
         float *stage = reinterpret_cast<float *>(smem + ring + (size_t)half * OUT_STAGE_BYTES);
-        float *wscr = reinterpret_cast<float *>(smem + ring + 2 * OUT_STAGE_BYTES + FWD_BAR_BYTES) +
-                      (size_t)ew * STAT_WARP_FLOATS;
+        float *wscr = reinterpret_cast<float *>(smem + ring + 2 * OUT_STAGE_BYTES) + (size_t)ew * STAT_WARP_FLOATS;
         const int sub_stride = p.tn * 16 * p.tile_pos;   // floats of one 16-channel sub-box
         uint32_t stores = 0;                              // bulk stores issued by this half so far
         const uint32_t plane = (uint32_t)p.dst_plane;
@@ -726,9 +818,10 @@ conv_tma_fwd_kernel(const __grid_constant__ CUtensorMap tm_src, const __grid_con
                 __nv_bfloat16 *dst16 = reinterpret_cast<__nv_bfloat16 *>(p.dst) +
                                        ((size_t)img * plane + (size_t)(oh * p.o_s + p.o_oy) * p.dst_w +
                                         (size_t)(ow * p.o_s + p.o_ox)) * (size_t)p.dst_c;
-                uint8_t *sb = reinterpret_cast<uint8_t *>(stage);
                 // row of the staged box: halo tiles drop their junk columns (box rows are tw wide)
                 const int r = p.halo ? rh * p.tw + rw : q * 32 + lane;
+                const bool stats = p.stat_partial != nullptr && !(p.dbg & 1);
+                const uint32_t vmask = (stats && p.stats_frag) ? __ballot_sync(0xffffffffu, valid) : 0u;
                 if (p.narrow) {
                     // Narrow tiles (one 64-channel group): both halves work on it, half h on the 32-
                     // channel chunk h, through ONE staging buffer and one store -- with the group left
@@ -747,7 +840,7 @@ conv_tma_fwd_kernel(const __grid_constant__ CUtensorMap tm_src, const __grid_con
                                 if (p.bias != nullptr && ch0 + j < p.dst_c) val += __ldg(p.bias + ch0 + j);
                                 if (p.act == ACT_RELU) val = fmaxf(val, 0.f);
                                 else if (p.act == ACT_LRELU) val = val > 0 ? val : 0.1f * val;
-                                else val = act_fwd(val, p.act, 0.f);
+                                else val = act_fwd_rare(val, p.act);
                                 v[j] = __float_as_uint(val);
                             }
                         }
@@ -760,8 +853,13 @@ conv_tma_fwd_kernel(const __grid_constant__ CUtensorMap tm_src, const __grid_con
                     }
                     if (p.out16 == 1 && (p.dbg & 8)) {
                     } else if (p.out16 == 1) {
-                        uint8_t *sbn = smem + ring;   // the first staging buffer
-                        if (ew == 0 && lane == 0) bulk_wait_read_all();
+                        // staging buffers 0 and 2 in turn (stage_bufs == 2), else buffer 0
+                        uint8_t *sbn = smem + ring + (size_t)((stores & (uint32_t)(p.stage_bufs - 1)) * 2) * OUT_STAGE_BYTES;
+                        ++stores;
+                        if (ew == 0 && lane == 0) {   // the store issued from this buffer has read it
+                            if (p.stage_bufs == 2) bulk_wait_read_le1();
+                            else bulk_wait_read_all();
+                        }
                         named_bar_sync(3, 256);
                         if (in_box) {
                             uint8_t *row = sbn + (size_t)r * 128;
@@ -801,10 +899,18 @@ conv_tma_fwd_kernel(const __grid_constant__ CUtensorMap tm_src, const __grid_con
                             }
                         }
                     }
-                    if (p.stat_partial != nullptr && ck < chunks32 && !(p.dbg & 1)) {
-                        uint32_t v[32];
-                        tmem_ld32(d_tmem + (uint32_t)(ck * 32), v);
-                        chunk_col_sums(v, valid, wscr, lane, acc1[0], acc2[0]);
+                    // statistics from a second read of the accumulators (cheaper than keeping the
+                    // registers alive across the store), while the bulk store drains
+                    if (stats && ck < chunks32) {
+                        if (p.stats_frag) {
+                            uint32_t lo[16], hi[16];
+                            tmem_ld_frag32(d_tmem + (uint32_t)(ck * 32), lo, hi);
+                            frag_col_sums<4>(lo, hi, vmask, lane, &acc1[0], &acc2[0]);
+                        } else {
+                            uint32_t v[32];
+                            tmem_ld32(d_tmem + (uint32_t)(ck * 32), v);
+                            chunk_col_sums(v, valid, wscr, lane, acc1[0], acc2[0]);
+                        }
                     }
                 } else
 #pragma unroll
@@ -826,7 +932,7 @@ conv_tma_fwd_kernel(const __grid_constant__ CUtensorMap tm_src, const __grid_con
                                     if (p.bias != nullptr && ch0 + j < p.dst_c) val += __ldg(p.bias + ch0 + j);
                                     if (p.act == ACT_RELU) val = fmaxf(val, 0.f);
                                     else if (p.act == ACT_LRELU) val = val > 0 ? val : 0.1f * val;
-                                    else val = act_fwd(val, p.act, 0.f);
+                                    else val = act_fwd_rare(val, p.act);
                                     v[j] = __float_as_uint(val);
                                 }
                             }
@@ -840,18 +946,16 @@ conv_tma_fwd_kernel(const __grid_constant__ CUtensorMap tm_src, const __grid_con
                     }
                     const int ch0 = c.tile_n * n_tile + gi * 64;
                     if (p.out16 == 1 && (p.dbg & 8)) {
-                        if (p.stat_partial != nullptr && !(p.dbg & 1)) {
-#pragma unroll
-                            for (int sc = 0; sc < 2; ++sc)
-                                if (2 * gi + sc < chunks32) {
-                                    uint32_t v[32];
-                                    tmem_ld32(d_tmem + (uint32_t)((2 * gi + sc) * 32), v);
-                                    chunk_col_sums(v, valid, wscr, lane, acc1[gj * 2 + sc], acc2[gj * 2 + sc]);
-                                }
-                        }
                     } else if (p.out16 == 1) {
-                        // the bulk store issued from this buffer one group ago has read it
-                        if (hw == 0 && lane == 0) bulk_wait_read_all();
+                        // this half's staging buffers half and 2 + half in turn (stage_bufs == 2): the
+                        // bulk store of one group drains while the next group is staged
+                        uint8_t *sb = smem + ring +
+                                      (size_t)((stores & (uint32_t)(p.stage_bufs - 1)) * 2 + half) * OUT_STAGE_BYTES;
+                        ++stores;
+                        if (hw == 0 && lane == 0) {   // the store issued from this buffer has read it
+                            if (p.stage_bufs == 2) bulk_wait_read_le1();
+                            else bulk_wait_read_all();
+                        }
                         named_bar_sync(1 + half, 128);
                         if (in_box) {
                             uint8_t *row = sb + (size_t)r * 128;
@@ -869,35 +973,7 @@ conv_tma_fwd_kernel(const __grid_constant__ CUtensorMap tm_src, const __grid_con
                             else tma_store_4d(&tm_dst, smem_u32(sb), ch0, c.w0, c.h0, c.img);
                             bulk_commit_group();
                         }
-                        // batch-norm statistics of this group while its bulk store drains. (Summing the
-                        // staged BF16 tile instead was measured slower: 0.237 vs 0.191 ms on 1x1 64->256
-                        // @56, gpurun r2j.)
-                        if (p.stat_partial != nullptr && !(p.dbg & 1)) {   // the accumulators are read again: cheaper than
-#pragma unroll                                                // keeping 64 registers alive across the store
-                            for (int sc = 0; sc < 2; ++sc)
-                                if (2 * gi + sc < chunks32) {
-                                    uint32_t v[32];
-                                    if (p.dbg & 2) {
-#pragma unroll
-                                        for (int j = 0; j < 32; ++j) v[j] = pk[sc][j & 15];
-                                    } else {
-                                        tmem_ld32(d_tmem + (uint32_t)((2 * gi + sc) * 32), v);
-                                    }
-                                    if (p.dbg & 4) { acc1[gj * 2 + sc] += __uint_as_float(v[0]) + __uint_as_float(v[31]); }
-                                    else chunk_col_sums(v, valid, wscr, lane, acc1[gj * 2 + sc], acc2[gj * 2 + sc]);
-                                }
-                        }
-                    } else {
-                        if (p.stat_partial != nullptr) {   // the accumulators are read again: cheaper than
-#pragma unroll                                                // keeping 64 registers alive across the store
-                            for (int sc = 0; sc < 2; ++sc)
-                                if (2 * gi + sc < chunks32) {
-                                    uint32_t v[32];
-                                    tmem_ld32(d_tmem + (uint32_t)((2 * gi + sc) * 32), v);
-                                    chunk_col_sums(v, valid, wscr, lane, acc1[gj * 2 + sc], acc2[gj * 2 + sc]);
-                                }
-                        }
-                        if (valid)
+                    } else if (valid) {
 #pragma unroll
                         for (int k8 = 0; k8 < 8; ++k8) {
                             if (ch0 + k8 * 8 < p.dst_c && gi * 64 + k8 * 8 < n_tile) {
@@ -921,6 +997,25 @@ conv_tma_fwd_kernel(const __grid_constant__ CUtensorMap tm_src, const __grid_con
                             }
                         }
                     }
+                    // batch-norm statistics of this group while its bulk store drains: the accumulators
+                    // are read again, cheaper than keeping 64 registers alive across the store. (Summing
+                    // the staged BF16 tile instead was measured slower: 0.237 vs 0.191 ms on 1x1 64->256
+                    // @56, gpurun r2j.)
+                    if (stats) {
+                        if (p.stats_frag) {
+                            uint32_t lo[32], hi[32];
+                            tmem_ld_frag64(d_tmem + (uint32_t)(gi * 64), lo, hi);
+                            frag_col_sums<8>(lo, hi, vmask, lane, &acc1[gj * 2], &acc2[gj * 2]);
+                        } else {
+#pragma unroll
+                            for (int sc = 0; sc < 2; ++sc)
+                                if (2 * gi + sc < chunks32) {
+                                    uint32_t v[32];
+                                    tmem_ld32(d_tmem + (uint32_t)((2 * gi + sc) * 32), v);
+                                    chunk_col_sums(v, valid, wscr, lane, acc1[gj * 2 + sc], acc2[gj * 2 + sc]);
+                                }
+                        }
+                    }
                 }
             } else if (p.tstore) {
                 const int pos0 = NHWC ? c.h0 * p.dst_w + c.w0 : c.w0;
@@ -938,7 +1033,7 @@ conv_tma_fwd_kernel(const __grid_constant__ CUtensorMap tm_src, const __grid_con
                                 if (p.bias != nullptr && ch0 + j < p.dst_c) val += __ldg(p.bias + ch0 + j);
                                 if (p.act == ACT_RELU) val = fmaxf(val, 0.f);
                                 else if (p.act == ACT_LRELU) val = val > 0 ? val : 0.1f * val;
-                                else val = act_fwd(val, p.act, 0.f);
+                                else val = act_fwd_rare(val, p.act);
                                 v[j] = __float_as_uint(val);
                             }
                         }
@@ -997,7 +1092,7 @@ conv_tma_fwd_kernel(const __grid_constant__ CUtensorMap tm_src, const __grid_con
                         if (j < nvalid) {
                             float val = __uint_as_float(v[j]);
                             if (b) val += __ldg(b + j);
-                            d[(size_t)((uint32_t)j * plane)] = act_fwd(val, p.act, 0.f);
+                            d[(size_t)((uint32_t)j * plane)] = act_fwd_rare(val, p.act);
                         }
                     }
                 }
@@ -1017,8 +1112,14 @@ conv_tma_fwd_kernel(const __grid_constant__ CUtensorMap tm_src, const __grid_con
                 // tiles (n_tile <= 64): chunk `half`, kept in slot 0
                 int ck = p.out16 ? 2 * (half + 2 * (ci >> 1)) + (ci & 1) : half + 2 * ci;
                 if (p.out16 && p.narrow) ck = ci == 0 ? half : chunks32;
-                const int ch = (int)tile_n * n_tile + ck * 32 + lane;
-                if (ck < chunks32 && lane < n_tile - ck * 32 && ch < p.dst_c) {
+                int col = ck * 32 + lane;   // column of the channel tile this lane's sums belong to
+                if (p.out16 && p.stats_frag) {
+                    // frag_col_sums: slots 2 gj + c hold column 2 * lane + c of group half + 2 gj; narrow
+                    // tiles: slot 0 holds column frag32_col(lane) of chunk `half`
+                    col = p.narrow ? ck * 32 + frag32_col(lane) : (half + 2 * (ci >> 1)) * 64 + 2 * lane + (ci & 1);
+                }
+                const int ch = (int)tile_n * n_tile + col;
+                if (ck < chunks32 && col < n_tile && ch < p.dst_c) {
                     p.stat_partial[(row * 2 + 0) * p.dst_c + ch] = acc1[ci];
                     p.stat_partial[(row * 2 + 1) * p.dst_c + ch] = acc2[ci];
                 }
@@ -1183,6 +1284,10 @@ bool plan_fwd(const FwdGeom &g, FwdPlan *pl) {
     int stages = (227 * 1024 - FWD_EXTRA_SMEM) / stage;  // persistent: one CTA per SM owns the shared memory
     if (stages > 8) stages = 8;
     if (stages < 2) stages = 2;
+    {
+        static const int smax = [] { const char *e = getenv("BCNN_B200_FWD_STAGES"); return e ? atoi(e) : 0; }();
+        if (smax >= 2 && stages > smax) stages = smax;
+    }
     pl->stages = stages;
     pl->wpack_bytes = align256((size_t)pl->n_tiles * pl->k_blocks * n * BLOCK_K * sizeof(float));
     pl->smem_bytes = (size_t)stages * stage + FWD_EXTRA_SMEM;
@@ -1428,9 +1533,12 @@ int run_fwd(const FwdGeom &g, const FwdPlan &pl, const void *src, const uint8_t 
     p.vw = pl.vw; p.sa = pl.sa; p.sb = pl.sb; p.b_resident = pl.b_resident;
     p.a_slot_bytes = pl.a_slot_bytes; p.ring_bytes = pl.ring_bytes;
     p.d_vw = FastDiv((uint32_t)(pl.vw > 0 ? pl.vw : 1));
+    // fused statistics of BF16 results in registers (BCNN_B200_STATS_SMEM=1: the shared-memory transpose
+    // of the FP32-tensor path); the transpose scratch then serves as second staging buffers
+    static const bool stats_smem = env_off("BCNN_B200_STATS_SMEM"), one_buf = env_off("BCNN_B200_ONE_STAGE_BUF");
+    p.stats_frag = (pl.out16 && !stats_smem) ? 1 : 0;
+    p.stage_bufs = (pl.out16 == 1 && (p.stats_frag || stat_partial == nullptr) && !one_buf) ? 2 : 1;
     {
-        const char *e = getenv("BCNN_B200_DBG_ROWSHIFT");
-        p.dbg_shift = (e && pl.nhwc && g.ksh == 1 && g.sh == 1) ? atoi(e) : 0;
         const char *e2 = getenv("BCNN_B200_DBG_EPI");
         p.dbg = e2 ? atoi(e2) : 0;
     }
@@ -1820,62 +1928,67 @@ conv_tma_wgrad_kernel(const __grid_constant__ CUtensorMap tm_dy, const __grid_co
     const int kb_end = min(p.kb_total, kb_begin + p.kb_per_split);
     const int iters = kb_end - kb_begin;
 
+    // running ring slot / phase / block coordinates instead of divisions per k-block (see the fprop kernel)
     if (warp == 0) {
         if (lane == 0) {
+            const uint32_t smem0 = smem_u32(smem), bar0 = smem_u32(bars);
+            uint32_t s = 0, ph = 1;
+            uint32_t img, rem, hb, wb;
+            p.d_img.divmod((uint32_t)kb_begin, img, rem);
+            p.d_bw.divmod(rem, hb, wb);
             for (int it = 0; it < iters; ++it) {
-                const int s = it % S;
-                mbar_wait(smem_u32(bars + S + s), ((it / S) & 1) ^ 1);
-                uint32_t img, rem, hb, wb;
-                p.d_img.divmod((uint32_t)(kb_begin + it), img, rem);
-                p.d_bw.divmod(rem, hb, wb);
-                const uint32_t full = smem_u32(bars + s);
-                uint8_t *a_stage = smem + (size_t)s * stage_bytes;
+                mbar_wait(bar0 + 8 * ((uint32_t)S + s), ph);
+                const uint32_t full = bar0 + 8 * s;
+                const uint32_t a_stage = smem0 + s * stage_bytes;
+                if (++s == (uint32_t)S) { s = 0; ph ^= 1; }
                 mbar_expect_tx(full, stage_bytes);
                 if (NHWC) {
                     const int ow0 = (int)wb * p.bw, oh0 = (int)hb * p.bh;
                     constexpr int CA = BF16 ? 64 : 32;   // channels per atom (128-byte rows)
                     for (int a = 0; a < TILE_M / CA; ++a)
-                        tma_load_4d(smem_u32(a_stage + a * p.atom_bytes), &tm_dy, co0 + CA * a, ow0, oh0,
-                                    (int)img, full);
+                        tma_load_4d(a_stage + a * p.atom_bytes, &tm_dy, co0 + CA * a, ow0, oh0, (int)img, full);
                     for (int b = 0; b < p.nb; ++b)
-                        tma_load_4d(smem_u32(a_stage + p.a_bytes + b * p.atom_bytes), &tm_x, ci0 + CA * b,
+                        tma_load_4d(a_stage + p.a_bytes + b * p.atom_bytes, &tm_x, ci0 + CA * b,
                                     ow0 * p.stride + kw - p.pad, oh0 * p.stride + kh - p.pad, (int)img, full);
                 } else {
-                    tma_load_4d(smem_u32(a_stage), &tm_dy, (int)wb * 32, (int)hb, co0, (int)img, full);
-                    tma_load_4d(smem_u32(a_stage + p.a_bytes), &tm_x, (int)wb * 32 + kw - p.pad,
-                                (int)hb + kh - p.pad, ci0, (int)img, full);
+                    tma_load_4d(a_stage, &tm_dy, (int)wb * 32, (int)hb, co0, (int)img, full);
+                    tma_load_4d(a_stage + p.a_bytes, &tm_x, (int)wb * 32 + kw - p.pad, (int)hb + kh - p.pad, ci0,
+                                (int)img, full);
+                }
+                // next k-block: column block fastest, then row block, then image
+                if (++wb == (uint32_t)p.blocks_w) {
+                    wb = 0;
+                    if (++hb == (uint32_t)p.blocks_h) { hb = 0; ++img; }
                 }
             }
         }
     } else if (warp == 1) {
-        if (lane == 0) {
-            const uint32_t idesc = BF16 ? make_idesc_bf16(TILE_M, n_tile, 1, 1)
-                                        : make_idesc_tf32(TILE_M, n_tile, NHWC ? 1 : 0, NHWC ? 1 : 0);
-            const int mmas = p.kpos / (BF16 ? 16 : UMMA_K);
-            for (int it = 0; it < iters; ++it) {
-                const int s = it % S;
-                mbar_wait(smem_u32(bars + s), (it / S) & 1);
-                tc_fence_after();
-                const uint32_t a_addr = smem_u32(smem + (size_t)s * stage_bytes);
-                const uint32_t b_addr = a_addr + p.a_bytes;
-                for (int g = 0; g < mmas; ++g) {
-                    uint64_t da, db;
-                    if (BF16) {  // 16 position rows = 2 KiB further inside every atom
-                        da = make_desc_mn_sw128_b16(a_addr + g * 2048, p.atom_bytes, 1024);
-                        db = make_desc_mn_sw128_b16(b_addr + g * 2048, p.atom_bytes, 1024);
-                    } else if (NHWC) {  // 8 position rows = 1 KiB further inside every atom
-                        da = make_desc_mn_sw128(a_addr + g * 1024, p.atom_bytes, 512);
-                        db = make_desc_mn_sw128(b_addr + g * 1024, p.atom_bytes, 512);
-                    } else {
-                        da = make_desc_sw128(a_addr) + (uint64_t)(2 * g);
-                        db = make_desc_sw128(b_addr) + (uint64_t)(2 * g);
-                    }
-                    if (BF16) umma_bf16(tmem_base, da, db, idesc, (it > 0 || g > 0) ? 1u : 0u);
-                    else umma_tf32(tmem_base, da, db, idesc, (it > 0 || g > 0) ? 1u : 0u);
+        // the whole warp walks the loop (uniform state), one elected lane issues
+        const uint32_t idesc = BF16 ? make_idesc_bf16(TILE_M, n_tile, 1, 1)
+                                    : make_idesc_tf32(TILE_M, n_tile, NHWC ? 1 : 0, NHWC ? 1 : 0);
+        const int mmas = p.kpos / (BF16 ? 16 : UMMA_K);
+        const uint32_t smem0 = smem_u32(smem), bar0 = smem_u32(bars);
+        // descriptors without their address: MN-major atoms (BF16 / TF32) or K-major rows (DIRECT)
+        const uint64_t desc0 = BF16 ? make_desc_mn_sw128_b16(0, p.atom_bytes, 1024)
+                                    : (NHWC ? make_desc_mn_sw128(0, p.atom_bytes, 512) : make_desc_sw128(0));
+        const uint32_t g_step = BF16 ? (2048u >> 4) : (NHWC ? (1024u >> 4) : 2u);   // per MMA, in 16-byte units
+        uint32_t s = 0, ph = 0;
+        for (int it = 0; it < iters; ++it) {
+            mbar_wait(bar0 + 8 * s, ph);
+            tc_fence_after();
+            const uint32_t a_addr = smem0 + s * stage_bytes;
+            uint64_t da = desc0 | (uint64_t)((a_addr & 0x3FFFF) >> 4);
+            uint64_t db = desc0 | (uint64_t)(((a_addr + p.a_bytes) & 0x3FFFF) >> 4);
+            if (elect_one()) {
+                for (int g = 0; g < mmas; ++g, da += g_step, db += g_step) {
+                    if (BF16) umma_bf16(tmem_base, da, db, idesc, (uint32_t)(it | g));
+                    else umma_tf32(tmem_base, da, db, idesc, (uint32_t)(it | g));
                 }
-                umma_commit(smem_u32(bars + S + s));
-                if (it == iters - 1) umma_commit(smem_u32(bars + 2 * S));
+                umma_commit(bar0 + 8 * ((uint32_t)S + s));
+                if (it == iters - 1) umma_commit(bar0 + 8 * (2u * (uint32_t)S));
             }
+            __syncwarp();
+            if (++s == (uint32_t)S) { s = 0; ph ^= 1; }
         }
     } else {
         // epilogue: D[co lane, ci column] -> out[split][co][ci][tap]

@@ -32,6 +32,19 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
             "}\n" : "=r"(done) : "r"(bar), "r"(parity) : "memory");
     } while (!done);
 }
+// One thread of a converged warp (the same one every time): the issuer of tcgen05.mma / commit.
+// ptxas keeps warp-uniform operands of the guarded instructions in uniform registers, which an
+// `if (lane == 0)` branch does not allow (it falls back to an ELECT / R2UR.BROADCAST loop per MMA).
+__device__ __forceinline__ bool elect_one() {
+    uint32_t pred;
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "elect.sync _|p, 0xffffffff;\n"
+        "selp.b32 %0, 1, 0, p;\n"
+        "}\n" : "=r"(pred));
+    return pred != 0;
+}
 __device__ __forceinline__ void bulk_copy_g2s(uint32_t dst_smem, const void *src, uint32_t bytes,
                                               uint32_t bar) {
     asm volatile(
@@ -86,6 +99,31 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
           "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
         : "r"(taddr));
     asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
+// Fragment-shaped TMEM loads of a warp's 32 lanes x 8N columns as two 16-lane halves (lo: lanes of
+// taddr, hi: 16 lanes further), both in flight before the one wait. tcgen05.ld.16x256b.xN gives thread t,
+// for every 8-column block b,
+//   v[4b + {0,1}] = (lane t/4,     columns 8b + 2(t%4) + {0,1})
+//   v[4b + {2,3}] = (lane t/4 + 8, same columns)
+// (the m16n8 accumulator fragment).
+__device__ __forceinline__ void tmem_ld_frag64(uint32_t taddr, uint32_t (&lo)[32], uint32_t (&hi)[32]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.16x256b.x8.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%64];\n"
+        "tcgen05.ld.sync.aligned.16x256b.x8.b32 {%32,%33,%34,%35,%36,%37,%38,%39,%40,%41,%42,%43,%44,%45,%46,%47,%48,%49,%50,%51,%52,%53,%54,%55,%56,%57,%58,%59,%60,%61,%62,%63}, [%65];\n"
+        "tcgen05.wait::ld.sync.aligned;"
+        : "=r"(lo[0]), "=r"(lo[1]), "=r"(lo[2]), "=r"(lo[3]), "=r"(lo[4]), "=r"(lo[5]), "=r"(lo[6]), "=r"(lo[7]), "=r"(lo[8]), "=r"(lo[9]), "=r"(lo[10]), "=r"(lo[11]), "=r"(lo[12]), "=r"(lo[13]), "=r"(lo[14]), "=r"(lo[15]), "=r"(lo[16]), "=r"(lo[17]), "=r"(lo[18]), "=r"(lo[19]), "=r"(lo[20]), "=r"(lo[21]), "=r"(lo[22]), "=r"(lo[23]), "=r"(lo[24]), "=r"(lo[25]), "=r"(lo[26]), "=r"(lo[27]), "=r"(lo[28]), "=r"(lo[29]), "=r"(lo[30]), "=r"(lo[31]),
+          "=r"(hi[0]), "=r"(hi[1]), "=r"(hi[2]), "=r"(hi[3]), "=r"(hi[4]), "=r"(hi[5]), "=r"(hi[6]), "=r"(hi[7]), "=r"(hi[8]), "=r"(hi[9]), "=r"(hi[10]), "=r"(hi[11]), "=r"(hi[12]), "=r"(hi[13]), "=r"(hi[14]), "=r"(hi[15]), "=r"(hi[16]), "=r"(hi[17]), "=r"(hi[18]), "=r"(hi[19]), "=r"(hi[20]), "=r"(hi[21]), "=r"(hi[22]), "=r"(hi[23]), "=r"(hi[24]), "=r"(hi[25]), "=r"(hi[26]), "=r"(hi[27]), "=r"(hi[28]), "=r"(hi[29]), "=r"(hi[30]), "=r"(hi[31])
+        : "r"(taddr), "r"(taddr + (16u << 16)) : "memory");
+}
+__device__ __forceinline__ void tmem_ld_frag32(uint32_t taddr, uint32_t (&lo)[16], uint32_t (&hi)[16]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.16x256b.x4.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%32];\n"
+        "tcgen05.ld.sync.aligned.16x256b.x4.b32 {%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%33];\n"
+        "tcgen05.wait::ld.sync.aligned;"
+        : "=r"(lo[0]), "=r"(lo[1]), "=r"(lo[2]), "=r"(lo[3]), "=r"(lo[4]), "=r"(lo[5]), "=r"(lo[6]), "=r"(lo[7]), "=r"(lo[8]), "=r"(lo[9]), "=r"(lo[10]), "=r"(lo[11]), "=r"(lo[12]), "=r"(lo[13]), "=r"(lo[14]), "=r"(lo[15]),
+          "=r"(hi[0]), "=r"(hi[1]), "=r"(hi[2]), "=r"(hi[3]), "=r"(hi[4]), "=r"(hi[5]), "=r"(hi[6]), "=r"(hi[7]), "=r"(hi[8]), "=r"(hi[9]), "=r"(hi[10]), "=r"(hi[11]), "=r"(hi[12]), "=r"(hi[13]), "=r"(hi[14]), "=r"(hi[15])
+        : "r"(taddr), "r"(taddr + (16u << 16)) : "memory");
 }
 
 // K-major, 128-byte-swizzled shared-memory matrix descriptor (cute::UMMA::SmemDescriptor):

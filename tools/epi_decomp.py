@@ -1,7 +1,6 @@
 """Timing decomposition of conv_tma_fwd_kernel<1,1> (resident fprop with fused statistics) through the
 BCNN_B200_DBG_EPI bit mask (results are garbage, only the time matters):
-  1 no statistics   2 statistics without the second TMEM read   4 second TMEM read without the column sums
-  8 no staging / bulk store   16 no MMAs   32 no TMA loads
+  1 no statistics   8 no staging / bulk store   16 no MMAs   32 no TMA loads   64 (with 16) plain mbarrier arrive instead of tcgen05.commit per k-block
     python tools/epi_decomp.py [batch]
 """
 import os
@@ -17,9 +16,8 @@ batch = int(sys.argv[1]) if len(sys.argv) > 1 else 256
 lib = capi.b200()
 SHAPES = [(64, 56, 256, 1, 1, 0), (64, 56, 64, 3, 1, 1), (128, 28, 512, 1, 1, 0), (256, 14, 256, 3, 1, 1),
           (256, 14, 1024, 1, 1, 0), (1024, 14, 256, 1, 1, 0), (512, 7, 512, 3, 1, 1)]
-VARIANTS = [(0, "full"), (1, "no stats"), (2, "stats, no 2nd tmem read"), (4, "2nd tmem read only"),
-            (8, "no store"), (9, "no store, no stats"), (16, "no mma"), (32, "no loads"), (48, "epilogue only"),
-            (25, "loads only"), (41, "mma only"), (57, "nothing")]
+VARIANTS = [(0, "full"), (1, "no stats"), (8, "no store"), (9, "no store, no stats"), (16, "no mma"), (32, "no loads"), (48, "epilogue only"),
+            (25, "loads only"), (41, "mma only"), (57, "nothing"), (121, "nothing, arrive")]
 
 
 def timeit(fn, iters=5):
