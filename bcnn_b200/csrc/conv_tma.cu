@@ -693,6 +693,46 @@ conv_tma_fwd_kernel(const __grid_constant__ CUtensorMap tm_src, const __grid_con
             const uint32_t fb0 = smem_u32(full_b), eb0 = smem_u32(empty_b);
             uint32_t sa = 0, pa = 0, sb = 0, pb = 0;   // ring slots and the parity a filled slot shows
             const uint32_t row_step = (uint32_t)(p.vw - p.ksw) * 128u;   // from the last tap of a row to the next row
+            if (p.b_resident) {
+                // Resident weights: after the tap tiles have landed (once per CTA) a tile is one wait per
+                // channel block and a straight run of MMAs whose descriptors advance by constants, all
+                // inside one elected region (~16 instructions per tap instead of ~75).
+                const int slots = p.kc_blocks * p.ksh * p.ksw;
+                for (int i = 0; i < slots; ++i) mbar_wait(fb0 + 8 * (uint32_t)i, 0u);
+                tc_fence_after();
+                const uint64_t b_step = (uint64_t)((uint32_t)b_stage_bytes >> 4);
+                for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++local) {
+                    const uint32_t buf = local & 1, use = local >> 1;
+                    mbar_wait(acce0 + 8 * buf, (use & 1) ^ 1);  // epilogue drained this buffer
+                    tc_fence_after();
+                    const uint32_t d_tmem = tmem_base + buf * acc_cols;
+                    const uint64_t db0 = desc_k | (uint64_t)((ring_b & 0x3FFFF) >> 4);
+                    uint32_t acc = 0;
+                    for (int cb = 0; cb < p.kc_blocks; ++cb) {
+                        mbar_wait(fa0 + 8 * sa, pa);
+                        tc_fence_after();
+                        if (elect_one()) {
+                            uint64_t da = desc_k | (uint64_t)(((smem0 + sa * p.a_slot_bytes) & 0x3FFFF) >> 4);
+                            uint64_t db = db0 + b_step * (uint64_t)(cb * p.ksh * p.ksw);   // slot of (cb, tap 0)
+                            for (int kh = 0; kh < p.ksh; ++kh, da += (uint64_t)(row_step >> 4)) {
+                                for (int kw = 0; kw < p.ksw; ++kw, da += 8u, db += b_step) {
+#pragma unroll
+                                    for (int g = 0; g < BLOCK_K / UMMA_K; ++g)
+                                        umma_bf16(d_tmem, da + (uint64_t)(2 * g), db + (uint64_t)(2 * g), idesc,
+                                                  acc | (uint32_t)g);
+                                    acc = 1;
+                                }
+                            }
+                            umma_commit(ea0 + 8 * sa);
+                        }
+                        __syncwarp();
+                        acc = 1;
+                        if (++sa == (uint32_t)p.sa) { sa = 0; pa ^= 1; }
+                    }
+                    if (elect_one()) umma_commit(accf0 + 8 * buf);
+                    __syncwarp();
+                }
+            } else
             for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++local) {
                 const uint32_t buf = local & 1, use = local >> 1;
                 mbar_wait(acce0 + 8 * buf, (use & 1) ^ 1);  // epilogue drained this buffer
@@ -1301,8 +1341,10 @@ bool plan_fwd(const FwdGeom &g, FwdPlan *pl) {
     // weights), but the kernel is 25-30 % SLOWER than the per-tap route on every ResNet-50 3x3 shape
     // (0.20 vs 0.19 ms, 0.134 vs 0.103, 0.090 vs 0.072; gpurun r2w) whatever the ring depths: the
     // per-tap route was not bound by that traffic after all. Kept for the next round's profiling.
-    static const bool halo_on = [] { const char *e = getenv("BCNN_B200_HALO"); return e && e[0] == '1'; }();
-    if (halo_on && g.resident && pl->bf16 && g.stride == 1 && g.o_s == 1 && g.ksh * g.ksw > 1 &&
+    // BCNN_B200_HALO: 1 every eligible layer, 0 none; default: layers whose weights stay resident in
+    // shared memory (64 -> 64 channels), where a tile is one patch load and a straight run of MMAs
+    static const int halo_mode = [] { const char *e = getenv("BCNN_B200_HALO"); return e ? atoi(e) : 2; }();
+    if (halo_mode && g.resident && pl->bf16 && g.stride == 1 && g.o_s == 1 && g.ksh * g.ksw > 1 &&
         g.ksw - 1 + 8 <= 128 && !env_off("BCNN_B200_NO_HALO")) {
         int tw = g.dw;
         if (tw + g.ksw - 1 > 128) {   // wide planes: balanced column segments
@@ -1333,8 +1375,11 @@ bool plan_fwd(const FwdGeom &g, FwdPlan *pl) {
             const int taps_all = g.ksh * g.ksw * pl->kc_blocks;
             const char *e_sa = getenv("BCNN_B200_HALO_SA"), *e_sb = getenv("BCNN_B200_HALO_SB");
             int sa = e_sa ? atoi(e_sa) : 3;
-            bool resident_b = pl->n_tiles == 1 && (long long)sa * a_slot + (long long)taps_all * b_slot <= avail &&
-                              !env_off("BCNN_B200_HALO_NO_RESIDENT_B");
+            bool resident_b = false;
+            if (pl->n_tiles == 1 && !env_off("BCNN_B200_HALO_NO_RESIDENT_B")) {   // weights resident: 3, else 2 patches in flight
+                if ((long long)sa * a_slot + (long long)taps_all * b_slot <= avail) resident_b = true;
+                else if (!e_sa && 2LL * a_slot + (long long)taps_all * b_slot <= avail) { sa = 2; resident_b = true; }
+            }
             int sb = resident_b ? taps_all : (int)((avail - (long long)sa * a_slot) / b_slot);
             if (!resident_b && sb > 8) sb = 8;
             if (e_sb && !resident_b) sb = atoi(e_sb);
@@ -1344,7 +1389,8 @@ bool plan_fwd(const FwdGeom &g, FwdPlan *pl) {
             }
             if ((long long)sa * a_slot + (long long)sb * b_slot > avail) sb = 0;
             // the box must fit the TMA limits and the rings must hold a few tap tiles
-            if (sb >= 3 && vw <= 256 && ph <= 256 && 2 * (sa + sb) + 5 <= FWD_BAR_BYTES / 8) {
+            if (sb >= 3 && vw <= 256 && ph <= 256 && 2 * (sa + sb) + 5 <= FWD_BAR_BYTES / 8 &&
+                (halo_mode == 1 || resident_b)) {
                 pl->halo = true;
                 pl->vw = vw; pl->ph = ph; pl->sa = sa; pl->sb = sb; pl->b_resident = resident_b ? 1 : 0;
                 pl->a_slot_bytes = a_slot;
