@@ -112,7 +112,7 @@ def yolo_tiny(net, batch=1, res=416):
 
 
 def resnet50(net, batch=256, res=224, classes=1000, widths=(64, 128, 256, 512),
-             blocks=(3, 4, 6, 3), stage_strides=(1, 2, 2, 2)):
+             blocks=(3, 4, 6, 3), stage_strides=(1, 2, 2, 2), metric=None):
     """ResNet-50 v1.5 (stride on the 3x3). Residual adds use bcnn_add_eltwise_layer."""
     net.set_input_shape(res, res, 3, batch)
     net.conv(widths[0], 7, 2, 3, 1, 1, "relu", "input", "conv1")
@@ -136,7 +136,10 @@ def resnet50(net, batch=256, res=224, classes=1000, widths=(64, 128, 256, 512),
     net.fullc(classes, "none", "gap", "fc")
     net.softmax("fc", "softmax")
     if net.mode != capi.MODE_PREDICT:
-        net.cost("softmax", "cost")
+        if metric is None:
+            net.cost("softmax", "cost")
+        else:
+            net.cost("softmax", "cost", metric=metric)
         net.sgd(0.005, 0.9, 0.0005)
     return dict(classes=classes, out="softmax")
 

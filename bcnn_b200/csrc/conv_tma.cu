@@ -1039,8 +1039,9 @@ conv_tma_fwd_kernel(const __grid_constant__ CUtensorMap tm_src, const __grid_con
                     }
                     // batch-norm statistics of this group while its bulk store drains: the accumulators
                     // are read again, cheaper than keeping 64 registers alive across the store. (Summing
-                    // the staged BF16 tile instead was measured slower: 0.237 vs 0.191 ms on 1x1 64->256
-                    // @56, gpurun r2j.)
+                    // the staged BF16 tile instead -- each warp reading back its own 32 rows, lane = channel
+                    // pair -- was measured slower twice: 0.237 vs 0.191 ms on 1x1 64->256 @56 in gpurun r2j,
+                    // 0.163 vs 0.145 ms after the fragment-shaped second read, gpurun r2zj.)
                     if (stats) {
                         if (p.stats_frag) {
                             uint32_t lo[32], hi[32];

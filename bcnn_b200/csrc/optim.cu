@@ -127,6 +127,57 @@ softmax_kernel(const float *__restrict__ x, float *__restrict__ y, int rows, int
     }
 }
 
+// sgd_kernel over a table of tensors: a CTA finds its tensor by bisection of first_block and owns
+// 4096 consecutive elements of it (four float4 per thread, loads first).
+__global__ void __launch_bounds__(256)
+sgd_multi_kernel(const __grid_constant__ bcnn_b200_sgd_batch b) {
+    int lo = 0, hi = b.count;
+    while (hi - lo > 1) {
+        const int mid = (lo + hi) >> 1;
+        if (blockIdx.x >= b.first_block[mid]) lo = mid;
+        else hi = mid;
+    }
+    float *__restrict__ w = b.w[lo];
+    float *__restrict__ g = b.g[lo];
+    const unsigned int n = b.n[lo];
+    const float wd_scale = b.wd_scale[lo], step = b.step, g_scale = b.g_scale;
+    const unsigned int base = (blockIdx.x - b.first_block[lo]) * 4096u + threadIdx.x * 4u;
+    float4 wv[4], gv[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+        const unsigned int j = base + u * 1024u;
+        if (j + 3 < n) {
+            wv[u] = *reinterpret_cast<const float4 *>(w + j);
+            gv[u] = *reinterpret_cast<const float4 *>(g + j);
+        }
+    }
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+        const unsigned int j = base + u * 1024u;
+        if (j + 3 < n) {
+            float4 x = wv[u], y = gv[u];
+            // separate mul / add roundings, as the reference's axpy (no FMA contraction)
+            y.x = __fadd_rn(y.x, __fmul_rn(wd_scale, x.x));
+            y.y = __fadd_rn(y.y, __fmul_rn(wd_scale, x.y));
+            y.z = __fadd_rn(y.z, __fmul_rn(wd_scale, x.z));
+            y.w = __fadd_rn(y.w, __fmul_rn(wd_scale, x.w));
+            x.x = __fadd_rn(x.x, __fmul_rn(step, y.x));
+            x.y = __fadd_rn(x.y, __fmul_rn(step, y.y));
+            x.z = __fadd_rn(x.z, __fmul_rn(step, y.z));
+            x.w = __fadd_rn(x.w, __fmul_rn(step, y.w));
+            y.x *= g_scale; y.y *= g_scale; y.z *= g_scale; y.w *= g_scale;
+            *reinterpret_cast<float4 *>(w + j) = x;
+            *reinterpret_cast<float4 *>(g + j) = y;
+        } else {
+            for (unsigned int e = j; e < n && e < j + 4; ++e) {   // the tensor's last, partial vector
+                const float y = __fadd_rn(g[e], __fmul_rn(wd_scale, w[e]));
+                w[e] = __fadd_rn(w[e], __fmul_rn(step, y));
+                g[e] = y * g_scale;
+            }
+        }
+    }
+}
+
 // grad = pred - label: plain stream over the n x classes tensor.
 __global__ void __launch_bounds__(256)
 cost_grad_kernel(const float *__restrict__ pred, const float *__restrict__ label, float *__restrict__ grad,
@@ -207,6 +258,15 @@ extern "C" int bcnn_b200_sgd_update(float *w, float *g, size_t n, float wd_scale
     bool vec = aligned16(w) && aligned16(g);
     sgd_kernel<<<stream_grid(vec ? n / 4 + 1 : n, 256), 256, 0, as_stream(stream)>>>(
         w, g, n, wd_scale, step, g_scale, vec);
+    return launched();
+}
+
+extern "C" int bcnn_b200_sgd_update_multi(const bcnn_b200_sgd_batch *batch, void *stream) {
+    if (!batch || batch->count <= 0) return 0;
+    if (batch->count > BCNN_B200_SGD_MULTI_MAX) return (int)cudaErrorInvalidValue;
+    const unsigned int grid = batch->first_block[batch->count];
+    if (grid == 0) return 0;
+    sgd_multi_kernel<<<grid, 256, 0, as_stream(stream)>>>(*batch);
     return launched();
 }
 

@@ -10,6 +10,8 @@
 #include "bcnn_learner.h"
 
 #include <math.h>
+#include <stdint.h>
+#include <stdlib.h>
 
 #include "bcnn_dp.h"
 #include "bcnn_net.h"
@@ -44,18 +46,46 @@ static void update_learning_rate(bcnn_net *net) {
     }
 }
 
+/* Launch what bcnn_update_nodes has collected so far. */
+static void sgd_batch_flush(bcnn_net *net) {
+    bcnn_b200_sgd_batch *b = bcnn_ctx(net)->sgd_batch;
+    if (b && b->count > 0) {
+        bcnn_cuda_check(bcnn_b200_sgd_update_multi(b, bcnn_stream(net)));
+        b->count = 0;
+        b->first_block[0] = 0;
+    }
+}
+
+/* One SGD pass over a tensor: joins the step's batch inside bcnn_update_nodes, its own launch
+ * otherwise (or when the tensor does not fit the batch's common scalars / alignment). */
+static void sgd_pass(bcnn_net *net, float *w, float *g, int n, float wd_scale, float step,
+                     float g_scale) {
+    bcnn_b200_sgd_batch *b = bcnn_ctx(net)->sgd_batch;
+    if (n <= 0) return;
+    if (!b || (((uintptr_t)w | (uintptr_t)g) & 15) != 0) {
+        bcnn_cuda_check(bcnn_b200_sgd_update(w, g, (size_t)n, wd_scale, step, g_scale, bcnn_stream(net)));
+        return;
+    }
+    if (b->count > 0 && (b->step != step || b->g_scale != g_scale)) sgd_batch_flush(net);
+    if (b->count == BCNN_B200_SGD_MULTI_MAX) sgd_batch_flush(net);
+    const int i = b->count++;
+    b->w[i] = w;
+    b->g[i] = g;
+    b->n[i] = (unsigned int)n;
+    b->wd_scale[i] = wd_scale;
+    b->step = step;
+    b->g_scale = g_scale;
+    b->first_block[i + 1] = b->first_block[i] + ((unsigned int)n + 4095u) / 4096u;
+}
+
 void bcnn_sgd_update_gpu(bcnn_net *net, float *weights, float *biases, float *weights_grad,
                          float *biases_grad, int weights_size, int biases_size, int batch_size,
                          float learning_rate, float momentum, float decay) {
-    void *stream = bcnn_stream(net);
     const float step = -learning_rate / batch_size;
     const float g_scale = bcnn_net_grad_post_scale(net, momentum);
-    if (biases && biases_grad)
-        bcnn_cuda_check(bcnn_b200_sgd_update(biases, biases_grad, (size_t)biases_size, 0.0f, step,
-                                             g_scale, stream));
+    if (biases && biases_grad) sgd_pass(net, biases, biases_grad, biases_size, 0.0f, step, g_scale);
     if (weights && weights_grad)
-        bcnn_cuda_check(bcnn_b200_sgd_update(weights, weights_grad, (size_t)weights_size,
-                                             decay * batch_size, step, g_scale, stream));
+        sgd_pass(net, weights, weights_grad, weights_size, decay * batch_size, step, g_scale);
 }
 
 /* Host side of bcnn_adam_update_gpu (reference :134-164). The bias branch is the SGD bias
@@ -120,10 +150,23 @@ void bcnn_optimizer_step_gpu(bcnn_net *net, bcnn_tensor *weights, bcnn_tensor *b
 void bcnn_update_schedule(bcnn_net *net) { update_learning_rate(net); }
 
 void bcnn_update_nodes(bcnn_net *net) {
+    /* the SGD passes of the step travel together (BCNN_B200_SGD_MULTI=0: one launch per tensor).
+     * Tensors are distinct buffers and every pass is element-wise, so the order of the passes --
+     * and of Adam's weight kernels among them -- does not matter. */
+    static int multi = -1;
+    if (multi < 0) {
+        const char *e = getenv("BCNN_B200_SGD_MULTI");
+        multi = (e && e[0] == '0') ? 0 : 1;
+    }
+    bcnn_b200_sgd_batch *batch = multi ? (bcnn_b200_sgd_batch *)calloc(1, sizeof(*batch)) : NULL;
+    bcnn_ctx(net)->sgd_batch = batch;
     for (int i = 0; i < net->num_nodes; ++i) {
         bcnn_node *node = &net->nodes[i];
         if (node->update) node->update(net, node);
     }
+    sgd_batch_flush(net);
+    bcnn_ctx(net)->sgd_batch = NULL;
+    free(batch);
 }
 
 void bcnn_update(bcnn_net *net) {

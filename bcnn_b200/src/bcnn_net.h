@@ -39,6 +39,9 @@ typedef struct bcnn_cuda_context {
     int conv_math_explicit;   /* chosen by the caller / environment: bcnn_compile_net keeps it */
     int reference_quirks;     /* see bcnn_b200_set_reference_quirks; default 1 */
     struct bcnn_dp_state *dp; /* NULL unless bcnn_b200_dp_init succeeded */
+    /* bcnn_update_nodes collects the SGD passes of all parameter tensors of a step here and launches
+     * them together (bcnn_b200_sgd_update_multi); NULL outside bcnn_update_nodes */
+    struct bcnn_b200_sgd_batch *sgd_batch;
     /* per-node CUDA-event timers (the reference only has commented-out bh_timer calls in
      * bcnn_forward, src/bcnn_net.c:416-420); 4 events per node: fwd begin/end, bwd begin/end */
     int profile;

@@ -292,6 +292,22 @@ BCNN_B200_API size_t bcnn_b200_depthwise_scratch_floats(int n, int c, int ksize)
  * momentum (momentum / world_size under data parallelism). */
 BCNN_B200_API int bcnn_b200_sgd_update(float *w, float *g, size_t n, float wd_scale,
                                        float step, float g_scale, void *stream);
+/* The same pass over up to BCNN_B200_SGD_MULTI_MAX parameter tensors in ONE launch (a ResNet-50 step
+ * has 108 of them, most of a few KB: 108 launches of ~3 us each plus the gaps between them). Every
+ * tensor keeps its own wd_scale; step and g_scale are common. first_block[i] = first CTA of tensor i
+ * (4096 elements per CTA), first_block[count] = grid size; w[i] / g[i] must be 16-byte aligned.
+ * Element arithmetic is that of bcnn_b200_sgd_update: results are bit-identical. */
+#define BCNN_B200_SGD_MULTI_MAX 96
+typedef struct bcnn_b200_sgd_batch {
+    float *w[BCNN_B200_SGD_MULTI_MAX];
+    float *g[BCNN_B200_SGD_MULTI_MAX];
+    unsigned int n[BCNN_B200_SGD_MULTI_MAX];
+    float wd_scale[BCNN_B200_SGD_MULTI_MAX];
+    unsigned int first_block[BCNN_B200_SGD_MULTI_MAX + 1];
+    int count;
+    float step, g_scale;
+} bcnn_b200_sgd_batch;
+BCNN_B200_API int bcnn_b200_sgd_update_multi(const bcnn_b200_sgd_batch *batch, void *stream);
 /* One fused pass of bcnn_adam_update_gpu's weight branch (src/bcnn_learner.c:148-161; the CPU
  * arithmetic of :118-129 is the parity target):
  *   g += wd_scale * w;  m = (1-beta1) g + beta1 m;  v = (1-beta2) g^2 + beta2 v;

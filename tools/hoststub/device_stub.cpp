@@ -63,6 +63,21 @@ int bcnn_b200_sgd_update(float *w, float *g, size_t n, float wd_scale, float ste
     }
     return 0;
 }
+// layout of bcnn_b200_sgd_batch (include/bcnn_b200.h)
+struct stub_sgd_batch {
+    float *w[96];
+    float *g[96];
+    unsigned int n[96];
+    float wd_scale[96];
+    unsigned int first_block[97];
+    int count;
+    float step, g_scale;
+};
+int bcnn_b200_sgd_update_multi(const stub_sgd_batch *b, void *stream) {
+    for (int i = 0; b && i < b->count; ++i)
+        bcnn_b200_sgd_update(b->w[i], b->g[i], b->n[i], b->wd_scale[i], b->step, b->g_scale, stream);
+    return 0;
+}
 int bcnn_b200_adam_update(float *w, float *g, float *m, float *v, size_t n, float wd_scale,
                           float beta1, float beta2, float alpha, void *) {
     const float omb1 = 1.0f - beta1, omb2 = 1.0f - beta2;
