@@ -571,7 +571,10 @@ def run_own_arm(args):
             "peaks": peaks,
         }
         if dominant:
-            heaviest = max((r for r in per_shape if r["kernel"].startswith(("conv_fprop", "conv_dgrad"))),
+            # the heaviest launch class of the dominant kernel that has an `ncu --set full` capture
+            # (profiles/ncu_traffic.json); without any capture, the heaviest one and traffic = null
+            cands = [r for r in per_shape if r["kernel"].startswith(("conv_fprop", "conv_dgrad"))]
+            heaviest = max([r for r in cands if r.get("traffic")] or cands,
                            key=lambda r: r["ms_per_launch"] * r["launches_per_step"])
             result["roofline"] = {k: dominant[k] for k in ("kernel", "bound", "achieved", "peak", "unit", "frac",
                                                            "mixed_roof", "launches_hbm_bound",

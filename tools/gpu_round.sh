@@ -52,6 +52,7 @@ if [[ $PARTS == *n* ]]; then
     # the traffic entry bench.py reads (merged into profiles/ncu_traffic.json back home)
     python tools/ncu_traffic.py $OUT/ncu_traffic.json "$NAME=/tmp/ncu_$TAG/full_$STEM.ncu-rep" > /dev/null 2>&1
   done <<'EOF'
+conv_fprop 7x7/2 3->64 @224|3,224,64,7,2,3|s|conv_tma_fwd
 conv_fprop 1x1/1 64->256 @56|64,56,256,1,1,0|s|conv_tma_fwd
 conv_fprop 3x3/1 64->64 @56|64,56,64,3,1,1|s|conv_tma_fwd
 conv_fprop 3x3/1 256->256 @14|256,14,256,3,1,1|s|conv_tma_fwd
