@@ -1,6 +1,7 @@
-O=gpurun_out/r2zm; mkdir -p $O
-timeout 900 python -m pytest tests/test_nhwc_bf16_gpu.py -x -q > $O/t.log 2>&1; tail -2 $O/t.log
-timeout 600 python -m pytest tests/test_baseline_parity_gpu.py -x -q -k "layer_shapes" > $O/t2.log 2>&1; tail -2 $O/t2.log
-timeout 300 python tools/resident_sweep.py 256 5 "" w > $O/sweep_w.txt 2>&1; tail -2 $O/sweep_w.txt
-BCNN_B200_WG_NO_PAIR=1 timeout 300 python tools/resident_sweep.py 256 5 "" w > $O/sweep_w_nopair.txt 2>&1; tail -2 $O/sweep_w_nopair.txt
-paste <(awk '{print $1,$2,$3,$4,$5,$6}' $O/sweep_w.txt) <(awk '{print $6}' $O/sweep_w_nopair.txt) | grep wgrad
+O=gpurun_out/r2zo; mkdir -p $O
+timeout 600 python bench.py > $O/bench_n1.json 2> $O/bench_n1.err; head -c 250 $O/bench_n1.json; echo; tail -2 $O/bench_n1.err
+timeout 900 python -m pytest tests/test_nets_gpu.py tests/test_kernels_gpu.py -x -q > $O/t.log 2>&1; tail -3 $O/t.log
+BCNN_B200_DW_PLANE=0 timeout 200 python tools/dw_sweep.py 64 > $O/dw_rows.txt 2>&1
+timeout 200 python tools/dw_sweep.py 64 > $O/dw_default.txt 2>&1
+BCNN_B200_DW_PLANE=12544 timeout 200 python tools/dw_sweep.py 64 > $O/dw_all.txt 2>&1
+paste -d'|' <(cut -c1-58 $O/dw_rows.txt) <(cut -c20-58 $O/dw_default.txt) <(cut -c20-58 $O/dw_all.txt)
