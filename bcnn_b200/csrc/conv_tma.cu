@@ -355,11 +355,10 @@ pack_weights_tf32_kernel(const float *__restrict__ w, uint8_t *__restrict__ wpac
 struct FwdParams {
     float *dst;
     // batch-norm statistics fused into the epilogue (nullptr = off): every epilogue warp sums the
-    // accumulator rows (and their squares) of all the tiles its CTA walks and leaves one row per
-    // (CTA of the channel tile, TMEM lane quarter): stat_partial[(row * 2 + {0, 1}) * dst_c + channel],
-    // row = (blockIdx.x / n_tiles) * 4 + quarter; the grid is a multiple of n_tiles, so a CTA stays on
-    // one channel tile. Every entry is written exactly once; bn_stats_from_partials folds the rows in
-    // a fixed order.
+    // accumulator rows (and their squares) of all the tiles its CTA walks; the lane quarters are folded
+    // at the end and the CTA leaves one row: stat_partial[(row * 2 + {0, 1}) * dst_c + channel],
+    // row = blockIdx.x / n_tiles; the grid is a multiple of n_tiles, so a CTA stays on one channel
+    // tile. Every entry is written exactly once; bn_stats_from_partials folds the rows in a fixed order.
     float *stat_partial;
     const float *bias;
     const uint8_t *wpack;
@@ -1144,9 +1143,33 @@ conv_tma_fwd_kernel(const __grid_constant__ CUtensorMap tm_src, const __grid_con
             if (lane == 0) mbar_arrive(smem_u32(acc_empty + buf));
         }
         if (p.stat_partial != nullptr) {
-            // row = (CTA index among those of this channel tile) * 4 + lane quarter
+            // The four lane quarters of each half are folded here, in quarter order, through the (now
+            // idle) staging region, so the CTA leaves ONE row: the finalize kernel reads a quarter of
+            // the rows it used to (148 instead of 592 for a full grid).
+            if ((p.tstore || p.out16 == 1) && hw == 0 && lane == 0) bulk_wait_read_all();
+            named_bar_sync(3, 32 * FWD_EPI_WARPS);
+            float *fold = reinterpret_cast<float *>(smem + ring) + (size_t)half * 3 * 8 * 32;
+            if (q != 0) {
+#pragma unroll
+                for (int ci = 0; ci < 4; ++ci) {
+                    fold[((q - 1) * 8 + ci) * 32 + lane] = acc1[ci];
+                    fold[((q - 1) * 8 + 4 + ci) * 32 + lane] = acc2[ci];
+                }
+            }
+            named_bar_sync(3, 32 * FWD_EPI_WARPS);
+            if (q == 0) {
+#pragma unroll
+                for (int qq = 0; qq < 3; ++qq)
+#pragma unroll
+                    for (int ci = 0; ci < 4; ++ci) {
+                        acc1[ci] += fold[(qq * 8 + ci) * 32 + lane];
+                        acc2[ci] += fold[(qq * 8 + 4 + ci) * 32 + lane];
+                    }
+            }
+            // row = CTA index among those of this channel tile
             const uint32_t tile_n = blockIdx.x % (uint32_t)p.n_tiles;
-            const size_t row = (size_t)(blockIdx.x / (uint32_t)p.n_tiles) * 4 + (size_t)q;
+            const size_t row = (size_t)(blockIdx.x / (uint32_t)p.n_tiles);
+            if (q == 0)
 #pragma unroll
             for (int ci = 0; ci < 4; ++ci) {
                 // out16: this half owns the 64-channel groups half, half + 2 (two chunks each); narrow
@@ -1203,7 +1226,7 @@ struct FwdPlan {
     int vw, ph, sa, sb, b_resident;
     uint32_t a_slot_bytes, ring_bytes;
     int tile_pos;
-    int stat_rows;           // rows of the fused batch-norm partials: 4 per position tile
+    int stat_rows;           // rows of the fused batch-norm partials: one per CTA of a channel tile
     size_t stat_bytes;
 };
 
@@ -1410,12 +1433,12 @@ bool plan_fwd(const FwdGeom &g, FwdPlan *pl) {
     // fused statistics: grid = a multiple of n_tiles (0 rows: more channel tiles than SMs, no fusion)
     const long long per_tile = sm_count() / pl->n_tiles;
     const long long m_tiles = total / pl->n_tiles;
-    pl->stat_rows = (pl->tstore || pl->out16) ? (int)(4 * (per_tile < m_tiles ? per_tile : m_tiles)) : 0;
+    pl->stat_rows = (pl->tstore || pl->out16) ? (int)(per_tile < m_tiles ? per_tile : m_tiles) : 0;
     pl->stat_bytes = align256((size_t)pl->stat_rows * 2 * g.dst_c * sizeof(float));
     return true;
 }
 
-int stat_grid(const FwdPlan &pl) { return pl.stat_rows / 4 * pl.n_tiles; }
+int stat_grid(const FwdPlan &pl) { return pl.stat_rows * pl.n_tiles; }
 
 // ---- how a (descriptor, pass) maps onto launches of the kernel
 enum FwdRoute { ROUTE_NONE = 0, ROUTE_PLAIN, ROUTE_IM2COL, ROUTE_STRIDED_DGRAD };
