@@ -598,6 +598,9 @@ def bind_kernel_abi(lib: C.CDLL) -> None:
         "bcnn_b200_actbwd_grad_bias_nhwc": (i, [vp, vp, vp, i, sz, i, vp, vp]),
         "bcnn_b200_eltwise_forward_bf16": (i, [vp, vp, vp, sz, sz, i, vp]),
         "bcnn_b200_eltwise_backward_bf16": (i, [vp, vp, vp, vp, sz, sz, i, i, vp]),
+        "bcnn_b200_eltwise_backward_bn_reduce_bf16": (i, [vp, vp, vp, vp, sz, i, i, i, vp, vp, vp, vp, vp, vp,
+                                                          C.POINTER(C.c_int), vp]),
+        "bcnn_b200_bn_backward_nhwc_partials": (i, [vp] * 11 + [sz, i, vp, i, vp]),
         "bcnn_b200_maxpool_forward_nhwc": (i, [vp, vp, vp, i, i, i, i, i, i, i, i, vp]),
         "bcnn_b200_maxpool_backward_nhwc": (i, [vp, vp, vp, i, i, i, i, i, i, i, i, i, vp]),
         "bcnn_b200_avgpool_forward_nhwc": (i, [vp, vp, i, i, i, vp]),

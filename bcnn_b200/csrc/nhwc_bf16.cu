@@ -334,6 +334,8 @@ bn_bwd_apply_nhwc_kernel(const __nv_bfloat16 *__restrict__ x, const __nv_bfloat1
         k2[j] = __ldg(d_var + ch0 + j) * 2.0f * inv_count;
         k3[j] = __ldg(d_mean + ch0 + j) * inv_count;
     }
+    // four vectors per pass at two blocks per SM: fewer in flight with more blocks measured slower
+    // (22.34 / 22.48 / 22.65 ms per ResNet-50 step for 4 / 2 / 1, gpurun r2zu)
     constexpr int UNROLL = 4;
     for (size_t i0 = first; i0 < vectors; i0 += stride * UNROLL) {
         uint4 xv[UNROLL], gv[UNROLL];
@@ -485,6 +487,130 @@ eltwise_bwd_bf16_kernel(const __nv_bfloat16 *__restrict__ y, __nv_bfloat16 *dy, 
             } else if (!(flags & 2)) {
                 st_u4(db + i * 8, make_uint4(0, 0, 0, 0));
             }
+        }
+    }
+}
+
+// Residual-add backward fused with the first pass of the batch-norm backward of the branches it feeds
+// (a branch = conv + BN without activation read only by this add: its incoming gradient IS the masked
+// dy left here): dy' = dy * act'(y) written back, da / db copies or accumulations as above, and per
+// channel S1 = sum dy', S2 = sum dy' (x_branch - mean_branch) for up to two branches, in the partial-row
+// layout of reduce_nhwc_kernel<0> -- the branch's own reduction pass (a read of x and of dy') becomes
+// one extra read of x here. Block = lanes x cgb threads as in reduce_nhwc_kernel.
+__global__ void __launch_bounds__(256, 3)
+eltwise_bwd_bn_reduce_kernel(const __nv_bfloat16 *__restrict__ y, __nv_bfloat16 *dy, __nv_bfloat16 *da,
+                             __nv_bfloat16 *db, int act, int flags, size_t P, int C, int cgb, int lanes,
+                             const __nv_bfloat16 *__restrict__ xa, const float *__restrict__ mean_a,
+                             float *__restrict__ partial_a, const __nv_bfloat16 *__restrict__ xb,
+                             const float *__restrict__ mean_b, float *__restrict__ partial_b) {
+    extern __shared__ float red[];   // [lanes][cgb * 16]
+    const int t = threadIdx.x;
+    const int g = t % cgb, lane = t / cgb;
+    const int cg0 = blockIdx.y * cgb;
+    const int ch0 = (cg0 + g) * 8;
+    const bool active = lane < lanes && ch0 < C;
+    float ma[8], mb[8], s1[8], s2a[8], s2b[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) { s1[j] = s2a[j] = s2b[j] = 0.f; ma[j] = mb[j] = 0.f; }
+    if (active) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            if (xa) ma[j] = __ldg(mean_a + ch0 + j);
+            if (xb) mb[j] = __ldg(mean_b + ch0 + j);
+        }
+        const size_t step = (size_t)gridDim.x * lanes;
+        // one position per pass and three blocks per SM: with two positions in flight per thread the
+        // kernel needed 117 registers (two blocks per SM) and ran at 0.75 of HBM, which cost what the
+        // fusion saves (23.02 vs 22.38 ms per ResNet-50 step, gpurun r2zt)
+        constexpr int UNROLL = 1;
+        for (size_t p0 = (size_t)blockIdx.x * lanes + lane; p0 < P; p0 += step * UNROLL) {
+            // every load of the pass goes out before the first use, the old value of an accumulated
+            // branch gradient included (a fused branch has no da / db: at most one of ov's two uses)
+            uint4 yv[UNROLL], gv[UNROLL], av[UNROLL], bv[UNROLL], ov[UNROLL];
+#pragma unroll
+            for (int u = 0; u < UNROLL; ++u) {
+                const size_t p = p0 + u * step;
+                if (p < P) {
+                    const size_t o = p * C + ch0;
+                    yv[u] = ld_stream_u4(y + o);
+                    gv[u] = ld_u4(dy + o);
+                    if (xa) av[u] = ld_stream_u4(xa + o);
+                    if (xb) bv[u] = ld_stream_u4(xb + o);
+                    if (da && (flags & 1)) ov[u] = ld_u4(da + o);
+                    else if (db && (flags & 2)) ov[u] = ld_u4(db + o);
+                }
+            }
+#pragma unroll
+            for (int u = 0; u < UNROLL; ++u) {
+                const size_t p = p0 + u * step;
+                if (p < P) {
+                    const size_t o = p * C + ch0;
+                    float yf[8], gf[8], xf[8];
+                    unpack8(yv[u], yf);
+                    unpack8(gv[u], gf);
+                    if (act != ACT_NONE) {
+#pragma unroll
+                        for (int j = 0; j < 8; ++j) gf[j] *= act_bwd_factor(yf[j], act, 0.f);
+                        const uint4 packed = pack8(gf);
+                        st_u4(dy + o, packed);
+                        unpack8(packed, gf);   // the sums are those of the stored (BF16) gradient
+                    }
+                    if (da) {
+                        if (flags & 1) {
+                            float of[8];
+                            unpack8(ov[u], of);
+#pragma unroll
+                            for (int j = 0; j < 8; ++j) of[j] += gf[j];
+                            st_u4(da + o, pack8(of));
+                        } else {
+                            st_u4(da + o, pack8(gf));
+                        }
+                    }
+                    if (db) {
+                        if (flags & 2) {
+                            float of[8];
+                            if (da && (flags & 1)) unpack8(ld_u4(db + o), of);   // both branches accumulate: rare
+                            else unpack8(ov[u], of);
+#pragma unroll
+                            for (int j = 0; j < 8; ++j) of[j] += gf[j];
+                            st_u4(db + o, pack8(of));
+                        } else {
+                            st_u4(db + o, pack8(gf));
+                        }
+                    }
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) s1[j] += gf[j];
+                    if (xa) {
+                        unpack8(av[u], xf);
+#pragma unroll
+                        for (int j = 0; j < 8; ++j) s2a[j] += gf[j] * (xf[j] - ma[j]);
+                    }
+                    if (xb) {
+                        unpack8(bv[u], xf);
+#pragma unroll
+                        for (int j = 0; j < 8; ++j) s2b[j] += gf[j] * (xf[j] - mb[j]);
+                    }
+                }
+            }
+        }
+    }
+    // fold the position lanes of this block, branch a then branch b
+    for (int br = 0; br < 2; ++br) {
+        float *partial = br == 0 ? partial_a : partial_b;
+        if ((br == 0 ? xa : xb) == nullptr) continue;   // uniform over the block
+        if (br == 1) __syncthreads();
+        if (lane < lanes) {
+            float *row = red + (size_t)lane * cgb * 16 + g * 16;
+#pragma unroll
+            for (int j = 0; j < 8; ++j) { row[j] = s1[j]; row[8 + j] = br == 0 ? s2a[j] : s2b[j]; }
+        }
+        __syncthreads();
+        for (int i = t; i < cgb * 16; i += 256) {
+            float s = 0.f;
+            for (int l = 0; l < lanes; ++l) s += red[(size_t)l * cgb * 16 + i];
+            const int gg = i / 16, k = (i % 16) / 8, j = i % 8;
+            const int ch = (cg0 + gg) * 8 + j;
+            if (ch < C) partial[((size_t)blockIdx.x * 2 + k) * C + ch] = s;
         }
     }
 }
@@ -729,14 +855,14 @@ maxpool_bwd_s2_nhwc_kernel(__nv_bfloat16 *dx, const __nv_bfloat16 *__restrict__ 
 }
 
 struct ReducePlan { int cgb, lanes, gx, gy; size_t smem; };
-ReducePlan plan_reduce(size_t P, int C) {
+ReducePlan plan_reduce(size_t P, int C, int blocks_per_sm = 2) {
     ReducePlan r;
     const int cg = C / 8;
     r.cgb = cg < 256 ? cg : 256;
     r.lanes = 256 / r.cgb;
     r.gy = ceil_div(cg, r.cgb);
     size_t want = ceil_div_sz(P, (size_t)r.lanes * 8);
-    size_t cap = (size_t)2 * sm_count() / r.gy;
+    size_t cap = (size_t)blocks_per_sm * sm_count() / r.gy;
     if (cap < 1) cap = 1;
     r.gx = (int)(want < cap ? (want ? want : 1) : cap);
     r.smem = (size_t)r.lanes * r.cgb * 16 * sizeof(float);
@@ -761,7 +887,7 @@ extern "C" int bcnn_b200_bf16nhwc_to_f32nchw(const void *in, float *out, int n, 
     return launched();
 }
 
-extern "C" size_t bcnn_b200_nhwc_scratch_floats(int c) { return (size_t)2 * 2 * sm_count() * c + 64; }
+extern "C" size_t bcnn_b200_nhwc_scratch_floats(int c) { return (size_t)2 * 4 * sm_count() * c + 64; }   // up to 4 partial rows per SM
 
 extern "C" int bcnn_b200_bn_stats_nhwc(const void *x, size_t positions, int c, float *saved_mean,
                                        float *saved_var, float *run_mean, float *run_var,
@@ -830,6 +956,50 @@ extern "C" int bcnn_b200_bn_backward_nhwc(const void *x, void *dy, void *dx, con
     bn_bwd_apply_nhwc_kernel<<<fixed_group_grid(vectors, cg, 256, 4), 256, 0, st>>>(
         xb, gb, reinterpret_cast<__nv_bfloat16 *>(dx), mean, var, gamma, beta, d_mean, d_var, act,
         1.0f / (float)positions, vectors, cg);
+    return launched();
+}
+
+// Second half of bcnn_b200_bn_backward_nhwc for a layer whose reduction pass was fused into the
+// residual add behind it (bcnn_b200_eltwise_backward_bn_reduce_bf16): finalize from its partial rows,
+// then apply. act must be NONE (the fused layers have no activation of their own).
+extern "C" int bcnn_b200_bn_backward_nhwc_partials(const void *x, void *dy, void *dx, const float *mean,
+                                                   const float *var, const float *gamma, const float *beta,
+                                                   float *g_gamma, float *g_beta, float *d_mean, float *d_var,
+                                                   size_t positions, int c, const float *partial, int rows,
+                                                   void *stream) {
+    if (positions == 0 || c == 0) return 0;
+    if (c % 8 || rows <= 0 || !partial) return (int)cudaErrorInvalidValue;
+    cudaStream_t st = as_stream(stream);
+    bn_bwd_finalize_nhwc_kernel<<<ceil_div(c, 32), dim3(32, 32), 0, st>>>(partial, rows, c, var, gamma, g_gamma,
+                                                                            g_beta, d_mean, d_var);
+    int err = launched();
+    if (err) return err;
+    const int cg = c / 8;
+    const size_t vectors = positions * cg;
+    bn_bwd_apply_nhwc_kernel<<<fixed_group_grid(vectors, cg, 256, 4), 256, 0, st>>>(
+        reinterpret_cast<const __nv_bfloat16 *>(x), reinterpret_cast<__nv_bfloat16 *>(dy),
+        reinterpret_cast<__nv_bfloat16 *>(dx), mean, var, gamma, beta, d_mean, d_var, ACT_NONE,
+        1.0f / (float)positions, vectors, cg);
+    return launched();
+}
+
+extern "C" int bcnn_b200_eltwise_backward_bn_reduce_bf16(const void *y, void *dy, void *da, void *db,
+                                                         size_t positions, int c, int act, int accumulate_flags,
+                                                         const void *xa, const float *mean_a, float *partial_a,
+                                                         const void *xb, const float *mean_b, float *partial_b,
+                                                         int *rows, void *stream) {
+    if (rows) *rows = 0;
+    if (positions == 0 || c == 0) return 0;
+    if (c % 8 || !(act == ACT_NONE || act == ACT_RELU || act == ACT_LRELU) || (!xa && !xb) ||
+        (xa && (!mean_a || !partial_a)) || (xb && (!mean_b || !partial_b)))
+        return (int)cudaErrorInvalidValue;
+    const ReducePlan r = plan_reduce(positions, c, 3);   // three blocks per SM
+    eltwise_bwd_bn_reduce_kernel<<<dim3(r.gx, r.gy), 256, r.smem, as_stream(stream)>>>(
+        reinterpret_cast<const __nv_bfloat16 *>(y), reinterpret_cast<__nv_bfloat16 *>(dy),
+        reinterpret_cast<__nv_bfloat16 *>(da), reinterpret_cast<__nv_bfloat16 *>(db), act, accumulate_flags,
+        positions, c, r.cgb, r.lanes, reinterpret_cast<const __nv_bfloat16 *>(xa), mean_a, partial_a,
+        reinterpret_cast<const __nv_bfloat16 *>(xb), mean_b, partial_b);
+    if (rows) *rows = r.gx;
     return launched();
 }
 

@@ -162,6 +162,32 @@ void bcnn_conv_layer_bn_operand(bcnn_net *net, bcnn_node *node, const void **raw
     }
 }
 
+int bcnn_conv_layer_bn_reduce_operand(bcnn_net *net, bcnn_node *node, const void **raw, const float **mean,
+                                      float **partial) {
+    static int off = -1;
+    if (off < 0) {
+        const char *e = getenv("BCNN_B200_FUSED_BN_REDUCE");
+        off = (e && e[0] == '0') ? 1 : 0;
+    }
+    bcnn_conv_param *param = (bcnn_conv_param *)node->param;
+    if (off || node->type != BCNN_LAYER_CONV2D || !param->batch_norm || net->mode != BCNN_MODE_TRAIN ||
+        param->activation != BCNN_ACT_NONE || !param->bn_raw16_gpu)
+        return 0;
+    if (!param->bn_partial_gpu) {
+        const int c = net->tensors[node->dst[0]].c;
+        param->bn_partial_gpu = (float *)bcnn_b200_malloc(bcnn_b200_nhwc_scratch_floats(c) * sizeof(float));
+        if (!param->bn_partial_gpu) return 0;
+    }
+    *raw = param->bn_raw16_gpu;
+    *mean = param->saved_mean.data_gpu;
+    *partial = param->bn_partial_gpu;
+    return 1;
+}
+
+void bcnn_conv_layer_bn_reduce_done(bcnn_node *node, int rows) {
+    ((bcnn_conv_param *)node->param)->bn_partial_rows = rows;
+}
+
 void bcnn_conv_layer_materialize(bcnn_net *net, bcnn_node *node) {
     bcnn_conv_param *param = (bcnn_conv_param *)node->param;
     bcnn_tensor *dst = &net->tensors[node->dst[0]];
@@ -293,6 +319,14 @@ static void conv_backward_resident(bcnn_net *net, bcnn_node *node) {
         const int train = net->mode == BCNN_MODE_TRAIN;
         const float *mean = train ? param->saved_mean.data_gpu : t[node->src[3]].data_gpu;
         const float *var = train ? param->saved_variance.data_gpu : t[node->src[4]].data_gpu;
+        if (param->bn_partial_rows > 0) {   /* the residual add behind this node did the reduction pass */
+            bcnn_cuda_check(bcnn_b200_bn_backward_nhwc_partials(
+                param->bn_raw16_gpu, dy_in, dy16, mean, var, t[node->src[5]].data_gpu, biases->data_gpu,
+                t[node->src[5]].grad_data_gpu, biases->grad_data_gpu, param->saved_mean.grad_data_gpu,
+                param->saved_variance.grad_data_gpu, positions, dst->c, param->bn_partial_gpu,
+                param->bn_partial_rows, stream));
+            param->bn_partial_rows = 0;
+        } else
         bcnn_cuda_check(bcnn_b200_bn_backward_nhwc(
             param->bn_raw16_gpu, dy_in, dy16, mean, var, t[node->src[5]].data_gpu, biases->data_gpu,
             t[node->src[5]].grad_data_gpu, biases->grad_data_gpu, param->saved_mean.grad_data_gpu,
@@ -462,6 +496,7 @@ void bcnn_release_param_conv_layer(bcnn_node *node) {
     bcnn_tensor_destroy(&param->saved_variance);
     bcnn_b200_free(param->bn_workspace_gpu);
     bcnn_b200_free(param->bn_raw16_gpu);
+    bcnn_b200_free(param->bn_partial_gpu);
     bcnn_b200_free(param->shadows.x);
     bcnn_b200_free(param->reduce_scratch_gpu);
     bcnn_b200_free(param->adam_m_gpu);

@@ -53,8 +53,18 @@ typedef struct bcnn_conv_param {
      * (0 = not decided yet, 1 = yes, -1 = no: it takes the FP32-tensor path) */
     void *bn_raw16_gpu;
     int resident_state;
+    /* batch-norm backward whose reduction pass the residual add behind this node has already done
+     * (bcnn_b200_eltwise_backward_bn_reduce_bf16): the partial rows and how many (0 = none pending) */
+    float *bn_partial_gpu;
+    int bn_partial_rows;
 } bcnn_conv_param;
 
+/* For the residual add that feeds this node's backward (grad alias): the raw convolution result, the
+ * saved mean and a buffer for the partial rows of the fused reduction; 0 when the node cannot take
+ * them (no batch norm, not TRAIN, allocation failed). bcnn_conv_layer_bn_reduce_done records the rows. */
+int bcnn_conv_layer_bn_reduce_operand(bcnn_net *net, bcnn_node *node, const void **raw, const float **mean,
+                                      float **partial);
+void bcnn_conv_layer_bn_reduce_done(bcnn_node *node, int rows);
 void bcnn_forward_conv_layer(bcnn_net *net, bcnn_node *node);
 void bcnn_backward_conv_layer(bcnn_net *net, bcnn_node *node);
 void bcnn_update_conv_layer(bcnn_net *net, bcnn_node *node);

@@ -207,6 +207,12 @@ void bcnn_backward_eltwise_layer(bcnn_net *net, bcnn_node *node) {
         const void *y16 = param->activation == BCNN_ACT_NONE ? NULL : bcnn_net_data16_in(net, node->dst[0]);
         void *dy16 = bcnn_net_grad16_in(net, node->dst[0]);
         void *g16[2] = {NULL, NULL};
+        /* aliased branches that are conv + BN: this node also does the reduction pass of their
+         * batch-norm backward (one extra read of the branch's raw result instead of a pass of its own) */
+        const void *bn_x[2] = {NULL, NULL};
+        const float *bn_mean[2] = {NULL, NULL};
+        float *bn_partial[2] = {NULL, NULL};
+        bcnn_node *bn_node[2] = {NULL, NULL};
         for (int i = 0; i < 2; ++i) {
             if (!t[node->src[i]].grad_data_gpu) continue;
             /* a source only this node reads, produced by a conv + BN without activation: its
@@ -218,11 +224,25 @@ void bcnn_backward_eltwise_layer(bcnn_net *net, bcnn_node *node) {
                 bcnn_net_sole_eltwise_consumer(net, node->src[i], &consumer) &&
                 &net->nodes[consumer] == node && bcnn_conv_layer_takes_grad_alias(net, node->src[i])) {
                 r->grad_alias = node->dst[0] + 1;
+                if (bcnn_conv_layer_bn_reduce_operand(net, &net->nodes[r->producer], &bn_x[i], &bn_mean[i],
+                                                      &bn_partial[i]))
+                    bn_node[i] = &net->nodes[r->producer];
                 continue;
             }
             g16[i] = (flags & (1 << i)) ? bcnn_net_grad16_in(net, node->src[i])
                                         : bcnn_net_grad16_out(net, node->src[i]);
         }
+        const bcnn_activation a = param->activation;
+        if ((bn_node[0] || bn_node[1]) && n_add == sz &&
+            (a == BCNN_ACT_NONE || a == BCNN_ACT_RELU || a == BCNN_ACT_LRELU)) {
+            int rows = 0;
+            bcnn_cuda_check(bcnn_b200_eltwise_backward_bn_reduce_bf16(
+                y16 ? y16 : dy16, dy16, g16[0], g16[1], (size_t)dst->n * dst->h * dst->w, dst->c, a, flags,
+                bn_node[0] ? bn_x[0] : NULL, bn_mean[0], bn_partial[0], bn_node[1] ? bn_x[1] : NULL, bn_mean[1],
+                bn_partial[1], &rows, bcnn_stream(net)));
+            for (int i = 0; i < 2; ++i)
+                if (bn_node[i]) bcnn_conv_layer_bn_reduce_done(bn_node[i], rows);
+        } else
         bcnn_cuda_check(bcnn_b200_eltwise_backward_bf16(y16 ? y16 : dy16, dy16, g16[0], g16[1], (size_t)sz,
                                                         (size_t)n_add, param->activation, flags,
                                                         bcnn_stream(net)));

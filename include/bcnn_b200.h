@@ -443,6 +443,25 @@ BCNN_B200_API int bcnn_b200_eltwise_forward_bf16(const void *a, const void *b, v
 BCNN_B200_API int bcnn_b200_eltwise_backward_bf16(const void *y, void *dy, void *da, void *db,
                                                   size_t sz, size_t n_add, int act,
                                                   int accumulate_flags, void *stream);
+/* Residual-add backward fused with the reduction pass of the batch-norm backward of the branches it
+ * feeds (conv + BN without activation whose only reader is the add, reference pair
+ * src/layers/bcnn_eltwise_layer.c:137-161 + src/layers/bcnn_batchnorm_layer.c:263-299): besides what
+ * bcnn_b200_eltwise_backward_bf16 does (whole-tensor add only), per channel S1 = sum dy',
+ * S2 = sum dy' (x - mean) of branch a and / or b (x = the branch's raw convolution result, NULL = not a
+ * fused branch) go to partial_a / partial_b (bcnn_b200_nhwc_scratch_floats(c) floats each) as *rows
+ * partial rows; bcnn_b200_bn_backward_nhwc_partials then finishes that branch's batch-norm backward
+ * (finalize + apply) without reading x and dy' a first time. */
+BCNN_B200_API int bcnn_b200_eltwise_backward_bn_reduce_bf16(const void *y, void *dy, void *da, void *db,
+                                                            size_t positions, int c, int act,
+                                                            int accumulate_flags, const void *xa,
+                                                            const float *mean_a, float *partial_a,
+                                                            const void *xb, const float *mean_b,
+                                                            float *partial_b, int *rows, void *stream);
+BCNN_B200_API int bcnn_b200_bn_backward_nhwc_partials(const void *x, void *dy, void *dx, const float *mean,
+                                                      const float *var, const float *gamma,
+                                                      const float *beta, float *g_gamma, float *g_beta,
+                                                      float *d_mean, float *d_var, size_t positions, int c,
+                                                      const float *partial, int rows, void *stream);
 /* max pooling with the reference's rule (first max wins, bottom / right padding only); the index
  * buffer is laid out like y (NHWC), its values are the reference's flat NCHW indices (-1: empty
  * window). Shadows bcnn_b200_maxpool_forward / _backward; accumulate == 0 overwrites dx. */

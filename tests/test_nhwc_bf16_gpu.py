@@ -384,3 +384,69 @@ def test_fused_bn_residual_add_matches_the_unfused_kernels(shape, kinds):
     check(lib.bcnn_b200_bn_add_act_nhwc(*args, got.ptr, pos, c, ACT["relu"], None))
     assert_close(nchw_from_bits(got.download(np.uint16), shape), nchw_from_bits(want.download(np.uint16), shape),
                  BF16_OUT_TOL, "fused vs unfused")
+
+
+@pytest.mark.parametrize("shape", [(3, 64, 14, 14), (2, 256, 7, 7), (4, 8, 5, 3), (2, 2048, 3, 3)])
+@pytest.mark.parametrize("branches", ["a", "b", "ab"])
+@pytest.mark.parametrize("act", ["relu", "none"])
+def test_fused_residual_add_backward_bn_reduce_matches_the_unfused_kernels(shape, branches, act):
+    """eltwise_backward_bn_reduce (mask the add's gradient, copy / accumulate it for a plain branch and
+    reduce S1, S2 for the batch-normed branches in one pass) + bn_backward_nhwc_partials against
+    eltwise_backward_bf16 + bn_backward_nhwc (itself held to the oracle above): the masked gradient and
+    the plain branch bit-identical, the parameter gradients 1e-4, dx within the BF16 output bar."""
+    lib = capi.b200()
+    n, c, h, w = shape
+    pos = n * h * w
+    r = rng(len(branches) + sum(shape))
+    y = dev(nhwc_bits(rounded(f32(np.maximum(r.normal(0.1, 1.0, size=shape), 0.0)))))
+    dy0 = nhwc_bits(rounded(f32(r.uniform(-1, 1, size=shape))))
+    xs = [dev(nhwc_bits(rounded(f32(r.normal(0.2, 1.0, size=shape))))) for _ in range(2)]
+    prm = [dict(mean=dev(f32(r.normal(0.2, 0.1, size=c))), var=dev(f32(r.uniform(0.5, 2.0, size=c))),
+                gamma=dev(f32(r.uniform(0.5, 1.5, size=c))), beta=dev(f32(r.uniform(-0.3, 0.3, size=c))))
+           for _ in range(2)]
+    plain0 = nhwc_bits(rounded(f32(r.uniform(-1, 1, size=shape))))   # existing gradient of a plain branch
+    fused = [("a" in branches), ("b" in branches)]
+
+    def bn_bwd(i, dy_buf, partial=None, rows=0):
+        gg, gb, dm, dv = dev(np.ones(c, np.float32)), dev(np.ones(c, np.float32)), dev_zeros(c), dev_zeros(c)
+        dx = dev_zeros(pos * c, 2)
+        q = prm[i]
+        if partial is None:
+            scratch = dev_zeros(lib.bcnn_b200_nhwc_scratch_floats(c))
+            check(lib.bcnn_b200_bn_backward_nhwc(xs[i].ptr, dy_buf.ptr, dx.ptr, q["mean"].ptr, q["var"].ptr,
+                                                 q["gamma"].ptr, q["beta"].ptr, gg.ptr, gb.ptr, dm.ptr, dv.ptr,
+                                                 pos, c, ACT["none"], scratch.ptr, None))
+        else:
+            check(lib.bcnn_b200_bn_backward_nhwc_partials(xs[i].ptr, dy_buf.ptr, dx.ptr, q["mean"].ptr,
+                                                          q["var"].ptr, q["gamma"].ptr, q["beta"].ptr, gg.ptr,
+                                                          gb.ptr, dm.ptr, dv.ptr, pos, c, partial.ptr, rows, None))
+        return gg.download(), gb.download(), dx.download(np.uint16)
+
+    # unfused: the add masks dy in place and accumulates into the plain branch (flag bit of that operand)
+    dy_u, plain_u = dev(dy0), dev(plain0)
+    da = None if fused[0] else plain_u.ptr
+    db = None if fused[1] else plain_u.ptr
+    flags = (0 if fused[0] else 1) | (0 if fused[1] else 2)
+    check(lib.bcnn_b200_eltwise_backward_bf16(y.ptr, dy_u.ptr, da, db, pos * c, pos * c, ACT[act], flags, None))
+    want = [bn_bwd(i, dy_u) if fused[i] else None for i in range(2)]
+    # fused
+    dy_f, plain_f = dev(dy0), dev(plain0)
+    da = None if fused[0] else plain_f.ptr
+    db = None if fused[1] else plain_f.ptr
+    partials = [dev_zeros(lib.bcnn_b200_nhwc_scratch_floats(c)) for _ in range(2)]
+    rows = capi.C.c_int(0)
+    check(lib.bcnn_b200_eltwise_backward_bn_reduce_bf16(
+        y.ptr, dy_f.ptr, da, db, pos, c, ACT[act], flags,
+        xs[0].ptr if fused[0] else None, prm[0]["mean"].ptr if fused[0] else None,
+        partials[0].ptr if fused[0] else None, xs[1].ptr if fused[1] else None,
+        prm[1]["mean"].ptr if fused[1] else None, partials[1].ptr if fused[1] else None, capi.C.byref(rows), None))
+    assert rows.value > 0
+    assert np.array_equal(dy_f.download(np.uint16), dy_u.download(np.uint16)), "masked gradient"
+    assert np.array_equal(plain_f.download(np.uint16), plain_u.download(np.uint16)), "plain branch"
+    for i in range(2):
+        if not fused[i]:
+            continue
+        gg, gb, dx = bn_bwd(i, dy_f, partials[i], rows.value)
+        assert_close(gb, want[i][1], 1e-4, f"g_beta {i}")
+        assert_close(gg, want[i][0], 1e-4, f"g_gamma {i}")
+        assert_close(nchw_from_bits(dx, shape), nchw_from_bits(want[i][2], shape), BF16_OUT_TOL, f"bn dx {i}")

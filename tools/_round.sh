@@ -1,1 +1,1 @@
-bash tools/gpu_round.sh r2final tbspln
+bash tools/gpu_round.sh r2final2 tbpl
