@@ -155,6 +155,21 @@ extern "C" int bcnn_b200_conv_forward_bn_stats_nhwc(const bcnn_b200_conv_desc *d
     return bcnn_b200_bn_stats_nhwc(y, positions, d->cout, saved_mean, saved_var, run_mean, run_var,
                                    nhwc_scratch, scratch, stream);
 }
+extern "C" size_t bcnn_b200_conv_pack_job_bytes(void) { return conv_pack_job_bytes(); }
+extern "C" int bcnn_b200_conv_nhwc_pack_jobs(const bcnn_b200_conv_desc *d, int dgrad, const float *w, void *dst,
+                                             void *jobs, int max_jobs, size_t *bytes) {
+    return conv_nhwc_pack_jobs(d, dgrad, w, dst, jobs, max_jobs, bytes);
+}
+extern "C" unsigned int bcnn_b200_conv_pack_table_finish(void *jobs, int count) {
+    return conv_pack_table_finish(jobs, count);
+}
+extern "C" int bcnn_b200_conv_pack_run(const void *jobs_dev, int count, unsigned int grid, void *stream) {
+    return conv_pack_run(jobs_dev, count, grid, as_stream(stream));
+}
+extern "C" void bcnn_b200_conv_prepacked_set(const float *w, int dgrad, const void *image) {
+    conv_prepacked_set(w, dgrad, image);
+}
+extern "C" void bcnn_b200_conv_prepacked_enable(int on) { conv_prepacked_enable(on); }
 extern "C" int bcnn_b200_conv_backward_data_nhwc(const bcnn_b200_conv_desc *d, const float *w,
                                                  const void *dy, void *dx, int accumulate,
                                                  void *workspace, size_t workspace_bytes, void *stream) {

@@ -73,6 +73,16 @@ int conv_nhwc_backward_weights(const bcnn_b200_conv_desc *d, const void *x, cons
                                void *workspace, size_t workspace_bytes, bcnn_b200_conv_shadows *sh,
                                cudaStream_t st);
 
+// Packed weight images kept by the caller (conv_tma.cu): jobs for one pack launch over many layers, and
+// the (weights, pass) -> image registry the resident launchers consult.
+size_t conv_pack_job_bytes();
+int conv_nhwc_pack_jobs(const bcnn_b200_conv_desc *d, int dgrad, const float *w, void *dst, void *jobs,
+                        int max_jobs, size_t *bytes);
+unsigned int conv_pack_table_finish(void *jobs, int count);
+int conv_pack_run(const void *jobs_dev, int count, unsigned int grid, cudaStream_t st);
+void conv_prepacked_set(const float *w, int dgrad, const void *image);
+void conv_prepacked_enable(int on);
+
 // batchnorm.cu: TRAIN statistics from the per-tile partial sums a convolution epilogue left
 // (partial[(row * 2 + {0: sum, 1: sum of squares}) * c + channel]), folded in a fixed order.
 int bn_stats_from_partials(const float *partial, int rows, int c, double count, float *saved_mean,

@@ -308,46 +308,82 @@ struct TapMap {
 };
 
 // BF16: rows of 64 bf16 (same 128 bytes, same 16-byte chunk swizzle), 8 elements per chunk.
+// One 16-byte chunk i of a packed image.
+template <bool BF16>
+__device__ __forceinline__ void pack_chunk(const float *__restrict__ w, uint8_t *__restrict__ wpack, int dgrad,
+                                           int cout, int cin, int kk, int n_tile, int kc_blocks,
+                                           const TapMap &taps, size_t i) {
+    constexpr int EPC = BF16 ? 8 : 4;   // elements per 16-byte chunk
+    const int k_blocks = taps.n * kc_blocks;
+    const int chunk = (int)(i & 7);
+    size_t r = i >> 3;
+    const int row_in_tile = (int)(r % n_tile);
+    size_t r2 = r / n_tile;
+    const int kb = (int)(r2 % k_blocks);
+    const int tile = (int)(r2 / k_blocks);
+    const int row = tile * n_tile + row_in_tile;
+    const int tap = kb / kc_blocks, cb = kb - tap * kc_blocks;
+    const int row_c = dgrad ? cin : cout;
+    const int k_c = dgrad ? cout : cin;
+    const int wtap = taps.idx[tap];
+    float v[EPC];
+#pragma unroll
+    for (int e = 0; e < EPC; ++e) {
+        const int kc = (cb * 8 + chunk) * EPC + e;
+        float val = 0.f;
+        if (row < row_c && kc < k_c) {
+            const int co = dgrad ? kc : row, ci = dgrad ? row : kc;
+            val = __ldg(w + ((size_t)co * cin + ci) * kk + wtap);
+        }
+        v[e] = val;
+    }
+    const size_t tile_base = ((size_t)tile * k_blocks + kb) * (size_t)n_tile * 128;
+    const size_t off = tile_base + (size_t)row_in_tile * 128 + (size_t)((chunk ^ (row_in_tile & 7)) * 16);
+    if constexpr (BF16) {
+        *reinterpret_cast<uint4 *>(wpack + off) =
+            make_uint4(pack_bf16x2(v[0], v[1]), pack_bf16x2(v[2], v[3]), pack_bf16x2(v[4], v[5]),
+                       pack_bf16x2(v[EPC - 2], v[EPC - 1]));
+    } else {
+        *reinterpret_cast<float4 *>(wpack + off) = make_float4(v[0], v[1], v[2], v[3]);
+    }
+}
+
 template <bool BF16>
 __global__ void __launch_bounds__(256)
 pack_weights_tf32_kernel(const float *__restrict__ w, uint8_t *__restrict__ wpack, int dgrad, int cout,
                          int cin, int kk, int n_tile, int n_tiles, int kc_blocks, const TapMap taps) {
-    constexpr int EPC = BF16 ? 8 : 4;   // elements per 16-byte chunk
-    const int k_blocks = taps.n * kc_blocks;
-    const size_t chunks = (size_t)n_tiles * n_tile * k_blocks * 8;
+    const size_t chunks = (size_t)n_tiles * n_tile * taps.n * kc_blocks * 8;
     for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < chunks;
-         i += (size_t)gridDim.x * blockDim.x) {
-        const int chunk = (int)(i & 7);
-        size_t r = i >> 3;
-        const int row_in_tile = (int)(r % n_tile);
-        size_t r2 = r / n_tile;
-        const int kb = (int)(r2 % k_blocks);
-        const int tile = (int)(r2 / k_blocks);
-        const int row = tile * n_tile + row_in_tile;
-        const int tap = kb / kc_blocks, cb = kb - tap * kc_blocks;
-        const int row_c = dgrad ? cin : cout;
-        const int k_c = dgrad ? cout : cin;
-        const int wtap = taps.idx[tap];
-        float v[EPC];
-#pragma unroll
-        for (int e = 0; e < EPC; ++e) {
-            const int kc = (cb * 8 + chunk) * EPC + e;
-            float val = 0.f;
-            if (row < row_c && kc < k_c) {
-                const int co = dgrad ? kc : row, ci = dgrad ? row : kc;
-                val = __ldg(w + ((size_t)co * cin + ci) * kk + wtap);
-            }
-            v[e] = val;
-        }
-        const size_t tile_base = ((size_t)tile * k_blocks + kb) * (size_t)n_tile * 128;
-        const size_t off = tile_base + (size_t)row_in_tile * 128 + (size_t)((chunk ^ (row_in_tile & 7)) * 16);
-        if constexpr (BF16) {
-            *reinterpret_cast<uint4 *>(wpack + off) =
-                make_uint4(pack_bf16x2(v[0], v[1]), pack_bf16x2(v[2], v[3]), pack_bf16x2(v[4], v[5]),
-                           pack_bf16x2(v[EPC - 2], v[EPC - 1]));
-        } else {
-            *reinterpret_cast<float4 *>(wpack + off) = make_float4(v[0], v[1], v[2], v[3]);
-        }
+         i += (size_t)gridDim.x * blockDim.x)
+        pack_chunk<BF16>(w, wpack, dgrad, cout, cin, kk, n_tile, kc_blocks, taps, i);
+}
+
+// Every packed BF16 image of a net in ONE launch (the resident step packed 114 images -- fprop, dgrad
+// and the classes of strided dgrads of 53 layers -- in 114 launches of ~4 us): a table of jobs in
+// device memory, CTA -> job by bisection of first_block, 2048 chunks per CTA.
+struct PackJob {
+    const float *w;
+    uint8_t *dst;
+    int dgrad, cout, cin, kk, n_tile, n_tiles, kc_blocks;
+    unsigned int first_block;   // first CTA of this job; the table ends with a sentinel job holding the grid size
+    TapMap taps;
+};
+constexpr int PACK_JOB_CHUNKS = 2048;
+
+__global__ void __launch_bounds__(256)
+pack_jobs_kernel(const PackJob *__restrict__ jobs, int count) {
+    int lo = 0, hi = count;
+    while (hi - lo > 1) {
+        const int mid = (lo + hi) >> 1;
+        if (blockIdx.x >= jobs[mid].first_block) lo = mid;
+        else hi = mid;
+    }
+    const PackJob &j = jobs[lo];
+    const size_t chunks = (size_t)j.n_tiles * j.n_tile * j.taps.n * j.kc_blocks * 8;
+    const size_t base = (size_t)(blockIdx.x - j.first_block) * PACK_JOB_CHUNKS;
+    for (int k = threadIdx.x; k < PACK_JOB_CHUNKS; k += 256) {
+        const size_t i = base + k;
+        if (i < chunks) pack_chunk<true>(j.w, j.dst, j.dgrad, j.cout, j.cin, j.kk, j.n_tile, j.kc_blocks, j.taps, i);
     }
 }
 
@@ -1627,6 +1663,20 @@ int run_fwd(const FwdGeom &g, const FwdPlan &pl, const void *src, const uint8_t 
                    : launch_fwd_kernel<true, false>(tm, tm_dst, p, smem, st, grid);
 }
 
+// Packed images somebody else keeps up to date (bcnn_b200_conv_prepacked_*: the net runtime packs every
+// layer's images in one launch at the start of a training step): (weights, fprop / dgrad) -> image.
+struct Prepacked { const float *w; int dgrad; const uint8_t *image; };
+constexpr int PREPACKED_MAX = 512;
+Prepacked g_prepacked[PREPACKED_MAX];
+int g_prepacked_n = 0;
+bool g_prepacked_on = false;
+const uint8_t *prepacked_lookup(const float *w, int dgrad) {
+    if (!g_prepacked_on) return nullptr;
+    for (int i = 0; i < g_prepacked_n; ++i)
+        if (g_prepacked[i].w == w && g_prepacked[i].dgrad == dgrad) return g_prepacked[i].image;
+    return nullptr;
+}
+
 int launch_pack(const float *w, uint8_t *wpack, bool dgrad, int cout, int cin, int kk, const FwdPlan &pl,
                 const TapMap &taps, cudaStream_t st) {
     const size_t chunks = (size_t)pl.n_tiles * pl.n_tile * pl.k_blocks * 8;
@@ -1842,6 +1892,62 @@ size_t strided_dgrad_pack_bytes_resident(const bcnn_b200_conv_desc *d) {
     return packs;
 }
 
+// filter taps of one class of a strided dgrad, in the kernel's walk order
+void class_taps(const bcnn_b200_conv_desc *d, const ClassAxis &ah, const ClassAxis &aw, TapMap *taps) {
+    const int s = d->stride;
+    taps->n = ah.n * aw.n;
+    for (int th = 0; th < ah.n; ++th)
+        for (int tw = 0; tw < aw.n; ++tw)
+            taps->idx[th * aw.n + tw] = (short)((ah.kfirst - s * th) * d->ksize + (aw.kfirst - s * tw));
+}
+
+// The packed images the resident fprop (dgrad == 0) / dgrad (1) of `d` consume, as jobs for
+// pack_jobs_kernel, in the order and at the offsets launch_fwd_resident / launch_dgrad_resident read
+// them from a prepacked base. Returns the number of jobs (-1: the route does not exist, -2: more than
+// max_jobs); *bytes = size of the images.
+int plan_pack_jobs(const bcnn_b200_conv_desc *d, int dgrad, const float *w, uint8_t *dst, PackJob *jobs,
+                   int max_jobs, size_t *bytes) {
+    FwdPlan pl;
+    const FwdRoute route = route_fwd_resident(d, dgrad != 0, &pl);
+    if (route == ROUTE_NONE) return -1;
+    const int kk = d->ksize * d->ksize;
+    int n = 0;
+    size_t off = 0;
+    auto add = [&](const FwdPlan &p, int cin, int kkk, const TapMap &taps) {
+        if (n >= max_jobs) return false;
+        if (!p.bf16) return false;
+        PackJob &j = jobs[n++];
+        j.w = w; j.dst = dst ? dst + off : nullptr; j.dgrad = dgrad ? 1 : 0; j.cout = d->cout; j.cin = cin; j.kk = kkk;
+        j.n_tile = p.n_tile; j.n_tiles = p.n_tiles; j.kc_blocks = p.kc_blocks; j.first_block = 0; j.taps = taps;
+        off += p.wpack_bytes;
+        return true;
+    };
+    TapMap taps;
+    if (route == ROUTE_IM2COL) {
+        taps.n = 1; taps.idx[0] = 0;
+        if (!add(pl, d->cin * kk, 1, taps)) return -2;
+    } else if (route == ROUTE_PLAIN) {
+        taps.n = kk;
+        for (int t = 0; t < kk; ++t) taps.idx[t] = (short)(dgrad ? kk - 1 - t : t);
+        if (!add(pl, d->cin, kk, taps)) return -2;
+    } else {   // strided dgrad: one image per class of input positions
+        const int s = d->stride;
+        for (int ph = 0; ph < s; ++ph)
+            for (int pw = 0; pw < s; ++pw) {
+                const ClassAxis ah = class_axis(ph, s, d->pad, d->ksize, d->h);
+                const ClassAxis aw = class_axis(pw, s, d->pad, d->ksize, d->w);
+                if (ah.n == 0 || aw.n == 0 || ah.extent == 0 || aw.extent == 0) continue;
+                FwdGeom g = geom_dgrad_class(d, ah, aw, ph, pw);
+                g.resident = true;
+                if (!plan_fwd(g, &pl)) return -1;
+                class_taps(d, ah, aw, &taps);
+                if (!add(pl, d->cin, kk, taps)) return -2;
+            }
+    }
+    *bytes = off;
+    return n;
+}
+
 // fprop: x is the BF16 NHWC activation, or the FP32 NCHW input of a thin first layer (im2col route)
 int launch_fwd_resident(const bcnn_b200_conv_desc *d, const void *x, const float *w, const float *bias,
                         int act, void *y16, void *workspace, size_t workspace_bytes,
@@ -1883,12 +1989,16 @@ int launch_fwd_resident(const bcnn_b200_conv_desc *d, const void *x, const float
         *stat_partial = stats;
         *stat_rows = pl.stat_rows;
     }
-    int err = route == ROUTE_IM2COL ? launch_pack(w, wpack, false, d->cout, d->cin * kk, 1, pl, taps, st)
-                                    : launch_pack(w, wpack, false, d->cout, d->cin, kk, pl, taps, st);
-    if (err) return err;
+    const uint8_t *image = prepacked_lookup(w, 0);
+    if (!image) {
+        int err = route == ROUTE_IM2COL ? launch_pack(w, wpack, false, d->cout, d->cin * kk, 1, pl, taps, st)
+                                        : launch_pack(w, wpack, false, d->cout, d->cin, kk, pl, taps, st);
+        if (err) return err;
+        image = wpack;
+    }
     FwdGeom g = route == ROUTE_IM2COL ? geom_im2col(d) : geom_resident(d, false);
     g.resident = true;
-    return run_fwd(g, pl, operand, wpack, bias, act, y16, 0, st, stats);
+    return run_fwd(g, pl, operand, image, bias, act, y16, 0, st, stats);
 }
 
 int launch_dgrad_resident(const bcnn_b200_conv_desc *d, const float *w, const void *dy16, void *dx16,
@@ -1906,9 +2016,13 @@ int launch_dgrad_resident(const bcnn_b200_conv_desc *d, const float *w, const vo
         TapMap taps;
         taps.n = kk;
         for (int t = 0; t < kk; ++t) taps.idx[t] = (short)(kk - 1 - t);
-        int err = launch_pack(w, ws, true, d->cout, d->cin, kk, pl, taps, st);
-        if (err) return err;
-        return run_fwd(geom_resident(d, true), pl, dy16, ws, nullptr, 0, dx16, accumulate, st);
+        const uint8_t *image = prepacked_lookup(w, 1);
+        if (!image) {
+            int err = launch_pack(w, ws, true, d->cout, d->cin, kk, pl, taps, st);
+            if (err) return err;
+            image = ws;
+        }
+        return run_fwd(geom_resident(d, true), pl, dy16, image, nullptr, 0, dx16, accumulate, st);
     }
     // strided: one stride-1 launch per class of input positions, scattered into dx
     if (workspace == nullptr || workspace_bytes < strided_dgrad_pack_bytes_resident(d))
@@ -1924,6 +2038,7 @@ int launch_dgrad_resident(const bcnn_b200_conv_desc *d, const float *w, const vo
         if (e != cudaSuccess) return (int)e;
     }
     size_t off = 0;
+    const uint8_t *pre = prepacked_lookup(w, 1);
     for (int ph = 0; ph < s; ++ph)
         for (int pw = 0; pw < s; ++pw) {
             const ClassAxis ah = class_axis(ph, s, d->pad, d->ksize, d->h);
@@ -1933,15 +2048,17 @@ int launch_dgrad_resident(const bcnn_b200_conv_desc *d, const float *w, const vo
             g.resident = true;
             if (!plan_fwd(g, &pl)) return (int)cudaErrorInvalidValue;
             uint8_t *wpack = ws + off;
+            const uint8_t *image = pre ? pre + off : nullptr;   // the classes' images in launch order
             off += pl.wpack_bytes;
-            TapMap taps;
-            taps.n = ah.n * aw.n;
-            for (int th = 0; th < ah.n; ++th)
-                for (int tw = 0; tw < aw.n; ++tw)
-                    taps.idx[th * aw.n + tw] = (short)((ah.kfirst - s * th) * d->ksize + (aw.kfirst - s * tw));
-            int err = launch_pack(w, wpack, true, d->cout, d->cin, kk, pl, taps, st);
-            if (err) return err;
-            err = run_fwd(g, pl, dy16, wpack, nullptr, 0, dx16, accumulate, st);
+            int err;
+            if (!image) {
+                TapMap taps;
+                class_taps(d, ah, aw, &taps);
+                err = launch_pack(w, wpack, true, d->cout, d->cin, kk, pl, taps, st);
+                if (err) return err;
+                image = wpack;
+            }
+            err = run_fwd(g, pl, dy16, image, nullptr, 0, dx16, accumulate, st);
             if (err) return err;
         }
     return 0;
@@ -2454,6 +2571,46 @@ int launch_im2col(const bcnn_b200_conv_desc *d, const float *x, void *col, bool 
 }  // namespace
 
 namespace b200 {
+
+size_t conv_pack_job_bytes() { return sizeof(PackJob); }
+int conv_nhwc_pack_jobs(const bcnn_b200_conv_desc *d, int dgrad, const float *w, void *dst, void *jobs,
+                        int max_jobs, size_t *bytes) {
+    if (!resident_desc_ok(d)) return -1;
+    return plan_pack_jobs(d, dgrad, w, reinterpret_cast<uint8_t *>(dst), reinterpret_cast<PackJob *>(jobs),
+                          max_jobs, bytes);
+}
+unsigned int conv_pack_table_finish(void *jobs, int count) {
+    PackJob *j = reinterpret_cast<PackJob *>(jobs);
+    unsigned int block = 0;
+    for (int i = 0; i < count; ++i) {
+        j[i].first_block = block;
+        const size_t chunks = (size_t)j[i].n_tiles * j[i].n_tile * j[i].taps.n * j[i].kc_blocks * 8;
+        block += (unsigned int)((chunks + PACK_JOB_CHUNKS - 1) / PACK_JOB_CHUNKS);
+    }
+    return block;
+}
+int conv_pack_run(const void *jobs_dev, int count, unsigned int grid, cudaStream_t st) {
+    if (count <= 0 || grid == 0) return 0;
+    pack_jobs_kernel<<<grid, 256, 0, st>>>(reinterpret_cast<const PackJob *>(jobs_dev), count);
+    return launched();
+}
+void conv_prepacked_set(const float *w, int dgrad, const void *image) {
+    int k = -1;
+    for (int i = 0; i < g_prepacked_n; ++i)
+        if (g_prepacked[i].w == w && g_prepacked[i].dgrad == dgrad) k = i;
+    if (!image) {
+        if (k >= 0) g_prepacked[k] = g_prepacked[--g_prepacked_n];
+        return;
+    }
+    if (k < 0) {
+        if (g_prepacked_n == PREPACKED_MAX) return;
+        k = g_prepacked_n++;
+    }
+    g_prepacked[k].w = w;
+    g_prepacked[k].dgrad = dgrad;
+    g_prepacked[k].image = reinterpret_cast<const uint8_t *>(image);
+}
+void conv_prepacked_enable(int on) { g_prepacked_on = on != 0; }
 
 bool conv_tma_supports_fprop(const bcnn_b200_conv_desc *d) {
     FwdPlan pl;

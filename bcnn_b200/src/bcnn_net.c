@@ -18,6 +18,7 @@
 #include <bcnn_b200_net.h>
 
 static void forward_graph_drop(bcnn_cuda_context *ctx);
+static void packs_drop(bcnn_net *net);
 
 static void *g_current_stream = NULL;
 void *bcnn_b200_current_stream(void) { return g_current_stream; }
@@ -82,6 +83,7 @@ void bcnn_end_net(bcnn_net **net) {
     bcnn_cuda_context *ctx = bcnn_ctx(p);
     if (ctx) {
         bcnn_b200_stream_sync(ctx->stream);
+        packs_drop(p);
         bcnn_dp_release(p);
         if (g_current_stream == ctx->stream) g_current_stream = NULL; /* about to be destroyed */
     }
@@ -195,6 +197,7 @@ bcnn_status bcnn_compile_net(bcnn_net *net) {
     bcnn_cuda_context *ctx = bcnn_ctx(net);
     choose_default_math(net);
     forward_graph_drop(ctx); /* buffers are reallocated below */
+    packs_drop(net);
     /* (re)allocate the input tensor, with an eager pinned host mirror the caller fills */
     BCNN_CHECK_STATUS(bcnn_tensor_allocate(&net->tensors[0], net->mode));
     BCNN_CHECK_STATUS(bcnn_tensor_ensure_host(&net->tensors[0]));
@@ -304,8 +307,104 @@ static inline void profile_mark(bcnn_net *net, int node, int slot) {
         bcnn_cuda_check(bcnn_b200_event_record(ctx->profile_events[4 * node + slot], ctx->stream));
 }
 
+/* ---- packed weight images (bcnn_net.h: packs_state) ---- */
+#include "bcnn_conv_layer.h"
+
+static void packs_drop(bcnn_net *net) {
+    bcnn_cuda_context *ctx = bcnn_ctx(net);
+    if (ctx->packs_jobs_host) { /* unregister: entry = {w, dst, dgrad, ...} (csrc/conv_tma.cu PackJob) */
+        const size_t jb = bcnn_b200_conv_pack_job_bytes();
+        for (int i = 0; i < ctx->packs_jobs; ++i) {
+            const char *job = (const char *)ctx->packs_jobs_host + (size_t)i * jb;
+            const float *w = *(const float *const *)job;
+            const int dgrad = *(const int *)(job + 2 * sizeof(void *));
+            bcnn_b200_conv_prepacked_set(w, dgrad, NULL);
+        }
+    }
+    free(ctx->packs_jobs_host);
+    bcnn_b200_free(ctx->packs_jobs_gpu);
+    bcnn_b200_free(ctx->packs_images_gpu);
+    ctx->packs_jobs_host = ctx->packs_jobs_gpu = ctx->packs_images_gpu = NULL;
+    ctx->packs_jobs = 0;
+    ctx->packs_grid = 0;
+    if (ctx->packs_state > 0) ctx->packs_state = 0;
+}
+
+static void packs_prepare(bcnn_net *net) {
+    bcnn_cuda_context *ctx = bcnn_ctx(net);
+    const char *e = getenv("BCNN_B200_PACK_TABLE");
+    ctx->packs_state = -1;
+    if ((e && e[0] == '0') || !bcnn_net_resident(net)) return;
+    const size_t jb = bcnn_b200_conv_pack_job_bytes();
+    const int max_jobs = 8 * net->num_nodes + 8;
+    char *jobs = (char *)calloc((size_t)max_jobs, jb);
+    if (!jobs) return;
+    /* pass 0 sizes the images, pass 1 lays them out */
+    size_t total = 0;
+    char *images = NULL;
+    int count = 0;
+    for (int pass = 0; pass < 2; ++pass) {
+        size_t off = 0;
+        count = 0;
+        for (int i = 0; i < net->num_nodes; ++i) {
+            bcnn_node *node = &net->nodes[i];
+            if (node->type != BCNN_LAYER_CONV2D || !bcnn_conv_layer_is_resident(net, node)) continue;
+            const bcnn_conv_param *param = (const bcnn_conv_param *)node->param;
+            const float *w = net->tensors[node->src[1]].data_gpu;
+            const int passes = net->tensors[node->src[0]].grad_data_gpu ? 2 : 1;
+            for (int dgrad = 0; dgrad < passes; ++dgrad) {
+                size_t bytes = 0;
+                const int n = bcnn_b200_conv_nhwc_pack_jobs(&param->desc, dgrad, w, pass ? images + off : NULL,
+                                                            jobs + (size_t)count * jb, max_jobs - count, &bytes);
+                if (n <= 0) continue; /* this pass of this layer keeps packing per call */
+                if (pass) bcnn_b200_conv_prepacked_set(w, dgrad, images + off);
+                count += n;
+                off += (bytes + 255) & ~(size_t)255;
+            }
+        }
+        if (!pass) {
+            total = off;
+            if (!count || !total) break;
+            images = (char *)bcnn_b200_malloc(total);
+            if (!images) { count = 0; break; }
+        }
+    }
+    if (!count || !images) {
+        bcnn_b200_free(images);
+        free(jobs);
+        return;
+    }
+    ctx->packs_grid = bcnn_b200_conv_pack_table_finish(jobs, count);
+    ctx->packs_jobs_gpu = bcnn_b200_malloc((size_t)count * jb);
+    ctx->packs_jobs_host = jobs;
+    ctx->packs_images_gpu = images;
+    ctx->packs_jobs = count;
+    if (!ctx->packs_jobs_gpu ||
+        bcnn_b200_memcpy_h2d(ctx->packs_jobs_gpu, jobs, (size_t)count * jb, bcnn_stream(net)) != 0) {
+        packs_drop(net);
+        ctx->packs_state = -1;
+        return;
+    }
+    /* the backward pass of this very step already reads the images */
+    if (bcnn_b200_conv_pack_run(ctx->packs_jobs_gpu, ctx->packs_jobs, ctx->packs_grid, bcnn_stream(net)) != 0) {
+        packs_drop(net);
+        ctx->packs_state = -1;
+        return;
+    }
+    bcnn_b200_stream_sync(bcnn_stream(net));
+    ctx->packs_state = 1;
+}
+
 static void forward_nodes(bcnn_net *net) {
     g_current_stream = bcnn_stream(net);
+    {   /* every packed weight image of the step in one launch (TRAIN; other modes pack per call) */
+        bcnn_cuda_context *ctx = bcnn_ctx(net);
+        const int on = ctx->packs_state == 1 && net->mode == BCNN_MODE_TRAIN;
+        bcnn_b200_conv_prepacked_enable(on);
+        if (on)
+            bcnn_cuda_check(bcnn_b200_conv_pack_run(ctx->packs_jobs_gpu, ctx->packs_jobs, ctx->packs_grid,
+                                                    ctx->stream));
+    }
     for (int i = 0; i < net->num_nodes; ++i) {
         bcnn_node *node = &net->nodes[i];
         profile_mark(net, i, 0);
@@ -318,6 +417,10 @@ static void forward_nodes(bcnn_net *net) {
             bcnn_net_node_f32_after_forward(net, node);
         }
         profile_mark(net, i, 1);
+    }
+    {   /* first eager TRAIN forward: every node knows its route now */
+        bcnn_cuda_context *ctx = bcnn_ctx(net);
+        if (ctx->packs_state == 0 && net->mode == BCNN_MODE_TRAIN && !ctx->capturing) packs_prepare(net);
     }
 }
 
@@ -410,6 +513,7 @@ void bcnn_backward(bcnn_net *net) { backward_range(net, 0, net->num_nodes); }
 /* backward of nodes end - 1 .. first */
 static void backward_range(bcnn_net *net, int first, int end) {
     g_current_stream = bcnn_stream(net);
+    bcnn_b200_conv_prepacked_enable(bcnn_ctx(net)->packs_state == 1 && net->mode == BCNN_MODE_TRAIN);
     for (int i = end - 1; i >= first; --i) {
         bcnn_node *node = &net->nodes[i];
         profile_mark(net, i, 2);
@@ -519,6 +623,8 @@ void bcnn_b200_set_conv_math(bcnn_net *net, int math) {
         ctx->res[i].data_at = ctx->res[i].grad_at = BCNN_RES_F32;
     }
     forward_graph_drop(ctx);
+    packs_drop(net);
+    ctx->packs_state = 0;
     ctx->conv_math = math;
 }
 void bcnn_b200_set_reference_quirks(bcnn_net *net, int on) {
@@ -698,6 +804,7 @@ static int train_graph(bcnn_net *net) {
             return 0;
         }
         const unsigned long long before = bcnn_b200_launch_count();
+        ctx->capturing = 1;
         bcnn_dp_set_deferred(net, 1); /* no NCCL call inside the capture */
         const int split = ctx->dp ? bcnn_dp_backward_split(net) : 0;
         bcnn_b200_graph_destroy(ctx->step_graph[slot].exec_tail);
@@ -725,6 +832,7 @@ static int train_graph(bcnn_net *net) {
         ctx->step_graph[slot].kernels = bcnn_b200_launch_count() - before;
         ctx->step_graph[slot].exec = bcnn_b200_graph_end(ctx->stream);
         }
+        ctx->capturing = 0;
         if (!ctx->step_graph[slot].exec) {
             BCNN_WARNING(net->log_ctx, "CUDA graph capture of the training step failed; running eagerly\n");
             ctx->graphs = 0;

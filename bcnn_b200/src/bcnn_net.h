@@ -42,6 +42,17 @@ typedef struct bcnn_cuda_context {
     /* bcnn_update_nodes collects the SGD passes of all parameter tensors of a step here and launches
      * them together (bcnn_b200_sgd_update_multi); NULL outside bcnn_update_nodes */
     struct bcnn_b200_sgd_batch *sgd_batch;
+    /* Packed weight images of every resident convolution node (fprop, dgrad, the classes of strided
+     * dgrads), kept here and re-packed by ONE launch at the start of every TRAIN-mode forward pass; the
+     * kernel library finds them through its (weights, pass) registry while packs_on. Built at the end
+     * of the first eager TRAIN forward (when every node has decided whether it is resident), dropped by
+     * bcnn_compile_net / math changes / bcnn_end_net. packs_state: 0 not built, 1 ready, -1 off
+     * (BCNN_B200_PACK_TABLE=0 or nothing to pack). */
+    int packs_state;
+    int packs_jobs;
+    unsigned int packs_grid;
+    void *packs_jobs_host, *packs_jobs_gpu, *packs_images_gpu;
+    int capturing; /* a CUDA-graph capture is open on the compute stream: no allocations */
     /* per-node CUDA-event timers (the reference only has commented-out bh_timer calls in
      * bcnn_forward, src/bcnn_net.c:416-420); 4 events per node: fwd begin/end, bwd begin/end */
     int profile;

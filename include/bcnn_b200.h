@@ -443,6 +443,27 @@ BCNN_B200_API int bcnn_b200_eltwise_forward_bf16(const void *a, const void *b, v
 BCNN_B200_API int bcnn_b200_eltwise_backward_bf16(const void *y, void *dy, void *da, void *db,
                                                   size_t sz, size_t n_add, int act,
                                                   int accumulate_flags, void *stream);
+/* Weight packing of many layers in one launch. The resident fprop / dgrad entry points above turn the
+ * FP32 weights of the call into the BF16 K-major image(s) their TMA loads want, one small launch per
+ * call (the im2col + GEMM operand set-up of src/layers/bcnn_conv_layer.c:628-656 has no counterpart
+ * that outlives a call either). A caller that knows when weights change can keep the images itself:
+ *   bcnn_b200_conv_nhwc_pack_jobs  appends the jobs of one layer and pass (dgrad: 0 fprop, 1 dgrad; a
+ *       strided dgrad has one image per class of input positions) to a host table of
+ *       bcnn_b200_conv_pack_job_bytes()-sized entries, images laid out from `dst` on; returns the number
+ *       of jobs (< 0: no such route) and the bytes of the images;
+ *   bcnn_b200_conv_pack_table_finish  numbers the CTAs of the finished table and returns the grid;
+ *   bcnn_b200_conv_pack_run  packs every image of the (device copy of the) table in one launch;
+ *   bcnn_b200_conv_prepacked_set / _enable  registers `dst` for (w, pass): while enabled, the entry
+ *       points use the registered images instead of packing (image == NULL unregisters). The images
+ *       must be re-packed whenever the weights change; the net runtime does so at the start of every
+ *       TRAIN-mode forward pass. */
+BCNN_B200_API size_t bcnn_b200_conv_pack_job_bytes(void);
+BCNN_B200_API int bcnn_b200_conv_nhwc_pack_jobs(const bcnn_b200_conv_desc *desc, int dgrad, const float *w,
+                                                void *dst, void *jobs, int max_jobs, size_t *bytes);
+BCNN_B200_API unsigned int bcnn_b200_conv_pack_table_finish(void *jobs, int count);
+BCNN_B200_API int bcnn_b200_conv_pack_run(const void *jobs_dev, int count, unsigned int grid, void *stream);
+BCNN_B200_API void bcnn_b200_conv_prepacked_set(const float *w, int dgrad, const void *image);
+BCNN_B200_API void bcnn_b200_conv_prepacked_enable(int on);
 /* Residual-add backward fused with the reduction pass of the batch-norm backward of the branches it
  * feeds (conv + BN without activation whose only reader is the add, reference pair
  * src/layers/bcnn_eltwise_layer.c:137-161 + src/layers/bcnn_batchnorm_layer.c:263-299): besides what
