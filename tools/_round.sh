@@ -1,1 +1,1 @@
-bash tools/gpu_round.sh r2final3 tb
+bash tools/gpu_round.sh r2final4 pl

@@ -30,10 +30,13 @@ fi
 if [[ $PARTS == *l* ]]; then
   BCNN_B200_GRAPHS=0 timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none --csv \
      --log-file $OUT/launches.csv python tools/profile_step.py resnet50 256 2 resident > $OUT/launches.log 2>&1
+  # the summary is the second step alone: it starts at the last pack_jobs_kernel launch (the first
+  # kernel of a TRAIN forward once the pack table exists), else behind the first step's launch count
   N=$(python -c "
 import csv
 rows=[r for r in csv.DictReader(l for l in open('$OUT/launches.csv') if l.startswith('\"')) if r.get('Metric Name')=='gpu__time_duration.sum']
-print(len(rows)//2)")
+idx=[i for i,r in enumerate(rows) if 'pack_jobs_kernel' in r['Kernel Name']]
+print(idx[-1] if idx else len(rows)//2)")
   python tools/summarize_launches.py $OUT/launches.csv $N > $OUT/launches_resident_b256.md 2>&1
   head -16 $OUT/launches_resident_b256.md
 fi
