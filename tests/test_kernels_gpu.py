@@ -603,6 +603,40 @@ def test_sgd_update_matches_reference_sequence(n):
     assert np.array_equal(dg.download().view(np.uint32), g.view(np.uint32))
 
 
+def test_sgd_update_multi_is_the_single_tensor_kernel():
+    """One launch over a table of tensors (odd sizes, a tensor shorter than a vector, one longer than a
+    CTA's 4096 elements, different weight-decay factors) against bcnn_b200_sgd_update per tensor (itself
+    bit-exact against the reference sequence above): bit-identical weights and gradients."""
+    lib = capi.b200()
+    r = rng(77)
+    sizes = [1, 3, 64, 4095, 4096, 4097, 100003, 12, 9 * 64 * 64]
+    wds = [0.0, 0.032, 0.032, 0.0, 0.032, 0.016, 0.032, 0.0, 0.032]
+    step, g_scale = -0.003 / 64, 0.9
+
+    class Batch(capi.C.Structure):   # include/bcnn_b200.h: bcnn_b200_sgd_batch
+        _fields_ = [("w", capi.C.c_void_p * 96), ("g", capi.C.c_void_p * 96), ("n", capi.C.c_uint * 96),
+                    ("wd_scale", capi.C.c_float * 96), ("first_block", capi.C.c_uint * 97),
+                    ("count", capi.C.c_int), ("step", capi.C.c_float), ("g_scale", capi.C.c_float)]
+
+    batch = Batch()
+    single, multi = [], []
+    for i, (n, wd) in enumerate(zip(sizes, wds)):
+        w0, g0 = f32(r.uniform(-1, 1, size=n)), f32(r.uniform(-1, 1, size=n))
+        a, b = (dev(w0), dev(g0)), (dev(w0), dev(g0))
+        check(lib.bcnn_b200_sgd_update(a[0].ptr, a[1].ptr, n, wd, step, g_scale, None))
+        single.append(a)
+        multi.append(b)
+        batch.w[i], batch.g[i], batch.n[i], batch.wd_scale[i] = b[0].ptr, b[1].ptr, n, wd
+        batch.first_block[i + 1] = batch.first_block[i] + (n + 4095) // 4096
+    batch.count, batch.step, batch.g_scale = len(sizes), step, g_scale
+    lib.bcnn_b200_sgd_update_multi.argtypes = [capi.C.c_void_p, capi.C.c_void_p]
+    lib.bcnn_b200_sgd_update_multi.restype = capi.C.c_int
+    check(lib.bcnn_b200_sgd_update_multi(capi.C.byref(batch), None))
+    for (sw, sg), (mw, mg), n in zip(single, multi, sizes):
+        assert np.array_equal(mw.download().view(np.uint32), sw.download().view(np.uint32)), n
+        assert np.array_equal(mg.download().view(np.uint32), sg.download().view(np.uint32)), n
+
+
 @pytest.mark.parametrize("n", [1, 7, 13, 4096, 100003])
 def test_adam_update_matches_reference_sequence(n):
     """Three chained Adam steps of the fused kernel against orc_adam_update (pinned bit-exact

@@ -404,3 +404,33 @@ def test_train_step_graph_replay_is_the_eager_step(case, math):
     assert np.array_equal(fast.get("cost"), eager.get("cost"))
     for net in nets:
         net.close()
+
+
+def test_pack_table_step_is_the_per_call_packing_step(monkeypatch):
+    """Packed weight images kept by the net and rebuilt by one launch per TRAIN forward
+    (bcnn_net.c:packs_prepare) against every convolution call packing its own (BCNN_B200_PACK_TABLE=0):
+    same bytes in the images, so losses and every parameter after three steps with weight updates in
+    between must be bit-identical -- stale images would show from the second step on."""
+    nets = []
+    for table in ("1", "0"):
+        monkeypatch.setenv("BCNN_B200_PACK_TABLE", table)
+        net = capi.Net()
+        net.set_conv_math(capi.MATH_TC_BF16)
+        net.set_reference_quirks(False)
+        netcases.small_resnet(net, batch=4)
+        net.compile()
+        configs.init_params(net, seed=33)
+        nets.append(net)
+    y = configs.synth_labels(nets[0].shape("label"))
+    for step in range(3):
+        losses = []
+        for table, net in zip(("1", "0"), nets):
+            monkeypatch.setenv("BCNN_B200_PACK_TABLE", table)   # read when the table is first built
+            net.set_host("input", configs.synth_input(net.shape("input"), seed=90 + step))
+            net.set_host("label", y)
+            losses.append(net.train_step(upload_inputs=True, fetch_loss=True))
+        assert losses[0] == losses[1], (step, losses)
+    for idx, name, _ in configs.param_tensors(nets[0]):
+        assert np.array_equal(nets[0].get(idx), nets[1].get(idx)), name
+    for net in nets:
+        net.close()
