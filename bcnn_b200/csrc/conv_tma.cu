@@ -882,17 +882,20 @@ conv_tma_fwd_kernel(const __grid_constant__ CUtensorMap tm_src, const __grid_con
             const int ow = c.w0 + rw, oh = c.h0 + rh, img = c.img + rn;
             bool valid = ow < p.out_w && oh < p.out_h && img < p.batch;
             if (NHWC) valid = valid && in_box;
-            float *dst = p.dst + (size_t)img * p.dst_c * plane +
-                         (size_t)(oh * p.o_s + p.o_oy) * p.dst_w + (ow * p.o_s + p.o_ox);
+            // (address arithmetic of the per-thread store paths is done inside them: the bulk-store paths,
+            // which run 99 % of the tiles, need none of it -- 155 instructions per warp and tile here
+            // were 10 % of the samples of a thin-K layer, ncu source page, gpurun r2zy)
             if (lane == 0) mbar_wait(smem_u32(acc_full + buf), use & 1);
             __syncwarp();
             tc_fence_after();
             const uint32_t d_tmem = tmem_base + buf * acc_cols + ((uint32_t)(q * 32) << 16);
             if (p.out16) {
                 // BF16 NHWC result: this half owns the 64-channel groups gi = half, half + 2
-                __nv_bfloat16 *dst16 = reinterpret_cast<__nv_bfloat16 *>(p.dst) +
-                                       ((size_t)img * plane + (size_t)(oh * p.o_s + p.o_oy) * p.dst_w +
-                                        (size_t)(ow * p.o_s + p.o_ox)) * (size_t)p.dst_c;
+                auto dst16_of = [&]() {   // this thread's position in the result (per-thread store paths only)
+                    return reinterpret_cast<__nv_bfloat16 *>(p.dst) +
+                           ((size_t)img * plane + (size_t)(oh * p.o_s + p.o_oy) * p.dst_w +
+                            (size_t)(ow * p.o_s + p.o_ox)) * (size_t)p.dst_c;
+                };
                 // row of the staged box: halo tiles drop their junk columns (box rows are tw wide)
                 const int r = p.halo ? rh * p.tw + rw : q * 32 + lane;
                 const bool stats = p.stat_partial != nullptr && !(p.dbg & 1);
@@ -937,11 +940,11 @@ conv_tma_fwd_kernel(const __grid_constant__ CUtensorMap tm_src, const __grid_con
                         }
                         named_bar_sync(3, 256);
                         if (in_box) {
-                            uint8_t *row = sbn + (size_t)r * 128;
+                            const uint32_t row = smem_u32(sbn) + (uint32_t)r * 128u;
 #pragma unroll
                             for (int j = 0; j < 4; ++j)
-                                *reinterpret_cast<uint4 *>(row + (((half * 4 + j) ^ (r & 7)) << 4)) =
-                                    make_uint4(pkn[4 * j], pkn[4 * j + 1], pkn[4 * j + 2], pkn[4 * j + 3]);
+                                st_shared_v4(row + (uint32_t)(((half * 4 + j) ^ (r & 7)) << 4), pkn[4 * j],
+                                             pkn[4 * j + 1], pkn[4 * j + 2], pkn[4 * j + 3]);
                         }
                         fence_proxy_async();
                         named_bar_sync(3, 256);
@@ -952,6 +955,7 @@ conv_tma_fwd_kernel(const __grid_constant__ CUtensorMap tm_src, const __grid_con
                             bulk_commit_group();
                         }
                     } else if (valid && ck < chunks32) {
+                        __nv_bfloat16 *dst16 = dst16_of();
 #pragma unroll
                         for (int j = 0; j < 4; ++j) {
                             if (ch0 + j * 8 < p.dst_c && ck * 32 + j * 8 < n_tile) {
@@ -1033,12 +1037,11 @@ conv_tma_fwd_kernel(const __grid_constant__ CUtensorMap tm_src, const __grid_con
                         }
                         named_bar_sync(1 + half, 128);
                         if (in_box) {
-                            uint8_t *row = sb + (size_t)r * 128;
+                            const uint32_t row = smem_u32(sb) + (uint32_t)r * 128u;
 #pragma unroll
                             for (int k8 = 0; k8 < 8; ++k8) {
                                 const uint32_t *w4 = &pk[k8 >> 2][(k8 & 3) * 4];
-                                *reinterpret_cast<uint4 *>(row + ((k8 ^ (r & 7)) << 4)) =
-                                    make_uint4(w4[0], w4[1], w4[2], w4[3]);
+                                st_shared_v4(row + (uint32_t)((k8 ^ (r & 7)) << 4), w4[0], w4[1], w4[2], w4[3]);
                             }
                         }
                         fence_proxy_async();
@@ -1049,6 +1052,7 @@ conv_tma_fwd_kernel(const __grid_constant__ CUtensorMap tm_src, const __grid_con
                             bulk_commit_group();
                         }
                     } else if (valid) {
+                        __nv_bfloat16 *dst16 = dst16_of();
 #pragma unroll
                         for (int k8 = 0; k8 < 8; ++k8) {
                             if (ch0 + k8 * 8 < p.dst_c && gi * 64 + k8 * 8 < n_tile) {
@@ -1150,6 +1154,8 @@ conv_tma_fwd_kernel(const __grid_constant__ CUtensorMap tm_src, const __grid_con
                 const int ch0 = c.tile_n * n_tile + ck * 32;
                 int nvalid = min(32, min(n_tile - ck * 32, p.dst_c - ch0));
                 if (!valid) nvalid = 0;
+                float *dst = p.dst + (size_t)img * p.dst_c * plane +
+                             (size_t)(oh * p.o_s + p.o_oy) * p.dst_w + (ow * p.o_s + p.o_ox);
                 float *d = dst + (size_t)ch0 * plane;
                 const float *b = p.bias ? p.bias + ch0 : nullptr;
                 if (p.accumulate) store_chunk_any<ACT_NONE, false, true>(v, d, plane, b, nvalid);

@@ -51,6 +51,11 @@ __device__ __forceinline__ void bulk_copy_g2s(uint32_t dst_smem, const void *src
         "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
         :: "r"(dst_smem), "l"(src), "r"(bytes), "r"(bar) : "memory");
 }
+// 16-byte store to shared memory by 32-bit shared address (a store through a generic pointer compiles
+// to ST.E with 64-bit address arithmetic)
+__device__ __forceinline__ void st_shared_v4(uint32_t addr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
+    asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" :: "r"(addr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
+}
 __device__ __forceinline__ void fence_proxy_async() {
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
 }
