@@ -1,1 +1,2 @@
-bash tools/gpu_round.sh r2final5 tb
+O=gpurun_out/r2n8; mkdir -p $O
+timeout 120 python -m torch.distributed.run --nnodes=1 --nproc-per-node 8 --master-addr 127.0.0.1 --master-port 29611 bench.py --gpus 8 --steps 10 --warmup 3 > $O/bench_n8.json 2> $O/bench_n8.err; head -c 300 $O/bench_n8.json; echo
